@@ -1,0 +1,1202 @@
+// engine.cu — host side of librsp_b200.so: device memory, shard bookkeeping, the batching front-end of
+// the apply path, flush/compaction scheduling, iterators, and the extern "C" ABI of include/rsp_b200.h.
+//
+// What it stands in for: the rocksdb::DB object the reference keeps behind
+// rocksdb_replicator/rocksdb_wrapper.cpp (Write / GetLatestSequenceNumber) and
+// rocksdb_admin/application_db.cpp:78-144 (Get / MultiGet / NewIterator / CompactRange).
+// No oracle, no CPU fallback: every data-path call ends in the kernels of k_*.cu or fails.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/rsp_b200.h"
+#include "kernels.h"
+
+using namespace rsp;
+
+#define CUDA_OK(x)                                                                                   \
+  do {                                                                                               \
+    cudaError_t e_ = (x);                                                                            \
+    if (e_ != cudaSuccess) {                                                                         \
+      fprintf(stderr, "[rsp_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__,     \
+              __LINE__, cudaGetErrorString(e_));                                                     \
+      abort();                                                                                       \
+    }                                                                                                \
+  } while (0)
+
+static const char* kMsgText[MSG_COUNT] = {
+    "",
+    "Corruption: malformed WriteBatch (too small)",
+    "Corruption: bad WriteBatch Put",
+    "Corruption: bad WriteBatch Delete",
+    "Corruption: bad WriteBatch Merge",
+    "Corruption: bad WriteBatch Blob",
+    "Corruption: unknown WriteBatch tag",
+    "Corruption: WriteBatch has wrong count",
+    "Invalid argument: Invalid column family specified in write batch",
+    "Not implemented: WriteBatch tag outside the replicated hot path",
+    "Invalid argument: merge_operator is not properly initialized.",
+    "Corruption: Error: Could not perform merge.",
+    "Busy: update larger than the reserved memtable",
+};
+
+// ------------------------------------------------------------------------------------------------
+// device arena: power-of-two size classes carved from large slabs
+// ------------------------------------------------------------------------------------------------
+struct Arena {
+  std::mutex mu;
+  size_t slab_bytes;
+  std::vector<void*> slabs;
+  u8* cur = nullptr;
+  size_t cur_left = 0;
+  std::map<size_t, std::vector<void*>> free_lists;
+  std::vector<void*> big;  // allocations larger than a slab get their own cudaMalloc
+  size_t in_use = 0;
+
+  static size_t cls(size_t n) {
+    size_t c = 256;
+    while (c < n) c <<= 1;
+    return c;
+  }
+  void* alloc(size_t n) {
+    if (n == 0) n = 1;
+    const size_t c = cls(n);
+    std::lock_guard<std::mutex> g(mu);
+    in_use += c;
+    auto& fl = free_lists[c];
+    if (!fl.empty()) {
+      void* p = fl.back();
+      fl.pop_back();
+      return p;
+    }
+    if (c > slab_bytes / 2) {
+      void* p = nullptr;
+      CUDA_OK(cudaMalloc(&p, c));
+      big.push_back(p);
+      return p;
+    }
+    if (cur_left < c) {
+      // the tail of the old slab is abandoned to the free lists in class-sized pieces
+      while (cur_left >= 256) {
+        size_t piece = 256;
+        while (piece * 2 <= cur_left) piece <<= 1;
+        free_lists[piece].push_back(cur);
+        cur += piece;
+        cur_left -= piece;
+      }
+      void* s = nullptr;
+      CUDA_OK(cudaMalloc(&s, slab_bytes));
+      slabs.push_back(s);
+      cur = (u8*)s;
+      cur_left = slab_bytes;
+    }
+    void* p = cur;
+    cur += c;
+    cur_left -= c;
+    return p;
+  }
+  void release(void* p, size_t n) {
+    if (!p) return;
+    if (n == 0) n = 1;
+    const size_t c = cls(n);
+    std::lock_guard<std::mutex> g(mu);
+    in_use -= c;
+    free_lists[c].push_back(p);
+  }
+  void destroy() {
+    for (void* s : slabs) cudaFree(s);
+    for (void* s : big) cudaFree(s);
+    slabs.clear();
+    big.clear();
+    free_lists.clear();
+  }
+};
+
+// growable device / pinned scratch
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void* get(size_t n) {
+    if (n > cap) {
+      if (p) CUDA_OK(cudaFree(p));
+      cap = std::max(n, cap * 2);
+      CUDA_OK(cudaMalloc(&p, cap));
+    }
+    return p;
+  }
+  void destroy() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void* get(size_t n) {
+    if (n > cap) {
+      if (p) CUDA_OK(cudaFreeHost(p));
+      cap = std::max(n, cap * 2);
+      CUDA_OK(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
+    }
+    return p;
+  }
+  void destroy() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct Run {
+  Arena* arena;
+  u8* heap = nullptr;
+  u32* ent_off = nullptr;
+  u32* hslots = nullptr;
+  u64* blk_pfx = nullptr;
+  u32 n_ent = 0, heap_units = 0, n_buckets = 0, ord_bits = 0, uniform_units = 0, n_blocks = 0;
+  RunDev dev() const {
+    RunDev r;
+    r.heap = heap; r.ent_off = ent_off; r.hslots = hslots; r.blk_pfx = blk_pfx;
+    r.n_ent = n_ent; r.n_buckets = n_buckets; r.ord_bits = ord_bits; r.uniform_units = uniform_units;
+    r.n_blocks = n_blocks; r.heap_units = heap_units; r.pad0 = r.pad1 = 0;
+    return r;
+  }
+  size_t bytes() const { return (size_t)heap_units * 16; }
+  ~Run() {
+    arena->release(heap, (size_t)heap_units * 16);
+    arena->release(ent_off, (size_t)n_ent * 4);
+    arena->release(hslots, (size_t)n_buckets * RUN_BUCKET_SLOTS * 4);
+    arena->release(blk_pfx, (size_t)n_blocks * 8);
+  }
+};
+
+struct rsp_engine;
+
+struct rsp_shard {
+  rsp_engine* eng;
+  std::string name;
+  u32 index;
+  rsp_shard_opts opts;
+  ShardDev h;  // host mirror of the device descriptor
+  std::atomic<u64> last_seq{0};
+  u32 latch = 0;
+  std::vector<std::shared_ptr<Run>> runs;  // [0] newest
+  std::string last_error;
+  std::mutex err_mu;
+  rsp_stats stats{};
+  size_t mt_heap_bytes = 0, mt_slot_bytes = 0, mt_ent_bytes = 0;
+};
+
+struct rsp_staged {
+  rsp_engine* eng;
+  size_t n = 0;
+  std::vector<u32> order;       // staged position -> caller's batch index
+  std::vector<rsp_shard*> group_shard;
+  std::vector<u32> need_units, need_ents;
+  void* dev = nullptr;          // device image
+  size_t dev_bytes = 0;
+  TickDev tick{};
+  size_t res_bytes = 0;         // bres + gres, contiguous
+  std::vector<u8> host_res;
+};
+
+struct rsp_engine {
+  int device = 0;
+  rsp_engine_cfg cfg{};
+  std::mutex mu;  // serialises GPU work issued through the ABI
+  cudaStream_t st = nullptr;
+  Arena arena;
+  ShardDev* d_shards = nullptr;
+  std::vector<rsp_shard*> slots;
+  std::unordered_map<std::string, rsp_shard*> by_name;
+  PinBuf pin_in, pin_out;
+  DevBuf dev_tick, dev_q;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::map<std::string, float> last_ms;
+  std::atomic<u64> launches{0};
+};
+
+static void set_err(rsp_shard* s, const std::string& m) {
+  std::lock_guard<std::mutex> g(s->err_mu);
+  s->last_error = m;
+}
+
+static void upload_shard(rsp_engine* e, rsp_shard* s) {
+  s->h.n_runs = (u32)s->runs.size();
+  for (u32 i = 0; i < RSP_MAX_RUNS; i++) {
+    if (i < s->runs.size()) s->h.runs[i] = s->runs[i]->dev();
+    else memset(&s->h.runs[i], 0, sizeof(RunDev));
+  }
+  CUDA_OK(cudaMemcpyAsync(e->d_shards + s->index, &s->h, sizeof(ShardDev), cudaMemcpyHostToDevice, e->st));
+  // the host mirror is pageable: the copy above is staged before the call returns
+}
+
+static u32 next_pow2(u32 x) {
+  u32 p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+// (re)allocate an empty memtable able to hold at least `units` heap units and `ents` entries
+static void alloc_memtable(rsp_engine* e, rsp_shard* s, u64 units, u64 ents) {
+  Arena& a = e->arena;
+  if (s->h.mt_heap) {
+    a.release(s->h.mt_heap, s->mt_heap_bytes);
+    a.release(s->h.mt_slots, s->mt_slot_bytes);
+    a.release(s->h.mt_ent_off, s->mt_ent_bytes);
+  }
+  u64 want_units = std::max<u64>(units, (s->opts.write_buffer_bytes ? s->opts.write_buffer_bytes : (1u << 20)) / 16);
+  u64 want_ents = std::max<u64>(ents, want_units / 7);  // a 16 B/64 B Put is 7 units
+  u32 slot_cap = next_pow2((u32)std::max<u64>(16, want_ents * 2));
+  s->mt_heap_bytes = want_units * 16;
+  s->mt_slot_bytes = (size_t)slot_cap * 8;
+  s->mt_ent_bytes = want_ents * 4;
+  s->h.mt_heap = (u8*)a.alloc(s->mt_heap_bytes);
+  s->h.mt_slots = (u64*)a.alloc(s->mt_slot_bytes);
+  s->h.mt_ent_off = (u32*)a.alloc(s->mt_ent_bytes);
+  s->h.mt_slot_mask = slot_cap - 1;
+  s->h.mt_heap_cap = (u32)want_units;
+  s->h.mt_ent_cap = (u32)want_ents;
+  s->h.mt_tail = 0;
+  s->h.mt_count = 0;
+  CUDA_OK(cudaMemsetAsync(s->h.mt_slots, 0, s->mt_slot_bytes, e->st));
+}
+
+// ------------------------------------------------------------------------------------------------
+// flush / compaction of a set of shards in one batched pass
+// ------------------------------------------------------------------------------------------------
+struct JobHost {
+  rsp_shard* s;
+  bool full;  // merge every run with the memtable
+  std::vector<std::shared_ptr<Run>> srcs;
+  size_t items_b, keep_b, fold_b;
+};
+
+static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards, bool force_full) {
+  std::vector<JobHost> jh;
+  std::vector<CompactJob> jobs;
+  Arena& a = e->arena;
+  for (rsp_shard* s : shards) {
+    const bool has_mem = s->h.mt_count > 0;
+    const bool full = force_full || (s->runs.size() + (has_mem ? 1 : 0) >= e->cfg.l0_compaction_trigger) ||
+                      s->runs.size() + 1 > RSP_MAX_RUNS;
+    if (!has_mem && (!full || s->runs.size() <= 1)) {
+      // nothing to flush; a single run is already fully compacted unless it holds tombstones
+      if (!(force_full && s->runs.size() == 1)) continue;
+    }
+    CompactJob j;
+    memset(&j, 0, sizeof(j));
+    JobHost h{s, full, {}, 0, 0, 0};
+    u32 ns = 0;
+    if (has_mem) {
+      j.src_heap[ns] = s->h.mt_heap; j.src_ent_off[ns] = s->h.mt_ent_off; j.src_n[ns] = s->h.mt_count;
+      j.src_is_mem[ns] = 1; ns++;
+    }
+    if (full) {
+      for (auto& r : s->runs) {
+        j.src_heap[ns] = r->heap; j.src_ent_off[ns] = r->ent_off; j.src_n[ns] = r->n_ent; j.src_is_mem[ns] = 0;
+        ns++;
+        h.srcs.push_back(r);
+      }
+    }
+    j.n_src = ns;
+    u64 n = 0;
+    for (u32 i = 0; i < ns; i++) n += j.src_n[i];
+    j.n_items = (u32)n;
+    j.n_pow2 = next_pow2(std::max<u32>(2, j.n_items));
+    j.bottom = (full || s->runs.empty()) ? 1 : 0;
+    j.merge_op = s->opts.merge_op;
+    h.items_b = (size_t)j.n_pow2 * sizeof(SortItem);
+    h.keep_b = (size_t)std::max<u32>(1, j.n_items) * 4;
+    h.fold_b = (size_t)std::max<u32>(1, j.n_items) * 8;
+    j.items = (SortItem*)a.alloc(h.items_b);
+    j.keep_units = (u32*)a.alloc(h.keep_b);
+    j.out_pos = (u32*)a.alloc(h.keep_b);
+    j.out_ord = (u32*)a.alloc(h.keep_b);
+    j.fold_val = (u64*)a.alloc(h.fold_b);
+    j.totals = (u32*)a.alloc(16);
+    jh.push_back(h);
+    jobs.push_back(j);
+  }
+  if (jobs.empty()) return;
+  const u32 nj = (u32)jobs.size();
+  CompactJob* d_jobs = (CompactJob*)a.alloc(sizeof(CompactJob) * nj);
+  CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CompactJob) * nj, cudaMemcpyHostToDevice, e->st));
+  CUDA_OK(cudaEventRecord(e->ev0, e->st));
+  launch_compact_sort(d_jobs, jobs.data(), nj, e->st);
+  launch_compact_size(d_jobs, nj, e->st);
+  e->launches += 3;
+  std::vector<u32> totals(4 * nj);
+  for (u32 i = 0; i < nj; i++)
+    CUDA_OK(cudaMemcpyAsync(&totals[4 * i], jobs[i].totals, 16, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  u32 max_items = 0;
+  std::vector<std::shared_ptr<Run>> outs(nj);
+  for (u32 i = 0; i < nj; i++) {
+    CompactJob& j = jobs[i];
+    const u32 units = totals[4 * i], ents = totals[4 * i + 1], uni = totals[4 * i + 2], keys = totals[4 * i + 3];
+    auto r = std::make_shared<Run>();
+    r->arena = &a;
+    r->n_ent = ents; r->heap_units = units; r->uniform_units = uni;
+    r->n_blocks = (ents + RSP_BLOCK_ENTRIES - 1) / RSP_BLOCK_ENTRIES;
+    // ~0.7 load: 8-slot buckets, at least one
+    r->n_buckets = std::max<u32>(1, (u32)(((u64)keys * 10 + 55) / 56));
+    r->ord_bits = 1;
+    while ((1ull << r->ord_bits) <= ents) r->ord_bits++;
+    r->heap = (u8*)a.alloc((size_t)units * 16);
+    r->ent_off = (u32*)a.alloc((size_t)ents * 4);
+    r->hslots = (u32*)a.alloc((size_t)r->n_buckets * RUN_BUCKET_SLOTS * 4);
+    r->blk_pfx = (u64*)a.alloc((size_t)r->n_blocks * 8);
+    CUDA_OK(cudaMemsetAsync(r->hslots, 0, (size_t)r->n_buckets * RUN_BUCKET_SLOTS * 4, e->st));
+    j.out_heap = r->heap; j.out_ent_off = r->ent_off; j.out_hslots = r->hslots; j.out_blk_pfx = r->blk_pfx;
+    j.out_n_buckets = r->n_buckets; j.out_ord_bits = r->ord_bits;
+    outs[i] = r;
+    max_items = std::max(max_items, j.n_items);
+  }
+  CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CompactJob) * nj, cudaMemcpyHostToDevice, e->st));
+  launch_compact_write(d_jobs, nj, max_items, e->st);
+  e->launches += 1;
+  CUDA_OK(cudaEventRecord(e->ev1, e->st));
+  // install
+  for (u32 i = 0; i < nj; i++) {
+    rsp_shard* s = jh[i].s;
+    u64 read_b = 0;
+    for (u32 k = 0; k < jobs[i].n_src; k++) read_b += 0;  // accounted below from sources
+    if (s->h.mt_count) read_b += (u64)s->h.mt_tail * 16;
+    for (auto& r : jh[i].srcs) read_b += r->bytes();
+    s->stats.compaction_bytes_read += read_b;
+    s->stats.compaction_bytes_written += outs[i]->bytes();
+    if (jh[i].full) { s->stats.compactions++; s->runs.clear(); } else { s->stats.flushes++; }
+    if (outs[i]->n_ent) s->runs.insert(s->runs.begin(), outs[i]);
+    if (s->h.mt_count) {
+      s->h.mt_tail = 0;
+      s->h.mt_count = 0;
+      CUDA_OK(cudaMemsetAsync(s->h.mt_slots, 0, s->mt_slot_bytes, e->st));
+    }
+    upload_shard(e, s);
+  }
+  CUDA_OK(cudaStreamSynchronize(e->st));  // sources may be released once nothing reads them
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->last_ms["compact"] = ms;
+  for (u32 i = 0; i < nj; i++) {
+    a.release(jobs[i].items, jh[i].items_b);
+    a.release(jobs[i].keep_units, jh[i].keep_b);
+    a.release(jobs[i].out_pos, jh[i].keep_b);
+    a.release(jobs[i].out_ord, jh[i].keep_b);
+    a.release(jobs[i].fold_val, jh[i].fold_b);
+    a.release(jobs[i].totals, 16);
+  }
+  a.release(d_jobs, sizeof(CompactJob) * nj);
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply path
+// ------------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Build the tick image (pinned) for n batches and copy it to the device.  Layout of the image:
+//   [BatchDesc x n][GroupDesc x g][blob ...] ; results [BatchRes x n][GroupRes x g] ; [OpRec x ops]
+static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob, const uint64_t* off,
+                       const uint64_t* ts_ms, rsp_staged* sg, bool own_dev) {
+  sg->eng = e;
+  sg->n = n;
+  // group by shard, preserving submission order within a shard
+  std::unordered_map<u32, u32> gid;
+  std::vector<std::vector<u32>> members;
+  for (size_t i = 0; i < n; i++) {
+    const u32 six = shard_ix[i];
+    if (six >= e->slots.size() || !e->slots[six]) return RSP_INVALID_ARGUMENT;
+    auto it = gid.find(six);
+    if (it == gid.end()) {
+      gid.emplace(six, (u32)members.size());
+      members.emplace_back();
+      sg->group_shard.push_back(e->slots[six]);
+      members.back().push_back((u32)i);
+    } else {
+      members[it->second].push_back((u32)i);
+    }
+  }
+  const size_t ng = members.size();
+  const size_t trailer = ts_ms ? 10 : 0;
+  size_t blob_bytes = 0;
+  u64 ops_cap = 0;
+  for (size_t i = 0; i < n; i++) blob_bytes += align_up((size_t)(off[i + 1] - off[i]) + trailer, 16);
+  blob_bytes += 64;  // slack for the insert kernel's aligned word reads
+  if (blob_bytes > 0xf0000000ull) return RSP_INVALID_ARGUMENT;
+  const size_t desc_b = align_up(n * sizeof(BatchDesc) + ng * sizeof(GroupDesc), 256);
+  const size_t in_b = desc_b + blob_bytes;
+  u8* pin = (u8*)e->pin_in.get(in_b);
+  BatchDesc* bd = (BatchDesc*)pin;
+  GroupDesc* gd = (GroupDesc*)(pin + n * sizeof(BatchDesc));
+  u8* pblob = pin + desc_b;
+  sg->order.resize(n);
+  sg->need_units.assign(ng, 0);
+  sg->need_ents.assign(ng, 0);
+  size_t pos = 0, boff = 0;
+  for (size_t g = 0; g < ng; g++) {
+    gd[g].shard_ix = sg->group_shard[g]->index;
+    gd[g].first_batch = (u32)pos;
+    gd[g].n_batches = (u32)members[g].size();
+    gd[g].pad = 0;
+    for (u32 i : members[g]) {
+      const size_t len = (size_t)(off[i + 1] - off[i]);
+      const size_t len_eff = len + trailer;
+      memcpy(pblob + boff, blob + off[i], len);
+      if (ts_ms) {  // rocksdb_wrapper.cpp:19-20: PutLogData(&timestamp, 8) appended to the rep
+        pblob[boff + len] = 0x03;
+        pblob[boff + len + 1] = 8;
+        memcpy(pblob + boff + len + 2, &ts_ms[i], 8);
+      }
+      const size_t pad = align_up(len_eff, 16) - len_eff;
+      memset(pblob + boff + len_eff, 0, pad);
+      u32 claimed = 0;
+      if (len_eff >= 12) memcpy(&claimed, pblob + boff + 8, 4);
+      const u32 max_ops = len_eff > 12 ? (u32)((len_eff - 12) / 2) : 0;
+      const u32 cap = std::min(claimed, max_ops);
+      BatchDesc& b = bd[pos];
+      b.shard_ix = gd[g].shard_ix; b.boff = (u32)boff; b.len = (u32)len_eff;
+      b.op_base = (u32)ops_cap; b.op_cap = cap; b.group = (u32)g; b.pad0 = b.pad1 = 0;
+      ops_cap += cap;
+      // upper bound on heap units: 2 header units + padding per op, payload bytes / 16
+      sg->need_units[g] += cap * 4u + (u32)(len_eff / 16) + 1u;
+      sg->need_ents[g] += cap;
+      sg->order[pos] = i;
+      boff += align_up(len_eff, 16);
+      pos++;
+    }
+  }
+  memset(pblob + boff, 0, 64);
+  if (ops_cap > 0xfff00000ull) return RSP_INVALID_ARGUMENT;
+  const size_t res_b = align_up(n * sizeof(BatchRes) + ng * sizeof(GroupRes), 256);
+  const size_t ops_b = (size_t)ops_cap * sizeof(OpRec);
+  const size_t dev_b = in_b + res_b + ops_b + 256;
+  u8* dev;
+  if (own_dev) {
+    CUDA_OK(cudaMalloc(&sg->dev, dev_b));
+    sg->dev_bytes = dev_b;
+    dev = (u8*)sg->dev;
+  } else {
+    dev = (u8*)e->dev_tick.get(dev_b);
+  }
+  CUDA_OK(cudaMemcpyAsync(dev, pin, in_b, cudaMemcpyHostToDevice, e->st));
+  TickDev& t = sg->tick;
+  t.batches = (const BatchDesc*)dev;
+  t.groups = (const GroupDesc*)(dev + n * sizeof(BatchDesc));
+  t.blob = dev + desc_b;
+  t.bres = (BatchRes*)(dev + in_b);
+  t.gres = (GroupRes*)(dev + in_b + n * sizeof(BatchRes));
+  t.ops = (OpRec*)(dev + in_b + res_b);
+  t.n_batches = (u32)n; t.n_groups = (u32)ng; t.n_ops_cap = (u32)ops_cap;
+  sg->res_bytes = n * sizeof(BatchRes) + ng * sizeof(GroupRes);
+  if (own_dev) CUDA_OK(cudaStreamSynchronize(e->st));  // the pinned staging buffer is reused
+  return RSP_OK;
+}
+
+// make sure every shard of the tick has room; flush (batched) or grow memtables as needed
+static void reserve_for(rsp_engine* e, const rsp_staged* sg) {
+  std::vector<rsp_shard*> to_flush;
+  for (size_t g = 0; g < sg->group_shard.size(); g++) {
+    rsp_shard* s = sg->group_shard[g];
+    const u64 nu = sg->need_units[g], ne = sg->need_ents[g];
+    const bool fits = (u64)s->h.mt_tail + nu <= s->h.mt_heap_cap && (u64)s->h.mt_count + ne <= s->h.mt_ent_cap &&
+                      ((u64)s->h.mt_count + ne) * 2 <= (u64)s->h.mt_slot_mask + 1;
+    if (!fits && s->h.mt_count) to_flush.push_back(s);
+  }
+  if (!to_flush.empty()) compact_shards(e, to_flush, false);
+  for (size_t g = 0; g < sg->group_shard.size(); g++) {
+    rsp_shard* s = sg->group_shard[g];
+    const u64 nu = sg->need_units[g], ne = sg->need_ents[g];
+    const bool fits = (u64)s->h.mt_tail + nu <= s->h.mt_heap_cap && (u64)s->h.mt_count + ne <= s->h.mt_ent_cap &&
+                      ((u64)s->h.mt_count + ne) * 2 <= (u64)s->h.mt_slot_mask + 1;
+    if (!fits) {  // empty but too small for this tick
+      alloc_memtable(e, s, nu + nu / 2, ne + ne / 2);
+      upload_shard(e, s);
+    }
+  }
+}
+
+static void tick_launch(rsp_engine* e, rsp_staged* sg, cudaStream_t st) {
+  launch_decode(sg->tick, st);
+  launch_sequence(sg->tick, e->d_shards, st);
+  launch_insert(sg->tick, e->d_shards, st);
+  launch_publish(sg->tick, e->d_shards, st);
+  e->launches += 4;
+}
+
+static int apply_many_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob,
+                             const uint64_t* off, const uint64_t* ts_ms, int32_t* st_out) {
+  if (n == 0) return RSP_OK;
+  rsp_staged sg;
+  // reserve first (may flush), then stage: staging uses the engine's tick buffers
+  // sizes are only known after grouping, so build the grouping twice is avoided by staging first into
+  // pinned memory and reserving before the H2D copy is consumed (same stream => ordered)
+  int rc = stage_build(e, n, shard_ix, blob, off, ts_ms, &sg, false);
+  if (rc != RSP_OK) return rc;
+  reserve_for(e, &sg);
+  CUDA_OK(cudaEventRecord(e->ev0, e->st));
+  tick_launch(e, &sg, e->st);
+  CUDA_OK(cudaEventRecord(e->ev1, e->st));
+  u8* pout = (u8*)e->pin_out.get(sg.res_bytes);
+  CUDA_OK(cudaMemcpyAsync(pout, sg.tick.bres, sg.res_bytes, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->last_ms["apply"] = ms;
+  const BatchRes* br = (const BatchRes*)pout;
+  const GroupRes* gr = (const GroupRes*)(pout + n * sizeof(BatchRes));
+  int worst = RSP_OK;
+  size_t p = 0;
+  const GroupDesc* gd = (const GroupDesc*)((const u8*)e->pin_in.p + n * sizeof(BatchDesc));
+  for (size_t g = 0; g < sg.group_shard.size(); g++) {
+    rsp_shard* s = sg.group_shard[g];
+    s->h.last_seq = gr[g].last_seq;
+    s->h.pub_seq = gr[g].last_seq;
+    s->h.mt_tail = gr[g].tail;
+    s->h.mt_count = gr[g].count;
+    s->h.latch = gr[g].latch;
+    s->latch = gr[g].latch;
+    s->last_seq.store(gr[g].last_seq, std::memory_order_release);
+    bool noted = false;
+    for (u32 k = 0; k < gd[g].n_batches; k++, p++) {
+      const u32 st = br[p].status;
+      const u32 code = st >> 8, msg = st & 0xff;
+      if (st_out) st_out[sg.order[p]] = (int32_t)code;
+      if (code) {
+        worst = (int)code;
+        if (!noted) { set_err(s, msg < MSG_COUNT ? kMsgText[msg] : "error"); noted = true; }
+      }
+    }
+  }
+  return worst;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side merge folding (operators that do not live on the device)
+// ------------------------------------------------------------------------------------------------
+struct OutCtx { std::string* s; };
+static void out_set_cb(void* ctx, const uint8_t* b, size_t n) { ((OutCtx*)ctx)->s->assign((const char*)b, n); }
+
+static bool host_merge_one(rsp_shard* s, const std::string& key, bool has, const std::string& ex,
+                           const std::string& operand, std::string* out) {
+  switch (s->opts.merge_op) {
+    case RSP_MERGE_APPEND:
+      *out = has ? ex + operand : operand;
+      return true;
+    case RSP_MERGE_CALLBACK: {
+      if (!s->opts.merge_fn) return false;
+      OutCtx c{out};
+      return s->opts.merge_fn(s->opts.merge_state, (const uint8_t*)key.data(), key.size(),
+                              has ? (const uint8_t*)ex.data() : nullptr, has ? ex.size() : 0,
+                              (const uint8_t*)operand.data(), operand.size(), out_set_cb, &c) != 0;
+    }
+    default:
+      return false;
+  }
+}
+
+// resolve one key through the version-dump kernel and the host operator
+static int host_fold_get(rsp_engine* e, rsp_shard* s, const uint8_t* key, size_t klen, std::string* value) {
+  size_t stride = 4096;
+  for (;;) {
+    u8* d = (u8*)e->dev_q.get(klen + 64 + stride + 64);
+    u64 koff[2] = {0, klen};
+    u32 six = s->index;
+    // layout: [koff 16][six 4 pad 12][n_rec 4][need 4][pad 8][key ...][out ...]
+    u8* d_koff = d; u8* d_six = d + 16; u8* d_nrec = d + 32; u8* d_need = d + 36;
+    u8* d_key = d + 48; u8* d_out = d + 48 + align_up(klen, 16) + 16;
+    CUDA_OK(cudaMemcpyAsync(d_koff, koff, 16, cudaMemcpyHostToDevice, e->st));
+    CUDA_OK(cudaMemcpyAsync(d_six, &six, 4, cudaMemcpyHostToDevice, e->st));
+    if (klen) CUDA_OK(cudaMemcpyAsync(d_key, key, klen, cudaMemcpyHostToDevice, e->st));
+    VersionsArgs a{e->d_shards, (const u32*)d_six, d_key, (const u64*)d_koff, d_out, stride - 64, (u32*)d_nrec, (u32*)d_need, 1};
+    launch_get_versions(a, e->st);
+    e->launches++;
+    u32 res[2];
+    CUDA_OK(cudaMemcpyAsync(res, d_nrec, 8, cudaMemcpyDeviceToHost, e->st));
+    CUDA_OK(cudaStreamSynchronize(e->st));
+    if (res[1] > stride - 64) { stride = (size_t)res[1] * 2 + 128; continue; }
+    std::vector<u8> buf(res[1] ? res[1] : 1);
+    if (res[1]) CUDA_OK(cudaMemcpy(buf.data(), d_out, res[1], cudaMemcpyDeviceToHost));
+    // records newest -> oldest; fold oldest -> newest
+    struct Rec { u32 type; std::string v; };
+    std::vector<Rec> recs;
+    size_t at = 0;
+    for (u32 i = 0; i < res[0]; i++) {
+      u32 type, vlen;
+      memcpy(&type, &buf[at], 4);
+      memcpy(&vlen, &buf[at + 4], 4);
+      recs.push_back({type, std::string((const char*)&buf[at + 8], vlen)});
+      at += 8 + ((vlen + 3) & ~3u);
+    }
+    if (recs.empty()) return RSP_NOT_FOUND;
+    bool has = false;
+    std::string cur;
+    size_t n_ops = recs.size();
+    if (recs.back().type != kTypeMerge) {
+      n_ops--;
+      if (recs.back().type == kTypeValue) { has = true; cur = recs.back().v; }
+    }
+    if (n_ops == 0) {
+      if (!has) return RSP_NOT_FOUND;
+      *value = cur;
+      return RSP_OK;
+    }
+    const std::string k((const char*)key, klen);
+    for (size_t i = n_ops; i-- > 0;) {
+      std::string nv;
+      if (!host_merge_one(s, k, has, cur, recs[i].v, &nv)) {
+        set_err(s, kMsgText[MSG_MERGE_FAILED]);
+        return RSP_CORRUPTION;
+      }
+      cur.swap(nv);
+      has = true;
+    }
+    *value = cur;
+    return RSP_OK;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reads
+// ------------------------------------------------------------------------------------------------
+static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, const uint64_t* koff,
+                            uint32_t klen_fixed, uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
+  if (n == 0) return RSP_OK;
+  for (size_t i = 0; i < n; i++)
+    if (shard_ix[i] >= e->slots.size() || !e->slots[shard_ix[i]]) return RSP_INVALID_ARGUMENT;
+  const size_t key_bytes = klen_fixed ? n * klen_fixed : (size_t)koff[n];
+  const size_t o_six = 0, o_koff = align_up(n * 4, 256), o_keys = o_koff + (klen_fixed ? 0 : align_up((n + 1) * 8, 256));
+  const size_t o_vlen = o_keys + align_up(key_bytes + 16, 256), o_st = o_vlen + align_up(n * 4, 256);
+  const size_t o_vals = o_st + align_up(n * 4, 256);
+  const size_t total = o_vals + n * val_stride + 256;
+  u8* d = (u8*)e->dev_q.get(total);
+  CUDA_OK(cudaMemcpyAsync(d + o_six, shard_ix, n * 4, cudaMemcpyHostToDevice, e->st));
+  if (!klen_fixed) CUDA_OK(cudaMemcpyAsync(d + o_koff, koff, (n + 1) * 8, cudaMemcpyHostToDevice, e->st));
+  if (key_bytes) CUDA_OK(cudaMemcpyAsync(d + o_keys, keys, key_bytes, cudaMemcpyHostToDevice, e->st));
+  GetArgs a;
+  a.shards = e->d_shards; a.shard_ix = (const u32*)(d + o_six); a.keys = d + o_keys;
+  a.koff = klen_fixed ? nullptr : (const u64*)(d + o_koff); a.klen_fixed = klen_fixed;
+  a.vals = d + o_vals; a.val_stride = val_stride; a.vlen = (u32*)(d + o_vlen); a.st = (i32*)(d + o_st); a.n = (u32)n;
+  CUDA_OK(cudaEventRecord(e->ev0, e->st));
+  launch_multi_get(a, e->st);
+  e->launches++;
+  CUDA_OK(cudaEventRecord(e->ev1, e->st));
+  CUDA_OK(cudaMemcpyAsync(vlen, d + o_vlen, n * 4, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaMemcpyAsync(st, d + o_st, n * 4, cudaMemcpyDeviceToHost, e->st));
+  if (val_stride) CUDA_OK(cudaMemcpyAsync(vals, d + o_vals, n * val_stride, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->last_ms["multi_get"] = ms;
+  // post-process: error texts, host-folded merges
+  for (size_t i = 0; i < n; i++) {
+    if (st[i] == ST_NEED_HOST_MERGE) {
+      rsp_shard* s = e->slots[shard_ix[i]];
+      const uint8_t* k = klen_fixed ? keys + i * klen_fixed : keys + koff[i];
+      const size_t kl = klen_fixed ? klen_fixed : (size_t)(koff[i + 1] - koff[i]);
+      std::string v;
+      int rc = host_fold_get(e, s, k, kl, &v);
+      st[i] = rc;
+      vlen[i] = 0;
+      if (rc == RSP_OK) {
+        vlen[i] = (u32)v.size();
+        if (v.size() > val_stride) st[i] = RSP_INCOMPLETE;
+        else memcpy(vals + i * val_stride, v.data(), v.size());
+      }
+    } else if (st[i] != RSP_OK && st[i] != RSP_NOT_FOUND && st[i] != RSP_INCOMPLETE) {
+      const u32 msg = vlen[i];
+      set_err(e->slots[shard_ix[i]], msg < MSG_COUNT ? kMsgText[msg] : "error");
+      vlen[i] = 0;
+    }
+  }
+  return RSP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// iterator
+// ------------------------------------------------------------------------------------------------
+struct rsp_iter {
+  rsp_shard* s;
+  std::vector<std::shared_ptr<Run>> pinned;
+  ScanView* d_view = nullptr;
+  std::vector<std::pair<std::string, std::string>> buf;
+  size_t pos = 0;
+  bool valid = false;
+  bool reverse = false;      // direction the buffer was fetched in
+  bool exhausted = true;     // no more entries beyond the buffer in that direction
+  int status = 0;
+  size_t want = 16;
+  size_t stride = 16384;
+};
+
+// fetch up to it->want entries starting at `key` (or the extreme) in the given direction
+static void iter_fetch(rsp_iter* it, const std::string* key, bool exclusive, bool reverse) {
+  rsp_engine* e = it->s->eng;
+  std::lock_guard<std::mutex> g(e->mu);
+  it->buf.clear();
+  it->pos = 0;
+  it->reverse = reverse;
+  const size_t klen = key ? key->size() : 0;
+  for (;;) {
+    const size_t o_key = 64, o_out = 64 + align_up(klen + 16, 256);
+    u8* d = (u8*)e->dev_q.get(o_out + it->stride + 256);
+    // header: [koff 2x8][flags 1][pad][n_out 4 @32][st 4 @36]
+    u64 koff[2] = {0, klen};
+    u8 flags = (exclusive ? 1 : 0) | (reverse ? 2 : 0) | (key ? 0 : 4);
+    CUDA_OK(cudaMemcpyAsync(d, koff, 16, cudaMemcpyHostToDevice, e->st));
+    CUDA_OK(cudaMemcpyAsync(d + 16, &flags, 1, cudaMemcpyHostToDevice, e->st));
+    if (klen) CUDA_OK(cudaMemcpyAsync(d + o_key, key->data(), klen, cudaMemcpyHostToDevice, e->st));
+    ScanArgs a;
+    a.shards = nullptr; a.views = it->d_view; a.shard_ix = nullptr; a.keys = d + o_key; a.koff = (const u64*)d;
+    a.klen_fixed = 0; a.flags = d + 16; a.max_entries = (u32)it->want; a.out = d + o_out; a.out_stride = it->stride;
+    a.n_out = (u32*)(d + 32); a.st = (i32*)(d + 36); a.n = 1;
+    launch_multi_scan(a, e->st);
+    e->launches++;
+    u32 res[2];
+    CUDA_OK(cudaMemcpyAsync(res, d + 32, 8, cudaMemcpyDeviceToHost, e->st));
+    CUDA_OK(cudaStreamSynchronize(e->st));
+    const u32 n_out = res[0];
+    const i32 st = (i32)res[1];
+    if (n_out == 0 && st == RSP_INCOMPLETE) { it->stride *= 4; continue; }
+    std::vector<u8> h(it->stride);
+    if (n_out) CUDA_OK(cudaMemcpy(h.data(), d + o_out, it->stride, cudaMemcpyDeviceToHost));
+    size_t at = 0;
+    for (u32 i = 0; i < n_out; i++) {
+      u32 kl, vl;
+      memcpy(&kl, &h[at], 4);
+      memcpy(&vl, &h[at + 4], 4);
+      it->buf.emplace_back(std::string((const char*)&h[at + 8], kl), std::string((const char*)&h[at + 8 + kl], vl));
+      at += 8 + kl + vl;
+    }
+    it->exhausted = !(st == RSP_INCOMPLETE || n_out == it->want);
+    if (st != 0 && st != RSP_INCOMPLETE) {
+      if (st == ST_NEED_HOST_MERGE) it->status = RSP_NOT_SUPPORTED;
+      else it->status = st >> 8;  // sticky, as DBIter's status_
+      if (st != ST_NEED_HOST_MERGE) it->exhausted = (n_out < it->want);
+    }
+    break;
+  }
+  it->valid = !it->buf.empty();
+  if (it->want < 1024) it->want *= 4;
+}
+
+// ------------------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* rsp_version(void) { return "rocksplicator_b200 0.1 (sm_100a)"; }
+
+int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
+  if (!out) return RSP_INVALID_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    fprintf(stderr, "[rsp_b200] no CUDA device %d (the engine has no CPU fallback)\n", device);
+    return RSP_IO_ERROR;
+  }
+  CUDA_OK(cudaSetDevice(device));
+  rsp_engine* e = new rsp_engine();
+  e->device = device;
+  if (cfg) e->cfg = *cfg;
+  if (!e->cfg.max_shards) e->cfg.max_shards = 16384;
+  if (!e->cfg.arena_bytes) e->cfg.arena_bytes = 1ull << 30;
+  if (!e->cfg.l0_compaction_trigger) e->cfg.l0_compaction_trigger = 4;
+  if (e->cfg.l0_compaction_trigger > RSP_MAX_RUNS) e->cfg.l0_compaction_trigger = RSP_MAX_RUNS;
+  e->arena.slab_bytes = e->cfg.arena_bytes;
+  CUDA_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&e->ev0));
+  CUDA_OK(cudaEventCreate(&e->ev1));
+  CUDA_OK(cudaMalloc(&e->d_shards, sizeof(ShardDev) * e->cfg.max_shards));
+  CUDA_OK(cudaMemset(e->d_shards, 0, sizeof(ShardDev) * e->cfg.max_shards));
+  *out = e;
+  return RSP_OK;
+}
+
+void rsp_engine_destroy(rsp_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->st);
+  for (rsp_shard* s : e->slots)
+    if (s) { s->runs.clear(); delete s; }
+  e->arena.destroy();
+  e->pin_in.destroy(); e->pin_out.destroy(); e->dev_tick.destroy(); e->dev_q.destroy();
+  cudaFree(e->d_shards);
+  cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+  cudaStreamDestroy(e->st);
+  delete e;
+}
+
+int rsp_engine_device(const rsp_engine* e) { return e->device; }
+
+int rsp_shard_open(rsp_engine* e, const char* name, const rsp_shard_opts* opts, rsp_shard** out) {
+  if (!e || !name || !out) return RSP_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  if (e->by_name.count(name)) return RSP_INVALID_ARGUMENT;
+  u32 ix = 0;
+  while (ix < e->slots.size() && e->slots[ix]) ix++;
+  if (ix >= e->cfg.max_shards) return RSP_BUSY;
+  if (ix == e->slots.size()) e->slots.push_back(nullptr);
+  rsp_shard* s = new rsp_shard();
+  s->eng = e; s->name = name; s->index = ix;
+  memset(&s->opts, 0, sizeof(s->opts));
+  if (opts) s->opts = *opts;
+  memset(&s->h, 0, sizeof(s->h));
+  s->h.merge_op = s->opts.merge_op;
+  s->h.live = 1;
+  alloc_memtable(e, s, 0, 0);
+  upload_shard(e, s);
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  e->slots[ix] = s;
+  e->by_name[name] = s;
+  *out = s;
+  return RSP_OK;
+}
+
+int rsp_shard_close(rsp_shard* s) {
+  if (!s) return RSP_INVALID_ARGUMENT;
+  rsp_engine* e = s->eng;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  e->slots[s->index] = nullptr;
+  e->by_name.erase(s->name);
+  ShardDev z;
+  memset(&z, 0, sizeof(z));
+  CUDA_OK(cudaMemcpy(e->d_shards + s->index, &z, sizeof(z), cudaMemcpyHostToDevice));
+  e->arena.release(s->h.mt_heap, s->mt_heap_bytes);
+  e->arena.release(s->h.mt_slots, s->mt_slot_bytes);
+  e->arena.release(s->h.mt_ent_off, s->mt_ent_bytes);
+  s->runs.clear();
+  delete s;
+  return RSP_OK;
+}
+
+uint32_t rsp_shard_index(const rsp_shard* s) { return s->index; }
+const char* rsp_shard_name(const rsp_shard* s) { return s->name.c_str(); }
+uint64_t rsp_latest_seq(const rsp_shard* s) { return s->last_seq.load(std::memory_order_acquire); }
+
+size_t rsp_last_error(const rsp_shard* s, char* buf, size_t cap) {
+  rsp_shard* m = const_cast<rsp_shard*>(s);
+  std::lock_guard<std::mutex> g(m->err_mu);
+  if (buf && cap) snprintf(buf, cap, "%s", m->last_error.c_str());
+  return m->last_error.size();
+}
+
+int rsp_apply_many(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob, const uint64_t* off,
+                   const uint64_t* ts_ms, int32_t* st_out) {
+  if (!e || (n && (!shard_ix || !off))) return RSP_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  return apply_many_locked(e, n, shard_ix, blob, off, ts_ms, st_out);
+}
+
+int rsp_apply(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t ts_ms, uint64_t* seq_out) {
+  if (!s) return RSP_INVALID_ARGUMENT;
+  const uint64_t off[2] = {0, len};
+  const uint32_t six = s->index;
+  int32_t st = 0;
+  static const uint8_t empty = 0;
+  int rc = rsp_apply_many(s->eng, 1, &six, batch ? batch : &empty, off, &ts_ms, &st);
+  if (rc == RSP_OK || rc == st) rc = st;
+  if (seq_out) *seq_out = rsp_latest_seq(s);
+  return rc;
+}
+
+int rsp_write(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t* seq_out) {
+  if (!s) return RSP_INVALID_ARGUMENT;
+  const uint64_t off[2] = {0, len};
+  const uint32_t six = s->index;
+  int32_t st = 0;
+  static const uint8_t empty = 0;
+  int rc = rsp_apply_many(s->eng, 1, &six, batch ? batch : &empty, off, nullptr, &st);
+  if (rc == RSP_OK || rc == st) rc = st;
+  if (seq_out) *seq_out = rsp_latest_seq(s);
+  return rc;
+}
+
+int rsp_multi_get(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, const uint64_t* koff,
+                  uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
+  if (!e || (n && (!shard_ix || !koff || !vlen || !st))) return RSP_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  return multi_get_locked(e, n, shard_ix, keys, koff, 0, vals, val_stride, vlen, st);
+}
+
+int rsp_multi_get_fixed(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, uint32_t klen,
+                        uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
+  if (!e || !klen || (n && (!shard_ix || !keys || !vlen || !st))) return RSP_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  return multi_get_locked(e, n, shard_ix, keys, nullptr, klen, vals, val_stride, vlen, st);
+}
+
+int rsp_get(rsp_shard* s, const uint8_t* key, size_t klen, uint8_t* val, size_t cap, size_t* vlen) {
+  if (!s) return RSP_INVALID_ARGUMENT;
+  const uint64_t koff[2] = {0, klen};
+  const uint32_t six = s->index;
+  uint32_t vl = 0;
+  int32_t st = 0;
+  static const uint8_t empty = 0;
+  int rc = rsp_multi_get(s->eng, 1, &six, key ? key : &empty, koff, val, cap, &vl, &st);
+  if (rc != RSP_OK) return rc;
+  if (vlen) *vlen = vl;
+  return st;
+}
+
+int rsp_flush(rsp_shard* s) {
+  if (!s) return RSP_INVALID_ARGUMENT;
+  rsp_engine* e = s->eng;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  compact_shards(e, {s}, false);
+  return RSP_OK;
+}
+int rsp_compact(rsp_shard* s) {
+  if (!s) return RSP_INVALID_ARGUMENT;
+  rsp_engine* e = s->eng;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  compact_shards(e, {s}, true);
+  return RSP_OK;
+}
+static int all_shards(rsp_engine* e, bool full) {
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  std::vector<rsp_shard*> v;
+  for (rsp_shard* s : e->slots) if (s) v.push_back(s);
+  // bounded batches keep the work buffers modest
+  for (size_t i = 0; i < v.size(); i += 256) {
+    std::vector<rsp_shard*> part(v.begin() + i, v.begin() + std::min(v.size(), i + 256));
+    compact_shards(e, part, full);
+  }
+  return RSP_OK;
+}
+int rsp_flush_all(rsp_engine* e) { return e ? all_shards(e, false) : RSP_INVALID_ARGUMENT; }
+int rsp_compact_all(rsp_engine* e) { return e ? all_shards(e, true) : RSP_INVALID_ARGUMENT; }
+
+int rsp_get_stats(const rsp_shard* s, rsp_stats* out) {
+  if (!s || !out) return RSP_INVALID_ARGUMENT;
+  rsp_engine* e = s->eng;
+  std::lock_guard<std::mutex> g(e->mu);
+  *out = s->stats;
+  out->latest_seq = s->last_seq.load();
+  out->memtable_entries = s->h.mt_count;
+  out->memtable_bytes = (u64)s->h.mt_tail * 16;
+  out->n_runs = s->runs.size();
+  out->run_entries = 0; out->run_bytes = 0;
+  for (auto& r : s->runs) { out->run_entries += r->n_ent; out->run_bytes += r->bytes(); }
+  return RSP_OK;
+}
+
+// ---- iterator ----
+rsp_iter* rsp_iter_create(rsp_shard* s) {
+  if (!s) return nullptr;
+  rsp_engine* e = s->eng;
+  rsp_iter* it = new rsp_iter();
+  it->s = s;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  // the memtable is unordered: freeze it into a sorted run, then pin the run set (the iterator's snapshot)
+  if (s->h.mt_count) compact_shards(e, {s}, false);
+  it->pinned = s->runs;
+  ScanView v;
+  memset(&v, 0, sizeof(v));
+  v.n_runs = (u32)it->pinned.size();
+  v.merge_op = s->opts.merge_op;
+  for (u32 i = 0; i < v.n_runs; i++) v.runs[i] = it->pinned[i]->dev();
+  it->d_view = (ScanView*)e->arena.alloc(sizeof(ScanView));
+  CUDA_OK(cudaMemcpyAsync(it->d_view, &v, sizeof(v), cudaMemcpyHostToDevice, e->st));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return it;
+}
+void rsp_iter_destroy(rsp_iter* it) {
+  if (!it) return;
+  rsp_engine* e = it->s->eng;
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_OK(cudaSetDevice(e->device));
+    CUDA_OK(cudaStreamSynchronize(e->st));
+    e->arena.release(it->d_view, sizeof(ScanView));
+    it->pinned.clear();
+  }
+  delete it;
+}
+void rsp_iter_seek_to_first(rsp_iter* it) { it->want = 16; iter_fetch(it, nullptr, false, false); }
+void rsp_iter_seek_to_last(rsp_iter* it) { it->want = 16; iter_fetch(it, nullptr, false, true); }
+void rsp_iter_seek(rsp_iter* it, const uint8_t* key, size_t klen) {
+  std::string k((const char*)key, klen);
+  it->want = 16;
+  iter_fetch(it, &k, false, false);
+}
+void rsp_iter_next(rsp_iter* it) {
+  if (!it->valid) return;
+  if (it->reverse) {  // direction change: refetch forward from the current key, exclusive
+    std::string k = it->buf[it->pos].first;
+    it->want = 16;
+    iter_fetch(it, &k, true, false);
+    return;
+  }
+  if (it->pos + 1 < it->buf.size()) { it->pos++; return; }
+  if (it->exhausted) { it->valid = false; return; }
+  std::string k = it->buf[it->pos].first;
+  iter_fetch(it, &k, true, false);
+}
+void rsp_iter_prev(rsp_iter* it) {
+  if (!it->valid) return;
+  if (!it->reverse) {
+    std::string k = it->buf[it->pos].first;
+    it->want = 16;
+    iter_fetch(it, &k, true, true);
+    return;
+  }
+  if (it->pos + 1 < it->buf.size()) { it->pos++; return; }
+  if (it->exhausted) { it->valid = false; return; }
+  std::string k = it->buf[it->pos].first;
+  iter_fetch(it, &k, true, true);
+}
+int rsp_iter_valid(const rsp_iter* it) { return it->valid ? 1 : 0; }
+const uint8_t* rsp_iter_key(const rsp_iter* it, size_t* klen) {
+  if (!it->valid) { if (klen) *klen = 0; return nullptr; }
+  if (klen) *klen = it->buf[it->pos].first.size();
+  return (const uint8_t*)it->buf[it->pos].first.data();
+}
+const uint8_t* rsp_iter_value(const rsp_iter* it, size_t* vlen) {
+  if (!it->valid) { if (vlen) *vlen = 0; return nullptr; }
+  if (vlen) *vlen = it->buf[it->pos].second.size();
+  return (const uint8_t*)it->buf[it->pos].second.data();
+}
+int rsp_iter_status(const rsp_iter* it) { return it->status; }
+
+// ---- batched scans (host buffers) ----
+int rsp_multi_scan(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, const uint64_t* koff,
+                   uint32_t max_entries, uint8_t* out, size_t out_stride, uint32_t* n_out, int32_t* st) {
+  if (!e || (n && (!shard_ix || !koff || !out || !n_out || !st))) return RSP_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  if (n == 0) return RSP_OK;
+  std::vector<rsp_shard*> fl;
+  for (size_t i = 0; i < n; i++) {
+    if (shard_ix[i] >= e->slots.size() || !e->slots[shard_ix[i]]) return RSP_INVALID_ARGUMENT;
+    rsp_shard* s = e->slots[shard_ix[i]];
+    if (s->h.mt_count && std::find(fl.begin(), fl.end(), s) == fl.end()) fl.push_back(s);
+  }
+  if (!fl.empty()) compact_shards(e, fl, false);
+  const size_t key_bytes = (size_t)koff[n];
+  const size_t o_koff = align_up(n * 4, 256), o_keys = o_koff + align_up((n + 1) * 8, 256);
+  const size_t o_nout = o_keys + align_up(key_bytes + 16, 256), o_st = o_nout + align_up(n * 4, 256);
+  const size_t o_out = o_st + align_up(n * 4, 256);
+  u8* d = (u8*)e->dev_q.get(o_out + n * out_stride + 256);
+  CUDA_OK(cudaMemcpyAsync(d, shard_ix, n * 4, cudaMemcpyHostToDevice, e->st));
+  CUDA_OK(cudaMemcpyAsync(d + o_koff, koff, (n + 1) * 8, cudaMemcpyHostToDevice, e->st));
+  if (key_bytes) CUDA_OK(cudaMemcpyAsync(d + o_keys, keys, key_bytes, cudaMemcpyHostToDevice, e->st));
+  ScanArgs a;
+  a.shards = e->d_shards; a.views = nullptr; a.shard_ix = (const u32*)d; a.keys = d + o_keys;
+  a.koff = (const u64*)(d + o_koff); a.klen_fixed = 0; a.flags = nullptr; a.max_entries = max_entries;
+  a.out = d + o_out; a.out_stride = out_stride; a.n_out = (u32*)(d + o_nout); a.st = (i32*)(d + o_st); a.n = (u32)n;
+  CUDA_OK(cudaEventRecord(e->ev0, e->st));
+  launch_multi_scan(a, e->st);
+  e->launches++;
+  CUDA_OK(cudaEventRecord(e->ev1, e->st));
+  CUDA_OK(cudaMemcpyAsync(n_out, d + o_nout, n * 4, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaMemcpyAsync(st, d + o_st, n * 4, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaMemcpyAsync(out, d + o_out, n * out_stride, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->last_ms["scan"] = ms;
+  for (size_t i = 0; i < n; i++)
+    if (st[i] > 255) st[i] = st[i] >> 8;
+  return RSP_OK;
+}
+
+// ---- device-pointer forms ----
+int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, const uint8_t* d_keys, uint32_t klen,
+                         uint8_t* d_vals, uint32_t val_stride, uint32_t* d_vlen, int32_t* d_st, void* stream) {
+  if (!e || !klen) return RSP_INVALID_ARGUMENT;
+  GetArgs a;
+  a.shards = e->d_shards; a.shard_ix = d_shard_ix; a.keys = d_keys; a.koff = nullptr; a.klen_fixed = klen;
+  a.vals = d_vals; a.val_stride = val_stride; a.vlen = d_vlen; a.st = d_st; a.n = (u32)n;
+  launch_multi_get(a, stream ? (cudaStream_t)stream : e->st);
+  e->launches++;
+  return cudaPeekAtLastError() == cudaSuccess ? RSP_OK : RSP_IO_ERROR;
+}
+
+int rsp_multi_scan_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, const uint8_t* d_keys, uint32_t klen,
+                          uint32_t max_entries, uint8_t* d_out, uint64_t out_stride, uint32_t* d_n_out, int32_t* d_st,
+                          void* stream) {
+  if (!e || !klen) return RSP_INVALID_ARGUMENT;
+  ScanArgs a;
+  a.shards = e->d_shards; a.views = nullptr; a.shard_ix = d_shard_ix; a.keys = d_keys; a.koff = nullptr;
+  a.klen_fixed = klen; a.flags = nullptr; a.max_entries = max_entries; a.out = d_out; a.out_stride = out_stride;
+  a.n_out = d_n_out; a.st = d_st; a.n = (u32)n;
+  launch_multi_scan(a, stream ? (cudaStream_t)stream : e->st);
+  e->launches++;
+  return cudaPeekAtLastError() == cudaSuccess ? RSP_OK : RSP_IO_ERROR;
+}
+
+int rsp_stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob, const uint64_t* off,
+                    const uint64_t* ts_ms, rsp_staged** out) {
+  if (!e || !out || !n) return RSP_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  rsp_staged* sg = new rsp_staged();
+  int rc = stage_build(e, n, shard_ix, blob, off, ts_ms, sg, true);
+  if (rc != RSP_OK) { delete sg; return rc; }
+  *out = sg;
+  return RSP_OK;
+}
+void rsp_stage_free(rsp_staged* sg) {
+  if (!sg) return;
+  if (sg->dev) { cudaSetDevice(sg->eng->device); cudaFree(sg->dev); }
+  delete sg;
+}
+int rsp_reserve(rsp_engine* e, const rsp_staged* sg) {
+  if (!e || !sg) return RSP_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  reserve_for(e, sg);
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return RSP_OK;
+}
+int rsp_apply_staged_device(rsp_engine* e, rsp_staged* sg, void* stream) {
+  if (!e || !sg) return RSP_INVALID_ARGUMENT;
+  tick_launch(e, sg, stream ? (cudaStream_t)stream : e->st);
+  return cudaPeekAtLastError() == cudaSuccess ? RSP_OK : RSP_IO_ERROR;
+}
+int rsp_apply_staged_finish(rsp_engine* e, rsp_staged* sg, int32_t* st_out) {
+  if (!e || !sg) return RSP_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  std::vector<u8> res(sg->res_bytes);
+  CUDA_OK(cudaMemcpy(res.data(), sg->tick.bres, sg->res_bytes, cudaMemcpyDeviceToHost));
+  const BatchRes* br = (const BatchRes*)res.data();
+  const GroupRes* gr = (const GroupRes*)(res.data() + sg->n * sizeof(BatchRes));
+  int worst = RSP_OK;
+  for (size_t g2 = 0; g2 < sg->group_shard.size(); g2++) {
+    rsp_shard* s = sg->group_shard[g2];
+    s->h.last_seq = gr[g2].last_seq; s->h.pub_seq = gr[g2].last_seq;
+    s->h.mt_tail = gr[g2].tail; s->h.mt_count = gr[g2].count;
+    s->h.latch = gr[g2].latch; s->latch = gr[g2].latch;
+    s->last_seq.store(gr[g2].last_seq, std::memory_order_release);
+  }
+  for (size_t p = 0; p < sg->n; p++) {
+    const u32 code = br[p].status >> 8;
+    if (st_out) st_out[sg->order[p]] = (int32_t)code;
+    if (code) worst = (int)code;
+  }
+  return worst;
+}
+
+float rsp_last_kernel_ms(const rsp_engine* e, const char* what) {
+  rsp_engine* m = const_cast<rsp_engine*>(e);
+  std::lock_guard<std::mutex> g(m->mu);
+  auto it = m->last_ms.find(what);
+  return it == m->last_ms.end() ? -1.f : it->second;
+}
+uint64_t rsp_kernel_launches(const rsp_engine* e) { return e->launches.load(); }
+
+}  // extern "C"

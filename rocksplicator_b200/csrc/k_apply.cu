@@ -1,0 +1,372 @@
+// k_apply.cu — the follower-side WriteBatch replay on the device.
+//
+// Replaces what RocksDbWrapper::HandleReplicateResponse hands to RocksDB
+// (rocksdb_replicator/rocksdb_wrapper.cpp:13-28): WriteBatch::Iterate's record walk, DB::Write's
+// sequence assignment, and the memtable insert — for a whole tick of batches across many shards.
+//
+//   k_decode   : one warp per batch.  Walks the records (tag byte, varint32 lengths), validates
+//                them with RocksDB's rules and error classes, counts ops / entry units, and emits
+//                one OpRec per op.  HBM read of the batch bytes only.
+//   k_sequence : one warp per shard group.  In submission order: accept batches until the first
+//                failure (which latches, as RocksDB 5.x does), assign sequence numbers
+//                last_seq+1.., heap offsets and ordinals by warp prefix sums.
+//   k_insert   : eight lanes per op.  Writes the 16-byte-unit entry (unaligned wire bytes ->
+//                aligned heap), then links it into the shard's open-addressed table with a
+//                lock-free, sequence-ordered version chain (CAS on the slot / on a link word).
+//   k_publish  : publishes last_seq to readers (batch atomicity: readers skip newer versions).
+#include "kernels.h"
+
+namespace rsp {
+
+// ------------------------------------------------------------------------------------------------
+// k_decode
+// ------------------------------------------------------------------------------------------------
+struct Cursor {
+  const u8* p;  // batch base
+  u32 pos, len;
+};
+// util/coding.cc GetVarint32Ptr: at most 5 bytes, shift <= 28
+__device__ __forceinline__ bool get_varint32(Cursor& c, u32& v) {
+  u32 result = 0;
+  for (u32 shift = 0; shift <= 28 && c.pos < c.len; shift += 7) {
+    u32 byte = __ldg(c.p + c.pos);
+    c.pos++;
+    if (byte & 128) {
+      result |= (byte & 127) << shift;
+    } else {
+      result |= byte << shift;
+      v = result;
+      return true;
+    }
+  }
+  return false;
+}
+// GetLengthPrefixedSlice
+__device__ __forceinline__ bool get_slice(Cursor& c, u32& off, u32& n) {
+  u32 len;
+  if (!get_varint32(c, len)) return false;
+  if (c.len - c.pos < len) return false;
+  off = c.pos;
+  n = len;
+  c.pos += len;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) k_decode(TickDev t) {
+  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  if (warp >= t.n_batches) return;
+  const BatchDesc bd = t.batches[warp];
+  Cursor c{t.blob + bd.boff, 12, bd.len};
+  u32 status = 0, found = 0, units = 0;
+  if (bd.len < 12) {
+    status = mk_status(2, MSG_TOO_SMALL);
+  } else {
+    const u32 count = (u32)__ldg(c.p + 8) | ((u32)__ldg(c.p + 9) << 8) | ((u32)__ldg(c.p + 10) << 16) |
+                      ((u32)__ldg(c.p + 11) << 24);
+    // every lane walks the same records (uniform control flow; loads broadcast); lane 0 writes
+    while (c.pos < c.len && status == 0) {
+      const u32 tag = __ldg(c.p + c.pos);
+      c.pos++;
+      u32 cf = 0, koff = 0, klen = 0, voff = 0, vlen = 0, type = kTypeInvalid;
+      switch (tag) {
+        case kTypeColumnFamilyValue:
+          if (!get_varint32(c, cf)) { status = mk_status(2, MSG_BAD_PUT); break; }
+          /* fallthrough */
+        case kTypeValue:
+          if (!get_slice(c, koff, klen) || !get_slice(c, voff, vlen)) { status = mk_status(2, MSG_BAD_PUT); break; }
+          type = kTypeValue;
+          break;
+        case kTypeColumnFamilyDeletion:
+        case kTypeColumnFamilySingleDeletion:
+          if (!get_varint32(c, cf)) { status = mk_status(2, MSG_BAD_DELETE); break; }
+          /* fallthrough */
+        case kTypeDeletion:
+        case kTypeSingleDeletion:
+          if (!get_slice(c, koff, klen)) { status = mk_status(2, MSG_BAD_DELETE); break; }
+          type = (tag == kTypeDeletion || tag == kTypeColumnFamilyDeletion) ? kTypeDeletion : kTypeSingleDeletion;
+          break;
+        case kTypeColumnFamilyMerge:
+          if (!get_varint32(c, cf)) { status = mk_status(2, MSG_BAD_MERGE); break; }
+          /* fallthrough */
+        case kTypeMerge:
+          if (!get_slice(c, koff, klen) || !get_slice(c, voff, vlen)) { status = mk_status(2, MSG_BAD_MERGE); break; }
+          type = kTypeMerge;
+          break;
+        case kTypeLogData:
+          if (!get_slice(c, koff, klen)) status = mk_status(2, MSG_BAD_BLOB);
+          continue;  // not counted, no sequence number
+        case kTypeNoop:
+          continue;
+        case kTypeColumnFamilyRangeDeletion:
+        case kTypeRangeDeletion:
+        case kTypeBeginPrepareXID:
+        case kTypeEndPrepareXID:
+        case kTypeCommitXID:
+        case kTypeRollbackXID:
+          status = mk_status(3, MSG_UNSUPPORTED_TAG);
+          break;
+        default:
+          status = mk_status(2, MSG_UNKNOWN_TAG);
+          break;
+      }
+      if (status) break;
+      if (cf != 0) { status = mk_status(4, MSG_BAD_CF); break; }
+      if (found < bd.op_cap && lane == 0) {
+        OpRec r;
+        r.koff = bd.boff + koff; r.klen = klen;
+        r.voff = bd.boff + voff; r.vlen = vlen;
+        r.rel_units = units; r.type = type;
+        r.batch_ix = warp; r.op_ix = found;
+        t.ops[bd.op_base + found] = r;
+      }
+      units += entry_units(type, klen, vlen, true);
+      found++;
+    }
+    if (status == 0 && found != count) status = mk_status(2, MSG_WRONG_COUNT);
+  }
+  // unused / rejected reserved op slots must read as invalid for k_insert
+  const u32 first_dead = status ? 0u : min(found, bd.op_cap);
+  for (u32 i = first_dead + lane; i < bd.op_cap; i += 32) t.ops[bd.op_base + i].type = kTypeInvalid;
+  if (lane == 0) {
+    BatchRes r;
+    r.status = status; r.n_ops = status ? 0u : found; r.units = status ? 0u : units;
+    r.unit_base = 0; r.seq_base = 0; r.ord_base = 0; r.accepted = 0;
+    t.bres[warp] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_sequence
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
+#pragma unroll
+  for (u32 d = 1; d < 32; d <<= 1) {
+    u32 n = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += n;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(128) k_sequence(TickDev t, ShardDev* shards) {
+  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  if (warp >= t.n_groups) return;
+  const GroupDesc g = t.groups[warp];
+  ShardDev* sd = shards + g.shard_ix;
+  u32 latch = sd->latch;
+  u64 seq = sd->last_seq;
+  u32 tail = sd->mt_tail, cnt = sd->mt_count;
+  const u32 heap_cap = sd->mt_heap_cap, ent_cap = sd->mt_ent_cap;
+  for (u32 base = 0; base < g.n_batches; base += 32) {
+    const u32 j = base + lane;
+    const bool in = j < g.n_batches;
+    BatchRes r;
+    r.status = 0; r.n_ops = 0; r.units = 0;
+    if (in) r = t.bres[g.first_batch + j];
+    const u32 bad_mask = __ballot_sync(0xffffffffu, in && r.status != 0);
+    const u32 first_bad = bad_mask ? (u32)(__ffs(bad_mask) - 1) : 32u;
+    bool accepted = in && latch == 0 && lane < first_bad;
+    const u32 ops_in = accepted ? r.n_ops : 0u, units_in = accepted ? r.units : 0u;
+    u32 ops_incl = warp_incl_scan(ops_in, lane);
+    u32 units_incl = warp_incl_scan(units_in, lane);
+    // defensive capacity guard (the host reserves before the tick; never expected to trigger):
+    // the first batch that does not fit and everything after it in this chunk is refused, unlatched
+    const bool over = accepted && ((u64)tail + units_incl > heap_cap || (u64)cnt + ops_incl > ent_cap);
+    const u32 over_mask = __ballot_sync(0xffffffffu, over);
+    const u32 first_over = over_mask ? (u32)(__ffs(over_mask) - 1) : 32u;
+    if (lane >= first_over) accepted = false;
+    const u32 ops2 = accepted ? r.n_ops : 0u, units2 = accepted ? r.units : 0u;
+    ops_incl = warp_incl_scan(ops2, lane);
+    units_incl = warp_incl_scan(units2, lane);
+    const u32 first_status = __shfl_sync(0xffffffffu, r.status, first_bad & 31);
+    if (in) {
+      r.accepted = accepted ? 1u : 0u;
+      r.seq_base = seq + 1 + (ops_incl - ops2);
+      r.unit_base = tail + (units_incl - units2);
+      r.ord_base = cnt + (ops_incl - ops2);
+      if (!accepted) {
+        if (latch) r.status = latch;
+        else if (lane >= first_over) r.status = mk_status(11, MSG_TOO_LARGE);
+        else if (lane > first_bad) r.status = first_status;  // the latch set by an earlier batch of this tick
+        r.n_ops = 0; r.units = 0;
+      }
+      t.bres[g.first_batch + j] = r;
+    }
+    seq += __shfl_sync(0xffffffffu, ops_incl, 31);
+    tail += __shfl_sync(0xffffffffu, units_incl, 31);
+    cnt += __shfl_sync(0xffffffffu, ops_incl, 31);
+    if (latch == 0 && bad_mask && first_bad < first_over) latch = first_status;
+    if (over_mask && latch == 0) {
+      // refuse the remainder of the group without latching: report busy
+      for (u32 b2 = base + 32; b2 < g.n_batches; b2 += 32) {
+        const u32 j2 = b2 + lane;
+        if (j2 < g.n_batches) {
+          BatchRes r2 = t.bres[g.first_batch + j2];
+          r2.status = mk_status(11, MSG_TOO_LARGE); r2.n_ops = 0; r2.units = 0; r2.accepted = 0;
+          t.bres[g.first_batch + j2] = r2;
+        }
+      }
+      break;
+    }
+  }
+  if (lane == 0) {
+    sd->last_seq = seq;
+    sd->mt_tail = tail;
+    sd->mt_count = cnt;
+    sd->latch = latch;
+    GroupRes gr;
+    gr.last_seq = seq; gr.tail = tail; gr.count = cnt; gr.latch = latch; gr.pad = 0;
+    t.gres[warp] = gr;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_insert
+// ------------------------------------------------------------------------------------------------
+constexpr u32 INS_LANES = 8;
+
+// copy n bytes from an arbitrarily aligned source to a 16-byte aligned destination, zero padding
+// the last unit; `lanes` lanes cooperate, one 16-byte unit each per step.
+__device__ __forceinline__ void copy_to_units(u8* dst, const u8* src, u32 n, u32 lane, u32 lanes) {
+  const u32 nu = units_of(n);
+  for (u32 u = lane; u < nu; u += lanes) {
+    const u8* s = src + 16u * u;
+    const u32 rem = n - 16u * u;  // > 0
+    const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+    const u32* w = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    const u32 sh = (u32)(a & 3u) * 8u;
+    u32 x0 = __ldg(w), x1 = __ldg(w + 1), x2 = __ldg(w + 2), x3 = __ldg(w + 3);
+    uint4 o;
+    if (sh) {
+      u32 x4 = __ldg(w + 4);
+      o.x = __funnelshift_r(x0, x1, sh);
+      o.y = __funnelshift_r(x1, x2, sh);
+      o.z = __funnelshift_r(x2, x3, sh);
+      o.w = __funnelshift_r(x3, x4, sh);
+    } else {
+      o.x = x0; o.y = x1; o.z = x2; o.w = x3;
+    }
+    if (rem < 16u) {  // zero the padding bytes
+      u32 words[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (u32 i = 0; i < 4; i++) {
+        const u32 lo = 4u * i;
+        if (rem <= lo) words[i] = 0;
+        else if (rem < lo + 4u) words[i] &= (1u << (8u * (rem - lo))) - 1u;
+      }
+      o = make_uint4(words[0], words[1], words[2], words[3]);
+    }
+    *reinterpret_cast<uint4*>(dst + 16u * u) = o;
+  }
+}
+
+__device__ __forceinline__ u64 ld_cg_u64(const u64* p) { return __ldcg(reinterpret_cast<const unsigned long long*>(p)); }
+__device__ __forceinline__ u32 ld_cg_u32(const u32* p) { return __ldcg(p); }
+
+__global__ void __launch_bounds__(256) k_insert(TickDev t, ShardDev* shards) {
+  const u32 gid = (blockIdx.x * blockDim.x + threadIdx.x) / INS_LANES;
+  const u32 lane = threadIdx.x & (INS_LANES - 1);
+  const u32 gmask = ((1u << INS_LANES) - 1u) << ((threadIdx.x & 31u) & ~(INS_LANES - 1u));
+  if (gid >= t.n_ops_cap) return;
+  const OpRec op = t.ops[gid];
+  if (op.type == kTypeInvalid) return;
+  const BatchRes br = t.bres[op.batch_ix];
+  if (!br.accepted) return;
+  ShardDev* sd = shards + t.batches[op.batch_ix].shard_ix;
+  u8* heap = sd->mt_heap;
+  const u32 unit = br.unit_base + op.rel_units;
+  const u64 seq = br.seq_base + op.op_ix;
+  const u32 ord = br.ord_base + op.op_ix;
+  u8* ent = heap + (u64)unit * 16u;
+  // every lane hashes the key (redundant but free: the loads broadcast)
+  const u8* kp = t.blob + op.koff;
+  const u64 h = hash_key(kp, op.klen);
+  if (lane == 0) {
+    uint4 hd;
+    const u64 st = (seq << 8) | op.type;
+    hd.x = (u32)st; hd.y = (u32)(st >> 32); hd.z = op.klen; hd.w = op.vlen;
+    *reinterpret_cast<uint4*>(ent) = hd;
+    sd->mt_ent_off[ord] = unit;
+  }
+  if (lane == 1) *reinterpret_cast<uint4*>(ent + 16) = make_uint4(0u, 0u, (u32)h, (u32)(h >> 32));
+  copy_to_units(ent + 32u, kp, op.klen, lane, INS_LANES);
+  copy_to_units(ent + 32u + 16u * units_of(op.klen), t.blob + op.voff, op.vlen, lane, INS_LANES);
+  __threadfence();  // the entry is complete before any pointer to it is published
+  __syncwarp(gmask);
+  if (lane != 0) return;
+
+  // ---- find (or claim) my user key's slot: one slot per key, newest version at the head
+  const u32 tag = hash_tag32(h);
+  const u32 mask = sd->mt_slot_mask;
+  u64* slots = sd->mt_slots;
+  const u32 P = unit + 1u;
+  u32* my_link = reinterpret_cast<u32*>(ent + 16);
+  u32 idx = (u32)h & mask;
+  for (;;) {
+    u64 cur = ld_cg_u64(slots + idx);
+    if (cur == 0) {
+      const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(slots + idx), 0ull, ((u64)tag << 32) | P);
+      if (old == 0) return;  // first version of a new key
+      cur = old;
+    }
+    if ((u32)(cur >> 32) == tag) {
+      const u8* he = heap + (u64)((u32)cur - 1u) * 16u;
+      const u32 hklen = ld_cg_u32(reinterpret_cast<const u32*>(he) + 2);
+      if (eq_key_vs_padded_cg(kp, op.klen, reinterpret_cast<const u64*>(he + 32), hklen)) break;
+    }
+    idx = (idx + 1u) & mask;
+  }
+  // ---- sequence-ordered insert into the version chain (lock-free; unit offsets grow with sequence)
+  for (;;) {
+    const u64 cur = ld_cg_u64(slots + idx);
+    const u32 H = (u32)cur;
+    if (H < P) {  // newer than the current head: become the head
+      *my_link = H;
+      __threadfence();
+      if (atomicCAS(reinterpret_cast<unsigned long long*>(slots + idx), cur, ((u64)tag << 32) | P) == cur) return;
+      continue;
+    }
+    u32 c = H;  // c > P: walk down to my place
+    for (;;) {
+      u32* clink = reinterpret_cast<u32*>(heap + (u64)(c - 1u) * 16u + 16u);
+      const u32 nxt = ld_cg_u32(clink);
+      if (nxt > P) {
+        c = nxt;
+        continue;
+      }
+      *my_link = nxt;
+      __threadfence();
+      if (atomicCAS(clink, nxt, P) == nxt) return;
+      // lost a race at this link: re-read it
+    }
+  }
+}
+
+__global__ void k_publish(TickDev t, ShardDev* shards) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.n_groups) return;
+  ShardDev* sd = shards + t.groups[i].shard_ix;
+  sd->pub_seq = sd->last_seq;
+}
+
+void launch_decode(const TickDev& t, cudaStream_t s) {
+  if (!t.n_batches) return;
+  const u32 warps_per_block = 8;
+  k_decode<<<(t.n_batches + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(t);
+}
+void launch_sequence(const TickDev& t, ShardDev* shards, cudaStream_t s) {
+  if (!t.n_groups) return;
+  k_sequence<<<(t.n_groups + 3) / 4, 128, 0, s>>>(t, shards);
+}
+void launch_insert(const TickDev& t, ShardDev* shards, cudaStream_t s) {
+  if (!t.n_ops_cap) return;
+  const u32 per_block = 256 / INS_LANES;
+  k_insert<<<(t.n_ops_cap + per_block - 1) / per_block, 256, 0, s>>>(t, shards);
+}
+void launch_publish(const TickDev& t, ShardDev* shards, cudaStream_t s) {
+  if (!t.n_groups) return;
+  k_publish<<<(t.n_groups + 127) / 128, 128, 0, s>>>(t, shards);
+}
+
+}  // namespace rsp

@@ -1,0 +1,268 @@
+// k_compact.cu — flush and compaction: memtable / sorted runs -> one new sorted run.
+//
+// Replaces RocksDB's background flush + compaction behind ApplicationDB::CompactRange
+// (rocksdb_admin/application_db.cpp:138-144) and the write-buffer / L0 triggers of
+// examples/counter_service/rocksdb_options.cpp:78-93.  Per shard ("job"):
+//
+//   k_compact_fill  : one SortItem {8-byte big-endian key prefix, entry ref, source|rank} per entry
+//   k_compact_sort  : bitonic sort by (user key asc, newest first) — prefix compare, full key on ties
+//   k_compact_size  : per user key: keep what a read can still observe (newest Put; tombstone unless
+//                     bottom-most; Merge operands folded with the device operators, otherwise the
+//                     operand stack down to its base), then an exclusive scan -> output offsets
+//   k_compact_write : copy / synthesise the kept entries into the new heap, write the restart array
+//                     (ent_off), the block index (first-key prefix per 32 entries) and the bucketised
+//                     hash index
+#include "kernels.h"
+
+namespace rsp {
+
+constexpr u32 KEEP_UNITS_MASK = 0x00ffffffu;
+constexpr u32 KEEP_HEAD = 1u << 24;
+constexpr u32 KEEP_MODE_SHIFT = 28;
+enum : u32 { MODE_COPY = 0, MODE_PUT_IMM = 1, MODE_PUT_BYTES = 2, MODE_MERGE_IMM = 3 };
+constexpr u32 PAD_REF = 0xffffffffu;
+
+struct EntView {
+  const u8* e;
+  u32 type, klen, vlen;
+  u64 seqtype;
+  const u64* key;
+  const u8* val;
+};
+__device__ __forceinline__ EntView view_item(const CompactJob& j, const SortItem& it) {
+  const u32 src = it.srcrank >> 28;
+  EntView v;
+  v.e = j.src_heap[src] + (u64)it.ref * 16u;
+  const uint4 hd = *reinterpret_cast<const uint4*>(v.e);
+  v.seqtype = ((u64)hd.y << 32) | hd.x;
+  v.type = hd.x & 0xffu;
+  v.klen = hd.z;
+  v.vlen = hd.w;
+  const u32 koff = j.src_is_mem[src] ? 32u : 16u;
+  v.key = reinterpret_cast<const u64*>(v.e + koff);
+  v.val = v.e + koff + 16u * units_of(v.klen);
+  return v;
+}
+
+__device__ __forceinline__ bool item_less(const CompactJob& j, const SortItem& a, const SortItem& b) {
+  if (a.ref == PAD_REF) return false;
+  if (b.ref == PAD_REF) return true;
+  if (a.prefix != b.prefix) return a.prefix < b.prefix;
+  const EntView x = view_item(j, a), y = view_item(j, b);
+  const int c = cmp_padded(x.key, x.klen, y.key, y.klen);
+  if (c) return c < 0;
+  return a.srcrank < b.srcrank;
+}
+__device__ __forceinline__ bool same_key(const CompactJob& j, const SortItem& a, const SortItem& b) {
+  if (a.prefix != b.prefix) return false;
+  const EntView x = view_item(j, a), y = view_item(j, b);
+  return cmp_padded(x.key, x.klen, y.key, y.klen) == 0;
+}
+
+__global__ void __launch_bounds__(256) k_compact_fill(const CompactJob* jobs) {
+  const CompactJob& j = jobs[blockIdx.y];
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.n_pow2) return;
+  SortItem it;
+  if (i >= j.n_items) {
+    it.prefix = ~0ull; it.ref = PAD_REF; it.srcrank = ~0u;
+  } else {
+    u32 src = 0, k = i;
+    while (k >= j.src_n[src]) { k -= j.src_n[src]; src++; }
+    it.ref = j.src_ent_off[src][k];
+    // ascending rank == newest first: the memtable's ordinals grow with sequence, a run is already
+    // stored newest-first within a key
+    it.srcrank = (src << 28) | (j.src_is_mem[src] ? (j.src_n[src] - 1u - k) : k);
+    const u8* e = j.src_heap[src] + (u64)it.ref * 16u;
+    const u32 klen = reinterpret_cast<const u32*>(e)[2];
+    const u64 w0 = klen ? *reinterpret_cast<const u64*>(e + (j.src_is_mem[src] ? 32u : 16u)) : 0ull;
+    it.prefix = bswap64(w0);
+  }
+  j.items[i] = it;
+}
+
+// one CTA per job; all passes through global memory (L2-resident for shard-sized jobs)
+__global__ void __launch_bounds__(1024) k_compact_sort(const CompactJob* jobs) {
+  const CompactJob& j = jobs[blockIdx.x];
+  const u32 n = j.n_pow2;
+  SortItem* it = j.items;
+  for (u32 k = 2; k <= n; k <<= 1) {
+    for (u32 s = k >> 1; s > 0; s >>= 1) {
+      for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+        const u32 p = i ^ s;
+        if (p > i) {
+          const SortItem a = it[i], b = it[p];
+          const bool asc = (i & k) == 0;
+          if (item_less(j, b, a) == asc) { it[i] = b; it[p] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ u32 imm_units(u32 klen) { return 1u + units_of(klen) + 1u; }
+
+__global__ void __launch_bounds__(1024) k_compact_size(const CompactJob* jobs) {
+  const CompactJob& j = jobs[blockIdx.x];
+  const u32 n = j.n_items;
+  const SortItem* it = j.items;
+  const bool foldable = j.merge_op == 1 || j.merge_op == 2;
+  for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+    if (i > 0 && same_key(j, it[i - 1], it[i])) continue;  // not the newest version of its key
+    // i heads a group of versions of one user key, newest first
+    const EntView e0 = view_item(j, it[i]);
+    u32 g_end = i + 1;  // exclusive end of the group
+    while (g_end < n && same_key(j, it[i], it[g_end])) g_end++;
+    for (u32 k = i; k < g_end; k++) j.keep_units[k] = 0;
+    if (e0.type == kTypeValue) {
+      j.keep_units[i] = entry_units(e0.type, e0.klen, e0.vlen, false) | KEEP_HEAD;
+    } else if (e0.type != kTypeMerge) {  // Delete / SingleDelete
+      if (!j.bottom) j.keep_units[i] = entry_units(e0.type, e0.klen, e0.vlen, false) | KEEP_HEAD;
+    } else {
+      // operands i .. m-1, optional base at m
+      u32 m = i, n_bad = 0;
+      u64 sum = 0;
+      while (m < g_end) {
+        const EntView x = view_item(j, it[m]);
+        if (x.type != kTypeMerge) break;
+        if (x.vlen == 8) sum += *reinterpret_cast<const u64*>(x.val); else n_bad++;
+        m++;
+      }
+      const u32 n_ops = m - i;
+      const bool has_base_ent = m < g_end;
+      EntView base;
+      bool base_put = false;
+      if (has_base_ent) { base = view_item(j, it[m]); base_put = base.type == kTypeValue; }
+      u32 mode = MODE_COPY;
+      bool folded = false;
+      u64 val = 0;
+      if (foldable) {
+        if (base_put) {
+          if (j.merge_op == 1) { if (n_bad == 0 && base.vlen == 8) { folded = true; val = sum + *reinterpret_cast<const u64*>(base.val); } }
+          else { folded = true; val = sum + (base.vlen == 8 ? *reinterpret_cast<const u64*>(base.val) : 0ull); }
+          mode = MODE_PUT_IMM;
+        } else if (has_base_ent || j.bottom) {  // existing value == nullptr
+          if (j.merge_op == 1) {
+            if (n_ops == 1) { folded = true; mode = MODE_PUT_BYTES; }
+            else if (n_bad == 0) { folded = true; val = sum; mode = MODE_PUT_IMM; }
+          } else { folded = true; val = sum; mode = MODE_PUT_IMM; }
+        } else if (n_ops >= 2 && (j.merge_op == 2 || n_bad == 0)) {  // partial merge of the operands
+          folded = true; val = sum; mode = MODE_MERGE_IMM;
+        }
+      }
+      if (folded) {
+        const u32 units = mode == MODE_PUT_BYTES ? entry_units(kTypeValue, e0.klen, e0.vlen, false) : imm_units(e0.klen);
+        j.keep_units[i] = units | KEEP_HEAD | (mode << KEEP_MODE_SHIFT);
+        j.fold_val[i] = val;
+      } else {
+        // keep the operand stack and its base as they are (reads fold them); a Delete base at the
+        // bottom is equivalent to "no existing value" and is dropped
+        for (u32 k = i; k < m; k++) {
+          const EntView x = view_item(j, it[k]);
+          j.keep_units[k] = entry_units(x.type, x.klen, x.vlen, false) | (k == i ? KEEP_HEAD : 0u);
+        }
+        if (has_base_ent && (base_put || !j.bottom))
+          j.keep_units[m] = entry_units(base.type, base.klen, base.vlen, false);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- exclusive scans of units and entry counts (one CTA, chunk per thread)
+  __shared__ u32 s_units[1024], s_cnt[1024], s_keys[1024], s_min[1024], s_max[1024];
+  const u32 chunk = (n + blockDim.x - 1) / blockDim.x;
+  const u32 lo = min(n, threadIdx.x * chunk), hi = min(n, lo + chunk);
+  u32 su = 0, sc = 0, sk = 0, mn = ~0u, mx = 0;
+  for (u32 i = lo; i < hi; i++) {
+    const u32 ku = j.keep_units[i];
+    const u32 u = ku & KEEP_UNITS_MASK;
+    if (u) { su += u; sc++; mn = min(mn, u); mx = max(mx, u); if (ku & KEEP_HEAD) sk++; }
+  }
+  s_units[threadIdx.x] = su; s_cnt[threadIdx.x] = sc; s_keys[threadIdx.x] = sk;
+  s_min[threadIdx.x] = mn; s_max[threadIdx.x] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 au = 0, ac = 0, ak = 0, amn = ~0u, amx = 0;
+    for (u32 t = 0; t < blockDim.x; t++) {
+      const u32 u = s_units[t], c = s_cnt[t];
+      s_units[t] = au; s_cnt[t] = ac;
+      au += u; ac += c; ak += s_keys[t];
+      amn = min(amn, s_min[t]); amx = max(amx, s_max[t]);
+    }
+    j.totals[0] = au; j.totals[1] = ac; j.totals[2] = (ac && amn == amx) ? amn : 0u; j.totals[3] = ak;
+  }
+  __syncthreads();
+  u32 pu = s_units[threadIdx.x], pc = s_cnt[threadIdx.x];
+  for (u32 i = lo; i < hi; i++) {
+    const u32 u = j.keep_units[i] & KEEP_UNITS_MASK;
+    j.out_pos[i] = pu; j.out_ord[i] = pc;
+    if (u) { pu += u; pc++; }
+  }
+}
+
+__device__ __forceinline__ void copy_units(u8* dst, const u8* src, u32 units) {
+  for (u32 u = 0; u < units; u++) reinterpret_cast<uint4*>(dst)[u] = reinterpret_cast<const uint4*>(src)[u];
+}
+
+__global__ void __launch_bounds__(256) k_compact_write(const CompactJob* jobs) {
+  const CompactJob& j = jobs[blockIdx.y];
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.n_items) return;
+  const u32 ku = j.keep_units[i];
+  const u32 units = ku & KEEP_UNITS_MASK;
+  if (!units) return;
+  const u32 mode = ku >> KEEP_MODE_SHIFT;
+  const EntView x = view_item(j, j.items[i]);
+  const u32 pos = j.out_pos[i], ord = j.out_ord[i];
+  u8* d = j.out_heap + (u64)pos * 16u;
+  const u32 ku_key = units_of(x.klen);
+  u32 type = x.type, vlen = x.vlen;
+  if (mode == MODE_PUT_IMM || mode == MODE_PUT_BYTES) type = kTypeValue;
+  if (mode == MODE_PUT_IMM || mode == MODE_MERGE_IMM) vlen = 8;
+  const u64 st = (x.seqtype & ~0xffull) | type;
+  *reinterpret_cast<uint4*>(d) = make_uint4((u32)st, (u32)(st >> 32), x.klen, vlen);
+  copy_units(d + 16, reinterpret_cast<const u8*>(x.key), ku_key);
+  if (mode == MODE_PUT_IMM || mode == MODE_MERGE_IMM) {
+    const u64 v = j.fold_val[i];
+    *reinterpret_cast<uint4*>(d + 16u + 16u * ku_key) = make_uint4((u32)v, (u32)(v >> 32), 0u, 0u);
+  } else {
+    copy_units(d + 16u + 16u * ku_key, x.val, units_of(x.vlen));
+  }
+  j.out_ent_off[ord] = pos;
+  if (ord % RSP_BLOCK_ENTRIES == 0) j.out_blk_pfx[ord / RSP_BLOCK_ENTRIES] = j.items[i].prefix;
+  if (ku & KEEP_HEAD) {
+    const u64 h = hash_key_padded(x.key, x.klen);
+    const u32 val = (((u32)(h >> 32) >> j.out_ord_bits) << j.out_ord_bits) | (ord + 1u);
+    u32 bucket = (u32)(((u64)(u32)h * j.out_n_buckets) >> 32);
+    for (;;) {
+      u32* b = j.out_hslots + (u64)bucket * RUN_BUCKET_SLOTS;
+      bool placed = false;
+      for (u32 s = 0; s < RUN_BUCKET_SLOTS && !placed; s++) {
+        if (b[s] == 0 && atomicCAS(b + s, 0u, val) == 0u) placed = true;
+      }
+      if (placed) break;
+      bucket = bucket + 1 == j.out_n_buckets ? 0 : bucket + 1;
+    }
+  }
+}
+
+void launch_compact_sort(const CompactJob* d_jobs, const CompactJob* h_jobs, u32 n_jobs, cudaStream_t s) {
+  if (!n_jobs) return;
+  u32 max_n = 0;
+  for (u32 i = 0; i < n_jobs; i++) max_n = h_jobs[i].n_pow2 > max_n ? h_jobs[i].n_pow2 : max_n;
+  if (!max_n) return;
+  dim3 grid((max_n + 255) / 256, n_jobs);
+  k_compact_fill<<<grid, 256, 0, s>>>(d_jobs);
+  k_compact_sort<<<n_jobs, 1024, 0, s>>>(d_jobs);
+}
+void launch_compact_size(const CompactJob* d_jobs, u32 n_jobs, cudaStream_t s) {
+  if (!n_jobs) return;
+  k_compact_size<<<n_jobs, 1024, 0, s>>>(d_jobs);
+}
+void launch_compact_write(const CompactJob* d_jobs, u32 n_jobs, u32 max_items, cudaStream_t s) {
+  if (!n_jobs || !max_items) return;
+  dim3 grid((max_items + 255) / 256, n_jobs);
+  k_compact_write<<<grid, 256, 0, s>>>(d_jobs);
+}
+
+}  // namespace rsp

@@ -1,0 +1,464 @@
+// k_read.cu — Get / MultiGet / range-scan kernels.
+//
+// Replaces what ApplicationDB::Get / MultiGet / NewIterator hand to rocksdb::DB
+// (rocksdb_admin/application_db.cpp:78-120): for each key, walk the versions newest -> oldest
+// (memtable chain, then each sorted run newest first); Put answers, Delete/SingleDelete hides,
+// Merge operands accumulate and are folded oldest -> newest with the AssociativeMergeOperator rules
+// of examples/counter_service/merge_operator.cpp:23-45 / RocksDB's uint64add on the device, or are
+// handed to the host for any other operator.
+//
+// A query is served by a group of G lanes (8 for MultiGet): one 32-byte sector of hash slots is one
+// coalesced group load, an entry is read as consecutive 16-byte units, the value leaves as
+// consecutive 16-byte stores.  All lanes of a group run the same control flow.
+#include "kernels.h"
+
+namespace rsp {
+
+__device__ __forceinline__ u64 ldcg64(const void* p) { return __ldcg(reinterpret_cast<const unsigned long long*>(p)); }
+__device__ __forceinline__ u32 ldcg32(const void* p) { return __ldcg(reinterpret_cast<const u32*>(p)); }
+
+// ---- merge accumulator (device-resident operators) ------------------------------------------------
+struct Acc {
+  u32 n_ops, n_bad;
+  u64 sum;             // wrapping sum of the 8-byte operands seen so far
+  const u8* last_ptr;  // oldest operand seen so far
+  u32 last_len;
+  u32 merge_op;
+  // result
+  bool done, imm;
+  i32 status;
+  u32 msg;
+  const u8* res_ptr;
+  u32 res_len;
+  u64 res_imm;
+  __device__ void init(u32 op) {
+    n_ops = n_bad = 0; sum = 0; last_ptr = nullptr; last_len = 0; merge_op = op;
+    done = false; imm = false; status = 1; msg = 0; res_ptr = nullptr; res_len = 0; res_imm = 0;
+  }
+  __device__ void fail(i32 st, u32 m) { status = st; msg = m; done = true; }
+  // fold the collected operands onto `base` (nullptr = no existing value)
+  __device__ void finish(const u8* base, u32 base_len) {
+    done = true;
+    if (merge_op == 1) {  // RSP_MERGE_COUNTER
+      if (base) {
+        if (base_len != 8 || n_bad) return fail(2, MSG_MERGE_FAILED);
+        res_imm = sum + ldcg64(base);
+      } else if (n_ops == 1) {  // existing == nullptr -> the operand itself, any size
+        status = 0; res_ptr = last_ptr; res_len = last_len;
+        return;
+      } else {
+        if (n_bad) return fail(2, MSG_MERGE_FAILED);
+        res_imm = sum;
+      }
+    } else {  // RSP_MERGE_UINT64ADD: malformed operands count as 0
+      res_imm = sum + ((base && base_len == 8) ? ldcg64(base) : 0ull);
+    }
+    status = 0; imm = true; res_len = 8;
+  }
+  // one version, newest first.  returns done.
+  __device__ bool visit(u32 type, const u8* vptr, u32 vlen) {
+    if (type == kTypeValue) {
+      if (n_ops == 0) { status = 0; res_ptr = vptr; res_len = vlen; done = true; }
+      else finish(vptr, vlen);
+    } else if (type == kTypeMerge) {
+      if (merge_op == 0) fail(4, MSG_MERGE_NOT_INIT);
+      else if (merge_op > 2) fail(ST_NEED_HOST_MERGE, 0);
+      else {
+        n_ops++;
+        if (vlen == 8) sum += ldcg64(vptr); else n_bad++;
+        last_ptr = vptr; last_len = vlen;
+      }
+    } else {  // Delete / SingleDelete
+      if (n_ops == 0) { status = 1; done = true; }
+      else finish(nullptr, 0);
+    }
+    return done;
+  }
+  __device__ void end_of_versions() {
+    if (done) return;
+    if (n_ops) finish(nullptr, 0);
+    else { status = 1; done = true; }
+  }
+};
+
+// ---- version walk over one shard ---------------------------------------------------------------------
+// V: visitor with bool visit(u32 type, const u8* vptr, u32 vlen) (true = stop).
+template <u32 G, class V>
+__device__ __forceinline__ void walk_memtable(const ShardDev* sd, const u8* kp, u32 klen, u64 h, u64 snap,
+                                              u32 lane, u32 gmask, u32 gbase, V& v) {
+  const u64* slots = sd->mt_slots;
+  const u8* heap = sd->mt_heap;
+  const u32 mask = sd->mt_slot_mask;
+  const u32 tag = hash_tag32(h);
+  u32 idx = (u32)h & mask;
+  for (u32 probes = 0; probes <= mask; probes += G) {
+    const u64 sv = ldcg64(slots + ((idx + lane) & mask));
+    const u32 empty_m = (__ballot_sync(gmask, sv == 0) >> gbase) & ((1u << G) - 1u);
+    u32 match_m = (__ballot_sync(gmask, (u32)(sv >> 32) == tag && sv != 0) >> gbase) & ((1u << G) - 1u);
+    const u32 first_empty = empty_m ? (u32)(__ffs(empty_m) - 1) : G;
+    match_m &= (first_empty >= 32u) ? 0xffffffffu : ((1u << first_empty) - 1u);
+    while (match_m) {
+      const u32 m = (u32)(__ffs(match_m) - 1);
+      match_m &= match_m - 1;
+      u32 c = (u32)__shfl_sync(gmask, (u32)sv, gbase + m);
+      const u8* he = heap + (u64)(c - 1u) * 16u;
+      const u32 hklen = ldcg32(he + 8);
+      if (!eq_key_vs_padded_cg(kp, klen, reinterpret_cast<const u64*>(he + 32), hklen)) continue;
+      // my key: walk the chain newest -> oldest, skipping versions newer than the published snapshot
+      while (c) {
+        const u8* e = heap + (u64)(c - 1u) * 16u;
+        const uint4 hd = __ldcg(reinterpret_cast<const uint4*>(e));
+        const u64 st = ((u64)hd.y << 32) | hd.x;
+        if ((st >> 8) <= snap) {
+          if (v.visit((u32)(st & 0xffu), e + 32u + 16u * units_of(hd.z), hd.w)) return;
+        }
+        c = ldcg32(e + 16);
+      }
+      return;  // chain exhausted, older versions live in the runs
+    }
+    if (empty_m) return;
+    idx = (idx + G) & mask;
+  }
+}
+
+__device__ __forceinline__ const u8* run_entry(const RunDev& r, u32 ord) {
+  const u32 unit = r.uniform_units ? ord * r.uniform_units : __ldg(r.ent_off + ord);
+  return r.heap + (u64)unit * 16u;
+}
+
+template <u32 G, class V>
+__device__ __forceinline__ bool walk_run(const RunDev& r, const u8* kp, u32 klen, u64 h, u32 lane, u32 gmask,
+                                         u32 gbase, V& v) {
+  if (r.n_ent == 0) return false;
+  const u32 tag = (u32)(h >> 32) >> r.ord_bits;
+  const u32 ord_mask = (1u << r.ord_bits) - 1u;
+  u32 bucket = (u32)(((u64)(u32)h * r.n_buckets) >> 32);
+  for (u32 nb = 0; nb < r.n_buckets; nb++) {
+    // one 32-byte sector of slots per bucket; with G < 8 lanes each lane covers several slots
+    u32 sv[RUN_BUCKET_SLOTS / G > 0 ? RUN_BUCKET_SLOTS / G : 1];
+    bool any_empty = false;
+#pragma unroll
+    for (u32 i = 0; i < RUN_BUCKET_SLOTS / G; i++) {
+      sv[i] = __ldg(r.hslots + (u64)bucket * RUN_BUCKET_SLOTS + i * G + lane);
+      any_empty |= sv[i] == 0;
+    }
+    const bool grp_empty = __ballot_sync(gmask, any_empty) != 0;
+#pragma unroll
+    for (u32 i = 0; i < RUN_BUCKET_SLOTS / G; i++) {
+      u32 match_m = (__ballot_sync(gmask, sv[i] != 0 && (sv[i] >> r.ord_bits) == tag) >> gbase) & ((1u << G) - 1u);
+      while (match_m) {
+        const u32 m = (u32)(__ffs(match_m) - 1);
+        match_m &= match_m - 1;
+        u32 ord = (__shfl_sync(gmask, sv[i], gbase + m) & ord_mask) - 1u;
+        const u8* e = run_entry(r, ord);
+        uint4 hd = __ldg(reinterpret_cast<const uint4*>(e));
+        if (!eq_key_vs_padded(kp, klen, reinterpret_cast<const u64*>(e + 16), hd.z)) continue;
+        // first (newest) version of my key in this run; older versions follow in sort order
+        for (;;) {
+          if (v.visit(hd.x & 0xffu, e + 16u + 16u * units_of(hd.z), hd.w)) return true;
+          if (++ord >= r.n_ent) return true;
+          e = run_entry(r, ord);
+          hd = __ldg(reinterpret_cast<const uint4*>(e));
+          if (!eq_key_vs_padded(kp, klen, reinterpret_cast<const u64*>(e + 16), hd.z)) return true;
+        }
+      }
+    }
+    if (grp_empty) return false;
+    bucket = bucket + 1 == r.n_buckets ? 0 : bucket + 1;
+  }
+  return false;
+}
+
+template <u32 G, class V>
+__device__ __forceinline__ void walk_shard(const ShardDev* sd, const u8* kp, u32 klen, u32 lane, u32 gmask,
+                                           u32 gbase, V& v, bool& stopped) {
+  const u64 h = hash_key(kp, klen);
+  const u64 snap = ldcg64(&sd->pub_seq);
+  stopped = false;
+  if (ldcg32(&sd->mt_count) != 0) {
+    walk_memtable<G>(sd, kp, klen, h, snap, lane, gmask, gbase, v);
+    if (v.done) { stopped = true; return; }
+  }
+  const u32 n_runs = sd->n_runs;
+  for (u32 ri = 0; ri < n_runs; ri++) {
+    walk_run<G>(sd->runs[ri], kp, klen, h, lane, gmask, gbase, v);
+    if (v.done) { stopped = true; return; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_multi_get
+// ------------------------------------------------------------------------------------------------
+constexpr u32 MG_LANES = 8;
+
+__device__ __forceinline__ void group_copy_out(u8* dst, const u8* src, u32 n, u32 lane, u32 lanes) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    const u32 full = n >> 4;
+    for (u32 u = lane; u < full; u += lanes)
+      reinterpret_cast<uint4*>(dst)[u] = __ldcg(reinterpret_cast<const uint4*>(src) + u);
+    for (u32 b = (full << 4) + lane; b < n; b += lanes) dst[b] = src[b];
+  } else {
+    for (u32 b = lane; b < n; b += lanes) dst[b] = src[b];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_multi_get(GetArgs a) {
+  const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) / MG_LANES;
+  const u32 lane = threadIdx.x & (MG_LANES - 1);
+  const u32 gbase = (threadIdx.x & 31u) & ~(MG_LANES - 1u);
+  const u32 gmask = ((1u << MG_LANES) - 1u) << gbase;
+  if (q >= a.n) return;
+  const u32 six = __ldg(a.shard_ix + q);
+  const ShardDev* sd = a.shards + six;
+  const u8* kp;
+  u32 klen;
+  if (a.klen_fixed) {
+    klen = a.klen_fixed;
+    kp = a.keys + (u64)q * klen;
+  } else {
+    const u64 o = __ldg(a.koff + q);
+    klen = (u32)(__ldg(a.koff + q + 1) - o);
+    kp = a.keys + o;
+  }
+  Acc acc;
+  acc.init(sd->merge_op);
+  bool stopped;
+  walk_shard<MG_LANES>(sd, kp, klen, lane, gmask, gbase, acc, stopped);
+  acc.end_of_versions();
+  i32 st = acc.status;
+  u32 vlen = 0;
+  if (st == 0) {
+    vlen = acc.res_len;
+    if ((u64)vlen > a.val_stride) {
+      st = 7;  // RSP_INCOMPLETE: vlen reports the size needed
+    } else {
+      u8* dst = a.vals + (u64)q * a.val_stride;
+      if (acc.imm) {
+        if (lane == 0) {
+#pragma unroll
+          for (u32 b = 0; b < 8; b++) dst[b] = (u8)(acc.res_imm >> (8u * b));
+        }
+      } else {
+        group_copy_out(dst, acc.res_ptr, vlen, lane, MG_LANES);
+      }
+    }
+  } else if (st != 1 && st != ST_NEED_HOST_MERGE) {
+    vlen = acc.msg;  // message id rides in vlen for error statuses
+  }
+  if (lane == 0) {
+    a.st[q] = st;
+    a.vlen[q] = vlen;
+  }
+}
+
+void launch_multi_get(const GetArgs& a, cudaStream_t s) {
+  if (!a.n) return;
+  const u32 per_block = 256 / MG_LANES;
+  k_multi_get<<<(a.n + per_block - 1) / per_block, 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_get_versions — slow path for host-folded merge operators: dump the version stack
+// ------------------------------------------------------------------------------------------------
+struct DumpVisitor {
+  u8* out;
+  u64 cap;
+  u32 used, n_rec;
+  bool done;
+  __device__ bool visit(u32 type, const u8* vptr, u32 vlen) {
+    const u32 rec = 8u + ((vlen + 3u) & ~3u);
+    if ((u64)used + rec <= cap) {
+      *reinterpret_cast<u32*>(out + used) = type;
+      *reinterpret_cast<u32*>(out + used + 4) = vlen;
+      for (u32 b = 0; b < vlen; b++) out[used + 8 + b] = __ldcg(vptr + b);
+      n_rec++;
+    }
+    used += rec;
+    if (type != kTypeMerge) done = true;
+    return done;
+  }
+};
+
+__global__ void k_get_versions(VersionsArgs a) {
+  const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.n) return;
+  const u32 lane_in_warp = threadIdx.x & 31u;
+  const ShardDev* sd = a.shards + a.shard_ix[q];
+  const u64 o = a.koff[q];
+  const u32 klen = (u32)(a.koff[q + 1] - o);
+  DumpVisitor v{a.out + (u64)q * a.out_stride, a.out_stride, 0, 0, false};
+  bool stopped;
+  walk_shard<1>(sd, a.keys + o, klen, 0, 1u << lane_in_warp, lane_in_warp, v, stopped);
+  a.n_rec[q] = v.n_rec;
+  a.need[q] = v.used;
+}
+
+void launch_get_versions(const VersionsArgs& a, cudaStream_t s) {
+  if (!a.n) return;
+  k_get_versions<<<(a.n + 63) / 64, 64, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_multi_scan — Seek + N x Next/Prev over the sorted runs (one warp per scan)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cmp_run_key(const RunDev& r, u32 ord, const u8* kp, u32 klen) {
+  const u8* e = run_entry(r, ord);
+  const u32 eklen = __ldg(reinterpret_cast<const u32*>(e) + 2);
+  return -cmp_key_vs_padded(kp, klen, reinterpret_cast<const u64*>(e + 16), eklen);  // sign of (entry - key)
+}
+// first ordinal whose key is >= key (strict: > key)
+__device__ u32 run_lower_bound(const RunDev& r, const u8* kp, u32 klen, bool strict) {
+  u32 lo = 0, hi = r.n_ent;
+  // block index first: 8-byte big-endian prefixes of every RSP_BLOCK_ENTRIES-th entry
+  if (r.n_blocks > 1 && klen) {
+    const u64 pfx = key_prefix_be(kp, klen);
+    u32 bl = 0, bh = r.n_blocks;  // last block whose first prefix < pfx bounds the answer from below
+    while (bl < bh) {
+      const u32 m = (bl + bh) >> 1;
+      if (__ldg(r.blk_pfx + m) < pfx) bl = m + 1; else bh = m;
+    }
+    lo = bl ? (bl - 1) * RSP_BLOCK_ENTRIES : 0;
+    // first block whose prefix > pfx bounds it from above
+    u32 cl = bl, ch = r.n_blocks;
+    while (cl < ch) {
+      const u32 m = (cl + ch) >> 1;
+      if (__ldg(r.blk_pfx + m) <= pfx) cl = m + 1; else ch = m;
+    }
+    hi = min(r.n_ent, cl * RSP_BLOCK_ENTRIES);
+  }
+  while (lo < hi) {
+    const u32 m = (lo + hi) >> 1;
+    const int c = cmp_run_key(r, m, kp, klen);
+    if (c < 0 || (strict && c == 0)) lo = m + 1; else hi = m;
+  }
+  return lo;
+}
+
+struct EntRef {
+  const u8* e;
+  u32 klen, vlen, type;
+  __device__ const u64* key() const { return reinterpret_cast<const u64*>(e + 16); }
+  __device__ const u8* val() const { return e + 16u + 16u * units_of(klen); }
+};
+__device__ __forceinline__ EntRef load_ent(const RunDev& r, u32 ord) {
+  EntRef x;
+  x.e = run_entry(r, ord);
+  const uint4 hd = __ldg(reinterpret_cast<const uint4*>(x.e));
+  x.type = hd.x & 0xffu; x.klen = hd.z; x.vlen = hd.w;
+  return x;
+}
+
+__device__ __forceinline__ void warp_copy_bytes(u8* dst, const u8* src, u32 n, u32 lane) {
+  for (u32 b = lane; b < n; b += 32) dst[b] = src[b];
+}
+
+__global__ void __launch_bounds__(128) k_multi_scan(ScanArgs a) {
+  const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 lane = threadIdx.x & 31u;
+  if (q >= a.n) return;
+  const RunDev* runs;
+  u32 n_runs, merge_op;
+  if (a.views) {
+    runs = a.views[q].runs; n_runs = a.views[q].n_runs; merge_op = a.views[q].merge_op;
+  } else {
+    const ShardDev* sd = a.shards + a.shard_ix[q];
+    runs = sd->runs; n_runs = sd->n_runs; merge_op = sd->merge_op;
+  }
+  const u8* kp;
+  u32 klen;
+  if (a.klen_fixed) { klen = a.klen_fixed; kp = a.keys + (u64)q * klen; }
+  else { const u64 o = a.koff[q]; klen = (u32)(a.koff[q + 1] - o); kp = a.keys + o; }
+  const u32 fl = a.flags ? a.flags[q] : 0u;
+  const bool exclusive = fl & 1u, reverse = fl & 2u, extreme = fl & 4u;
+  u8* out = a.out + (u64)q * a.out_stride;
+  u64 used = 0;
+  u32 n_out = 0;
+  i32 st = 0;
+
+  // cursors: forward = next ordinal to consume; reverse = (last ordinal to consume) + 1
+  u32 cur[RSP_MAX_RUNS];
+  for (u32 r = 0; r < n_runs; r++) {
+    if (extreme) cur[r] = reverse ? runs[r].n_ent : 0u;
+    else if (!reverse) cur[r] = run_lower_bound(runs[r], kp, klen, exclusive);
+    else cur[r] = run_lower_bound(runs[r], kp, klen, !exclusive);  // entries < key (or <= key)
+  }
+
+  while (n_out < a.max_entries) {
+    // pick the next user key: min over forward cursors / max over reverse cursors (newest run wins ties)
+    int best = -1;
+    EntRef bk;
+    for (u32 r = 0; r < n_runs; r++) {
+      if (!reverse ? cur[r] >= runs[r].n_ent : cur[r] == 0) continue;
+      const EntRef x = load_ent(runs[r], reverse ? cur[r] - 1 : cur[r]);
+      if (best < 0) { best = (int)r; bk = x; continue; }
+      const int c = cmp_padded(x.key(), x.klen, bk.key(), bk.klen);
+      if (!reverse ? c < 0 : c > 0) { best = (int)r; bk = x; }
+    }
+    if (best < 0) break;
+    // resolve this key across the runs that hold it, newest run first
+    Acc acc;
+    acc.init(merge_op);
+    for (u32 r = 0; r < n_runs; r++) {
+      const RunDev& R = runs[r];
+      if (!reverse) {
+        while (cur[r] < R.n_ent) {
+          const EntRef x = load_ent(R, cur[r]);
+          if (cmp_padded(x.key(), x.klen, bk.key(), bk.klen) != 0) break;
+          if (!acc.done) acc.visit(x.type, x.val(), x.vlen);
+          cur[r]++;
+        }
+      } else {
+        // group = [g, cur[r]) with the same key; versions are newest-first from g upward
+        u32 g = cur[r];
+        while (g > 0) {
+          const EntRef x = load_ent(R, g - 1);
+          if (cmp_padded(x.key(), x.klen, bk.key(), bk.klen) != 0) break;
+          g--;
+        }
+        for (u32 o = g; o < cur[r] && !acc.done; o++) {
+          const EntRef x = load_ent(R, o);
+          acc.visit(x.type, x.val(), x.vlen);
+        }
+        cur[r] = g;
+      }
+    }
+    acc.end_of_versions();
+    if (acc.status == 1) continue;  // deleted
+    u32 vlen = 0;
+    if (acc.status == ST_NEED_HOST_MERGE) { st = ST_NEED_HOST_MERGE; break; }
+    if (acc.status != 0) {
+      // DBIter keeps the key with an empty value and records the (sticky) status
+      st = (i32)mk_status((u32)acc.status, acc.msg);
+    } else {
+      vlen = acc.res_len;
+    }
+    const u64 rec = 8ull + bk.klen + vlen;
+    if (used + rec > a.out_stride) { if (st == 0) st = 7; break; }
+    if (lane == 0) {
+      u8 hdr[8];
+      for (u32 b = 0; b < 4; b++) { hdr[b] = (u8)(bk.klen >> (8 * b)); hdr[4 + b] = (u8)(vlen >> (8 * b)); }
+      for (u32 b = 0; b < 8; b++) out[used + b] = hdr[b];
+    }
+    warp_copy_bytes(out + used + 8, reinterpret_cast<const u8*>(bk.key()), bk.klen, lane);
+    if (vlen) {
+      if (acc.imm) {
+        if (lane < 8) out[used + 8 + bk.klen + lane] = (u8)(acc.res_imm >> (8u * lane));
+      } else {
+        warp_copy_bytes(out + used + 8 + bk.klen, acc.res_ptr, vlen, lane);
+      }
+    }
+    used += rec;
+    n_out++;
+  }
+  if (lane == 0) {
+    a.n_out[q] = n_out;
+    a.st[q] = st;
+  }
+}
+
+void launch_multi_scan(const ScanArgs& a, cudaStream_t s) {
+  if (!a.n) return;
+  k_multi_scan<<<(a.n + 3) / 4, 128, 0, s>>>(a);
+}
+
+}  // namespace rsp

@@ -1,0 +1,156 @@
+// kernels.h — launch wrappers of the engine's CUDA kernels (implemented in k_*.cu).
+#pragma once
+#include "format.cuh"
+
+namespace rsp {
+
+// ---- apply tick image (device) -------------------------------------------------------------------
+struct BatchDesc {
+  u32 shard_ix;
+  u32 boff;    // byte offset of the batch in the tick blob (16-byte aligned)
+  u32 len;     // bytes, including the appended LogData(timestamp) record when present
+  u32 op_base; // first reserved slot in the op table
+  u32 op_cap;  // reserved slots (min(header count, (len-12)/2))
+  u32 group;
+  u32 pad0, pad1;
+};
+struct GroupDesc {
+  u32 shard_ix;
+  u32 first_batch;
+  u32 n_batches;
+  u32 pad;
+};
+struct BatchRes {
+  u32 status;    // k_decode: mk_status(code,msg) or 0; k_sequence: final status
+  u32 n_ops;
+  u32 units;
+  u32 unit_base; // k_sequence
+  u64 seq_base;  // k_sequence: sequence of the first op
+  u32 ord_base;  // k_sequence: insertion ordinal of the first op
+  u32 accepted;  // k_sequence
+};
+struct GroupRes {
+  u64 last_seq;
+  u32 tail;
+  u32 count;
+  u32 latch;
+  u32 pad;
+};
+struct __align__(16) OpRec {
+  u32 koff, klen;  // key bytes in the blob
+  u32 voff, vlen;  // value bytes in the blob
+  u32 rel_units;   // entry offset (units) relative to the batch's unit_base
+  u32 type;        // kTypeValue / kTypeDeletion / kTypeSingleDeletion / kTypeMerge / kTypeInvalid
+  u32 batch_ix;
+  u32 op_ix;       // index within the batch (sequence = seq_base + op_ix)
+};
+
+struct TickDev {
+  const u8* blob;
+  const BatchDesc* batches;
+  const GroupDesc* groups;
+  BatchRes* bres;
+  GroupRes* gres;
+  OpRec* ops;
+  u32 n_batches;
+  u32 n_groups;
+  u32 n_ops_cap;
+};
+
+void launch_decode(const TickDev& t, cudaStream_t s);
+void launch_sequence(const TickDev& t, ShardDev* shards, cudaStream_t s);
+void launch_insert(const TickDev& t, ShardDev* shards, cudaStream_t s);
+void launch_publish(const TickDev& t, ShardDev* shards, cudaStream_t s);
+
+// ---- reads ---------------------------------------------------------------------------------------
+struct GetArgs {
+  const ShardDev* shards;
+  const u32* shard_ix;   // [n]
+  const u8* keys;        // key bytes
+  const u64* koff;       // [n+1] or nullptr when klen_fixed > 0
+  u32 klen_fixed;
+  u8* vals;              // value i at vals + i * val_stride
+  u64 val_stride;
+  u32* vlen;             // [n]
+  i32* st;               // [n]
+  u32 n;
+};
+void launch_multi_get(const GetArgs& a, cudaStream_t s);
+
+// dump the version stack of each key (newest first, up to and including the first Put/Delete) for
+// host-side merge folding: records [u32 type][u32 vlen][value, padded to 4] at out + i*stride
+struct VersionsArgs {
+  const ShardDev* shards;
+  const u32* shard_ix;
+  const u8* keys;
+  const u64* koff;
+  u8* out;
+  u64 out_stride;
+  u32* n_rec;   // [n] records written
+  u32* need;    // [n] bytes needed
+  u32 n;
+};
+void launch_get_versions(const VersionsArgs& a, cudaStream_t s);
+
+// range scan over a pinned set of runs (the memtable is flushed first by the host)
+struct ScanView {
+  RunDev runs[RSP_MAX_RUNS];
+  u32 n_runs;
+  u32 merge_op;
+  u32 pad0, pad1;
+};
+struct ScanArgs {
+  const ShardDev* shards;   // used when views == nullptr (shard_ix indexes it)
+  const ScanView* views;    // or explicit pinned views (one per request)
+  const u32* shard_ix;
+  const u8* keys;
+  const u64* koff;
+  u32 klen_fixed;
+  const u8* flags;          // per request: bit0 = exclusive start, bit1 = reverse, bit2 = from extreme
+  u32 max_entries;
+  u8* out;
+  u64 out_stride;
+  u32* n_out;
+  i32* st;
+  u32 n;
+};
+void launch_multi_scan(const ScanArgs& a, cudaStream_t s);
+
+// ---- flush / compaction ---------------------------------------------------------------------------
+struct SortItem {
+  u64 prefix;   // big-endian first 8 key bytes
+  u32 ref;      // unit offset of the entry in its source heap
+  u32 srcrank;  // src << 28 | rank : ascending == newest first among equal keys
+};
+struct CompactJob {
+  // sources: src 0 = memtable (optional), 1.. = runs newest first
+  const u8* src_heap[RSP_MAX_RUNS + 1];
+  const u32* src_ent_off[RSP_MAX_RUNS + 1];
+  u32 src_n[RSP_MAX_RUNS + 1];
+  u32 src_is_mem[RSP_MAX_RUNS + 1];
+  u32 n_src;
+  u32 n_items;      // sum of src_n
+  u32 n_pow2;       // padded sort size
+  u32 bottom;       // 1 = no older data below the output: tombstones can be dropped
+  u32 merge_op;
+  u32 pad;
+  // work buffers
+  SortItem* items;  // [n_pow2]
+  u32* keep_units;  // [n_items] output size in units of each sorted item (0 = dropped)
+  u32* out_pos;     // [n_items] exclusive scan of keep_units
+  u32* out_ord;     // [n_items] exclusive scan of (keep_units != 0)
+  u64* fold_val;    // [n_items] folded 8-byte merge results
+  u32* totals;      // [4]: units, entries, uniform_units (or 0), distinct keys
+  // outputs (allocated by the host after the sizing pass)
+  u8* out_heap;
+  u32* out_ent_off;
+  u32* out_hslots;
+  u64* out_blk_pfx;
+  u32 out_n_buckets;
+  u32 out_ord_bits;
+};
+void launch_compact_sort(const CompactJob* d_jobs, const CompactJob* h_jobs, u32 n_jobs, cudaStream_t s);
+void launch_compact_size(const CompactJob* d_jobs, u32 n_jobs, cudaStream_t s);
+void launch_compact_write(const CompactJob* d_jobs, u32 n_jobs, u32 max_items, cudaStream_t s);
+
+}  // namespace rsp

@@ -1,0 +1,300 @@
+"""GPU parity: the CUDA engine, called through the C ABI, against
+  (1) fixtures generated from the reference's own RocksDB binary (tests/golden, oracle/gen_golden.py),
+  (2) the oracle port on fresh seeded streams, incl. flush/compaction at arbitrary points,
+  (3) batched multi-shard ticks (rsp_apply_many / rsp_multi_get) vs per-shard oracle replay.
+Bit-exact: byte/integer work only.
+"""
+import random
+import struct
+
+import numpy as np
+import pytest
+
+import golden_util as G
+from oracle import okv
+from rocksplicator_b200.write_batch import WriteBatch
+from streams import bench_key, bench_value, corrupt_cases, random_stream
+
+pytestmark = pytest.mark.gpu
+u64 = lambda x: struct.pack("<Q", x)  # noqa: E731
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from rocksplicator_b200 import engine
+    e = engine.Engine(0)
+    yield e
+    e.close()
+
+
+_n = [0]
+
+
+def new_shard(eng, merge_op=0, **kw):
+    _n[0] += 1
+    return eng.open_shard("t%05d" % _n[0], merge_op=merge_op, **kw)
+
+
+@pytest.mark.parametrize("case", G.load("streams.json"), ids=lambda c: c["name"])
+def test_golden_streams(eng, case):
+    s = new_shard(eng, G.MERGE_IDS[case["merge"]])
+    G.replay_stream_case(s, case)
+    s.close()
+
+
+@pytest.mark.parametrize("case", G.load("streams.json")[:6], ids=lambda c: c["name"])
+def test_golden_streams_memtable_only(eng, case):
+    """same streams, never flushed: reads served by the hash memtable + version chains"""
+    s = new_shard(eng, G.MERGE_IDS[case["merge"]])
+    keys = [bytes.fromhex(k) for k in case["keys"]]
+    for st in case["steps"]:
+        assert s.apply(bytes.fromhex(st["batch"]), st["ts"]) == st["rc"]
+        assert s.latest_seq() == st["seq"]
+    probe = keys + [b"zz-missing"] + keys[:3]
+    for (khex, rc, vhex), k in zip(case["final"]["get"], probe):
+        assert s.get(k) == (rc, G.unhex(vhex)), khex
+    assert s.multi_get(probe) == [(rc, G.unhex(v)) for rc, v in case["final"]["multi_get"]]
+    s.close()
+
+
+def test_golden_corrupt(eng):
+    pre = WriteBatch().put(b"pre", b"x").data()
+    for c in G.load("corrupt.json"):
+        s = new_shard(eng, okv.MERGE_UINT64ADD)
+        assert s.apply(pre, 1) == 0
+        assert s.apply(bytes.fromhex(c["batch"]), 0x1122334455667788) == c["rc"], c["name"]
+        if c["rc"]:
+            assert s.last_error == c["msg"], c["name"]
+        assert s.latest_seq() == c["seq"], c["name"]
+        assert s.apply(pre, 2) == c["rc_after"], c["name"]  # the error latch
+        assert s.latest_seq() == c["seq_after"], c["name"]
+        assert [[k.hex(), v.hex()] for k, v in s.scan()] == c["scan"], c["name"]
+        s.close()
+
+
+def test_known_answers(eng):
+    want = {r[0]: r[1:] for r in G.load("known_answers.json")}
+    s = new_shard(eng, okv.MERGE_UINT64ADD)
+    assert [s.latest_seq()] == want["fresh_seq"]
+    b = WriteBatch().put(b"k1", b"v1").delete(b"k2").merge(b"c", u64(5)).put_log_data(u64(1234)).set_sequence(999)
+    assert [s.apply(b.data(), 5)] == want["row2_rc"]
+    assert [s.latest_seq()] == want["row2_seq"]
+    s.apply(WriteBatch().put_log_data(u64(1)).data(), 5)
+    assert [s.latest_seq()] == want["row3_seq"]
+    s.apply(bytes(12), 5)
+    assert [s.latest_seq()] == want["row4_seq"]
+    s.apply(WriteBatch().merge(b"c", u64(7)).data(), 5)
+    assert [s.get(b"c")[1].hex()] == want["row5_get_c"]
+    s.apply(WriteBatch().merge(b"k1", u64(1)).data(), 5)
+    assert [s.get(b"k1")[1].hex()] == want["row6_get_k1"]
+    s.apply(WriteBatch().put(b"z", u64(100)).delete(b"z").merge(b"z", u64(3)).merge(b"z", u64(4)).data(), 5)
+    assert [s.latest_seq()] == want["row7_seq"]
+    assert [s.get(b"z")[1].hex()] == want["row7_get_z"]
+    s.apply(WriteBatch().put(b"x", b"1").put(b"x", b"2").delete(b"x").put(b"x", b"3").delete(b"y").data(), 5)
+    assert [s.latest_seq()] == want["row8_seq"]
+    assert [s.get(b"x")[1].hex()] == want["row8_get_x"]
+    assert [s.get(b"y")[0]] == want["row8_get_y_rc"]
+    s.apply(WriteBatch().put(b"", b"").put(b"ev", b"").data(), 5)
+    assert [s.get(b"")[0], s.get(b"")[1].hex()] == want["row9_get_empty"]
+    assert [[[k.hex(), v.hex()] for k, v in s.scan()]] == want["row10_scan"]
+    assert [[[k.hex(), v.hex()] for k, v in s.scan(start=b"k", limit=1)]] == want["row10_seek_k"]
+    mg = [[rc, v.hex() if v is not None else None] for rc, v in s.multi_get([b"c", b"zz", b"c", b"k2", b"ev", b""])]
+    assert [mg] == want["row11_multi_get"]
+    s.flush()
+    assert [[[k.hex(), v.hex()] for k, v in s.scan()]] == want["row12_scan_after_flush"]
+    s.apply(WriteBatch().single_delete(b"ev").data(), 5)
+    assert [s.latest_seq()] == want["row18_seq"]
+    assert [s.get(b"ev")[0]] == want["row18_get_ev_rc"]
+    s.close()
+    s = new_shard(eng, okv.MERGE_NONE)
+    assert [s.apply(WriteBatch().merge(b"m", b"1").data(), 5)] == want["row13_write_rc"]
+    assert [s.latest_seq()] == want["row13_seq"]
+    rc, _ = s.get(b"m")
+    assert [rc, s.last_error] == want["row13_get_rc"]
+    s.close()
+
+
+def compare_all(s, o, keys, tag):
+    assert s.latest_seq() == o.latest_seq(), tag
+    probe = keys + [b"zz-missing"]
+    for k in probe:
+        assert s.get(k) == o.get(k), (tag, k)
+    assert s.multi_get(probe + probe[:5]) == o.multi_get(probe + probe[:5]), tag
+    assert s.scan() == o.scan(), tag
+    a, b = s.iterator(), o.iterator()
+    a.seek_to_last()
+    b.seek_to_last()
+    while True:
+        assert a.valid() == b.valid(), tag
+        if not a.valid():
+            break
+        assert (a.key(), a.value()) == (b.key(), b.value()), tag
+        a.prev()
+        b.prev()
+    rng = random.Random(5)
+    for _ in range(12):
+        k = rng.choice(keys) if rng.random() < 0.6 else bytes(rng.getrandbits(8) for _ in range(rng.randint(0, 4)))
+        a.seek(k)
+        b.seek(k)
+        for _step in range(5):
+            assert a.valid() == b.valid(), (tag, "seek", k)
+            if not a.valid():
+                break
+            assert (a.key(), a.value()) == (b.key(), b.value()), (tag, "seek", k)
+            if rng.random() < 0.5:
+                a.next(), b.next()
+            else:
+                a.prev(), b.prev()
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("merge,mname", [(okv.MERGE_COUNTER, "counter"), (okv.MERGE_APPEND, "append"),
+                                         (okv.MERGE_UINT64ADD, "counter"), (okv.MERGE_NONE, None)])
+def test_random_streams_vs_oracle(eng, port_lib, merge, mname):
+    """rocksdb_assumption_test.cpp:329-432 restated: the same shuffled stream through the oracle and the
+    engine gives equal sequence numbers and equal reads, with flush/compaction at arbitrary points."""
+    for seed in range(4):
+        rng = random.Random(seed)
+        keys, stream = random_stream(500 + seed * 13 + merge, 150, merge=mname, bad_operands=(seed == 3))
+        s = new_shard(eng, merge, write_buffer_bytes=(4096 if seed == 1 else 0))
+        o = okv.Okv(port_lib, merge_op=merge)
+        for i, (bt, ts) in enumerate(stream):
+            assert s.apply(bt, ts) == o.apply(bt, ts), (seed, i)
+            r = rng.random()
+            if r < 0.04:
+                s.flush()
+            elif r < 0.06:
+                s.compact()
+            if i % 50 == 49:
+                compare_all(s, o, keys, (merge, seed, i))
+        s.compact()
+        compare_all(s, o, keys, (merge, seed, "final"))
+        st = s.stats()
+        assert st["latest_seq"] == o.latest_seq()
+        s.close()
+        o.close()
+
+
+def test_replicator_test_vectors(eng):
+    """rocksdb_replicator_test.cpp:146-208 (100 x 2 Puts -> seq 200) and
+    rocksdb_assumption_test.cpp:136-187 (each op +1, batch of n +n)."""
+    s = new_shard(eng, okv.MERGE_APPEND)
+    for i in range(100):
+        t = str(i).encode()
+        assert s.apply(WriteBatch().put(t + b"key", t + b"value").put(t + b"key2", t + b"value2").data(), i) == 0
+        assert s.latest_seq() == 2 * (i + 1)
+    for i in range(100):
+        t = str(i).encode()
+        assert s.get(t + b"key") == (0, t + b"value")
+        assert s.get(t + b"key2") == (0, t + b"value2")
+    seq = s.latest_seq()
+    s.apply(WriteBatch().delete(b"a").put(b"b", b"1").put(b"c", b"2").merge(b"b", b"3").data(), 0)
+    assert s.latest_seq() == seq + 4
+    assert s.get(b"b") == (0, b"13")
+    s.close()
+
+
+def test_apply_many_multi_shard(eng, port_lib):
+    """one tick = many batches for many shards (the batching front-end), vs per-shard oracle replay;
+    includes a corrupt batch mid-tick: it and every later batch of THAT shard fail, others proceed."""
+    n_shards = 37
+    shards = [new_shard(eng, okv.MERGE_COUNTER) for _ in range(n_shards)]
+    oracles = [okv.Okv(port_lib, merge_op=okv.MERGE_COUNTER) for _ in range(n_shards)]
+    rng = random.Random(99)
+    all_keys = [[] for _ in range(n_shards)]
+    for tick in range(6):
+        six, batches, ts = [], [], []
+        for _ in range(400):
+            j = rng.randrange(n_shards)
+            wb = WriteBatch()
+            for _ in range(rng.randint(1, 4)):
+                k = bench_key(7, rng.randrange(200))
+                all_keys[j].append(k)
+                r = rng.random()
+                if r < 0.6:
+                    wb.put(k, bench_value(7, j, rng.randrange(200), tick))
+                elif r < 0.8:
+                    wb.merge(k, struct.pack("<q", rng.randint(-9, 9)))
+                else:
+                    wb.delete(k)
+            b = wb.data()
+            if tick == 3 and j == 5 and rng.random() < 0.3:
+                b = b[:-2]  # corrupt: shard 5 latches
+            six.append(shards[j].index)
+            batches.append(b)
+            ts.append(rng.getrandbits(40))
+        st = eng.apply_many(six, batches, ts)
+        want = [oracles[[s.index for s in shards].index(ix)].apply(b, t) for ix, b, t in zip(six, batches, ts)]
+        assert list(st) == want, tick
+    for j in range(n_shards):
+        assert shards[j].latest_seq() == oracles[j].latest_seq()
+        keys = sorted(set(all_keys[j]))
+        assert shards[j].multi_get(keys) == oracles[j].multi_get(keys)
+    # cross-shard MultiGet in one call
+    six, keys = [], []
+    for j in range(n_shards):
+        for k in sorted(set(all_keys[j]))[:20]:
+            six.append(shards[j].index)
+            keys.append(k)
+    got = eng.multi_get(six, keys, stride=64)
+    want = []
+    for ix, k in zip(six, keys):
+        j = [s.index for s in shards].index(ix)
+        want.append(oracles[j].get(k))
+    assert got == want
+    for s in shards:
+        s.close()
+
+
+def test_scale_properties(eng, port_lib):
+    """size-independent properties at a scale the oracle replays in seconds: load N keys over S shards
+    through the apply path, overwrite a third, delete a tenth; every shard compacted; then
+    (a) every live key reads its newest value, deleted keys NotFound, (b) scans are sorted, complete and
+    equal to the oracle's, (c) sequence numbers equal the op counts, (d) MultiGet == Get."""
+    S, N = 16, 40000
+    shards = [new_shard(eng, 0, write_buffer_bytes=1 << 18) for _ in range(S)]
+    oracles = [okv.Okv(port_lib) for _ in range(S)]
+    seed = 0x5EED0001
+    idx = np.arange(N)
+    for rnd, sel in enumerate((idx, idx[::3])):
+        six, batches, ts = [], [], []
+        for i in sel:
+            j = int(i) % S
+            six.append(shards[j].index)
+            batches.append(WriteBatch().put(bench_key(seed, int(i)), bench_value(seed, j, int(i), rnd)).data())
+            ts.append(1000 + int(i))
+        for lo in range(0, len(six), 8192):
+            st = eng.apply_many(six[lo:lo + 8192], batches[lo:lo + 8192], ts[lo:lo + 8192])
+            assert not st.any()
+        for ix, b, t in zip(six, batches, ts):
+            oracles[[s.index for s in shards].index(ix)].apply(b, t)
+    dels = idx[::10]
+    six = [shards[int(i) % S].index for i in dels]
+    batches = [WriteBatch().delete(bench_key(seed, int(i))).data() for i in dels]
+    assert not eng.apply_many(six, batches, [0] * len(six)).any()
+    for i, b in zip(dels, batches):
+        oracles[int(i) % S].apply(b, 0)
+    for j in range(S):
+        assert shards[j].latest_seq() == oracles[j].latest_seq()
+    eng.compact_all()
+    for j in range(S):
+        got = shards[j].scan()
+        assert got == oracles[j].scan()
+        assert all(got[i][0] < got[i + 1][0] for i in range(len(got) - 1))
+        assert shards[j].stats()["n_runs"] == 1
+    keys = [bench_key(seed, int(i)) for i in idx[::7]]
+    six = [shards[int(i) % S].index for i in idx[::7]]
+    got = eng.multi_get(six, keys, stride=64)
+    for (rc, v), i in zip(got, idx[::7]):
+        want = oracles[int(i) % S].get(bench_key(seed, int(i)))
+        assert (rc, v) == want
+    # batched scans: Seek + 128 x Next
+    starts = [bench_key(seed, int(i)) for i in idx[5::5000]]
+    six = [shards[int(i) % S].index for i in idx[5::5000]]
+    res = eng.multi_scan(six, starts, 128, 128 * (8 + 16 + 64))
+    for (st, recs), i, k in zip(res, idx[5::5000], starts):
+        assert st == 0
+        assert recs == oracles[int(i) % S].scan(start=k, limit=128)
+    for s in shards:
+        s.close()
