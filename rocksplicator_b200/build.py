@@ -52,7 +52,8 @@ def build(force=False, verbose=False):
         list(ex.map(run, jobs))
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(OUT, objs):
-        run([_nvcc(), "-shared", "-o", OUT] + objs + ["-cudart", "static", "-lpthread", "-ldl", "-lrt"])
+        run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs +
+            ["-cudart", "static", "-lpthread", "-ldl", "-lrt"])
     return OUT
 
 

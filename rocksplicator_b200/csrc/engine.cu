@@ -598,7 +598,8 @@ static bool host_merge_one(rsp_shard* s, const std::string& key, bool has, const
 }
 
 // resolve one key through the version-dump kernel and the host operator
-static int host_fold_get(rsp_engine* e, rsp_shard* s, const uint8_t* key, size_t klen, std::string* value) {
+static int host_fold_get(rsp_engine* e, rsp_shard* s, const uint8_t* key, size_t klen, std::string* value,
+                         const ScanView* d_view = nullptr) {
   size_t stride = 4096;
   for (;;) {
     u8* d = (u8*)e->dev_q.get(klen + 64 + stride + 64);
@@ -610,7 +611,7 @@ static int host_fold_get(rsp_engine* e, rsp_shard* s, const uint8_t* key, size_t
     CUDA_OK(cudaMemcpyAsync(d_koff, koff, 16, cudaMemcpyHostToDevice, e->st));
     CUDA_OK(cudaMemcpyAsync(d_six, &six, 4, cudaMemcpyHostToDevice, e->st));
     if (klen) CUDA_OK(cudaMemcpyAsync(d_key, key, klen, cudaMemcpyHostToDevice, e->st));
-    VersionsArgs a{e->d_shards, (const u32*)d_six, d_key, (const u64*)d_koff, d_out, stride - 64, (u32*)d_nrec, (u32*)d_need, 1};
+    VersionsArgs a{e->d_shards, d_view, (const u32*)d_six, d_key, (const u64*)d_koff, d_out, stride - 64, (u32*)d_nrec, (u32*)d_need, 1};
     launch_get_versions(a, e->st);
     e->launches++;
     u32 res[2];
@@ -735,11 +736,13 @@ struct rsp_iter {
 static void iter_fetch(rsp_iter* it, const std::string* key, bool exclusive, bool reverse) {
   rsp_engine* e = it->s->eng;
   std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
   it->buf.clear();
   it->pos = 0;
   it->reverse = reverse;
-  const size_t klen = key ? key->size() : 0;
+  std::string fetch_key;
   for (;;) {
+    const size_t klen = key ? key->size() : 0;
     const size_t o_key = 64, o_out = 64 + align_up(klen + 16, 256);
     u8* d = (u8*)e->dev_q.get(o_out + it->stride + 256);
     // header: [koff 2x8][flags 1][pad][n_out 4 @32][st 4 @36]
@@ -763,18 +766,31 @@ static void iter_fetch(rsp_iter* it, const std::string* key, bool exclusive, boo
     std::vector<u8> h(it->stride);
     if (n_out) CUDA_OK(cudaMemcpy(h.data(), d + o_out, it->stride, cudaMemcpyDeviceToHost));
     size_t at = 0;
+    std::string last_key;
     for (u32 i = 0; i < n_out; i++) {
       u32 kl, vl;
       memcpy(&kl, &h[at], 4);
       memcpy(&vl, &h[at + 4], 4);
-      it->buf.emplace_back(std::string((const char*)&h[at + 8], kl), std::string((const char*)&h[at + 8 + kl], vl));
-      at += 8 + kl + vl;
+      std::string k((const char*)&h[at + 8], kl);
+      last_key = k;
+      if (vl == 0xffffffffu) {  // operator lives on the host: fold this key against the pinned view
+        std::string v;
+        const int rc = host_fold_get(e, it->s, (const uint8_t*)k.data(), k.size(), &v, it->d_view);
+        if (rc == RSP_OK) it->buf.emplace_back(std::move(k), std::move(v));
+        else if (rc != RSP_NOT_FOUND) { it->status = rc; it->buf.emplace_back(std::move(k), std::string()); }
+        at += 8 + kl;
+        // (the scan kernel's scratch was reused by the fold: the copy in `h` is what we keep reading)
+      } else {
+        it->buf.emplace_back(std::move(k), std::string((const char*)&h[at + 8 + kl], vl));
+        at += 8 + kl + vl;
+      }
     }
     it->exhausted = !(st == RSP_INCOMPLETE || n_out == it->want);
-    if (st != 0 && st != RSP_INCOMPLETE) {
-      if (st == ST_NEED_HOST_MERGE) it->status = RSP_NOT_SUPPORTED;
-      else it->status = st >> 8;  // sticky, as DBIter's status_
-      if (st != ST_NEED_HOST_MERGE) it->exhausted = (n_out < it->want);
+    if (st > 255) it->status = st >> 8;  // a failed merge: sticky, as DBIter's status_
+    if (it->buf.empty() && !it->exhausted) {
+      // every fetched key folded to "deleted": keep going from the last key the kernel returned
+      fetch_key = last_key; key = &fetch_key; exclusive = true;
+      continue;
     }
     break;
   }
@@ -1107,8 +1123,10 @@ int rsp_multi_scan(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->last_ms["scan"] = ms;
-  for (size_t i = 0; i < n; i++)
-    if (st[i] > 255) st[i] = st[i] >> 8;
+  for (size_t i = 0; i < n; i++) {
+    if (st[i] == ST_NEED_HOST_MERGE) st[i] = RSP_NOT_SUPPORTED;  // host-folded operators: use the iterator
+    else if (st[i] > 255) st[i] = st[i] >> 8;
+  }
   return RSP_OK;
 }
 

@@ -283,12 +283,19 @@ __global__ void k_get_versions(VersionsArgs a) {
   const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= a.n) return;
   const u32 lane_in_warp = threadIdx.x & 31u;
-  const ShardDev* sd = a.shards + a.shard_ix[q];
+  const ShardDev* sd = a.views ? nullptr : a.shards + a.shard_ix[q];
   const u64 o = a.koff[q];
   const u32 klen = (u32)(a.koff[q + 1] - o);
   DumpVisitor v{a.out + (u64)q * a.out_stride, a.out_stride, 0, 0, false};
   bool stopped;
-  walk_shard<1>(sd, a.keys + o, klen, 0, 1u << lane_in_warp, lane_in_warp, v, stopped);
+  if (a.views) {  // a pinned iterator snapshot: sorted runs only
+    const ScanView& vw = a.views[q];
+    const u64 h = hash_key(a.keys + o, klen);
+    for (u32 ri = 0; ri < vw.n_runs && !v.done; ri++)
+      walk_run<1>(vw.runs[ri], a.keys + o, klen, h, 0, 1u << lane_in_warp, lane_in_warp, v);
+  } else {
+    walk_shard<1>(sd, a.keys + o, klen, 0, 1u << lane_in_warp, lane_in_warp, v, stopped);
+  }
   a.n_rec[q] = v.n_rec;
   a.need[q] = v.used;
 }
@@ -425,8 +432,12 @@ __global__ void __launch_bounds__(128) k_multi_scan(ScanArgs a) {
     acc.end_of_versions();
     if (acc.status == 1) continue;  // deleted
     u32 vlen = 0;
-    if (acc.status == ST_NEED_HOST_MERGE) { st = ST_NEED_HOST_MERGE; break; }
-    if (acc.status != 0) {
+    bool host_fold = false;
+    if (acc.status == ST_NEED_HOST_MERGE) {
+      // the operator lives on the host: hand back the key alone (vlen marker 0xffffffff)
+      if (st == 0) st = ST_NEED_HOST_MERGE;
+      host_fold = true;
+    } else if (acc.status != 0) {
       // DBIter keeps the key with an empty value and records the (sticky) status
       st = (i32)mk_status((u32)acc.status, acc.msg);
     } else {
@@ -436,7 +447,8 @@ __global__ void __launch_bounds__(128) k_multi_scan(ScanArgs a) {
     if (used + rec > a.out_stride) { if (st == 0) st = 7; break; }
     if (lane == 0) {
       u8 hdr[8];
-      for (u32 b = 0; b < 4; b++) { hdr[b] = (u8)(bk.klen >> (8 * b)); hdr[4 + b] = (u8)(vlen >> (8 * b)); }
+      const u32 vl_out = host_fold ? 0xffffffffu : vlen;
+      for (u32 b = 0; b < 4; b++) { hdr[b] = (u8)(bk.klen >> (8 * b)); hdr[4 + b] = (u8)(vl_out >> (8 * b)); }
       for (u32 b = 0; b < 8; b++) out[used + b] = hdr[b];
     }
     warp_copy_bytes(out + used + 8, reinterpret_cast<const u8*>(bk.key()), bk.klen, lane);

@@ -79,8 +79,10 @@ void launch_multi_get(const GetArgs& a, cudaStream_t s);
 
 // dump the version stack of each key (newest first, up to and including the first Put/Delete) for
 // host-side merge folding: records [u32 type][u32 vlen][value, padded to 4] at out + i*stride
+struct ScanView;
 struct VersionsArgs {
   const ShardDev* shards;
+  const ScanView* views;   // when set: one pinned view per query (runs only), shards/shard_ix unused
   const u32* shard_ix;
   const u8* keys;
   const u64* koff;
