@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of BASELINE.json on B200: MultiGet lookups/s + replicated applies/s per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1], SURVEY.md §8d "config 2"): 1024 shards on one GPU, 10 M KV total,
+16 B keys / 64 B values, loaded through the apply path and fully compacted.  One step =
+  * one MultiGet pass: 256 concurrent MultiGet(4096) calls = 1,048,576 uniform lookups in one launch, and
+  * one apply tick: 1024 shards x 50 replicated single-Put WriteBatches (pull-sized, 105 wire bytes each).
+`value` is MultiGet lookups/s with queries and results resident in HBM (CUDA events on the engine's
+stream); `applies` carries the apply-side numbers; `e2e` is the same through the host-buffer C ABI
+(rsp_multi_get_fixed / rsp_apply_many) with pinned host memory, H2D + D2H inside the timed region.
+N > 1: one process per GPU (torchrun), each rank an independent engine with its own 1024 shards —
+shards partition shard_id -> GPU, no collective on the data path ("scaling": "weak").
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+A_GET = 16 + (16 + 64 + 8) + 64          # algorithmic bytes per MultiGet hit
+A_PUT = 83 + 22 + 88                     # per single-Put apply
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_cpu(lib_kind, threads, shards, kv, apply_cap, get_secs, batch=4096, wal=1):
+    """times oracle/okv_cpu_bench (the reference's RocksDB binary when oracle/_ref is present, else the port)"""
+    from oracle import okv
+    okv.build(ref=os.path.isdir("/root/reference"))
+    lib = okv.REF_SO if (lib_kind == "reference" and okv.ref_available()) else okv.PORT_SO
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    d = os.path.join(base, "okv_bench_%d" % os.getpid())
+    subprocess.call(["rm", "-rf", d])
+    os.makedirs(d)
+    try:
+        out = subprocess.check_output([os.path.join(ROOT, "oracle", "okv_cpu_bench"), lib, str(threads), str(shards),
+                                       str(kv), "64", str(wal), str(apply_cap), str(get_secs), str(batch), "1", d],
+                                      text=True)
+    finally:
+        subprocess.call(["rm", "-rf", d])
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--kv", type=int, default=10_000_000)
+    ap.add_argument("--shards", type=int, default=1024)
+    ap.add_argument("--mg-batches", type=int, default=256, help="concurrent MultiGet(4096) calls per launch")
+    ap.add_argument("--tick", type=int, default=50, help="replicated updates per shard per apply tick")
+    ap.add_argument("--cpu-kv", type=int, default=2_000_000)
+    ap.add_argument("--cpu-get-secs", type=float, default=6.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    K, W = args.steps, max(args.warmup, 0)
+    ncores = os.cpu_count() or 1
+    workload = "%d shards x %d KV total, 16B key/64B value, uniform MultiGet batch=4096 x %d in flight, apply tick %d shards x %d single-Put WriteBatch" % (
+        args.shards, args.kv, args.mg_batches, args.shards, args.tick)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = run_cpu("reference", ncores, args.shards, args.cpu_kv, 60.0, max(2.0, min(20.0, 1.0 * K)))
+        line = {
+            "impl": "reference", "metric": "multiget_lookups_per_s", "value": r["lookups_per_s"], "unit": "lookups/s",
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * r["get_s"] / max(K, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload, "sample": "%d KV applied (WAL on, default WriteOptions), flush+compact, %.0f s of MultiGet(4096) split per shard" % (r["applied"], r["get_s"])},
+            "applies": {"value": r["applies_per_s"], "unit": "applies/s"},
+            "cpu_baseline": {"value": r["lookups_per_s"], "unit": "lookups/s", "cores": r["threads"], "kind": r["kind"],
+                             "sample": "%d KV over %d shards, %d threads" % (r["applied"], r["shards"], r["threads"]),
+                             "applies_per_s": r["applies_per_s"]},
+            "e2e": {"value": r["lookups_per_s"], "unit": "lookups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rocksplicator_b200 import build, engine, synth
+    if not os.path.exists(engine.SO_PATH):
+        build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    lib = engine.load_library()
+    eng = engine.Engine(local_rank, max_shards=max(16384, args.shards))
+    stream = torch.cuda.ExternalStream(lib.rsp_engine_stream(eng.h), device=torch.device("cuda", local_rank))
+    S, NKV = args.shards, args.kv
+    shards = [eng.open_shard("segment%05d" % (rank * S + i), write_buffer_bytes=2 << 20) for i in range(S)]
+    six_of = np.array([s.index for s in shards], dtype=np.uint32)
+    seed = synth.SEED_DATA + rank
+
+    # ---- load through the apply path, then fully compact -------------------------------------------
+    t_load = time.perf_counter()
+    CH = 1 << 20
+    for lo in range(0, NKV, CH):
+        idx = np.arange(lo, min(NKV, lo + CH), dtype=np.uint64)
+        sh = (idx % np.uint64(S)).astype(np.int64)
+        b = synth.single_put_batches(synth.keys16(seed, idx), synth.values(seed, sh, idx, 0), 1000 + idx)
+        off = (np.arange(idx.size + 1, dtype=np.uint64) * np.uint64(b.shape[1]))
+        st = eng.apply_packed(six_of[sh], b.reshape(-1), off, 1000 + idx)
+        assert not st.any(), "load failed"
+    eng.compact_all()
+    t_load = time.perf_counter() - t_load
+    assert sum(s.latest_seq() for s in shards) == NKV
+
+    # ---- MultiGet: device-resident queries -----------------------------------------------------------
+    Q = args.mg_batches * 4096
+    n_sets = W + K
+    rng = np.random.default_rng(synth.SEED_QUERY + rank)
+    with torch.cuda.stream(stream):
+        q_idx = [rng.integers(0, NKV, size=Q, dtype=np.uint64) for _ in range(n_sets)]
+        d_keys = [torch.from_numpy(synth.keys16(seed, qi).reshape(-1)).cuda() for qi in q_idx]
+        d_six = [torch.from_numpy(six_of[(qi % np.uint64(S)).astype(np.int64)].astype(np.int32)).cuda() for qi in q_idx]
+        d_vals = torch.empty(Q * 64, dtype=torch.uint8, device="cuda")
+        d_vlen = torch.empty(Q, dtype=torch.int32, device="cuda")
+        d_st = torch.empty(Q, dtype=torch.int32, device="cuda")
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def mg(i):
+        rc = lib.rsp_multi_get_device(eng.h, Q, d_six[i].data_ptr(), d_keys[i].data_ptr(), 16, d_vals.data_ptr(), 64,
+                                      d_vlen.data_ptr(), d_st.data_ptr(), sp)
+        assert rc == 0
+
+    for i in range(W):
+        mg(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = eng.kernel_launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record(stream)
+    for k in range(K):
+        ev[k][0].record(stream)
+        mg(W + k)
+        ev[k][1].record(stream)
+    e_end.record(stream)
+    barrier()
+    mg_total_ms = max_over_ranks(e_start.elapsed_time(e_end))
+    mg_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    mg_launches = eng.kernel_launches() - launches0
+    # parity at full size (size-independent property: every value is a pure function of its key)
+    last = q_idx[W + K - 1] if K else q_idx[-1]
+    assert int(d_st.count_nonzero().item()) == 0 and int((d_vlen != 64).count_nonzero().item()) == 0
+    want = synth.values(seed, (last % np.uint64(S)).astype(np.int64), last, 0)
+    got = d_vals.cpu().numpy().reshape(Q, 64)
+    assert np.array_equal(got, want), "MultiGet parity failed at full size"
+
+    # ---- MultiGet end to end: host (pinned) buffers through rsp_multi_get_fixed ------------------------
+    h_keys = [torch.from_numpy(synth.keys16(seed, qi).reshape(-1)).pin_memory() for qi in q_idx[:min(n_sets, 4)]]
+    h_six = [torch.from_numpy(six_of[(qi % np.uint64(S)).astype(np.int64)].astype(np.int32)).pin_memory() for qi in q_idx[:min(n_sets, 4)]]
+    h_vals = torch.empty(Q * 64, dtype=torch.uint8).pin_memory()
+    h_vlen = torch.empty(Q, dtype=torch.int32).pin_memory()
+    h_st = torch.empty(Q, dtype=torch.int32).pin_memory()
+
+    def mg_e2e(i):
+        j = i % len(h_keys)
+        rc = lib.rsp_multi_get_fixed(eng.h, Q, h_six[j].data_ptr(), h_keys[j].data_ptr(), 16, h_vals.data_ptr(), 64,
+                                     h_vlen.data_ptr(), h_st.data_ptr())
+        assert rc == 0
+
+    for i in range(W):
+        mg_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        mg_e2e(W + k)
+    barrier()
+    mg_e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert int(h_st.count_nonzero().item()) == 0
+    jl = (W + K - 1) % len(h_keys)
+    assert np.array_equal(h_vals.numpy().reshape(Q, 64),
+                          synth.values(seed, (q_idx[jl] % np.uint64(S)).astype(np.int64), q_idx[jl], 0))
+
+    # ---- apply: replicated single-Put updates to existing keys, pull-sized groups per shard -----------
+    T = S * args.tick
+    ticks = []
+    upd_idx = []
+    for stp in range(n_sets * 2):
+        # `tick` updates per shard: shard-local ordinals uniform, global index = shard + ordinal * S
+        per = NKV // S
+        ordn = rng.integers(0, per, size=T, dtype=np.uint64)
+        sh = np.repeat(np.arange(S, dtype=np.uint64), args.tick)
+        idx = sh + ordn * np.uint64(S)
+        b = synth.single_put_batches(synth.keys16(seed, idx), synth.values(seed, sh.astype(np.int64), idx, stp + 1), 5000 + idx)
+        ticks.append((six_of[sh.astype(np.int64)], b, (np.arange(T + 1, dtype=np.uint64) * np.uint64(b.shape[1])), 5000 + idx))
+        upd_idx.append(idx)
+    staged = []
+    for stp in range(n_sets):
+        six, b, off, ts = ticks[stp]
+        h = C.c_void_p()
+        rc = lib.rsp_stage_build(eng.h, T, six.ctypes.data, b.ctypes.data, off.ctypes.data, ts.ctypes.data, C.byref(h))
+        assert rc == 0
+        staged.append(h)
+    st_out = np.zeros(T, dtype=np.int32)
+
+    def apply_dev(i):
+        assert lib.rsp_reserve(eng.h, staged[i]) == 0
+        assert lib.rsp_apply_staged_device(eng.h, staged[i], sp) == 0
+        assert lib.rsp_apply_staged_finish(eng.h, staged[i], st_out.ctypes.data) == 0
+
+    for i in range(W):
+        apply_dev(i)
+    barrier()
+    launches1 = eng.kernel_launches()
+    a_start, a_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a_start.record(stream)
+    for k in range(K):
+        apply_dev(W + k)
+    a_end.record(stream)
+    barrier()
+    ap_total_ms = max_over_ranks(a_start.elapsed_time(a_end))
+    ap_kernel_ms = eng.last_kernel_ms("apply")
+    ap_launches = eng.kernel_launches() - launches1
+    assert not st_out.any()
+
+    # e2e apply: host blob through rsp_apply_many (staging + H2D + kernels + D2H of statuses)
+    def apply_e2e(i):
+        six, b, off, ts = ticks[n_sets + i]
+        st = eng.apply_packed(six, b.reshape(-1), off, ts)
+        assert not st.any()
+
+    for i in range(W):
+        apply_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        apply_e2e(W + k)
+    barrier()
+    ap_e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clk = clocks.stop()
+
+    # parity after the update ticks: the newest version wins for every updated key (last writer)
+    newest = {}
+    for stp in range(2 * n_sets):
+        for i in upd_idx[stp][::97]:
+            newest[int(i)] = stp + 1
+    chk = np.fromiter(newest.keys(), dtype=np.uint64)
+    ver = np.fromiter(newest.values(), dtype=np.int64)
+    # a key sampled at step s may have been rewritten later by an unsampled update: resolve exactly
+    lastver = {}
+    for stp in range(2 * n_sets):
+        for i in upd_idx[stp]:
+            lastver[int(i)] = stp + 1
+    ver = np.array([lastver[int(i)] for i in chk], dtype=np.int64)
+    res = eng.multi_get(six_of[(chk % np.uint64(S)).astype(np.int64)], [k.tobytes() for k in synth.keys16(seed, chk)], stride=64)
+    for (rc, v), i, vr in zip(res, chk, ver):
+        w = synth.values(seed, np.array([int(i) % S]), np.array([i], dtype=np.uint64), int(vr))[0].tobytes()
+        assert rc == 0 and v == w, "apply parity failed"
+    assert sum(s.latest_seq() for s in shards) == NKV + 2 * n_sets * T
+
+    # ---- numbers ---------------------------------------------------------------------------------------
+    peak, peak_src = peaks()
+    lookups_per_s = sum_over_ranks(Q * K) / (mg_total_ms * 1e-3)
+    applies_per_s = sum_over_ranks(T * K) / (ap_total_ms * 1e-3)
+    ach = A_GET * Q / (mg_kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "multiget_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    cpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu:
+        r = run_cpu("reference", ncores, S, args.cpu_kv, 30.0, args.cpu_get_secs)
+        cpu = {"value": r["lookups_per_s"], "unit": "lookups/s", "cores": r["threads"], "kind": r["kind"],
+               "sample": "%d KV applied over %d shards with default WriteOptions (WAL on), flush+compact, then %.0f s of MultiGet(4096) split per shard; %d threads" % (
+                   r["applied"], r["shards"], r["get_s"], r["threads"]),
+               "applies_per_s": r["applies_per_s"]}
+    if rank == 0:
+        line = {
+            "metric": "multiget_lookups_per_s", "value": lookups_per_s, "unit": "lookups/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": (mg_total_ms + ap_total_ms) / max(K, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload, "l2": "inputs larger than L2: 0.96 GB entry heap per GPU, fresh uniform keys every step",
+                       "timing": "CUDA events on the engine stream, max over ranks", "load_s": round(t_load, 2)},
+            "applies": {"value": applies_per_s, "unit": "applies/s", "ms_per_tick": ap_total_ms / max(K, 1),
+                        "kernel_ms_last_tick": ap_kernel_ms, "batches_per_tick": T,
+                        "hbm_frac_of_peak": (A_PUT * T / (ap_kernel_ms * 1e-3) / 1e9 / peak) if ap_kernel_ms and ap_kernel_ms > 0 else None,
+                        "e2e": {"value": sum_over_ranks(T * K) / ap_e2e_s, "unit": "applies/s", "h2d_bytes_per_step": int(ticks[0][1].size + 10 * T), "d2h_bytes_per_step": 32 * T}},
+            "roofline": {"kernel": "k_multi_get", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_lookup": A_GET,
+                         "lookups_per_launch": Q, "launch_ms": mg_kernel_ms},
+            "e2e": {"value": sum_over_ranks(Q * K) / mg_e2e_s, "unit": "lookups/s", "h2d_bytes_per_step": Q * 20, "d2h_bytes_per_step": Q * 72},
+            "cpu_baseline": cpu,
+            "gpu_launches": int(mg_launches + ap_launches),
+            "clocks": clk,
+        }
+        print(json.dumps(line))
+    for h in staged:
+        lib.rsp_stage_free(h)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

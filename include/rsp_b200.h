@@ -94,6 +94,8 @@ typedef struct rsp_stats {
 int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out);
 void rsp_engine_destroy(rsp_engine* e);
 int rsp_engine_device(const rsp_engine* e);
+/* the engine's CUDA stream (cudaStream_t as void*): lets a caller order its own work / events with it */
+void* rsp_engine_stream(const rsp_engine* e);
 int rsp_shard_open(rsp_engine* e, const char* name, const rsp_shard_opts* opts, rsp_shard** out);
 int rsp_shard_close(rsp_shard* s); /* frees the shard's HBM (removeDB + DB close) */
 uint32_t rsp_shard_index(const rsp_shard* s); /* index used by the batched calls below */

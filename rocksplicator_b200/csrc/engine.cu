@@ -845,6 +845,7 @@ void rsp_engine_destroy(rsp_engine* e) {
 }
 
 int rsp_engine_device(const rsp_engine* e) { return e->device; }
+void* rsp_engine_stream(const rsp_engine* e) { return (void*)e->st; }
 
 int rsp_shard_open(rsp_engine* e, const char* name, const rsp_shard_opts* opts, rsp_shard** out) {
   if (!e || !name || !out) return RSP_INVALID_ARGUMENT;

@@ -42,6 +42,7 @@ EXPORTS = {
     "rsp_engine_create": (C.c_int, [C.c_int, C.POINTER(EngineCfg), C.POINTER(C.c_void_p)]),
     "rsp_engine_destroy": (None, [C.c_void_p]),
     "rsp_engine_device": (C.c_int, [C.c_void_p]),
+    "rsp_engine_stream": (C.c_void_p, [C.c_void_p]),
     "rsp_shard_open": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(ShardOpts), C.POINTER(C.c_void_p)]),
     "rsp_shard_close": (C.c_int, [C.c_void_p]),
     "rsp_shard_index": (C.c_uint32, [C.c_void_p]),

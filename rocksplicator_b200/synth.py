@@ -1,0 +1,75 @@
+"""Synthetic shard data of SURVEY.md §8(d), vectorised with numpy (bench + tests).
+
+keys   : 16 B = big-endian u64 index ‖ big-endian u64 splitmix64(seed ^ index); shard = index % n_shards
+values : vlen bytes from a splitmix64 stream keyed by (seed, shard, index, version)
+batches: the replicated unit — one Put + the leader's 8-byte timestamp LogData = 105 wire bytes at 16/64
+seeds  : data 0x5EED0001, queries 0x5EED0002, zipf 0x5EED0003
+"""
+import numpy as np
+
+SEED_DATA, SEED_QUERY, SEED_ZIPF = 0x5EED0001, 0x5EED0002, 0x5EED0003
+
+
+def splitmix64(x):
+    x = (np.asarray(x, dtype=np.uint64) + np.uint64(0x9E3779B97F4A7C15))
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def keys16(seed, idx):
+    """(n, 16) uint8"""
+    idx = np.asarray(idx, dtype=np.uint64)
+    out = np.empty((idx.size, 2), dtype=">u8")
+    out[:, 0] = idx
+    out[:, 1] = splitmix64(np.uint64(seed) ^ idx)
+    return out.view(np.uint8).reshape(idx.size, 16)
+
+
+def values(seed, shard, idx, version, vlen=64):
+    """(n, vlen) uint8"""
+    idx = np.asarray(idx, dtype=np.uint64)
+    shard = np.asarray(shard, dtype=np.uint64)
+    s = splitmix64(np.uint64(seed) ^ (shard << np.uint64(40)) ^ (idx << np.uint64(8)) ^ np.uint64(version))
+    nw = (vlen + 7) // 8
+    out = np.empty((idx.size, nw), dtype="<u8")
+    for w in range(nw):
+        s = splitmix64(s)
+        out[:, w] = s
+    return out.view(np.uint8).reshape(idx.size, nw * 8)[:, :vlen]
+
+
+def _varint(n):
+    out = bytearray()
+    while n >= 0x80:
+        out.append((n & 0x7F) | 0x80)
+        n >>= 7
+    out.append(n)
+    return bytes(out)
+
+
+def single_put_batches(keys, vals, ts_ms):
+    """(n, L) uint8 wire bytes: header(seq=0,count=1) Put(key,val) LogData(ts) — what the leader serves
+    (replicated_db.cpp:115-117, 527-530)."""
+    n, klen = keys.shape
+    vlen = vals.shape[1]
+    kv, vv = _varint(klen), _varint(vlen)
+    L = 12 + 1 + len(kv) + klen + len(vv) + vlen + 10
+    b = np.zeros((n, L), dtype=np.uint8)
+    b[:, 8] = 1
+    at = 12
+    b[:, at] = 1
+    at += 1
+    b[:, at:at + len(kv)] = np.frombuffer(kv, dtype=np.uint8)
+    at += len(kv)
+    b[:, at:at + klen] = keys
+    at += klen
+    b[:, at:at + len(vv)] = np.frombuffer(vv, dtype=np.uint8)
+    at += len(vv)
+    b[:, at:at + vlen] = vals
+    at += vlen
+    b[:, at] = 3
+    b[:, at + 1] = 8
+    b[:, at + 2:at + 10] = np.asarray(ts_ms, dtype="<u8").reshape(n, 1).view(np.uint8)
+    return b
