@@ -212,7 +212,7 @@ struct rsp_engine {
   std::vector<rsp_shard*> slots;
   std::unordered_map<std::string, rsp_shard*> by_name;
   PinBuf pin_in, pin_out;
-  DevBuf dev_tick, dev_q;
+  DevBuf dev_tick, dev_q, dev_pending;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::map<std::string, float> last_ms;
   std::atomic<u64> launches{0};
@@ -680,6 +680,8 @@ static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, c
   a.shards = e->d_shards; a.shard_ix = (const u32*)(d + o_six); a.keys = d + o_keys;
   a.koff = klen_fixed ? nullptr : (const u64*)(d + o_koff); a.klen_fixed = klen_fixed;
   a.vals = d + o_vals; a.val_stride = val_stride; a.vlen = (u32*)(d + o_vlen); a.st = (i32*)(d + o_st); a.n = (u32)n;
+  a.n_pending = (u32*)e->dev_pending.get((n + 1) * 4);
+  a.pending = a.n_pending + 1;
   CUDA_OK(cudaEventRecord(e->ev0, e->st));
   launch_multi_get(a, e->st);
   e->launches++;
@@ -813,6 +815,12 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
     return RSP_IO_ERROR;
   }
   CUDA_OK(cudaSetDevice(device));
+  {
+    // random 96-byte entry reads: ask L2 for sector-sized DRAM fetches (default is wider)
+    const char* g = getenv("RSP_L2_FETCH_BYTES");
+    const size_t gran = g ? (size_t)atoi(g) : 32;
+    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+  }
   rsp_engine* e = new rsp_engine();
   e->device = device;
   if (cfg) e->cfg = *cfg;
@@ -837,7 +845,7 @@ void rsp_engine_destroy(rsp_engine* e) {
   for (rsp_shard* s : e->slots)
     if (s) { s->runs.clear(); delete s; }
   e->arena.destroy();
-  e->pin_in.destroy(); e->pin_out.destroy(); e->dev_tick.destroy(); e->dev_q.destroy();
+  e->pin_in.destroy(); e->pin_out.destroy(); e->dev_tick.destroy(); e->dev_q.destroy(); e->dev_pending.destroy();
   cudaFree(e->d_shards);
   cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
   cudaStreamDestroy(e->st);
@@ -1138,8 +1146,13 @@ int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, co
   GetArgs a;
   a.shards = e->d_shards; a.shard_ix = d_shard_ix; a.keys = d_keys; a.koff = nullptr; a.klen_fixed = klen;
   a.vals = d_vals; a.val_stride = val_stride; a.vlen = d_vlen; a.st = d_st; a.n = (u32)n;
+  {
+    std::lock_guard<std::mutex> g(e->mu);  // the pending-list scratch is per engine
+    a.n_pending = (u32*)e->dev_pending.get((n + 1) * 4);
+    a.pending = a.n_pending + 1;
+  }
   launch_multi_get(a, stream ? (cudaStream_t)stream : e->st);
-  e->launches++;
+  e->launches += 2;
   return cudaPeekAtLastError() == cudaSuccess ? RSP_OK : RSP_IO_ERROR;
 }
 

@@ -10,6 +10,9 @@
 // A query is served by a group of G lanes (8 for MultiGet): one 32-byte sector of hash slots is one
 // coalesced group load, an entry is read as consecutive 16-byte units, the value leaves as
 // consecutive 16-byte stores.  All lanes of a group run the same control flow.
+#include <algorithm>
+#include <cstddef>
+
 #include "kernels.h"
 
 namespace rsp {
@@ -202,12 +205,8 @@ __device__ __forceinline__ void group_copy_out(u8* dst, const u8* src, u32 n, u3
   }
 }
 
-__global__ void __launch_bounds__(256) k_multi_get(GetArgs a) {
-  const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) / MG_LANES;
-  const u32 lane = threadIdx.x & (MG_LANES - 1);
-  const u32 gbase = (threadIdx.x & 31u) & ~(MG_LANES - 1u);
-  const u32 gmask = ((1u << MG_LANES) - 1u) << gbase;
-  if (q >= a.n) return;
+// generic path: any key length, any entry shape, memtable chains, merges, multiple runs
+__device__ __noinline__ void lookup_generic(const GetArgs& a, u32 q, u32 lane, u32 gmask, u32 gbase) {
   const u32 six = __ldg(a.shard_ix + q);
   const ShardDev* sd = a.shards + six;
   const u8* kp;
@@ -251,10 +250,161 @@ __global__ void __launch_bounds__(256) k_multi_get(GetArgs a) {
   }
 }
 
+__global__ void __launch_bounds__(256) k_multi_get(GetArgs a) {
+  const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) / MG_LANES;
+  const u32 lane = threadIdx.x & (MG_LANES - 1);
+  const u32 gbase = (threadIdx.x & 31u) & ~(MG_LANES - 1u);
+  const u32 gmask = ((1u << MG_LANES) - 1u) << gbase;
+  if (q >= a.n) return;
+  lookup_generic(a, q, lane, gmask, gbase);
+}
+
+// ---- the hot kernel: 16-byte keys, eight lanes per lookup, four dependent memory round trips --------
+//   1. shard id + query key (coalesced across the warp)
+//   2. the shard descriptor: lane L loads 16-byte unit L of ShardDev (memtable header, published
+//      sequence, run 0) — one 128-byte group load, fields exchanged by shuffle
+//   3. the hash bucket: one 32-byte sector of run 0's index, one u32 slot per lane
+//      (or, when the memtable is not empty, eight u64 memtable slots first)
+//   4. the entry: lane L loads unit L of the candidate entry (header | key | value units) in ONE
+//      group load; the key lane compares, the value lanes store their registers straight to the output
+// Anything else — tag false positive, overflowed bucket, Delete / Merge, version chains, several runs,
+// odd value sizes — drops to lookup_generic for that group.
+static_assert(offsetof(ShardDev, mt_count) == 40 && offsetof(ShardDev, merge_op) == 44, "ShardDev unit 2");
+static_assert(offsetof(ShardDev, pub_seq) == 56 && offsetof(ShardDev, n_runs) == 68, "ShardDev units 3/4");
+static_assert(offsetof(ShardDev, runs) == 80 && sizeof(RunDev) == 64, "ShardDev run 0 at unit 5");
+
+__device__ __forceinline__ u64 shfl64(u32 gmask, u32 lo, u32 hi, u32 src) {
+  return ((u64)__shfl_sync(gmask, hi, src) << 32) | __shfl_sync(gmask, lo, src);
+}
+
+__global__ void __launch_bounds__(256, 8) k_multi_get16(GetArgs a) {
+  const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const u32 lane = threadIdx.x & 7u;
+  const u32 gbase = (threadIdx.x & 31u) & ~7u;
+  const u32 gmask = 0xffu << gbase;
+  if (q >= a.n) return;
+  // (1)
+  const u32 six = __ldg(a.shard_ix + q);
+  const uint4 kq = __ldg(reinterpret_cast<const uint4*>(a.keys) + q);
+  // (2) unit `lane` of the shard descriptor, through L2 (mt_count / pub_seq change between ticks)
+  const uint4 du = __ldcg(reinterpret_cast<const uint4*>(a.shards + six) + lane);
+  const u32 mt_count = __shfl_sync(gmask, du.z, gbase + 2);
+  const u32 n_runs = __shfl_sync(gmask, du.y, gbase + 4);
+  const u64 k0 = ((u64)kq.y << 32) | kq.x, k1 = ((u64)kq.w << 32) | kq.z;
+  const u64 h = hash_final(hash_step(hash_step(hash_init(16), k0), k1));
+  bool slow = n_runs > 1;
+  bool hit = false;     // answered by the fast path
+  i32 st = 1;
+  u32 vlen = 0;
+  if (!slow && mt_count) {
+    // ---- memtable: eight u64 slots from the home position
+    const u64 slots_p = shfl64(gmask, du.z, du.w, gbase + 0);
+    const u64 heap_p = shfl64(gmask, du.x, du.y, gbase + 0);
+    const u32 mask = __shfl_sync(gmask, du.z, gbase + 1);
+    const u64 snap = shfl64(gmask, du.z, du.w, gbase + 3);
+    const u32 tag = hash_tag32(h);
+    const u64 sv = ldcg64(reinterpret_cast<const u64*>(slots_p) + (((u32)h + lane) & mask));
+    const u32 empty_m = (__ballot_sync(gmask, sv == 0) >> gbase) & 0xffu;
+    u32 match_m = (__ballot_sync(gmask, sv != 0 && (u32)(sv >> 32) == tag) >> gbase) & 0xffu;
+    if (empty_m) match_m &= (1u << (__ffs(empty_m) - 1)) - 1u;
+    if (match_m) {
+      if (match_m & (match_m - 1)) slow = true;
+      else {
+        const u32 c = __shfl_sync(gmask, (u32)sv, gbase + (__ffs(match_m) - 1));
+        // memtable entry: unit0 header, unit1 link, unit2 key, units 3.. value (7 units at 16 B / 64 B)
+        const uint4 eu = lane < 7 ? __ldcg(reinterpret_cast<const uint4*>(heap_p + (u64)(c - 1u) * 16u) + lane)
+                                  : make_uint4(0, 0, 0, 0);
+        const u32 e_type = __shfl_sync(gmask, eu.x, gbase + 0) & 0xffu;
+        const u64 e_seq = shfl64(gmask, eu.x, eu.y, gbase + 0) >> 8;
+        const u32 e_klen = __shfl_sync(gmask, eu.z, gbase + 0);
+        const u32 e_vlen = __shfl_sync(gmask, eu.w, gbase + 0);
+        const bool keq = eu.x == kq.x && eu.y == kq.y && eu.z == kq.z && eu.w == kq.w;
+        const bool key_ok = (__ballot_sync(gmask, lane == 2 && keq) != 0) && e_klen == 16;
+        if (!key_ok) {
+          slow = true;  // tag false positive: let the generic walk continue the probe
+        } else if (e_seq <= snap && e_type == kTypeValue && e_vlen <= 64 && e_vlen <= a.val_stride &&
+                   ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u) == 0) {
+          const u32 vu = (e_vlen + 15u) >> 4;
+          if (lane >= 3 && lane < 3 + vu) reinterpret_cast<uint4*>(a.vals + (u64)q * a.val_stride)[lane - 3] = eu;
+          hit = true; st = 0; vlen = e_vlen;
+        } else {
+          slow = true;  // Delete / Merge / newer than the snapshot / odd shape
+        }
+      }
+    } else if (!empty_m) {
+      slow = true;  // eight occupied slots without my tag: the probe continues
+    }
+  }
+  if (!slow && !hit && n_runs == 1) {
+    // ---- run 0 through its hash index
+    const u64 heap_p = shfl64(gmask, du.x, du.y, gbase + 5);
+    const u64 hs_p = shfl64(gmask, du.x, du.y, gbase + 6);
+    const u32 n_buckets = __shfl_sync(gmask, du.y, gbase + 7);
+    const u32 ord_bits = __shfl_sync(gmask, du.z, gbase + 7);
+    const u32 U = __shfl_sync(gmask, du.w, gbase + 7);
+    const u32 bucket = (u32)(((u64)(u32)h * n_buckets) >> 32);
+    const u32 sv = __ldg(reinterpret_cast<const u32*>(hs_p) + (u64)bucket * RUN_BUCKET_SLOTS + lane);
+    const u32 tag = (u32)(h >> 32) >> ord_bits;
+    const u32 empty_m = (__ballot_sync(gmask, sv == 0) >> gbase) & 0xffu;
+    const u32 match_m = (__ballot_sync(gmask, sv != 0 && (sv >> ord_bits) == tag) >> gbase) & 0xffu;
+    if (U == 0 || U > 8 || (match_m & (match_m - 1))) {
+      slow = true;
+    } else if (match_m) {
+      const u32 ord = (__shfl_sync(gmask, sv, gbase + (__ffs(match_m) - 1)) & ((1u << ord_bits) - 1u)) - 1u;
+      // run entry: unit0 header, unit1 key, units 2.. value
+      const uint4 eu = lane < U ? __ldg(reinterpret_cast<const uint4*>(heap_p + (u64)ord * U * 16u) + lane)
+                                : make_uint4(0, 0, 0, 0);
+      const u32 e_type = __shfl_sync(gmask, eu.x, gbase + 0) & 0xffu;
+      const u32 e_klen = __shfl_sync(gmask, eu.z, gbase + 0);
+      const u32 e_vlen = __shfl_sync(gmask, eu.w, gbase + 0);
+      const bool keq = eu.x == kq.x && eu.y == kq.y && eu.z == kq.z && eu.w == kq.w;
+      const bool key_ok = (__ballot_sync(gmask, lane == 1 && keq) != 0) && e_klen == 16;
+      if (key_ok && e_type == kTypeValue && e_vlen <= a.val_stride &&
+          ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u) == 0 && ((e_vlen + 15u) & ~15u) <= a.val_stride) {
+        const u32 vu = (e_vlen + 15u) >> 4;
+        if (lane >= 2 && lane < 2 + vu) reinterpret_cast<uint4*>(a.vals + (u64)q * a.val_stride)[lane - 2] = eu;
+        hit = true; st = 0; vlen = e_vlen;
+      } else {
+        slow = true;
+      }
+    } else if (!empty_m) {
+      slow = true;  // full bucket: the probe continues in the next one
+    }
+    // no match and an empty slot: NOT_FOUND (st = 1)
+  }
+  if (lane == 0) {
+    if (slow) {
+      // hand the query to k_multi_get_pending (generic path) through the pending list
+      a.pending[atomicAdd(a.n_pending, 1u)] = q;
+    } else {
+      a.st[q] = st;
+      a.vlen[q] = vlen;
+    }
+  }
+}
+
+// generic path over the queries the fast kernel deferred; a small fixed grid strides over the list
+__global__ void __launch_bounds__(256) k_multi_get_pending(GetArgs a) {
+  const u32 lane = threadIdx.x & (MG_LANES - 1);
+  const u32 gbase = (threadIdx.x & 31u) & ~(MG_LANES - 1u);
+  const u32 gmask = ((1u << MG_LANES) - 1u) << gbase;
+  const u32 n = __ldcg(a.n_pending);
+  const u32 groups = gridDim.x * (blockDim.x / MG_LANES);
+  for (u32 i = (blockIdx.x * blockDim.x + threadIdx.x) / MG_LANES; i < n; i += groups)
+    lookup_generic(a, __ldcg(a.pending + i), lane, gmask, gbase);
+}
+
 void launch_multi_get(const GetArgs& a, cudaStream_t s) {
   if (!a.n) return;
   const u32 per_block = 256 / MG_LANES;
-  k_multi_get<<<(a.n + per_block - 1) / per_block, 256, 0, s>>>(a);
+  const u32 grid = (a.n + per_block - 1) / per_block;
+  if (a.klen_fixed == 16 && (reinterpret_cast<uintptr_t>(a.keys) & 15u) == 0 && a.pending) {
+    cudaMemsetAsync(a.n_pending, 0, 4, s);
+    k_multi_get16<<<grid, 256, 0, s>>>(a);
+    k_multi_get_pending<<<std::min<u32>(grid, 148u * 4u), 256, 0, s>>>(a);
+  } else {
+    k_multi_get<<<grid, 256, 0, s>>>(a);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -74,6 +74,8 @@ struct GetArgs {
   u32* vlen;             // [n]
   i32* st;               // [n]
   u32 n;
+  u32* pending;          // [n] scratch: queries deferred by the fast kernel (may be nullptr)
+  u32* n_pending;        // [1]
 };
 void launch_multi_get(const GetArgs& a, cudaStream_t s);
 
