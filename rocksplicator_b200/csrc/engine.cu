@@ -209,6 +209,7 @@ struct rsp_engine {
   cudaStream_t st = nullptr;
   Arena arena;
   ShardDev* d_shards = nullptr;
+  ShardFast* d_fast = nullptr;
   std::vector<rsp_shard*> slots;
   std::unordered_map<std::string, rsp_shard*> by_name;
   PinBuf pin_in, pin_out;
@@ -230,6 +231,17 @@ static void upload_shard(rsp_engine* e, rsp_shard* s) {
     else memset(&s->h.runs[i], 0, sizeof(RunDev));
   }
   CUDA_OK(cudaMemcpyAsync(e->d_shards + s->index, &s->h, sizeof(ShardDev), cudaMemcpyHostToDevice, e->st));
+  ShardFast f;
+  memset(&f, 0, sizeof(f));
+  if (!s->runs.empty()) {
+    const Run& r0 = *s->runs[0];
+    f.run0_heap = (u64)r0.heap; f.run0_hslots = (u64)r0.hslots; f.n_buckets = r0.n_buckets;
+    f.meta = r0.ord_bits | (std::min<u32>(r0.uniform_units, 255u) << 8);
+  }
+  f.meta |= (u32)std::min<size_t>(s->runs.size(), 255) << 16;
+  f.mt_count = s->h.mt_count;
+  f.merge_op = s->h.merge_op;
+  CUDA_OK(cudaMemcpyAsync(e->d_fast + s->index, &f, sizeof(f), cudaMemcpyHostToDevice, e->st));
   // the host mirror is pageable: the copy above is staged before the call returns
 }
 
@@ -520,7 +532,7 @@ static void reserve_for(rsp_engine* e, const rsp_staged* sg) {
 
 static void tick_launch(rsp_engine* e, rsp_staged* sg, cudaStream_t st) {
   launch_decode(sg->tick, st);
-  launch_sequence(sg->tick, e->d_shards, st);
+  launch_sequence(sg->tick, e->d_shards, e->d_fast, st);
   launch_insert(sg->tick, e->d_shards, st);
   launch_publish(sg->tick, e->d_shards, st);
   e->launches += 4;
@@ -677,7 +689,7 @@ static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, c
   if (!klen_fixed) CUDA_OK(cudaMemcpyAsync(d + o_koff, koff, (n + 1) * 8, cudaMemcpyHostToDevice, e->st));
   if (key_bytes) CUDA_OK(cudaMemcpyAsync(d + o_keys, keys, key_bytes, cudaMemcpyHostToDevice, e->st));
   GetArgs a;
-  a.shards = e->d_shards; a.shard_ix = (const u32*)(d + o_six); a.keys = d + o_keys;
+  a.shards = e->d_shards; a.fast = e->d_fast; a.shard_ix = (const u32*)(d + o_six); a.keys = d + o_keys;
   a.koff = klen_fixed ? nullptr : (const u64*)(d + o_koff); a.klen_fixed = klen_fixed;
   a.vals = d + o_vals; a.val_stride = val_stride; a.vlen = (u32*)(d + o_vlen); a.st = (i32*)(d + o_st); a.n = (u32)n;
   a.n_pending = (u32*)e->dev_pending.get((n + 1) * 4);
@@ -834,6 +846,8 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   CUDA_OK(cudaEventCreate(&e->ev1));
   CUDA_OK(cudaMalloc(&e->d_shards, sizeof(ShardDev) * e->cfg.max_shards));
   CUDA_OK(cudaMemset(e->d_shards, 0, sizeof(ShardDev) * e->cfg.max_shards));
+  CUDA_OK(cudaMalloc(&e->d_fast, sizeof(ShardFast) * e->cfg.max_shards));
+  CUDA_OK(cudaMemset(e->d_fast, 0, sizeof(ShardFast) * e->cfg.max_shards));
   *out = e;
   return RSP_OK;
 }
@@ -847,6 +861,7 @@ void rsp_engine_destroy(rsp_engine* e) {
   e->arena.destroy();
   e->pin_in.destroy(); e->pin_out.destroy(); e->dev_tick.destroy(); e->dev_q.destroy(); e->dev_pending.destroy();
   cudaFree(e->d_shards);
+  cudaFree(e->d_fast);
   cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
   cudaStreamDestroy(e->st);
   delete e;
@@ -891,6 +906,7 @@ int rsp_shard_close(rsp_shard* s) {
   ShardDev z;
   memset(&z, 0, sizeof(z));
   CUDA_OK(cudaMemcpy(e->d_shards + s->index, &z, sizeof(z), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemset(e->d_fast + s->index, 0, sizeof(ShardFast)));
   e->arena.release(s->h.mt_heap, s->mt_heap_bytes);
   e->arena.release(s->h.mt_slots, s->mt_slot_bytes);
   e->arena.release(s->h.mt_ent_off, s->mt_ent_bytes);
@@ -1144,7 +1160,7 @@ int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, co
                          uint8_t* d_vals, uint32_t val_stride, uint32_t* d_vlen, int32_t* d_st, void* stream) {
   if (!e || !klen) return RSP_INVALID_ARGUMENT;
   GetArgs a;
-  a.shards = e->d_shards; a.shard_ix = d_shard_ix; a.keys = d_keys; a.koff = nullptr; a.klen_fixed = klen;
+  a.shards = e->d_shards; a.fast = e->d_fast; a.shard_ix = d_shard_ix; a.keys = d_keys; a.koff = nullptr; a.klen_fixed = klen;
   a.vals = d_vals; a.val_stride = val_stride; a.vlen = d_vlen; a.st = d_st; a.n = (u32)n;
   {
     std::lock_guard<std::mutex> g(e->mu);  // the pending-list scratch is per engine

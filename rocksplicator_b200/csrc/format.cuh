@@ -122,6 +122,17 @@ struct __align__(16) ShardDev {
   RunDev runs[RSP_MAX_RUNS];  // [0] = newest
 };
 
+// The 32 bytes of a shard the 16-byte-key MultiGet kernel needs before it touches data: small enough
+// (32 B x #shards) to stay L1/L2-resident.  Written by the host when runs change, mt_count by k_sequence.
+struct __align__(32) ShardFast {
+  u64 run0_heap;
+  u64 run0_hslots;
+  u32 n_buckets;
+  u32 meta;      // ord_bits | uniform_units << 8 | n_runs << 16
+  u32 mt_count;
+  u32 merge_op;
+};
+
 // ---- entry accessors ----------------------------------------------------------------------------
 struct EntryHdr {
   u64 seqtype;

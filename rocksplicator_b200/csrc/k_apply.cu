@@ -148,7 +148,7 @@ __device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(128) k_sequence(TickDev t, ShardDev* shards) {
+__global__ void __launch_bounds__(128) k_sequence(TickDev t, ShardDev* shards, ShardFast* fast) {
   const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 lane = threadIdx.x & 31;
   if (warp >= t.n_groups) return;
@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(128) k_sequence(TickDev t, ShardDev* shards) {
     sd->last_seq = seq;
     sd->mt_tail = tail;
     sd->mt_count = cnt;
+    fast[g.shard_ix].mt_count = cnt;
     sd->latch = latch;
     GroupRes gr;
     gr.last_seq = seq; gr.tail = tail; gr.count = cnt; gr.latch = latch; gr.pad = 0;
@@ -355,9 +356,9 @@ void launch_decode(const TickDev& t, cudaStream_t s) {
   const u32 warps_per_block = 8;
   k_decode<<<(t.n_batches + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(t);
 }
-void launch_sequence(const TickDev& t, ShardDev* shards, cudaStream_t s) {
+void launch_sequence(const TickDev& t, ShardDev* shards, ShardFast* fast, cudaStream_t s) {
   if (!t.n_groups) return;
-  k_sequence<<<(t.n_groups + 3) / 4, 128, 0, s>>>(t, shards);
+  k_sequence<<<(t.n_groups + 3) / 4, 128, 0, s>>>(t, shards, fast);
 }
 void launch_insert(const TickDev& t, ShardDev* shards, cudaStream_t s) {
   if (!t.n_ops_cap) return;

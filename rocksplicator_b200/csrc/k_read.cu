@@ -259,125 +259,137 @@ __global__ void __launch_bounds__(256) k_multi_get(GetArgs a) {
   lookup_generic(a, q, lane, gmask, gbase);
 }
 
-// ---- the hot kernel: 16-byte keys, eight lanes per lookup, four dependent memory round trips --------
-//   1. shard id + query key (coalesced across the warp)
-//   2. the shard descriptor: lane L loads 16-byte unit L of ShardDev (memtable header, published
-//      sequence, run 0) — one 128-byte group load, fields exchanged by shuffle
-//   3. the hash bucket: one 32-byte sector of run 0's index, one u32 slot per lane
-//      (or, when the memtable is not empty, eight u64 memtable slots first)
-//   4. the entry: lane L loads unit L of the candidate entry (header | key | value units) in ONE
-//      group load; the key lane compares, the value lanes store their registers straight to the output
-// Anything else — tag false positive, overflowed bucket, Delete / Merge, version chains, several runs,
-// odd value sizes — drops to lookup_generic for that group.
-static_assert(offsetof(ShardDev, mt_count) == 40 && offsetof(ShardDev, merge_op) == 44, "ShardDev unit 2");
-static_assert(offsetof(ShardDev, pub_seq) == 56 && offsetof(ShardDev, n_runs) == 68, "ShardDev units 3/4");
-static_assert(offsetof(ShardDev, runs) == 80 && sizeof(RunDev) == 64, "ShardDev run 0 at unit 5");
+// ---- the hot kernel: 16-byte keys, TWO lanes per lookup, three dependent memory round trips ----------
+//   1. shard id + query key (coalesced across the warp) and the 32-byte ShardFast descriptor
+//      (32 B x #shards: L1/L2-resident); both lanes load the same words (one broadcast transaction)
+//   2. the hash bucket: one 32-byte sector of run 0's index, four u32 slots (one 16-byte load) per lane
+//      (when the memtable is not empty: eight u64 memtable slots first, four per lane)
+//   3. the entry: both lanes read the header and key units (same sector, broadcast) and decide alike with
+//      no shuffles; lane L then moves value units L, L+2, .. straight from its registers to the output
+//      (2 lanes x 2 x 16 B = the 64-byte value)
+// The kernel is issue-bound before it is HBM-bound, so the lane count per lookup is what the instruction
+// budget allows: 8 lanes cost ~70 warp instructions per lookup, 2 lanes ~1/4 of that.
+// Anything else — tag false positive, probe longer than 4 buckets, Delete / Merge, version chains, several
+// runs, odd sizes — is appended to the pending list and served by the generic path (k_multi_get_pending).
+static_assert(offsetof(ShardDev, mt_slot_mask) == 24 && offsetof(ShardDev, pub_seq) == 56, "ShardDev units 0-3");
+static_assert(sizeof(ShardFast) == 32, "ShardFast");
 
-__device__ __forceinline__ u64 shfl64(u32 gmask, u32 lo, u32 hi, u32 src) {
-  return ((u64)__shfl_sync(gmask, hi, src) << 32) | __shfl_sync(gmask, lo, src);
+constexpr u32 FL = 2;  // lanes per lookup
+
+// Candidate entry at `ent`: header unit 0, key unit KU, value units KU+1.. (U units in all).
+// Returns 0 = served, 1 = not my key (tag false positive), 2 = needs the generic path.
+template <bool CG>
+__device__ __forceinline__ u32 fast_entry(const u8* ent, u32 U, u32 KU, const uint4& kq, u64 snap, u8* dst,
+                                          u64 val_stride, u32 lane, u32& vlen_out) {
+  const uint4* ep = reinterpret_cast<const uint4*>(ent);
+  const uint4 hd = CG ? __ldcg(ep) : __ldg(ep);
+  const uint4 ek = CG ? __ldcg(ep + KU) : __ldg(ep + KU);
+  const u32 fv = KU + 1;  // first value unit; lane L owns units fv+L, fv+L+2, fv+L+4
+  uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
+  if (fv + lane < U) v0 = CG ? __ldcg(ep + fv + lane) : __ldg(ep + fv + lane);
+  if (fv + lane + 2 < U) v1 = CG ? __ldcg(ep + fv + lane + 2) : __ldg(ep + fv + lane + 2);
+  if (fv + lane + 4 < U) v2 = CG ? __ldcg(ep + fv + lane + 4) : __ldg(ep + fv + lane + 4);
+  if (ek.x != kq.x || ek.y != kq.y || ek.z != kq.z || ek.w != kq.w || hd.z != 16) return 1;
+  const u64 seq = (((u64)hd.y << 32) | hd.x) >> 8;
+  const u32 vu = (hd.w + 15u) >> 4;
+  if ((hd.x & 0xffu) != kTypeValue || seq > snap || fv + vu > U || vu > 6 || (u64)vu * 16u > val_stride) return 2;
+  uint4* out = reinterpret_cast<uint4*>(dst);
+  if (lane < vu) out[lane] = v0;
+  if (lane + 2 < vu) out[lane + 2] = v1;
+  if (lane + 4 < vu) out[lane + 4] = v2;
+  vlen_out = hd.w;
+  return 0;
 }
 
-__global__ void __launch_bounds__(256, 8) k_multi_get16(GetArgs a) {
-  const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  const u32 lane = threadIdx.x & 7u;
-  const u32 gbase = (threadIdx.x & 31u) & ~7u;
-  const u32 gmask = 0xffu << gbase;
+__global__ void __launch_bounds__(256, 6) k_multi_get16(GetArgs a) {
+  const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) / FL;
+  const u32 lane = threadIdx.x & (FL - 1);
   if (q >= a.n) return;
   // (1)
   const u32 six = __ldg(a.shard_ix + q);
   const uint4 kq = __ldg(reinterpret_cast<const uint4*>(a.keys) + q);
-  // (2) unit `lane` of the shard descriptor, through L2 (mt_count / pub_seq change between ticks)
-  const uint4 du = __ldcg(reinterpret_cast<const uint4*>(a.shards + six) + lane);
-  const u32 mt_count = __shfl_sync(gmask, du.z, gbase + 2);
-  const u32 n_runs = __shfl_sync(gmask, du.y, gbase + 4);
+  const uint4 f0 = __ldg(reinterpret_cast<const uint4*>(a.fast + six));
+  const uint4 f1 = __ldg(reinterpret_cast<const uint4*>(a.fast + six) + 1);
+  const u32 n_buckets = f1.x, ord_bits = f1.y & 0xffu, U = (f1.y >> 8) & 0xffu, n_runs = (f1.y >> 16) & 0xffu;
   const u64 k0 = ((u64)kq.y << 32) | kq.x, k1 = ((u64)kq.w << 32) | kq.z;
   const u64 h = hash_final(hash_step(hash_step(hash_init(16), k0), k1));
-  bool slow = n_runs > 1;
-  bool hit = false;     // answered by the fast path
-  i32 st = 1;
+  u8* dst = a.vals + (u64)q * a.val_stride;
+  u32 state = 3;  // 0 served, 2 generic path, 3 undecided, 4 not found
   u32 vlen = 0;
-  if (!slow && mt_count) {
-    // ---- memtable: eight u64 slots from the home position
-    const u64 slots_p = shfl64(gmask, du.z, du.w, gbase + 0);
-    const u64 heap_p = shfl64(gmask, du.x, du.y, gbase + 0);
-    const u32 mask = __shfl_sync(gmask, du.z, gbase + 1);
-    const u64 snap = shfl64(gmask, du.z, du.w, gbase + 3);
+  if (n_runs > 1 || ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u)) state = 2;
+  if (state == 3 && f1.z /* mt_count */) {
+    // ---- memtable: eight u64 slots from the home position, four per lane; descriptor through L2
+    const uint4* dp = reinterpret_cast<const uint4*>(a.shards + six);
+    const uint4 d0 = __ldcg(dp), d1 = __ldcg(dp + 1), d3 = __ldcg(dp + 3);
+    const u8* heap = reinterpret_cast<const u8*>(((u64)d0.y << 32) | d0.x);
+    const u64* sp = reinterpret_cast<const u64*>(((u64)d0.w << 32) | d0.z);
+    const u32 mask = d1.z;
+    const u64 snap = ((u64)d3.w << 32) | d3.z;
     const u32 tag = hash_tag32(h);
-    const u64 sv = ldcg64(reinterpret_cast<const u64*>(slots_p) + (((u32)h + lane) & mask));
-    const u32 empty_m = (__ballot_sync(gmask, sv == 0) >> gbase) & 0xffu;
-    u32 match_m = (__ballot_sync(gmask, sv != 0 && (u32)(sv >> 32) == tag) >> gbase) & 0xffu;
-    if (empty_m) match_m &= (1u << (__ffs(empty_m) - 1)) - 1u;
-    if (match_m) {
-      if (match_m & (match_m - 1)) slow = true;
-      else {
-        const u32 c = __shfl_sync(gmask, (u32)sv, gbase + (__ffs(match_m) - 1));
-        // memtable entry: unit0 header, unit1 link, unit2 key, units 3.. value (7 units at 16 B / 64 B)
-        const uint4 eu = lane < 7 ? __ldcg(reinterpret_cast<const uint4*>(heap_p + (u64)(c - 1u) * 16u) + lane)
-                                  : make_uint4(0, 0, 0, 0);
-        const u32 e_type = __shfl_sync(gmask, eu.x, gbase + 0) & 0xffu;
-        const u64 e_seq = shfl64(gmask, eu.x, eu.y, gbase + 0) >> 8;
-        const u32 e_klen = __shfl_sync(gmask, eu.z, gbase + 0);
-        const u32 e_vlen = __shfl_sync(gmask, eu.w, gbase + 0);
-        const bool keq = eu.x == kq.x && eu.y == kq.y && eu.z == kq.z && eu.w == kq.w;
-        const bool key_ok = (__ballot_sync(gmask, lane == 2 && keq) != 0) && e_klen == 16;
-        if (!key_ok) {
-          slow = true;  // tag false positive: let the generic walk continue the probe
-        } else if (e_seq <= snap && e_type == kTypeValue && e_vlen <= 64 && e_vlen <= a.val_stride &&
-                   ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u) == 0) {
-          const u32 vu = (e_vlen + 15u) >> 4;
-          if (lane >= 3 && lane < 3 + vu) reinterpret_cast<uint4*>(a.vals + (u64)q * a.val_stride)[lane - 3] = eu;
-          hit = true; st = 0; vlen = e_vlen;
-        } else {
-          slow = true;  // Delete / Merge / newer than the snapshot / odd shape
-        }
-      }
-    } else if (!empty_m) {
-      slow = true;  // eight occupied slots without my tag: the probe continues
+    u32 cand = 0, info = 0;  // info: matches | (position of my first empty + 1) << 8
+#pragma unroll
+    for (u32 i = 0; i < 4; i++) {
+      const u64 sv = ldcg64(sp + (((u32)h + 4u * lane + i) & mask));
+      if (sv == 0) { if (!(info >> 8)) info |= (4u * lane + i + 1u) << 8; }
+      else if ((u32)(sv >> 32) == tag && !(info >> 8)) { if (!cand) cand = (u32)sv; info++; }
+    }
+    const u32 o_cand = __shfl_xor_sync(0xffffffffu, cand, 1), o_info = __shfl_xor_sync(0xffffffffu, info, 1);
+    // lane 1's slots come after lane 0's in probe order: they count only if lane 0 saw no empty slot
+    const u32 lo_info = lane ? o_info : info, hi_info = lane ? info : o_info;
+    const u32 lo_cand = lane ? o_cand : cand, hi_cand = lane ? cand : o_cand;
+    const bool lo_empty = (lo_info >> 8) != 0;
+    const u32 n_match = (lo_info & 0xffu) + (lo_empty ? 0u : (hi_info & 0xffu));
+    const bool any_empty = lo_empty || (hi_info >> 8) != 0;
+    if (n_match == 1) {
+      const u32 c = (lo_info & 0xffu) ? lo_cand : hi_cand;
+      // memtable entry: unit0 header, unit1 link, unit2 key, units 3.. value
+      const u32 r = fast_entry<true>(heap + (u64)(c - 1u) * 16u, 7, 2, kq, snap, dst, a.val_stride, lane, vlen);
+      state = r == 0 ? 0 : 2;
+    } else if (n_match > 1 || !any_empty) {
+      state = 2;
     }
   }
-  if (!slow && !hit && n_runs == 1) {
-    // ---- run 0 through its hash index
-    const u64 heap_p = shfl64(gmask, du.x, du.y, gbase + 5);
-    const u64 hs_p = shfl64(gmask, du.x, du.y, gbase + 6);
-    const u32 n_buckets = __shfl_sync(gmask, du.y, gbase + 7);
-    const u32 ord_bits = __shfl_sync(gmask, du.z, gbase + 7);
-    const u32 U = __shfl_sync(gmask, du.w, gbase + 7);
-    const u32 bucket = (u32)(((u64)(u32)h * n_buckets) >> 32);
-    const u32 sv = __ldg(reinterpret_cast<const u32*>(hs_p) + (u64)bucket * RUN_BUCKET_SLOTS + lane);
-    const u32 tag = (u32)(h >> 32) >> ord_bits;
-    const u32 empty_m = (__ballot_sync(gmask, sv == 0) >> gbase) & 0xffu;
-    const u32 match_m = (__ballot_sync(gmask, sv != 0 && (sv >> ord_bits) == tag) >> gbase) & 0xffu;
-    if (U == 0 || U > 8 || (match_m & (match_m - 1))) {
-      slow = true;
-    } else if (match_m) {
-      const u32 ord = (__shfl_sync(gmask, sv, gbase + (__ffs(match_m) - 1)) & ((1u << ord_bits) - 1u)) - 1u;
-      // run entry: unit0 header, unit1 key, units 2.. value
-      const uint4 eu = lane < U ? __ldg(reinterpret_cast<const uint4*>(heap_p + (u64)ord * U * 16u) + lane)
-                                : make_uint4(0, 0, 0, 0);
-      const u32 e_type = __shfl_sync(gmask, eu.x, gbase + 0) & 0xffu;
-      const u32 e_klen = __shfl_sync(gmask, eu.z, gbase + 0);
-      const u32 e_vlen = __shfl_sync(gmask, eu.w, gbase + 0);
-      const bool keq = eu.x == kq.x && eu.y == kq.y && eu.z == kq.z && eu.w == kq.w;
-      const bool key_ok = (__ballot_sync(gmask, lane == 1 && keq) != 0) && e_klen == 16;
-      if (key_ok && e_type == kTypeValue && e_vlen <= a.val_stride &&
-          ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u) == 0 && ((e_vlen + 15u) & ~15u) <= a.val_stride) {
-        const u32 vu = (e_vlen + 15u) >> 4;
-        if (lane >= 2 && lane < 2 + vu) reinterpret_cast<uint4*>(a.vals + (u64)q * a.val_stride)[lane - 2] = eu;
-        hit = true; st = 0; vlen = e_vlen;
-      } else {
-        slow = true;
+  if (state == 3) {
+    if (n_runs == 0) state = 4;
+    else if (U == 0 || U > 8) state = 2;
+    else {
+      // ---- run 0 through its hash index: one bucket = one 32-byte sector, four slots per lane
+      const u8* heap = reinterpret_cast<const u8*>(((u64)f0.y << 32) | f0.x);
+      const uint4* hs = reinterpret_cast<const uint4*>(((u64)f0.w << 32) | f0.z);
+      u32 bucket = (u32)(((u64)(u32)h * n_buckets) >> 32);
+      const u32 tag = (u32)(h >> 32) >> ord_bits;
+      state = 2;  // a probe longer than 4 buckets goes to the generic path
+#pragma unroll 1
+      for (u32 probe = 0; probe < 4; probe++) {
+        const uint4 sv = __ldg(hs + (u64)bucket * 2u + lane);
+        u32 cand = 0, info = 0;  // info: matches | any empty << 8
+        if (sv.x == 0) info = 256; else if ((sv.x >> ord_bits) == tag) { cand = sv.x; info++; }
+        if (sv.y == 0) info |= 256; else if ((sv.y >> ord_bits) == tag) { cand = sv.y; info++; }
+        if (sv.z == 0) info |= 256; else if ((sv.z >> ord_bits) == tag) { cand = sv.z; info++; }
+        if (sv.w == 0) info |= 256; else if ((sv.w >> ord_bits) == tag) { cand = sv.w; info++; }
+        info += __shfl_xor_sync(0xffffffffu, info, 1);
+        cand |= __shfl_xor_sync(0xffffffffu, cand, 1);
+        const u32 n_match = info & 0xffu;
+        if (n_match == 1) {
+          const u32 ord = (cand & ((1u << ord_bits) - 1u)) - 1u;
+          // run entry: unit0 header, unit1 key, units 2.. value
+          const u32 r = fast_entry<false>(heap + (u64)ord * U * 16u, U, 1, kq, ~0ull, dst, a.val_stride, lane, vlen);
+          if (r == 0) { state = 0; break; }
+          if (r == 2) break;
+          // tag false positive: treat as no match in this bucket
+        } else if (n_match > 1) {
+          break;
+        }
+        if (info >> 8) { state = 4; break; }  // an empty slot ends the probe: NOT_FOUND
+        bucket = bucket + 1 == n_buckets ? 0 : bucket + 1;
       }
-    } else if (!empty_m) {
-      slow = true;  // full bucket: the probe continues in the next one
     }
-    // no match and an empty slot: NOT_FOUND (st = 1)
   }
   if (lane == 0) {
-    if (slow) {
-      // hand the query to k_multi_get_pending (generic path) through the pending list
+    if (state == 2) {
       a.pending[atomicAdd(a.n_pending, 1u)] = q;
     } else {
-      a.st[q] = st;
+      a.st[q] = state == 0 ? 0 : 1;
       a.vlen[q] = vlen;
     }
   }
@@ -398,9 +410,9 @@ void launch_multi_get(const GetArgs& a, cudaStream_t s) {
   if (!a.n) return;
   const u32 per_block = 256 / MG_LANES;
   const u32 grid = (a.n + per_block - 1) / per_block;
-  if (a.klen_fixed == 16 && (reinterpret_cast<uintptr_t>(a.keys) & 15u) == 0 && a.pending) {
+  if (a.klen_fixed == 16 && (reinterpret_cast<uintptr_t>(a.keys) & 15u) == 0 && a.pending && a.fast) {
     cudaMemsetAsync(a.n_pending, 0, 4, s);
-    k_multi_get16<<<grid, 256, 0, s>>>(a);
+    k_multi_get16<<<(a.n + 256 / FL - 1) / (256 / FL), 256, 0, s>>>(a);
     k_multi_get_pending<<<std::min<u32>(grid, 148u * 4u), 256, 0, s>>>(a);
   } else {
     k_multi_get<<<grid, 256, 0, s>>>(a);

@@ -58,13 +58,14 @@ struct TickDev {
 };
 
 void launch_decode(const TickDev& t, cudaStream_t s);
-void launch_sequence(const TickDev& t, ShardDev* shards, cudaStream_t s);
+void launch_sequence(const TickDev& t, ShardDev* shards, ShardFast* fast, cudaStream_t s);
 void launch_insert(const TickDev& t, ShardDev* shards, cudaStream_t s);
 void launch_publish(const TickDev& t, ShardDev* shards, cudaStream_t s);
 
 // ---- reads ---------------------------------------------------------------------------------------
 struct GetArgs {
   const ShardDev* shards;
+  const ShardFast* fast;   // compact per-shard descriptors for the 16-byte-key kernel (may be nullptr)
   const u32* shard_ix;   // [n]
   const u8* keys;        // key bytes
   const u64* koff;       // [n+1] or nullptr when klen_fixed > 0
