@@ -192,6 +192,9 @@ float rsp_last_kernel_ms(const rsp_engine* e, const char* what);
 /* number of engine kernels launched so far (bench.py's gpu_launches) */
 uint64_t rsp_kernel_launches(const rsp_engine* e);
 
+/* diagnostics: lookups of the last MultiGet launch that left the fast kernel for the generic path */
+uint32_t rsp_debug_last_pending(rsp_engine* e, uint32_t* first, uint32_t cap);
+
 const char* rsp_version(void);
 
 #ifdef __cplusplus

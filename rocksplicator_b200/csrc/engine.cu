@@ -353,8 +353,9 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
     r->arena = &a;
     r->n_ent = ents; r->heap_units = units; r->uniform_units = uni;
     r->n_blocks = (ents + RSP_BLOCK_ENTRIES - 1) / RSP_BLOCK_ENTRIES;
-    // ~0.7 load: 8-slot buckets, at least one
-    r->n_buckets = std::max<u32>(1, (u32)(((u64)keys * 10 + 55) / 56));
+    // 8-slot buckets at load <= 0.5: a key overflows its home bucket with p ~ 2 % (Poisson(4) > 8), and
+    // an overflow costs the 16-lookup warp of k_multi_get16 one more dependent sector read
+    r->n_buckets = std::max<u32>(1, (u32)(((u64)keys + 3) / 4));
     r->ord_bits = 1;
     while ((1ull << r->ord_bits) <= ents) r->ord_bits++;
     r->heap = (u8*)a.alloc((size_t)units * 16);
@@ -1246,5 +1247,17 @@ float rsp_last_kernel_ms(const rsp_engine* e, const char* what) {
   return it == m->last_ms.end() ? -1.f : it->second;
 }
 uint64_t rsp_kernel_launches(const rsp_engine* e) { return e->launches.load(); }
+
+// diagnostics: how many lookups of the last MultiGet launch took the generic path (synchronises)
+uint32_t rsp_debug_last_pending(rsp_engine* e, uint32_t* first, uint32_t cap) {
+  std::lock_guard<std::mutex> g(e->mu);
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  if (!e->dev_pending.p) return 0;
+  u32 n = 0;
+  cudaMemcpy(&n, e->dev_pending.p, 4, cudaMemcpyDeviceToHost);
+  if (first && cap) cudaMemcpy(first, (u32*)e->dev_pending.p + 1, 4 * std::min(n, cap), cudaMemcpyDeviceToHost);
+  return n;
+}
 
 }  // extern "C"

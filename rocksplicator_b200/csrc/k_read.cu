@@ -301,9 +301,11 @@ __device__ __forceinline__ u32 fast_entry(const u8* ent, u32 U, u32 KU, const ui
   return 0;
 }
 
-__global__ void __launch_bounds__(256, 6) k_multi_get16(GetArgs a) {
+__global__ void __launch_bounds__(256, 5) k_multi_get16(GetArgs a) {
   const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) / FL;
   const u32 lane = threadIdx.x & (FL - 1);
+  const u32 pbase = (threadIdx.x & 31u) & ~1u;
+  const u32 pmask = 3u << pbase;  // the two lanes of this lookup always branch together
   if (q >= a.n) return;
   // (1)
   const u32 six = __ldg(a.shard_ix + q);
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(256, 6) k_multi_get16(GetArgs a) {
       if (sv == 0) { if (!(info >> 8)) info |= (4u * lane + i + 1u) << 8; }
       else if ((u32)(sv >> 32) == tag && !(info >> 8)) { if (!cand) cand = (u32)sv; info++; }
     }
-    const u32 o_cand = __shfl_xor_sync(0xffffffffu, cand, 1), o_info = __shfl_xor_sync(0xffffffffu, info, 1);
+    const u32 o_cand = __shfl_xor_sync(pmask, cand, 1), o_info = __shfl_xor_sync(pmask, info, 1);
     // lane 1's slots come after lane 0's in probe order: they count only if lane 0 saw no empty slot
     const u32 lo_info = lane ? o_info : info, hi_info = lane ? info : o_info;
     const u32 lo_cand = lane ? o_cand : cand, hi_cand = lane ? cand : o_cand;
@@ -358,30 +360,37 @@ __global__ void __launch_bounds__(256, 6) k_multi_get16(GetArgs a) {
       const uint4* hs = reinterpret_cast<const uint4*>(((u64)f0.w << 32) | f0.z);
       u32 bucket = (u32)(((u64)(u32)h * n_buckets) >> 32);
       const u32 tag = (u32)(h >> 32) >> ord_bits;
-      state = 2;  // a probe longer than 4 buckets goes to the generic path
+      // Walk the tag matches in probe order; a false positive (18-bit tags at 16 K entries: ~1 per 60 K
+      // lookups) just moves on to the next candidate, a full bucket to the next bucket.
+      u32 m8 = 0, e8 = 1, probe = 0;  // e8 != 0 before the first load only so that the loop loads first
+      uint4 sv = make_uint4(0, 0, 0, 0);
+      state = 2;
 #pragma unroll 1
-      for (u32 probe = 0; probe < 4; probe++) {
-        const uint4 sv = __ldg(hs + (u64)bucket * 2u + lane);
-        u32 cand = 0, info = 0;  // info: matches | any empty << 8
-        if (sv.x == 0) info = 256; else if ((sv.x >> ord_bits) == tag) { cand = sv.x; info++; }
-        if (sv.y == 0) info |= 256; else if ((sv.y >> ord_bits) == tag) { cand = sv.y; info++; }
-        if (sv.z == 0) info |= 256; else if ((sv.z >> ord_bits) == tag) { cand = sv.z; info++; }
-        if (sv.w == 0) info |= 256; else if ((sv.w >> ord_bits) == tag) { cand = sv.w; info++; }
-        info += __shfl_xor_sync(0xffffffffu, info, 1);
-        cand |= __shfl_xor_sync(0xffffffffu, cand, 1);
-        const u32 n_match = info & 0xffu;
-        if (n_match == 1) {
-          const u32 ord = (cand & ((1u << ord_bits) - 1u)) - 1u;
-          // run entry: unit0 header, unit1 key, units 2.. value
-          const u32 r = fast_entry<false>(heap + (u64)ord * U * 16u, U, 1, kq, ~0ull, dst, a.val_stride, lane, vlen);
-          if (r == 0) { state = 0; break; }
-          if (r == 2) break;
-          // tag false positive: treat as no match in this bucket
-        } else if (n_match > 1) {
-          break;
+      for (;;) {
+        if (!m8) {
+          if (probe && e8) { state = 4; break; }  // an empty slot ends the probe: NOT_FOUND
+          if (probe == n_buckets) { state = 4; break; }  // (a table without an empty slot)
+          if (probe) bucket = bucket + 1 == n_buckets ? 0 : bucket + 1;
+          probe++;
+          sv = __ldg(hs + (u64)bucket * 2u + lane);
+          const u32 m = ((sv.x && (sv.x >> ord_bits) == tag) ? 1u : 0u) | ((sv.y && (sv.y >> ord_bits) == tag) ? 2u : 0u) |
+                        ((sv.z && (sv.z >> ord_bits) == tag) ? 4u : 0u) | ((sv.w && (sv.w >> ord_bits) == tag) ? 8u : 0u);
+          const u32 e = (sv.x == 0 || sv.y == 0 || sv.z == 0 || sv.w == 0) ? 1u : 0u;
+          const u32 mine = m | (e << 4);
+          const u32 other = __shfl_xor_sync(pmask, mine, 1);
+          m8 = lane ? ((other & 15u) | ((mine & 15u) << 4)) : ((mine & 15u) | ((other & 15u) << 4));
+          e8 = (mine | other) >> 4;
+          if (!m8) continue;
         }
-        if (info >> 8) { state = 4; break; }  // an empty slot ends the probe: NOT_FOUND
-        bucket = bucket + 1 == n_buckets ? 0 : bucket + 1;
+        const u32 p = __ffs(m8) - 1;
+        m8 &= m8 - 1;
+        const u32 pick = (p & 2u) ? ((p & 1u) ? sv.w : sv.z) : ((p & 1u) ? sv.y : sv.x);
+        const u32 val = __shfl_sync(pmask, pick, pbase + (p >> 2));
+        // run entry: unit0 header, unit1 key, units 2.. value
+        const u32 r = fast_entry<false>(heap + (u64)((val & ((1u << ord_bits) - 1u)) - 1u) * U * 16u, U, 1, kq, ~0ull, dst,
+                                        a.val_stride, lane, vlen);
+        if (r == 0) { state = 0; break; }
+        if (r == 2) break;
       }
     }
   }
@@ -413,7 +422,7 @@ void launch_multi_get(const GetArgs& a, cudaStream_t s) {
   if (a.klen_fixed == 16 && (reinterpret_cast<uintptr_t>(a.keys) & 15u) == 0 && a.pending && a.fast) {
     cudaMemsetAsync(a.n_pending, 0, 4, s);
     k_multi_get16<<<(a.n + 256 / FL - 1) / (256 / FL), 256, 0, s>>>(a);
-    k_multi_get_pending<<<std::min<u32>(grid, 148u * 4u), 256, 0, s>>>(a);
+    k_multi_get_pending<<<std::min<u32>(grid, 148u), 256, 0, s>>>(a);
   } else {
     k_multi_get<<<grid, 256, 0, s>>>(a);
   }

@@ -88,6 +88,7 @@ EXPORTS = {
     "rsp_apply_staged_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rsp_last_kernel_ms": (C.c_float, [C.c_void_p, C.c_char_p]),
     "rsp_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "rsp_debug_last_pending": (C.c_uint32, [C.c_void_p, C.c_void_p, C.c_uint32]),
 }
 
 _lib = None
