@@ -15,7 +15,7 @@ OUT = os.path.join(HERE, "librsp_b200.so")
 SOURCES = ["k_apply.cu", "k_read.cu", "k_compact.cu", "engine.cu"]
 HEADERS = ["format.cuh", "kernels.h", os.path.join("..", "..", "include", "rsp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + os.environ.get("RSP_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

@@ -275,6 +275,12 @@ static_assert(offsetof(ShardDev, mt_slot_mask) == 24 && offsetof(ShardDev, pub_s
 static_assert(sizeof(ShardFast) == 32, "ShardFast");
 
 constexpr u32 FL = 2;  // lanes per lookup
+#ifndef RSP_MG_TPB
+#define RSP_MG_TPB 128
+#endif
+#ifndef RSP_MG_MINB
+#define RSP_MG_MINB 10
+#endif
 
 // Candidate entry at `ent`: header unit 0, key unit KU, value units KU+1.. (U units in all).
 // Returns 0 = served, 1 = not my key (tag false positive), 2 = needs the generic path.
@@ -301,7 +307,7 @@ __device__ __forceinline__ u32 fast_entry(const u8* ent, u32 U, u32 KU, const ui
   return 0;
 }
 
-__global__ void __launch_bounds__(256, 5) k_multi_get16(GetArgs a) {
+__global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs a) {
   const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) / FL;
   const u32 lane = threadIdx.x & (FL - 1);
   const u32 pbase = (threadIdx.x & 31u) & ~1u;
@@ -421,7 +427,7 @@ void launch_multi_get(const GetArgs& a, cudaStream_t s) {
   const u32 grid = (a.n + per_block - 1) / per_block;
   if (a.klen_fixed == 16 && (reinterpret_cast<uintptr_t>(a.keys) & 15u) == 0 && a.pending && a.fast) {
     cudaMemsetAsync(a.n_pending, 0, 4, s);
-    k_multi_get16<<<(a.n + 256 / FL - 1) / (256 / FL), 256, 0, s>>>(a);
+    k_multi_get16<<<(a.n + RSP_MG_TPB / FL - 1) / (RSP_MG_TPB / FL), RSP_MG_TPB, 0, s>>>(a);
     k_multi_get_pending<<<std::min<u32>(grid, 148u), 256, 0, s>>>(a);
   } else {
     k_multi_get<<<grid, 256, 0, s>>>(a);
