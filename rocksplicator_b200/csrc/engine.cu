@@ -214,6 +214,8 @@ struct rsp_engine {
   std::unordered_map<std::string, rsp_shard*> by_name;
   PinBuf pin_in, pin_out;
   DevBuf dev_tick, dev_q, dev_pending;
+  u32 mg_parity = 0;
+  size_t pending_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::map<std::string, float> last_ms;
   std::atomic<u64> launches{0};
@@ -675,6 +677,20 @@ static int host_fold_get(rsp_engine* e, rsp_shard* s, const uint8_t* key, size_t
 // ------------------------------------------------------------------------------------------------
 // reads
 // ------------------------------------------------------------------------------------------------
+// pending-list scratch of the 16-byte-key kernel: [2 counters][n indices]; the counters alternate per launch
+static void set_pending(rsp_engine* e, GetArgs& a, size_t n) {
+  if ((n + 2) * 4 > e->pending_cap) {
+    e->pending_cap = std::max<size_t>((n + 2) * 4, e->pending_cap * 2);
+    u32* p = (u32*)e->dev_pending.get(e->pending_cap);
+    CUDA_OK(cudaMemset(p, 0, 8));
+    e->mg_parity = 0;
+  }
+  a.n_pending = (u32*)e->dev_pending.p;
+  a.pending = a.n_pending + 2;
+  a.parity = e->mg_parity;
+  e->mg_parity ^= 1u;
+}
+
 static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, const uint64_t* koff,
                             uint32_t klen_fixed, uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
   if (n == 0) return RSP_OK;
@@ -693,8 +709,7 @@ static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, c
   a.shards = e->d_shards; a.fast = e->d_fast; a.shard_ix = (const u32*)(d + o_six); a.keys = d + o_keys;
   a.koff = klen_fixed ? nullptr : (const u64*)(d + o_koff); a.klen_fixed = klen_fixed;
   a.vals = d + o_vals; a.val_stride = val_stride; a.vlen = (u32*)(d + o_vlen); a.st = (i32*)(d + o_st); a.n = (u32)n;
-  a.n_pending = (u32*)e->dev_pending.get((n + 1) * 4);
-  a.pending = a.n_pending + 1;
+  set_pending(e, a, n);
   CUDA_OK(cudaEventRecord(e->ev0, e->st));
   launch_multi_get(a, e->st);
   e->launches++;
@@ -1165,8 +1180,7 @@ int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, co
   a.vals = d_vals; a.val_stride = val_stride; a.vlen = d_vlen; a.st = d_st; a.n = (u32)n;
   {
     std::lock_guard<std::mutex> g(e->mu);  // the pending-list scratch is per engine
-    a.n_pending = (u32*)e->dev_pending.get((n + 1) * 4);
-    a.pending = a.n_pending + 1;
+    set_pending(e, a, n);
   }
   launch_multi_get(a, stream ? (cudaStream_t)stream : e->st);
   e->launches += 2;
@@ -1255,8 +1269,8 @@ uint32_t rsp_debug_last_pending(rsp_engine* e, uint32_t* first, uint32_t cap) {
   cudaDeviceSynchronize();
   if (!e->dev_pending.p) return 0;
   u32 n = 0;
-  cudaMemcpy(&n, e->dev_pending.p, 4, cudaMemcpyDeviceToHost);
-  if (first && cap) cudaMemcpy(first, (u32*)e->dev_pending.p + 1, 4 * std::min(n, cap), cudaMemcpyDeviceToHost);
+  cudaMemcpy(&n, (u32*)e->dev_pending.p + (e->mg_parity ^ 1u), 4, cudaMemcpyDeviceToHost);
+  if (first && cap) cudaMemcpy(first, (u32*)e->dev_pending.p + 2, 4 * std::min(n, cap), cudaMemcpyDeviceToHost);
   return n;
 }
 

@@ -275,6 +275,34 @@ static_assert(offsetof(ShardDev, mt_slot_mask) == 24 && offsetof(ShardDev, pub_s
 static_assert(sizeof(ShardFast) == 32, "ShardFast");
 
 constexpr u32 FL = 2;  // lanes per lookup
+
+// L2 residency control (createpolicy + ld/st .L2::cache_hint): the hash-index sectors are the only
+// data with reuse across lookups (80 MB at 10 M keys vs a 126 MB L2); entries, query keys and results
+// stream through once.  RSP_MG_HINTS: 0 = none, 1 = index evict_last (+1 %), 2 = also streams evict_first
+// (measured 20 % SLOWER on B200: kept only as an experiment switch).  RSP_MG_NOALLOC: entry units bypass L1.
+#ifndef RSP_MG_HINTS
+#define RSP_MG_HINTS 1
+#endif
+__device__ __forceinline__ u64 pol_evict_last() {
+  u64 p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ u64 pol_evict_first() {
+  u64 p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ldg_pol(const uint4* p, u64 pol) {
+  uint4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_pol(uint4* p, const uint4& v, u64 pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
 #ifndef RSP_MG_TPB
 #define RSP_MG_TPB 128
 #endif
@@ -284,25 +312,53 @@ constexpr u32 FL = 2;  // lanes per lookup
 
 // Candidate entry at `ent`: header unit 0, key unit KU, value units KU+1.. (U units in all).
 // Returns 0 = served, 1 = not my key (tag false positive), 2 = needs the generic path.
+#ifndef RSP_MG_NOALLOC
+#define RSP_MG_NOALLOC 0  // measured 5 % slower with L1::no_allocate on the entry units
+#endif
+#ifndef RSP_MG_MEMSET
+#define RSP_MG_MEMSET 1
+#endif
+__device__ __forceinline__ uint4 ldg_noalloc(const uint4* p) {
+  uint4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+template <bool CG>
+__device__ __forceinline__ uint4 ld_entry_unit(const uint4* p, u64 pol) {
+  if (CG) return __ldcg(p);
+#if RSP_MG_HINTS >= 2
+  return ldg_pol(p, pol);
+#elif RSP_MG_NOALLOC
+  return ldg_noalloc(p);
+#else
+  return __ldg(p);
+#endif
+}
 template <bool CG>
 __device__ __forceinline__ u32 fast_entry(const u8* ent, u32 U, u32 KU, const uint4& kq, u64 snap, u8* dst,
-                                          u64 val_stride, u32 lane, u32& vlen_out) {
+                                          u64 val_stride, u32 lane, u32& vlen_out, u64 pol) {
   const uint4* ep = reinterpret_cast<const uint4*>(ent);
-  const uint4 hd = CG ? __ldcg(ep) : __ldg(ep);
-  const uint4 ek = CG ? __ldcg(ep + KU) : __ldg(ep + KU);
+  const uint4 hd = ld_entry_unit<CG>(ep, pol);
+  const uint4 ek = ld_entry_unit<CG>(ep + KU, pol);
   const u32 fv = KU + 1;  // first value unit; lane L owns units fv+L, fv+L+2, fv+L+4
   uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
-  if (fv + lane < U) v0 = CG ? __ldcg(ep + fv + lane) : __ldg(ep + fv + lane);
-  if (fv + lane + 2 < U) v1 = CG ? __ldcg(ep + fv + lane + 2) : __ldg(ep + fv + lane + 2);
-  if (fv + lane + 4 < U) v2 = CG ? __ldcg(ep + fv + lane + 4) : __ldg(ep + fv + lane + 4);
+  if (fv + lane < U) v0 = ld_entry_unit<CG>(ep + fv + lane, pol);
+  if (fv + lane + 2 < U) v1 = ld_entry_unit<CG>(ep + fv + lane + 2, pol);
+  if (fv + lane + 4 < U) v2 = ld_entry_unit<CG>(ep + fv + lane + 4, pol);
   if (ek.x != kq.x || ek.y != kq.y || ek.z != kq.z || ek.w != kq.w || hd.z != 16) return 1;
   const u64 seq = (((u64)hd.y << 32) | hd.x) >> 8;
   const u32 vu = (hd.w + 15u) >> 4;
   if ((hd.x & 0xffu) != kTypeValue || seq > snap || fv + vu > U || vu > 6 || (u64)vu * 16u > val_stride) return 2;
   uint4* out = reinterpret_cast<uint4*>(dst);
+#if RSP_MG_HINTS >= 2
+  if (lane < vu) stg_pol(out + lane, v0, pol);
+  if (lane + 2 < vu) stg_pol(out + lane + 2, v1, pol);
+  if (lane + 4 < vu) stg_pol(out + lane + 4, v2, pol);
+#else
   if (lane < vu) out[lane] = v0;
   if (lane + 2 < vu) out[lane + 2] = v1;
   if (lane + 4 < vu) out[lane + 4] = v2;
+#endif
   vlen_out = hd.w;
   return 0;
 }
@@ -314,8 +370,13 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
   const u32 pmask = 3u << pbase;  // the two lanes of this lookup always branch together
   if (q >= a.n) return;
   // (1)
+  const u64 pol_stream = pol_evict_first();
   const u32 six = __ldg(a.shard_ix + q);
+#if RSP_MG_HINTS >= 2
+  const uint4 kq = ldg_pol(reinterpret_cast<const uint4*>(a.keys) + q, pol_stream);
+#else
   const uint4 kq = __ldg(reinterpret_cast<const uint4*>(a.keys) + q);
+#endif
   const uint4 f0 = __ldg(reinterpret_cast<const uint4*>(a.fast + six));
   const uint4 f1 = __ldg(reinterpret_cast<const uint4*>(a.fast + six) + 1);
   const u32 n_buckets = f1.x, ord_bits = f1.y & 0xffu, U = (f1.y >> 8) & 0xffu, n_runs = (f1.y >> 16) & 0xffu;
@@ -351,7 +412,7 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
     if (n_match == 1) {
       const u32 c = (lo_info & 0xffu) ? lo_cand : hi_cand;
       // memtable entry: unit0 header, unit1 link, unit2 key, units 3.. value
-      const u32 r = fast_entry<true>(heap + (u64)(c - 1u) * 16u, 7, 2, kq, snap, dst, a.val_stride, lane, vlen);
+      const u32 r = fast_entry<true>(heap + (u64)(c - 1u) * 16u, 7, 2, kq, snap, dst, a.val_stride, lane, vlen, pol_stream);
       state = r == 0 ? 0 : 2;
     } else if (n_match > 1 || !any_empty) {
       state = 2;
@@ -378,7 +439,11 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
           if (probe == n_buckets) { state = 4; break; }  // (a table without an empty slot)
           if (probe) bucket = bucket + 1 == n_buckets ? 0 : bucket + 1;
           probe++;
+#if RSP_MG_HINTS >= 1
+          sv = ldg_pol(hs + (u64)bucket * 2u + lane, pol_evict_last());
+#else
           sv = __ldg(hs + (u64)bucket * 2u + lane);
+#endif
           const u32 m = ((sv.x && (sv.x >> ord_bits) == tag) ? 1u : 0u) | ((sv.y && (sv.y >> ord_bits) == tag) ? 2u : 0u) |
                         ((sv.z && (sv.z >> ord_bits) == tag) ? 4u : 0u) | ((sv.w && (sv.w >> ord_bits) == tag) ? 8u : 0u);
           const u32 e = (sv.x == 0 || sv.y == 0 || sv.z == 0 || sv.w == 0) ? 1u : 0u;
@@ -394,7 +459,7 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
         const u32 val = __shfl_sync(pmask, pick, pbase + (p >> 2));
         // run entry: unit0 header, unit1 key, units 2.. value
         const u32 r = fast_entry<false>(heap + (u64)((val & ((1u << ord_bits) - 1u)) - 1u) * U * 16u, U, 1, kq, ~0ull, dst,
-                                        a.val_stride, lane, vlen);
+                                        a.val_stride, lane, vlen, pol_stream);
         if (r == 0) { state = 0; break; }
         if (r == 2) break;
       }
@@ -402,12 +467,18 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
   }
   if (lane == 0) {
     if (state == 2) {
-      a.pending[atomicAdd(a.n_pending, 1u)] = q;
+      a.pending[atomicAdd(a.n_pending + a.parity, 1u)] = q;
     } else {
       a.st[q] = state == 0 ? 0 : 1;
       a.vlen[q] = vlen;
     }
   }
+  // this launch counts in n_pending[parity].  Clearing the other counter here instead of a memset node
+  // before the launch measured 20 % SLOWER end to end on B200 (14.98 -> 12.08 G lookups/s), so the
+  // memset node stays (RSP_MG_MEMSET=1).
+#if !RSP_MG_MEMSET
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.n_pending[a.parity ^ 1u] = 0;
+#endif
 }
 
 // generic path over the queries the fast kernel deferred; a small fixed grid strides over the list
@@ -415,7 +486,7 @@ __global__ void __launch_bounds__(256) k_multi_get_pending(GetArgs a) {
   const u32 lane = threadIdx.x & (MG_LANES - 1);
   const u32 gbase = (threadIdx.x & 31u) & ~(MG_LANES - 1u);
   const u32 gmask = ((1u << MG_LANES) - 1u) << gbase;
-  const u32 n = __ldcg(a.n_pending);
+  const u32 n = __ldcg(a.n_pending + a.parity);
   const u32 groups = gridDim.x * (blockDim.x / MG_LANES);
   for (u32 i = (blockIdx.x * blockDim.x + threadIdx.x) / MG_LANES; i < n; i += groups)
     lookup_generic(a, __ldcg(a.pending + i), lane, gmask, gbase);
@@ -426,7 +497,9 @@ void launch_multi_get(const GetArgs& a, cudaStream_t s) {
   const u32 per_block = 256 / MG_LANES;
   const u32 grid = (a.n + per_block - 1) / per_block;
   if (a.klen_fixed == 16 && (reinterpret_cast<uintptr_t>(a.keys) & 15u) == 0 && a.pending && a.fast) {
-    cudaMemsetAsync(a.n_pending, 0, 4, s);
+#if RSP_MG_MEMSET
+    cudaMemsetAsync(a.n_pending + a.parity, 0, 4, s);
+#endif
     k_multi_get16<<<(a.n + RSP_MG_TPB / FL - 1) / (RSP_MG_TPB / FL), RSP_MG_TPB, 0, s>>>(a);
     k_multi_get_pending<<<std::min<u32>(grid, 148u), 256, 0, s>>>(a);
   } else {

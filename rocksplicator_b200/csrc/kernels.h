@@ -76,7 +76,8 @@ struct GetArgs {
   i32* st;               // [n]
   u32 n;
   u32* pending;          // [n] scratch: queries deferred by the fast kernel (may be nullptr)
-  u32* n_pending;        // [1]
+  u32* n_pending;        // [2] counters used alternately (launch parity), so no memset between launches
+  u32 parity;
 };
 void launch_multi_get(const GetArgs& a, cudaStream_t s);
 
