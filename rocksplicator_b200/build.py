@@ -59,3 +59,34 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+
+
+HOST = os.path.join(HERE, "host")
+HOST_SRCS = ["gpu_db.cpp", "rocksdb_replicator/rocksdb_replicator.cpp", "rocksdb_replicator/gpu_db_wrapper.cpp",
+             "rocksdb_admin/application_db.cpp", "rocksdb_admin/application_db_manager.cpp"]
+HOST_SO = os.path.join(HERE, "librsp_host.so")
+HOST_TESTS = os.path.join(os.path.dirname(HERE), "tests", "cpp", "host_tests")
+
+
+def build_host(force=False, verbose=False):
+    """The C++ mirror of the reference interfaces (host/) -> librsp_host.so, and its test binary."""
+    build(force=False, verbose=verbose)
+    srcs = [os.path.join(HOST, s) for s in HOST_SRCS]
+    deps = list(srcs)
+    for dp, _, fs in os.walk(HOST):
+        deps += [os.path.join(dp, f) for f in fs if f.endswith(".h")]
+    cxx = os.environ.get("CXX", "g++")
+    flags = ["-std=c++17", "-O2", "-g", "-fPIC", "-Wall", "-I", HOST, "-pthread"]
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+
+    if force or _stale(HOST_SO, deps + [OUT]):
+        run([cxx] + flags + ["-shared", "-o", HOST_SO] + srcs + ["-L", HERE, "-lrsp_b200", "-Wl,-rpath,$ORIGIN"])
+    tsrc = os.path.join(os.path.dirname(HERE), "tests", "cpp", "host_tests.cpp")
+    if force or _stale(HOST_TESTS, [tsrc, HOST_SO] + deps):
+        run([cxx] + flags + ["-o", HOST_TESTS, tsrc, "-L", HERE, "-lrsp_host", "-lrsp_b200",
+                             "-Wl,-rpath," + HERE])
+    return HOST_SO, HOST_TESTS

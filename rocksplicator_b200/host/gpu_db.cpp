@@ -1,0 +1,282 @@
+// gpu_db.cpp — see gpu_db.h.  Call sites replaced: rocksdb_replicator/rocksdb_wrapper.cpp:4-28,
+// rocksdb_admin/application_db.cpp:78-144.
+#include "gpu_db.h"
+
+#include <cstring>
+#include <map>
+
+namespace b200 {
+
+using rocksdb::Slice;
+using rocksdb::Status;
+
+std::shared_ptr<GpuEngine> GpuEngine::ForDevice(int device) {
+  static std::mutex mu;
+  static std::map<int, std::weak_ptr<GpuEngine>> engines;
+  std::lock_guard<std::mutex> g(mu);
+  if (auto e = engines[device].lock()) return e;
+  rsp_engine* raw = nullptr;
+  rsp_engine_cfg cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.abi_version = RSP_ABI_VERSION;
+  if (rsp_engine_create(device, &cfg, &raw) != RSP_OK) return nullptr;
+  std::shared_ptr<GpuEngine> e(new GpuEngine(raw));
+  engines[device] = e;
+  return e;
+}
+GpuEngine::~GpuEngine() { rsp_engine_destroy(e_); }
+
+int GpuDB::MergeTrampoline(void* state, const uint8_t* key, size_t klen, const uint8_t* existing, size_t elen,
+                           const uint8_t* operand, size_t olen, void (*out_set)(void*, const uint8_t*, size_t),
+                           void* out_ctx) {
+  auto* op = static_cast<rocksdb::MergeOperator*>(state);
+  Slice ex((const char*)existing, elen);
+  std::string nv;
+  if (!op->Merge(Slice((const char*)key, klen), existing ? &ex : nullptr, Slice((const char*)operand, olen), &nv, nullptr))
+    return 0;
+  out_set(out_ctx, (const uint8_t*)nv.data(), nv.size());
+  return 1;
+}
+
+Status GpuDB::Open(const rocksdb::Options& options, const std::string& name, rocksdb::DB** dbptr, int device) {
+  *dbptr = nullptr;
+  auto engine = GpuEngine::ForDevice(device);
+  if (!engine) return Status::IOError("no usable CUDA device for the B200 engine (there is no CPU fallback)");
+  rsp_shard_opts so;
+  memset(&so, 0, sizeof(so));
+  so.write_buffer_bytes = options.write_buffer_size;
+  if (options.merge_operator) {
+    const std::string n = options.merge_operator->Name();
+    // operators whose semantics the device implements exactly; anything else folds on the host through the callback
+    if (n == "CounterMergeOperator") so.merge_op = RSP_MERGE_COUNTER;        // examples/counter_service/merge_operator.cpp
+    else if (n == "UInt64AddOperator") so.merge_op = RSP_MERGE_UINT64ADD;    // RocksDB built-in
+    else { so.merge_op = RSP_MERGE_CALLBACK; so.merge_fn = &GpuDB::MergeTrampoline; so.merge_state = options.merge_operator.get(); }
+  }
+  rsp_shard* sh = nullptr;
+  const int rc = rsp_shard_open(engine->raw(), name.c_str(), &so, &sh);
+  if (rc != RSP_OK) return rc == RSP_INVALID_ARGUMENT ? Status::InvalidArgument("db already open: " + name) : Status::IOError("rsp_shard_open");
+  GpuDB* db = new GpuDB();
+  db->name_ = name;
+  db->options_ = options;
+  db->engine_ = engine;
+  db->shard_ = sh;
+  *dbptr = db;
+  return Status::OK();
+}
+
+GpuDB::~GpuDB() {
+  if (shard_) rsp_shard_close(shard_);
+}
+
+Status GpuDB::ToStatus(int code) const {
+  if (code == RSP_OK) return Status::OK();
+  char buf[256];
+  buf[0] = 0;
+  rsp_last_error(shard_, buf, sizeof(buf));
+  return Status::FromCode(code, buf);
+}
+
+void GpuDB::LogAppend(rocksdb::SequenceNumber first_seq, std::string&& bytes, uint32_t count) {
+  auto e = std::make_shared<LogEntry>();
+  e->first_seq = first_seq;
+  e->count = count;
+  e->bytes = std::move(bytes);
+  std::lock_guard<std::mutex> g(log_mu_);
+  log_bytes_ += e->bytes.size();
+  log_.push_back(std::move(e));
+  while (log_bytes_ > log_cap_bytes_ && log_.size() > 1) {  // WAL TTL / size limit stand-in
+    log_bytes_ -= log_.front()->bytes.size();
+    log_.pop_front();
+    log_base_id_++;
+  }
+}
+
+Status GpuDB::Write(const rocksdb::WriteOptions&, rocksdb::WriteBatch* updates) {
+  std::lock_guard<std::mutex> g(write_mu_);
+  uint64_t seq = 0;
+  const std::string& rep = updates->Data();
+  const int rc = rsp_write(shard_, (const uint8_t*)rep.data(), rep.size(), &seq);
+  if (rc != RSP_OK) return ToStatus(rc);
+  const uint32_t count = (uint32_t)updates->Count();
+  if (count) {
+    std::string bytes = rep;
+    const uint64_t first = seq - count + 1;
+    memcpy(&bytes[0], &first, 8);  // DB::Write stamps the batch's sequence in place
+    updates->SetSequence(first);
+    LogAppend(first, std::move(bytes), count);
+  }
+  return Status::OK();
+}
+
+Status GpuDB::ApplyReplicated(const Slice& raw, uint64_t ts) {
+  std::lock_guard<std::mutex> g(write_mu_);
+  uint64_t seq = 0;
+  const int rc = rsp_apply(shard_, (const uint8_t*)raw.data(), raw.size(), ts, &seq);
+  if (rc != RSP_OK) return ToStatus(rc);
+  if (raw.size() >= rocksdb::WriteBatch::kHeader) {
+    uint32_t count;
+    memcpy(&count, raw.data() + 8, 4);
+    if (count) {  // what the follower's own WAL would hold: the batch + its LogData(timestamp)
+      std::string bytes(raw.data(), raw.size());
+      bytes.push_back(0x3);
+      bytes.push_back(8);
+      bytes.append((const char*)&ts, 8);
+      const uint64_t first = seq - count + 1;
+      memcpy(&bytes[0], &first, 8);
+      LogAppend(first, std::move(bytes), count);
+    }
+  }
+  return Status::OK();
+}
+
+Status GpuDB::Get(const rocksdb::ReadOptions&, const Slice& key, std::string* value) {
+  size_t cap = 256, n = 0;
+  for (;;) {
+    value->resize(cap);
+    const int rc = rsp_get(shard_, (const uint8_t*)key.data(), key.size(), (uint8_t*)&(*value)[0], cap, &n);
+    if (rc == RSP_INCOMPLETE) { cap = n; continue; }
+    if (rc != RSP_OK) { value->clear(); return rc == RSP_NOT_FOUND ? Status::NotFound() : ToStatus(rc); }
+    value->resize(n);
+    return Status::OK();
+  }
+}
+
+Status GpuDB::Get(const rocksdb::ReadOptions& o, rocksdb::ColumnFamilyHandle*, const Slice& key, rocksdb::PinnableSlice* value) {
+  Status s = Get(o, key, value->GetSelf());
+  if (s.ok()) value->PinSelf();
+  return s;
+}
+
+std::vector<Status> GpuDB::MultiGet(const rocksdb::ReadOptions&, const std::vector<Slice>& keys, std::vector<std::string>* values) {
+  const size_t n = keys.size();
+  std::vector<Status> out(n);
+  values->assign(n, std::string());
+  if (!n) return out;
+  std::vector<uint64_t> koff(n + 1, 0);
+  for (size_t i = 0; i < n; i++) koff[i + 1] = koff[i] + keys[i].size();
+  std::string blob;
+  blob.reserve(koff[n] + 1);
+  for (auto& k : keys) blob.append(k.data(), k.size());
+  blob.push_back('\0');
+  std::vector<uint32_t> six(n, rsp_shard_index(shard_)), vlen(n);
+  std::vector<int32_t> st(n);
+  size_t stride = 256;
+  for (;;) {
+    std::vector<uint8_t> vals(n * stride);
+    if (rsp_multi_get(engine(), n, six.data(), (const uint8_t*)blob.data(), koff.data(), vals.data(), stride, vlen.data(),
+                      st.data()) != RSP_OK) {
+      for (auto& s : out) s = Status::IOError("rsp_multi_get");
+      return out;
+    }
+    size_t need = 0;
+    for (size_t i = 0; i < n; i++) if (st[i] == RSP_INCOMPLETE) need = std::max<size_t>(need, vlen[i]);
+    if (need) { stride = need; continue; }
+    for (size_t i = 0; i < n; i++) {
+      if (st[i] == RSP_OK) (*values)[i].assign((const char*)&vals[i * stride], vlen[i]);
+      else out[i] = st[i] == RSP_NOT_FOUND ? Status::NotFound() : ToStatus(st[i]);
+    }
+    return out;
+  }
+}
+
+namespace {
+class GpuIterator : public rocksdb::Iterator {
+ public:
+  explicit GpuIterator(rsp_iter* it) : it_(it) {}
+  ~GpuIterator() override { rsp_iter_destroy(it_); }
+  bool Valid() const override { return rsp_iter_valid(it_) != 0; }
+  void SeekToFirst() override { rsp_iter_seek_to_first(it_); }
+  void SeekToLast() override { rsp_iter_seek_to_last(it_); }
+  void Seek(const Slice& t) override { rsp_iter_seek(it_, (const uint8_t*)t.data(), t.size()); }
+  void Next() override { rsp_iter_next(it_); }
+  void Prev() override { rsp_iter_prev(it_); }
+  Slice key() const override { size_t n; auto p = rsp_iter_key(it_, &n); return Slice((const char*)p, n); }
+  Slice value() const override { size_t n; auto p = rsp_iter_value(it_, &n); return Slice((const char*)p, n); }
+  Status status() const override {
+    const int c = rsp_iter_status(it_);
+    return c ? Status::FromCode(c, c == 2 ? "Corruption: Error: Could not perform merge." : "error") : Status::OK();
+  }
+
+ private:
+  rsp_iter* it_;
+};
+}  // namespace
+
+rocksdb::Iterator* GpuDB::NewIterator(const rocksdb::ReadOptions&) { return new GpuIterator(rsp_iter_create(shard_)); }
+
+Status GpuDB::CompactRange(const rocksdb::CompactRangeOptions&, const Slice* begin, const Slice* end) {
+  if (begin || end) return Status::NotSupported("partial CompactRange");  // the reference passes (nullptr, nullptr)
+  return ToStatus(rsp_compact(shard_));
+}
+Status GpuDB::Flush(const rocksdb::FlushOptions&) { return ToStatus(rsp_flush(shard_)); }
+rocksdb::SequenceNumber GpuDB::GetLatestSequenceNumber() const { return rsp_latest_seq(shard_); }
+
+// TransactionLogIterator over the update log; tails new writes like RocksDB's WAL iterator
+class GpuDB::LogIter : public rocksdb::TransactionLogIterator {
+ public:
+  LogIter(GpuDB* db, uint64_t id) : db_(db), id_(id) { Load(); }
+  bool Valid() override { return cur_ != nullptr; }
+  void Next() override { if (cur_) id_++; Load(); }
+  Status status() override { return Status::OK(); }
+  rocksdb::BatchResult GetBatch() override {
+    rocksdb::BatchResult r;
+    r.sequence = cur_->first_seq;
+    r.writeBatchPtr.reset(new rocksdb::WriteBatch(cur_->bytes));
+    return r;
+  }
+
+ private:
+  void Load() {
+    std::lock_guard<std::mutex> g(db_->log_mu_);
+    if (id_ < db_->log_base_id_) id_ = db_->log_base_id_;  // trimmed: first available (a gap, as after WAL TTL)
+    const uint64_t off = id_ - db_->log_base_id_;
+    cur_ = off < db_->log_.size() ? db_->log_[off] : nullptr;
+  }
+  GpuDB* db_;
+  uint64_t id_;
+  std::shared_ptr<const LogEntry> cur_;
+};
+
+Status GpuDB::GetUpdatesSince(rocksdb::SequenceNumber seq, std::unique_ptr<rocksdb::TransactionLogIterator>* iter) {
+  iter->reset();
+  if (seq > GetLatestSequenceNumber()) return Status::NotFound("Requested sequence not yet written in the db");
+  uint64_t id;
+  {
+    std::lock_guard<std::mutex> g(log_mu_);
+    // first entry whose last sequence >= seq
+    size_t lo = 0, hi = log_.size();
+    while (lo < hi) {
+      const size_t m = (lo + hi) / 2;
+      if (log_[m]->first_seq + log_[m]->count - 1 < seq) lo = m + 1; else hi = m;
+    }
+    id = log_base_id_ + lo;
+  }
+  iter->reset(new LogIter(this, id));
+  return Status::OK();
+}
+
+bool GpuDB::GetProperty(const Slice& property, std::string* value) {
+  rsp_stats st;
+  if (rsp_get_stats(shard_, &st) != RSP_OK) return false;
+  const std::string p = property.ToString();
+  if (p == "rocksdb.estimate-num-keys") { *value = std::to_string(st.memtable_entries + st.run_entries); return true; }
+  if (p == "rocksdb.num-entries-active-mem-table") { *value = std::to_string(st.memtable_entries); return true; }
+  if (p == "rocksdb.cur-size-active-mem-table") { *value = std::to_string(st.memtable_bytes); return true; }
+  if (p == "rocksdb.total-sst-files-size") { *value = std::to_string(st.run_bytes); return true; }
+  if (p == "rocksdb.num-files-at-level0") { *value = std::to_string(st.n_runs > 1 ? st.n_runs - 1 : 0); return true; }
+  return false;
+}
+
+void GpuDB::GetColumnFamilyMetaData(rocksdb::ColumnFamilyMetaData* meta) {
+  // the newest runs play level 0, the oldest (fully merged) run the bottom level
+  rsp_stats st;
+  rsp_get_stats(shard_, &st);
+  meta->levels.clear();
+  for (int l = 0; l < options_.num_levels; l++) meta->levels.push_back({l, 0});
+  if (st.n_runs == 1) meta->levels.back().size = st.run_bytes;
+  else if (st.n_runs > 1) { meta->levels[0].size = st.run_bytes / 2; meta->levels.back().size = st.run_bytes - st.run_bytes / 2; }
+  meta->size = st.run_bytes;
+  meta->file_count = st.n_runs;
+}
+
+}  // namespace b200

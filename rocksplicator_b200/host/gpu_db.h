@@ -1,0 +1,86 @@
+// gpu_db.h — rocksdb::DB over the B200 engine's C ABI (include/rsp_b200.h).  This is the object handed to
+// RocksDBReplicator::addDB / ApplicationDB in place of the rocksdb::DB* that rocksdb::DB::Open returns at
+// rocksdb_admin/admin_handler.cpp:640.  Host code only: no CUDA types; every data call ends in librsp_b200.so.
+#pragma once
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+
+#include "../../include/rsp_b200.h"
+#include "rocksdb/db.h"
+
+namespace b200 {
+
+// one engine per GPU, shared by every DB placed on it (shard_id -> GPU partitioning)
+class GpuEngine {
+ public:
+  static std::shared_ptr<GpuEngine> ForDevice(int device);
+  ~GpuEngine();
+  rsp_engine* raw() const { return e_; }
+
+ private:
+  explicit GpuEngine(rsp_engine* e) : e_(e) {}
+  rsp_engine* e_;
+};
+
+class GpuDB : public rocksdb::DB {
+ public:
+  // rocksdb::DB::Open(options, path, &db): `name` plays the path's role (segmentNNNNN)
+  static rocksdb::Status Open(const rocksdb::Options& options, const std::string& name, rocksdb::DB** dbptr,
+                              int device = 0);
+  ~GpuDB() override;
+
+  rocksdb::Status Write(const rocksdb::WriteOptions& options, rocksdb::WriteBatch* updates) override;
+  rocksdb::Status Get(const rocksdb::ReadOptions& options, const rocksdb::Slice& key, std::string* value) override;
+  rocksdb::Status Get(const rocksdb::ReadOptions& options, rocksdb::ColumnFamilyHandle* cf, const rocksdb::Slice& key,
+                      rocksdb::PinnableSlice* value) override;
+  std::vector<rocksdb::Status> MultiGet(const rocksdb::ReadOptions& options, const std::vector<rocksdb::Slice>& keys,
+                                        std::vector<std::string>* values) override;
+  rocksdb::Iterator* NewIterator(const rocksdb::ReadOptions& options) override;
+  rocksdb::Status CompactRange(const rocksdb::CompactRangeOptions& options, const rocksdb::Slice* begin,
+                               const rocksdb::Slice* end) override;
+  rocksdb::Status Flush(const rocksdb::FlushOptions& options) override;
+  rocksdb::SequenceNumber GetLatestSequenceNumber() const override;
+  rocksdb::Status GetUpdatesSince(rocksdb::SequenceNumber seq,
+                                  std::unique_ptr<rocksdb::TransactionLogIterator>* iter) override;
+  rocksdb::ColumnFamilyHandle* DefaultColumnFamily() const override { return &default_cf_; }
+  rocksdb::Options GetOptions() const override { return options_; }
+  bool GetProperty(const rocksdb::Slice& property, std::string* value) override;
+  int NumberLevels() override { return options_.num_levels; }
+  void GetColumnFamilyMetaData(rocksdb::ColumnFamilyMetaData* meta) override;
+  const std::string& GetName() const override { return name_; }
+
+  // The follower fast path: RocksDbWrapper::HandleReplicateResponse's body
+  // (rocksdb_replicator/rocksdb_wrapper.cpp:13-28) as one engine call — the raw bytes go to the device,
+  // which appends the LogData(timestamp) record, decodes, sequences and inserts.
+  rocksdb::Status ApplyReplicated(const rocksdb::Slice& raw_data, uint64_t timestamp_ms);
+
+  rsp_shard* shard() const { return shard_; }
+  rsp_engine* engine() const { return engine_->raw(); }
+
+ private:
+  GpuDB() {}
+  rocksdb::Status ToStatus(int code) const;
+  void LogAppend(rocksdb::SequenceNumber first_seq, std::string&& bytes, uint32_t count);
+  static int MergeTrampoline(void* state, const uint8_t* key, size_t klen, const uint8_t* existing, size_t elen,
+                             const uint8_t* operand, size_t olen, void (*out_set)(void*, const uint8_t*, size_t),
+                             void* out_ctx);
+  struct LogEntry { rocksdb::SequenceNumber first_seq; uint32_t count; std::string bytes; };
+  class LogIter;
+
+  std::string name_;
+  rocksdb::Options options_;
+  std::shared_ptr<GpuEngine> engine_;
+  rsp_shard* shard_ = nullptr;
+  mutable rocksdb::ColumnFamilyHandle default_cf_;
+  // update log (the WAL's role for GetUpdatesSince): applied batches by sequence number, bounded
+  std::mutex write_mu_;  // keeps log order == sequence order
+  std::mutex log_mu_;
+  std::deque<std::shared_ptr<const LogEntry>> log_;
+  uint64_t log_base_id_ = 0;  // id of log_[0]
+  size_t log_bytes_ = 0;
+  size_t log_cap_bytes_ = 256u << 20;
+};
+
+}  // namespace b200

@@ -1,0 +1,30 @@
+"""The C++ mirror of the reference interfaces (rocksplicator_b200/host/): tests/cpp/host_tests.cpp restates the
+reference's own gtest cases (see the header of that file).  CPU part: helpers + the replication protocol over
+a counting DbWrapper; GPU part: the same topologies with GpuDB below the DbWrapper seam."""
+import subprocess
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def host_tests():
+    from rocksplicator_b200 import build
+    _, exe = build.build_host()
+    return exe
+
+
+def _run(exe, mode, timeout):
+    p = subprocess.run([exe, mode], capture_output=True, text=True, timeout=timeout)
+    print(p.stdout[-4000:])
+    print(p.stderr[-2000:])
+    assert p.returncode == 0, p.stdout[-3000:]
+    assert " 0 failures" in p.stdout
+
+
+def test_host_helpers_and_protocol_cpu(host_tests):
+    _run(host_tests, "cpu", 300)
+
+
+@pytest.mark.gpu
+def test_host_gpu_backed(host_tests):
+    _run(host_tests, "gpu-only", 600)
