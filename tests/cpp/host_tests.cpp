@@ -507,7 +507,7 @@ int main(int argc, char** argv) {
       {"application_db_manager", test_application_db_manager, true},
   };
   for (auto& t : tests) {
-    if (t.gpu && mode != "gpu") continue;
+    if (t.gpu && mode != "gpu" && mode != "gpu-only") continue;
     if (!t.gpu && mode == "gpu-only") continue;
     const int before = g_fail;
     printf("[ RUN  ] %s\n", t.name);
