@@ -207,6 +207,8 @@ struct rsp_engine {
   rsp_engine_cfg cfg{};
   std::mutex mu;  // serialises GPU work issued through the ABI
   cudaStream_t st = nullptr;
+  cudaStream_t cs[3] = {nullptr, nullptr, nullptr};  // chunk streams of the pipelined host MultiGet
+  cudaEvent_t cs_done[3] = {nullptr, nullptr, nullptr};
   Arena arena;
   ShardDev* d_shards = nullptr;
   ShardFast* d_fast = nullptr;
@@ -214,6 +216,7 @@ struct rsp_engine {
   std::unordered_map<std::string, rsp_shard*> by_name;
   PinBuf pin_in, pin_out;
   DevBuf dev_tick, dev_q, dev_pending;
+  std::vector<u32> gid_scratch;
   u32 mg_parity = 0;
   size_t pending_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -241,6 +244,7 @@ static void upload_shard(rsp_engine* e, rsp_shard* s) {
     f.meta = r0.ord_bits | (std::min<u32>(r0.uniform_units, 255u) << 8);
   }
   f.meta |= (u32)std::min<size_t>(s->runs.size(), 255) << 16;
+  f.meta |= 1u << 24;  // live
   f.mt_count = s->h.mt_count;
   f.merge_op = s->h.merge_op;
   CUDA_OK(cudaMemcpyAsync(e->d_fast + s->index, &f, sizeof(f), cudaMemcpyHostToDevice, e->st));
@@ -418,23 +422,34 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
                        const uint64_t* ts_ms, rsp_staged* sg, bool own_dev) {
   sg->eng = e;
   sg->n = n;
-  // group by shard, preserving submission order within a shard
-  std::unordered_map<u32, u32> gid;
-  std::vector<std::vector<u32>> members;
+  // group by shard, preserving submission order within a shard (counting sort over shard ids)
+  std::vector<u32>& gid_of = e->gid_scratch;
+  if (gid_of.size() < e->slots.size()) gid_of.assign(e->slots.size(), 0xffffffffu);
+  std::vector<u32> g_count, g_of_batch(n);
   for (size_t i = 0; i < n; i++) {
     const u32 six = shard_ix[i];
-    if (six >= e->slots.size() || !e->slots[six]) return RSP_INVALID_ARGUMENT;
-    auto it = gid.find(six);
-    if (it == gid.end()) {
-      gid.emplace(six, (u32)members.size());
-      members.emplace_back();
-      sg->group_shard.push_back(e->slots[six]);
-      members.back().push_back((u32)i);
-    } else {
-      members[it->second].push_back((u32)i);
+    if (six >= e->slots.size() || !e->slots[six]) {
+      for (rsp_shard* s : sg->group_shard) gid_of[s->index] = 0xffffffffu;
+      return RSP_INVALID_ARGUMENT;
     }
+    u32 g = gid_of[six];
+    if (g == 0xffffffffu) {
+      g = gid_of[six] = (u32)sg->group_shard.size();
+      sg->group_shard.push_back(e->slots[six]);
+      g_count.push_back(0);
+    }
+    g_of_batch[i] = g;
+    g_count[g]++;
   }
-  const size_t ng = members.size();
+  for (rsp_shard* s : sg->group_shard) gid_of[s->index] = 0xffffffffu;
+  std::vector<u32> g_start(g_count.size() + 1, 0);
+  for (size_t g = 0; g < g_count.size(); g++) g_start[g + 1] = g_start[g] + g_count[g];
+  std::vector<u32> by_group(n);
+  {
+    std::vector<u32> fill(g_start.begin(), g_start.end() - 1);
+    for (size_t i = 0; i < n; i++) by_group[fill[g_of_batch[i]]++] = (u32)i;
+  }
+  const size_t ng = sg->group_shard.size();
   const size_t trailer = ts_ms ? 10 : 0;
   size_t blob_bytes = 0;
   u64 ops_cap = 0;
@@ -454,9 +469,10 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
   for (size_t g = 0; g < ng; g++) {
     gd[g].shard_ix = sg->group_shard[g]->index;
     gd[g].first_batch = (u32)pos;
-    gd[g].n_batches = (u32)members[g].size();
+    gd[g].n_batches = g_count[g];
     gd[g].pad = 0;
-    for (u32 i : members[g]) {
+    for (u32 bi = g_start[g]; bi < g_start[g + 1]; bi++) {
+      const u32 i = by_group[bi];
       const size_t len = (size_t)(off[i + 1] - off[i]);
       const size_t len_eff = len + trailer;
       memcpy(pblob + boff, blob + off[i], len);
@@ -679,49 +695,80 @@ static int host_fold_get(rsp_engine* e, rsp_shard* s, const uint8_t* key, size_t
 // ------------------------------------------------------------------------------------------------
 // pending-list scratch of the 16-byte-key kernel: [2 counters][n indices]; the counters alternate per launch
 static void set_pending(rsp_engine* e, GetArgs& a, size_t n) {
-  if ((n + 2) * 4 > e->pending_cap) {
-    e->pending_cap = std::max<size_t>((n + 2) * 4, e->pending_cap * 2);
+  if ((n + 8) * 4 > e->pending_cap) {
+    e->pending_cap = std::max<size_t>((n + 8) * 4, e->pending_cap * 2);
     u32* p = (u32*)e->dev_pending.get(e->pending_cap);
-    CUDA_OK(cudaMemset(p, 0, 8));
+    CUDA_OK(cudaMemset(p, 0, 16));
     e->mg_parity = 0;
   }
-  a.n_pending = (u32*)e->dev_pending.p;
+  a.n_special = (u32*)e->dev_pending.p;
+  a.n_pending = (u32*)e->dev_pending.p + 2;
   a.pending = a.n_pending + 2;
   a.parity = e->mg_parity;
   e->mg_parity ^= 1u;
 }
 
+// One MultiGet over host buffers.  Large fixed-key batches are cut into chunks that ride three streams
+// (H2D -> kernel -> D2H per chunk), so the copy engines and the SMs overlap: the end-to-end rate is set by
+// the slower PCIe direction, not by the sum of both plus the kernel.
 static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, const uint64_t* koff,
                             uint32_t klen_fixed, uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
   if (n == 0) return RSP_OK;
-  for (size_t i = 0; i < n; i++)
-    if (shard_ix[i] >= e->slots.size() || !e->slots[shard_ix[i]]) return RSP_INVALID_ARGUMENT;
   const size_t key_bytes = klen_fixed ? n * klen_fixed : (size_t)koff[n];
   const size_t o_six = 0, o_koff = align_up(n * 4, 256), o_keys = o_koff + (klen_fixed ? 0 : align_up((n + 1) * 8, 256));
   const size_t o_vlen = o_keys + align_up(key_bytes + 16, 256), o_st = o_vlen + align_up(n * 4, 256);
   const size_t o_vals = o_st + align_up(n * 4, 256);
   const size_t total = o_vals + n * val_stride + 256;
   u8* d = (u8*)e->dev_q.get(total);
-  CUDA_OK(cudaMemcpyAsync(d + o_six, shard_ix, n * 4, cudaMemcpyHostToDevice, e->st));
-  if (!klen_fixed) CUDA_OK(cudaMemcpyAsync(d + o_koff, koff, (n + 1) * 8, cudaMemcpyHostToDevice, e->st));
-  if (key_bytes) CUDA_OK(cudaMemcpyAsync(d + o_keys, keys, key_bytes, cudaMemcpyHostToDevice, e->st));
-  GetArgs a;
-  a.shards = e->d_shards; a.fast = e->d_fast; a.shard_ix = (const u32*)(d + o_six); a.keys = d + o_keys;
-  a.koff = klen_fixed ? nullptr : (const u64*)(d + o_koff); a.klen_fixed = klen_fixed;
-  a.vals = d + o_vals; a.val_stride = val_stride; a.vlen = (u32*)(d + o_vlen); a.st = (i32*)(d + o_st); a.n = (u32)n;
-  set_pending(e, a, n);
+  const size_t CH = 1u << 18;
+  const bool piped = klen_fixed && n >= 2 * CH;
+  const size_t n_chunks = piped ? (n + CH - 1) / CH : 1;
+  // scratch: [n_special][pad][2 counters per chunk][pending indices]
+  const size_t scratch_u32 = 4 + 2 * n_chunks + n + 16;
+  if (scratch_u32 * 4 > e->pending_cap) {
+    e->pending_cap = std::max(scratch_u32 * 4, e->pending_cap * 2);
+    e->dev_pending.get(e->pending_cap);
+  }
+  u32* scratch = (u32*)e->dev_pending.p;
+  CUDA_OK(cudaMemsetAsync(scratch, 0, (4 + 2 * n_chunks) * 4, e->st));
+  e->mg_parity = 0;
   CUDA_OK(cudaEventRecord(e->ev0, e->st));
-  launch_multi_get(a, e->st);
-  e->launches++;
+  for (size_t c = 0; c < n_chunks; c++) {
+    const size_t c0 = c * CH, cn = piped ? std::min(CH, n - c0) : n;
+    cudaStream_t cs = piped ? e->cs[c % 3] : e->st;
+    if (piped && c < 3) CUDA_OK(cudaStreamWaitEvent(cs, e->ev0, 0));
+    CUDA_OK(cudaMemcpyAsync(d + o_six + c0 * 4, shard_ix + c0, cn * 4, cudaMemcpyHostToDevice, cs));
+    if (!klen_fixed) CUDA_OK(cudaMemcpyAsync(d + o_koff, koff, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
+    const size_t kb0 = klen_fixed ? c0 * klen_fixed : 0, kbn = klen_fixed ? cn * klen_fixed : key_bytes;
+    if (kbn) CUDA_OK(cudaMemcpyAsync(d + o_keys + kb0, keys + kb0, kbn, cudaMemcpyHostToDevice, cs));
+    GetArgs a;
+    a.shards = e->d_shards; a.fast = e->d_fast; a.max_shards = e->cfg.max_shards;
+    a.shard_ix = (const u32*)(d + o_six) + c0; a.keys = d + o_keys + kb0;
+    a.koff = klen_fixed ? nullptr : (const u64*)(d + o_koff); a.klen_fixed = klen_fixed;
+    a.vals = d + o_vals + c0 * val_stride; a.val_stride = val_stride;
+    a.vlen = (u32*)(d + o_vlen) + c0; a.st = (i32*)(d + o_st) + c0; a.n = (u32)cn;
+    a.n_special = scratch; a.n_pending = scratch + 4 + 2 * c; a.pending = scratch + 4 + 2 * n_chunks + c0; a.parity = 0;
+    launch_multi_get(a, cs);
+    e->launches += 2;
+    CUDA_OK(cudaMemcpyAsync(vlen + c0, d + o_vlen + c0 * 4, cn * 4, cudaMemcpyDeviceToHost, cs));
+    CUDA_OK(cudaMemcpyAsync(st + c0, d + o_st + c0 * 4, cn * 4, cudaMemcpyDeviceToHost, cs));
+    if (val_stride) CUDA_OK(cudaMemcpyAsync(vals + c0 * val_stride, d + o_vals + c0 * val_stride, cn * val_stride, cudaMemcpyDeviceToHost, cs));
+  }
+  if (piped) {
+    for (int k = 0; k < 3; k++) {
+      CUDA_OK(cudaEventRecord(e->cs_done[k], e->cs[k]));
+      CUDA_OK(cudaStreamWaitEvent(e->st, e->cs_done[k], 0));
+    }
+  }
   CUDA_OK(cudaEventRecord(e->ev1, e->st));
-  CUDA_OK(cudaMemcpyAsync(vlen, d + o_vlen, n * 4, cudaMemcpyDeviceToHost, e->st));
-  CUDA_OK(cudaMemcpyAsync(st, d + o_st, n * 4, cudaMemcpyDeviceToHost, e->st));
-  if (val_stride) CUDA_OK(cudaMemcpyAsync(vals, d + o_vals, n * val_stride, cudaMemcpyDeviceToHost, e->st));
+  u32 n_special = 0;
+  CUDA_OK(cudaMemcpyAsync(&n_special, scratch, 4, cudaMemcpyDeviceToHost, e->st));
   CUDA_OK(cudaStreamSynchronize(e->st));
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->last_ms["multi_get"] = ms;
-  // post-process: error texts, host-folded merges
+  if (!n_special) return RSP_OK;
+  // post-process the rare statuses: error texts, host-folded merges, unknown shards
   for (size_t i = 0; i < n; i++) {
     if (st[i] == ST_NEED_HOST_MERGE) {
       rsp_shard* s = e->slots[shard_ix[i]];
@@ -738,7 +785,8 @@ static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, c
       }
     } else if (st[i] != RSP_OK && st[i] != RSP_NOT_FOUND && st[i] != RSP_INCOMPLETE) {
       const u32 msg = vlen[i];
-      set_err(e->slots[shard_ix[i]], msg < MSG_COUNT ? kMsgText[msg] : "error");
+      if (shard_ix[i] < e->slots.size() && e->slots[shard_ix[i]])
+        set_err(e->slots[shard_ix[i]], msg < MSG_COUNT ? kMsgText[msg] : "error");
       vlen[i] = 0;
     }
   }
@@ -858,6 +906,10 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   if (e->cfg.l0_compaction_trigger > RSP_MAX_RUNS) e->cfg.l0_compaction_trigger = RSP_MAX_RUNS;
   e->arena.slab_bytes = e->cfg.arena_bytes;
   CUDA_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  for (int k = 0; k < 3; k++) {
+    CUDA_OK(cudaStreamCreateWithFlags(&e->cs[k], cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&e->cs_done[k], cudaEventDisableTiming));
+  }
   CUDA_OK(cudaEventCreate(&e->ev0));
   CUDA_OK(cudaEventCreate(&e->ev1));
   CUDA_OK(cudaMalloc(&e->d_shards, sizeof(ShardDev) * e->cfg.max_shards));
@@ -879,6 +931,7 @@ void rsp_engine_destroy(rsp_engine* e) {
   cudaFree(e->d_shards);
   cudaFree(e->d_fast);
   cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+  for (int k = 0; k < 3; k++) { cudaStreamDestroy(e->cs[k]); cudaEventDestroy(e->cs_done[k]); }
   cudaStreamDestroy(e->st);
   delete e;
 }
@@ -1181,6 +1234,7 @@ int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, co
   {
     std::lock_guard<std::mutex> g(e->mu);  // the pending-list scratch is per engine
     set_pending(e, a, n);
+    a.max_shards = e->cfg.max_shards;
   }
   launch_multi_get(a, stream ? (cudaStream_t)stream : e->st);
   e->launches += 2;
@@ -1269,8 +1323,8 @@ uint32_t rsp_debug_last_pending(rsp_engine* e, uint32_t* first, uint32_t cap) {
   cudaDeviceSynchronize();
   if (!e->dev_pending.p) return 0;
   u32 n = 0;
-  cudaMemcpy(&n, (u32*)e->dev_pending.p + (e->mg_parity ^ 1u), 4, cudaMemcpyDeviceToHost);
-  if (first && cap) cudaMemcpy(first, (u32*)e->dev_pending.p + 2, 4 * std::min(n, cap), cudaMemcpyDeviceToHost);
+  cudaMemcpy(&n, (u32*)e->dev_pending.p + 2 + (e->mg_parity ^ 1u), 4, cudaMemcpyDeviceToHost);
+  if (first && cap) cudaMemcpy(first, (u32*)e->dev_pending.p + 4, 4 * std::min(n, cap), cudaMemcpyDeviceToHost);
   return n;
 }
 

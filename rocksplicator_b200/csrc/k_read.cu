@@ -208,6 +208,14 @@ __device__ __forceinline__ void group_copy_out(u8* dst, const u8* src, u32 n, u3
 // generic path: any key length, any entry shape, memtable chains, merges, multiple runs
 __device__ __noinline__ void lookup_generic(const GetArgs& a, u32 q, u32 lane, u32 gmask, u32 gbase) {
   const u32 six = __ldg(a.shard_ix + q);
+  if (six >= a.max_shards || !a.shards[six].live) {  // unknown / closed shard
+    if (lane == 0) {
+      a.st[q] = 4;
+      a.vlen[q] = 0;
+      if (a.n_special) atomicAdd(a.n_special, 1u);
+    }
+    return;
+  }
   const ShardDev* sd = a.shards + six;
   const u8* kp;
   u32 klen;
@@ -247,6 +255,7 @@ __device__ __noinline__ void lookup_generic(const GetArgs& a, u32 q, u32 lane, u
   if (lane == 0) {
     a.st[q] = st;
     a.vlen[q] = vlen;
+    if (st != 0 && st != 1 && st != 7 && a.n_special) atomicAdd(a.n_special, 1u);
   }
 }
 
@@ -371,7 +380,9 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
   if (q >= a.n) return;
   // (1)
   const u64 pol_stream = pol_evict_first();
-  const u32 six = __ldg(a.shard_ix + q);
+  u32 six = __ldg(a.shard_ix + q);
+  const bool bad_shard = six >= a.max_shards;
+  if (bad_shard) six = 0;
 #if RSP_MG_HINTS >= 2
   const uint4 kq = ldg_pol(reinterpret_cast<const uint4*>(a.keys) + q, pol_stream);
 #else
@@ -385,7 +396,7 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
   u8* dst = a.vals + (u64)q * a.val_stride;
   u32 state = 3;  // 0 served, 2 generic path, 3 undecided, 4 not found
   u32 vlen = 0;
-  if (n_runs > 1 || ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u)) state = 2;
+  if (n_runs > 1 || ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u) || bad_shard || !(f1.y >> 24)) state = 2;
   if (state == 3 && f1.z /* mt_count */) {
     // ---- memtable: eight u64 slots from the home position, four per lane; descriptor through L2
     const uint4* dp = reinterpret_cast<const uint4*>(a.shards + six);

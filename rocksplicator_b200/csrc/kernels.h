@@ -76,8 +76,10 @@ struct GetArgs {
   i32* st;               // [n]
   u32 n;
   u32* pending;          // [n] scratch: queries deferred by the fast kernel (may be nullptr)
-  u32* n_pending;        // [2] counters used alternately (launch parity), so no memset between launches
+  u32* n_pending;        // [2] counters (launch parity)
   u32 parity;
+  u32* n_special;        // [1] counts lookups whose status is none of OK / NotFound / Incomplete (may be nullptr)
+  u32 max_shards;        // shard ids >= this answer InvalidArgument
 };
 void launch_multi_get(const GetArgs& a, cudaStream_t s);
 
