@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(128) k_sequence(TickDev t, ShardDev* shards, S
         r.n_ops = 0; r.units = 0;
       }
       t.bres[g.first_batch + j] = r;
+      t.bstat[g.first_batch + j] = accepted ? 0u : r.status;
     }
     seq += __shfl_sync(0xffffffffu, ops_incl, 31);
     tail += __shfl_sync(0xffffffffu, units_incl, 31);
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(128) k_sequence(TickDev t, ShardDev* shards, S
           BatchRes r2 = t.bres[g.first_batch + j2];
           r2.status = mk_status(11, MSG_TOO_LARGE); r2.n_ops = 0; r2.units = 0; r2.accepted = 0;
           t.bres[g.first_batch + j2] = r2;
+          t.bstat[g.first_batch + j2] = r2.status;
         }
       }
       break;

@@ -51,6 +51,7 @@ struct TickDev {
   const GroupDesc* groups;
   BatchRes* bres;
   GroupRes* gres;
+  u32* bstat;     // final status word of each batch (k_sequence): what the host reads back
   OpRec* ops;
   u32 n_batches;
   u32 n_groups;
