@@ -344,8 +344,11 @@ def main():
 
     # ---- numbers ---------------------------------------------------------------------------------------
     peak, peak_src = peaks()
-    lookups_per_s = sum_over_ranks(Q * K) / (mg_total_ms * 1e-3)
-    applies_per_s = sum_over_ranks(T * K) / (ap_total_ms * 1e-3)
+    # every collective is issued by every rank, before any rank-0-only code
+    tot_lookups = sum_over_ranks(Q * K)
+    tot_applies = sum_over_ranks(T * K)
+    lookups_per_s = tot_lookups / (mg_total_ms * 1e-3)
+    applies_per_s = tot_applies / (ap_total_ms * 1e-3)
     ach = A_GET * Q / (mg_kernel_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "multiget_traffic.json")
@@ -371,11 +374,11 @@ def main():
             "applies": {"value": applies_per_s, "unit": "applies/s", "ms_per_tick": ap_total_ms / max(K, 1),
                         "kernel_ms_last_tick": ap_kernel_ms, "batches_per_tick": T,
                         "hbm_frac_of_peak": (A_PUT * T / (ap_kernel_ms * 1e-3) / 1e9 / peak) if ap_kernel_ms and ap_kernel_ms > 0 else None,
-                        "e2e": {"value": sum_over_ranks(T * K) / ap_e2e_s, "unit": "applies/s", "h2d_bytes_per_step": int(ticks[0][1].size + 10 * T), "d2h_bytes_per_step": 32 * T}},
+                        "e2e": {"value": tot_applies / ap_e2e_s, "unit": "applies/s", "h2d_bytes_per_step": int(ticks[0][1].size + 10 * T), "d2h_bytes_per_step": 32 * T}},
             "roofline": {"kernel": "k_multi_get", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_lookup": A_GET,
                          "lookups_per_launch": Q, "launch_ms": mg_kernel_ms},
-            "e2e": {"value": sum_over_ranks(Q * K) / mg_e2e_s, "unit": "lookups/s", "h2d_bytes_per_step": Q * 20, "d2h_bytes_per_step": Q * 72},
+            "e2e": {"value": tot_lookups / mg_e2e_s, "unit": "lookups/s", "h2d_bytes_per_step": Q * 20, "d2h_bytes_per_step": Q * 72},
             "cpu_baseline": cpu,
             "gpu_launches": int(mg_launches + ap_launches),
             "clocks": clk,
