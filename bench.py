@@ -265,6 +265,49 @@ def main():
     assert np.array_equal(h_vals.numpy().reshape(Q, 64),
                           synth.values(seed, (q_idx[jl] % np.uint64(S)).astype(np.int64), q_idx[jl], 0))
 
+    # ---- range scans: Seek(random existing key) + 128 x Next, device-resident (config-4 shape on one GPU) --
+    NSC, LSC = 16384, 128
+    REC = 8 + 16 + 64
+    sc_idx = [rng.integers(0, NKV, size=NSC, dtype=np.uint64) for _ in range(n_sets)]
+    with torch.cuda.stream(stream):
+        d_sk = [torch.from_numpy(synth.keys16(seed, qi).reshape(-1)).cuda() for qi in sc_idx]
+        d_ss = [torch.from_numpy(six_of[(qi % np.uint64(S)).astype(np.int64)].astype(np.int32)).cuda() for qi in sc_idx]
+        d_sout = torch.empty(NSC * LSC * REC, dtype=torch.uint8, device="cuda")
+        d_snout = torch.empty(NSC, dtype=torch.int32, device="cuda")
+        d_sst = torch.empty(NSC, dtype=torch.int32, device="cuda")
+
+    def scan(i):
+        rc = lib.rsp_multi_scan_device(eng.h, NSC, d_ss[i].data_ptr(), d_sk[i].data_ptr(), 16, LSC, d_sout.data_ptr(),
+                                       LSC * REC, d_snout.data_ptr(), d_sst.data_ptr(), sp)
+        assert rc == 0
+
+    for i in range(W):
+        scan(i)
+    barrier()
+    s_start, s_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_start.record(stream)
+    for k in range(K):
+        scan(W + k)
+    s_end.record(stream)
+    barrier()
+    sc_total_ms = max_over_ranks(s_start.elapsed_time(s_end))
+    assert int(d_sst.count_nonzero().item()) == 0
+    # parity: scan i of the last set returns the next keys of its shard in order, each with its value
+    last_sc = sc_idx[W + K - 1] if K else sc_idx[-1]
+    n_out = d_snout.cpu().numpy()
+    entries_last = int(n_out.sum())
+    per = NKV // S
+    for qn in (0, 1, NSC // 2, NSC - 1):
+        i0 = int(last_sc[qn]); sh0 = i0 % S; j0 = i0 // S
+        cnt = int(n_out[qn])
+        n_in_shard = len(range(sh0, NKV, S))
+        assert cnt == min(LSC, n_in_shard - j0), (cnt, j0, n_in_shard)
+        want_idx = np.arange(j0, j0 + cnt, dtype=np.uint64) * np.uint64(S) + np.uint64(sh0)
+        got = d_sout[qn * LSC * REC: qn * LSC * REC + cnt * REC].cpu().numpy().reshape(cnt, REC)
+        assert np.array_equal(got[:, 8:24], synth.keys16(seed, want_idx)), "scan keys"
+        assert np.array_equal(got[:, 24:], synth.values(seed, np.full(cnt, sh0), want_idx, 0)), "scan values"
+        assert (got[:, 0] == 16).all() and (got[:, 4] == 64).all()
+
     # ---- apply: replicated single-Put updates to existing keys, pull-sized groups per shard -----------
     T = S * args.tick
     ticks = []
@@ -347,6 +390,8 @@ def main():
     # every collective is issued by every rank, before any rank-0-only code
     tot_lookups = sum_over_ranks(Q * K)
     tot_applies = sum_over_ranks(T * K)
+    tot_scans = sum_over_ranks(NSC * K)
+    tot_scan_entries = sum_over_ranks(entries_last * K)
     lookups_per_s = tot_lookups / (mg_total_ms * 1e-3)
     applies_per_s = tot_applies / (ap_total_ms * 1e-3)
     ach = A_GET * Q / (mg_kernel_ms * 1e-3) / 1e9
@@ -369,7 +414,7 @@ def main():
             "metric": "multiget_lookups_per_s", "value": lookups_per_s, "unit": "lookups/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": (mg_total_ms + ap_total_ms) / max(K, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload, "l2": "inputs larger than L2: 0.96 GB entry heap per GPU, fresh uniform keys every step",
+            "config": {"workload": workload, "l2": "inputs larger than L2: %.2f GB entry heap per GPU, fresh uniform keys every step" % (NKV * 96 / 1e9),
                        "timing": "CUDA events on the engine stream, max over ranks", "load_s": round(t_load, 2)},
             "applies": {"value": applies_per_s, "unit": "applies/s", "ms_per_tick": ap_total_ms / max(K, 1),
                         "kernel_ms_last_tick": ap_kernel_ms, "batches_per_tick": T,
@@ -378,6 +423,9 @@ def main():
             "roofline": {"kernel": "k_multi_get", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_lookup": A_GET,
                          "lookups_per_launch": Q, "launch_ms": mg_kernel_ms},
+            "scans": {"value": tot_scans / (sc_total_ms * 1e-3), "unit": "scans/s", "entries_per_s": tot_scan_entries / (sc_total_ms * 1e-3),
+                      "scan_len": LSC, "scans_per_launch": NSC,
+                      "hbm_frac_of_peak": (entries_last * 168 + 16 * NSC) / (sc_total_ms * 1e-3 / max(K, 1)) / 1e9 / peak},
             "e2e": {"value": tot_lookups / mg_e2e_s, "unit": "lookups/s", "h2d_bytes_per_step": Q * 20, "d2h_bytes_per_step": Q * 72},
             "cpu_baseline": cpu,
             "gpu_launches": int(mg_launches + ap_launches),

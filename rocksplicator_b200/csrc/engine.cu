@@ -156,12 +156,12 @@ struct Run {
   u32* ent_off = nullptr;
   u32* hslots = nullptr;
   u64* blk_pfx = nullptr;
-  u32 n_ent = 0, heap_units = 0, n_buckets = 0, ord_bits = 0, uniform_units = 0, n_blocks = 0;
+  u32 n_ent = 0, heap_units = 0, n_buckets = 0, ord_bits = 0, uniform_units = 0, n_blocks = 0, flags = 0, kv_len = 0;
   RunDev dev() const {
     RunDev r;
     r.heap = heap; r.ent_off = ent_off; r.hslots = hslots; r.blk_pfx = blk_pfx;
     r.n_ent = n_ent; r.n_buckets = n_buckets; r.ord_bits = ord_bits; r.uniform_units = uniform_units;
-    r.n_blocks = n_blocks; r.heap_units = heap_units; r.pad0 = r.pad1 = 0;
+    r.n_blocks = n_blocks; r.heap_units = heap_units; r.flags = flags; r.kv_len = kv_len;
     return r;
   }
   size_t bytes() const { return (size_t)heap_units * 16; }
@@ -337,7 +337,7 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
     j.out_pos = (u32*)a.alloc(h.keep_b);
     j.out_ord = (u32*)a.alloc(h.keep_b);
     j.fold_val = (u64*)a.alloc(h.fold_b);
-    j.totals = (u32*)a.alloc(16);
+    j.totals = (u32*)a.alloc(32);
     jh.push_back(h);
     jobs.push_back(j);
   }
@@ -349,18 +349,20 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
   launch_compact_sort(d_jobs, jobs.data(), nj, e->st);
   launch_compact_size(d_jobs, nj, e->st);
   e->launches += 3;
-  std::vector<u32> totals(4 * nj);
+  std::vector<u32> totals(8 * nj);
   for (u32 i = 0; i < nj; i++)
-    CUDA_OK(cudaMemcpyAsync(&totals[4 * i], jobs[i].totals, 16, cudaMemcpyDeviceToHost, e->st));
+    CUDA_OK(cudaMemcpyAsync(&totals[8 * i], jobs[i].totals, 32, cudaMemcpyDeviceToHost, e->st));
   CUDA_OK(cudaStreamSynchronize(e->st));
   u32 max_items = 0;
   std::vector<std::shared_ptr<Run>> outs(nj);
   for (u32 i = 0; i < nj; i++) {
     CompactJob& j = jobs[i];
-    const u32 units = totals[4 * i], ents = totals[4 * i + 1], uni = totals[4 * i + 2], keys = totals[4 * i + 3];
+    const u32 units = totals[8 * i], ents = totals[8 * i + 1], uni = totals[8 * i + 2], keys = totals[8 * i + 3];
+    const u32 non_put = totals[8 * i + 4], kvmin = totals[8 * i + 5], kvmax = totals[8 * i + 6];
     auto r = std::make_shared<Run>();
     r->arena = &a;
     r->n_ent = ents; r->heap_units = units; r->uniform_units = uni;
+    if (ents && uni && non_put == 0 && kvmin == kvmax) { r->flags = RUN_ALL_PUT_FIXED; r->kv_len = kvmin; }
     r->n_blocks = (ents + RSP_BLOCK_ENTRIES - 1) / RSP_BLOCK_ENTRIES;
     // 8-slot buckets at load <= 0.5: a key overflows its home bucket with p ~ 2 % (Poisson(4) > 8), and
     // an overflow costs the 16-lookup warp of k_multi_get16 one more dependent sector read
@@ -409,7 +411,7 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
     a.release(jobs[i].out_pos, jh[i].keep_b);
     a.release(jobs[i].out_ord, jh[i].keep_b);
     a.release(jobs[i].fold_val, jh[i].fold_b);
-    a.release(jobs[i].totals, 16);
+    a.release(jobs[i].totals, 32);
   }
   a.release(d_jobs, sizeof(CompactJob) * nj);
 }
@@ -1344,7 +1346,9 @@ int rsp_reserve(rsp_engine* e, const rsp_staged* sg) {
 int rsp_apply_staged_device(rsp_engine* e, rsp_staged* sg, void* stream) {
   if (!e || !sg) return RSP_INVALID_ARGUMENT;
   sg->last_stream = stream ? (cudaStream_t)stream : e->st;
+  cudaEventRecord(e->ev0, sg->last_stream);
   tick_launch(e, sg, sg->last_stream);
+  cudaEventRecord(e->ev1, sg->last_stream);
   return cudaPeekAtLastError() == cudaSuccess ? RSP_OK : RSP_IO_ERROR;
 }
 int rsp_apply_staged_finish(rsp_engine* e, rsp_staged* sg, int32_t* st_out) {
@@ -1355,6 +1359,8 @@ int rsp_apply_staged_finish(rsp_engine* e, rsp_staged* sg, int32_t* st_out) {
   cudaStream_t st = sg->last_stream ? sg->last_stream : e->st;
   CUDA_OK(cudaMemcpyAsync(pout, sg->tick.gres, sg->res_bytes, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_ms["apply"] = ms;
   return tick_results(sg, pout, st_out);
 }
 

@@ -99,8 +99,10 @@ struct __align__(16) RunDev {
   u32 uniform_units;
   u32 n_blocks;
   u32 heap_units;
-  u32 pad0, pad1;
+  u32 flags;     // RUN_ALL_PUT_FIXED: every entry is a Put with the same klen and vlen (scan fast path)
+  u32 kv_len;    // klen | vlen << 16 when RUN_ALL_PUT_FIXED
 };
+constexpr u32 RUN_ALL_PUT_FIXED = 1u;
 
 struct __align__(16) ShardDev {
   // ---- memtable

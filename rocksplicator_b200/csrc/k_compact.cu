@@ -169,27 +169,40 @@ __global__ void __launch_bounds__(1024) k_compact_size(const CompactJob* jobs) {
   }
   __syncthreads();
   // ---- exclusive scans of units and entry counts (one CTA, chunk per thread)
-  __shared__ u32 s_units[1024], s_cnt[1024], s_keys[1024], s_min[1024], s_max[1024];
+  __shared__ u32 s_units[1024], s_cnt[1024], s_keys[1024], s_min[1024], s_max[1024], s_np[1024], s_kvmin[1024], s_kvmax[1024];
   const u32 chunk = (n + blockDim.x - 1) / blockDim.x;
   const u32 lo = min(n, threadIdx.x * chunk), hi = min(n, lo + chunk);
-  u32 su = 0, sc = 0, sk = 0, mn = ~0u, mx = 0;
+  u32 su = 0, sc = 0, sk = 0, mn = ~0u, mx = 0, np = 0, kvmin = ~0u, kvmax = 0;
   for (u32 i = lo; i < hi; i++) {
     const u32 ku = j.keep_units[i];
     const u32 u = ku & KEEP_UNITS_MASK;
-    if (u) { su += u; sc++; mn = min(mn, u); mx = max(mx, u); if (ku & KEEP_HEAD) sk++; }
+    if (u) {
+      su += u; sc++; mn = min(mn, u); mx = max(mx, u); if (ku & KEEP_HEAD) sk++;
+      // entry shape as it will be written (folded merges become 8-byte Puts / Merges)
+      const u32 mode = ku >> KEEP_MODE_SHIFT;
+      const EntView x = view_item(j, it[i]);
+      const u32 type = (mode == MODE_PUT_IMM || mode == MODE_PUT_BYTES) ? (u32)kTypeValue : (mode == MODE_MERGE_IMM ? (u32)kTypeMerge : x.type);
+      const u32 vlen = (mode == MODE_PUT_IMM || mode == MODE_MERGE_IMM) ? 8u : x.vlen;
+      if (type != kTypeValue || x.klen > 0xffffu || vlen > 0xffffu) np++;
+      const u32 kv = (x.klen & 0xffffu) | (vlen << 16);
+      kvmin = min(kvmin, kv); kvmax = max(kvmax, kv);
+    }
   }
   s_units[threadIdx.x] = su; s_cnt[threadIdx.x] = sc; s_keys[threadIdx.x] = sk;
   s_min[threadIdx.x] = mn; s_max[threadIdx.x] = mx;
+  s_np[threadIdx.x] = np; s_kvmin[threadIdx.x] = kvmin; s_kvmax[threadIdx.x] = kvmax;
   __syncthreads();
   if (threadIdx.x == 0) {
-    u32 au = 0, ac = 0, ak = 0, amn = ~0u, amx = 0;
+    u32 au = 0, ac = 0, ak = 0, amn = ~0u, amx = 0, anp = 0, akmin = ~0u, akmax = 0;
     for (u32 t = 0; t < blockDim.x; t++) {
       const u32 u = s_units[t], c = s_cnt[t];
       s_units[t] = au; s_cnt[t] = ac;
       au += u; ac += c; ak += s_keys[t];
       amn = min(amn, s_min[t]); amx = max(amx, s_max[t]);
+      anp += s_np[t]; akmin = min(akmin, s_kvmin[t]); akmax = max(akmax, s_kvmax[t]);
     }
     j.totals[0] = au; j.totals[1] = ac; j.totals[2] = (ac && amn == amx) ? amn : 0u; j.totals[3] = ak;
+    j.totals[4] = anp; j.totals[5] = akmin; j.totals[6] = akmax; j.totals[7] = 0;
   }
   __syncthreads();
   u32 pu = s_units[threadIdx.x], pc = s_cnt[threadIdx.x];

@@ -643,6 +643,36 @@ __global__ void __launch_bounds__(128) k_multi_scan(ScanArgs a) {
   u32 n_out = 0;
   i32 st = 0;
 
+  // ---- fast path: one fully compacted run of fixed-size Puts, forward scan.  Seek (block index + binary
+  // search), then the warp streams the consecutive entries out as 8-byte words: record i =
+  // [u32 klen][u32 vlen][key][value] at out + i * (8 + klen + vlen).
+  if (n_runs == 1 && !reverse && (runs[0].flags & RUN_ALL_PUT_FIXED)) {
+    const RunDev& R = runs[0];
+    const u32 kl = R.kv_len & 0xffffu, vl = R.kv_len >> 16;
+    const u32 rec = 8u + kl + vl;
+    if ((kl & 15u) == 0 && (vl & 7u) == 0 && ((reinterpret_cast<uintptr_t>(out) | a.out_stride) & 7u) == 0) {
+      const u32 start = extreme ? 0u : run_lower_bound(R, kp, klen, exclusive);
+      u32 cnt = min(a.max_entries, R.n_ent - start);
+      i32 fst = 0;
+      if ((u64)cnt * rec > a.out_stride) { cnt = (u32)(a.out_stride / rec); fst = 7; }
+      const u32 wpr = rec >> 3;  // 8-byte words per record
+      const u64* src = reinterpret_cast<const u64*>(R.heap) + (u64)start * R.uniform_units * 2u;
+      u64* dst = reinterpret_cast<u64*>(out);
+      const u32 total = cnt * wpr;
+      for (u32 w = lane; w < total; w += 32) {
+        const u32 r = w / wpr, jw = w - r * wpr;
+        // source words of entry r: word 1 = (klen, vlen); key from word 2; value follows (klen % 16 == 0)
+        const u64* e = src + (u64)r * R.uniform_units * 2u;
+        dst[w] = jw == 0 ? __ldg(e + 1) : __ldg(e + 1 + jw);
+      }
+      if (lane == 0) {
+        a.n_out[q] = cnt;
+        a.st[q] = fst;
+      }
+      return;
+    }
+  }
+
   // cursors: forward = next ordinal to consume; reverse = (last ordinal to consume) + 1
   u32 cur[RSP_MAX_RUNS];
   for (u32 r = 0; r < n_runs; r++) {

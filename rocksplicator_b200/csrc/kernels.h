@@ -149,7 +149,7 @@ struct CompactJob {
   u32* out_pos;     // [n_items] exclusive scan of keep_units
   u32* out_ord;     // [n_items] exclusive scan of (keep_units != 0)
   u64* fold_val;    // [n_items] folded 8-byte merge results
-  u32* totals;      // [4]: units, entries, uniform_units (or 0), distinct keys
+  u32* totals;      // [8]: units, entries, uniform_units (or 0), distinct keys, non-Put entries, min/max klen<<16|vlen..
   // outputs (allocated by the host after the sizing pass)
   u8* out_heap;
   u32* out_ent_off;

@@ -298,3 +298,77 @@ def test_scale_properties(eng, port_lib):
         assert recs == oracles[int(i) % S].scan(start=k, limit=128)
     for s in shards:
         s.close()
+
+
+def test_hot_keys_one_tick(eng, port_lib):
+    """thousands of batches in ONE tick hammering the same few keys (Put / Merge / Delete mixed): the
+    lock-free, sequence-ordered version-chain insert must leave every key exactly as serial replay does."""
+    s = new_shard(eng, okv.MERGE_COUNTER, write_buffer_bytes=4 << 20)
+    o = okv.Okv(port_lib, merge_op=okv.MERGE_COUNTER)
+    rng = random.Random(7)
+    keys = [b"hot%d" % i for i in range(5)] + [bench_key(3, i) for i in range(3)]
+    for rnd in range(3):
+        batches = []
+        for _ in range(3000):
+            wb = WriteBatch()
+            for _ in range(rng.randint(1, 3)):
+                k = rng.choice(keys)
+                r = rng.random()
+                if r < 0.3:
+                    wb.put(k, struct.pack("<q", rng.randint(-5, 5)))
+                elif r < 0.9:
+                    wb.merge(k, struct.pack("<q", rng.randint(-5, 5)))
+                else:
+                    wb.delete(k)
+            batches.append(wb.data())
+        st = eng.apply_many([s.index] * len(batches), batches, list(range(len(batches))))
+        assert not st.any()
+        for i, b in enumerate(batches):
+            assert o.apply(b, i) == 0
+        assert s.latest_seq() == o.latest_seq()
+        for k in keys:
+            assert s.get(k) == o.get(k), (rnd, k)
+        if rnd == 1:
+            s.flush()
+    assert s.scan() == o.scan()
+    s.close()
+    o.close()
+
+
+def test_concurrent_callers(eng, port_lib):
+    """the C ABI is thread-safe (rocksdb_replicator.h:80-82): 8 threads apply to their own shards and read
+    concurrently; each shard ends equal to its oracle."""
+    import threading
+    n = 8
+    shards = [new_shard(eng, okv.MERGE_COUNTER) for _ in range(n)]
+    streams = [random_stream(800 + i, 120, merge="counter") for i in range(n)]
+    errs = []
+
+    def work(i):
+        try:
+            keys, stream = streams[i]
+            for j, (bt, ts) in enumerate(stream):
+                shards[i].apply(bt, ts)
+                if j % 10 == 0:
+                    shards[i].get(keys[j % len(keys)])
+                if j == 60:
+                    shards[i].flush()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for i in range(n):
+        o = okv.Okv(port_lib, merge_op=okv.MERGE_COUNTER)
+        keys, stream = streams[i]
+        for bt, ts in stream:
+            o.apply(bt, ts)
+        assert shards[i].latest_seq() == o.latest_seq()
+        assert shards[i].multi_get(keys) == o.multi_get(keys)
+        assert shards[i].scan() == o.scan()
+        o.close()
+        shards[i].close()
