@@ -366,16 +366,72 @@ def main():
     ap_e2e_s = max_over_ranks(time.perf_counter() - t0)
     clk = clocks.stop()
 
+    # ---- config 3: apply ticks and MultiGet launches CONCURRENTLY (two streams, lock-free memtable) --------
+    mticks = []
+    for stp in range(2 * n_sets, 2 * n_sets + K):
+        per = NKV // S
+        ordn = rng.integers(0, per, size=T, dtype=np.uint64)
+        sh = np.repeat(np.arange(S, dtype=np.uint64), args.tick)
+        idx = sh + ordn * np.uint64(S)
+        b = synth.single_put_batches(synth.keys16(seed, idx), synth.values(seed, sh.astype(np.int64), idx, stp + 1), 5000 + idx)
+        six = six_of[sh.astype(np.int64)]
+        off = np.arange(T + 1, dtype=np.uint64) * np.uint64(b.shape[1])
+        ts = 5000 + idx
+        h = C.c_void_p()
+        assert lib.rsp_stage_build(eng.h, T, six.ctypes.data, b.ctypes.data, off.ctypes.data, ts.ctypes.data, C.byref(h)) == 0
+        mticks.append(h)
+        upd_idx.append(idx)
+    stream_b = torch.cuda.Stream(device=torch.device("cuda", local_rank))
+    spb = C.c_void_p(stream_b.cuda_stream)
+    barrier()
+    mb0, mb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ma0, ma1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream_b.wait_stream(stream)
+    t_mixed = time.perf_counter()
+    mb0.record(stream_b)
+    for k in range(K):  # reads: K launches queued on stream B
+        assert lib.rsp_multi_get_device(eng.h, Q, d_six[W + k].data_ptr(), d_keys[W + k].data_ptr(), 16, d_vals.data_ptr(), 64,
+                                        d_vlen.data_ptr(), d_st.data_ptr(), spb) == 0
+    mb1.record(stream_b)
+    ma0.record(stream)
+    for k in range(K):  # writes: K ticks on the engine stream while B runs
+        assert lib.rsp_reserve(eng.h, mticks[k]) == 0
+        assert lib.rsp_apply_staged_device(eng.h, mticks[k], sp) == 0
+        assert lib.rsp_apply_staged_finish(eng.h, mticks[k], st_out.ctypes.data) == 0
+        assert not st_out.any()
+    ma1.record(stream)
+    barrier()
+    mixed_wall_s = max_over_ranks(time.perf_counter() - t_mixed)
+    mixed_get_ms = max_over_ranks(mb0.elapsed_time(mb1))
+    mixed_apply_ms = max_over_ranks(ma0.elapsed_time(ma1))
+    # a lookup that raced a tick may see the value before or after it: every result is SOME version of its key
+    assert int(d_st.count_nonzero().item()) == 0
+    lastq = q_idx[W + K - 1] if K else q_idx[-1]
+    samp = np.arange(0, Q, 64)
+    got_m = d_vals.cpu().numpy().reshape(Q, 64)[samp]
+    idx_m = lastq[samp]
+    ok_m = np.zeros(samp.size, dtype=bool)
+    for ver in range(0, 2 * n_sets + K + 1):
+        todo = ~ok_m
+        if not todo.any():
+            break
+        cand = synth.values(seed, (idx_m[todo] % np.uint64(S)).astype(np.int64), idx_m[todo], ver)
+        ok_m[np.flatnonzero(todo)[(cand == got_m[todo]).all(axis=1)]] = True
+    assert ok_m.all(), "mixed-phase MultiGet returned bytes that are no version of the key"
+    for h in mticks:
+        lib.rsp_stage_free(h)
+    n_ticks_total = 2 * n_sets + K
+
     # parity after the update ticks: the newest version wins for every updated key (last writer)
     newest = {}
-    for stp in range(2 * n_sets):
+    for stp in range(n_ticks_total):
         for i in upd_idx[stp][::97]:
             newest[int(i)] = stp + 1
     chk = np.fromiter(newest.keys(), dtype=np.uint64)
     ver = np.fromiter(newest.values(), dtype=np.int64)
     # a key sampled at step s may have been rewritten later by an unsampled update: resolve exactly
     lastver = {}
-    for stp in range(2 * n_sets):
+    for stp in range(n_ticks_total):
         for i in upd_idx[stp]:
             lastver[int(i)] = stp + 1
     ver = np.array([lastver[int(i)] for i in chk], dtype=np.int64)
@@ -383,7 +439,7 @@ def main():
     for (rc, v), i, vr in zip(res, chk, ver):
         w = synth.values(seed, np.array([int(i) % S]), np.array([i], dtype=np.uint64), int(vr))[0].tobytes()
         assert rc == 0 and v == w, "apply parity failed"
-    assert sum(s.latest_seq() for s in shards) == NKV + 2 * n_sets * T
+    assert sum(s.latest_seq() for s in shards) == NKV + n_ticks_total * T
 
     # ---- numbers ---------------------------------------------------------------------------------------
     peak, peak_src = peaks()
@@ -423,6 +479,9 @@ def main():
             "roofline": {"kernel": "k_multi_get", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_lookup": A_GET,
                          "lookups_per_launch": Q, "launch_ms": mg_kernel_ms},
+            "mixed": {"what": "config 3: %d apply ticks on the engine stream concurrent with %d MultiGet launches on a second stream" % (K, K),
+                      "lookups_per_s": tot_lookups / (mixed_get_ms * 1e-3), "applies_per_s": tot_applies / (mixed_apply_ms * 1e-3),
+                      "wall_ms": mixed_wall_s * 1e3},
             "scans": {"value": tot_scans / (sc_total_ms * 1e-3), "unit": "scans/s", "entries_per_s": tot_scan_entries / (sc_total_ms * 1e-3),
                       "scan_len": LSC, "scans_per_launch": NSC,
                       "hbm_frac_of_peak": (entries_last * 168 + 16 * NSC) / (sc_total_ms * 1e-3 / max(K, 1)) / 1e9 / peak},

@@ -219,6 +219,11 @@ struct rsp_engine {
   PinBuf pin_in, pin_out;
   DevBuf dev_tick, dev_q, dev_pending;
   std::vector<u32> gid_scratch;
+  // ordering between reads launched on caller streams and memtable flushes / re-allocations on the engine stream
+  cudaEvent_t reader_ev[8] = {};
+  u32 reader_head = 0, reader_pending = 0;
+  cudaEvent_t mut_ev = nullptr;
+  bool mut_recorded = false;
   size_t stage_threads = 1;
   u32 mg_parity = 0;
   size_t pending_cap = 0;
@@ -230,6 +235,28 @@ struct rsp_engine {
 static void set_err(rsp_shard* s, const std::string& m) {
   std::lock_guard<std::mutex> g(s->err_mu);
   s->last_error = m;
+}
+
+// Reads launched on a caller's stream (rsp_multi_get_device / rsp_multi_scan_device) are lock-free against apply
+// ticks, but a flush or a memtable re-allocation recycles memory they may be reading: the engine stream waits for
+// the outstanding reader events first, and later reads wait for the mutation event.
+static void wait_readers(rsp_engine* e) {
+  const u32 n = std::min<u32>(e->reader_pending, 8);
+  for (u32 k = 0; k < n; k++) CUDA_OK(cudaStreamWaitEvent(e->st, e->reader_ev[(e->reader_head + 8 - 1 - k) % 8], 0));
+  e->reader_pending = 0;
+}
+static void note_mutation(rsp_engine* e) {
+  CUDA_OK(cudaEventRecord(e->mut_ev, e->st));
+  e->mut_recorded = true;
+}
+static void reader_begin(rsp_engine* e, cudaStream_t s) {
+  if (s != e->st && e->mut_recorded) CUDA_OK(cudaStreamWaitEvent(s, e->mut_ev, 0));
+}
+static void reader_end(rsp_engine* e, cudaStream_t s) {
+  if (s == e->st) return;
+  CUDA_OK(cudaEventRecord(e->reader_ev[e->reader_head], s));
+  e->reader_head = (e->reader_head + 1) % 8;
+  e->reader_pending++;
 }
 
 static void upload_shard(rsp_engine* e, rsp_shard* s) {
@@ -264,6 +291,8 @@ static u32 next_pow2(u32 x) {
 static void alloc_memtable(rsp_engine* e, rsp_shard* s, u64 units, u64 ents) {
   Arena& a = e->arena;
   if (s->h.mt_heap) {
+    wait_readers(e);
+    CUDA_OK(cudaStreamSynchronize(e->st));  // nothing may still read the buffers being recycled
     a.release(s->h.mt_heap, s->mt_heap_bytes);
     a.release(s->h.mt_slots, s->mt_slot_bytes);
     a.release(s->h.mt_ent_off, s->mt_ent_bytes);
@@ -342,6 +371,7 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
     jobs.push_back(j);
   }
   if (jobs.empty()) return;
+  wait_readers(e);
   const u32 nj = (u32)jobs.size();
   CompactJob* d_jobs = (CompactJob*)a.alloc(sizeof(CompactJob) * nj);
   CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CompactJob) * nj, cudaMemcpyHostToDevice, e->st));
@@ -401,6 +431,7 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
     }
     upload_shard(e, s);
   }
+  note_mutation(e);
   CUDA_OK(cudaStreamSynchronize(e->st));  // sources may be released once nothing reads them
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
@@ -974,6 +1005,8 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
     CUDA_OK(cudaStreamCreateWithFlags(&e->cs[k], cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&e->cs_done[k], cudaEventDisableTiming));
   }
+  for (int k = 0; k < 8; k++) CUDA_OK(cudaEventCreateWithFlags(&e->reader_ev[k], cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&e->mut_ev, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&e->ev0));
   CUDA_OK(cudaEventCreate(&e->ev1));
   CUDA_OK(cudaMalloc(&e->d_shards, sizeof(ShardDev) * e->cfg.max_shards));
@@ -995,6 +1028,8 @@ void rsp_engine_destroy(rsp_engine* e) {
   cudaFree(e->d_shards);
   cudaFree(e->d_fast);
   cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+  for (int k = 0; k < 8; k++) cudaEventDestroy(e->reader_ev[k]);
+  cudaEventDestroy(e->mut_ev);
   for (int k = 0; k < 3; k++) { cudaStreamDestroy(e->cs[k]); cudaEventDestroy(e->cs_done[k]); }
   cudaStreamDestroy(e->st);
   delete e;
@@ -1299,8 +1334,11 @@ int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, co
     std::lock_guard<std::mutex> g(e->mu);  // the pending-list scratch is per engine
     set_pending(e, a, n);
     a.max_shards = e->cfg.max_shards;
+    cudaStream_t rs = stream ? (cudaStream_t)stream : e->st;
+    reader_begin(e, rs);
+    launch_multi_get(a, rs);
+    reader_end(e, rs);
   }
-  launch_multi_get(a, stream ? (cudaStream_t)stream : e->st);
   e->launches += 2;
   return cudaPeekAtLastError() == cudaSuccess ? RSP_OK : RSP_IO_ERROR;
 }
@@ -1313,7 +1351,13 @@ int rsp_multi_scan_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, c
   a.shards = e->d_shards; a.views = nullptr; a.shard_ix = d_shard_ix; a.keys = d_keys; a.koff = nullptr;
   a.klen_fixed = klen; a.flags = nullptr; a.max_entries = max_entries; a.out = d_out; a.out_stride = out_stride;
   a.n_out = d_n_out; a.st = d_st; a.n = (u32)n;
-  launch_multi_scan(a, stream ? (cudaStream_t)stream : e->st);
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    cudaStream_t rs = stream ? (cudaStream_t)stream : e->st;
+    reader_begin(e, rs);
+    launch_multi_scan(a, rs);
+    reader_end(e, rs);
+  }
   e->launches++;
   return cudaPeekAtLastError() == cudaSuccess ? RSP_OK : RSP_IO_ERROR;
 }

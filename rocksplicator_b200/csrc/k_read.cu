@@ -620,7 +620,81 @@ __device__ __forceinline__ void warp_copy_bytes(u8* dst, const u8* src, u32 n, u
   for (u32 b = lane; b < n; b += 32) dst[b] = src[b];
 }
 
+// ---- TMA-staged block index + warp-ballot search (Seek on a sorted run) --------------------------------
+// The run's block index (8-byte big-endian first-key prefix per RSP_BLOCK_ENTRIES entries) is pulled into
+// shared memory with ONE bulk asynchronous copy (cp.async.bulk global -> shared, completion on an mbarrier:
+// the TMA engine, SASS UBLKCP) instead of a dependent chain of ~log2(n_blocks) global loads; the warp then
+// counts prefixes below / not above the target 32 at a time with ballots, and resolves the final position
+// inside the 1-2 candidate blocks by comparing 32 entry keys at once.
+constexpr u32 SCAN_WARPS = 4;
+constexpr u32 SCAN_STAGE_PFX = 512;  // prefixes staged per warp (4 KB): runs up to 16 K entries
+
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, u32 bytes, u64* mbar) {
+  const u32 dst = (u32)__cvta_generic_to_shared(smem_dst);
+  const u32 bar = (u32)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(u64* mbar, u32 count) {
+  const u32 bar = (u32)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* mbar, u32 parity) {
+  const u32 bar = (u32)__cvta_generic_to_shared(mbar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// warp-cooperative lower bound: first ordinal of R whose key is >= key (strict: > key)
+__device__ u32 run_lower_bound_warp(const RunDev& R, const u8* kp, u32 klen, bool strict, u64* s_pfx, u64* mbar,
+                                    u32 lane) {
+  u32 lo = 0, hi = R.n_ent;
+  if (R.n_blocks > 1 && klen) {
+    if (lane == 0) tma_load_1d(s_pfx, R.blk_pfx, (R.n_blocks * 8u + 15u) & ~15u, mbar);
+    const u64 pfx = key_prefix_be(kp, klen);
+    mbar_wait(mbar, 0);
+    u32 n_lt = 0, n_le = 0;
+    for (u32 b = 0; b < R.n_blocks; b += 32) {
+      const u64 p = b + lane < R.n_blocks ? s_pfx[b + lane] : ~0ull;
+      const u32 in = b + lane < R.n_blocks;
+      n_lt += __popc(__ballot_sync(0xffffffffu, in && p < pfx));
+      n_le += __popc(__ballot_sync(0xffffffffu, in && p <= pfx));
+    }
+    lo = n_lt ? (n_lt - 1) * RSP_BLOCK_ENTRIES : 0;
+    hi = min(R.n_ent, n_le * RSP_BLOCK_ENTRIES);
+  }
+  // entries [lo, hi) are sorted: the answer is lo + #(entries below the target)
+  u32 below = 0;
+  for (u32 b = lo; b < hi; b += 32) {
+    bool is_below = false;
+    if (b + lane < hi) {
+      const int c = cmp_run_key(R, b + lane, kp, klen);
+      is_below = c < 0 || (strict && c == 0);
+    }
+    const u32 m = __ballot_sync(0xffffffffu, is_below);
+    below += __popc(m);
+    if (m != 0xffffffffu) break;  // sorted: once an entry is not below, none after it is
+  }
+  return lo + below;
+}
+
 __global__ void __launch_bounds__(128) k_multi_scan(ScanArgs a) {
+  __shared__ __align__(16) u64 s_pfx_all[SCAN_WARPS][SCAN_STAGE_PFX];
+  __shared__ __align__(8) u64 s_mbar[SCAN_WARPS];
+  {
+    const u32 wi = threadIdx.x >> 5;
+    if ((threadIdx.x & 31u) == 0) mbar_init(&s_mbar[wi], 1);
+    __syncwarp();
+  }
   const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 lane = threadIdx.x & 31u;
   if (q >= a.n) return;
@@ -651,7 +725,12 @@ __global__ void __launch_bounds__(128) k_multi_scan(ScanArgs a) {
     const u32 kl = R.kv_len & 0xffffu, vl = R.kv_len >> 16;
     const u32 rec = 8u + kl + vl;
     if ((kl & 15u) == 0 && (vl & 7u) == 0 && ((reinterpret_cast<uintptr_t>(out) | a.out_stride) & 7u) == 0) {
-      const u32 start = extreme ? 0u : run_lower_bound(R, kp, klen, exclusive);
+      u32 start = 0;
+      if (!extreme) {
+        const u32 wi = threadIdx.x >> 5;
+        start = R.n_blocks <= SCAN_STAGE_PFX ? run_lower_bound_warp(R, kp, klen, exclusive, s_pfx_all[wi], &s_mbar[wi], lane)
+                                             : run_lower_bound(R, kp, klen, exclusive);
+      }
       u32 cnt = min(a.max_entries, R.n_ent - start);
       i32 fst = 0;
       if ((u64)cnt * rec > a.out_stride) { cnt = (u32)(a.out_stride / rec); fst = 7; }
