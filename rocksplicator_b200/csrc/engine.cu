@@ -7,6 +7,7 @@
 // No oracle, no CPU fallback: every data-path call ends in the kernels of k_*.cu or fails.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -451,6 +452,10 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
 // apply path
 // ------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline double now_us() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static const bool g_trace = getenv("RSP_TRACE") != nullptr;
 
 // Build the tick image (pinned) for n batches and copy it to the device.  Layout of the image:
 //   [BatchDesc x n][GroupDesc x g][blob ...] ; results [BatchRes x n][GroupRes x g] ; [OpRec x ops]
@@ -458,6 +463,7 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
                        const uint64_t* ts_ms, rsp_staged* sg, bool own_dev) {
   sg->eng = e;
   sg->n = n;
+  const double t_a = now_us();
   // group by shard, preserving submission order within a shard (counting sort over shard ids)
   std::vector<u32>& gid_of = e->gid_scratch;
   if (gid_of.size() < e->slots.size()) gid_of.assign(e->slots.size(), 0xffffffffu);
@@ -487,6 +493,7 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
   }
   const size_t ng = sg->group_shard.size();
   const size_t trailer = ts_ms ? 10 : 0;
+  const double t_b = now_us();
   // ---- plan (serial, no byte copies): staged order, blob offsets, reserved op slots, capacity bounds
   sg->order.resize(n);
   sg->need_units.assign(ng, 0);
@@ -540,6 +547,7 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
     gd[g].n_batches = g_count[g];
     gd[g].pad = 0;
   }
+  const double t_c = now_us();
   // ---- copy (parallel over staged positions): batch bytes + the follower's LogData record + descriptors
   const u32* order = sg->order.data();
   const u32* g_of = g_of_batch.data();
@@ -574,6 +582,8 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
     for (auto& t : th) t.join();
   }
   memset(pblob + boff, 0, 64);
+  const double t_d = now_us();
+  if (g_trace) fprintf(stderr, "[rsp trace] stage n=%zu group %.0f us plan %.0f us copy %.0f us\n", n, t_b - t_a, t_c - t_b, t_d - t_c);
   // device image: [descs | blob] [BatchRes x n] [GroupRes x g | u32 status x n] [OpRec x ops]
   const size_t bres_b = align_up(n * sizeof(BatchRes), 256);
   const size_t out_b = align_up(ng * sizeof(GroupRes) + n * 4, 256);
@@ -681,8 +691,10 @@ static int apply_many_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, 
   // reserve first (may flush), then stage: staging uses the engine's tick buffers
   // sizes are only known after grouping, so build the grouping twice is avoided by staging first into
   // pinned memory and reserving before the H2D copy is consumed (same stream => ordered)
+  const double t0 = now_us();
   int rc = stage_build(e, n, shard_ix, blob, off, ts_ms, &sg, false);
   if (rc != RSP_OK) return rc;
+  const double t1 = now_us();
   reserve_for(e, &sg);
   CUDA_OK(cudaEventRecord(e->ev0, e->st));
   tick_launch(e, &sg, e->st);
@@ -693,7 +705,10 @@ static int apply_many_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, 
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->last_ms["apply"] = ms;
-  return tick_results(&sg, pout, st_out);
+  const double t2 = now_us();
+  const int worst = tick_results(&sg, pout, st_out);
+  if (g_trace) fprintf(stderr, "[rsp trace] apply_many n=%zu stage %.0f us device+sync %.0f us (kernels %.0f us) results %.0f us\n", n, t1 - t0, t2 - t1, ms * 1e3, now_us() - t2);
+  return worst;
 }
 
 // ------------------------------------------------------------------------------------------------
