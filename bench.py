@@ -239,6 +239,33 @@ def main():
     got = d_vals.cpu().numpy().reshape(Q, 64)
     assert np.array_equal(got, want), "MultiGet parity failed at full size"
 
+    # ---- zipf(0.99) MultiGet (config-4 access pattern on one GPU): hot keys are served from L2 ---------
+    zrng = np.random.default_rng(synth.SEED_ZIPF + rank)
+    z_idx = [synth.scatter_ranks(synth.zipf_ranks(zrng, NKV, 0.99, Q), NKV) for _ in range(3)]
+    with torch.cuda.stream(stream):
+        z_keys = [torch.from_numpy(synth.keys16(seed, zi).reshape(-1)).cuda() for zi in z_idx]
+        z_six = [torch.from_numpy(six_of[(zi % np.uint64(S)).astype(np.int64)].astype(np.int32)).cuda() for zi in z_idx]
+
+    def mgz(i):
+        j = i % 3
+        assert lib.rsp_multi_get_device(eng.h, Q, z_six[j].data_ptr(), z_keys[j].data_ptr(), 16, d_vals.data_ptr(), 64,
+                                        d_vlen.data_ptr(), d_st.data_ptr(), sp) == 0
+
+    for i in range(W):
+        mgz(i)
+    barrier()
+    z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    z0.record(stream)
+    for k in range(K):
+        mgz(W + k)
+    z1.record(stream)
+    barrier()
+    zipf_ms = max_over_ranks(z0.elapsed_time(z1))
+    jz = (W + K - 1) % 3
+    assert int(d_st.count_nonzero().item()) == 0
+    assert np.array_equal(d_vals.cpu().numpy().reshape(Q, 64),
+                          synth.values(seed, (z_idx[jz] % np.uint64(S)).astype(np.int64), z_idx[jz], 0)), "zipf MultiGet parity"
+
     # ---- MultiGet end to end: host (pinned) buffers through rsp_multi_get_fixed ------------------------
     h_keys = [torch.from_numpy(synth.keys16(seed, qi).reshape(-1)).pin_memory() for qi in q_idx[:min(n_sets, 4)]]
     h_six = [torch.from_numpy(six_of[(qi % np.uint64(S)).astype(np.int64)].astype(np.int32)).pin_memory() for qi in q_idx[:min(n_sets, 4)]]
@@ -479,6 +506,7 @@ def main():
             "roofline": {"kernel": "k_multi_get", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_lookup": A_GET,
                          "lookups_per_launch": Q, "launch_ms": mg_kernel_ms},
+            "zipf": {"theta": 0.99, "lookups_per_s": tot_lookups / (zipf_ms * 1e-3), "hbm_frac_of_peak_algorithmic": A_GET * Q / (zipf_ms * 1e-3 / max(K, 1)) / 1e9 / peak},
             "mixed": {"what": "config 3: %d apply ticks on the engine stream concurrent with %d MultiGet launches on a second stream" % (K, K),
                       "lookups_per_s": tot_lookups / (mixed_get_ms * 1e-3), "applies_per_s": tot_applies / (mixed_apply_ms * 1e-3),
                       "wall_ms": mixed_wall_s * 1e3},

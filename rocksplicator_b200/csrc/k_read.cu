@@ -349,25 +349,35 @@ __device__ __forceinline__ u32 fast_entry(const u8* ent, u32 U, u32 KU, const ui
   const uint4* ep = reinterpret_cast<const uint4*>(ent);
   const uint4 hd = ld_entry_unit<CG>(ep, pol);
   const uint4 ek = ld_entry_unit<CG>(ep + KU, pol);
-  const u32 fv = KU + 1;  // first value unit; lane L owns units fv+L, fv+L+2, fv+L+4
+  const u32 fv = KU + 1;  // first value unit; lane L owns value units L, L+2, L+4, ...
   uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
-  if (fv + lane < U) v0 = ld_entry_unit<CG>(ep + fv + lane, pol);
-  if (fv + lane + 2 < U) v1 = ld_entry_unit<CG>(ep + fv + lane + 2, pol);
-  if (fv + lane + 4 < U) v2 = ld_entry_unit<CG>(ep + fv + lane + 4, pol);
+  if (!CG) {
+    // a run: the entry size U is known before the header arrives, so the first six value units are
+    // requested together with header and key (one round trip for values up to 96 bytes)
+    if (fv + lane < U) v0 = ld_entry_unit<CG>(ep + fv + lane, pol);
+    if (fv + lane + 2 < U) v1 = ld_entry_unit<CG>(ep + fv + lane + 2, pol);
+    if (fv + lane + 4 < U) v2 = ld_entry_unit<CG>(ep + fv + lane + 4, pol);
+  }
   if (ek.x != kq.x || ek.y != kq.y || ek.z != kq.z || ek.w != kq.w || hd.z != 16) return 1;
   const u64 seq = (((u64)hd.y << 32) | hd.x) >> 8;
   const u32 vu = (hd.w + 15u) >> 4;
-  if ((hd.x & 0xffu) != kTypeValue || seq > snap || fv + vu > U || vu > 6 || (u64)vu * 16u > val_stride) return 2;
+  if ((hd.x & 0xffu) != kTypeValue || seq > snap || (!CG && fv + vu > U) || (u64)vu * 16u > val_stride) return 2;
   uint4* out = reinterpret_cast<uint4*>(dst);
+  if (CG) {
+    // the memtable: the entry's size is only known from its header, so the value follows in a second trip
+    for (u32 u = lane; u < vu; u += FL) out[u] = ld_entry_unit<CG>(ep + fv + u, pol);
+  } else {
 #if RSP_MG_HINTS >= 2
-  if (lane < vu) stg_pol(out + lane, v0, pol);
-  if (lane + 2 < vu) stg_pol(out + lane + 2, v1, pol);
-  if (lane + 4 < vu) stg_pol(out + lane + 4, v2, pol);
+    if (lane < vu) stg_pol(out + lane, v0, pol);
+    if (lane + 2 < vu) stg_pol(out + lane + 2, v1, pol);
+    if (lane + 4 < vu) stg_pol(out + lane + 4, v2, pol);
 #else
-  if (lane < vu) out[lane] = v0;
-  if (lane + 2 < vu) out[lane + 2] = v1;
-  if (lane + 4 < vu) out[lane + 4] = v2;
+    if (lane < vu) out[lane] = v0;
+    if (lane + 2 < vu) out[lane + 2] = v1;
+    if (lane + 4 < vu) out[lane + 4] = v2;
 #endif
+    for (u32 u = lane + 6; u < vu; u += FL) out[u] = ld_entry_unit<CG>(ep + fv + u, pol);  // values > 96 bytes
+  }
   vlen_out = hd.w;
   return 0;
 }
@@ -431,7 +441,7 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
   }
   if (state == 3) {
     if (n_runs == 0) state = 4;
-    else if (U == 0 || U > 8) state = 2;
+    else if (U == 0 || U >= 255) state = 2;
     else {
       // ---- run 0 through its hash index: one bucket = one 32-byte sector, four slots per lane
       const u8* heap = reinterpret_cast<const u8*>(((u64)f0.y << 32) | f0.x);

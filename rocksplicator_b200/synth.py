@@ -73,3 +73,23 @@ def single_put_batches(keys, vals, ts_ms):
     b[:, at + 1] = 8
     b[:, at + 2:at + 10] = np.asarray(ts_ms, dtype="<u8").reshape(n, 1).view(np.uint8)
     return b
+
+
+def zipf_ranks(rng, n_items, theta, size):
+    """YCSB-style zipfian ranks in [0, n_items): P(rank r) ~ 1 / (r+1)^theta (Gray et al. generator)."""
+    i = np.arange(1, n_items + 1, dtype=np.float64)
+    zetan = float(np.sum(1.0 / np.power(i, theta)))
+    zeta2 = 1.0 + 0.5 ** theta
+    alpha = 1.0 / (1.0 - theta)
+    eta = (1.0 - (2.0 / n_items) ** (1.0 - theta)) / (1.0 - zeta2 / zetan)
+    u = rng.random(size)
+    uz = u * zetan
+    r = (n_items * np.power(eta * u - eta + 1.0, alpha)).astype(np.int64)
+    r[uz < zeta2] = 1
+    r[uz < 1.0] = 0
+    return np.clip(r, 0, n_items - 1).astype(np.uint64)
+
+
+def scatter_ranks(ranks, n_items):
+    """spread popularity ranks over the key space (hot keys land on many shards)"""
+    return (ranks * np.uint64(2654435761) + np.uint64(12345)) % np.uint64(n_items)

@@ -372,3 +372,63 @@ def test_concurrent_callers(eng, port_lib):
         assert shards[i].scan() == o.scan()
         o.close()
         shards[i].close()
+
+
+def _mgf(eng, six, keys, stride):
+    """rsp_multi_get_fixed (the 16-byte-key kernel k_multi_get16 + pending list) -> [(st, value|None)]"""
+    n = len(keys)
+    k = np.frombuffer(b"".join(keys), dtype=np.uint8).copy()
+    s = np.ascontiguousarray(six, dtype=np.uint32)
+    vals = np.zeros(n * stride, dtype=np.uint8)
+    vlen = np.zeros(n, dtype=np.uint32)
+    st = np.zeros(n, dtype=np.int32)
+    assert eng.multi_get_fixed(s, k, 16, vals, stride, vlen, st) == 0
+    return [(int(st[i]), vals[i * stride:i * stride + vlen[i]].tobytes() if st[i] == 0 else None) for i in range(n)], vlen
+
+
+def test_fixed_key_kernel_shapes(eng, port_lib):
+    """the 2-lane 16-byte-key kernel on everything but the benchmark shape: 256-byte and odd-sized values,
+    Deletes, counter Merges, versions still in the memtable, several runs, misses, too-small output stride."""
+    s = new_shard(eng, okv.MERGE_COUNTER, write_buffer_bytes=1 << 20)
+    o = okv.Okv(port_lib, merge_op=okv.MERGE_COUNTER)
+    rng = random.Random(21)
+    keys = [bench_key(9, i) for i in range(600)]
+
+    def tick(sel, mk):
+        bs = [mk(k) for k in sel]
+        st = eng.apply_many([s.index] * len(bs), bs, [1] * len(bs))
+        assert not st.any()
+        for b in bs:
+            assert o.apply(b, 1) == 0
+
+    def check(tag):
+        probe = keys + [bench_key(9, 10_000 + i) for i in range(50)]
+        got, _ = _mgf(eng, [s.index] * len(probe), probe, 512)
+        assert got == o.multi_get(probe), tag
+
+    tick(keys, lambda k: WriteBatch().put(k, bytes(rng.getrandbits(8) for _ in range(256))).data())
+    check("memtable 256B")
+    s.flush()
+    check("one run 256B")
+    tick(keys[::3], lambda k: WriteBatch().put(k, bytes(rng.getrandbits(8) for _ in range(rng.choice([0, 1, 10, 64, 100, 300])))).data())
+    check("run + memtable, odd sizes")
+    s.flush()
+    tick(keys[::5], lambda k: WriteBatch().delete(k).data())
+    tick(keys[::7], lambda k: WriteBatch().merge(k, struct.pack("<q", 5)).merge(k, struct.pack("<q", 7)).data())
+    tick(keys[1::7], lambda k: WriteBatch().put(k, struct.pack("<q", 100)).merge(k, struct.pack("<q", -1)).data())
+    check("two runs + memtable, deletes and merges")
+    s.compact()
+    check("compacted")
+    # stride smaller than some values: those report INCOMPLETE with the size needed
+    got, vlen = _mgf(eng, [s.index] * len(keys), keys, 64)
+    want = o.multi_get(keys)
+    for (st, v), (wst, wv), vl in zip(got, want, vlen):
+        if wst == 0 and len(wv) > 64:
+            assert st == 7 and vl == len(wv)
+        else:
+            assert (st, v) == (wst, wv)
+    # an unknown shard id answers InvalidArgument, not a crash
+    got, _ = _mgf(eng, [60000, s.index], [keys[0], keys[1]], 512)
+    assert got[0][0] == 4 and got[1] == o.get(keys[1])
+    s.close()
+    o.close()
