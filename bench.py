@@ -111,7 +111,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--kv", type=int, default=10_000_000)
     ap.add_argument("--shards", type=int, default=1024)
-    ap.add_argument("--mg-batches", type=int, default=1024, help="concurrent MultiGet(4096) calls per launch")
+    ap.add_argument("--mg-batches", type=int, default=2048, help="concurrent MultiGet(4096) calls per launch")
     ap.add_argument("--tick", type=int, default=50, help="replicated updates per shard per apply tick")
     ap.add_argument("--cpu-kv", type=int, default=2_000_000)
     ap.add_argument("--cpu-get-secs", type=float, default=6.0)

@@ -313,10 +313,10 @@ __device__ __forceinline__ void stg_pol(uint4* p, const uint4& v, u64 pol) {
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 #ifndef RSP_MG_TPB
-#define RSP_MG_TPB 128
+#define RSP_MG_TPB 64
 #endif
 #ifndef RSP_MG_MINB
-#define RSP_MG_MINB 10
+#define RSP_MG_MINB 24
 #endif
 
 // Candidate entry at `ent`: header unit 0, key unit KU, value units KU+1.. (U units in all).
@@ -343,7 +343,7 @@ __device__ __forceinline__ uint4 ld_entry_unit(const uint4* p, u64 pol) {
   return __ldg(p);
 #endif
 }
-template <bool CG>
+template <bool CG, bool BIG>
 __device__ __forceinline__ u32 fast_entry(const u8* ent, u32 U, u32 KU, const uint4& kq, u64 snap, u8* dst,
                                           u64 val_stride, u32 lane, u32& vlen_out, u64 pol) {
   const uint4* ep = reinterpret_cast<const uint4*>(ent);
@@ -361,7 +361,7 @@ __device__ __forceinline__ u32 fast_entry(const u8* ent, u32 U, u32 KU, const ui
   if (ek.x != kq.x || ek.y != kq.y || ek.z != kq.z || ek.w != kq.w || hd.z != 16) return 1;
   const u64 seq = (((u64)hd.y << 32) | hd.x) >> 8;
   const u32 vu = (hd.w + 15u) >> 4;
-  if ((hd.x & 0xffu) != kTypeValue || seq > snap || (!CG && fv + vu > U) || (u64)vu * 16u > val_stride) return 2;
+  if ((hd.x & 0xffu) != kTypeValue || seq > snap || (!CG && fv + vu > U) || (u64)vu * 16u > val_stride || (!BIG && vu > 6)) return 2;
   uint4* out = reinterpret_cast<uint4*>(dst);
   if (CG) {
     // the memtable: the entry's size is only known from its header, so the value follows in a second trip
@@ -376,12 +376,16 @@ __device__ __forceinline__ u32 fast_entry(const u8* ent, u32 U, u32 KU, const ui
     if (lane + 2 < vu) out[lane + 2] = v1;
     if (lane + 4 < vu) out[lane + 4] = v2;
 #endif
-    for (u32 u = lane + 6; u < vu; u += FL) out[u] = ld_entry_unit<CG>(ep + fv + u, pol);  // values > 96 bytes
+    if (BIG)
+      for (u32 u = lane + 6; u < vu; u += FL) out[u] = ld_entry_unit<CG>(ep + fv + u, pol);  // values > 96 bytes
   }
   vlen_out = hd.w;
   return 0;
 }
 
+// BIG = false: values up to 96 bytes (larger ones take the pending list); BIG = true adds the tail loop for
+// larger values at the price of a few registers — the host picks by the caller's value stride.
+template <bool BIG>
 __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs a) {
   const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) / FL;
   const u32 lane = threadIdx.x & (FL - 1);
@@ -433,7 +437,7 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
     if (n_match == 1) {
       const u32 c = (lo_info & 0xffu) ? lo_cand : hi_cand;
       // memtable entry: unit0 header, unit1 link, unit2 key, units 3.. value
-      const u32 r = fast_entry<true>(heap + (u64)(c - 1u) * 16u, 7, 2, kq, snap, dst, a.val_stride, lane, vlen, pol_stream);
+      const u32 r = fast_entry<true, BIG>(heap + (u64)(c - 1u) * 16u, 7, 2, kq, snap, dst, a.val_stride, lane, vlen, pol_stream);
       state = r == 0 ? 0 : 2;
     } else if (n_match > 1 || !any_empty) {
       state = 2;
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
         const u32 pick = (p & 2u) ? ((p & 1u) ? sv.w : sv.z) : ((p & 1u) ? sv.y : sv.x);
         const u32 val = __shfl_sync(pmask, pick, pbase + (p >> 2));
         // run entry: unit0 header, unit1 key, units 2.. value
-        const u32 r = fast_entry<false>(heap + (u64)((val & ((1u << ord_bits) - 1u)) - 1u) * U * 16u, U, 1, kq, ~0ull, dst,
+        const u32 r = fast_entry<false, BIG>(heap + (u64)((val & ((1u << ord_bits) - 1u)) - 1u) * U * 16u, U, 1, kq, ~0ull, dst,
                                         a.val_stride, lane, vlen, pol_stream);
         if (r == 0) { state = 0; break; }
         if (r == 2) break;
@@ -521,7 +525,9 @@ void launch_multi_get(const GetArgs& a, cudaStream_t s) {
 #if RSP_MG_MEMSET
     cudaMemsetAsync(a.n_pending + a.parity, 0, 4, s);
 #endif
-    k_multi_get16<<<(a.n + RSP_MG_TPB / FL - 1) / (RSP_MG_TPB / FL), RSP_MG_TPB, 0, s>>>(a);
+    const u32 g16 = (a.n + RSP_MG_TPB / FL - 1) / (RSP_MG_TPB / FL);
+    if (a.val_stride > 96) k_multi_get16<true><<<g16, RSP_MG_TPB, 0, s>>>(a);
+    else k_multi_get16<false><<<g16, RSP_MG_TPB, 0, s>>>(a);
     k_multi_get_pending<<<std::min<u32>(grid, 148u), 256, 0, s>>>(a);
   } else {
     k_multi_get<<<grid, 256, 0, s>>>(a);
