@@ -203,6 +203,7 @@ struct rsp_staged {
   cudaStream_t last_stream = nullptr;
   size_t res_bytes = 0;         // gres + per-batch status words, contiguous
   std::vector<u32> group_first;  // staged position of each group's first batch (+ total at the end)
+  bool identity_order = false;   // packed ticks: staged position == caller's batch index
 };
 
 struct rsp_engine {
@@ -218,8 +219,9 @@ struct rsp_engine {
   std::vector<rsp_shard*> slots;
   std::unordered_map<std::string, rsp_shard*> by_name;
   PinBuf pin_in, pin_out;
-  DevBuf dev_tick, dev_q, dev_pending;
+  DevBuf dev_tick, dev_q, dev_pending, dev_ops;
   std::vector<u32> gid_scratch;
+  std::vector<u8> seen_scratch;
   // ordering between reads launched on caller streams and memtable flushes / re-allocations on the engine stream
   cudaEvent_t reader_ev[8] = {};
   u32 reader_head = 0, reader_pending = 0;
@@ -568,7 +570,7 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
       BatchDesc& b = bd[pos];
       const u32 g = g_of[i];
       b.shard_ix = gd[g].shard_ix; b.boff = p_boff[pos]; b.len = (u32)len_eff;
-      b.op_base = p_opbase[pos]; b.op_cap = p_cap[pos]; b.group = g; b.pad0 = b.pad1 = 0;
+      b.op_base = p_opbase[pos]; b.op_cap = p_cap[pos]; b.group = g; b.raw_len = (u32)len_eff; b.pad1 = 0;
     }
   };
   const size_t n_workers = n >= 16384 ? std::min<size_t>(e->stage_threads, 8) : 1;
@@ -599,6 +601,7 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
   }
   CUDA_OK(cudaMemcpyAsync(dev, pin, in_b, cudaMemcpyHostToDevice, e->st));
   TickDev& t = sg->tick;
+  t.ts = nullptr;  // the LogData record is physically in the staged blob
   t.batches = (const BatchDesc*)dev;
   t.groups = (const GroupDesc*)(dev + n * sizeof(BatchDesc));
   t.blob = dev + desc_b;
@@ -666,7 +669,7 @@ static int tick_results(rsp_staged* sg, const u8* pout, int32_t* st_out) {
   bool any_bad = false;
   for (size_t p = 0; p < sg->n; p++) {
     const u32 code = bs[p] >> 8;
-    if (st_out) st_out[sg->order[p]] = (int32_t)code;
+    if (st_out) st_out[sg->identity_order ? p : sg->order[p]] = (int32_t)code;
     any_bad |= code != 0;
   }
   if (any_bad) {
@@ -684,9 +687,98 @@ static int tick_results(rsp_staged* sg, const u8* pout, int32_t* st_out) {
   return worst;
 }
 
+// Packed tick: when the caller's batches are already grouped by shard (each shard's batches contiguous, in
+// order — what a per-shard aggregator produces), nothing is re-laid out on the host: the caller's blob, offsets and
+// timestamps go to the device as they are (four copies), k_prepare derives the descriptors there, and the
+// follower's LogData(timestamp) record is a VIRTUAL suffix the decode kernel synthesises.  Host work per batch: one
+// comparison.  Returns -1 when the input does not qualify (the general, host-staged path takes over).
+static int apply_many_packed(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob, const uint64_t* off,
+                             const uint64_t* ts_ms, int32_t* st_out) {
+  if (n < 1024 || off[0] != 0 || off[n] > 0xe0000000ull) return -1;
+  const double t0 = now_us();
+  rsp_staged sg;
+  sg.eng = e;
+  sg.n = n;
+  sg.identity_order = true;
+  std::vector<GroupDesc> groups;
+  std::vector<u8>& seen = e->seen_scratch;
+  if (seen.size() < e->slots.size()) seen.assign(e->slots.size(), 0);
+  bool ok = true;
+  for (size_t i = 0; i < n; i++) {
+    const u32 six = shard_ix[i];
+    if (groups.empty() || six != groups.back().shard_ix) {
+      if (six >= e->slots.size() || !e->slots[six] || seen[six]) { ok = false; break; }  // unknown, or not grouped
+      seen[six] = 1;
+      groups.push_back(GroupDesc{six, (u32)i, 0, 0});
+      sg.group_shard.push_back(e->slots[six]);
+    }
+    groups.back().n_batches++;
+  }
+  for (const GroupDesc& g : groups) seen[g.shard_ix] = 0;
+  if (!ok) return -1;
+  const size_t ng = groups.size();
+  sg.group_first.resize(ng + 1);
+  for (size_t g = 0; g < ng; g++) sg.group_first[g] = groups[g].first_batch;
+  sg.group_first[ng] = (u32)n;
+  const size_t blob_b = (size_t)off[n];
+  // device image: [groups][off][ts][need | total][BatchDesc][blob + slack][BatchRes][GroupRes | status]
+  const size_t o_groups = 0, o_off = align_up(ng * sizeof(GroupDesc), 256), o_ts = o_off + align_up((n + 1) * 8, 256);
+  const size_t o_need = o_ts + align_up(n * 8, 256), o_desc = o_need + align_up((2 * ng + 1) * 4, 256);
+  const size_t o_blob = o_desc + align_up(n * sizeof(BatchDesc), 256), o_bres = o_blob + align_up(blob_b + 64, 256);
+  const size_t o_out = o_bres + align_up(n * sizeof(BatchRes), 256);
+  const size_t total = o_out + align_up(ng * sizeof(GroupRes) + n * 4, 256);
+  u8* dev = (u8*)e->dev_tick.get(total);
+  CUDA_OK(cudaMemcpyAsync(dev + o_groups, groups.data(), ng * sizeof(GroupDesc), cudaMemcpyHostToDevice, e->st));
+  CUDA_OK(cudaMemcpyAsync(dev + o_off, off, (n + 1) * 8, cudaMemcpyHostToDevice, e->st));
+  if (ts_ms) CUDA_OK(cudaMemcpyAsync(dev + o_ts, ts_ms, n * 8, cudaMemcpyHostToDevice, e->st));
+  CUDA_OK(cudaMemcpyAsync(dev + o_blob, blob, blob_b, cudaMemcpyHostToDevice, e->st));
+  CUDA_OK(cudaMemsetAsync(dev + o_blob + blob_b, 0, 64, e->st));
+  CUDA_OK(cudaMemsetAsync(dev + o_need, 0, (2 * ng + 1) * 4, e->st));
+  PrepareArgs pa;
+  pa.blob = dev + o_blob; pa.off = (const u64*)(dev + o_off); pa.ts = ts_ms ? (const u64*)(dev + o_ts) : nullptr;
+  pa.groups = (const GroupDesc*)(dev + o_groups); pa.n_groups = (u32)ng; pa.n_batches = (u32)n;
+  pa.batches = (BatchDesc*)(dev + o_desc); pa.need = (u32*)(dev + o_need); pa.total_ops = (u32*)(dev + o_need) + 2 * ng;
+  launch_prepare(pa, e->st);
+  e->launches++;
+  u32* pneed = (u32*)e->pin_out.get((2 * ng + 1) * 4 + ng * sizeof(GroupRes) + n * 4 + 256);
+  CUDA_OK(cudaMemcpyAsync(pneed, dev + o_need, (2 * ng + 1) * 4, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  const double t1 = now_us();
+  sg.need_units.resize(ng);
+  sg.need_ents.resize(ng);
+  for (size_t g = 0; g < ng; g++) { sg.need_units[g] = pneed[2 * g]; sg.need_ents[g] = pneed[2 * g + 1]; }
+  const u32 total_ops = pneed[2 * ng];
+  reserve_for(e, &sg);
+  TickDev& t = sg.tick;
+  t.blob = dev + o_blob; t.ts = pa.ts; t.batches = pa.batches; t.groups = pa.groups;
+  t.bres = (BatchRes*)(dev + o_bres); t.gres = (GroupRes*)(dev + o_out);
+  t.bstat = (u32*)(dev + o_out + ng * sizeof(GroupRes));
+  t.ops = (OpRec*)e->dev_ops.get((size_t)std::max<u32>(total_ops, 1) * sizeof(OpRec));
+  t.n_batches = (u32)n; t.n_groups = (u32)ng; t.n_ops_cap = total_ops;
+  sg.res_bytes = ng * sizeof(GroupRes) + n * 4;
+  CUDA_OK(cudaEventRecord(e->ev0, e->st));
+  tick_launch(e, &sg, e->st);
+  CUDA_OK(cudaEventRecord(e->ev1, e->st));
+  u8* pout = (u8*)pneed + align_up((2 * ng + 1) * 4, 16);
+  CUDA_OK(cudaMemcpyAsync(pout, t.gres, sg.res_bytes, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->last_ms["apply"] = ms;
+  const double t2 = now_us();
+  const int worst = tick_results(&sg, pout, st_out);
+  if (g_trace) fprintf(stderr, "[rsp trace] apply_many(packed) n=%zu copy+prepare %.0f us tick+sync %.0f us (kernels %.0f us) results %.0f us\n",
+                       n, t1 - t0, t2 - t1, ms * 1e3, now_us() - t2);
+  return worst;
+}
+
 static int apply_many_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob,
                              const uint64_t* off, const uint64_t* ts_ms, int32_t* st_out) {
   if (n == 0) return RSP_OK;
+  if (!getenv("RSP_NO_PACKED")) {
+    const int prc = apply_many_packed(e, n, shard_ix, blob, off, ts_ms, st_out);
+    if (prc >= 0) return prc;
+  }
   rsp_staged sg;
   // reserve first (may flush), then stage: staging uses the engine's tick buffers
   // sizes are only known after grouping, so build the grouping twice is avoided by staging first into
@@ -1039,7 +1131,7 @@ void rsp_engine_destroy(rsp_engine* e) {
   for (rsp_shard* s : e->slots)
     if (s) { s->runs.clear(); delete s; }
   e->arena.destroy();
-  e->pin_in.destroy(); e->pin_out.destroy(); e->dev_tick.destroy(); e->dev_q.destroy(); e->dev_pending.destroy();
+  e->pin_in.destroy(); e->pin_out.destroy(); e->dev_tick.destroy(); e->dev_q.destroy(); e->dev_pending.destroy(); e->dev_ops.destroy();
   cudaFree(e->d_shards);
   cudaFree(e->d_fast);
   cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);

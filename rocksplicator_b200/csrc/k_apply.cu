@@ -24,12 +24,21 @@ namespace rsp {
 struct Cursor {
   const u8* p;  // batch base
   u32 pos, len;
+  u32 raw_len;  // bytes present in the blob; the rest is the virtual LogData(timestamp) record
+  u64 ts;
 };
+// byte `pos` of the batch as RocksDB sees it after PutLogData(&timestamp, 8): rocksdb_wrapper.cpp:19-20
+__device__ __forceinline__ u32 batch_byte(const u8* p, u32 raw_len, u64 ts, u32 pos) {
+  if (pos < raw_len) return __ldg(p + pos);
+  const u32 t = pos - raw_len;
+  return t == 0 ? 0x03u : (t == 1 ? 0x08u : (u32)((ts >> (8u * (t - 2u))) & 0xffu));
+}
+__device__ __forceinline__ u32 cur_byte(const Cursor& c, u32 pos) { return batch_byte(c.p, c.raw_len, c.ts, pos); }
 // util/coding.cc GetVarint32Ptr: at most 5 bytes, shift <= 28
 __device__ __forceinline__ bool get_varint32(Cursor& c, u32& v) {
   u32 result = 0;
   for (u32 shift = 0; shift <= 28 && c.pos < c.len; shift += 7) {
-    u32 byte = __ldg(c.p + c.pos);
+    u32 byte = cur_byte(c, c.pos);
     c.pos++;
     if (byte & 128) {
       result |= (byte & 127) << shift;
@@ -57,16 +66,15 @@ __global__ void __launch_bounds__(256) k_decode(TickDev t) {
   const u32 lane = threadIdx.x & 31;
   if (warp >= t.n_batches) return;
   const BatchDesc bd = t.batches[warp];
-  Cursor c{t.blob + bd.boff, 12, bd.len};
+  Cursor c{t.blob + bd.boff, 12, bd.len, bd.raw_len, t.ts ? __ldg(t.ts + warp) : 0ull};
   u32 status = 0, found = 0, units = 0;
   if (bd.len < 12) {
     status = mk_status(2, MSG_TOO_SMALL);
   } else {
-    const u32 count = (u32)__ldg(c.p + 8) | ((u32)__ldg(c.p + 9) << 8) | ((u32)__ldg(c.p + 10) << 16) |
-                      ((u32)__ldg(c.p + 11) << 24);
+    const u32 count = cur_byte(c, 8) | (cur_byte(c, 9) << 8) | (cur_byte(c, 10) << 16) | (cur_byte(c, 11) << 24);
     // every lane walks the same records (uniform control flow; loads broadcast); lane 0 writes
     while (c.pos < c.len && status == 0) {
-      const u32 tag = __ldg(c.p + c.pos);
+      const u32 tag = cur_byte(c, c.pos);
       c.pos++;
       u32 cf = 0, koff = 0, klen = 0, voff = 0, vlen = 0, type = kTypeInvalid;
       switch (tag) {
@@ -267,39 +275,17 @@ __device__ __forceinline__ void copy_to_units(u8* dst, const u8* src, u32 n, u32
 __device__ __forceinline__ u64 ld_cg_u64(const u64* p) { return __ldcg(reinterpret_cast<const unsigned long long*>(p)); }
 __device__ __forceinline__ u32 ld_cg_u32(const u32* p) { return __ldcg(p); }
 
-__global__ void __launch_bounds__(256) k_insert(TickDev t, ShardDev* shards) {
-  const u32 gid = (blockIdx.x * blockDim.x + threadIdx.x) / INS_LANES;
-  const u32 lane = threadIdx.x & (INS_LANES - 1);
-  const u32 gmask = ((1u << INS_LANES) - 1u) << ((threadIdx.x & 31u) & ~(INS_LANES - 1u));
-  if (gid >= t.n_ops_cap) return;
-  const OpRec op = t.ops[gid];
-  if (op.type == kTypeInvalid) return;
-  const BatchRes br = t.bres[op.batch_ix];
-  if (!br.accepted) return;
-  ShardDev* sd = shards + t.batches[op.batch_ix].shard_ix;
-  u8* heap = sd->mt_heap;
-  const u32 unit = br.unit_base + op.rel_units;
-  const u64 seq = br.seq_base + op.op_ix;
-  const u32 ord = br.ord_base + op.op_ix;
-  u8* ent = heap + (u64)unit * 16u;
-  // every lane hashes the key (redundant but free: the loads broadcast)
-  const u8* kp = t.blob + op.koff;
-  const u64 h = hash_key(kp, op.klen);
-  if (lane == 0) {
-    uint4 hd;
-    const u64 st = (seq << 8) | op.type;
-    hd.x = (u32)st; hd.y = (u32)(st >> 32); hd.z = op.klen; hd.w = op.vlen;
-    *reinterpret_cast<uint4*>(ent) = hd;
-    sd->mt_ent_off[ord] = unit;
-  }
-  if (lane == 1) *reinterpret_cast<uint4*>(ent + 16) = make_uint4(0u, 0u, (u32)h, (u32)(h >> 32));
-  copy_to_units(ent + 32u, kp, op.klen, lane, INS_LANES);
-  copy_to_units(ent + 32u + 16u * units_of(op.klen), t.blob + op.voff, op.vlen, lane, INS_LANES);
-  __threadfence();  // the entry is complete before any pointer to it is published
-  __syncwarp(gmask);
-  if (lane != 0) return;
-
-  // ---- find (or claim) my user key's slot: one slot per key, newest version at the head
+// Link the finished entry at `unit` into the shard's table: find (or claim) the user key's slot, then insert
+// the version into the key's chain in sequence order (lock-free; unit offsets grow with sequence).  Keys are
+// compared through the entry's own padded heap copy, read through L2.
+__device__ __forceinline__ bool eq_heap_keys_cg(const u8* a, u32 an, const u8* b, u32 bn) {
+  if (an != bn) return false;
+  const u32 nw = (an + 7u) >> 3;
+  for (u32 i = 0; i < nw; i++)
+    if (ld_cg_u64(reinterpret_cast<const u64*>(a) + i) != ld_cg_u64(reinterpret_cast<const u64*>(b) + i)) return false;
+  return true;
+}
+__device__ __noinline__ void link_into_table(ShardDev* sd, u8* heap, u8* ent, u32 unit, u32 klen, u64 h) {
   const u32 tag = hash_tag32(h);
   const u32 mask = sd->mt_slot_mask;
   u64* slots = sd->mt_slots;
@@ -316,11 +302,10 @@ __global__ void __launch_bounds__(256) k_insert(TickDev t, ShardDev* shards) {
     if ((u32)(cur >> 32) == tag) {
       const u8* he = heap + (u64)((u32)cur - 1u) * 16u;
       const u32 hklen = ld_cg_u32(reinterpret_cast<const u32*>(he) + 2);
-      if (eq_key_vs_padded_cg(kp, op.klen, reinterpret_cast<const u64*>(he + 32), hklen)) break;
+      if (eq_heap_keys_cg(ent + 32, klen, he + 32, hklen)) break;
     }
     idx = (idx + 1u) & mask;
   }
-  // ---- sequence-ordered insert into the version chain (lock-free; unit offsets grow with sequence)
   for (;;) {
     const u64 cur = ld_cg_u64(slots + idx);
     const u32 H = (u32)cur;
@@ -344,6 +329,102 @@ __global__ void __launch_bounds__(256) k_insert(TickDev t, ShardDev* shards) {
       // lost a race at this link: re-read it
     }
   }
+}
+
+__global__ void __launch_bounds__(256) k_insert(TickDev t, ShardDev* shards) {
+  const u32 gid = (blockIdx.x * blockDim.x + threadIdx.x) / INS_LANES;
+  const u32 lane = threadIdx.x & (INS_LANES - 1);
+  const u32 gmask = ((1u << INS_LANES) - 1u) << ((threadIdx.x & 31u) & ~(INS_LANES - 1u));
+  if (gid >= t.n_ops_cap) return;
+  const OpRec op = t.ops[gid];
+  if (op.type == kTypeInvalid) return;
+  const BatchRes br = t.bres[op.batch_ix];
+  if (!br.accepted) return;
+  const BatchDesc bdx = t.batches[op.batch_ix];
+  ShardDev* sd = shards + bdx.shard_ix;
+  u8* heap = sd->mt_heap;
+  const u32 unit = br.unit_base + op.rel_units;
+  const u64 seq = br.seq_base + op.op_ix;
+  const u32 ord = br.ord_base + op.op_ix;
+  u8* ent = heap + (u64)unit * 16u;
+  u8* kdst = ent + 32u;
+  u8* vdst = kdst + 16u * units_of(op.klen);
+  // A record whose key or value reaches into the VIRTUAL LogData bytes of a packed tick (a truncated batch
+  // that still parses, SURVEY §9 "swallow") is assembled byte by byte; everything else is word copies.
+  const u32 raw_end = bdx.boff + bdx.raw_len;
+  const bool crosses = op.koff + op.klen > raw_end || op.voff + op.vlen > raw_end;
+  u64 h;
+  if (!crosses) {
+    const u8* kp = t.blob + op.koff;
+    h = hash_key(kp, op.klen);  // every lane (redundant but free: the loads broadcast)
+    copy_to_units(kdst, kp, op.klen, lane, INS_LANES);
+    copy_to_units(vdst, t.blob + op.voff, op.vlen, lane, INS_LANES);
+  } else {
+    const u8* base = t.blob + bdx.boff;
+    const u64 ts = t.ts ? t.ts[op.batch_ix] : 0ull;
+    const u32 kpad = units_of(op.klen) * 16u, vpad = units_of(op.vlen) * 16u;
+    for (u32 b = lane; b < kpad; b += INS_LANES)
+      kdst[b] = b < op.klen ? (u8)batch_byte(base, bdx.raw_len, ts, op.koff - bdx.boff + b) : (u8)0;
+    for (u32 b = lane; b < vpad; b += INS_LANES)
+      vdst[b] = b < op.vlen ? (u8)batch_byte(base, bdx.raw_len, ts, op.voff - bdx.boff + b) : (u8)0;
+    __threadfence();
+    __syncwarp(gmask);
+    h = 0;
+    if (lane <= 1) {  // lanes 0 and 1 need the hash: recompute it from the padded heap copy
+      u64 hh = hash_init(op.klen);
+      for (u32 i = 0; i < ((op.klen + 7u) >> 3); i++) hh = hash_step(hh, ld_cg_u64(reinterpret_cast<const u64*>(kdst) + i));
+      h = hash_final(hh);
+    }
+  }
+  if (lane == 0) {
+    uint4 hd;
+    const u64 st = (seq << 8) | op.type;
+    hd.x = (u32)st; hd.y = (u32)(st >> 32); hd.z = op.klen; hd.w = op.vlen;
+    *reinterpret_cast<uint4*>(ent) = hd;
+    sd->mt_ent_off[ord] = unit;
+  }
+  if (lane == 1) *reinterpret_cast<uint4*>(ent + 16) = make_uint4(0u, 0u, (u32)h, (u32)(h >> 32));
+  __threadfence();  // the entry is complete before any pointer to it is published
+  __syncwarp(gmask);
+  if (lane != 0) return;
+  link_into_table(sd, heap, ent, unit, op.klen, h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_prepare — packed ticks: BatchDesc straight from the caller's arrays (no host re-layout of the blob)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prepare(PrepareArgs a) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_batches) return;
+  // group of batch i: last group whose first_batch <= i
+  u32 lo = 0, hi = a.n_groups;
+  while (hi - lo > 1) {
+    const u32 m = (lo + hi) >> 1;
+    if (__ldg(&a.groups[m].first_batch) <= i) lo = m; else hi = m;
+  }
+  const u64 o0 = __ldg(a.off + i), o1 = __ldg(a.off + i + 1);
+  const u32 raw_len = (u32)(o1 - o0);
+  const u32 len_eff = raw_len + (a.ts ? 10u : 0u);
+  const u64 ts = a.ts ? __ldg(a.ts + i) : 0ull;
+  u32 claimed = 0;
+  if (len_eff >= 12) {
+    const u8* p = a.blob + o0;
+    claimed = batch_byte(p, raw_len, ts, 8) | (batch_byte(p, raw_len, ts, 9) << 8) | (batch_byte(p, raw_len, ts, 10) << 16) |
+              (batch_byte(p, raw_len, ts, 11) << 24);
+  }
+  const u32 max_ops = len_eff > 12 ? (len_eff - 12u) / 2u : 0u;
+  const u32 cap = min(claimed, max_ops);
+  BatchDesc b;
+  b.shard_ix = __ldg(&a.groups[lo].shard_ix);
+  b.boff = (u32)o0; b.len = len_eff; b.op_base = cap ? atomicAdd(a.total_ops, cap) : 0u; b.op_cap = cap; b.group = lo;
+  b.raw_len = raw_len; b.pad1 = 0;
+  a.batches[i] = b;
+  atomicAdd(a.need + 2 * lo, cap * 4u + len_eff / 16u + 1u);
+  atomicAdd(a.need + 2 * lo + 1, cap);
+}
+void launch_prepare(const PrepareArgs& a, cudaStream_t s) {
+  if (!a.n_batches) return;
+  k_prepare<<<(a.n_batches + 255) / 256, 256, 0, s>>>(a);
 }
 
 __global__ void k_publish(TickDev t, ShardDev* shards) {

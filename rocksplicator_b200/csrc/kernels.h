@@ -7,12 +7,14 @@ namespace rsp {
 // ---- apply tick image (device) -------------------------------------------------------------------
 struct BatchDesc {
   u32 shard_ix;
-  u32 boff;    // byte offset of the batch in the tick blob (16-byte aligned)
+  u32 boff;    // byte offset of the batch in the tick blob
   u32 len;     // bytes, including the appended LogData(timestamp) record when present
   u32 op_base; // first reserved slot in the op table
   u32 op_cap;  // reserved slots (min(header count, (len-12)/2))
   u32 group;
-  u32 pad0, pad1;
+  u32 raw_len; // bytes physically present in the blob; [raw_len, len) is the VIRTUAL LogData record
+               // {0x03, 0x08, timestamp LE} (packed ticks: nobody copies the batch to append it)
+  u32 pad1;
 };
 struct GroupDesc {
   u32 shard_ix;
@@ -47,6 +49,7 @@ struct __align__(16) OpRec {
 
 struct TickDev {
   const u8* blob;
+  const u64* ts;   // packed ticks: timestamp of batch i (virtual trailer); nullptr when the trailer is in the blob
   const BatchDesc* batches;
   const GroupDesc* groups;
   BatchRes* bres;
@@ -58,6 +61,19 @@ struct TickDev {
   u32 n_ops_cap;
 };
 
+// packed tick: descriptors are derived on the device from the caller's own arrays (no host re-layout)
+struct PrepareArgs {
+  const u8* blob;       // the caller's blob as given
+  const u64* off;       // [n+1]
+  const u64* ts;        // [n] or nullptr
+  const GroupDesc* groups;
+  u32 n_groups;
+  u32 n_batches;
+  BatchDesc* batches;   // out
+  u32* need;            // out [2 * n_groups]: upper bounds (heap units, entries) per group
+  u32* total_ops;       // out [1]
+};
+void launch_prepare(const PrepareArgs& a, cudaStream_t s);
 void launch_decode(const TickDev& t, cudaStream_t s);
 void launch_sequence(const TickDev& t, ShardDev* shards, ShardFast* fast, cudaStream_t s);
 void launch_insert(const TickDev& t, ShardDev* shards, cudaStream_t s);

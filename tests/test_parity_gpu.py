@@ -432,3 +432,53 @@ def test_fixed_key_kernel_shapes(eng, port_lib):
     assert got[0][0] == 4 and got[1] == o.get(keys[1])
     s.close()
     o.close()
+
+
+def test_packed_tick_virtual_trailer(eng, port_lib):
+    """>= 1024 batches already grouped by shard take the packed path (descriptors derived on the device, the
+    follower's LogData(timestamp) record is virtual).  Includes a batch whose last value legally SWALLOWS the
+    first bytes of that record (the rest of the timestamp parses as Noop tags), and corrupt batches that latch."""
+    from rocksplicator_b200.write_batch import varint32
+    a, b, c = (new_shard(eng, okv.MERGE_COUNTER) for _ in range(3))
+    oa, ob, oc = (okv.Okv(port_lib, merge_op=okv.MERGE_COUNTER) for _ in range(3))
+    rng = random.Random(77)
+    six, batches, ts = [], [], []
+
+    def add(sh, data, t):
+        six.append(sh.index)
+        batches.append(data)
+        ts.append(t)
+
+    for i in range(700):
+        wb = WriteBatch().put(bench_key(5, i), bench_value(5, 0, i, 0))
+        if i % 7 == 0:
+            wb.merge(b"ctr", struct.pack("<q", i))
+        add(a, wb.data(), 1000 + i)
+    swallow_ts = int.from_bytes(bytes([0x41] + [0x0D] * 7), "little")
+    for i in range(400):
+        if i == 200:
+            v = b"tail-swallows-"
+            raw = bytes(8) + struct.pack("<I", 1) + b"\x01" + varint32(3) + b"swk" + varint32(len(v) + 3) + v
+            add(b, raw, swallow_ts)
+        else:
+            add(b, WriteBatch().put(b"k%d" % (i % 50), bytes(rng.getrandbits(8) for _ in range(rng.choice([0, 5, 64, 200])))).data(), 5 + i)
+    good = WriteBatch().put(b"x", b"1").data()
+    for i in range(300):
+        if i == 250:
+            add(c, good[:-1], 9)        # truncated: latches shard c
+        else:
+            add(c, WriteBatch().put(b"c%d" % i, b"v").delete(b"c%d" % (i - 1)).data(), 9)
+    st = eng.apply_many(six, batches, ts)
+    want = []
+    for ix, bt, t in zip(six, batches, ts):
+        o = oa if ix == a.index else (ob if ix == b.index else oc)
+        want.append(o.apply(bt, t))
+    assert list(st) == want
+    assert want[700 + 200] == 0 and want[-1] != 0
+    for s, o in ((a, oa), (b, ob), (c, oc)):
+        assert s.latest_seq() == o.latest_seq()
+        assert s.scan() == o.scan()
+    assert b.get(b"swk") == ob.get(b"swk") == (0, b"tail-swallows-" + bytes([0x03, 0x08, 0x41]))
+    assert c.last_error == oc.last_error
+    for s in (a, b, c):
+        s.close()
