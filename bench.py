@@ -377,11 +377,19 @@ def main():
     ap_launches = eng.kernel_launches() - launches1
     assert not st_out.any()
 
-    # e2e apply: host blob through rsp_apply_many (staging + H2D + kernels + D2H of statuses)
-    def apply_e2e(i):
+    # e2e apply: pinned host buffers through rsp_apply_many (H2D + kernels + D2H of statuses inside)
+    pinned_ticks = []
+    for i in range(n_sets):
         six, b, off, ts = ticks[n_sets + i]
-        st = eng.apply_packed(six, b.reshape(-1), off, ts)
-        assert not st.any()
+        pinned_ticks.append(tuple(torch.from_numpy(np.ascontiguousarray(x).reshape(-1)).pin_memory()
+                                  for x in (six, b, off, ts.astype(np.uint64))))
+    h_ast = torch.zeros(T, dtype=torch.int32).pin_memory()
+
+    def apply_e2e(i):
+        six_t, b_t, off_t, ts_t = pinned_ticks[i]
+        rc = lib.rsp_apply_many(eng.h, T, six_t.data_ptr(), b_t.data_ptr(), off_t.data_ptr(), ts_t.data_ptr(),
+                                h_ast.data_ptr())
+        assert rc == 0 and int(h_ast.count_nonzero().item()) == 0
 
     for i in range(W):
         apply_e2e(i)
