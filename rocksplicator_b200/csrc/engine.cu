@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/rsp_b200.h"
+#include "group_commit.h"
 #include "kernels.h"
 
 using namespace rsp;
@@ -206,8 +207,19 @@ struct rsp_staged {
   bool identity_order = false;   // packed ticks: staged position == caller's batch index
 };
 
+// one rsp_apply / rsp_write call waiting for its tick
+struct ApplyReq {
+  uint32_t shard_ix;
+  const uint8_t* batch;
+  size_t len;
+  uint64_t ts_ms;
+  bool has_ts;
+  int32_t status;
+};
+
 struct rsp_engine {
   int device = 0;
+  std::unique_ptr<rsp::GroupCommit<ApplyReq>> single_applies;  // combines concurrent rsp_apply / rsp_write callers
   rsp_engine_cfg cfg{};
   std::mutex mu;  // serialises GPU work issued through the ABI
   cudaStream_t st = nullptr;
@@ -803,6 +815,30 @@ static int apply_many_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, 
   return worst;
 }
 
+// leader body of the group commit: one tick for every queued single-update call.  Requests with and without the
+// follower's timestamp record cannot share a tick (the trailer is per tick), so they go as two calls.
+static void run_single_applies(rsp_engine* e, std::vector<ApplyReq*>& batch) {
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  for (int pass = 0; pass < 2; pass++) {
+    const bool want_ts = pass == 0;
+    std::vector<ApplyReq*> part;
+    for (ApplyReq* r : batch) if (r->has_ts == want_ts) part.push_back(r);
+    if (part.empty()) continue;
+    const size_t n = part.size();
+    std::vector<uint32_t> six(n);
+    std::vector<uint64_t> off(n + 1, 0), ts(n);
+    size_t total = 0;
+    for (size_t i = 0; i < n; i++) { six[i] = part[i]->shard_ix; off[i] = total; total += part[i]->len; ts[i] = part[i]->ts_ms; }
+    off[n] = total;
+    std::vector<uint8_t> blob(total + 1);
+    for (size_t i = 0; i < n; i++) if (part[i]->len) memcpy(&blob[off[i]], part[i]->batch, part[i]->len);
+    std::vector<int32_t> st(n, 0);
+    const int rc = apply_many_locked(e, n, six.data(), blob.data(), off.data(), want_ts ? ts.data() : nullptr, st.data());
+    for (size_t i = 0; i < n; i++) part[i]->status = (rc == RSP_INVALID_ARGUMENT && st[i] == 0) ? rc : st[i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side merge folding (operators that do not live on the device)
 // ------------------------------------------------------------------------------------------------
@@ -1108,6 +1144,7 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   e->stage_threads = 2;
   if (const char* t = getenv("RSP_STAGE_THREADS")) e->stage_threads = (size_t)std::max(1, atoi(t));
   CUDA_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  e->single_applies.reset(new rsp::GroupCommit<ApplyReq>([e](std::vector<ApplyReq*>& b) { run_single_applies(e, b); }));
   for (int k = 0; k < 3; k++) {
     CUDA_OK(cudaStreamCreateWithFlags(&e->cs[k], cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&e->cs_done[k], cudaEventDisableTiming));
@@ -1211,26 +1248,20 @@ int rsp_apply_many(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint
 
 int rsp_apply(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t ts_ms, uint64_t* seq_out) {
   if (!s) return RSP_INVALID_ARGUMENT;
-  const uint64_t off[2] = {0, len};
-  const uint32_t six = s->index;
-  int32_t st = 0;
   static const uint8_t empty = 0;
-  int rc = rsp_apply_many(s->eng, 1, &six, batch ? batch : &empty, off, &ts_ms, &st);
-  if (rc == RSP_OK || rc == st) rc = st;
+  ApplyReq r{s->index, batch ? batch : &empty, len, ts_ms, true, 0};
+  s->eng->single_applies->submit(&r);  // concurrent callers share one device tick
   if (seq_out) *seq_out = rsp_latest_seq(s);
-  return rc;
+  return r.status;
 }
 
 int rsp_write(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t* seq_out) {
   if (!s) return RSP_INVALID_ARGUMENT;
-  const uint64_t off[2] = {0, len};
-  const uint32_t six = s->index;
-  int32_t st = 0;
   static const uint8_t empty = 0;
-  int rc = rsp_apply_many(s->eng, 1, &six, batch ? batch : &empty, off, nullptr, &st);
-  if (rc == RSP_OK || rc == st) rc = st;
+  ApplyReq r{s->index, batch ? batch : &empty, len, 0, false, 0};
+  s->eng->single_applies->submit(&r);
   if (seq_out) *seq_out = rsp_latest_seq(s);
-  return rc;
+  return r.status;
 }
 
 int rsp_multi_get(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, const uint64_t* koff,

@@ -16,6 +16,7 @@
 #include <thread>
 #include <vector>
 
+#include "../../rocksplicator_b200/csrc/group_commit.h"
 #include "common/segment_utils.h"
 #include "gpu_db.h"
 #include "rocksdb_admin/application_db_manager.h"
@@ -117,6 +118,42 @@ static void test_write_batch_and_status() {
   EXPECT_EQ(common::SegmentToDbName("seg", 7), std::string("seg00007"));
   EXPECT_EQ(common::DbNameToSegment("seg00007"), std::string("seg"));
   EXPECT_EQ(common::ExtractShardId("seg00042"), 42);
+}
+
+// the batching front-end's core: concurrent single-update callers share device ticks (csrc/group_commit.h)
+static void test_group_commit() {
+  struct Req { int thread, seq; int result; };
+  std::atomic<int> executed{0};
+  std::vector<int> last_seq(16, -1);
+  bool order_ok = true;
+  std::mutex chk;
+  rsp::GroupCommit<Req> gc([&](std::vector<Req*>& batch) {
+    sleep_ms(1);  // a "tick"
+    std::lock_guard<std::mutex> g(chk);
+    for (Req* r : batch) {
+      if (last_seq[r->thread] != r->seq - 1) order_ok = false;  // a caller's requests stay in order
+      last_seq[r->thread] = r->seq;
+      r->result = r->thread * 1000 + r->seq;
+      executed++;
+    }
+  });
+  std::vector<std::thread> th;
+  std::atomic<int> wrong{0};
+  for (int t = 0; t < 16; t++)
+    th.emplace_back([&, t] {
+      for (int i = 0; i < 50; i++) {
+        Req r{t, i, -1};
+        gc.submit(&r);
+        if (r.result != t * 1000 + i) wrong++;
+      }
+    });
+  for (auto& t : th) t.join();
+  EXPECT_EQ(executed.load(), 16 * 50);
+  EXPECT_EQ(wrong.load(), 0);
+  EXPECT_TRUE(order_ok);
+  EXPECT_EQ(gc.requests(), (uint64_t)800);
+  EXPECT_TRUE(gc.batches() < 400);  // combining happened: far fewer ticks than requests
+  printf("  group commit: %llu requests in %llu ticks\n", (unsigned long long)gc.requests(), (unsigned long long)gc.batches());
 }
 
 // ---- a DbWrapper that only counts and logs: rocksdb_replicator/test_db_proxy.cpp's role -------------
@@ -498,6 +535,7 @@ int main(int argc, char** argv) {
       {"max_number_box", test_max_number_box, false},
       {"non_blocking_condition_variable", test_nbcv, false},
       {"write_batch_and_status", test_write_batch_and_status, false},
+      {"group_commit", test_group_commit, false},
       {"replication_protocol_counting", test_replication_protocol_counting, false},
       {"ack_modes_counting", test_ack_modes_counting, false},
       {"gpu_sequence_numbers", test_gpu_sequence_numbers, true},
