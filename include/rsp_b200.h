@@ -67,7 +67,7 @@ typedef struct rsp_engine_cfg {
   uint32_t abi_version;      /* RSP_ABI_VERSION */
   uint32_t max_shards;       /* shard-table capacity on the device (default 16384) */
   uint64_t arena_bytes;      /* device arena slab size (default 1 GiB; grows by slabs) */
-  uint64_t staging_bytes;    /* pinned staging per direction (default 64 MiB; grows) */
+  uint64_t staging_bytes;    /* reserved (pinned staging grows on demand) */
   uint32_t l0_compaction_trigger; /* runs per shard before a merge (rocksdb_options.cpp:82; default 4) */
   uint32_t reserved;
 } rsp_engine_cfg;
@@ -151,7 +151,8 @@ const uint8_t* rsp_iter_key(const rsp_iter* it, size_t* klen);
 const uint8_t* rsp_iter_value(const rsp_iter* it, size_t* vlen);
 int rsp_iter_status(const rsp_iter* it);
 
-/* Batched range scans (BASELINE config 4: Seek + 128 x Next).  Scan i starts at the first key >=
+/* Batched range scans (BASELINE config 4: Seek + 128 x Next).  Memtables of the shards involved are flushed first
+ * (the device form below scans the sorted runs only: call rsp_flush_all before it if memtables are not empty).  Scan i starts at the first key >=
  * start key i and returns up to max_entries live entries in key order.  Output i is a sequence of
  * [u32 klen][u32 vlen][key][value] records at out + i*out_stride; n_out[i] = entries written;
  * st[i] = RSP_INCOMPLETE when out_stride was too small for max_entries (n_out[i] entries are valid). */

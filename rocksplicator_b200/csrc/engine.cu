@@ -432,7 +432,6 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
   for (u32 i = 0; i < nj; i++) {
     rsp_shard* s = jh[i].s;
     u64 read_b = 0;
-    for (u32 k = 0; k < jobs[i].n_src; k++) read_b += 0;  // accounted below from sources
     if (s->h.mt_count) read_b += (u64)s->h.mt_tail * 16;
     for (auto& r : jh[i].srcs) read_b += r->bytes();
     s->stats.compaction_bytes_read += read_b;

@@ -26,3 +26,10 @@ def ref_lib(port_lib):
     if not okv.ref_available():
         pytest.skip("oracle/_ref (the reference's own RocksDB binary) not built here")
     return okv.load_ref()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """librsp_b200.so is built in-tree (nvcc, sm_100a); rebuild only when sources are newer.  No GPU needed."""
+    from rocksplicator_b200 import build
+    build.build()
