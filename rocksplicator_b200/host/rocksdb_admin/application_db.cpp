@@ -1,122 +1,149 @@
-// application_db.cpp — rocksdb_admin/application_db.cpp:52-234 restated over the shim headers.
+// application_db.cpp — the read/write facade of one shard.
+//
+// Behavioural target: rocksdb_admin/application_db.cpp:52-234 in the reference — registration with the
+// replicator on construction (:52-70), de-registration on destruction (:72-76), reads forwarded to the DB with a
+// counter + latency metric each (:78-120, metric names :29-39), writes routed through ReplicatedDB::Write when the
+// shard is replicated (:122-136), the two applicationdb.* properties (:171-225).
 #include "rocksdb_admin/application_db.h"
 
-#include <set>
+#include <algorithm>
 
 #include "common/stats.h"
-
-namespace {
-const std::string kRocksdbNewIterator = "rocksdb_new_iterator";
-const std::string kRocksdbNewIteratorMs = "rocksdb_new_iterator_ms";
-const std::string kRocksdbGet = "rocksdb_get";
-const std::string kRocksdbGetMs = "rocksdb_get_ms";
-const std::string kRocksdbMultiGet = "rocksdb_multi_get";
-const std::string kRocksdbMultiGetMs = "rocksdb_multi_get_ms";
-const std::string kRocksdbWrite = "rocksdb_write";
-const std::string kRocksdbWriteBytes = "rocksdb_write_bytes";
-const std::string kRocksdbWriteMs = "rocksdb_write_ms";
-const std::string kRocksdbCompaction = "rocksdb_compact_range";
-const std::string kRocksdbCompactionMs = "rocksdb_compact_range_ms";
-}  // namespace
 
 namespace admin {
 
 bool FLAGS_disable_rocksplicator_db_stats = false;
-static const std::string rocksdb_prefix = "rocksdb.";
-static const std::string applicationdb_prefix = "applicationdb.";
-const std::string ApplicationDB::Properties::kNumLevels = applicationdb_prefix + "num-levels";
-const std::string ApplicationDB::Properties::kHighestEmptyLevel = applicationdb_prefix + "highest-empty-level";
+
+const std::string ApplicationDB::Properties::kNumLevels = "applicationdb.num-levels";
+const std::string ApplicationDB::Properties::kHighestEmptyLevel = "applicationdb.highest-empty-level";
+
+namespace {
+
+// every facade operation reports "<name>" (count) and "<name>_ms" (latency); Write also "<name>_bytes"
+enum class Op { kNewIterator, kGet, kMultiGet, kWrite, kCompactRange };
+const char* OpName(Op op) {
+  switch (op) {
+    case Op::kNewIterator: return "rocksdb_new_iterator";
+    case Op::kGet: return "rocksdb_get";
+    case Op::kMultiGet: return "rocksdb_multi_get";
+    case Op::kWrite: return "rocksdb_write";
+    case Op::kCompactRange: return "rocksdb_compact_range";
+  }
+  return "rocksdb_unknown";
+}
+
+// counts the call now, records its duration when the scope ends
+class Metered {
+ public:
+  explicit Metered(Op op) : timer_(std::string(OpName(op)) + "_ms") { common::Stats::get()->Incr(OpName(op)); }
+
+ private:
+  common::Timer timer_;
+};
+
+bool HasPrefix(const rocksdb::Slice& s, const char* prefix) { return s.starts_with(rocksdb::Slice(prefix)); }
+
+}  // namespace
 
 ApplicationDB::ApplicationDB(const std::string& db_name, std::shared_ptr<rocksdb::DB> db, replicator::ReplicaRole role,
                              std::unique_ptr<replicator::SocketAddress> upstream_addr,
                              replicator::RocksDBReplicator* repl)
-    : db_name_(db_name), db_(std::move(db)), role_(role), upstream_addr_(std::move(upstream_addr)),
-      replicator_(repl ? repl : replicator::RocksDBReplicator::instance()), replicated_db_(nullptr) {
-  if (!IsSlave() || upstream_addr_) {
-    auto ret = replicator_->addDB(db_name_, db_, role_, upstream_addr_ ? *upstream_addr_ : replicator::SocketAddress(),
-                                  &replicated_db_);
-    if (ret != replicator::ReturnCode::OK) throw ret;
-  }
+    : db_name_(db_name),
+      db_(std::move(db)),
+      role_(role),
+      upstream_addr_(std::move(upstream_addr)),
+      replicator_(repl != nullptr ? repl : replicator::RocksDBReplicator::instance()),
+      replicated_db_(nullptr) {
+  // a follower without an upstream is a plain local DB; everything else joins the replication library
+  const bool standalone = IsSlave() && upstream_addr_ == nullptr;
+  if (standalone) return;
+  const replicator::SocketAddress upstream = upstream_addr_ ? *upstream_addr_ : replicator::SocketAddress();
+  const replicator::ReturnCode rc = replicator_->addDB(db_name_, db_, role_, upstream, &replicated_db_);
+  if (rc != replicator::ReturnCode::OK) throw rc;
 }
 
 ApplicationDB::~ApplicationDB() {
-  if (replicated_db_) replicator_->removeDB(db_name_);
+  if (replicated_db_ != nullptr) replicator_->removeDB(db_name_);
 }
 
 rocksdb::Iterator* ApplicationDB::NewIterator(const rocksdb::ReadOptions& options) {
-  common::Stats::get()->Incr(kRocksdbNewIterator);
-  common::Timer timer(kRocksdbNewIteratorMs);
+  Metered m(Op::kNewIterator);
   return db_->NewIterator(options);
 }
 
-rocksdb::Status ApplicationDB::Get(const rocksdb::ReadOptions& options, const rocksdb::Slice& slice, std::string* value) {
-  // "We need to call Get() nearly 10M times per second" (application_db.cpp:89-91): stats are skippable
-  if (FLAGS_disable_rocksplicator_db_stats) return db_->Get(options, slice, value);
-  common::Stats::get()->Incr(kRocksdbGet);
-  common::Timer timer(kRocksdbGetMs);
-  return db_->Get(options, slice, value);
+// Get is the hottest call of the service ("nearly 10M times per second" in the reference's own comment), so its
+// accounting can be switched off.
+rocksdb::Status ApplicationDB::Get(const rocksdb::ReadOptions& options, const rocksdb::Slice& key, std::string* value) {
+  if (!FLAGS_disable_rocksplicator_db_stats) {
+    Metered m(Op::kGet);
+    return db_->Get(options, key, value);
+  }
+  return db_->Get(options, key, value);
 }
 
 rocksdb::Status ApplicationDB::Get(const rocksdb::ReadOptions& options, const rocksdb::Slice& key,
                                    rocksdb::PinnableSlice* value) {
-  if (FLAGS_disable_rocksplicator_db_stats) return db_->Get(options, db_->DefaultColumnFamily(), key, value);
-  common::Stats::get()->Incr(kRocksdbGet);
-  common::Timer timer(kRocksdbGetMs);
-  return db_->Get(options, db_->DefaultColumnFamily(), key, value);
+  rocksdb::ColumnFamilyHandle* cf = db_->DefaultColumnFamily();
+  if (!FLAGS_disable_rocksplicator_db_stats) {
+    Metered m(Op::kGet);
+    return db_->Get(options, cf, key, value);
+  }
+  return db_->Get(options, cf, key, value);
 }
 
 std::vector<rocksdb::Status> ApplicationDB::MultiGet(const rocksdb::ReadOptions& options,
-                                                     const std::vector<rocksdb::Slice>& slice,
-                                                     std::vector<std::string>* value) {
-  common::Stats::get()->Incr(kRocksdbMultiGet);
-  common::Timer timer(kRocksdbMultiGetMs);
-  return db_->MultiGet(options, slice, value);
+                                                     const std::vector<rocksdb::Slice>& keys,
+                                                     std::vector<std::string>* values) {
+  Metered m(Op::kMultiGet);
+  return db_->MultiGet(options, keys, values);
 }
 
 rocksdb::Status ApplicationDB::Write(const rocksdb::WriteOptions& options, rocksdb::WriteBatch* write_batch) {
-  common::Stats::get()->Incr(kRocksdbWrite);
-  common::Stats::get()->Incr(kRocksdbWriteBytes, write_batch->GetDataSize());
-  common::Timer timer(kRocksdbWriteMs);
-  if (replicated_db_) return replicated_db_->Write(options, write_batch);
-  // un-replicated instance (FOLLOWER without upstream): write the local db (application_db.cpp:129-135)
-  return db_->Write(options, write_batch);
+  Metered m(Op::kWrite);
+  common::Stats::get()->Incr(std::string(OpName(Op::kWrite)) + "_bytes", write_batch->GetDataSize());
+  // replicated shards write through the replication library (leader check, timestamp, ACK modes); a shard that
+  // the manager keeps without replication writes its DB directly
+  return replicated_db_ != nullptr ? replicated_db_->Write(options, write_batch) : db_->Write(options, write_batch);
 }
 
 rocksdb::Status ApplicationDB::CompactRange(const rocksdb::CompactRangeOptions& options, const rocksdb::Slice* begin,
                                             const rocksdb::Slice* end) {
-  common::Stats::get()->Incr(kRocksdbCompaction);
-  common::Timer timer(kRocksdbCompactionMs);
+  Metered m(Op::kCompactRange);
   return db_->CompactRange(options, begin, end);
 }
 
 bool ApplicationDB::GetProperty(const rocksdb::Slice& property, std::string* value) {
-  if (property.starts_with(applicationdb_prefix)) {
-    if (property == rocksdb::Slice(Properties::kHighestEmptyLevel)) { *value = std::to_string(getHighestEmptyLevel()); return true; }
-    if (property == rocksdb::Slice(Properties::kNumLevels)) { *value = std::to_string(db_->NumberLevels()); return true; }
-  } else if (property.starts_with(rocksdb_prefix)) {
-    return db_->GetProperty(property, value);
+  if (HasPrefix(property, "rocksdb.")) return db_->GetProperty(property, value);
+  if (!HasPrefix(property, "applicationdb.")) return false;
+  const std::string name = property.ToString();
+  if (name == Properties::kNumLevels) {
+    *value = std::to_string(db_->NumberLevels());
+    return true;
+  }
+  if (name == Properties::kHighestEmptyLevel) {
+    *value = std::to_string(getHighestEmptyLevel());
+    return true;
   }
   return false;
 }
 
 bool ApplicationDB::DBLmaxEmpty() {
-  std::string num_levels, highest_empty_level;
-  return GetProperty(Properties::kNumLevels, &num_levels) && GetProperty(Properties::kHighestEmptyLevel, &highest_empty_level) &&
-         std::stoi(num_levels) - 1 == std::stoi(highest_empty_level);
+  std::string levels, highest_empty;
+  if (!GetProperty(Properties::kNumLevels, &levels) || !GetProperty(Properties::kHighestEmptyLevel, &highest_empty)) return false;
+  return std::stoi(highest_empty) == std::stoi(levels) - 1;
 }
 
 uint32_t ApplicationDB::getHighestEmptyLevel() {
-  rocksdb::ColumnFamilyMetaData cf_metadata;
-  db_->GetColumnFamilyMetaData(&cf_metadata);
-  std::set<uint32_t> empty_levels;
-  for (const auto& level_meta : cf_metadata.levels)
-    if (level_meta.size == 0) empty_levels.insert((uint32_t)level_meta.level);
-  return empty_levels.empty() ? 0 : *empty_levels.rbegin();
+  rocksdb::ColumnFamilyMetaData meta;
+  db_->GetColumnFamilyMetaData(&meta);
+  uint32_t highest = 0;
+  for (const rocksdb::LevelMetaData& level : meta.levels)
+    if (level.size == 0) highest = std::max(highest, static_cast<uint32_t>(level.level));
+  return highest;
 }
 
 std::string ApplicationDB::Introspect() {
-  if (replicated_db_) return replicated_db_->Introspect();
-  return "__no_replicated_db__";
+  return replicated_db_ != nullptr ? replicated_db_->Introspect() : std::string("__no_replicated_db__");
 }
 
 }  // namespace admin

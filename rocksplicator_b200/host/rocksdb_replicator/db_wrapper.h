@@ -1,21 +1,38 @@
-// db_wrapper.h — THE plugin boundary of the replication library: rocksdb_replicator/db_wrapper.h:6-15.
-// Same four virtuals, same argument meaning.  RocksDbWrapper (rocksdb_wrapper.cpp) is the reference's
-// implementation over rocksdb::DB; GpuDbWrapper (gpu_db_wrapper.h) is ours over the B200 engine;
-// cdc_admin/cdc_application_db.cpp:19-37 and test_db_proxy.cpp are further implementations in the reference.
+// db_wrapper.h — the plugin seam between the replication state machine and whatever stores the data.
+//
+// Interface parity target: replicator::DbWrapper in the reference (rocksdb_replicator/db_wrapper.h:6-15) — the same
+// four operations with the same argument meaning, so that a wrapper written against one compiles against the other.
+// Implementations: GpuDbWrapper (gpu_db_wrapper.h, the B200 engine); in the reference RocksDbWrapper
+// (rocksdb_wrapper.cpp), the CDC observer (cdc_admin/cdc_application_db.cpp:19-37) and TestDBProxy.
 #pragma once
+#include <cstdint>
 #include <memory>
 
 #include "rocksdb/db.h"
 #include "rocksdb_replicator/replicator_types.h"
 
 namespace replicator {
+
 class DbWrapper {
  public:
-  virtual ~DbWrapper() {}
+  using LogIterator = std::unique_ptr<rocksdb::TransactionLogIterator>;
+
+  virtual ~DbWrapper() = default;
+
+  // LEADER side.  Commit a client batch locally (ReplicatedDB::Write has already appended its timestamp record).
   virtual rocksdb::Status WriteToLeader(const rocksdb::WriteOptions& options, rocksdb::WriteBatch* updates) = 0;
-  virtual rocksdb::Status GetUpdatesFromLeader(rocksdb::SequenceNumber seq_number,
-                                               std::unique_ptr<rocksdb::TransactionLogIterator>* iter) = 0;
+
+  // LEADER side.  Open a cursor over committed batches starting at the one that contains `seq_number`
+  // (NotFound when that sequence has not been written yet).
+  virtual rocksdb::Status GetUpdatesFromLeader(rocksdb::SequenceNumber seq_number, LogIterator* iter) = 0;
+
+  // Both sides.  Sequence number of the last committed operation; the follower's resume cursor and the
+  // quantity ACKed back to the leader.
   virtual uint64_t LatestSequenceNumber() = 0;
+
+  // FOLLOWER side.  Apply one replicated update (raw WriteBatch bytes + the leader's timestamp).  false = not
+  // applied; the pull loop backs off and asks for the same sequence again.
   virtual bool HandleReplicateResponse(Update* update) = 0;
 };
+
 }  // namespace replicator
