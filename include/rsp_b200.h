@@ -97,7 +97,8 @@ int rsp_engine_device(const rsp_engine* e);
 /* the engine's CUDA stream (cudaStream_t as void*): lets a caller order its own work / events with it */
 void* rsp_engine_stream(const rsp_engine* e);
 int rsp_shard_open(rsp_engine* e, const char* name, const rsp_shard_opts* opts, rsp_shard** out);
-int rsp_shard_close(rsp_shard* s); /* frees the shard's HBM (removeDB + DB close) */
+int rsp_shard_close(rsp_shard* s); /* frees the shard's HBM (removeDB + DB close); the caller drains its own calls on
+                                     * the shard first, as RocksDBReplicator::removeDB does (rocksdb_replicator.cpp:143-151) */
 uint32_t rsp_shard_index(const rsp_shard* s); /* index used by the batched calls below */
 const char* rsp_shard_name(const rsp_shard* s);
 
@@ -106,7 +107,8 @@ const char* rsp_shard_name(const rsp_shard* s);
  *               WriteBatch(bytes) -> PutLogData(&ts_ms, 8) -> DB::Write(default WriteOptions).
  * rsp_write  == RocksDbWrapper::WriteToLeader (rocksdb_wrapper.cpp:5-8): DB::Write of the batch as is.
  * On success *seq_out (optional) is DB::GetLatestSequenceNumber() after the write.  A failed write
- * leaves the shard unchanged and LATCHES the error for later writes, as RocksDB 5.x does. */
+ * leaves the shard unchanged and LATCHES the error for later writes, as RocksDB 5.x does.
+ * Concurrent callers are group-committed: whoever arrives first runs one device tick for everybody queued. */
 int rsp_apply(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t ts_ms, uint64_t* seq_out);
 int rsp_write(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t* seq_out);
 
