@@ -9,7 +9,9 @@
 #include <random>
 #include <sstream>
 
+#include "common/dbconfig.h"
 #include "rocksdb_replicator/gpu_db_wrapper.h"
+#include "rocksdb_replicator/replicator_stats.h"
 
 namespace replicator {
 
@@ -21,6 +23,11 @@ ReplicatorFlags& Flags() {
 namespace {
 uint64_t NowMs() {
   return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
+}
+// max(flag, per-dataset setting): replicated_db.cpp:131-136
+int EffectiveReplicationMode(const std::string& db_name) {
+  const int cfg = (int)common::DBConfigManager::get()->getReplicationMode(db_name);
+  return std::max(Flags().replicator_replication_mode, cfg);
 }
 uint32_t Rand(uint32_t lo, uint32_t hi) {
   static thread_local std::mt19937 g{std::random_device{}()};
@@ -45,15 +52,20 @@ RocksDBReplicator::ReplicatedDB::~ReplicatedDB() {}
 rocksdb::Status RocksDBReplicator::ReplicatedDB::Write(const rocksdb::WriteOptions& options,
                                                        rocksdb::WriteBatch* updates, rocksdb::SequenceNumber* seq_no) {
   if (role_ == ReplicaRole::FOLLOWER || role_ == ReplicaRole::OBSERVER) throw ReturnCode::WRITE_TO_SLAVE;
+  incCounter(kReplicatorWriteBytes, updates->GetDataSize(), db_name_);
   // the timestamp travels inside the batch (replicated_db.cpp:115-117)
   const uint64_t ms = NowMs();
   updates->PutLogData(rocksdb::Slice(reinterpret_cast<const char*>(&ms), sizeof(ms)));
   auto status = db_wrapper_->WriteToLeader(options, updates);
-  if (!status.ok()) return status;
+  logMetric(kReplicatorWriteToLeaderMs, (int64_t)(NowMs() - ms), db_name_);
+  if (!status.ok()) {
+    incCounter(kReplicatorWriteLeaderFailure, 1, db_name_);
+    return status;
+  }
   cond_var_.notifyAll();  // release the followers' long-polls
   const auto cur_seq_no = db_wrapper_->LatestSequenceNumber();
   if (seq_no) *seq_no = cur_seq_no;
-  switch (Flags().replicator_replication_mode) {
+  switch (EffectiveReplicationMode(db_name_)) {
     case 1:
     case 2: {
       auto s = writeWaitFollowerACK(cur_seq_no);
@@ -63,24 +75,29 @@ rocksdb::Status RocksDBReplicator::ReplicatedDB::Write(const rocksdb::WriteOptio
     default:
       break;
   }
+  incCounter(kReplicatorWriteSuccess, 1, db_name_);
   return status;
 }
 
 rocksdb::Status RocksDBReplicator::ReplicatedDB::writeWaitFollowerACK(uint64_t cur_seq_no) {
   const auto& F = Flags();
   if (!max_seq_no_acked_.wait(cur_seq_no, current_replicator_timeout_ms_.load())) {
+    incCounter(kReplicatorWriteWaitTimedOut, 1, db_name_);
     numConsecutiveReplTimeout_++;
     // degrade to a short timeout after a run of timeouts, to fail fast (replicated_db.cpp:245-259)
     if (numConsecutiveReplTimeout_.load() >= F.replicator_consecutive_ack_timeout_before_degradation &&
         current_replicator_timeout_ms_.load() == F.replicator_timeout_ms &&
         F.replicator_timeout_degraded_ms < F.replicator_timeout_ms && F.replicator_timeout_degraded_ms >= kMinReplTimeoutMs) {
       current_replicator_timeout_ms_.store((uint32_t)F.replicator_timeout_degraded_ms);
+      incCounter(kReplicatorWriteTwoAckDegraded, 1, db_name_);
     }
     return rocksdb::Status::TimedOut("Failed to receive ack from follower");
   }
   numConsecutiveReplTimeout_.store(0);
-  if (current_replicator_timeout_ms_.load() != F.replicator_timeout_ms)
+  if (current_replicator_timeout_ms_.load() != F.replicator_timeout_ms) {
     current_replicator_timeout_ms_.store((uint32_t)F.replicator_timeout_ms);
+    incCounter(kReplicatorWriteTwoAckRecovered, 1, db_name_);
+  }
   return rocksdb::Status::OK();
 }
 
@@ -119,6 +136,7 @@ void RocksDBReplicator::ReplicatedDB::pullFromUpstream() {
   req.max_wait_ms = Flags().replicator_max_server_wait_time_ms;
   req.max_updates = Flags().replicator_max_updates_per_response;
   req.set_role(role_);
+  incCounter(kReplicatorPullRequests, 1, db_name_);
   SocketAddress up;
   {
     std::lock_guard<std::mutex> g(upstream_mu_);
@@ -138,24 +156,41 @@ void RocksDBReplicator::ReplicatedDB::pullFromUpstream() {
     bool delay_next_pull = false;
     if (!t.ok) {
       delay_next_pull = true;
-      if (t.is_replicate_exception && t.ex.code == ErrorCode::SOURCE_NOT_FOUND) db->resetUpstream();
+      incCounter(kReplicatorPullRequestsFailure, 1, db->db_name_);
+      if (t.is_replicate_exception) {
+        incCounter(kReplicatorRemoteApplicationExceptions, 1, db->db_name_);
+        if (t.ex.code == ErrorCode::SOURCE_NOT_FOUND) db->resetUpstream();
+      } else {
+        incCounter(kReplicatorConnectionErrors, 1, db->db_name_);
+      }
     } else {
+      incCounter(kReplicatorPullRequestsSuccess, 1, db->db_name_);
       auto& response = t.response;
+      uint64_t in_bytes = 0;
+      const uint64_t now = NowMs();
       for (auto& update : response.updates) {
         // THE HOT LOOP (replicated_db.cpp:369-383): one DbWrapper call per update, in order
+        if (update.timestamp != 0)
+          logMetric(kReplicatorLatency, (uint64_t)update.timestamp < now ? (int64_t)(now - (uint64_t)update.timestamp) : 0, db->db_name_);
+        in_bytes += update.raw_data.size();
         if (!db->db_wrapper_->HandleReplicateResponse(&update)) {
+          incCounter(kReplicatorHandleResponseFailure, 1, db->db_name_);
           delay_next_pull = true;
           break;
         }
       }
+      incCounter(kReplicatorInBytes, in_bytes, db->db_name_);
+      if (response.has_role && response.role != ReplicaRole::LEADER) incCounter(kReplicatorPullFromNonLeader, 1, db->db_name_);
       if (!response.updates.empty()) {
         db->pullFromUpstreamNoUpdates_ = 0;
         db->cond_var_.notifyAll();  // chained followers long-polling on us
       } else {
+        incCounter(kReplicatorPullRequestsNoUpdates, 1, db->db_name_);
         db->pullFromUpstreamNoUpdates_++;
         if (response.has_role && response.role != ReplicaRole::LEADER &&
             Flags().reset_upstream_on_empty_updates_from_non_leader &&
             db->pullFromUpstreamNoUpdates_ >= (uint32_t)Flags().replicator_max_consecutive_no_updates_before_upstream_reset) {
+          incCounter(kReplicatorResetUpstreamOnNoUpdates, 1, db->db_name_);
           db->resetUpstream();
           db->pullFromUpstreamNoUpdates_ = 0;
         }
@@ -179,8 +214,11 @@ void RocksDBReplicator::ReplicatedDB::handleReplicateRequest(std::unique_ptr<Rep
   std::weak_ptr<ReplicatedDB> weak_db = db;
   const auto seq_no = static_cast<rocksdb::SequenceNumber>(request->seq_no);
   // the follower's request carries the largest sequence number it has committed: that is the ACK
-  if (!(request->has_role && request->role == ReplicaRole::OBSERVER)) max_seq_no_acked_.post(seq_no);
-  const int replication_mode = Flags().replicator_replication_mode;
+  const uint64_t leader_seq = db_wrapper_->LatestSequenceNumber();
+  if (leader_seq < seq_no) logMetric(kReplicatorLeaderSequenceNumbersBehind, (int64_t)(seq_no - leader_seq), db_name_);
+  if (request->has_role && request->role == ReplicaRole::OBSERVER) incCounter(kReplicatorHandleObserverRequests, 1, db_name_);
+  else max_seq_no_acked_.post(seq_no);
+  const int replication_mode = EffectiveReplicationMode(db_name_);
   const uint64_t timeout = (uint64_t)request->max_wait_ms;
   std::shared_ptr<ReplicateRequest> req(std::move(request));
   auto cb = std::make_shared<ReplicateCallback>(std::move(callback));
@@ -219,10 +257,15 @@ void RocksDBReplicator::ReplicatedDB::handleReplicateRequest(std::unique_ptr<Rep
             update.timestamp = ret.ok() ? (int64_t)extractor.ms : 0;
             out.response.updates.emplace_back(std::move(update));
           }
+          uint64_t out_bytes = 0;
+          for (const auto& u : out.response.updates) out_bytes += u.raw_data.size();
+          logMetric(kReplicatorOutNumUpdates, (int64_t)out.response.updates.size(), db->db_name_);
+          incCounter(kReplicatorOutBytes, out_bytes, db->db_name_);
           (*cb)(std::move(out));
           if (replication_mode == 1) db->max_seq_no_acked_.post(next_seq_no - 1);
         } else {
           out.is_replicate_exception = true;
+          incCounter(kReplicatorGetUpdatesSinceErrors, 1, db->db_name_);
           out.ex.code = ErrorCode::SOURCE_READ_ERROR;
           out.ex.msg = status.ToString();
           (*cb)(std::move(out));

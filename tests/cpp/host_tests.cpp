@@ -17,7 +17,10 @@
 #include <vector>
 
 #include "../../rocksplicator_b200/csrc/group_commit.h"
+#include "common/dbconfig.h"
 #include "common/segment_utils.h"
+#include "common/stats.h"
+#include "rocksdb_replicator/replicator_stats.h"
 #include "gpu_db.h"
 #include "rocksdb_admin/application_db_manager.h"
 #include "rocksdb_replicator/rocksdb_replicator.h"
@@ -280,6 +283,44 @@ static void test_ack_modes_counting() {
   fast_flags();
 }
 
+// common/dbconfig: per-dataset ack mode from the reference's JSON document; max(flag, dataset) is what Write uses
+static void test_dbconfig_and_stats() {
+  fast_flags();
+  auto* cfg = common::DBConfigManager::get();
+  cfg->clear();
+  EXPECT_EQ(cfg->getReplicationMode("seg00001"), 0u);
+  EXPECT_TRUE(cfg->loadJsonText("{\"dataset\": {\"seg\": {\"ack_mode\": 2, \"other\": [1, {\"x\": null}]}, \"b\": {\"ack_mode\": 1}}, \"v\": \"1\"}"));
+  EXPECT_EQ(cfg->getReplicationMode("seg00001"), 2u);
+  EXPECT_EQ(cfg->getReplicationMode("b00042"), 1u);
+  EXPECT_EQ(cfg->getReplicationMode("zzz00001", 7), 7u);
+  EXPECT_TRUE(!cfg->loadJsonText("{\"dataset\": {\"seg\": {\"ack_mode\": }}}"));  // malformed: config unchanged
+  EXPECT_EQ(cfg->getReplicationMode("seg00001"), 2u);
+  // dataset "seg" is in 2-ACK mode through the config alone (flag stays 0): a leader without followers times out
+  Flags().replicator_timeout_ms = 100;
+  const uint64_t timed_out_before = common::Stats::get()->GetCounter(kReplicatorWriteWaitTimedOut);
+  const uint64_t success_before = common::Stats::get()->GetCounter(kReplicatorWriteSuccess);
+  {
+    RocksDBReplicator host(19141);
+    auto db = std::make_shared<CountingDb>(), db2 = std::make_shared<CountingDb>();
+    RocksDBReplicator::ReplicatedDB *r = nullptr, *r2 = nullptr;
+    host.addDB("seg00001", std::static_pointer_cast<DbWrapper>(db), ReplicaRole::LEADER, SocketAddress(), &r);
+    host.addDB("plain00001", std::static_pointer_cast<DbWrapper>(db2), ReplicaRole::LEADER, SocketAddress(), &r2);
+    WriteBatch b; b.Put("k", "v");
+    EXPECT_TRUE(r->Write(rocksdb::WriteOptions(), &b).IsTimedOut());
+    WriteBatch b2; b2.Put("k", "v");
+    EXPECT_TRUE(r2->Write(rocksdb::WriteOptions(), &b2).ok());  // other datasets stay in mode 0
+    host.removeDB("seg00001"); host.removeDB("plain00001");
+  }
+  EXPECT_EQ(common::Stats::get()->GetCounter(kReplicatorWriteWaitTimedOut), timed_out_before + 1);
+  EXPECT_EQ(common::Stats::get()->GetCounter(kReplicatorWriteSuccess), success_before + 1);
+  EXPECT_TRUE(common::Stats::get()->GetCounter(kReplicatorWriteBytes) > 0);
+  StatFlags().replicator_enable_per_dataset_stats = true;
+  EXPECT_EQ(TaggedName(kReplicatorPullRequests, "seg00007"), std::string("replicator_pull_requests dataset=seg"));
+  StatFlags().replicator_enable_per_dataset_stats = false;
+  cfg->clear();
+  fast_flags();
+}
+
 // ---- GPU-backed: the DB below the seam is the B200 engine -----------------------------------------------
 class CounterMergeOperator : public rocksdb::AssociativeMergeOperator {  // examples/counter_service/merge_operator.cpp
  public:
@@ -538,6 +579,7 @@ int main(int argc, char** argv) {
       {"group_commit", test_group_commit, false},
       {"replication_protocol_counting", test_replication_protocol_counting, false},
       {"ack_modes_counting", test_ack_modes_counting, false},
+      {"dbconfig_and_stats", test_dbconfig_and_stats, false},
       {"gpu_sequence_numbers", test_gpu_sequence_numbers, true},
       {"gpu_replication_chain", test_gpu_replication_chain, true},
       {"gpu_follower_equals_leader", test_gpu_follower_equals_leader, true},
