@@ -102,6 +102,22 @@ FN(void, rocksdb_flushoptions_destroy, (rocksdb_flushoptions_t*));
 FN(void, rocksdb_flushoptions_set_wait, (rocksdb_flushoptions_t*, unsigned char));
 FN(void, rocksdb_flush, (rocksdb_t*, const rocksdb_flushoptions_t*, char**));
 FN(void, rocksdb_compact_range, (rocksdb_t*, const char*, size_t, const char*, size_t));
+typedef struct rocksdb_envoptions_t rocksdb_envoptions_t;
+typedef struct rocksdb_sstfilewriter_t rocksdb_sstfilewriter_t;
+typedef struct rocksdb_ingestexternalfileoptions_t rocksdb_ingestexternalfileoptions_t;
+FN(rocksdb_envoptions_t*, rocksdb_envoptions_create, (void));
+FN(void, rocksdb_envoptions_destroy, (rocksdb_envoptions_t*));
+FN(rocksdb_sstfilewriter_t*, rocksdb_sstfilewriter_create, (const rocksdb_envoptions_t*, const rocksdb_options_t*));
+FN(void, rocksdb_sstfilewriter_open, (rocksdb_sstfilewriter_t*, const char*, char**));
+FN(void, rocksdb_sstfilewriter_add, (rocksdb_sstfilewriter_t*, const char*, size_t, const char*, size_t, char**));
+FN(void, rocksdb_sstfilewriter_finish, (rocksdb_sstfilewriter_t*, char**));
+FN(void, rocksdb_sstfilewriter_destroy, (rocksdb_sstfilewriter_t*));
+FN(rocksdb_ingestexternalfileoptions_t*, rocksdb_ingestexternalfileoptions_create, (void));
+FN(void, rocksdb_ingestexternalfileoptions_destroy, (rocksdb_ingestexternalfileoptions_t*));
+FN(void, rocksdb_ingestexternalfileoptions_set_move_files, (rocksdb_ingestexternalfileoptions_t*, unsigned char));
+FN(void, rocksdb_ingestexternalfileoptions_set_allow_global_seqno, (rocksdb_ingestexternalfileoptions_t*, unsigned char));
+FN(void, rocksdb_ingestexternalfileoptions_set_allow_blocking_flush, (rocksdb_ingestexternalfileoptions_t*, unsigned char));
+FN(void, rocksdb_ingest_external_file, (rocksdb_t*, const char* const*, size_t, const rocksdb_ingestexternalfileoptions_t*, char**));
 /* not in the C API: DBImpl::GetLatestSequenceNumber() const, called on *(DB**)rocksdb_t
  * (rocksdb_t is struct { DB* rep; }) — the call rocksdb_wrapper.cpp:4 makes */
 static uint64_t (*p_latest_seq)(const void*);
@@ -168,6 +184,12 @@ static void load_all(void) {
   LD(rocksdb_iter_key); LD(rocksdb_iter_value); LD(rocksdb_iter_get_error);
   LD(rocksdb_flushoptions_create); LD(rocksdb_flushoptions_destroy); LD(rocksdb_flushoptions_set_wait);
   LD(rocksdb_flush); LD(rocksdb_compact_range);
+  LD(rocksdb_envoptions_create); LD(rocksdb_envoptions_destroy); LD(rocksdb_sstfilewriter_create);
+  LD(rocksdb_sstfilewriter_open); LD(rocksdb_sstfilewriter_add); LD(rocksdb_sstfilewriter_finish);
+  LD(rocksdb_sstfilewriter_destroy); LD(rocksdb_ingestexternalfileoptions_create);
+  LD(rocksdb_ingestexternalfileoptions_destroy); LD(rocksdb_ingestexternalfileoptions_set_move_files);
+  LD(rocksdb_ingestexternalfileoptions_set_allow_global_seqno);
+  LD(rocksdb_ingestexternalfileoptions_set_allow_blocking_flush); LD(rocksdb_ingest_external_file);
   *(void**)(&p_latest_seq) = dlsym(h, "_ZNK7rocksdb6DBImpl23GetLatestSequenceNumberEv");
   if (!p_latest_seq) {
     snprintf(g_load_err, sizeof(g_load_err), "dlsym DBImpl::GetLatestSequenceNumber failed");
@@ -454,4 +476,39 @@ int okv_flush(okv_db* d) {
 int okv_compact(okv_db* d) {
   p_rocksdb_compact_range(d->db, NULL, 0, NULL, 0); /* CompactRange(nullptr, nullptr) */
   return OKV_OK;
+}
+
+/* ---- SST interchange (reference-only extras used by tests/test_sst_cpu.py) --------------------------------------
+ * okv_write_sst: RocksDB's own SstFileWriter (rocksdb_assumption_test.cpp:209-243) -> an external SST file.
+ * okv_ingest_sst: DB::IngestExternalFile (rocksdb_admin/tests/sst_binary.cpp:64-72, admin_handler.cpp:1820-1845). */
+int okv_write_sst(const char* path, size_t n, const uint8_t* keys, const uint64_t* koff, const uint8_t* vals,
+                  const uint64_t* voff, char* err, size_t errcap) {
+  pthread_once(&g_once, load_all);
+  if (!g_loaded) { if (err && errcap) snprintf(err, errcap, "%s", g_load_err); return OKV_IO_ERROR; }
+  rocksdb_options_t* o = p_rocksdb_options_create();
+  p_rocksdb_options_set_compression(o, 0);
+  rocksdb_envoptions_t* eo = p_rocksdb_envoptions_create();
+  rocksdb_sstfilewriter_t* w = p_rocksdb_sstfilewriter_create(eo, o);
+  char* e = NULL;
+  p_rocksdb_sstfilewriter_open(w, path, &e);
+  for (size_t i = 0; i < n && !e; i++)
+    p_rocksdb_sstfilewriter_add(w, (const char*)keys + koff[i], (size_t)(koff[i + 1] - koff[i]), (const char*)vals + voff[i],
+                                (size_t)(voff[i + 1] - voff[i]), &e);
+  if (!e) p_rocksdb_sstfilewriter_finish(w, &e);
+  p_rocksdb_sstfilewriter_destroy(w);
+  p_rocksdb_envoptions_destroy(eo);
+  p_rocksdb_options_destroy(o);
+  return take_err(e, err, errcap);
+}
+
+int okv_ingest_sst(okv_db* d, const char* path, int allow_global_seqno, char* err, size_t errcap) {
+  rocksdb_ingestexternalfileoptions_t* io = p_rocksdb_ingestexternalfileoptions_create();
+  p_rocksdb_ingestexternalfileoptions_set_move_files(io, 0);
+  p_rocksdb_ingestexternalfileoptions_set_allow_global_seqno(io, allow_global_seqno ? 1 : 0);
+  p_rocksdb_ingestexternalfileoptions_set_allow_blocking_flush(io, allow_global_seqno ? 1 : 0);
+  const char* files[1] = {path};
+  char* e = NULL;
+  p_rocksdb_ingest_external_file(d->db, files, 1, io, &e);
+  p_rocksdb_ingestexternalfileoptions_destroy(io);
+  return take_err(e, err, errcap);
 }
