@@ -170,6 +170,14 @@ int rsp_flush_all(rsp_engine* e);
 int rsp_compact_all(rsp_engine* e);
 int rsp_get_stats(const rsp_shard* s, rsp_stats* out);
 
+/* ---- bulk load: DB::IngestExternalFile for n sorted Puts (rocksdb_admin/admin_handler.cpp:1820-1845) -----------
+ * Key i is keys[koff[i] .. koff[i+1]) (strictly increasing), value i vals[voff[i] .. voff[i+1]).  The keys become one
+ * new sorted run.  Sequence numbers follow rocksdb_replicator/tests/rocksdb_assumption_test.cpp:248-283: unchanged when
+ * the key range does not intersect existing data, +1 (the file's global sequence number) when it does — refused with
+ * InvalidArgument unless allow_global_seqno.  host/sst/sst_format.h turns an SST file into these arrays. */
+int rsp_ingest_sorted(rsp_shard* s, size_t n, const uint8_t* keys, const uint64_t* koff, const uint8_t* vals,
+                      const uint64_t* voff, int allow_global_seqno, uint64_t* seq_out);
+
 /* ---- device-pointer forms (kernel-level measurement; inputs/outputs already in HBM) -------------
  * `stream` is a cudaStream_t passed as void* (0 = the engine's own read stream).  No host
  * synchronisation is performed; the caller owns ordering and timing. */

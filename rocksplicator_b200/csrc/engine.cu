@@ -1181,10 +1181,7 @@ void rsp_engine_destroy(rsp_engine* e) {
 int rsp_engine_device(const rsp_engine* e) { return e->device; }
 void* rsp_engine_stream(const rsp_engine* e) { return (void*)e->st; }
 
-int rsp_shard_open(rsp_engine* e, const char* name, const rsp_shard_opts* opts, rsp_shard** out) {
-  if (!e || !name || !out) return RSP_INVALID_ARGUMENT;
-  std::lock_guard<std::mutex> g(e->mu);
-  CUDA_OK(cudaSetDevice(e->device));
+static int shard_open_locked(rsp_engine* e, const char* name, const rsp_shard_opts* opts, rsp_shard** out) {
   if (e->by_name.count(name)) return RSP_INVALID_ARGUMENT;
   u32 ix = 0;
   while (ix < e->slots.size() && e->slots[ix]) ix++;
@@ -1206,11 +1203,9 @@ int rsp_shard_open(rsp_engine* e, const char* name, const rsp_shard_opts* opts, 
   return RSP_OK;
 }
 
-int rsp_shard_close(rsp_shard* s) {
-  if (!s) return RSP_INVALID_ARGUMENT;
+static void shard_close_locked(rsp_shard* s) {
   rsp_engine* e = s->eng;
-  std::lock_guard<std::mutex> g(e->mu);
-  CUDA_OK(cudaSetDevice(e->device));
+  wait_readers(e);
   CUDA_OK(cudaStreamSynchronize(e->st));
   e->slots[s->index] = nullptr;
   e->by_name.erase(s->name);
@@ -1223,7 +1218,127 @@ int rsp_shard_close(rsp_shard* s) {
   e->arena.release(s->h.mt_ent_off, s->mt_ent_bytes);
   s->runs.clear();
   delete s;
+}
+
+int rsp_shard_open(rsp_engine* e, const char* name, const rsp_shard_opts* opts, rsp_shard** out) {
+  if (!e || !name || !out) return RSP_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  return shard_open_locked(e, name, opts, out);
+}
+
+int rsp_shard_close(rsp_shard* s) {
+  if (!s) return RSP_INVALID_ARGUMENT;
+  rsp_engine* e = s->eng;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  shard_close_locked(s);
   return RSP_OK;
+}
+
+// first / last user key of a run (two small copies: the run is immutable)
+static void run_key_range(rsp_engine* e, const Run& r, std::string* first, std::string* last) {
+  auto key_at = [&](u32 unit, std::string* out) {
+    u32 hd[4];
+    CUDA_OK(cudaMemcpy(hd, r.heap + (size_t)unit * 16, 16, cudaMemcpyDeviceToHost));
+    out->resize(hd[2]);
+    if (hd[2]) CUDA_OK(cudaMemcpy(&(*out)[0], r.heap + (size_t)unit * 16 + 16, hd[2], cudaMemcpyDeviceToHost));
+  };
+  key_at(0, first);
+  u32 last_unit = 0;
+  CUDA_OK(cudaMemcpy(&last_unit, r.ent_off + (r.n_ent - 1), 4, cudaMemcpyDeviceToHost));
+  key_at(last_unit, last);
+  (void)e;
+}
+
+// DB::IngestExternalFile for a sorted set of Puts (rocksdb_admin/admin_handler.cpp:1820-1845, sequence rules of
+// rocksdb_replicator/tests/rocksdb_assumption_test.cpp:248-283): the keys become ONE new sorted run.  When its key
+// range intersects existing data the run is newer than everything and the shard's sequence number advances by one
+// (refused unless allow_global_seqno); otherwise the sequence number does not move.  The run is produced by the
+// ordinary apply + flush kernels on a scratch shard and then handed to the target (sequence numbers inside runs are
+// not consulted by reads: recency is the run order).
+int rsp_ingest_sorted(rsp_shard* s, size_t n, const uint8_t* keys, const uint64_t* koff, const uint8_t* vals,
+                      const uint64_t* voff, int allow_global_seqno, uint64_t* seq_out) {
+  if (!s || !n || !keys || !koff || !voff) return RSP_INVALID_ARGUMENT;
+  rsp_engine* e = s->eng;
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  auto key = [&](size_t i) { return std::string((const char*)keys + koff[i], (size_t)(koff[i + 1] - koff[i])); };
+  for (size_t i = 1; i < n; i++) {
+    const size_t al = (size_t)(koff[i] - koff[i - 1]), bl = (size_t)(koff[i + 1] - koff[i]);
+    const int c = memcmp(keys + koff[i - 1], keys + koff[i], std::min(al, bl));
+    if (c > 0 || (c == 0 && al >= bl)) { set_err(s, "Invalid argument: Keys must be added in order"); return RSP_INVALID_ARGUMENT; }
+  }
+  if (s->latch) return (int)(s->latch >> 8);
+  // everything the shard holds must be in runs before ranges are compared
+  if (s->h.mt_count) compact_shards(e, {s}, false);
+  if (s->runs.size() + 1 > RSP_MAX_RUNS) compact_shards(e, {s}, true);
+  const std::string lo = key(0), hi = key(n - 1);
+  bool overlap = false;
+  for (auto& r : s->runs) {
+    if (!r->n_ent) continue;
+    std::string rf, rl;
+    run_key_range(e, *r, &rf, &rl);
+    if (!(hi < rf) && !(rl < lo)) { overlap = true; break; }
+  }
+  if (overlap && !allow_global_seqno) {
+    set_err(s, "Invalid argument: Global seqno is required, but disabled");
+    return RSP_INVALID_ARGUMENT;
+  }
+  // build the run on a scratch shard with the ordinary apply + flush path
+  rsp_shard* tmp = nullptr;
+  rsp_shard_opts so;
+  memset(&so, 0, sizeof(so));
+  size_t payload = (size_t)koff[n] + (size_t)voff[n];
+  so.write_buffer_bytes = payload + n * 64 + (1u << 20);
+  static std::atomic<u64> ctr{0};
+  const std::string tname = "__ingest_" + std::to_string(ctr++);
+  int rc = shard_open_locked(e, tname.c_str(), &so, &tmp);
+  if (rc != RSP_OK) return rc;
+  const size_t CH = 1u << 16;
+  for (size_t c0 = 0; c0 < n && rc == RSP_OK; c0 += CH) {
+    const size_t cn = std::min(CH, n - c0);
+    std::string blob;
+    std::vector<uint64_t> off(cn + 1, 0);
+    std::vector<uint32_t> six(cn, tmp->index);
+    for (size_t i = 0; i < cn; i++) {
+      const std::string k = key(c0 + i);
+      const size_t vl = (size_t)(voff[c0 + i + 1] - voff[c0 + i]);
+      off[i] = blob.size();
+      blob.append(8, '\0');
+      const uint32_t one = 1;
+      blob.append((const char*)&one, 4);
+      blob.push_back(0x1);
+      for (uint32_t v = (uint32_t)k.size(); ; v >>= 7) { if (v >= 128) blob.push_back((char)((v & 127) | 128)); else { blob.push_back((char)v); break; } }
+      blob.append(k);
+      for (uint32_t v = (uint32_t)vl; ; v >>= 7) { if (v >= 128) blob.push_back((char)((v & 127) | 128)); else { blob.push_back((char)v); break; } }
+      blob.append((const char*)vals + voff[c0 + i], vl);
+    }
+    off[cn] = blob.size();
+    blob.push_back('\0');
+    std::vector<int32_t> st(cn, 0);
+    rc = apply_many_locked(e, cn, six.data(), (const uint8_t*)blob.data(), off.data(), nullptr, st.data());
+  }
+  if (rc == RSP_OK) {
+    compact_shards(e, {tmp}, false);
+    if (tmp->runs.size() > 1) compact_shards(e, {tmp}, true);
+    if (!tmp->runs.empty()) {
+      s->runs.insert(s->runs.begin(), tmp->runs[0]);
+      tmp->runs.clear();
+    }
+    if (overlap) {
+      const u64 seq = s->last_seq.load() + 1;
+      s->h.last_seq = seq;
+      s->h.pub_seq = seq;
+      s->last_seq.store(seq, std::memory_order_release);
+    }
+    upload_shard(e, s);
+    note_mutation(e);
+    CUDA_OK(cudaStreamSynchronize(e->st));
+  }
+  shard_close_locked(tmp);
+  if (seq_out) *seq_out = s->last_seq.load();
+  return rc;
 }
 
 uint32_t rsp_shard_index(const rsp_shard* s) { return s->index; }

@@ -76,6 +76,8 @@ EXPORTS = {
     "rsp_flush_all": (C.c_int, [C.c_void_p]),
     "rsp_compact_all": (C.c_int, [C.c_void_p]),
     "rsp_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "rsp_ingest_sorted": (C.c_int, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int,
+                                    C.POINTER(C.c_uint64)]),
     "rsp_multi_get_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rsp_multi_scan_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
@@ -225,6 +227,18 @@ class Shard:
 
     def flush(self): return self.lib.rsp_flush(self.h)
     def compact(self): return self.lib.rsp_compact(self.h)
+
+    def ingest(self, sorted_kv, allow_global_seqno=True) -> int:
+        """DB::IngestExternalFile for sorted (key, value) pairs (see rocksplicator_b200/sst.py for SST files)"""
+        n = len(sorted_kv)
+        koff = np.zeros(n + 1, dtype=np.uint64)
+        voff = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(np.fromiter((len(k) for k, _ in sorted_kv), dtype=np.uint64, count=n), out=koff[1:])
+        np.cumsum(np.fromiter((len(v) for _, v in sorted_kv), dtype=np.uint64, count=n), out=voff[1:])
+        keys = b"".join(k for k, _ in sorted_kv) + b"\0"
+        vals = b"".join(v for _, v in sorted_kv) + b"\0"
+        return self.lib.rsp_ingest_sorted(self.h, n, keys, koff.ctypes.data, vals, voff.ctypes.data,
+                                          1 if allow_global_seqno else 0, None)
 
     def stats(self):
         st = Stats()
