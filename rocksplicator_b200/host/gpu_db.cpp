@@ -2,8 +2,12 @@
 // rocksdb_admin/application_db.cpp:78-144.
 #include "gpu_db.h"
 
+#include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <map>
+
+#include "sst/sst_format.h"
 
 namespace b200 {
 
@@ -105,6 +109,79 @@ Status GpuDB::Write(const rocksdb::WriteOptions&, rocksdb::WriteBatch* updates) 
     updates->SetSequence(first);
     LogAppend(first, std::move(bytes), count);
   }
+  return Status::OK();
+}
+
+namespace {
+bool ReadWholeFile(const std::string& path, std::string* out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  char buf[1 << 16];
+  size_t n;
+  out->clear();
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) out->append(buf, n);
+  fclose(f);
+  return true;
+}
+}  // namespace
+
+Status GpuDB::IngestExternalFile(const std::vector<std::string>& files, const rocksdb::IngestExternalFileOptions& opt) {
+  if (files.empty()) return Status::InvalidArgument("external_files is empty");
+  struct Parsed { std::vector<sst::Entry> entries; };
+  std::vector<Parsed> parsed(files.size());
+  for (size_t i = 0; i < files.size(); i++) {
+    std::string bytes, err;
+    if (!ReadWholeFile(files[i], &bytes)) return Status::IOError("While opening a file for sequentially reading: " + files[i]);
+    sst::Props props;
+    if (!sst::ReadSst(bytes, &parsed[i].entries, &props, &err)) return Status::Corruption(err);
+    if (props.external_version == 0) return Status::InvalidArgument("External file version not found");
+    if (parsed[i].entries.empty()) return Status::InvalidArgument("Can't ingest empty file: " + files[i]);
+    for (const auto& e : parsed[i].entries) {
+      if (e.type != 1) return Status::NotSupported("external file holds a record that is not a Put");
+      if (e.seq != 0) return Status::Corruption("external file have non zero sequence number");
+    }
+  }
+  // several files: their ranges must be disjoint; together they are one sorted run with one sequence number
+  std::sort(parsed.begin(), parsed.end(),
+            [](const Parsed& a, const Parsed& b) { return a.entries.front().user_key < b.entries.front().user_key; });
+  for (size_t i = 1; i < parsed.size(); i++)
+    if (!(parsed[i - 1].entries.back().user_key < parsed[i].entries.front().user_key))
+      return Status::NotSupported("Files have overlapping ranges");
+  std::string keys, vals;
+  std::vector<uint64_t> koff(1, 0), voff(1, 0);
+  for (const auto& p : parsed)
+    for (const auto& e : p.entries) {
+      keys += e.user_key;
+      vals += e.value;
+      koff.push_back(keys.size());
+      voff.push_back(vals.size());
+    }
+  keys.push_back('\0');
+  vals.push_back('\0');
+  std::lock_guard<std::mutex> g(write_mu_);
+  const int rc = rsp_ingest_sorted(shard_, koff.size() - 1, (const uint8_t*)keys.data(), koff.data(), (const uint8_t*)vals.data(),
+                                   voff.data(), opt.allow_global_seqno ? 1 : 0, nullptr);
+  if (rc != RSP_OK) return ToStatus(rc);
+  if (opt.move_files)
+    for (const auto& f : files) remove(f.c_str());  // the data now lives in HBM; a moved file is gone from its old place
+  return Status::OK();
+}
+
+Status GpuDB::ExportSstFile(const std::string& path, uint64_t* entries) {
+  std::vector<std::pair<std::string, std::string>> kv;
+  {
+    std::unique_ptr<rocksdb::Iterator> it(NewIterator(rocksdb::ReadOptions()));
+    for (it->SeekToFirst(); it->Valid(); it->Next()) kv.emplace_back(it->key().ToString(), it->value().ToString());
+    if (!it->status().ok()) return it->status();
+  }
+  if (kv.empty()) return Status::InvalidArgument("nothing to export: " + name_);
+  std::string file, err;
+  if (!sst::WriteSst(kv, &file, &err)) return Status::InvalidArgument(err);
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return Status::IOError("While open a file for appending: " + path);
+  const size_t w = fwrite(file.data(), 1, file.size(), f);
+  if (fclose(f) != 0 || w != file.size()) return Status::IOError("While appending to file: " + path);
+  if (entries) *entries = kv.size();
   return Status::OK();
 }
 

@@ -41,6 +41,14 @@ class GpuDB : public rocksdb::DB {
   rocksdb::Status CompactRange(const rocksdb::CompactRangeOptions& options, const rocksdb::Slice* begin,
                                const rocksdb::Slice* end) override;
   rocksdb::Status Flush(const rocksdb::FlushOptions& options) override;
+  // bulk load of SstFileWriter output (rocksdb_admin/admin_handler.cpp:1820-1845): the files are parsed on the host
+  // (sst/sst_format.h) and become ONE new sorted run on the device; sequence rules of
+  // rocksdb_replicator/tests/rocksdb_assumption_test.cpp:248-283
+  rocksdb::Status IngestExternalFile(const std::vector<std::string>& external_files,
+                                     const rocksdb::IngestExternalFileOptions& options) override;
+  // the shard's visible contents (merges folded, tombstones dropped) as one ingestible block-based SST file: what a
+  // backup of a volatile HBM shard is.  Returns the number of entries through *entries when it is not null.
+  rocksdb::Status ExportSstFile(const std::string& path, uint64_t* entries = nullptr);
   rocksdb::SequenceNumber GetLatestSequenceNumber() const override;
   rocksdb::Status GetUpdatesSince(rocksdb::SequenceNumber seq,
                                   std::unique_ptr<rocksdb::TransactionLogIterator>* iter) override;

@@ -39,6 +39,9 @@ class DB {
   virtual Iterator* NewIterator(const ReadOptions& options) = 0;
   virtual Status CompactRange(const CompactRangeOptions& options, const Slice* begin, const Slice* end) = 0;
   virtual Status Flush(const FlushOptions& options) = 0;
+  virtual Status IngestExternalFile(const std::vector<std::string>& /*external_files*/, const IngestExternalFileOptions&) {
+    return Status::NotSupported("IngestExternalFile");
+  }
   virtual SequenceNumber GetLatestSequenceNumber() const = 0;
   virtual Status GetUpdatesSince(SequenceNumber seq, std::unique_ptr<TransactionLogIterator>* iter) = 0;
   virtual ColumnFamilyHandle* DefaultColumnFamily() const = 0;

@@ -11,6 +11,13 @@ struct WriteOptions { bool sync = false; bool disableWAL = false; };
 struct ReadOptions { bool verify_checksums = true; bool fill_cache = true; };
 struct CompactRangeOptions { bool change_level = false; int target_level = -1; };
 struct FlushOptions { bool wait = true; };
+// rocksdb_admin/admin_handler.cpp:1820-1828 sets move_files and allow_global_seqno, the rest stay default
+struct IngestExternalFileOptions {
+  bool move_files = false;
+  bool snapshot_consistency = true;
+  bool allow_global_seqno = true;
+  bool allow_blocking_flush = true;
+};
 struct Options {
   bool create_if_missing = false;
   bool error_if_exists = false;

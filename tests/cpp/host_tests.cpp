@@ -12,9 +12,12 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <unistd.h>
 
 #include "../../rocksplicator_b200/csrc/group_commit.h"
 #include "common/dbconfig.h"
@@ -399,6 +402,66 @@ static void test_gpu_sequence_numbers() {
   EXPECT_EQ(n, 10);
 }
 
+// backup / bulk load through SST files: ExportSstFile -> IngestExternalFile (admin_handler.cpp:1820-1845), with the
+// sequence rules of rocksdb_assumption_test.cpp:248-283 (empty target: none consumed; overlap: +1; refused without
+// allow_global_seqno)
+static void test_gpu_export_and_ingest() {
+  auto src = open_gpu("sst_src", std::make_shared<SimpleMergeOperator>());
+  if (!src) return;
+  rocksdb::WriteOptions wo; rocksdb::ReadOptions ro;
+  std::map<std::string, std::string> want;
+  for (int i = 0; i < 2000; i++) {
+    char k[32]; snprintf(k, sizeof(k), "key%06d", i * 3);
+    const std::string v = "value" + std::to_string(i) + std::string(i % 97, 'x');
+    EXPECT_TRUE(src->Put(wo, k, v).ok());
+    want[k] = v;
+  }
+  EXPECT_TRUE(src->Merge(wo, "key000003", "+m").ok()); want["key000003"] += "+m";
+  EXPECT_TRUE(src->Delete(wo, "key000006").ok()); want.erase("key000006");
+  const char* tdir = getenv("TMPDIR") ? getenv("TMPDIR") : "/tmp";
+  const std::string path = std::string(tdir) + "/rsp_host_test_" + std::to_string((long)getpid()) + ".sst";
+  uint64_t n = 0;
+  auto* gsrc = static_cast<b200::GpuDB*>(src.get());
+  EXPECT_TRUE(gsrc->ExportSstFile(path, &n).ok());
+  EXPECT_EQ(n, (uint64_t)want.size());
+  auto dst = open_gpu("sst_dst", std::make_shared<SimpleMergeOperator>());
+  rocksdb::IngestExternalFileOptions io;
+  EXPECT_TRUE(dst->IngestExternalFile({path}, io).ok());
+  EXPECT_EQ(dst->GetLatestSequenceNumber(), 0u);
+  {
+    std::unique_ptr<rocksdb::Iterator> it(dst->NewIterator(ro));
+    auto w = want.begin();
+    size_t seen = 0;
+    for (it->SeekToFirst(); it->Valid() && w != want.end(); it->Next(), ++w, seen++) {
+      if (it->key().ToString() != w->first || it->value().ToString() != w->second) break;
+    }
+    EXPECT_EQ(seen, want.size());
+    EXPECT_TRUE(!it->Valid());
+  }
+  std::string v;
+  EXPECT_TRUE(dst->Get(ro, "key000003", &v).ok() && v == want["key000003"]);
+  EXPECT_TRUE(dst->Get(ro, "key000006", &v).IsNotFound());
+  // the same file again overlaps what is there: refused without global sequence numbers, else last + 1
+  io.allow_global_seqno = false;
+  Status st = dst->IngestExternalFile({path}, io);
+  EXPECT_TRUE(st.IsInvalidArgument());
+  EXPECT_EQ(dst->GetLatestSequenceNumber(), 0u);
+  io.allow_global_seqno = true;
+  EXPECT_TRUE(dst->Put(wo, "key000003", "newer").ok());
+  EXPECT_TRUE(dst->IngestExternalFile({path}, io).ok());
+  EXPECT_EQ(dst->GetLatestSequenceNumber(), 2u);
+  EXPECT_TRUE(dst->Get(ro, "key000003", &v).ok() && v == want["key000003"]);  // the ingested file is the newest
+  EXPECT_TRUE(dst->IngestExternalFile({path + ".missing"}, io).IsIOError());
+  EXPECT_TRUE(dst->IngestExternalFile({}, io).IsInvalidArgument());
+  io.move_files = true;
+  auto dst2 = open_gpu("sst_dst2", nullptr);
+  EXPECT_TRUE(dst2->IngestExternalFile({path}, io).ok());
+  FILE* gone = fopen(path.c_str(), "rb");
+  EXPECT_TRUE(gone == nullptr);
+  if (gone) fclose(gone);
+  remove(path.c_str());
+}
+
 // rocksdb_replicator_test.cpp:146-208 + :270-368 with real engines: leader -> follower -> chained follower
 static void test_gpu_replication_chain() {
   fast_flags();
@@ -581,6 +644,7 @@ int main(int argc, char** argv) {
       {"ack_modes_counting", test_ack_modes_counting, false},
       {"dbconfig_and_stats", test_dbconfig_and_stats, false},
       {"gpu_sequence_numbers", test_gpu_sequence_numbers, true},
+      {"gpu_export_and_ingest", test_gpu_export_and_ingest, true},
       {"gpu_replication_chain", test_gpu_replication_chain, true},
       {"gpu_follower_equals_leader", test_gpu_follower_equals_leader, true},
       {"counter_service_config1", test_counter_service_config1, true},
