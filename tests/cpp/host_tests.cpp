@@ -633,6 +633,8 @@ static void test_application_db_manager() {
 
 int main(int argc, char** argv) {
   const std::string mode = argc > 1 ? argv[1] : "cpu";
+  // `only=<name>` (second argument) runs one test by name, whatever its mode
+  const std::string only = argc > 2 ? argv[2] : "";
   struct T { const char* name; std::function<void()> fn; bool gpu; };
   std::vector<T> tests = {
       {"fast_read_map", test_fast_read_map, false},
@@ -651,8 +653,13 @@ int main(int argc, char** argv) {
       {"application_db_manager", test_application_db_manager, true},
   };
   for (auto& t : tests) {
-    if (t.gpu && mode != "gpu" && mode != "gpu-only") continue;
-    if (!t.gpu && mode == "gpu-only") continue;
+    if (!only.empty()) {
+      if (only != t.name) continue;
+    } else {
+      if (t.gpu && mode != "gpu" && mode != "gpu-only") continue;
+      if (!t.gpu && mode == "gpu-only") continue;
+      if (std::string(t.name) == "gpu_export_and_ingest") continue;  // run by name from tests/test_zz_ingest_gpu.py
+    }
     const int before = g_fail;
     printf("[ RUN  ] %s\n", t.name);
     fflush(stdout);

@@ -138,3 +138,14 @@ def test_port_vs_reference_live(port_lib, ref_lib):
         assert a.latest_seq() == b.latest_seq(), name
         a.close()
         b.close()
+
+
+def test_port_vs_reference_fuzz(port_lib, ref_lib):
+    """oracle/fuzz_port_vs_ref.py on a few seeds: flush/compaction at random points, MultiGet, iterator walks."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "fuzz_port_vs_ref.py")
+    spec = importlib.util.spec_from_file_location("fuzz_port_vs_ref", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(200, 212, port_lib, ref_lib) == 0

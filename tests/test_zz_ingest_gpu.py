@@ -133,3 +133,13 @@ def test_ingest_fixed_shape_serves_the_fast_path(eng):
     assert got[:-1] == [(0, kv[i][1]) for i in range(0, n, 37)] and got[-1] == (1, None)
     assert s.scan(limit=100) == kv[:100]
     s.close()
+
+
+def test_gpudb_export_and_ingest_files():
+    """GpuDB::ExportSstFile -> GpuDB::IngestExternalFile (tests/cpp/host_tests.cpp::test_gpu_export_and_ingest)"""
+    import subprocess
+    from rocksplicator_b200 import build
+    _, exe = build.build_host()
+    p = subprocess.run([exe, "gpu", "gpu_export_and_ingest"], capture_output=True, text=True, timeout=300)
+    print(p.stdout[-4000:], p.stderr[-2000:])
+    assert p.returncode == 0 and " 0 failures" in p.stdout and "[ RUN  ] gpu_export_and_ingest" in p.stdout, p.stdout[-3000:]
