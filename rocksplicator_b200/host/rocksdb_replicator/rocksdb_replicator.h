@@ -65,6 +65,8 @@ class RocksDBReplicator {
     rocksdb::Status Write(const rocksdb::WriteOptions& options, rocksdb::WriteBatch* updates,
                           rocksdb::SequenceNumber* seq_no = nullptr);
     std::string Introspect();
+    // how often this replica tried to re-resolve its upstream (rocksdb_replicator.h:139: kept for tests)
+    uint32_t resetUpstreamAttempts() const { return resetUpstreamAttempts_.load(); }
     ~ReplicatedDB();
 
    private:

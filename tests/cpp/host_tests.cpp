@@ -247,6 +247,124 @@ static void test_replication_protocol_counting() {
   EXPECT_EQ(leader_host.removeDB("master"), ReturnCode::OK);
 }
 
+// what a follower's log must hold: the leader's batches, in order, each followed by the follower's own LogData(ts)
+static bool follower_matches(CountingDb& leader, CountingDb& follower) {
+  std::lock_guard<std::mutex> g1(leader.mu_);
+  std::lock_guard<std::mutex> g2(follower.mu_);
+  if (leader.log_.size() != follower.log_.size()) return false;
+  for (size_t i = 0; i < leader.log_.size(); i++) {
+    const std::string& a = leader.log_[i].second;
+    const std::string& b = follower.log_[i].second;
+    if (leader.log_[i].first != follower.log_[i].first) return false;
+    if (b.size() != a.size() + 10 || b.compare(0, a.size(), a) != 0 || (uint8_t)b[a.size()] != 0x03 || (uint8_t)b[a.size() + 1] != 8) return false;
+  }
+  return true;
+}
+
+// rocksdb_replicator_test.cpp:210-268: two followers pulling from the same leader
+static void test_tree_counting() {
+  fast_flags();
+  RocksDBReplicator leader_host(19101), f1_host(19102), f2_host(19103);
+  auto ldb = std::make_shared<CountingDb>(), f1 = std::make_shared<CountingDb>(), f2 = std::make_shared<CountingDb>();
+  EXPECT_EQ(leader_host.addDB("shard1", std::static_pointer_cast<DbWrapper>(ldb), ReplicaRole::LEADER), ReturnCode::OK);
+  EXPECT_EQ(f1_host.addDB("shard1", std::static_pointer_cast<DbWrapper>(f1), ReplicaRole::FOLLOWER, SocketAddress("127.0.0.1", 19101)), ReturnCode::OK);
+  EXPECT_EQ(f2_host.addDB("shard1", std::static_pointer_cast<DbWrapper>(f2), ReplicaRole::FOLLOWER, SocketAddress("127.0.0.1", 19101)), ReturnCode::OK);
+  rocksdb::WriteOptions wo;
+  for (uint32_t i = 0; i < 100; i++) {
+    WriteBatch b;
+    b.Put(std::to_string(i) + "key", std::to_string(i) + "value");
+    EXPECT_EQ(leader_host.write("shard1", wo, &b), ReturnCode::OK);
+    EXPECT_EQ(ldb->LatestSequenceNumber(), (uint64_t)i + 1);
+  }
+  EXPECT_TRUE(wait_until([&] { return f1->LatestSequenceNumber() == 100 && f2->LatestSequenceNumber() == 100; }));
+  EXPECT_TRUE(follower_matches(*ldb, *f1));
+  EXPECT_TRUE(follower_matches(*ldb, *f2));
+  f1_host.removeDB("shard1"); f2_host.removeDB("shard1"); leader_host.removeDB("shard1");
+}
+
+// rocksdb_replicator_test.cpp:372-428 and :430-492: a follower whose upstream is itself, and two followers whose
+// upstreams are each other, never see the leader's writes; empty responses from a non-leader make them try to reset
+// their upstream (which cannot succeed without a cluster manager), the leader never does
+static void test_upstream_reset_counting() {
+  fast_flags();
+  auto& F = Flags();
+  F.replicator_max_server_wait_time_ms = 100;
+  F.replicator_client_server_timeout_difference_ms = 100;
+  F.reset_upstream_on_empty_updates_from_non_leader = true;
+  F.replicator_max_consecutive_no_updates_before_upstream_reset = 1;
+  {
+    RocksDBReplicator leader_host(19104), self_host(19105), a_host(19106), b_host(19107);
+    auto ldb = std::make_shared<CountingDb>(), sdb = std::make_shared<CountingDb>(), adb = std::make_shared<CountingDb>(), bdb = std::make_shared<CountingDb>();
+    RocksDBReplicator::ReplicatedDB *rl = nullptr, *rs = nullptr, *ra = nullptr, *rb = nullptr;
+    EXPECT_EQ(leader_host.addDB("shard1", std::static_pointer_cast<DbWrapper>(ldb), ReplicaRole::LEADER, SocketAddress(), &rl), ReturnCode::OK);
+    EXPECT_EQ(self_host.addDB("shard1", std::static_pointer_cast<DbWrapper>(sdb), ReplicaRole::FOLLOWER, SocketAddress("127.0.0.1", 19105), &rs), ReturnCode::OK);
+    EXPECT_EQ(a_host.addDB("shard1", std::static_pointer_cast<DbWrapper>(adb), ReplicaRole::FOLLOWER, SocketAddress("127.0.0.1", 19107), &ra), ReturnCode::OK);
+    EXPECT_EQ(b_host.addDB("shard1", std::static_pointer_cast<DbWrapper>(bdb), ReplicaRole::FOLLOWER, SocketAddress("127.0.0.1", 19106), &rb), ReturnCode::OK);
+    rocksdb::WriteOptions wo;
+    for (uint32_t i = 0; i < 100; i++) {
+      WriteBatch b;
+      b.Put(std::to_string(i) + "key", std::to_string(i) + "value");
+      b.Put(std::to_string(i) + "key2", std::to_string(i) + "value2");
+      EXPECT_EQ(leader_host.write("shard1", wo, &b), ReturnCode::OK);
+    }
+    EXPECT_EQ(ldb->LatestSequenceNumber(), 200u);
+    EXPECT_TRUE(wait_until([&] { return rs->resetUpstreamAttempts() != 0 && ra->resetUpstreamAttempts() != 0 && rb->resetUpstreamAttempts() != 0; }, 3000));
+    EXPECT_EQ(rl->resetUpstreamAttempts(), 0u);
+    EXPECT_EQ(sdb->LatestSequenceNumber(), 0u);
+    EXPECT_EQ(adb->LatestSequenceNumber(), 0u);
+    EXPECT_EQ(bdb->LatestSequenceNumber(), 0u);
+    self_host.removeDB("shard1"); a_host.removeDB("shard1"); b_host.removeDB("shard1"); leader_host.removeDB("shard1");
+  }
+  Flags() = ReplicatorFlags();
+  fast_flags();
+}
+
+// rocksdb_replicator_test.cpp:740-823: 20 shards over three hosts, leader on host i % 3, followers on the other two;
+// every write is offered to all three hosts and lands only on the shard's leader
+static void test_stress_counting() {
+  fast_flags();
+  const int n_shards = 20;
+  const uint32_t n_keys = 100;
+  const uint16_t ports[3] = {19108, 19109, 19110};
+  RocksDBReplicator h0(ports[0]), h1(ports[1]), h2(ports[2]);
+  RocksDBReplicator* hosts[3] = {&h0, &h1, &h2};
+  std::vector<std::shared_ptr<CountingDb>> leaders, f1s, f2s;
+  for (int i = 0; i < n_shards; i++) {
+    leaders.push_back(std::make_shared<CountingDb>());
+    f1s.push_back(std::make_shared<CountingDb>());
+    f2s.push_back(std::make_shared<CountingDb>());
+    const std::string shard = "shard" + std::to_string(i);
+    const int start = i % 3;
+    EXPECT_EQ(hosts[start]->addDB(shard, std::static_pointer_cast<DbWrapper>(leaders[i]), ReplicaRole::LEADER), ReturnCode::OK);
+    EXPECT_EQ(hosts[(start + 1) % 3]->addDB(shard, std::static_pointer_cast<DbWrapper>(f1s[i]), ReplicaRole::FOLLOWER, SocketAddress("127.0.0.1", ports[start])), ReturnCode::OK);
+    EXPECT_EQ(hosts[(start + 2) % 3]->addDB(shard, std::static_pointer_cast<DbWrapper>(f2s[i]), ReplicaRole::FOLLOWER, SocketAddress("127.0.0.1", ports[start])), ReturnCode::OK);
+  }
+  rocksdb::WriteOptions wo;
+  int bad_codes = 0;
+  for (uint32_t i = 0; i < n_keys; i++)
+    for (int j = 0; j < n_shards; j++) {
+      const std::string shard = "shard" + std::to_string(j);
+      WriteBatch b;
+      b.Put(std::to_string(i) + "key", std::to_string(i) + "value");
+      int oks = 0;
+      for (auto* h : hosts) {
+        const ReturnCode rc = h->write(shard, wo, &b);
+        if (rc == ReturnCode::OK) oks++;
+        else if (rc != ReturnCode::WRITE_TO_SLAVE) bad_codes++;
+      }
+      if (oks != 1) bad_codes++;
+    }
+  EXPECT_EQ(bad_codes, 0);
+  for (int i = 0; i < n_shards; i++) {
+    EXPECT_EQ(leaders[i]->LatestSequenceNumber(), (uint64_t)n_keys);
+    EXPECT_TRUE(wait_until([&] { return f1s[i]->LatestSequenceNumber() == n_keys && f2s[i]->LatestSequenceNumber() == n_keys; }));
+    EXPECT_TRUE(follower_matches(*leaders[i], *f1s[i]));
+    EXPECT_TRUE(follower_matches(*leaders[i], *f2s[i]));
+  }
+  for (int i = 0; i < n_shards; i++)
+    for (auto* h : hosts) EXPECT_EQ(h->removeDB("shard" + std::to_string(i)), ReturnCode::OK);
+}
+
 // rocksdb_replicator_test.cpp:494-624 (2-ACK mode: success, timeout, degradation) and :626-738 (observer is no ACK)
 static void test_ack_modes_counting() {
   fast_flags();
@@ -643,6 +761,9 @@ int main(int argc, char** argv) {
       {"write_batch_and_status", test_write_batch_and_status, false},
       {"group_commit", test_group_commit, false},
       {"replication_protocol_counting", test_replication_protocol_counting, false},
+      {"tree_counting", test_tree_counting, false},
+      {"upstream_reset_counting", test_upstream_reset_counting, false},
+      {"stress_counting", test_stress_counting, false},
       {"ack_modes_counting", test_ack_modes_counting, false},
       {"dbconfig_and_stats", test_dbconfig_and_stats, false},
       {"gpu_sequence_numbers", test_gpu_sequence_numbers, true},
