@@ -240,6 +240,10 @@ struct rsp_engine {
   cudaEvent_t mut_ev = nullptr;
   bool mut_recorded = false;
   size_t stage_threads = 1;
+  // EXPERIMENT (RSP_DIRECT_RUNS=1): fully compacted fixed-shape runs are laid out as RUN_DIRECT (format.cuh) and
+  // MultiGet goes through k_multi_get16d.  Off by default; direct_load = entries / slots.
+  bool direct_runs = false;
+  double direct_load = 0.5;
   u32 mg_parity = 0;
   size_t pending_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -287,6 +291,13 @@ static void upload_shard(rsp_engine* e, rsp_shard* s) {
     const Run& r0 = *s->runs[0];
     f.run0_heap = (u64)r0.heap; f.run0_hslots = (u64)r0.hslots; f.n_buckets = r0.n_buckets;
     f.meta = r0.ord_bits | (std::min<u32>(r0.uniform_units, 255u) << 8);
+    if (r0.flags & RUN_DIRECT) {
+      // uniform_units is 0 for such a run, so k_multi_get16 defers to the generic path; k_multi_get16d reads the
+      // slot geometry from the (for it unused) index pointer field
+      const u32 U = 1u + units_of(r0.kv_len & 0xffffu) + units_of(r0.kv_len >> 16);
+      f.run0_hslots = (u64)U | ((u64)(r0.heap_units / U) << 32);
+      f.meta |= FAST_META_DIRECT;
+    }
   }
   f.meta |= (u32)std::min<size_t>(s->runs.size(), 255) << 16;
   f.meta |= 1u << 24;  // live
@@ -427,6 +438,44 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
   CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CompactJob) * nj, cudaMemcpyHostToDevice, e->st));
   launch_compact_write(d_jobs, nj, max_items, e->st);
   e->launches += 1;
+  // EXPERIMENT: a fully compacted run of same-size Puts with 16-byte keys, one version per key, is re-laid out as
+  // RUN_DIRECT; the sorted heap it was written to is released after the sync below
+  std::vector<std::pair<void*, size_t>> sorted_heaps;
+  PlaceJob* d_place = nullptr;
+  size_t n_place = 0;
+  if (e->direct_runs) {
+    std::vector<PlaceJob> pj;
+    u32 max_ent = 0;
+    for (u32 i = 0; i < nj; i++) {
+      Run& r = *outs[i];
+      const u32 keys = totals[8 * i + 3];
+      const u32 U = r.uniform_units;
+      const bool only_run = jh[i].full || jh[i].s->runs.empty();
+      if (!(r.flags & RUN_ALL_PUT_FIXED) || !only_run || (r.kv_len & 0xffffu) != 16 || keys != r.n_ent || U < 2 || U > 254) continue;
+      const u64 n_slots = std::max<u64>(8, (u64)((double)r.n_ent / e->direct_load) + 1);
+      if (n_slots * U > 0xffffffffull) continue;
+      PlaceJob p;
+      memset(&p, 0, sizeof(p));
+      p.src_heap = r.heap; p.ent_off = r.ent_off; p.n_ent = r.n_ent; p.U = U; p.n_slots = (u32)n_slots;
+      p.dst_heap = (u8*)a.alloc((size_t)n_slots * U * 16);
+      CUDA_OK(cudaMemsetAsync(p.dst_heap, 0, (size_t)n_slots * U * 16, e->st));
+      sorted_heaps.emplace_back(r.heap, (size_t)r.heap_units * 16);
+      r.heap = p.dst_heap;
+      r.heap_units = (u32)(n_slots * U);
+      r.uniform_units = 0;
+      r.flags = RUN_DIRECT;
+      pj.push_back(p);
+      max_ent = std::max(max_ent, p.n_ent);
+    }
+    if (!pj.empty()) {
+      n_place = pj.size();
+      d_place = (PlaceJob*)a.alloc(sizeof(PlaceJob) * n_place);
+      CUDA_OK(cudaMemcpyAsync(d_place, pj.data(), sizeof(PlaceJob) * n_place, cudaMemcpyHostToDevice, e->st));
+      launch_compact_place(d_place, (u32)n_place, max_ent, e->st);
+      e->launches += 1;
+      // pj is pageable: the copy above is staged before the call returns
+    }
+  }
   CUDA_OK(cudaEventRecord(e->ev1, e->st));
   // install
   for (u32 i = 0; i < nj; i++) {
@@ -459,6 +508,8 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
     a.release(jobs[i].totals, 32);
   }
   a.release(d_jobs, sizeof(CompactJob) * nj);
+  for (auto& h : sorted_heaps) a.release(h.first, h.second);
+  if (d_place) a.release(d_place, sizeof(PlaceJob) * n_place);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -982,7 +1033,7 @@ static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, c
     a.vals = d + o_vals + c0 * val_stride; a.val_stride = val_stride;
     a.vlen = (u32*)(d + o_vlen) + c0; a.st = (i32*)(d + o_st) + c0; a.n = (u32)cn;
     a.n_special = scratch; a.n_pending = scratch + 4 + 2 * c; a.pending = scratch + 4 + 2 * n_chunks + c0; a.parity = 0;
-    launch_multi_get(a, cs);
+    if (e->direct_runs) launch_multi_get_direct(a, cs); else launch_multi_get(a, cs);
     e->launches += 2;
     CUDA_OK(cudaMemcpyAsync(vlen + c0, d + o_vlen + c0 * 4, cn * 4, cudaMemcpyDeviceToHost, cs));
     CUDA_OK(cudaMemcpyAsync(st + c0, d + o_st + c0 * 4, cn * 4, cudaMemcpyDeviceToHost, cs));
@@ -1142,6 +1193,8 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   // measured on the B200 host (128 cores): 2 staging threads 29 M applies/s, 1: 27, 8: 19 (spawn cost wins)
   e->stage_threads = 2;
   if (const char* t = getenv("RSP_STAGE_THREADS")) e->stage_threads = (size_t)std::max(1, atoi(t));
+  if (const char* t = getenv("RSP_DIRECT_RUNS")) e->direct_runs = atoi(t) != 0;
+  if (const char* t = getenv("RSP_DIRECT_LOAD")) e->direct_load = std::min(0.9, std::max(0.05, atof(t)));
   CUDA_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   e->single_applies.reset(new rsp::GroupCommit<ApplyReq>([e](std::vector<ApplyReq*>& b) { run_single_applies(e, b); }));
   for (int k = 0; k < 3; k++) {
@@ -1244,9 +1297,10 @@ static void run_key_range(rsp_engine* e, const Run& r, std::string* first, std::
     out->resize(hd[2]);
     if (hd[2]) CUDA_OK(cudaMemcpy(&(*out)[0], r.heap + (size_t)unit * 16 + 16, hd[2], cudaMemcpyDeviceToHost));
   };
-  key_at(0, first);
-  u32 last_unit = 0;
+  u32 first_unit = 0, last_unit = 0;
+  CUDA_OK(cudaMemcpy(&first_unit, r.ent_off, 4, cudaMemcpyDeviceToHost));
   CUDA_OK(cudaMemcpy(&last_unit, r.ent_off + (r.n_ent - 1), 4, cudaMemcpyDeviceToHost));
+  key_at(first_unit, first);
   key_at(last_unit, last);
   (void)e;
 }
@@ -1588,7 +1642,7 @@ int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, co
     a.max_shards = e->cfg.max_shards;
     cudaStream_t rs = stream ? (cudaStream_t)stream : e->st;
     reader_begin(e, rs);
-    launch_multi_get(a, rs);
+    if (e->direct_runs) launch_multi_get_direct(a, rs); else launch_multi_get(a, rs);
     reader_end(e, rs);
   }
   e->launches += 2;

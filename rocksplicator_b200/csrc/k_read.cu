@@ -517,6 +517,115 @@ __global__ void __launch_bounds__(256) k_multi_get_pending(GetArgs a) {
     lookup_generic(a, __ldcg(a.pending + i), lane, gmask, gbase);
 }
 
+// ------------------------------------------------------------------------------------------------
+// EXPERIMENT (RSP_DIRECT_RUNS=1): k_multi_get16d — k_multi_get16 for shards whose single run is RUN_DIRECT.
+// The run's heap IS the hash table (format.cuh), so the bucket round trip disappears: ShardFast -> entry slot.
+// Same memtable stage, same pending list for everything the fast path does not cover.
+// ------------------------------------------------------------------------------------------------
+// One slot: 0 = served, 1 = another key (probe on), 2 = generic path, 4 = empty slot (NOT_FOUND).
+template <bool BIG>
+__device__ __forceinline__ u32 direct_slot(const u8* ent, u32 U, const uint4& kq, u8* dst, u64 val_stride, u32 lane,
+                                           u32& vlen_out) {
+  const uint4* ep = reinterpret_cast<const uint4*>(ent);
+  const uint4 hd = __ldg(ep);
+  const uint4 ek = __ldg(ep + 1);
+  uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
+  if (2u + lane < U) v0 = __ldg(ep + 2u + lane);
+  if (4u + lane < U) v1 = __ldg(ep + 4u + lane);
+  if (6u + lane < U) v2 = __ldg(ep + 6u + lane);
+  if (hd.z != 16) return 4;  // an occupied slot of a direct run always holds a 16-byte key
+  if (ek.x != kq.x || ek.y != kq.y || ek.z != kq.z || ek.w != kq.w) return 1;
+  const u32 vu = (hd.w + 15u) >> 4;
+  if ((hd.x & 0xffu) != kTypeValue || 2u + vu > U || (u64)vu * 16u > val_stride || (!BIG && vu > 6)) return 2;
+  uint4* out = reinterpret_cast<uint4*>(dst);
+  if (lane < vu) out[lane] = v0;
+  if (lane + 2 < vu) out[lane + 2] = v1;
+  if (lane + 4 < vu) out[lane + 4] = v2;
+  if (BIG)
+    for (u32 u = lane + 6; u < vu; u += FL) out[u] = __ldg(ep + 2u + u);
+  vlen_out = hd.w;
+  return 0;
+}
+
+template <bool BIG>
+__global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16d(GetArgs a) {
+  const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) / FL;
+  const u32 lane = threadIdx.x & (FL - 1);
+  const u32 pbase = (threadIdx.x & 31u) & ~1u;
+  const u32 pmask = 3u << pbase;
+  if (q >= a.n) return;
+  const u64 pol_stream = pol_evict_first();
+  u32 six = __ldg(a.shard_ix + q);
+  const bool bad_shard = six >= a.max_shards;
+  if (bad_shard) six = 0;
+  const uint4 kq = __ldg(reinterpret_cast<const uint4*>(a.keys) + q);
+  const uint4 f0 = __ldg(reinterpret_cast<const uint4*>(a.fast + six));
+  const uint4 f1 = __ldg(reinterpret_cast<const uint4*>(a.fast + six) + 1);
+  const u32 n_runs = (f1.y >> 16) & 0xffu;
+  const u64 k0 = ((u64)kq.y << 32) | kq.x, k1 = ((u64)kq.w << 32) | kq.z;
+  const u64 h = hash_final(hash_step(hash_step(hash_init(16), k0), k1));
+  u8* dst = a.vals + (u64)q * a.val_stride;
+  u32 state = 3;  // 0 served, 2 generic path, 3 undecided, 4 not found
+  u32 vlen = 0;
+  if (n_runs > 1 || ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u) || bad_shard || !(f1.y & FAST_META_LIVE)) state = 2;
+  if (state == 3 && f1.z /* mt_count */) {
+    // ---- memtable stage: identical to k_multi_get16
+    const uint4* dp = reinterpret_cast<const uint4*>(a.shards + six);
+    const uint4 d0 = __ldcg(dp), d1 = __ldcg(dp + 1), d3 = __ldcg(dp + 3);
+    const u8* heap = reinterpret_cast<const u8*>(((u64)d0.y << 32) | d0.x);
+    const u64* sp = reinterpret_cast<const u64*>(((u64)d0.w << 32) | d0.z);
+    const u32 mask = d1.z;
+    const u64 snap = ((u64)d3.w << 32) | d3.z;
+    const u32 tag = hash_tag32(h);
+    u32 cand = 0, info = 0;
+#pragma unroll
+    for (u32 i = 0; i < 4; i++) {
+      const u64 sv = ldcg64(sp + (((u32)h + 4u * lane + i) & mask));
+      if (sv == 0) { if (!(info >> 8)) info |= (4u * lane + i + 1u) << 8; }
+      else if ((u32)(sv >> 32) == tag && !(info >> 8)) { if (!cand) cand = (u32)sv; info++; }
+    }
+    const u32 o_cand = __shfl_xor_sync(pmask, cand, 1), o_info = __shfl_xor_sync(pmask, info, 1);
+    const u32 lo_info = lane ? o_info : info, hi_info = lane ? info : o_info;
+    const u32 lo_cand = lane ? o_cand : cand, hi_cand = lane ? cand : o_cand;
+    const bool lo_empty = (lo_info >> 8) != 0;
+    const u32 n_match = (lo_info & 0xffu) + (lo_empty ? 0u : (hi_info & 0xffu));
+    const bool any_empty = lo_empty || (hi_info >> 8) != 0;
+    if (n_match == 1) {
+      const u32 c = (lo_info & 0xffu) ? lo_cand : hi_cand;
+      const u32 r = fast_entry<true, BIG>(heap + (u64)(c - 1u) * 16u, 7, 2, kq, snap, dst, a.val_stride, lane, vlen, pol_stream);
+      state = r == 0 ? 0 : 2;
+    } else if (n_match > 1 || !any_empty) {
+      state = 2;
+    }
+  }
+  if (state == 3) {
+    if (n_runs == 0) state = 4;
+    else if (!(f1.y & FAST_META_DIRECT)) state = 2;
+    else {
+      const u8* heap = reinterpret_cast<const u8*>(((u64)f0.y << 32) | f0.x);
+      const u32 U = f0.z & 0xffu, n_slots = f0.w;
+      u32 slot = (u32)(((u64)(u32)h * n_slots) >> 32);
+      state = 2;
+#pragma unroll 1
+      for (u32 probe = 0; probe < n_slots; probe++) {
+        const u32 r = direct_slot<BIG>(heap + (u64)slot * U * 16u, U, kq, dst, a.val_stride, lane, vlen);
+        if (r == 0) { state = 0; break; }
+        if (r == 4) { state = 4; break; }
+        if (r == 2) break;
+        slot = slot + 1 == n_slots ? 0 : slot + 1;
+      }
+    }
+  }
+  if (lane == 0) {
+    if (state == 2) {
+      a.pending[atomicAdd(a.n_pending + a.parity, 1u)] = q;
+    } else {
+      a.st[q] = state == 0 ? 0 : 1;
+      a.vlen[q] = vlen;
+    }
+  }
+}
+
 void launch_multi_get(const GetArgs& a, cudaStream_t s) {
   if (!a.n) return;
   const u32 per_block = 256 / MG_LANES;
@@ -532,6 +641,21 @@ void launch_multi_get(const GetArgs& a, cudaStream_t s) {
   } else {
     k_multi_get<<<grid, 256, 0, s>>>(a);
   }
+}
+
+void launch_multi_get_direct(const GetArgs& a, cudaStream_t s) {
+  if (!a.n) return;
+  if (!(a.klen_fixed == 16 && (reinterpret_cast<uintptr_t>(a.keys) & 15u) == 0 && a.pending && a.fast)) {
+    launch_multi_get(a, s);
+    return;
+  }
+  const u32 per_block = 256 / MG_LANES;
+  const u32 grid = (a.n + per_block - 1) / per_block;
+  cudaMemsetAsync(a.n_pending + a.parity, 0, 4, s);
+  const u32 g16 = (a.n + RSP_MG_TPB / FL - 1) / (RSP_MG_TPB / FL);
+  if (a.val_stride > 96) k_multi_get16d<true><<<g16, RSP_MG_TPB, 0, s>>>(a);
+  else k_multi_get16d<false><<<g16, RSP_MG_TPB, 0, s>>>(a);
+  k_multi_get_pending<<<std::min<u32>(grid, 148u), 256, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
