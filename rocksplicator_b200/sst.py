@@ -67,3 +67,23 @@ def write_sst(sorted_kv, block_size=4096) -> bytes:
     data = C.string_at(out.value, out_len.value)
     lib.rsp_host_free(out)
     return data
+
+
+def ingest_file(shard, path, allow_global_seqno=True) -> int:
+    """DB::IngestExternalFile(path) on an engine shard (rocksdb_admin/admin_handler.cpp:1820-1845): parse on the host,
+    install as one sorted run on the device (rsp_ingest_sorted).  Returns a rocksdb::Status code."""
+    with open(path, "rb") as f:
+        entries, props = read_sst(f.read())
+    if props["external_version"] == 0:
+        raise ValueError("External file version not found")
+    if any(t != 1 or seq != 0 for _, seq, t, _ in entries):
+        raise ValueError("external file holds a record that is not a Put with sequence number 0")
+    return shard.ingest([(k, v) for k, _, _, v in entries], allow_global_seqno)
+
+
+def export_file(shard, path) -> int:
+    """The shard's visible contents (merges folded, tombstones dropped) as one ingestible SST file; -> entries"""
+    kv = shard.scan()
+    with open(path, "wb") as f:
+        f.write(write_sst(kv))
+    return len(kv)
