@@ -102,7 +102,11 @@ __device__ __forceinline__ void sort_tile_steps(const CompactJob& j, SortItem* t
 }
 
 __global__ void __launch_bounds__(1024) k_compact_sort(const CompactJob* jobs) {
+#ifdef RSP_EMUL
+  unsigned char* sort_smem = emul_dyn_smem;  // tests/emul: dynamic shared memory of the running block
+#else
   extern __shared__ __align__(16) unsigned char sort_smem[];
+#endif
   SortItem* tile = reinterpret_cast<SortItem*>(sort_smem);
   const CompactJob& j = jobs[blockIdx.x];
   const u32 n = j.n_pow2;

@@ -294,23 +294,41 @@ constexpr u32 FL = 2;  // lanes per lookup
 #endif
 __device__ __forceinline__ u64 pol_evict_last() {
   u64 p;
+#ifdef RSP_EMUL  // tests/emul: cache policies have no meaning on the CPU
+  p = 0;
+#else
   asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+#endif
   return p;
 }
 __device__ __forceinline__ u64 pol_evict_first() {
   u64 p;
+#ifdef RSP_EMUL
+  p = 0;
+#else
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+#endif
   return p;
 }
 __device__ __forceinline__ uint4 ldg_pol(const uint4* p, u64 pol) {
   uint4 v;
+#ifdef RSP_EMUL
+  (void)pol;
+  v = *p;
+#else
   asm("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+#endif
   return v;
 }
 __device__ __forceinline__ void stg_pol(uint4* p, const uint4& v, u64 pol) {
+#ifdef RSP_EMUL
+  (void)pol;
+  *p = v;
+#else
   asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+#endif
 }
 #ifndef RSP_MG_TPB
 #define RSP_MG_TPB 64
@@ -329,7 +347,11 @@ __device__ __forceinline__ void stg_pol(uint4* p, const uint4& v, u64 pol) {
 #endif
 __device__ __forceinline__ uint4 ldg_noalloc(const uint4* p) {
   uint4 v;
+#ifdef RSP_EMUL
+  v = *p;
+#else
   asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#endif
   return v;
 }
 template <bool CG>
@@ -769,6 +791,17 @@ __device__ __forceinline__ void warp_copy_bytes(u8* dst, const u8* src, u32 n, u
 constexpr u32 SCAN_WARPS = 4;
 constexpr u32 SCAN_STAGE_PFX = 512;  // prefixes staged per warp (4 KB): runs up to 16 K entries
 
+#ifdef RSP_EMUL
+// tests/emul: the bulk copy completes at issue; the mbarrier word counts completed phases
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, u32 bytes, u64* mbar) {
+  memcpy(smem_dst, gmem_src, bytes);
+  *mbar += 1;
+}
+__device__ __forceinline__ void mbar_init(u64* mbar, u32) { *mbar = 0; }
+__device__ __forceinline__ void mbar_wait(u64* mbar, u32 parity) {
+  while ((*mbar & 1u) == parity) emul_yield();
+}
+#else
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, u32 bytes, u64* mbar) {
   const u32 dst = (u32)__cvta_generic_to_shared(smem_dst);
   const u32 bar = (u32)__cvta_generic_to_shared(mbar);
@@ -793,6 +826,7 @@ __device__ __forceinline__ void mbar_wait(u64* mbar, u32 parity) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+#endif
 
 // warp-cooperative lower bound: first ordinal of R whose key is >= key (strict: > key)
 __device__ u32 run_lower_bound_warp(const RunDev& R, const u8* kp, u32 klen, bool strict, u64* s_pfx, u64* mbar,

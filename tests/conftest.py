@@ -33,3 +33,17 @@ def _built_library():
     """librsp_b200.so is built in-tree (nvcc, sm_100a); rebuild only when sources are newer.  No GPU needed."""
     from rocksplicator_b200 import build
     build.build()
+
+
+# tests/emul (CPU emulation of the CUDA slice the engine uses — test infrastructure, see tests/emul/include/
+# cuda_runtime.h): tests/test_emul_cpu.py re-runs the GPU parity tests in a SUBPROCESS with this variable set, so the
+# ctypes binding in that process binds the emulated library instead of librsp_b200.so.  Never set on a GPU box.
+if os.environ.get("RSP_TEST_EMUL_LIB"):
+    from rocksplicator_b200 import engine as _engine
+    _engine.SO_PATH = os.environ["RSP_TEST_EMUL_LIB"]
+    if os.environ.get("RSP_TEST_EMUL_ARENA"):  # tiny arena slabs: every device allocation becomes its own malloc (ASan)
+        _orig_init = _engine.Engine.__init__
+
+        def _init(self, device=0, max_shards=0, arena_bytes=0, l0_compaction_trigger=0):
+            _orig_init(self, device, max_shards, arena_bytes or int(os.environ["RSP_TEST_EMUL_ARENA"]), l0_compaction_trigger)
+        _engine.Engine.__init__ = _init

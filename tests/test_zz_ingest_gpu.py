@@ -140,6 +140,8 @@ def test_gpudb_export_and_ingest_files():
     import subprocess
     from rocksplicator_b200 import build
     _, exe = build.build_host()
+    if os.environ.get("RSP_TEST_EMUL_LIB"):  # tests/test_emul_cpu.py: the same test binary linked against the emulation
+        exe = os.path.join(os.path.dirname(os.environ["RSP_TEST_EMUL_LIB"]), "host_tests_emul")
     p = subprocess.run([exe, "gpu", "gpu_export_and_ingest"], capture_output=True, text=True, timeout=300)
     print(p.stdout[-4000:], p.stderr[-2000:])
     assert p.returncode == 0 and " 0 failures" in p.stdout and "[ RUN  ] gpu_export_and_ingest" in p.stdout, p.stdout[-3000:]
