@@ -69,8 +69,16 @@ struct Arena {
     while (c < n) c <<= 1;
     return c;
   }
+#ifdef RSP_EMUL
+  // tests/emul under AddressSanitizer: every request is its own exactly-sized allocation, freed on release, so an
+  // access past the requested size or after release is reported instead of landing in a neighbour
+  static bool exact() { static const bool on = getenv("RSP_EMUL_EXACT_ALLOC") != nullptr; return on; }
+#endif
   void* alloc(size_t n) {
     if (n == 0) n = 1;
+#ifdef RSP_EMUL
+    if (exact()) { void* p = nullptr; CUDA_OK(cudaMalloc(&p, n)); return p; }
+#endif
     const size_t c = cls(n);
     std::lock_guard<std::mutex> g(mu);
     in_use += c;
@@ -108,6 +116,9 @@ struct Arena {
   }
   void release(void* p, size_t n) {
     if (!p) return;
+#ifdef RSP_EMUL
+    if (exact()) { cudaFree(p); return; }
+#endif
     if (n == 0) n = 1;
     const size_t c = cls(n);
     std::lock_guard<std::mutex> g(mu);
@@ -152,6 +163,9 @@ struct PinBuf {
 };
 
 // ------------------------------------------------------------------------------------------------
+// the block index is staged by one TMA bulk copy, whose size is a multiple of 16 bytes (k_read.cu run_lower_bound_warp)
+static inline size_t blk_pfx_bytes(u32 n_blocks) { return ((size_t)n_blocks * 8 + 15) & ~(size_t)15; }
+
 struct Run {
   Arena* arena;
   u8* heap = nullptr;
@@ -171,7 +185,7 @@ struct Run {
     arena->release(heap, (size_t)heap_units * 16);
     arena->release(ent_off, (size_t)n_ent * 4);
     arena->release(hslots, (size_t)n_buckets * RUN_BUCKET_SLOTS * 4);
-    arena->release(blk_pfx, (size_t)n_blocks * 8);
+    arena->release(blk_pfx, blk_pfx_bytes(n_blocks));
   }
 };
 
@@ -428,7 +442,7 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
     r->heap = (u8*)a.alloc((size_t)units * 16);
     r->ent_off = (u32*)a.alloc((size_t)ents * 4);
     r->hslots = (u32*)a.alloc((size_t)r->n_buckets * RUN_BUCKET_SLOTS * 4);
-    r->blk_pfx = (u64*)a.alloc((size_t)r->n_blocks * 8);
+    r->blk_pfx = (u64*)a.alloc(blk_pfx_bytes(r->n_blocks));
     CUDA_OK(cudaMemsetAsync(r->hslots, 0, (size_t)r->n_buckets * RUN_BUCKET_SLOTS * 4, e->st));
     j.out_heap = r->heap; j.out_ent_off = r->ent_off; j.out_hslots = r->hslots; j.out_blk_pfx = r->blk_pfx;
     j.out_n_buckets = r->n_buckets; j.out_ord_bits = r->ord_bits;

@@ -225,10 +225,9 @@ cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvali
 cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 cudaError_t cudaMalloc(void** p, size_t n) {
-  const size_t r = (n + 255) & ~(size_t)255;
-  *p = aligned_alloc(256, r ? r : 256);
-  if (!*p) return cudaErrorMemoryAllocation;
-  if (r <= (16u << 20)) memset(*p, 0xCD, r);  // device memory is not zeroed: make a missing memset visible (big slabs stay lazy)
+  // exactly n bytes (ASan's red zone starts right behind them), 256-byte aligned like the real allocator
+  if (posix_memalign(p, 256, n ? n : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  if (n <= (16u << 20)) memset(*p, 0xCD, n);  // device memory is not zeroed: make a missing memset visible (big slabs stay lazy)
   return cudaSuccess;
 }
 cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
