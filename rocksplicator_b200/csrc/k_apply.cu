@@ -14,6 +14,8 @@
 //                aligned heap), then links it into the shard's open-addressed table with a
 //                lock-free, sequence-ordered version chain (CAS on the slot / on a link word).
 //   k_publish  : publishes last_seq to readers (batch atomicity: readers skip newer versions).
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace rsp {
@@ -61,10 +63,10 @@ __device__ __forceinline__ bool get_slice(Cursor& c, u32& off, u32& n) {
   return true;
 }
 
-__global__ void __launch_bounds__(256) k_decode(TickDev t) {
-  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 lane = threadIdx.x & 31;
-  if (warp >= t.n_batches) return;
+// WARP = true: 32 lanes walk the batch `warp` together (uniform control flow, lane 0 writes).  WARP = false
+// (experiment, RSP_DECODE_THREAD=1): the caller is a single thread that owns the batch (lane == 0).
+template <bool WARP>
+__device__ __forceinline__ void decode_batch(const TickDev& t, const u32 warp, const u32 lane) {
   const BatchDesc bd = t.batches[warp];
   Cursor c{t.blob + bd.boff, 12, bd.len, bd.raw_len, t.ts ? __ldg(t.ts + warp) : 0ull};
   u32 status = 0, found = 0, units = 0;
@@ -135,13 +137,28 @@ __global__ void __launch_bounds__(256) k_decode(TickDev t) {
   }
   // unused / rejected reserved op slots must read as invalid for k_insert
   const u32 first_dead = status ? 0u : min(found, bd.op_cap);
-  for (u32 i = first_dead + lane; i < bd.op_cap; i += 32) t.ops[bd.op_base + i].type = kTypeInvalid;
+  for (u32 i = first_dead + lane; i < bd.op_cap; i += (WARP ? 32u : 1u)) t.ops[bd.op_base + i].type = kTypeInvalid;
   if (lane == 0) {
     BatchRes r;
     r.status = status; r.n_ops = status ? 0u : found; r.units = status ? 0u : units;
     r.unit_base = 0; r.seq_base = 0; r.ord_base = 0; r.accepted = 0;
     t.bres[warp] = r;
   }
+}
+
+__global__ void __launch_bounds__(256) k_decode(TickDev t) {
+  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  if (warp >= t.n_batches) return;
+  decode_batch<true>(t, warp, lane);
+}
+
+// EXPERIMENT (RSP_DECODE_THREAD=1, off by default): a thread per batch.  A 105-byte single-Put batch keeps 31 of the
+// 32 lanes of k_decode idle; here 32 batches share a warp (their bytes are read through L1, a line or two per batch).
+__global__ void __launch_bounds__(128) k_decode_thread(TickDev t) {
+  const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= t.n_batches) return;
+  decode_batch<false>(t, b, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -436,6 +453,11 @@ __global__ void k_publish(TickDev t, ShardDev* shards) {
 
 void launch_decode(const TickDev& t, cudaStream_t s) {
   if (!t.n_batches) return;
+  static const bool per_thread = getenv("RSP_DECODE_THREAD") != nullptr && atoi(getenv("RSP_DECODE_THREAD")) != 0;
+  if (per_thread) {
+    k_decode_thread<<<(t.n_batches + 127) / 128, 128, 0, s>>>(t);
+    return;
+  }
   const u32 warps_per_block = 8;
   k_decode<<<(t.n_batches + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(t);
 }

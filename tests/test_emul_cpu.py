@@ -40,13 +40,14 @@ PARITY = ["tests/test_parity_gpu.py", "tests/test_zz_ingest_gpu.py"]
 
 
 def test_parity_suite_under_emulation(emul):
-    out = _pytest_under_emulation(emul[0], {"RSP_DIRECT_RUNS": "0"}, PARITY)
+    out = _pytest_under_emulation(emul[0], {"RSP_DIRECT_RUNS": "0", "RSP_DECODE_THREAD": "0"}, PARITY)
     assert " passed" in out and "failed" not in out
 
 
-def test_parity_suite_under_emulation_direct_runs(emul):
-    """the RSP_DIRECT_RUNS=1 experiment (hash-addressed run heaps, k_multi_get16d): functional check"""
-    out = _pytest_under_emulation(emul[0], {"RSP_DIRECT_RUNS": "1"}, PARITY)
+def test_parity_suite_under_emulation_experiments_on(emul):
+    """functional check of the experiments that wait for GPU time: RSP_DIRECT_RUNS=1 (hash-addressed
+    run heaps, k_multi_get16d) and RSP_DECODE_THREAD=1 (a thread per batch in the decode stage)"""
+    out = _pytest_under_emulation(emul[0], {"RSP_DIRECT_RUNS": "1", "RSP_DECODE_THREAD": "1"}, PARITY)
     assert " passed" in out and "failed" not in out
 
 
