@@ -1132,7 +1132,7 @@ static void iter_fetch(rsp_iter* it, const std::string* key, bool exclusive, boo
     a.shards = nullptr; a.views = it->d_view; a.shard_ix = nullptr; a.keys = d + o_key; a.koff = (const u64*)d;
     a.klen_fixed = 0; a.flags = d + 16; a.max_entries = (u32)it->want; a.out = d + o_out; a.out_stride = it->stride;
     a.n_out = (u32*)(d + 32); a.st = (i32*)(d + 36); a.n = 1;
-    launch_multi_scan(a, e->st);
+    if (e->direct_runs) launch_multi_scan_direct(a, e->st); else launch_multi_scan(a, e->st);
     e->launches++;
     u32 res[2];
     CUDA_OK(cudaMemcpyAsync(res, d + 32, 8, cudaMemcpyDeviceToHost, e->st));
@@ -1626,7 +1626,7 @@ int rsp_multi_scan(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint
   a.koff = (const u64*)(d + o_koff); a.klen_fixed = 0; a.flags = nullptr; a.max_entries = max_entries;
   a.out = d + o_out; a.out_stride = out_stride; a.n_out = (u32*)(d + o_nout); a.st = (i32*)(d + o_st); a.n = (u32)n;
   CUDA_OK(cudaEventRecord(e->ev0, e->st));
-  launch_multi_scan(a, e->st);
+  if (e->direct_runs) launch_multi_scan_direct(a, e->st); else launch_multi_scan(a, e->st);
   e->launches++;
   CUDA_OK(cudaEventRecord(e->ev1, e->st));
   CUDA_OK(cudaMemcpyAsync(n_out, d + o_nout, n * 4, cudaMemcpyDeviceToHost, e->st));
@@ -1675,7 +1675,7 @@ int rsp_multi_scan_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, c
     std::lock_guard<std::mutex> g(e->mu);
     cudaStream_t rs = stream ? (cudaStream_t)stream : e->st;
     reader_begin(e, rs);
-    launch_multi_scan(a, rs);
+    if (e->direct_runs) launch_multi_scan_direct(a, rs); else launch_multi_scan(a, rs);
     reader_end(e, rs);
   }
   e->launches++;

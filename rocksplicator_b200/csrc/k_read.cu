@@ -861,7 +861,10 @@ __device__ u32 run_lower_bound_warp(const RunDev& R, const u8* kp, u32 klen, boo
   return lo + below;
 }
 
-__global__ void __launch_bounds__(128) k_multi_scan(ScanArgs a) {
+// DIRECT = false is the shipped kernel; DIRECT = true (experiment, RSP_DIRECT_RUNS=1) adds the gather form of the
+// streaming fast path for RUN_DIRECT runs, whose consecutive ordinals are not consecutive in memory.
+template <bool DIRECT>
+__device__ __forceinline__ void multi_scan_body(const ScanArgs& a) {
   __shared__ __align__(16) u64 s_pfx_all[SCAN_WARPS][SCAN_STAGE_PFX];
   __shared__ __align__(8) u64 s_mbar[SCAN_WARPS];
   {
@@ -917,6 +920,38 @@ __global__ void __launch_bounds__(128) k_multi_scan(ScanArgs a) {
         // source words of entry r: word 1 = (klen, vlen); key from word 2; value follows (klen % 16 == 0)
         const u64* e = src + (u64)r * R.uniform_units * 2u;
         dst[w] = jw == 0 ? __ldg(e + 1) : __ldg(e + 1 + jw);
+      }
+      if (lane == 0) {
+        a.n_out[q] = cnt;
+        a.st[q] = fst;
+      }
+      return;
+    }
+  }
+
+  if (DIRECT && n_runs == 1 && !reverse && (runs[0].flags & RUN_DIRECT)) {
+    // same record stream as above; entry r of the scan is reached through the restart array
+    const RunDev& R = runs[0];
+    const u32 kl = R.kv_len & 0xffffu, vl = R.kv_len >> 16;
+    const u32 rec = 8u + kl + vl;
+    if ((kl & 15u) == 0 && (vl & 7u) == 0 && ((reinterpret_cast<uintptr_t>(out) | a.out_stride) & 7u) == 0) {
+      u32 start = 0;
+      if (!extreme) {
+        const u32 wi = threadIdx.x >> 5;
+        start = R.n_blocks <= SCAN_STAGE_PFX ? run_lower_bound_warp(R, kp, klen, exclusive, s_pfx_all[wi], &s_mbar[wi], lane)
+                                             : run_lower_bound(R, kp, klen, exclusive);
+      }
+      u32 cnt = min(a.max_entries, R.n_ent - start);
+      i32 fst = 0;
+      if ((u64)cnt * rec > a.out_stride) { cnt = (u32)(a.out_stride / rec); fst = 7; }
+      const u32 wpr = rec >> 3;
+      const u64* heap64 = reinterpret_cast<const u64*>(R.heap);
+      u64* dst = reinterpret_cast<u64*>(out);
+      const u32 total = cnt * wpr;
+      for (u32 w = lane; w < total; w += 32) {
+        const u32 r = w / wpr, jw = w - r * wpr;
+        const u64* e = heap64 + (u64)__ldg(R.ent_off + start + r) * 2u;
+        dst[w] = __ldg(e + 1 + jw);  // word 1 = (klen, vlen), key from word 2, value follows (klen % 16 == 0)
       }
       if (lane == 0) {
         a.n_out[q] = cnt;
@@ -1012,9 +1047,16 @@ __global__ void __launch_bounds__(128) k_multi_scan(ScanArgs a) {
   }
 }
 
+__global__ void __launch_bounds__(128) k_multi_scan(ScanArgs a) { multi_scan_body<false>(a); }
+__global__ void __launch_bounds__(128) k_multi_scan_d(ScanArgs a) { multi_scan_body<true>(a); }
+
 void launch_multi_scan(const ScanArgs& a, cudaStream_t s) {
   if (!a.n) return;
   k_multi_scan<<<(a.n + 3) / 4, 128, 0, s>>>(a);
+}
+void launch_multi_scan_direct(const ScanArgs& a, cudaStream_t s) {
+  if (!a.n) return;
+  k_multi_scan_d<<<(a.n + 3) / 4, 128, 0, s>>>(a);
 }
 
 }  // namespace rsp

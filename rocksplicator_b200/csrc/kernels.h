@@ -142,6 +142,7 @@ struct ScanArgs {
   u32 n;
 };
 void launch_multi_scan(const ScanArgs& a, cudaStream_t s);
+void launch_multi_scan_direct(const ScanArgs& a, cudaStream_t s);  // experiment: + gather fast path for RUN_DIRECT
 
 // ---- flush / compaction ---------------------------------------------------------------------------
 struct SortItem {

@@ -81,6 +81,15 @@ buf = np.zeros(16, dtype=np.uint32)
 assert e.lib.rsp_debug_last_pending(e.h, buf.ctypes.data, 16) == 0
 want = sorted((bytes(keys[i]), bytes(vals[i])) for i in range(n))
 assert s.scan(limit=64) == want[:64]
+# batched range scans (Seek + 128 x Next, the bench's scan shape): the gather form of the streaming fast path
+starts = [want[i][0] for i in (0, 17, 1500, n - 5)] + [b"\x00" * 16, b"\xff" * 16, want[40][0][:15] + b"\xff"]
+res = e.multi_scan([s.index] * len(starts), starts, 128, 128 * 88)
+import bisect
+keys_sorted = [k for k, _ in want]
+for k0, (st_, recs) in zip(starts, res):
+    lo = bisect.bisect_left(keys_sorted, k0)
+    assert st_ == 0 and recs == want[lo:lo + 128], (k0, len(recs))
+assert e.multi_scan([s.index], [want[10][0]], 128, 5 * 88 + 8)[0] == (7, want[10:15])   # output buffer too small: Incomplete
 it = s.iterator(); it.seek_to_last(); assert it.key() == want[-1][0]; it.prev(); assert it.key() == want[-2][0]; it.close()
 # later writes land in the memtable above the direct run; a second compaction rebuilds it
 wb = WriteBatch(); wb.put(bytes(keys[3]), b"x" * 64); wb.delete(bytes(keys[4])); assert s.write(wb.data()) == 0
