@@ -1099,7 +1099,8 @@ struct rsp_iter {
   rsp_shard* s;
   std::vector<std::shared_ptr<Run>> pinned;
   ScanView* d_view = nullptr;
-  std::vector<std::pair<std::string, std::string>> buf;
+  struct Ent { std::string first, second; int status; };  // status != 0: the merge of this key failed (empty value)
+  std::vector<Ent> buf;
   size_t pos = 0;
   bool valid = false;
   bool reverse = false;      // direction the buffer was fetched in
@@ -1108,6 +1109,12 @@ struct rsp_iter {
   size_t want = 16;
   size_t stride = 16384;
 };
+
+// DBIter's status_ is sticky and is raised when the iterator REACHES a key whose merge fails (it keeps that key, with
+// an empty value); entries are fetched ahead in chunks, so the status travels with the entry
+static inline void iter_landed(rsp_iter* it) {
+  if (it->valid && it->buf[it->pos].status) it->status = it->buf[it->pos].status;
+}
 
 // fetch up to it->want entries starting at `key` (or the extreme) in the given direction
 static void iter_fetch(rsp_iter* it, const std::string* key, bool exclusive, bool reverse) {
@@ -1150,20 +1157,22 @@ static void iter_fetch(rsp_iter* it, const std::string* key, bool exclusive, boo
       memcpy(&vl, &h[at + 4], 4);
       std::string k((const char*)&h[at + 8], kl);
       last_key = k;
-      if (vl == 0xffffffffu) {  // operator lives on the host: fold this key against the pinned view
+      if (vl == SCAN_VLEN_HOST_FOLD) {  // operator lives on the host: fold this key against the pinned view
         std::string v;
         const int rc = host_fold_get(e, it->s, (const uint8_t*)k.data(), k.size(), &v, it->d_view);
-        if (rc == RSP_OK) it->buf.emplace_back(std::move(k), std::move(v));
-        else if (rc != RSP_NOT_FOUND) { it->status = rc; it->buf.emplace_back(std::move(k), std::string()); }
+        if (rc == RSP_OK) it->buf.push_back({std::move(k), std::move(v), 0});
+        else if (rc != RSP_NOT_FOUND) it->buf.push_back({std::move(k), std::string(), rc});
         at += 8 + kl;
         // (the scan kernel's scratch was reused by the fold: the copy in `h` is what we keep reading)
+      } else if (vl == SCAN_VLEN_MERGE_FAILED) {
+        it->buf.push_back({std::move(k), std::string(), st > 255 ? (int)(st >> 8) : RSP_CORRUPTION});
+        at += 8 + kl;
       } else {
-        it->buf.emplace_back(std::move(k), std::string((const char*)&h[at + 8 + kl], vl));
+        it->buf.push_back({std::move(k), std::string((const char*)&h[at + 8 + kl], vl), 0});
         at += 8 + kl + vl;
       }
     }
     it->exhausted = !(st == RSP_INCOMPLETE || n_out == it->want);
-    if (st > 255) it->status = st >> 8;  // a failed merge: sticky, as DBIter's status_
     if (it->buf.empty() && !it->exhausted) {
       // every fetched key folded to "deleted": keep going from the last key the kernel returned
       fetch_key = last_key; key = &fetch_key; exclusive = true;
@@ -1173,6 +1182,7 @@ static void iter_fetch(rsp_iter* it, const std::string* key, bool exclusive, boo
   }
   it->valid = !it->buf.empty();
   if (it->want < 1024) it->want *= 4;
+  iter_landed(it);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1568,7 +1578,7 @@ void rsp_iter_next(rsp_iter* it) {
     iter_fetch(it, &k, true, false);
     return;
   }
-  if (it->pos + 1 < it->buf.size()) { it->pos++; return; }
+  if (it->pos + 1 < it->buf.size()) { it->pos++; iter_landed(it); return; }
   if (it->exhausted) { it->valid = false; return; }
   std::string k = it->buf[it->pos].first;
   iter_fetch(it, &k, true, false);
@@ -1581,7 +1591,7 @@ void rsp_iter_prev(rsp_iter* it) {
     iter_fetch(it, &k, true, true);
     return;
   }
-  if (it->pos + 1 < it->buf.size()) { it->pos++; return; }
+  if (it->pos + 1 < it->buf.size()) { it->pos++; iter_landed(it); return; }
   if (it->exhausted) { it->valid = false; return; }
   std::string k = it->buf[it->pos].first;
   iter_fetch(it, &k, true, true);
@@ -1638,7 +1648,18 @@ int rsp_multi_scan(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint
   e->last_ms["scan"] = ms;
   for (size_t i = 0; i < n; i++) {
     if (st[i] == ST_NEED_HOST_MERGE) st[i] = RSP_NOT_SUPPORTED;  // host-folded operators: use the iterator
-    else if (st[i] > 255) st[i] = st[i] >> 8;
+    else if (st[i] > 255) {
+      // a merge failed somewhere in this scan: its record reads as an empty value, the status is the scan's
+      st[i] = st[i] >> 8;
+      u8* r = out + i * out_stride;
+      for (u32 k = 0; k < n_out[i]; k++) {
+        u32 kl, vl;
+        memcpy(&kl, r, 4);
+        memcpy(&vl, r + 4, 4);
+        if (vl == SCAN_VLEN_MERGE_FAILED) { vl = 0; memcpy(r + 4, &vl, 4); }
+        r += 8 + kl + vl;
+      }
+    }
   }
   return RSP_OK;
 }

@@ -1011,14 +1011,16 @@ __device__ __forceinline__ void multi_scan_body(const ScanArgs& a) {
     acc.end_of_versions();
     if (acc.status == 1) continue;  // deleted
     u32 vlen = 0;
-    bool host_fold = false;
+    bool host_fold = false, merge_failed = false;
     if (acc.status == ST_NEED_HOST_MERGE) {
       // the operator lives on the host: hand back the key alone (vlen marker 0xffffffff)
       if (st == 0) st = ST_NEED_HOST_MERGE;
       host_fold = true;
     } else if (acc.status != 0) {
-      // DBIter keeps the key with an empty value and records the (sticky) status
+      // DBIter keeps the key with an empty value and records the (sticky) status; the record carries the marker
+      // SCAN_VLEN_MERGE_FAILED so that an iterator can raise the status when it REACHES this key, as DBIter does
       st = (i32)mk_status((u32)acc.status, acc.msg);
+      merge_failed = true;
     } else {
       vlen = acc.res_len;
     }
@@ -1026,7 +1028,7 @@ __device__ __forceinline__ void multi_scan_body(const ScanArgs& a) {
     if (used + rec > a.out_stride) { if (st == 0) st = 7; break; }
     if (lane == 0) {
       u8 hdr[8];
-      const u32 vl_out = host_fold ? 0xffffffffu : vlen;
+      const u32 vl_out = host_fold ? SCAN_VLEN_HOST_FOLD : (merge_failed ? SCAN_VLEN_MERGE_FAILED : vlen);
       for (u32 b = 0; b < 4; b++) { hdr[b] = (u8)(bk.klen >> (8 * b)); hdr[4 + b] = (u8)(vl_out >> (8 * b)); }
       for (u32 b = 0; b < 8; b++) out[used + b] = hdr[b];
     }

@@ -126,6 +126,9 @@ struct ScanView {
   u32 merge_op;
   u32 pad0, pad1;
 };
+// vlen markers in scan records (the value is absent: the record is [u32 klen][u32 marker][key])
+constexpr u32 SCAN_VLEN_HOST_FOLD = 0xffffffffu;     // the merge operator lives on the host: fold this key there
+constexpr u32 SCAN_VLEN_MERGE_FAILED = 0xfffffffeu;  // the merge failed: empty value, the scan's st holds the status
 struct ScanArgs {
   const ShardDev* shards;   // used when views == nullptr (shard_ix indexes it)
   const ScanView* views;    // or explicit pinned views (one per request)

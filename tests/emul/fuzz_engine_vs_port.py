@@ -1,0 +1,124 @@
+"""TEST INFRASTRUCTURE — differential fuzzer: the engine (compiled against the CPU emulation, tests/emul) against the
+oracle port on random streams: every merge operator, variable and fixed key shapes, tiny and default write buffers
+(forced flushes), flush / compaction at random points, single applies and multi-shard ticks (rsp_apply_many),
+Get / MultiGet / full scans / iterator walks compared after every few batches.  GPU time is too scarce for hundreds of
+seeds; the emulation runs them for free.  `python tests/emul/fuzz_engine_vs_port.py FIRST LAST [env VAR=1 ...]`.
+A short range runs in tests/test_emul_cpu.py.
+"""
+import os
+import random
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from oracle import okv  # noqa: E402
+from rocksplicator_b200 import engine  # noqa: E402
+from streams import random_stream  # noqa: E402
+
+
+def iter_walk(db, keys, seed):
+    rng = random.Random(seed)
+    it = db.iterator()
+    out = []
+    for _ in range(24):
+        r = rng.random()
+        if r < 0.15:
+            it.seek_to_first()
+        elif r < 0.3:
+            it.seek_to_last()
+        elif r < 0.55:
+            k = rng.choice(keys) if rng.random() < 0.7 else bytes(rng.getrandbits(8) for _ in range(rng.randint(0, 5)))
+            it.seek(k)
+        elif r < 0.8:
+            if it.valid():
+                it.next()
+        else:
+            if it.valid():
+                it.prev()
+        out.append((it.valid(), it.key() if it.valid() else None, it.value() if it.valid() else None, it.status()))
+    it.close()
+    return out
+
+
+def compare(s, o, keys, tag):
+    assert s.latest_seq() == o.latest_seq(), (tag, "seq", s.latest_seq(), o.latest_seq())
+    probe = keys + [b"zz-missing", b""]
+    assert s.multi_get(probe) == o.multi_get(probe), (tag, "multi_get")
+    for k in probe[::5]:
+        assert s.get(k) == o.get(k), (tag, "get", k)
+    assert s.scan() == o.scan(), (tag, "scan")
+    assert iter_walk(s, keys, hash(tag) & 0xffff) == iter_walk(o, keys, hash(tag) & 0xffff), (tag, "iter")
+
+
+def one_seed(eng, port, seed):
+    rng = random.Random(seed * 7919 + 3)
+    mop, mname = rng.choice([(okv.MERGE_COUNTER, "counter"), (okv.MERGE_APPEND, "append"),
+                             (okv.MERGE_UINT64ADD, "counter"), (okv.MERGE_NONE, None)])
+    bad = mop == okv.MERGE_COUNTER and rng.random() < 0.25
+    n_shards = rng.choice([1, 1, 3])
+    fixed = rng.random() < 0.35
+    keys, stream = random_stream(9000 + seed, rng.randint(20, 160), n_keys=rng.choice([4, 12, 40, 90]), merge=mname,
+                                 max_ops=rng.choice([1, 3, 8, 25]), var_len=not fixed, bad_operands=bad)
+    wb = rng.choice([0, 0, 2048, 8192])
+    shards = [eng.open_shard("fz%d_%d" % (seed, i), merge_op=mop, write_buffer_bytes=wb) for i in range(n_shards)]
+    oracles = [okv.Okv(port, merge_op=mop) for _ in range(n_shards)]
+    try:
+        i = 0
+        while i < len(stream):
+            if n_shards > 1 or rng.random() < 0.3:
+                # one tick for several batches over several shards; per-shard order == submission order
+                m = min(len(stream) - i, rng.randint(1, 12))
+                six = [rng.randrange(n_shards) for _ in range(m)]
+                st = eng.apply_many([shards[x].index for x in six], [stream[i + j][0] for j in range(m)],
+                                    [stream[i + j][1] for j in range(m)])
+                want = [oracles[six[j]].apply(stream[i + j][0], stream[i + j][1]) for j in range(m)]
+                assert list(st) == want, (seed, i, list(st), want)
+                i += m
+            else:
+                bt, ts = stream[i]
+                assert shards[0].apply(bt, ts) == oracles[0].apply(bt, ts), (seed, i)
+                i += 1
+            r = rng.random()
+            x = rng.randrange(n_shards)
+            if not bad:
+                if r < 0.05:
+                    shards[x].flush()
+                elif r < 0.08:
+                    shards[x].compact()
+            if rng.random() < 0.08:
+                compare(shards[x], oracles[x], keys, (seed, i, x))
+        for x in range(n_shards):
+            compare(shards[x], oracles[x], keys, (seed, "end", x))
+            if not bad:
+                shards[x].compact()
+                compare(shards[x], oracles[x], keys, (seed, "compacted", x))
+    finally:
+        for s in shards:
+            s.close()
+        for o in oracles:
+            o.close()
+
+
+def run(first, last, lib_path, verbose=False):
+    engine.SO_PATH = lib_path
+    port = okv.load_port()
+    eng = engine.Engine(0, arena_bytes=1 << 24)
+    bad = 0
+    for seed in range(first, last):
+        try:
+            one_seed(eng, port, seed)
+        except AssertionError as ex:
+            bad += 1
+            print("DIVERGE seed", seed, str(ex)[:400])
+        if verbose and seed % 10 == 9:
+            print("seed", seed, "bad", bad, flush=True)
+    eng.close()
+    return bad
+
+
+if __name__ == "__main__":
+    lib = os.environ.get("RSP_TEST_EMUL_LIB", os.path.join(ROOT, "tests", "emul", "build", "librsp_b200_emul.so"))
+    print("done bad=", run(int(sys.argv[1]), int(sys.argv[2]), lib, verbose=True))

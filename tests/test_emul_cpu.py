@@ -106,6 +106,16 @@ print("direct-ok")
     assert p.returncode == 0 and "direct-ok" in p.stdout
 
 
+def test_engine_vs_oracle_fuzz_under_emulation(emul):
+    """tests/emul/fuzz_engine_vs_port.py on a few dozen seeds (hundreds run in minutes from the command line)"""
+    env = dict(os.environ)
+    env.update({"RSP_TEST_EMUL_LIB": emul[0]})
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "fuzz_engine_vs_port.py"), "3000", "3060"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    print(p.stdout[-2000:], p.stderr[-2000:])
+    assert p.returncode == 0 and "done bad= 0" in p.stdout
+
+
 def test_host_mirror_over_emulated_engine(emul):
     """tests/cpp/host_tests.cpp's GpuDB-backed cases (replication chain, follower == leader, counter_service config 1,
     ApplicationDBManager, SST export / ingest) against the emulated engine"""

@@ -482,3 +482,43 @@ def test_packed_tick_virtual_trailer(eng, port_lib):
     assert c.last_error == oc.last_error
     for s in (a, b, c):
         s.close()
+
+
+def test_iterator_status_rises_when_the_failing_key_is_reached(eng, port_lib):
+    """DBIter's status_ is sticky and is set when the iterator lands on a key whose merge fails (the key stays, with an
+    empty value) — not earlier, although the engine fetches entries ahead in chunks.  Found by the emulation fuzzer."""
+    s = new_shard(eng, okv.MERGE_COUNTER)
+    o = okv.Okv(port_lib, merge_op=okv.MERGE_COUNTER)
+    wb = WriteBatch()
+    for i in range(40):
+        wb.put(b"k%03d" % i, struct.pack("<q", i))
+    wb.merge(b"k020", b"xyz")          # operand of the wrong size: the counter operator refuses it
+    wb.put(b"k021", b"")               # a legitimately empty value right behind it
+    for db in (s, o):
+        assert db.apply(wb.data(), 5) == 0
+    for flushed in (False, True):
+        if flushed:
+            s.flush()
+        a, b = s.iterator(), o.iterator()
+        a.seek_to_first(), b.seek_to_first()
+        steps = 0
+        while b.valid():
+            assert a.valid() and (a.key(), a.value(), a.status()) == (b.key(), b.value(), b.status()), (flushed, steps)
+            a.next(), b.next()
+            steps += 1
+        assert not a.valid() and a.status() == b.status() != 0 and steps == 40
+        a.close(), b.close()
+        a, b = s.iterator(), o.iterator()
+        a.seek_to_last(), b.seek_to_last()
+        for _ in range(25):
+            assert (a.valid(), a.key(), a.value(), a.status()) == (b.valid(), b.key(), b.value(), b.status()), flushed
+            a.prev(), b.prev()
+        a.seek(b"k030"), b.seek(b"k030")   # the status is sticky: a later Seek does not clear it
+        assert (a.key(), a.status()) == (b.key(), b.status())
+        a.close(), b.close()
+        # the batched scan reports the failure for the scan and an empty value for the key
+        st, recs = eng.multi_scan([s.index], [b"k018"], 5, 4096)[0]
+        assert st == 2 and recs == [(b"k018", struct.pack("<q", 18)), (b"k019", struct.pack("<q", 19)), (b"k020", b""),
+                                    (b"k021", b""), (b"k022", struct.pack("<q", 22))]
+    s.close()
+    o.close()
