@@ -50,6 +50,28 @@ def compare(s, o, keys, tag):
     for k in probe[::5]:
         assert s.get(k) == o.get(k), (tag, "get", k)
     assert s.scan() == o.scan(), (tag, "scan")
+    k16 = [k for k in keys if len(k) == 16]
+    if k16:
+        # the 16-byte-key kernels (k_multi_get16 / k_multi_get16d) through the fixed-shape entry point, hits and misses
+        import numpy as np
+        q = k16 + [bytes(15) + b"\x01", b"\xff" * 16]
+        n = len(q)
+        for stride in (64, 256):
+            vals = np.zeros((n, stride), dtype=np.uint8)
+            vlen = np.zeros(n, dtype=np.uint32)
+            st = np.zeros(n, dtype=np.int32)
+            rc = s.engine.multi_get_fixed(np.full(n, s.index, dtype=np.uint32), np.frombuffer(b"".join(q), dtype=np.uint8).copy(),
+                                          16, vals, stride, vlen, st)
+            assert rc == 0, (tag, "multi_get_fixed rc", rc)
+            want = o.multi_get(q)
+            for i in range(n):
+                w_st, w_v = want[i]
+                if w_st == 0 and len(w_v) > stride:
+                    assert st[i] == 7 and vlen[i] == len(w_v), (tag, "fixed incomplete", i, st[i], vlen[i])
+                else:
+                    assert st[i] == w_st, (tag, "fixed st", i, int(st[i]), w_st)
+                    if w_st == 0:
+                        assert bytes(vals[i, :vlen[i]]) == w_v, (tag, "fixed value", i)
     assert iter_walk(s, keys, hash(tag) & 0xffff) == iter_walk(o, keys, hash(tag) & 0xffff), (tag, "iter")
 
 
