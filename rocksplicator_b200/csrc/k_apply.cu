@@ -173,10 +173,11 @@ __device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(128) k_sequence(TickDev t, ShardDev* shards, ShardFast* fast) {
-  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 lane = threadIdx.x & 31;
-  if (warp >= t.n_groups) return;
+// FUSED = false is the shipped kernel (k_decode ran before it).  FUSED = true (experiment, RSP_FUSE_DECODE=1): each
+// lane decodes its own batch right here (decode_batch<false>), so the tick has one launch and one pass over the
+// per-batch results less.
+template <bool FUSED>
+__device__ __forceinline__ void sequence_body(const TickDev& t, ShardDev* shards, ShardFast* fast, const u32 warp, const u32 lane) {
   const GroupDesc g = t.groups[warp];
   ShardDev* sd = shards + g.shard_ix;
   u32 latch = sd->latch;
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(128) k_sequence(TickDev t, ShardDev* shards, S
     const bool in = j < g.n_batches;
     BatchRes r;
     r.status = 0; r.n_ops = 0; r.units = 0;
+    if (FUSED && in) decode_batch<false>(t, g.first_batch + j, 0);
     if (in) r = t.bres[g.first_batch + j];
     const u32 bad_mask = __ballot_sync(0xffffffffu, in && r.status != 0);
     const u32 first_bad = bad_mask ? (u32)(__ffs(bad_mask) - 1) : 32u;
@@ -247,6 +249,19 @@ __global__ void __launch_bounds__(128) k_sequence(TickDev t, ShardDev* shards, S
     gr.last_seq = seq; gr.tail = tail; gr.count = cnt; gr.latch = latch; gr.pad = 0;
     t.gres[warp] = gr;
   }
+}
+
+__global__ void __launch_bounds__(128) k_sequence(TickDev t, ShardDev* shards, ShardFast* fast) {
+  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  if (warp >= t.n_groups) return;
+  sequence_body<false>(t, shards, fast, warp, lane);
+}
+__global__ void __launch_bounds__(128) k_decode_sequence(TickDev t, ShardDev* shards, ShardFast* fast) {
+  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  if (warp >= t.n_groups) return;
+  sequence_body<true>(t, shards, fast, warp, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -451,8 +466,13 @@ __global__ void k_publish(TickDev t, ShardDev* shards) {
   sd->pub_seq = sd->last_seq;
 }
 
+static bool fuse_decode() {
+  static const bool on = getenv("RSP_FUSE_DECODE") != nullptr && atoi(getenv("RSP_FUSE_DECODE")) != 0;
+  return on;
+}
 void launch_decode(const TickDev& t, cudaStream_t s) {
   if (!t.n_batches) return;
+  if (fuse_decode()) return;  // experiment: decoded inside k_decode_sequence
   static const bool per_thread = getenv("RSP_DECODE_THREAD") != nullptr && atoi(getenv("RSP_DECODE_THREAD")) != 0;
   if (per_thread) {
     k_decode_thread<<<(t.n_batches + 127) / 128, 128, 0, s>>>(t);
@@ -463,6 +483,10 @@ void launch_decode(const TickDev& t, cudaStream_t s) {
 }
 void launch_sequence(const TickDev& t, ShardDev* shards, ShardFast* fast, cudaStream_t s) {
   if (!t.n_groups) return;
+  if (fuse_decode()) {
+    k_decode_sequence<<<(t.n_groups + 3) / 4, 128, 0, s>>>(t, shards, fast);
+    return;
+  }
   k_sequence<<<(t.n_groups + 3) / 4, 128, 0, s>>>(t, shards, fast);
 }
 void launch_insert(const TickDev& t, ShardDev* shards, cudaStream_t s) {

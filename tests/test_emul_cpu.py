@@ -116,6 +116,12 @@ def test_engine_vs_oracle_fuzz_under_emulation(emul):
     assert p.returncode == 0 and "done bad= 0" in p.stdout
 
 
+def test_parity_suite_under_emulation_fused_decode(emul):
+    """RSP_FUSE_DECODE=1 (decode inside the sequencing kernel; excludes RSP_DECODE_THREAD): functional check"""
+    out = _pytest_under_emulation(emul[0], {"RSP_FUSE_DECODE": "1"}, ["tests/test_parity_gpu.py"])
+    assert " passed" in out and "failed" not in out
+
+
 def test_host_mirror_over_emulated_engine(emul):
     """tests/cpp/host_tests.cpp's GpuDB-backed cases (replication chain, follower == leader, counter_service config 1,
     ApplicationDBManager, SST export / ingest) against the emulated engine"""

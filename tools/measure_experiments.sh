@@ -9,10 +9,12 @@ run() { echo "=== $*"; "$@"; echo "rc=$?"; }
 {
   run timeout 600 python -m pytest tests -m gpu -x -q
   RSP_DIRECT_RUNS=1 RSP_DECODE_THREAD=1 run timeout 600 python -m pytest tests -m gpu -x -q
+  RSP_FUSE_DECODE=1 run timeout 600 python -m pytest tests -m gpu -x -q
 } > gpurun_out/exp/parity.log 2>&1
 tail -5 gpurun_out/exp/parity.log
 timeout 300 python bench.py --no-cpu > gpurun_out/exp/bench_shipped.json 2> gpurun_out/exp/bench_shipped.err
 RSP_DECODE_THREAD=1 timeout 300 python bench.py --no-cpu > gpurun_out/exp/bench_decode_thread.json 2> gpurun_out/exp/bench_decode_thread.err
+RSP_FUSE_DECODE=1 timeout 300 python bench.py --no-cpu > gpurun_out/exp/bench_fuse_decode.json 2> gpurun_out/exp/bench_fuse_decode.err
 for load in 0.5 0.25 0.75; do
   RSP_DIRECT_RUNS=1 RSP_DIRECT_LOAD=$load timeout 300 python bench.py --no-cpu > gpurun_out/exp/bench_direct_$load.json 2> gpurun_out/exp/bench_direct_$load.err
 done
