@@ -42,3 +42,22 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".cc")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "okv_" not in txt and "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_product_library_has_no_emulation_or_cpu_path():
+    """librsp_b200.so is the nvcc build: none of tests/emul's symbols, device code for sm_100a inside, and the Python
+    binding names no other library.  (tests/emul builds a separate test-only library from the same sources.)"""
+    import subprocess
+    from rocksplicator_b200 import engine
+    so = os.path.join(ROOT, "rocksplicator_b200", "librsp_b200.so")
+    assert os.path.realpath(engine.SO_PATH) == os.path.realpath(so)
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
+    assert "emul_launch" not in syms and "emul_collective" not in syms
+    elf = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True)
+    if elf.returncode == 0:  # cuobjdump ships with the CUDA toolkit
+        assert "sm_100a" in elf.stdout, elf.stdout[:300]
+    for dp, _, fs in os.walk(os.path.join(ROOT, "rocksplicator_b200")):
+        for f in fs:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "tests/emul" not in txt and "_emul.so" not in txt and "RSP_TEST_EMUL" not in txt, f
