@@ -116,6 +116,16 @@ def test_engine_vs_oracle_fuzz_under_emulation(emul):
     assert p.returncode == 0 and "done bad= 0" in p.stdout
 
 
+@pytest.mark.parametrize("direct", ["0", "1"])
+def test_compaction_size_boundaries_under_emulation(emul, direct):
+    env = dict(os.environ)
+    env.update({"RSP_TEST_EMUL_LIB": emul[0], "RSP_DIRECT_RUNS": direct})
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "sweep_sizes.py")], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=900)
+    print(p.stdout[-1500:], p.stderr[-1500:])
+    assert p.returncode == 0 and "SWEEP OK" in p.stdout
+
+
 def test_parity_suite_under_emulation_fused_decode(emul):
     """RSP_FUSE_DECODE=1 (decode inside the sequencing kernel; excludes RSP_DECODE_THREAD): functional check"""
     out = _pytest_under_emulation(emul[0], {"RSP_FUSE_DECODE": "1"}, ["tests/test_parity_gpu.py"])
