@@ -29,6 +29,7 @@ def _pytest_under_emulation(lib, extra_env, files, timeout=1500):
     env = dict(os.environ)
     env.update(extra_env)
     env["RSP_TEST_EMUL_LIB"] = lib
+    env.setdefault("RSP_TEST_EMUL_ARENA", str(16 << 20))  # 16 MiB slabs: the emulated cudaMalloc poisons them (0xCD)
     p = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider"] + files,
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
     print(p.stdout[-3000:], p.stderr[-2000:])
