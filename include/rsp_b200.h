@@ -159,7 +159,8 @@ int rsp_iter_status(const rsp_iter* it);
  * [u32 klen][u32 vlen][key][value] records at out + i*out_stride; n_out[i] = entries written;
  * st[i] = RSP_INCOMPLETE when out_stride was too small for max_entries (n_out[i] entries are valid); a key whose
  * merge fails is returned with an empty value and st[i] = the failure (what DBIter does).  In the device form such a
- * record carries vlen = 0xfffffffe (and no value bytes), a key that needs a host-side merge operator 0xffffffff. */
+ * record carries vlen = 0xfffffffe (and no value bytes), a key that needs a host-side merge operator 0xffffffff, and a
+ * status other than 0 / RSP_INCOMPLETE has bit 30 set when the scan also ran out of room. */
 int rsp_multi_scan(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys,
                    const uint64_t* koff, uint32_t max_entries, uint8_t* out, size_t out_stride,
                    uint32_t* n_out, int32_t* st);

@@ -1145,8 +1145,9 @@ static void iter_fetch(rsp_iter* it, const std::string* key, bool exclusive, boo
     CUDA_OK(cudaMemcpyAsync(res, d + 32, 8, cudaMemcpyDeviceToHost, e->st));
     CUDA_OK(cudaStreamSynchronize(e->st));
     const u32 n_out = res[0];
-    const i32 st = (i32)res[1];
-    if (n_out == 0 && st == RSP_INCOMPLETE) { it->stride *= 4; continue; }
+    const bool truncated = (i32)res[1] == RSP_INCOMPLETE || ((i32)res[1] & SCAN_ST_TRUNCATED) != 0;
+    const i32 st = (i32)res[1] & ~SCAN_ST_TRUNCATED;
+    if (n_out == 0 && truncated) { it->stride *= 4; continue; }
     std::vector<u8> h(it->stride);
     if (n_out) CUDA_OK(cudaMemcpy(h.data(), d + o_out, it->stride, cudaMemcpyDeviceToHost));
     size_t at = 0;
@@ -1172,7 +1173,9 @@ static void iter_fetch(rsp_iter* it, const std::string* key, bool exclusive, boo
         at += 8 + kl + vl;
       }
     }
-    it->exhausted = !(st == RSP_INCOMPLETE || n_out == it->want);
+    it->exhausted = !(truncated || n_out == it->want);
+    if (g_trace) fprintf(stderr, "[rsp trace] iter_fetch want=%zu stride=%zu reverse=%d exclusive=%d klen=%zu -> n_out=%u st=%d kept=%zu exhausted=%d\n",
+                         it->want, it->stride, (int)reverse, (int)exclusive, key ? key->size() : 0, n_out, st, it->buf.size(), (int)it->exhausted);
     if (it->buf.empty() && !it->exhausted) {
       // every fetched key folded to "deleted": keep going from the last key the kernel returned
       fetch_key = last_key; key = &fetch_key; exclusive = true;
@@ -1647,6 +1650,7 @@ int rsp_multi_scan(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->last_ms["scan"] = ms;
   for (size_t i = 0; i < n; i++) {
+    st[i] &= ~SCAN_ST_TRUNCATED;  // (n_out[i] < max_entries tells the caller that the scan stopped early)
     if (st[i] == ST_NEED_HOST_MERGE) st[i] = RSP_NOT_SUPPORTED;  // host-folded operators: use the iterator
     else if (st[i] > 255) {
       // a merge failed somewhere in this scan: its record reads as an empty value, the status is the scan's

@@ -1025,7 +1025,8 @@ __device__ __forceinline__ void multi_scan_body(const ScanArgs& a) {
       vlen = acc.res_len;
     }
     const u64 rec = 8ull + bk.klen + vlen;
-    if (used + rec > a.out_stride) { if (st == 0) st = 7; break; }
+    // out of room: INCOMPLETE, or its flag on top of a status that is already there (host-fold request, failed merge)
+    if (used + rec > a.out_stride) { st = st == 0 ? 7 : (st | SCAN_ST_TRUNCATED); break; }
     if (lane == 0) {
       u8 hdr[8];
       const u32 vl_out = host_fold ? SCAN_VLEN_HOST_FOLD : (merge_failed ? SCAN_VLEN_MERGE_FAILED : vlen);

@@ -129,6 +129,9 @@ struct ScanView {
 // vlen markers in scan records (the value is absent: the record is [u32 klen][u32 marker][key])
 constexpr u32 SCAN_VLEN_HOST_FOLD = 0xffffffffu;     // the merge operator lives on the host: fold this key there
 constexpr u32 SCAN_VLEN_MERGE_FAILED = 0xfffffffeu;  // the merge failed: empty value, the scan's st holds the status
+// scan status word: 0, 7 (Incomplete: the output stride was too small for max_entries), ST_NEED_HOST_MERGE, or
+// mk_status(code, msg) of a failed merge; the last two carry SCAN_ST_TRUNCATED when the scan ALSO ran out of room
+constexpr i32 SCAN_ST_TRUNCATED = 1 << 30;
 struct ScanArgs {
   const ShardDev* shards;   // used when views == nullptr (shard_ix indexes it)
   const ScanView* views;    // or explicit pinned views (one per request)

@@ -82,7 +82,9 @@ def one_seed(eng, port, seed):
     bad = mop == okv.MERGE_COUNTER and rng.random() < 0.25
     n_shards = rng.choice([1, 1, 3])
     fixed = rng.random() < 0.35
-    keys, stream = random_stream(9000 + seed, rng.randint(20, 160), n_keys=rng.choice([4, 12, 40, 90]), merge=mname,
+    heavy = os.environ.get("FUZZ_HEAVY") == "1"  # longer streams over more keys, flushes twice as often
+    keys, stream = random_stream(9000 + seed, rng.randint(300, 800) if heavy else rng.randint(20, 160),
+                                 n_keys=rng.choice([200, 600]) if heavy else rng.choice([4, 12, 40, 90]), merge=mname,
                                  max_ops=rng.choice([1, 3, 8, 25]), var_len=not fixed, bad_operands=bad)
     wb = rng.choice([0, 0, 2048, 8192])
     shards = [eng.open_shard("fz%d_%d" % (seed, i), merge_op=mop, write_buffer_bytes=wb) for i in range(n_shards)]
@@ -106,9 +108,9 @@ def one_seed(eng, port, seed):
             r = rng.random()
             x = rng.randrange(n_shards)
             if not bad:
-                if r < 0.05:
+                if r < (0.10 if heavy else 0.05):
                     shards[x].flush()
-                elif r < 0.08:
+                elif r < (0.13 if heavy else 0.08):
                     shards[x].compact()
             if rng.random() < 0.08:
                 compare(shards[x], oracles[x], keys, (seed, i, x))
@@ -127,9 +129,14 @@ def one_seed(eng, port, seed):
 def run(first, last, lib_path, verbose=False):
     engine.SO_PATH = lib_path
     port = okv.load_port()
-    eng = engine.Engine(0, arena_bytes=1 << 24)
+    eng = None
     bad = 0
     for seed in range(first, last):
+        if eng is None or seed % 25 == 0:
+            # a fresh engine now and then, with a different number of runs allowed to pile up before they are merged
+            if eng is not None:
+                eng.close()
+            eng = engine.Engine(0, arena_bytes=1 << 24, l0_compaction_trigger=[0, 2, 8, 3][(seed // 25) % 4])
         try:
             one_seed(eng, port, seed)
         except AssertionError as ex:

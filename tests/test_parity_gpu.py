@@ -522,3 +522,41 @@ def test_iterator_status_rises_when_the_failing_key_is_reached(eng, port_lib):
                                     (b"k021", b""), (b"k022", struct.pack("<q", 22))]
     s.close()
     o.close()
+
+
+@pytest.mark.parametrize("merge", [okv.MERGE_APPEND, okv.MERGE_COUNTER])
+def test_long_scan_over_merged_keys_with_large_values(eng, port_lib, merge):
+    """A fetch-ahead chunk that runs out of room while it already carries another status (a key to fold on the host, a
+    failed merge) must still be continued: the iterator once stopped there.  Found by the emulation fuzzer."""
+    s = new_shard(eng, merge)
+    o = okv.Okv(port_lib, merge_op=merge)
+    rnd = random.Random(11)
+    for c in range(8):
+        wb = WriteBatch()
+        for i in range(60):
+            k = b"key%04d" % (c * 60 + i)
+            wb.put(k, rnd.randbytes(rnd.choice([8, 300, 900])))
+            if i % 7 == 0:
+                wb.merge(k, b"tail" if merge == okv.MERGE_APPEND else b"xyz")   # append folds on the host; counter refuses
+        for db in (s, o):
+            assert db.apply(wb.data(), c) == 0
+        if c == 3:
+            s.flush()
+    a, b = s.iterator(), o.iterator()
+    a.seek_to_first(), b.seek_to_first()
+    n = 0
+    while b.valid():
+        assert a.valid() and (a.key(), a.value(), a.status()) == (b.key(), b.value(), b.status()), n
+        a.next(), b.next()
+        n += 1
+    assert not a.valid() and n == 480
+    a.seek_to_last(), b.seek_to_last()
+    n = 0
+    while b.valid():
+        assert a.valid() and (a.key(), a.value()) == (b.key(), b.value()), n
+        a.prev(), b.prev()
+        n += 1
+    assert not a.valid() and n == 480
+    a.close(), b.close()
+    s.close()
+    o.close()
