@@ -89,6 +89,7 @@ def one_seed(eng, port, seed):
     wb = rng.choice([0, 0, 2048, 8192])
     shards = [eng.open_shard("fz%d_%d" % (seed, i), merge_op=mop, write_buffer_bytes=wb) for i in range(n_shards)]
     oracles = [okv.Okv(port, merge_op=mop) for _ in range(n_shards)]
+    live = []  # iterators opened at some point and stepped while writes, flushes and compactions go on (snapshots)
     try:
         i = 0
         while i < len(stream):
@@ -114,12 +115,31 @@ def one_seed(eng, port, seed):
                     shards[x].compact()
             if rng.random() < 0.08:
                 compare(shards[x], oracles[x], keys, (seed, i, x))
+            if rng.random() < 0.06 and len(live) < 6:
+                ia, ib = shards[x].iterator(), oracles[x].iterator()
+                if rng.random() < 0.5:
+                    ia.seek_to_first(), ib.seek_to_first()
+                else:
+                    ia.seek_to_last(), ib.seek_to_last()
+                live.append((ia, ib))
+            for ia, ib in live:
+                for _ in range(3):
+                    got = (ia.valid(), ia.key() if ia.valid() else None, ia.value() if ia.valid() else None, ia.status())
+                    want = (ib.valid(), ib.key() if ib.valid() else None, ib.value() if ib.valid() else None, ib.status())
+                    assert got == want, (seed, i, "live iterator")
+                    if ia.valid():
+                        if rng.random() < 0.7:
+                            ia.next(), ib.next()
+                        else:
+                            ia.prev(), ib.prev()
         for x in range(n_shards):
             compare(shards[x], oracles[x], keys, (seed, "end", x))
             if not bad:
                 shards[x].compact()
                 compare(shards[x], oracles[x], keys, (seed, "compacted", x))
     finally:
+        for ia, ib in live:
+            ia.close(), ib.close()
         for s in shards:
             s.close()
         for o in oracles:
