@@ -49,6 +49,10 @@ static const char* kMsgText[MSG_COUNT] = {
     "Invalid argument: merge_operator is not properly initialized.",
     "Corruption: Error: Could not perform merge.",
     "Busy: update larger than the reserved memtable",
+    "Corruption: bad EndPrepare XID",
+    "Corruption: bad Commit XID",
+    "Corruption: bad Rollback XID",
+    "Corruption: bad WriteBatch DeleteRange",
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -77,6 +77,10 @@ enum : u32 {
   MSG_MERGE_NOT_INIT,
   MSG_MERGE_FAILED,
   MSG_TOO_LARGE,
+  MSG_BAD_END_PREPARE,
+  MSG_BAD_COMMIT,
+  MSG_BAD_ROLLBACK,
+  MSG_BAD_DELETE_RANGE,
   MSG_COUNT
 };
 __host__ __device__ inline u32 mk_status(u32 code, u32 msg) { return (code << 8) | msg; }

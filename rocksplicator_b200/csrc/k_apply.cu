@@ -70,6 +70,7 @@ __device__ __forceinline__ void decode_batch(const TickDev& t, const u32 warp, c
   const BatchDesc bd = t.batches[warp];
   Cursor c{t.blob + bd.boff, 12, bd.len, bd.raw_len, t.ts ? __ldg(t.ts + warp) : 0ull};
   u32 status = 0, found = 0, units = 0;
+  bool range_del = false;
   if (bd.len < 12) {
     status = mk_status(2, MSG_TOO_SMALL);
   } else {
@@ -108,14 +109,29 @@ __device__ __forceinline__ void decode_batch(const TickDev& t, const u32 warp, c
           continue;  // not counted, no sequence number
         case kTypeNoop:
           continue;
-        case kTypeColumnFamilyRangeDeletion:
-        case kTypeRangeDeletion:
+        // two-phase-commit markers: parsed and (outside WAL recovery) ignored by RocksDB; not counted, no sequence number
         case kTypeBeginPrepareXID:
+          continue;
         case kTypeEndPrepareXID:
+          if (!get_slice(c, koff, klen)) status = mk_status(2, MSG_BAD_END_PREPARE);
+          continue;
         case kTypeCommitXID:
+          if (!get_slice(c, koff, klen)) status = mk_status(2, MSG_BAD_COMMIT);
+          continue;
         case kTypeRollbackXID:
-          status = mk_status(3, MSG_UNSUPPORTED_TAG);
-          break;
+          if (!get_slice(c, koff, klen)) status = mk_status(2, MSG_BAD_ROLLBACK);
+          continue;
+        // range deletions: parsed and counted with RocksDB's rules; the batch is refused (NotSupported) only if
+        // everything else about it is valid, so any other defect is reported as RocksDB reports it
+        case kTypeColumnFamilyRangeDeletion:
+          if (!get_varint32(c, cf)) { status = mk_status(2, MSG_BAD_DELETE_RANGE); break; }
+          /* fallthrough */
+        case kTypeRangeDeletion:
+          if (!get_slice(c, koff, klen) || !get_slice(c, voff, vlen)) { status = mk_status(2, MSG_BAD_DELETE_RANGE); break; }
+          if (cf != 0) { status = mk_status(4, MSG_BAD_CF); break; }
+          range_del = true;
+          found++;
+          continue;
         default:
           status = mk_status(2, MSG_UNKNOWN_TAG);
           break;
@@ -134,6 +150,7 @@ __device__ __forceinline__ void decode_batch(const TickDev& t, const u32 warp, c
       found++;
     }
     if (status == 0 && found != count) status = mk_status(2, MSG_WRONG_COUNT);
+    if (status == 0 && range_del) status = mk_status(3, MSG_UNSUPPORTED_TAG);
   }
   // unused / rejected reserved op slots must read as invalid for k_insert
   const u32 first_dead = status ? 0u : min(found, bd.op_cap);

@@ -106,5 +106,20 @@ def corrupt_cases():
         ("varint5", WriteBatch().put(b"a" * 300, b"b" * 70000).data()),
         ("klen_over", g[:12] + b"\x01" + varint32(1000) + b"abc"),
         ("swallow_logdata", WriteBatch().put(b"k", b"").data()[:-1] + varint32(4)),
+        # two-phase-commit markers: RocksDB parses them and, outside WAL recovery, ignores them (not counted)
+        ("2pc_markers_ok", g + b"\x09" + b"\x0a\x03abc" + b"\x0b\x00" + b"\x0c\x01x"),
+        ("2pc_only", bytes(12) + b"\x09\x0a\x01x\x0b\x01x"),
+        ("2pc_begin_is_not_counted", g[:8] + struct.pack("<I", 4) + g[12:] + b"\x09"),
+        ("2pc_end_bad", g + b"\x0a\x7f"),
+        ("2pc_commit_bad", g + b"\x0b\x7f"),
+        ("2pc_rollback_bad", g + b"\x0c\x7f"),
+        # range deletions: only malformed ones here (RocksDB's error class); a well-formed one is refused by this
+        # engine and applied by RocksDB — the one deliberate difference, tested in test_range_deletion_is_refused
+        ("delrange_bad_begin", g[:8] + struct.pack("<I", 4) + g[12:] + b"\x0f\x7f"),
+        ("delrange_bad_end", g[:8] + struct.pack("<I", 4) + g[12:] + b"\x0f\x01a\x7f"),
+        ("delrange_cf_bad_varint", g[:8] + struct.pack("<I", 4) + g[12:] + b"\x0e\xff\xff\xff\xff\xff\xff"),
+        ("delrange_cf9", g[:8] + struct.pack("<I", 4) + g[12:] + b"\x0e\x09\x01a\x01z"),
+        ("delrange_then_unknown_tag", g[:8] + struct.pack("<I", 4) + g[12:] + b"\x0f\x01a\x01z\x40"),
+        ("delrange_wrong_count", g + b"\x0f\x01a\x01z"),
     ]
     return cases

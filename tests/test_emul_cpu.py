@@ -133,6 +133,16 @@ def test_parity_suite_under_emulation_fused_decode(emul):
     assert " passed" in out and "failed" not in out
 
 
+def test_engine_vs_oracle_corruption_fuzz_under_emulation(emul):
+    """mutated WriteBatches: the decode kernel's error classes, texts, latch and all-or-nothing effect vs the oracle"""
+    env = dict(os.environ)
+    env.update({"RSP_TEST_EMUL_LIB": emul[0]})
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "fuzz_corrupt_engine_vs_port.py"), "1000", "1030"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    print(p.stdout[-2000:], p.stderr[-2000:])
+    assert p.returncode == 0 and "done bad= 0" in p.stdout
+
+
 def test_host_mirror_over_emulated_engine(emul):
     """tests/cpp/host_tests.cpp's GpuDB-backed cases (replication chain, follower == leader, counter_service config 1,
     ApplicationDBManager, SST export / ingest) against the emulated engine"""

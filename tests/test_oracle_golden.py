@@ -149,3 +149,14 @@ def test_port_vs_reference_fuzz(port_lib, ref_lib):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run(200, 212, port_lib, ref_lib) == 0
+
+
+def test_port_vs_reference_corruption_fuzz(port_lib, ref_lib):
+    """oracle/fuzz_corrupt_port_vs_ref.py on a few seeds: mutated batches, error class + text + latch + contents"""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "fuzz_corrupt_port_vs_ref.py")
+    spec = importlib.util.spec_from_file_location("fuzz_corrupt_port_vs_ref", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(0, 25, port_lib, ref_lib) == 0

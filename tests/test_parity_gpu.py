@@ -560,3 +560,22 @@ def test_long_scan_over_merged_keys_with_large_values(eng, port_lib, merge):
     a.close(), b.close()
     s.close()
     o.close()
+
+
+def test_range_deletion_is_refused(eng, port_lib):
+    """The one deliberate difference from RocksDB on this path: a well-formed DeleteRange record
+    — which the reference never issues — is refused with NotSupported, whole batch, nothing applied; RocksDB would
+    apply a range tombstone.  Malformed ones fail with RocksDB's own error (tests/golden/corrupt.json)."""
+    for bt in (WriteBatch().put(b"k", b"v").data()[:8] + struct.pack("<I", 2) + b"\x01\x01k\x01v" + b"\x0f\x01a\x01z",
+               bytes(8) + struct.pack("<I", 1) + b"\x0e\x00\x01a\x01z"):
+        s = new_shard(eng)
+        o = okv.Okv(port_lib)
+        for db in (s, o):
+            assert db.apply(WriteBatch().put(b"pre", b"x").data(), 1) == 0
+            assert db.apply(bt, 2) == 3
+            assert db.last_error == "Not implemented: WriteBatch tag outside the replicated hot path"
+            assert db.latest_seq() == 1 and db.scan() == [(b"pre", b"x")]
+        assert s.apply(WriteBatch().put(b"q", b"y").data(), 3) == o.apply(WriteBatch().put(b"q", b"y").data(), 3)
+        assert s.latest_seq() == o.latest_seq() and s.scan() == o.scan()
+        s.close()
+        o.close()
