@@ -86,6 +86,14 @@ def one_seed(eng, port, seed):
     keys, stream = random_stream(9000 + seed, rng.randint(300, 800) if heavy else rng.randint(20, 160),
                                  n_keys=rng.choice([200, 600]) if heavy else rng.choice([4, 12, 40, 90]), merge=mname,
                                  max_ops=rng.choice([1, 3, 8, 25]), var_len=not fixed, bad_operands=bad)
+    if rng.random() < 0.3:
+        # now and then a value far larger than the write buffer (the memtable has to be re-sized for the tick)
+        from rocksplicator_b200.write_batch import WriteBatch
+        for _ in range(rng.randint(1, 3)):
+            big = WriteBatch().put(rng.choice(keys), rng.randbytes(rng.choice([5000, 70000, 300000])))
+            if mname and rng.random() < 0.5:
+                big.merge(rng.choice(keys), (8).to_bytes(8, "little") if mname == "counter" else b"+")
+            stream.insert(rng.randrange(len(stream) + 1), (big.data(), rng.getrandbits(40)))
     wb = rng.choice([0, 0, 2048, 8192])
     shards = [eng.open_shard("fz%d_%d" % (seed, i), merge_op=mop, write_buffer_bytes=wb) for i in range(n_shards)]
     oracles = [okv.Okv(port, merge_op=mop) for _ in range(n_shards)]
@@ -132,6 +140,11 @@ def one_seed(eng, port, seed):
                             ia.next(), ib.next()
                         else:
                             ia.prev(), ib.prev()
+        if n_shards > 1:
+            # one MultiGet call over a mix of shards (what a router fans in): any order, duplicates, misses
+            pick = [(rng.randrange(n_shards), rng.choice(keys + [b"zz-missing"])) for _ in range(150)]
+            got = eng.multi_get([shards[x].index for x, _ in pick], [k for _, k in pick])
+            assert got == [oracles[x].get(k) for x, k in pick], (seed, "cross-shard multi_get")
         for x in range(n_shards):
             compare(shards[x], oracles[x], keys, (seed, "end", x))
             if not bad:
