@@ -788,6 +788,9 @@ __device__ __forceinline__ void warp_copy_bytes(u8* dst, const u8* src, u32 n, u
 // the TMA engine, SASS UBLKCP) instead of a dependent chain of ~log2(n_blocks) global loads; the warp then
 // counts prefixes below / not above the target 32 at a time with ballots, and resolves the final position
 // inside the 1-2 candidate blocks by comparing 32 entry keys at once.
+#ifndef RSP_SCAN_UNROLL
+#define RSP_SCAN_UNROLL 4  // independent loads per lane in the streaming loop (1 = the r01 form)
+#endif
 constexpr u32 SCAN_WARPS = 4;
 constexpr u32 SCAN_STAGE_PFX = 512;  // prefixes staged per warp (4 KB): runs up to 16 K entries
 
@@ -915,11 +918,24 @@ __device__ __forceinline__ void multi_scan_body(const ScanArgs& a) {
       const u64* src = reinterpret_cast<const u64*>(R.heap) + (u64)start * R.uniform_units * 2u;
       u64* dst = reinterpret_cast<u64*>(out);
       const u32 total = cnt * wpr;
-      for (u32 w = lane; w < total; w += 32) {
-        const u32 r = w / wpr, jw = w - r * wpr;
-        // source words of entry r: word 1 = (klen, vlen); key from word 2; value follows (klen % 16 == 0)
-        const u64* e = src + (u64)r * R.uniform_units * 2u;
-        dst[w] = jw == 0 ? __ldg(e + 1) : __ldg(e + 1 + jw);
+      // RSP_SCAN_UNROLL loads are issued before the first of their stores: with one load in flight per warp (what
+      // the plain loop compiles to: LDG, STG, LDG, ...) the kernel is bound by latency x occupancy, not by HBM
+      for (u32 w0 = lane; w0 < total; w0 += 32u * RSP_SCAN_UNROLL) {
+        u64 v[RSP_SCAN_UNROLL];
+#pragma unroll
+        for (u32 u = 0; u < RSP_SCAN_UNROLL; u++) {
+          const u32 w = w0 + 32u * u;
+          if (w < total) {
+            const u32 r = w / wpr, jw = w - r * wpr;
+            // source words of entry r: word 1 = (klen, vlen); key from word 2; value follows (klen % 16 == 0)
+            v[u] = __ldg(src + (u64)r * R.uniform_units * 2u + 1 + jw);
+          }
+        }
+#pragma unroll
+        for (u32 u = 0; u < RSP_SCAN_UNROLL; u++) {
+          const u32 w = w0 + 32u * u;
+          if (w < total) dst[w] = v[u];
+        }
       }
       if (lane == 0) {
         a.n_out[q] = cnt;
@@ -948,10 +964,22 @@ __device__ __forceinline__ void multi_scan_body(const ScanArgs& a) {
       const u64* heap64 = reinterpret_cast<const u64*>(R.heap);
       u64* dst = reinterpret_cast<u64*>(out);
       const u32 total = cnt * wpr;
-      for (u32 w = lane; w < total; w += 32) {
-        const u32 r = w / wpr, jw = w - r * wpr;
-        const u64* e = heap64 + (u64)__ldg(R.ent_off + start + r) * 2u;
-        dst[w] = __ldg(e + 1 + jw);  // word 1 = (klen, vlen), key from word 2, value follows (klen % 16 == 0)
+      for (u32 w0 = lane; w0 < total; w0 += 32u * RSP_SCAN_UNROLL) {
+        u64 v[RSP_SCAN_UNROLL];
+#pragma unroll
+        for (u32 u = 0; u < RSP_SCAN_UNROLL; u++) {
+          const u32 w = w0 + 32u * u;
+          if (w < total) {
+            const u32 r = w / wpr, jw = w - r * wpr;
+            // word 1 = (klen, vlen), key from word 2, value follows (klen % 16 == 0)
+            v[u] = __ldg(heap64 + (u64)__ldg(R.ent_off + start + r) * 2u + 1 + jw);
+          }
+        }
+#pragma unroll
+        for (u32 u = 0; u < RSP_SCAN_UNROLL; u++) {
+          const u32 w = w0 + 32u * u;
+          if (w < total) dst[w] = v[u];
+        }
       }
       if (lane == 0) {
         a.n_out[q] = cnt;
