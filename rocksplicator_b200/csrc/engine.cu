@@ -262,6 +262,8 @@ struct rsp_engine {
   // MultiGet goes through k_multi_get16d.  Off by default; direct_load = entries / slots.
   bool direct_runs = false;
   double direct_load = 0.5;
+  // EXPERIMENT (RSP_MG_PREFETCH=<lookups>): k_multi_get16d<.., PF> requests lookup q + distance's first sectors into L2
+  u32 mg_prefetch = 0;
   u32 mg_parity = 0;
   size_t pending_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1051,7 +1053,8 @@ static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, c
     a.vals = d + o_vals + c0 * val_stride; a.val_stride = val_stride;
     a.vlen = (u32*)(d + o_vlen) + c0; a.st = (i32*)(d + o_st) + c0; a.n = (u32)cn;
     a.n_special = scratch; a.n_pending = scratch + 4 + 2 * c; a.pending = scratch + 4 + 2 * n_chunks + c0; a.parity = 0;
-    if (e->direct_runs) launch_multi_get_direct(a, cs); else launch_multi_get(a, cs);
+    a.pf_dist = e->mg_prefetch;
+    if (e->direct_runs || e->mg_prefetch) launch_multi_get_direct(a, cs); else launch_multi_get(a, cs);
     e->launches += 2;
     CUDA_OK(cudaMemcpyAsync(vlen + c0, d + o_vlen + c0 * 4, cn * 4, cudaMemcpyDeviceToHost, cs));
     CUDA_OK(cudaMemcpyAsync(st + c0, d + o_st + c0 * 4, cn * 4, cudaMemcpyDeviceToHost, cs));
@@ -1226,6 +1229,7 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   if (const char* t = getenv("RSP_STAGE_THREADS")) e->stage_threads = (size_t)std::max(1, atoi(t));
   if (const char* t = getenv("RSP_DIRECT_RUNS")) e->direct_runs = atoi(t) != 0;
   if (const char* t = getenv("RSP_DIRECT_LOAD")) e->direct_load = std::min(0.9, std::max(0.05, atof(t)));
+  if (const char* t = getenv("RSP_MG_PREFETCH")) e->mg_prefetch = (u32)std::max(0, atoi(t));
   CUDA_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   e->single_applies.reset(new rsp::GroupCommit<ApplyReq>([e](std::vector<ApplyReq*>& b) { run_single_applies(e, b); }));
   for (int k = 0; k < 3; k++) {
@@ -1685,7 +1689,8 @@ int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, co
     a.max_shards = e->cfg.max_shards;
     cudaStream_t rs = stream ? (cudaStream_t)stream : e->st;
     reader_begin(e, rs);
-    if (e->direct_runs) launch_multi_get_direct(a, rs); else launch_multi_get(a, rs);
+    a.pf_dist = e->mg_prefetch;
+    if (e->direct_runs || e->mg_prefetch) launch_multi_get_direct(a, rs); else launch_multi_get(a, rs);
     reader_end(e, rs);
   }
   e->launches += 2;

@@ -569,13 +569,48 @@ __device__ __forceinline__ u32 direct_slot(const u8* ent, u32 U, const uint4& kq
   return 0;
 }
 
-template <bool BIG>
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifdef RSP_EMUL
+  (void)p;
+#else
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
+// PF = true (RSP_MG_PREFETCH=<distance>): before its own lookup, every pair requests the first sector(s) lookup
+// q + distance will touch (index bucket, or entry slot of a direct run) into L2.  k_multi_get16 holds ~113 K lookups
+// in flight on 148 SMs and is bound by latency x occupancy (two dependent DRAM trips per lookup); a distance a few
+// times that window turns the first trip of every lookup into an L2 hit without costing a register of occupancy.
+template <bool BIG, bool PF>
 __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16d(GetArgs a) {
   const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) / FL;
   const u32 lane = threadIdx.x & (FL - 1);
   const u32 pbase = (threadIdx.x & 31u) & ~1u;
   const u32 pmask = 3u << pbase;
   if (q >= a.n) return;
+  if (PF) {
+    const u32 qp = q + a.pf_dist;
+    if (qp < a.n && qp >= q) {
+      const u32 psix = __ldg(a.shard_ix + qp);
+      if (psix < a.max_shards) {
+        const uint4 pk = __ldg(reinterpret_cast<const uint4*>(a.keys) + qp);
+        const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(a.fast + psix));
+        const uint4 p1 = __ldg(reinterpret_cast<const uint4*>(a.fast + psix) + 1);
+        const u64 ph = hash_final(hash_step(hash_step(hash_init(16), ((u64)pk.y << 32) | pk.x), ((u64)pk.w << 32) | pk.z));
+        if (((p1.y >> 16) & 0xffu) == 1 && (p1.y & FAST_META_LIVE)) {
+          if (p1.y & FAST_META_DIRECT) {
+            const u32 pU = p0.z & 0xffu, pn = p0.w;
+            const u8* slot = reinterpret_cast<const u8*>(((u64)p0.y << 32) | p0.x) + (u64)(u32)(((u64)(u32)ph * pn) >> 32) * pU * 16u;
+            prefetch_l2(slot + 32u * lane);             // header+key sector / first value sector
+            if (lane == 0 && pU > 4) prefetch_l2(slot + 64u);
+          } else if (((p1.y >> 8) & 0xffu) != 0 && lane == 0) {
+            const uint4* hs = reinterpret_cast<const uint4*>(((u64)p0.w << 32) | p0.z);
+            prefetch_l2(hs + (u64)(u32)(((u64)(u32)ph * p1.x) >> 32) * 2u);
+          }
+        }
+      }
+    }
+  }
   const u64 pol_stream = pol_evict_first();
   u32 six = __ldg(a.shard_ix + q);
   const bool bad_shard = six >= a.max_shards;
@@ -622,8 +657,46 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16d(GetArg
   }
   if (state == 3) {
     if (n_runs == 0) state = 4;
-    else if (!(f1.y & FAST_META_DIRECT)) state = 2;
-    else {
+    else if (!(f1.y & FAST_META_DIRECT)) {
+      // an indexed run: the probe of k_multi_get16 (kept in step with it)
+      const u32 n_buckets = f1.x, ord_bits = f1.y & 0xffu, U = (f1.y >> 8) & 0xffu;
+      if (U == 0 || U >= 255) state = 2;
+      else {
+        const u8* heap = reinterpret_cast<const u8*>(((u64)f0.y << 32) | f0.x);
+        const uint4* hs = reinterpret_cast<const uint4*>(((u64)f0.w << 32) | f0.z);
+        u32 bucket = (u32)(((u64)(u32)h * n_buckets) >> 32);
+        const u32 tag = (u32)(h >> 32) >> ord_bits;
+        u32 m8 = 0, e8 = 1, probe = 0;
+        uint4 sv = make_uint4(0, 0, 0, 0);
+        state = 2;
+#pragma unroll 1
+        for (;;) {
+          if (!m8) {
+            if (probe && e8) { state = 4; break; }
+            if (probe == n_buckets) { state = 4; break; }
+            if (probe) bucket = bucket + 1 == n_buckets ? 0 : bucket + 1;
+            probe++;
+            sv = ldg_pol(hs + (u64)bucket * 2u + lane, pol_evict_last());
+            const u32 m = ((sv.x && (sv.x >> ord_bits) == tag) ? 1u : 0u) | ((sv.y && (sv.y >> ord_bits) == tag) ? 2u : 0u) |
+                          ((sv.z && (sv.z >> ord_bits) == tag) ? 4u : 0u) | ((sv.w && (sv.w >> ord_bits) == tag) ? 8u : 0u);
+            const u32 e = (sv.x == 0 || sv.y == 0 || sv.z == 0 || sv.w == 0) ? 1u : 0u;
+            const u32 mine = m | (e << 4);
+            const u32 other = __shfl_xor_sync(pmask, mine, 1);
+            m8 = lane ? ((other & 15u) | ((mine & 15u) << 4)) : ((mine & 15u) | ((other & 15u) << 4));
+            e8 = (mine | other) >> 4;
+            if (!m8) continue;
+          }
+          const u32 p = __ffs(m8) - 1;
+          m8 &= m8 - 1;
+          const u32 pick = (p & 2u) ? ((p & 1u) ? sv.w : sv.z) : ((p & 1u) ? sv.y : sv.x);
+          const u32 val = __shfl_sync(pmask, pick, pbase + (p >> 2));
+          const u32 r = fast_entry<false, BIG>(heap + (u64)((val & ((1u << ord_bits) - 1u)) - 1u) * U * 16u, U, 1, kq, ~0ull, dst,
+                                               a.val_stride, lane, vlen, pol_stream);
+          if (r == 0) { state = 0; break; }
+          if (r == 2) break;
+        }
+      }
+    } else {
       const u8* heap = reinterpret_cast<const u8*>(((u64)f0.y << 32) | f0.x);
       const u32 U = f0.z & 0xffu, n_slots = f0.w;
       u32 slot = (u32)(((u64)(u32)h * n_slots) >> 32);
@@ -675,8 +748,13 @@ void launch_multi_get_direct(const GetArgs& a, cudaStream_t s) {
   const u32 grid = (a.n + per_block - 1) / per_block;
   cudaMemsetAsync(a.n_pending + a.parity, 0, 4, s);
   const u32 g16 = (a.n + RSP_MG_TPB / FL - 1) / (RSP_MG_TPB / FL);
-  if (a.val_stride > 96) k_multi_get16d<true><<<g16, RSP_MG_TPB, 0, s>>>(a);
-  else k_multi_get16d<false><<<g16, RSP_MG_TPB, 0, s>>>(a);
+  if (a.pf_dist) {
+    if (a.val_stride > 96) k_multi_get16d<true, true><<<g16, RSP_MG_TPB, 0, s>>>(a);
+    else k_multi_get16d<false, true><<<g16, RSP_MG_TPB, 0, s>>>(a);
+  } else {
+    if (a.val_stride > 96) k_multi_get16d<true, false><<<g16, RSP_MG_TPB, 0, s>>>(a);
+    else k_multi_get16d<false, false><<<g16, RSP_MG_TPB, 0, s>>>(a);
+  }
   k_multi_get_pending<<<std::min<u32>(grid, 148u), 256, 0, s>>>(a);
 }
 

@@ -97,6 +97,7 @@ struct GetArgs {
   u32 parity;
   u32* n_special;        // [1] counts lookups whose status is none of OK / NotFound / Incomplete (may be nullptr)
   u32 max_shards;        // shard ids >= this answer InvalidArgument
+  u32 pf_dist;           // experiment (k_multi_get16d<.., PF>): prefetch distance in lookups, 0 = off
 };
 void launch_multi_get(const GetArgs& a, cudaStream_t s);
 // experiment: shards whose only run is RUN_DIRECT are served by k_multi_get16d (everything else -> generic path)
