@@ -506,7 +506,8 @@ def main():
             "steps": K, "warmup": W, "ms_per_step": (mg_total_ms + ap_total_ms) / max(K, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload, "l2": "inputs larger than L2: %.2f GB entry heap per GPU, fresh uniform keys every step" % (NKV * 96 / 1e9),
-                       "timing": "CUDA events on the engine stream, max over ranks", "load_s": round(t_load, 2)},
+                       "timing": "CUDA events on the engine stream, max over ranks", "load_s": round(t_load, 2),
+                       "flags": {k: os.environ[k] for k in sorted(os.environ) if k.startswith("RSP_")}},
             "applies": {"value": applies_per_s, "unit": "applies/s", "ms_per_tick": ap_total_ms / max(K, 1),
                         "kernel_ms_last_tick": ap_kernel_ms, "batches_per_tick": T,
                         "hbm_frac_of_peak": (A_PUT * T / (ap_kernel_ms * 1e-3) / 1e9 / peak) if ap_kernel_ms and ap_kernel_ms > 0 else None,
