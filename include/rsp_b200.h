@@ -183,7 +183,9 @@ int rsp_ingest_sorted(rsp_shard* s, size_t n, const uint8_t* keys, const uint64_
 
 /* ---- device-pointer forms (kernel-level measurement; inputs/outputs already in HBM) -------------
  * `stream` is a cudaStream_t passed as void* (0 = the engine's own read stream).  No host
- * synchronisation is performed; the caller owns ordering and timing. */
+ * synchronisation is performed; the caller owns ordering and timing.  A lookup that needs a host-side merge operator
+ * (RSP_MERGE_CALLBACK shards with merge operands on the key) cannot be finished on the device: its d_st is 100 and the
+ * caller resolves it with rsp_get / rsp_multi_get. */
 int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, const uint8_t* d_keys,
                          uint32_t klen, uint8_t* d_vals, uint32_t val_stride, uint32_t* d_vlen,
                          int32_t* d_st, void* stream);

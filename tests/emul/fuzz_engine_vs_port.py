@@ -63,6 +63,8 @@ def compare(s, o, keys, tag):
             rc = s.engine.multi_get_fixed(np.full(n, s.index, dtype=np.uint32), np.frombuffer(b"".join(q), dtype=np.uint8).copy(),
                                           16, vals, stride, vlen, st)
             assert rc == 0, (tag, "multi_get_fixed rc", rc)
+            if stride == 64 and getattr(s, "fz_device_form", True):
+                st, vlen, vals = device_multi_get(s, q, stride)   # same answers through the device-pointer form
             want = o.multi_get(q)
             for i in range(n):
                 w_st, w_v = want[i]
@@ -73,6 +75,42 @@ def compare(s, o, keys, tag):
                     if w_st == 0:
                         assert bytes(vals[i, :vlen[i]]) == w_v, (tag, "fixed value", i)
     assert iter_walk(s, keys, hash(tag) & 0xffff) == iter_walk(o, keys, hash(tag) & 0xffff), (tag, "iter")
+
+
+def staged_tick(eng, six, batches, ts):
+    """the pre-staged form of a tick (what bench.py times): rsp_stage_build, rsp_reserve, kernels, finish"""
+    import ctypes as C
+    import numpy as np
+    n = len(batches)
+    six = np.ascontiguousarray(six, dtype=np.uint32)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(np.fromiter((len(b) for b in batches), dtype=np.uint64, count=n), out=off[1:])
+    blob = np.frombuffer(b"".join(batches) + b"\0", dtype=np.uint8).copy()
+    tsa = np.ascontiguousarray(ts, dtype=np.uint64)
+    h = C.c_void_p()
+    lib = eng.lib
+    assert lib.rsp_stage_build(eng.h, n, six.ctypes.data, blob.ctypes.data, off.ctypes.data, tsa.ctypes.data, C.byref(h)) == 0
+    st = np.zeros(n, dtype=np.int32)
+    assert lib.rsp_reserve(eng.h, h) == 0
+    assert lib.rsp_apply_staged_device(eng.h, h, None) == 0
+    lib.rsp_apply_staged_finish(eng.h, h, st.ctypes.data)
+    lib.rsp_stage_free(h)
+    return st
+
+
+def device_multi_get(s, q, stride):
+    """rsp_multi_get_device with (emulated) device buffers: what bench.py's kernel-level phase calls"""
+    import numpy as np
+    n = len(q)
+    six = np.full(n, s.index, dtype=np.uint32)
+    keys = np.frombuffer(b"".join(q), dtype=np.uint8).copy()
+    vals = np.zeros((n, stride), dtype=np.uint8)
+    vlen = np.zeros(n, dtype=np.uint32)
+    st = np.full(n, -1, dtype=np.int32)
+    rc = s.engine.lib.rsp_multi_get_device(s.engine.h, n, six.ctypes.data, keys.ctypes.data, 16, vals.ctypes.data, stride,
+                                           vlen.ctypes.data, st.ctypes.data, None)
+    assert rc == 0
+    return st, vlen, vals
 
 
 def one_seed(eng, port, seed):
@@ -97,6 +135,8 @@ def one_seed(eng, port, seed):
     wb = rng.choice([0, 0, 2048, 8192])
     shards = [eng.open_shard("fz%d_%d" % (seed, i), merge_op=mop, write_buffer_bytes=wb) for i in range(n_shards)]
     oracles = [okv.Okv(port, merge_op=mop) for _ in range(n_shards)]
+    for s_ in shards:
+        s_.fz_device_form = mop != okv.MERGE_APPEND  # the device form hands host-folded keys back (status 100)
     live = []  # iterators opened at some point and stepped while writes, flushes and compactions go on (snapshots)
     try:
         i = 0
@@ -105,8 +145,12 @@ def one_seed(eng, port, seed):
                 # one tick for several batches over several shards; per-shard order == submission order
                 m = min(len(stream) - i, rng.randint(1, 12))
                 six = [rng.randrange(n_shards) for _ in range(m)]
-                st = eng.apply_many([shards[x].index for x in six], [stream[i + j][0] for j in range(m)],
-                                    [stream[i + j][1] for j in range(m)])
+                if rng.random() < 0.3:
+                    st = staged_tick(eng, [shards[x].index for x in six], [stream[i + j][0] for j in range(m)],
+                                     [stream[i + j][1] for j in range(m)])
+                else:
+                    st = eng.apply_many([shards[x].index for x in six], [stream[i + j][0] for j in range(m)],
+                                        [stream[i + j][1] for j in range(m)])
                 want = [oracles[six[j]].apply(stream[i + j][0], stream[i + j][1]) for j in range(m)]
                 assert list(st) == want, (seed, i, list(st), want)
                 i += m
