@@ -143,6 +143,29 @@ def test_engine_vs_oracle_corruption_fuzz_under_emulation(emul):
     assert p.returncode == 0 and "done bad= 0" in p.stdout
 
 
+@pytest.mark.parametrize("flags", [{}, {"RSP_DIRECT_RUNS": "1", "RSP_MG_PREFETCH": "100", "RSP_FUSE_DECODE": "1"}],
+                         ids=["shipped", "experiments"])
+def test_bench_control_flow_under_emulation(emul, flags):
+    """bench.py end to end at toy size (tests/emul/bench_dryrun.py): every phase, its own full-size parity assertions
+    and the JSON contract keys — an edit to bench.py or an API drift shows up here, not on the GPU box"""
+    import json
+    env = dict(os.environ)
+    env.update(flags)
+    env["RSP_TEST_EMUL_LIB"] = emul[0]
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "bench_dryrun.py")], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=900)
+    print(p.stdout[-1500:], p.stderr[-2500:])
+    assert p.returncode == 0
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    seen = {k: v for k, v in line["config"]["flags"].items() if not k.startswith("RSP_TEST_")}
+    assert line["metric"] == "multiget_lookups_per_s" and seen == flags
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+
+
 def test_host_mirror_over_emulated_engine(emul):
     """tests/cpp/host_tests.cpp's GpuDB-backed cases (replication chain, follower == leader, counter_service config 1,
     ApplicationDBManager, SST export / ingest) against the emulated engine"""
