@@ -198,7 +198,10 @@ typedef struct rsp_staged rsp_staged;
 int rsp_stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob,
                     const uint64_t* off, const uint64_t* ts_ms, rsp_staged** out); /* H2D once */
 void rsp_stage_free(rsp_staged* st);
-int rsp_reserve(rsp_engine* e, const rsp_staged* st);       /* flush/grow memtables as needed */
+/* Reserve memtable room for the tick (flushing / re-sizing as needed).  Several ticks may be reserved and launched back to
+ * back before their results are folded (rsp_apply_staged_finish, in launch order): each reservation counts the earlier
+ * ones.  RSP_BUSY: a shard is full while earlier ticks are in flight — finish those, then reserve again. */
+int rsp_reserve(rsp_engine* e, const rsp_staged* st);
 int rsp_apply_staged_device(rsp_engine* e, rsp_staged* st, void* stream); /* kernels only */
 int rsp_apply_staged_finish(rsp_engine* e, rsp_staged* st, int32_t* st_out); /* D2H + host seq update */
 

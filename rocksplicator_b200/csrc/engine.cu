@@ -201,6 +201,9 @@ struct rsp_shard {
   u32 index;
   rsp_shard_opts opts;
   ShardDev h;  // host mirror of the device descriptor
+  // upper bounds of ticks that were reserved (and possibly launched) but whose results are not folded into `h` yet:
+  // a later tick is reserved against mirror + in-flight, so several ticks can be on the device back to back
+  u64 inflight_units = 0, inflight_ents = 0;
   std::atomic<u64> last_seq{0};
   u32 latch = 0;
   std::vector<std::shared_ptr<Run>> runs;  // [0] newest
@@ -223,6 +226,7 @@ struct rsp_staged {
   size_t res_bytes = 0;         // gres + per-batch status words, contiguous
   std::vector<u32> group_first;  // staged position of each group's first batch (+ total at the end)
   bool identity_order = false;   // packed ticks: staged position == caller's batch index
+  mutable bool reserved = false; // its upper bounds are counted in the shards' in-flight totals until the results are folded
 };
 
 // one rsp_apply / rsp_write call waiting for its tick
@@ -699,29 +703,49 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
 }
 
 // make sure every shard of the tick has room; flush (batched) or grow memtables as needed
-static bool reserve_for(rsp_engine* e, const rsp_staged* sg) {
+static void unreserve(const rsp_staged* sg) {
+  if (!sg->reserved) return;
+  for (size_t g = 0; g < sg->group_shard.size(); g++) {
+    rsp_shard* s = sg->group_shard[g];
+    s->inflight_units -= std::min<u64>(s->inflight_units, sg->need_units[g]);
+    s->inflight_ents -= std::min<u64>(s->inflight_ents, sg->need_ents[g]);
+  }
+  sg->reserved = false;
+}
+
+// Make room for the tick's upper bounds.  Returns 1 when memtables were flushed or re-sized (work on the engine
+// stream), 0 when nothing had to be done, -1 when a shard is full while earlier ticks are still in flight (their
+// results must be folded first: rsp_apply_staged_finish).
+static int reserve_for(rsp_engine* e, const rsp_staged* sg) {
   bool did_work = false;
+  unreserve(sg);  // reserving twice counts once
+  auto fits = [](const rsp_shard* s, u64 nu, u64 ne) {
+    const u64 tail = (u64)s->h.mt_tail + s->inflight_units, cnt = (u64)s->h.mt_count + s->inflight_ents;
+    return tail + nu <= s->h.mt_heap_cap && cnt + ne <= s->h.mt_ent_cap && (cnt + ne) * 2 <= (u64)s->h.mt_slot_mask + 1;
+  };
   std::vector<rsp_shard*> to_flush;
   for (size_t g = 0; g < sg->group_shard.size(); g++) {
     rsp_shard* s = sg->group_shard[g];
-    const u64 nu = sg->need_units[g], ne = sg->need_ents[g];
-    const bool fits = (u64)s->h.mt_tail + nu <= s->h.mt_heap_cap && (u64)s->h.mt_count + ne <= s->h.mt_ent_cap &&
-                      ((u64)s->h.mt_count + ne) * 2 <= (u64)s->h.mt_slot_mask + 1;
-    if (!fits && s->h.mt_count) to_flush.push_back(s);
+    if (fits(s, sg->need_units[g], sg->need_ents[g])) continue;
+    if (s->inflight_units || s->inflight_ents) return -1;  // the mirror lags the device: neither flush nor re-size now
+    if (s->h.mt_count) to_flush.push_back(s);
   }
   if (!to_flush.empty()) { compact_shards(e, to_flush, false); did_work = true; }
   for (size_t g = 0; g < sg->group_shard.size(); g++) {
     rsp_shard* s = sg->group_shard[g];
     const u64 nu = sg->need_units[g], ne = sg->need_ents[g];
-    const bool fits = (u64)s->h.mt_tail + nu <= s->h.mt_heap_cap && (u64)s->h.mt_count + ne <= s->h.mt_ent_cap &&
-                      ((u64)s->h.mt_count + ne) * 2 <= (u64)s->h.mt_slot_mask + 1;
-    if (!fits) {  // empty but too small for this tick
+    if (!fits(s, nu, ne)) {  // empty but too small for this tick
       alloc_memtable(e, s, nu + nu / 2, ne + ne / 2);
       upload_shard(e, s);
       did_work = true;
     }
   }
-  return did_work;
+  for (size_t g = 0; g < sg->group_shard.size(); g++) {
+    sg->group_shard[g]->inflight_units += sg->need_units[g];
+    sg->group_shard[g]->inflight_ents += sg->need_ents[g];
+  }
+  sg->reserved = true;
+  return did_work ? 1 : 0;
 }
 
 static void tick_launch(rsp_engine* e, rsp_staged* sg, cudaStream_t st) {
@@ -734,6 +758,7 @@ static void tick_launch(rsp_engine* e, rsp_staged* sg, cudaStream_t st) {
 
 // fold a tick's results (per-shard state + one status word per batch) into the host mirrors
 static int tick_results(rsp_staged* sg, const u8* pout, int32_t* st_out) {
+  unreserve(sg);  // the mirrors below now include this tick
   const size_t ng = sg->group_shard.size();
   const GroupRes* gr = (const GroupRes*)pout;
   const u32* bs = (const u32*)(pout + ng * sizeof(GroupRes));
@@ -830,7 +855,11 @@ static int apply_many_packed(rsp_engine* e, size_t n, const uint32_t* shard_ix, 
   sg.need_ents.resize(ng);
   for (size_t g = 0; g < ng; g++) { sg.need_units[g] = pneed[2 * g]; sg.need_ents[g] = pneed[2 * g + 1]; }
   const u32 total_ops = pneed[2 * ng];
-  reserve_for(e, &sg);
+  if (reserve_for(e, &sg) < 0) {
+    // pre-staged ticks are still in flight on these shards and the memtable is full: the caller folds them first
+    if (st_out) for (size_t i = 0; i < n; i++) st_out[i] = RSP_BUSY;
+    return RSP_BUSY;
+  }
   TickDev& t = sg.tick;
   t.blob = dev + o_blob; t.ts = pa.ts; t.batches = pa.batches; t.groups = pa.groups;
   t.bres = (BatchRes*)(dev + o_bres); t.gres = (GroupRes*)(dev + o_out);
@@ -869,7 +898,11 @@ static int apply_many_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, 
   int rc = stage_build(e, n, shard_ix, blob, off, ts_ms, &sg, false);
   if (rc != RSP_OK) return rc;
   const double t1 = now_us();
-  reserve_for(e, &sg);
+  if (reserve_for(e, &sg) < 0) {
+    // pre-staged ticks are still in flight on these shards and the memtable is full: the caller folds them first
+    if (st_out) for (size_t i = 0; i < n; i++) st_out[i] = RSP_BUSY;
+    return RSP_BUSY;
+  }
   CUDA_OK(cudaEventRecord(e->ev0, e->st));
   tick_launch(e, &sg, e->st);
   CUDA_OK(cudaEventRecord(e->ev1, e->st));
@@ -1729,6 +1762,7 @@ int rsp_stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uin
 }
 void rsp_stage_free(rsp_staged* sg) {
   if (!sg) return;
+  if (sg->reserved) { std::lock_guard<std::mutex> g(sg->eng->mu); unreserve(sg); }
   if (sg->dev) { cudaSetDevice(sg->eng->device); cudaFree(sg->dev); }
   delete sg;
 }
@@ -1738,7 +1772,9 @@ int rsp_reserve(rsp_engine* e, const rsp_staged* sg) {
   CUDA_OK(cudaSetDevice(e->device));
   // flushes / re-allocations run on the engine stream: wait only when there were any, so that a tick
   // launched on another stream is ordered after them
-  if (reserve_for(e, sg)) CUDA_OK(cudaStreamSynchronize(e->st));
+  const int r = reserve_for(e, sg);
+  if (r < 0) return RSP_BUSY;  // fold the results of the ticks in flight (rsp_apply_staged_finish), then retry
+  if (r > 0) CUDA_OK(cudaStreamSynchronize(e->st));
   return RSP_OK;
 }
 int rsp_apply_staged_device(rsp_engine* e, rsp_staged* sg, void* stream) {

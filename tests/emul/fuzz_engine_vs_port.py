@@ -95,7 +95,41 @@ def compare(s, o, keys, tag):
 
 
 def staged_tick(eng, six, batches, ts):
-    """the pre-staged form of a tick (what bench.py times): rsp_stage_build, rsp_reserve, kernels, finish"""
+    """the pre-staged form (what bench.py times): the batches go as one tick, or as two or three ticks that are all
+    reserved and launched back to back before the first one's results are folded (in-flight reservations)"""
+    import numpy as np
+    n = len(batches)
+    cuts = sorted(set(random.Random(n * 31 + len(batches[0])).sample(range(1, n), min(n - 1, random.Random(n).randint(0, 2))))) if n > 1 else []
+    parts = [(a, b) for a, b in zip([0] + cuts, cuts + [n])]
+    handles = [_stage(eng, six[a:b], batches[a:b], ts[a:b]) for a, b in parts]
+    lib = eng.lib
+    out = [None] * len(handles)
+    launched = []
+
+    def finish_launched():
+        for j in launched:
+            a, b = parts[j]
+            st = np.zeros(b - a, dtype=np.int32)
+            lib.rsp_apply_staged_finish(eng.h, handles[j], st.ctypes.data)
+            out[j] = [int(x) for x in st]
+        del launched[:]
+
+    for j, h in enumerate(handles):
+        rc = lib.rsp_reserve(eng.h, h)
+        if rc == 11:  # Busy: a shard is full while earlier ticks are in flight — fold those first
+            assert launched
+            finish_launched()
+            rc = lib.rsp_reserve(eng.h, h)
+        assert rc == 0, rc
+        assert lib.rsp_apply_staged_device(eng.h, h, None) == 0
+        launched.append(j)
+    finish_launched()
+    for h in handles:
+        lib.rsp_stage_free(h)
+    return np.array([x for part in out for x in part], dtype=np.int32)
+
+
+def _stage(eng, six, batches, ts):
     import ctypes as C
     import numpy as np
     n = len(batches)
@@ -107,12 +141,7 @@ def staged_tick(eng, six, batches, ts):
     h = C.c_void_p()
     lib = eng.lib
     assert lib.rsp_stage_build(eng.h, n, six.ctypes.data, blob.ctypes.data, off.ctypes.data, tsa.ctypes.data, C.byref(h)) == 0
-    st = np.zeros(n, dtype=np.int32)
-    assert lib.rsp_reserve(eng.h, h) == 0
-    assert lib.rsp_apply_staged_device(eng.h, h, None) == 0
-    lib.rsp_apply_staged_finish(eng.h, h, st.ctypes.data)
-    lib.rsp_stage_free(h)
-    return st
+    return h
 
 
 def device_multi_get(s, q, stride):
