@@ -573,7 +573,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 #ifdef RSP_EMUL
   (void)p;
 #else
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(p)));
 #endif
 }
 
