@@ -1,6 +1,7 @@
 """The C++ mirror of the reference interfaces (rocksplicator_b200/host/): tests/cpp/host_tests.cpp restates the
 reference's own gtest cases (see the header of that file).  CPU part: helpers + the replication protocol over
 a counting DbWrapper; GPU part: the same topologies with GpuDB below the DbWrapper seam."""
+import os
 import subprocess
 
 import pytest
@@ -27,4 +28,6 @@ def test_host_helpers_and_protocol_cpu(host_tests):
 
 @pytest.mark.gpu
 def test_host_gpu_backed(host_tests):
+    if os.environ.get("RSP_TEST_EMUL_LIB"):  # tests/test_emul_cpu.py: the same binary linked against the emulation
+        host_tests = os.path.join(os.path.dirname(os.environ["RSP_TEST_EMUL_LIB"]), "host_tests_emul")
     _run(host_tests, "gpu-only", 600)
