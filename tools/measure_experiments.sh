@@ -25,6 +25,10 @@ done
 RSP_DIRECT_RUNS=1 RSP_MG_PREFETCH=262144 timeout 300 python bench.py --no-cpu > gpurun_out/exp/bench_direct_prefetch.json 2> gpurun_out/exp/bench_direct_prefetch.err
 RSP_DIRECT_RUNS=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_multi_get16d -s 1 -c 1 \
   -o gpurun_out/exp/multiget16d python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/exp/ncu.log 2>&1
+# the scan fast path with one load in flight per lane (the r01 form) against the default four
+RSP_NVCC_EXTRA=-DRSP_SCAN_UNROLL=1 python -m rocksplicator_b200.build --force > gpurun_out/exp/rebuild_unroll1.log 2>&1
+timeout 300 python bench.py --no-cpu > gpurun_out/exp/bench_scan_unroll1.json 2> gpurun_out/exp/bench_scan_unroll1.err
+python -m rocksplicator_b200.build --force > gpurun_out/exp/rebuild_default.log 2>&1
 python - <<'PY'
 import glob, json
 for f in sorted(glob.glob("gpurun_out/exp/bench_*.json")):
