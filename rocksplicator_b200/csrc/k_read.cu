@@ -577,8 +577,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 #endif
 }
 
-// PF = true (RSP_MG_PREFETCH=<distance>): before its own lookup, every pair requests the first sector(s) lookup
-// q + distance will touch (index bucket, or entry slot of a direct run) into L2.  k_multi_get16 holds ~113 K lookups
+// PF = true (RSP_MG_PREFETCH=<distance>): before its own lookup, every pair works two software-pipeline stages for
+// lookups further down the grid: the first sector(s) of lookup q + 2 * distance (index bucket, or entry slot of a
+// direct run), and — for indexed runs — the entry that lookup q + distance's bucket (by now in L2) points at.  k_multi_get16 holds ~113 K lookups
 // in flight on 148 SMs and is bound by latency x occupancy (two dependent DRAM trips per lookup); a distance a few
 // times that window turns the first trip of every lookup into an L2 hit without costing a register of occupancy.
 template <bool BIG, bool PF>
@@ -589,23 +590,46 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16d(GetArg
   const u32 pmask = 3u << pbase;
   if (q >= a.n) return;
   if (PF) {
-    const u32 qp = q + a.pf_dist;
-    if (qp < a.n && qp >= q) {
+    // stage 0, lookup q + 2 * distance: its first sector(s) — index bucket, or entry slot of a direct run
+    // stage 1, lookup q + distance (indexed runs): its bucket should be in L2 by now; read my half of it and request
+    //          the entries of the tag matches, so that BOTH dependent trips of that lookup end in L2
+    for (u32 stage = 0; stage < 2; stage++) {
+      const u32 qp = q + (2u - stage) * a.pf_dist;
+      if (qp >= a.n || qp < q) continue;
       const u32 psix = __ldg(a.shard_ix + qp);
-      if (psix < a.max_shards) {
-        const uint4 pk = __ldg(reinterpret_cast<const uint4*>(a.keys) + qp);
-        const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(a.fast + psix));
-        const uint4 p1 = __ldg(reinterpret_cast<const uint4*>(a.fast + psix) + 1);
-        const u64 ph = hash_final(hash_step(hash_step(hash_init(16), ((u64)pk.y << 32) | pk.x), ((u64)pk.w << 32) | pk.z));
-        if (((p1.y >> 16) & 0xffu) == 1 && (p1.y & FAST_META_LIVE)) {
-          if (p1.y & FAST_META_DIRECT) {
-            const u32 pU = p0.z & 0xffu, pn = p0.w;
-            const u8* slot = reinterpret_cast<const u8*>(((u64)p0.y << 32) | p0.x) + (u64)(u32)(((u64)(u32)ph * pn) >> 32) * pU * 16u;
-            prefetch_l2(slot + 32u * lane);             // header+key sector / first value sector
-            if (lane == 0 && pU > 4) prefetch_l2(slot + 64u);
-          } else if (((p1.y >> 8) & 0xffu) != 0 && lane == 0) {
-            const uint4* hs = reinterpret_cast<const uint4*>(((u64)p0.w << 32) | p0.z);
-            prefetch_l2(hs + (u64)(u32)(((u64)(u32)ph * p1.x) >> 32) * 2u);
+      if (psix >= a.max_shards) continue;
+      const uint4 pk = __ldg(reinterpret_cast<const uint4*>(a.keys) + qp);
+      const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(a.fast + psix));
+      const uint4 p1 = __ldg(reinterpret_cast<const uint4*>(a.fast + psix) + 1);
+      const u64 ph = hash_final(hash_step(hash_step(hash_init(16), ((u64)pk.y << 32) | pk.x), ((u64)pk.w << 32) | pk.z));
+      if (((p1.y >> 16) & 0xffu) != 1 || !(p1.y & FAST_META_LIVE)) continue;
+      if (p1.y & FAST_META_DIRECT) {
+        if (stage == 0) {
+          const u32 pU = p0.z & 0xffu, pn = p0.w;
+          const u8* slot = reinterpret_cast<const u8*>(((u64)p0.y << 32) | p0.x) + (u64)(u32)(((u64)(u32)ph * pn) >> 32) * pU * 16u;
+          prefetch_l2(slot + 32u * lane);  // header+key sector / first value sector
+          if (lane == 0 && pU > 4) prefetch_l2(slot + 64u);
+        }
+        continue;
+      }
+      const u32 pU = (p1.y >> 8) & 0xffu, pob = p1.y & 0xffu;
+      if (pU == 0 || pU >= 255) continue;
+      const uint4* hs = reinterpret_cast<const uint4*>(((u64)p0.w << 32) | p0.z);
+      const u32 bucket = (u32)(((u64)(u32)ph * p1.x) >> 32);
+      if (stage == 0) {
+        if (lane == 0) prefetch_l2(hs + (u64)bucket * 2u);
+      } else {
+        const uint4 sv = __ldg(hs + (u64)bucket * 2u + lane);
+        const u32 tag = (u32)(ph >> 32) >> pob, omask = (1u << pob) - 1u;
+        const u8* heap = reinterpret_cast<const u8*>(((u64)p0.y << 32) | p0.x);
+        const u32 w[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+        for (u32 i = 0; i < 4; i++) {
+          if (w[i] && (w[i] >> pob) == tag) {
+            const u8* ent = heap + (u64)((w[i] & omask) - 1u) * pU * 16u;
+            prefetch_l2(ent);
+            prefetch_l2(ent + 32u);
+            if (pU > 4) prefetch_l2(ent + 64u);
           }
         }
       }
