@@ -496,10 +496,46 @@ def main():
         assert rc == 0 and v == w, "apply parity failed"
     assert sum(s.latest_seq() for s in shards) == NKV + n_ticks_total * T
 
+    # ---- config-2 variant: MultiGet while the newest version of many keys is still in the memtables -----
+    # (every update tick above landed in a memtable: nothing has been flushed since the load).  Informational: a
+    # failure here is reported in the line, it does not void the phases above.
+    mt_ms, mt_err, mt_entries = -1.0, None, 0
+    try:
+        mt_entries = int(sum(s.stats()["memtable_entries"] for s in shards))
+        for i in range(W):
+            mg(i)
+        torch.cuda.synchronize()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record(stream)
+        for k in range(K):
+            mg(W + k)
+        m1.record(stream)
+        torch.cuda.synchronize()
+        mt_ms = float(m0.elapsed_time(m1))
+        assert int(d_st.count_nonzero().item()) == 0 and int((d_vlen != 64).count_nonzero().item()) == 0, "status / length"
+        # full-size parity: the expected version of every queried key is its last update tick (0 = never updated)
+        uk = np.fromiter(lastver.keys(), dtype=np.uint64, count=len(lastver))
+        uv = np.fromiter(lastver.values(), dtype=np.int64, count=len(lastver))
+        order = np.argsort(uk)
+        uk, uv = uk[order], uv[order]
+        lastq = q_idx[W + K - 1] if K else q_idx[-1]
+        pos = np.minimum(np.searchsorted(uk, lastq), len(uk) - 1)
+        qver = np.where(uk[pos] == lastq, uv[pos], 0)
+        got = d_vals.cpu().numpy().reshape(Q, 64)
+        qsh = (lastq % np.uint64(S)).astype(np.int64)
+        for v in np.unique(qver):
+            m = qver == v
+            assert np.array_equal(got[m], synth.values(seed, qsh[m], lastq[m], int(v))), "value parity (version %d)" % v
+    except Exception as ex:  # noqa: BLE001
+        mt_err = "%s: %s" % (type(ex).__name__, str(ex)[:160])
+
     # ---- numbers ---------------------------------------------------------------------------------------
     peak, peak_src = peaks()
     # every collective is issued by every rank, before any rank-0-only code
     tot_lookups = sum_over_ranks(Q * K)
+    mt_ms_all = max_over_ranks(mt_ms)
+    mt_failed = sum_over_ranks(1.0 if mt_err else 0.0)
+    mt_entries_all = sum_over_ranks(float(mt_entries))
     tot_applies = sum_over_ranks(T * K)
     tot_scans = sum_over_ranks(NSC * K)
     tot_scan_entries = sum_over_ranks(entries_last * K)
@@ -536,6 +572,10 @@ def main():
             "roofline": {"kernel": "k_multi_get16", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_lookup": A_GET,
                          "lookups_per_launch": Q, "launch_ms": mg_kernel_ms},
+            "memtable": ({"error": mt_err or "failed on another rank"} if mt_failed else
+                         {"what": "config-2 variant: the same uniform MultiGet with the update ticks still in the memtables (entries there = %.0f %% of the key count; nothing flushed since the load); values checked at full size" % (100.0 * mt_entries_all / max(1, NKV * world)),
+                          "lookups_per_s": tot_lookups / (mt_ms_all * 1e-3), "memtable_entries": int(mt_entries_all),
+                          "hbm_frac_of_peak_algorithmic": A_GET * Q / (mt_ms_all * 1e-3 / max(K, 1)) / 1e9 / peak}),
             "zipf": {"theta": 0.99, "lookups_per_s": tot_lookups / (zipf_ms * 1e-3), "hbm_frac_of_peak_algorithmic": A_GET * Q / (zipf_ms * 1e-3 / max(K, 1)) / 1e9 / peak},
             "mixed": {"what": "config 3: %d apply ticks on the engine stream concurrent with %d MultiGet launches on a second stream" % (K, K),
                       "lookups_per_s": tot_lookups / (mixed_get_ms * 1e-3), "applies_per_s": tot_applies / (mixed_apply_ms * 1e-3),

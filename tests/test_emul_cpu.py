@@ -164,6 +164,7 @@ def test_bench_control_flow_under_emulation(emul, flags):
     assert line["metric"] == "multiget_lookups_per_s" and seen == flags
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert "error" not in line["memtable"] and line["memtable"]["lookups_per_s"] > 0 and line["memtable"]["memtable_entries"] > 0
 
 
 def test_host_mirror_over_emulated_engine(emul):
