@@ -268,6 +268,10 @@ struct rsp_engine {
   double direct_load = 0.5;
   // EXPERIMENT (RSP_MG_PREFETCH=<lookups>): k_multi_get16d<.., PF> requests lookup q + distance's first sectors into L2
   u32 mg_prefetch = 0;
+  // EXPERIMENT (RSP_MG_MULTIRUN=1): per-run descriptors for k_multi_get16d, so a shard with several runs stays on the
+  // fast path (newest run first) instead of the generic kernel
+  bool mg_multirun = false;
+  ShardFast* d_fast_runs = nullptr;  // = d_fast + max_shards: [max_shards][RSP_MAX_RUNS], same allocation
   u32 mg_parity = 0;
   size_t pending_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -309,19 +313,25 @@ static void upload_shard(rsp_engine* e, rsp_shard* s) {
     else memset(&s->h.runs[i], 0, sizeof(RunDev));
   }
   CUDA_OK(cudaMemcpyAsync(e->d_shards + s->index, &s->h, sizeof(ShardDev), cudaMemcpyHostToDevice, e->st));
-  ShardFast f;
-  memset(&f, 0, sizeof(f));
-  if (!s->runs.empty()) {
-    const Run& r0 = *s->runs[0];
-    f.run0_heap = (u64)r0.heap; f.run0_hslots = (u64)r0.hslots; f.n_buckets = r0.n_buckets;
-    f.meta = r0.ord_bits | (std::min<u32>(r0.uniform_units, 255u) << 8);
-    if (r0.flags & RUN_DIRECT) {
+  auto describe = [](const Run& r, ShardFast* f) {
+    f->run0_heap = (u64)r.heap; f->run0_hslots = (u64)r.hslots; f->n_buckets = r.n_buckets;
+    f->meta = r.ord_bits | (std::min<u32>(r.uniform_units, 255u) << 8);
+    if (r.flags & RUN_DIRECT) {
       // uniform_units is 0 for such a run, so k_multi_get16 defers to the generic path; k_multi_get16d reads the
       // slot geometry from the (for it unused) index pointer field
-      const u32 U = 1u + units_of(r0.kv_len & 0xffffu) + units_of(r0.kv_len >> 16);
-      f.run0_hslots = (u64)U | ((u64)(r0.heap_units / U) << 32);
-      f.meta |= FAST_META_DIRECT;
+      const u32 U = 1u + units_of(r.kv_len & 0xffffu) + units_of(r.kv_len >> 16);
+      f->run0_hslots = (u64)U | ((u64)(r.heap_units / U) << 32);
+      f->meta |= FAST_META_DIRECT;
     }
+  };
+  ShardFast f;
+  memset(&f, 0, sizeof(f));
+  if (!s->runs.empty()) describe(*s->runs[0], &f);
+  if (e->d_fast_runs) {
+    ShardFast fr[RSP_MAX_RUNS];
+    memset(fr, 0, sizeof(fr));
+    for (size_t i = 0; i < s->runs.size() && i < RSP_MAX_RUNS; i++) describe(*s->runs[i], &fr[i]);
+    CUDA_OK(cudaMemcpyAsync(e->d_fast_runs + (size_t)s->index * RSP_MAX_RUNS, fr, sizeof(fr), cudaMemcpyHostToDevice, e->st));
   }
   f.meta |= (u32)std::min<size_t>(s->runs.size(), 255) << 16;
   f.meta |= 1u << 24;  // live
@@ -1086,8 +1096,8 @@ static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, c
     a.vals = d + o_vals + c0 * val_stride; a.val_stride = val_stride;
     a.vlen = (u32*)(d + o_vlen) + c0; a.st = (i32*)(d + o_st) + c0; a.n = (u32)cn;
     a.n_special = scratch; a.n_pending = scratch + 4 + 2 * c; a.pending = scratch + 4 + 2 * n_chunks + c0; a.parity = 0;
-    a.pf_dist = e->mg_prefetch;
-    if (e->direct_runs || e->mg_prefetch) launch_multi_get_direct(a, cs); else launch_multi_get(a, cs);
+    a.pf_dist = (e->mg_prefetch & ~GET_MULTIRUN) | (e->mg_multirun ? GET_MULTIRUN : 0u);
+    if (e->direct_runs || e->mg_prefetch || e->mg_multirun) launch_multi_get_direct(a, cs); else launch_multi_get(a, cs);
     e->launches += 2;
     CUDA_OK(cudaMemcpyAsync(vlen + c0, d + o_vlen + c0 * 4, cn * 4, cudaMemcpyDeviceToHost, cs));
     CUDA_OK(cudaMemcpyAsync(st + c0, d + o_st + c0 * 4, cn * 4, cudaMemcpyDeviceToHost, cs));
@@ -1275,8 +1285,13 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   CUDA_OK(cudaEventCreate(&e->ev1));
   CUDA_OK(cudaMalloc(&e->d_shards, sizeof(ShardDev) * e->cfg.max_shards));
   CUDA_OK(cudaMemset(e->d_shards, 0, sizeof(ShardDev) * e->cfg.max_shards));
-  CUDA_OK(cudaMalloc(&e->d_fast, sizeof(ShardFast) * e->cfg.max_shards));
-  CUDA_OK(cudaMemset(e->d_fast, 0, sizeof(ShardFast) * e->cfg.max_shards));
+  if (const char* t = getenv("RSP_MG_MULTIRUN")) e->mg_multirun = atoi(t) != 0;
+  {
+    const size_t n_fast = (size_t)e->cfg.max_shards * (e->mg_multirun ? 1 + RSP_MAX_RUNS : 1);
+    CUDA_OK(cudaMalloc(&e->d_fast, sizeof(ShardFast) * n_fast));
+    CUDA_OK(cudaMemset(e->d_fast, 0, sizeof(ShardFast) * n_fast));
+    if (e->mg_multirun) e->d_fast_runs = e->d_fast + e->cfg.max_shards;
+  }
   *out = e;
   return RSP_OK;
 }
@@ -1722,8 +1737,8 @@ int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, co
     a.max_shards = e->cfg.max_shards;
     cudaStream_t rs = stream ? (cudaStream_t)stream : e->st;
     reader_begin(e, rs);
-    a.pf_dist = e->mg_prefetch;
-    if (e->direct_runs || e->mg_prefetch) launch_multi_get_direct(a, rs); else launch_multi_get(a, rs);
+    a.pf_dist = (e->mg_prefetch & ~GET_MULTIRUN) | (e->mg_multirun ? GET_MULTIRUN : 0u);
+    if (e->direct_runs || e->mg_prefetch || e->mg_multirun) launch_multi_get_direct(a, rs); else launch_multi_get(a, rs);
     reader_end(e, rs);
   }
   e->launches += 2;

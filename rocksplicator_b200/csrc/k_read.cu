@@ -577,6 +577,61 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 #endif
 }
 
+// One run of a shard for k_multi_get16d: g0/g1 are the run's 32-byte descriptor in ShardFast's layout (heap pointer,
+// index pointer or direct geometry, bucket count, meta).  Returns 0 = served, 2 = generic path, 4 = not in this run.
+template <bool BIG>
+__device__ __forceinline__ u32 probe_one_run(const uint4& g0, const uint4& g1, const uint4& kq, u64 h, u8* dst, u64 val_stride,
+                                             u32 lane, u32 pmask, u32 pbase, u32& vlen, u64 pol_stream) {
+  const u8* heap = reinterpret_cast<const u8*>(((u64)g0.y << 32) | g0.x);
+  if (!(g1.y & FAST_META_DIRECT)) {
+    // an indexed run: the probe of k_multi_get16 (kept in step with it)
+    const u32 n_buckets = g1.x, ord_bits = g1.y & 0xffu, U = (g1.y >> 8) & 0xffu;
+    if (U == 0 || U >= 255) return 2;
+    const uint4* hs = reinterpret_cast<const uint4*>(((u64)g0.w << 32) | g0.z);
+    u32 bucket = (u32)(((u64)(u32)h * n_buckets) >> 32);
+    const u32 tag = (u32)(h >> 32) >> ord_bits;
+    u32 m8 = 0, e8 = 1, probe = 0;
+    uint4 sv = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+    for (;;) {
+      if (!m8) {
+        if (probe && e8) return 4;
+        if (probe == n_buckets) return 4;
+        if (probe) bucket = bucket + 1 == n_buckets ? 0 : bucket + 1;
+        probe++;
+        sv = ldg_pol(hs + (u64)bucket * 2u + lane, pol_evict_last());
+        const u32 m = ((sv.x && (sv.x >> ord_bits) == tag) ? 1u : 0u) | ((sv.y && (sv.y >> ord_bits) == tag) ? 2u : 0u) |
+                      ((sv.z && (sv.z >> ord_bits) == tag) ? 4u : 0u) | ((sv.w && (sv.w >> ord_bits) == tag) ? 8u : 0u);
+        const u32 e = (sv.x == 0 || sv.y == 0 || sv.z == 0 || sv.w == 0) ? 1u : 0u;
+        const u32 mine = m | (e << 4);
+        const u32 other = __shfl_xor_sync(pmask, mine, 1);
+        m8 = lane ? ((other & 15u) | ((mine & 15u) << 4)) : ((mine & 15u) | ((other & 15u) << 4));
+        e8 = (mine | other) >> 4;
+        if (!m8) continue;
+      }
+      const u32 p = __ffs(m8) - 1;
+      m8 &= m8 - 1;
+      const u32 pick = (p & 2u) ? ((p & 1u) ? sv.w : sv.z) : ((p & 1u) ? sv.y : sv.x);
+      const u32 val = __shfl_sync(pmask, pick, pbase + (p >> 2));
+      const u32 r = fast_entry<false, BIG>(heap + (u64)((val & ((1u << ord_bits) - 1u)) - 1u) * U * 16u, U, 1, kq, ~0ull, dst,
+                                           val_stride, lane, vlen, pol_stream);
+      if (r == 0) return 0;
+      if (r == 2) return 2;
+    }
+  }
+  const u32 U = g0.z & 0xffu, n_slots = g0.w;
+  u32 slot = (u32)(((u64)(u32)h * n_slots) >> 32);
+#pragma unroll 1
+  for (u32 probe = 0; probe < n_slots; probe++) {
+    const u32 r = direct_slot<BIG>(heap + (u64)slot * U * 16u, U, kq, dst, val_stride, lane, vlen);
+    if (r == 0) return 0;
+    if (r == 4) return 4;
+    if (r == 2) return 2;
+    slot = slot + 1 == n_slots ? 0 : slot + 1;
+  }
+  return 2;
+}
+
 // PF = true (RSP_MG_PREFETCH=<distance>): before its own lookup, every pair works two software-pipeline stages for
 // lookups further down the grid: the first sector(s) of lookup q + 2 * distance (index bucket, or entry slot of a
 // direct run), and — for indexed runs — the entry that lookup q + distance's bucket (by now in L2) points at.  k_multi_get16 holds ~113 K lookups
@@ -594,7 +649,7 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16d(GetArg
     // stage 1, lookup q + distance (indexed runs): its bucket should be in L2 by now; read my half of it and request
     //          the entries of the tag matches, so that BOTH dependent trips of that lookup end in L2
     for (u32 stage = 0; stage < 2; stage++) {
-      const u32 qp = q + (2u - stage) * a.pf_dist;
+      const u32 qp = q + (2u - stage) * (a.pf_dist & ~GET_MULTIRUN);
       if (qp >= a.n || qp < q) continue;
       const u32 psix = __ldg(a.shard_ix + qp);
       if (psix >= a.max_shards) continue;
@@ -648,7 +703,7 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16d(GetArg
   u8* dst = a.vals + (u64)q * a.val_stride;
   u32 state = 3;  // 0 served, 2 generic path, 3 undecided, 4 not found
   u32 vlen = 0;
-  if (n_runs > 1 || ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u) || bad_shard || !(f1.y & FAST_META_LIVE)) state = 2;
+  if ((n_runs > 1 && !(a.pf_dist & GET_MULTIRUN)) || ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u) || bad_shard || !(f1.y & FAST_META_LIVE)) state = 2;
   if (state == 3 && f1.z /* mt_count */) {
     // ---- memtable stage: identical to k_multi_get16
     const uint4* dp = reinterpret_cast<const uint4*>(a.shards + six);
@@ -680,59 +735,18 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16d(GetArg
     }
   }
   if (state == 3) {
-    if (n_runs == 0) state = 4;
-    else if (!(f1.y & FAST_META_DIRECT)) {
-      // an indexed run: the probe of k_multi_get16 (kept in step with it)
-      const u32 n_buckets = f1.x, ord_bits = f1.y & 0xffu, U = (f1.y >> 8) & 0xffu;
-      if (U == 0 || U >= 255) state = 2;
-      else {
-        const u8* heap = reinterpret_cast<const u8*>(((u64)f0.y << 32) | f0.x);
-        const uint4* hs = reinterpret_cast<const uint4*>(((u64)f0.w << 32) | f0.z);
-        u32 bucket = (u32)(((u64)(u32)h * n_buckets) >> 32);
-        const u32 tag = (u32)(h >> 32) >> ord_bits;
-        u32 m8 = 0, e8 = 1, probe = 0;
-        uint4 sv = make_uint4(0, 0, 0, 0);
-        state = 2;
-#pragma unroll 1
-        for (;;) {
-          if (!m8) {
-            if (probe && e8) { state = 4; break; }
-            if (probe == n_buckets) { state = 4; break; }
-            if (probe) bucket = bucket + 1 == n_buckets ? 0 : bucket + 1;
-            probe++;
-            sv = ldg_pol(hs + (u64)bucket * 2u + lane, pol_evict_last());
-            const u32 m = ((sv.x && (sv.x >> ord_bits) == tag) ? 1u : 0u) | ((sv.y && (sv.y >> ord_bits) == tag) ? 2u : 0u) |
-                          ((sv.z && (sv.z >> ord_bits) == tag) ? 4u : 0u) | ((sv.w && (sv.w >> ord_bits) == tag) ? 8u : 0u);
-            const u32 e = (sv.x == 0 || sv.y == 0 || sv.z == 0 || sv.w == 0) ? 1u : 0u;
-            const u32 mine = m | (e << 4);
-            const u32 other = __shfl_xor_sync(pmask, mine, 1);
-            m8 = lane ? ((other & 15u) | ((mine & 15u) << 4)) : ((mine & 15u) | ((other & 15u) << 4));
-            e8 = (mine | other) >> 4;
-            if (!m8) continue;
-          }
-          const u32 p = __ffs(m8) - 1;
-          m8 &= m8 - 1;
-          const u32 pick = (p & 2u) ? ((p & 1u) ? sv.w : sv.z) : ((p & 1u) ? sv.y : sv.x);
-          const u32 val = __shfl_sync(pmask, pick, pbase + (p >> 2));
-          const u32 r = fast_entry<false, BIG>(heap + (u64)((val & ((1u << ord_bits) - 1u)) - 1u) * U * 16u, U, 1, kq, ~0ull, dst,
-                                               a.val_stride, lane, vlen, pol_stream);
-          if (r == 0) { state = 0; break; }
-          if (r == 2) break;
-        }
+    // newest run first; a run that does not hold the key hands over to the next older one (RSP_MG_MULTIRUN=1 provides
+    // the descriptors of runs 1.. next to ShardFast; without them a shard with several runs took the generic path above)
+    state = 4;
+    for (u32 r = 0; r < n_runs; r++) {
+      uint4 g0 = f0, g1 = f1;
+      if (r) {
+        const uint4* fr = reinterpret_cast<const uint4*>(a.fast + a.max_shards) + ((u64)six * RSP_MAX_RUNS + r) * 2u;
+        g0 = __ldg(fr);
+        g1 = __ldg(fr + 1);
       }
-    } else {
-      const u8* heap = reinterpret_cast<const u8*>(((u64)f0.y << 32) | f0.x);
-      const u32 U = f0.z & 0xffu, n_slots = f0.w;
-      u32 slot = (u32)(((u64)(u32)h * n_slots) >> 32);
-      state = 2;
-#pragma unroll 1
-      for (u32 probe = 0; probe < n_slots; probe++) {
-        const u32 r = direct_slot<BIG>(heap + (u64)slot * U * 16u, U, kq, dst, a.val_stride, lane, vlen);
-        if (r == 0) { state = 0; break; }
-        if (r == 4) { state = 4; break; }
-        if (r == 2) break;
-        slot = slot + 1 == n_slots ? 0 : slot + 1;
-      }
+      const u32 rs = probe_one_run<BIG>(g0, g1, kq, h, dst, a.val_stride, lane, pmask, pbase, vlen, pol_stream);
+      if (rs != 4) { state = rs; break; }
     }
   }
   if (lane == 0) {
@@ -772,7 +786,7 @@ void launch_multi_get_direct(const GetArgs& a, cudaStream_t s) {
   const u32 grid = (a.n + per_block - 1) / per_block;
   cudaMemsetAsync(a.n_pending + a.parity, 0, 4, s);
   const u32 g16 = (a.n + RSP_MG_TPB / FL - 1) / (RSP_MG_TPB / FL);
-  if (a.pf_dist) {
+  if (a.pf_dist & ~GET_MULTIRUN) {
     if (a.val_stride > 96) k_multi_get16d<true, true><<<g16, RSP_MG_TPB, 0, s>>>(a);
     else k_multi_get16d<false, true><<<g16, RSP_MG_TPB, 0, s>>>(a);
   } else {

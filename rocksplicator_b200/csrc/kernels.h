@@ -97,8 +97,10 @@ struct GetArgs {
   u32 parity;
   u32* n_special;        // [1] counts lookups whose status is none of OK / NotFound / Incomplete (may be nullptr)
   u32 max_shards;        // shard ids >= this answer InvalidArgument
-  u32 pf_dist;           // experiment (k_multi_get16d<.., PF>): prefetch distance in lookups, 0 = off
+  u32 pf_dist;           // experiment (k_multi_get16d<.., PF>): prefetch distance in lookups (low 31 bits), 0 = off;
+                         // bit 31 (GET_MULTIRUN): `fast` is followed by [max_shards][RSP_MAX_RUNS] per-run descriptors
 };
+constexpr u32 GET_MULTIRUN = 1u << 31;
 void launch_multi_get(const GetArgs& a, cudaStream_t s);
 // experiment: shards whose only run is RUN_DIRECT are served by k_multi_get16d (everything else -> generic path)
 void launch_multi_get_direct(const GetArgs& a, cudaStream_t s);

@@ -48,7 +48,7 @@ def test_parity_suite_under_emulation(emul):
 def test_parity_suite_under_emulation_experiments_on(emul):
     """functional check of the experiments that wait for GPU time: RSP_DIRECT_RUNS=1 (hash-addressed
     run heaps, k_multi_get16d), RSP_MG_PREFETCH (grid-level L2 prefetch) and RSP_DECODE_THREAD=1 (a thread per batch)"""
-    out = _pytest_under_emulation(emul[0], {"RSP_DIRECT_RUNS": "1", "RSP_DECODE_THREAD": "1", "RSP_MG_PREFETCH": "5"}, PARITY)
+    out = _pytest_under_emulation(emul[0], {"RSP_DIRECT_RUNS": "1", "RSP_DECODE_THREAD": "1", "RSP_MG_PREFETCH": "5", "RSP_MG_MULTIRUN": "1"}, PARITY)
     assert " passed" in out and "failed" not in out
 
 
@@ -129,7 +129,7 @@ def test_compaction_size_boundaries_under_emulation(emul, direct):
 
 def test_parity_suite_under_emulation_fused_decode(emul):
     """RSP_FUSE_DECODE=1 (decode inside the sequencing kernel; excludes RSP_DECODE_THREAD): functional check"""
-    out = _pytest_under_emulation(emul[0], {"RSP_FUSE_DECODE": "1", "RSP_MG_PREFETCH": "64"}, ["tests/test_parity_gpu.py"])
+    out = _pytest_under_emulation(emul[0], {"RSP_FUSE_DECODE": "1", "RSP_MG_PREFETCH": "64", "RSP_MG_MULTIRUN": "1"}, ["tests/test_parity_gpu.py"])
     assert " passed" in out and "failed" not in out
 
 

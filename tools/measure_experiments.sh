@@ -9,7 +9,7 @@ run() { echo "=== $*"; "$@"; echo "rc=$?"; }
 {
   run timeout 600 python -m pytest tests -m gpu -x -q
   RSP_DIRECT_RUNS=1 RSP_DECODE_THREAD=1 run timeout 600 python -m pytest tests -m gpu -x -q
-  RSP_MG_PREFETCH=4096 run timeout 600 python -m pytest tests -m gpu -x -q
+  RSP_MG_PREFETCH=4096 RSP_MG_MULTIRUN=1 run timeout 600 python -m pytest tests -m gpu -x -q
   RSP_FUSE_DECODE=1 run timeout 600 python -m pytest tests -m gpu -x -q
 } > gpurun_out/exp/parity.log 2>&1
 tail -5 gpurun_out/exp/parity.log
