@@ -499,9 +499,9 @@ def main():
     # ---- config-2 variant: MultiGet while the newest version of many keys is still in the memtables -----
     # (every update tick above landed in a memtable: nothing has been flushed since the load).  Informational: a
     # failure here is reported in the line, it does not void the phases above.
-    mt_ms, mt_err, mt_entries = -1.0, None, 0
-    try:
-        mt_entries = int(sum(s.stats()["memtable_entries"] for s in shards))
+    def mg_phase_checked():
+        """W + K MultiGet launches of the uniform query sets, K of them timed; status, length and (full size) values
+        checked against the last update tick of every queried key.  Local to the rank: no collectives inside."""
         for i in range(W):
             mg(i)
         torch.cuda.synchronize()
@@ -511,9 +511,8 @@ def main():
             mg(W + k)
         m1.record(stream)
         torch.cuda.synchronize()
-        mt_ms = float(m0.elapsed_time(m1))
+        ms = float(m0.elapsed_time(m1))
         assert int(d_st.count_nonzero().item()) == 0 and int((d_vlen != 64).count_nonzero().item()) == 0, "status / length"
-        # full-size parity: the expected version of every queried key is its last update tick (0 = never updated)
         uk = np.fromiter(lastver.keys(), dtype=np.uint64, count=len(lastver))
         uv = np.fromiter(lastver.values(), dtype=np.int64, count=len(lastver))
         order = np.argsort(uk)
@@ -526,8 +525,24 @@ def main():
         for v in np.unique(qver):
             m = qver == v
             assert np.array_equal(got[m], synth.values(seed, qsh[m], lastq[m], int(v))), "value parity (version %d)" % v
+        return ms
+
+    mt_ms, mt_err, mt_entries = -1.0, None, 0
+    try:
+        mt_entries = int(sum(s.stats()["memtable_entries"] for s in shards))
+        mt_ms = mg_phase_checked()
     except Exception as ex:  # noqa: BLE001
         mt_err = "%s: %s" % (type(ex).__name__, str(ex)[:160])
+
+    # ---- the same once more after a flush WITHOUT compaction: every shard now has two sorted runs (the state between a
+    # flush and the merge at level0_file_num_compaction_trigger; config 5 lives there).  Informational, non-fatal.
+    r2_ms, r2_err, r2_runs = -1.0, None, 0
+    try:
+        assert eng.flush_all() == 0
+        r2_runs = int(max(s.stats()["n_runs"] for s in shards))
+        r2_ms = mg_phase_checked()
+    except Exception as ex:  # noqa: BLE001
+        r2_err = "%s: %s" % (type(ex).__name__, str(ex)[:160])
 
     # ---- numbers ---------------------------------------------------------------------------------------
     peak, peak_src = peaks()
@@ -536,6 +551,8 @@ def main():
     mt_ms_all = max_over_ranks(mt_ms)
     mt_failed = sum_over_ranks(1.0 if mt_err else 0.0)
     mt_entries_all = sum_over_ranks(float(mt_entries))
+    r2_ms_all = max_over_ranks(r2_ms)
+    r2_failed = sum_over_ranks(1.0 if r2_err else 0.0)
     tot_applies = sum_over_ranks(T * K)
     tot_scans = sum_over_ranks(NSC * K)
     tot_scan_entries = sum_over_ranks(entries_last * K)
@@ -576,6 +593,10 @@ def main():
                          {"what": "config-2 variant: the same uniform MultiGet with the update ticks still in the memtables (entries there = %.0f %% of the key count; nothing flushed since the load); values checked at full size" % (100.0 * mt_entries_all / max(1, NKV * world)),
                           "lookups_per_s": tot_lookups / (mt_ms_all * 1e-3), "memtable_entries": int(mt_entries_all),
                           "hbm_frac_of_peak_algorithmic": A_GET * Q / (mt_ms_all * 1e-3 / max(K, 1)) / 1e9 / peak}),
+            "two_runs": ({"error": r2_err or "failed on another rank"} if r2_failed else
+                         {"what": "the same MultiGet after a flush without compaction: %d sorted runs per shard (lookups that miss the newest run go on to the older one); values checked at full size" % r2_runs,
+                          "lookups_per_s": tot_lookups / (r2_ms_all * 1e-3),
+                          "hbm_frac_of_peak_algorithmic": A_GET * Q / (r2_ms_all * 1e-3 / max(K, 1)) / 1e9 / peak}),
             "zipf": {"theta": 0.99, "lookups_per_s": tot_lookups / (zipf_ms * 1e-3), "hbm_frac_of_peak_algorithmic": A_GET * Q / (zipf_ms * 1e-3 / max(K, 1)) / 1e9 / peak},
             "mixed": {"what": "config 3: %d apply ticks on the engine stream concurrent with %d MultiGet launches on a second stream" % (K, K),
                       "lookups_per_s": tot_lookups / (mixed_get_ms * 1e-3), "applies_per_s": tot_applies / (mixed_apply_ms * 1e-3),
