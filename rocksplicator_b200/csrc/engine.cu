@@ -438,6 +438,7 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
   CUDA_OK(cudaEventRecord(e->ev0, e->st));
   launch_compact_sort(d_jobs, jobs.data(), nj, e->st);
   launch_compact_size(d_jobs, nj, e->st);
+  CUDA_OK(cudaGetLastError());  // a refused launch (e.g. shared-memory opt-in) must not pass as an unsorted run
   e->launches += 3;
   std::vector<u32> totals(8 * nj);
   for (u32 i = 0; i < nj; i++)
@@ -471,6 +472,7 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
   }
   CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CompactJob) * nj, cudaMemcpyHostToDevice, e->st));
   launch_compact_write(d_jobs, nj, max_items, e->st);
+  CUDA_OK(cudaGetLastError());
   e->launches += 1;
   // EXPERIMENT: a fully compacted run of same-size Puts with 16-byte keys, one version per key, is re-laid out as
   // RUN_DIRECT; the sorted heap it was written to is released after the sync below
@@ -763,6 +765,7 @@ static void tick_launch(rsp_engine* e, rsp_staged* sg, cudaStream_t st) {
   launch_sequence(sg->tick, e->d_shards, e->d_fast, st);
   launch_insert(sg->tick, e->d_shards, st);
   launch_publish(sg->tick, e->d_shards, st);
+  CUDA_OK(cudaGetLastError());
   e->launches += 4;
 }
 

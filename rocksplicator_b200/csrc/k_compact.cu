@@ -12,6 +12,8 @@
 //   k_compact_write : copy / synthesise the kept entries into the new heap, write the restart array
 //                     (ent_off), the block index (first-key prefix per 32 entries) and the bucketised
 //                     hash index
+#include <atomic>
+
 #include "kernels.h"
 
 namespace rsp {
@@ -338,10 +340,14 @@ void launch_compact_sort(const CompactJob* d_jobs, const CompactJob* h_jobs, u32
   if (!max_n) return;
   dim3 grid((max_n + 255) / 256, n_jobs);
   k_compact_fill<<<grid, 256, 0, s>>>(d_jobs);
-  static bool smem_opt_in = false;
-  if (!smem_opt_in) {
+  // the opt-in is a per-DEVICE function attribute: one engine per GPU may live in the same process
+  static std::atomic<unsigned long long> opted_in{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(opted_in.load(std::memory_order_acquire) & bit)) {
     cudaFuncSetAttribute(k_compact_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_TILE * sizeof(SortItem)));
-    smem_opt_in = true;
+    opted_in.fetch_or(bit, std::memory_order_release);
   }
   k_compact_sort<<<n_jobs, 1024, SORT_TILE * sizeof(SortItem), s>>>(d_jobs);
 }

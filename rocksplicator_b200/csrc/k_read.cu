@@ -917,8 +917,9 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
   *mbar += 1;
 }
 __device__ __forceinline__ void mbar_init(u64* mbar, u32) { *mbar = 0; }
-__device__ __forceinline__ void mbar_wait(u64* mbar, u32 parity) {
+__device__ __forceinline__ bool mbar_wait(u64* mbar, u32 parity) {
   while ((*mbar & 1u) == parity) emul_yield();
+  return true;
 }
 #else
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, u32 bytes, u64* mbar) {
@@ -933,17 +934,21 @@ __device__ __forceinline__ void mbar_init(u64* mbar, u32 count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_wait(u64* mbar, u32 parity) {
+// Bounded wait: try_wait itself blocks for a hardware time slice per attempt, so 2^20 attempts are seconds, not a
+// hang.  false = the bulk copy never completed (never seen; the caller then searches the index in global memory).
+__device__ __forceinline__ bool mbar_wait(u64* mbar, u32 parity) {
   const u32 bar = (u32)__cvta_generic_to_shared(mbar);
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
+  for (u32 tries = 0; tries < (1u << 20); tries++) {
+    u32 ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
 }
 #endif
 
@@ -954,7 +959,7 @@ __device__ u32 run_lower_bound_warp(const RunDev& R, const u8* kp, u32 klen, boo
   if (R.n_blocks > 1 && klen) {
     if (lane == 0) tma_load_1d(s_pfx, R.blk_pfx, (R.n_blocks * 8u + 15u) & ~15u, mbar);
     const u64 pfx = key_prefix_be(kp, klen);
-    mbar_wait(mbar, 0);
+    if (!__all_sync(0xffffffffu, mbar_wait(mbar, 0))) return run_lower_bound(R, kp, klen, strict);
     u32 n_lt = 0, n_le = 0;
     for (u32 b = 0; b < R.n_blocks; b += 32) {
       const u64 p = b + lane < R.n_blocks ? s_pfx[b + lane] : ~0ull;

@@ -220,8 +220,13 @@ void emul_launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<voi
 struct emul_stream { int id; };
 struct emul_event { std::chrono::steady_clock::time_point t; };
 
-cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+// RSP_EMUL_DEVICES=<n>: pretend n devices (memory is malloc-backed, so they are interchangeable) — lets the
+// several-engines-in-one-process paths (router) run on the CPU
+static int emul_n_devices() { const char* e = getenv("RSP_EMUL_DEVICES"); const int n = e ? atoi(e) : 1; return n > 0 ? n : 1; }
+static thread_local int g_cur_device = 0;
+cudaError_t cudaGetDeviceCount(int* n) { *n = emul_n_devices(); return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= emul_n_devices()) return cudaErrorInvalidValue; g_cur_device = d; return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = g_cur_device; return cudaSuccess; }
 cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 cudaError_t cudaMalloc(void** p, size_t n) {

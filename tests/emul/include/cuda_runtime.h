@@ -57,6 +57,7 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 
 cudaError_t cudaGetDeviceCount(int* n);
 cudaError_t cudaSetDevice(int d);
+cudaError_t cudaGetDevice(int* d);
 cudaError_t cudaDeviceSetLimit(cudaLimit, size_t);
 cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaMalloc(void** p, size_t n);
@@ -109,6 +110,8 @@ template <class T> static inline T __shfl_sync(unsigned mask, T v, int lane, int
 template <class T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int = 32) { return emul_shfl(EMUL_SHFL_UP, mask, v, d); }
 template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int m, int = 32) { return emul_shfl(EMUL_SHFL_XOR, mask, v, (unsigned)m); }
 static inline unsigned __ballot_sync(unsigned mask, int pred) { return (unsigned)emul_collective(EMUL_BALLOT, mask, pred ? 1 : 0, 0); }
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, !pred) == 0; }
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emul_collective(EMUL_SYNCWARP, mask, 0, 0); }
 static inline void __syncthreads() { emul_syncthreads(); }
 static inline void __threadfence() {}
