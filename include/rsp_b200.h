@@ -108,7 +108,7 @@ const char* rsp_shard_name(const rsp_shard* s);
  * rsp_write  == RocksDbWrapper::WriteToLeader (rocksdb_wrapper.cpp:5-8): DB::Write of the batch as is.
  * On success *seq_out (optional) is DB::GetLatestSequenceNumber() after the write.  A failed write
  * leaves the shard unchanged and LATCHES the error for later writes, as RocksDB 5.x does.
- * Concurrent callers are group-committed: whoever arrives first runs one device tick for everybody queued. */
+ * Concurrent callers share device ticks (the apply combiner, see rsp_apply_updates). */
 int rsp_apply(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t ts_ms, uint64_t* seq_out);
 int rsp_write(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t* seq_out);
 
@@ -118,6 +118,21 @@ int rsp_write(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t* seq_out)
  * ts_ms == NULL means rsp_write semantics (no LogData append).  st_out[i] gets each batch's status. */
 int rsp_apply_many(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob,
                    const uint64_t* off, const uint64_t* ts_ms, int32_t* st_out);
+
+/* The pull loop's unit of work: the <= replicator_max_updates_per_response updates of ONE ReplicateResponse, applied in
+ * order (rocksdb_replicator/replicated_db.cpp:369-383 calls HandleReplicateResponse once per update; here the whole
+ * response is one call).  batches[i] has the layout of rocksdb::Slice / folly::IOBuf's contiguous bytes; ts_ms[i] is
+ * update i's timestamp (NULL = rsp_write semantics: nothing appended).  The bytes are copied before the call returns.
+ * Calls from many threads (one per shard's response) share device ticks: each caller copies its updates into the open
+ * tick's pinned staging buffer in parallel, a dispatcher thread runs one tick after the other (stager.h).
+ *   done == NULL : blocks until the tick has run; returns the first failing update's status (RSP_OK when all were
+ *                  applied) and, through *n_applied, how many leading updates were applied.
+ *   done != NULL : returns RSP_OK at once; done(ctx, status, n_applied, latest_seq) runs on an engine-owned completion
+ *                  thread after the tick (the follower then issues its next pull, replicated_db.cpp:430). */
+typedef struct rsp_slice { const uint8_t* data; size_t size; } rsp_slice;
+typedef void (*rsp_done_fn)(void* ctx, int status, size_t n_applied, uint64_t latest_seq);
+int rsp_apply_updates(rsp_shard* s, size_t n, const rsp_slice* batches, const uint64_t* ts_ms, rsp_done_fn done,
+                      void* ctx, size_t* n_applied);
 
 /* RocksDbWrapper::LatestSequenceNumber (rocksdb_wrapper.cpp:4) */
 uint64_t rsp_latest_seq(const rsp_shard* s);
@@ -135,6 +150,13 @@ int rsp_get(rsp_shard* s, const uint8_t* key, size_t klen, uint8_t* val, size_t 
 int rsp_multi_get(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys,
                   const uint64_t* koff, uint8_t* vals, size_t val_stride, uint32_t* vlen,
                   int32_t* st);
+
+/* ApplicationDB::MultiGet as the reference calls it: one shard, an array of rocksdb::Slice keys, results delivered one
+ * by one (fn(ctx, i, status, value, vlen) on the calling thread, straight from the pinned result buffer: the caller
+ * assigns its std::string from there, no intermediate copy).  value_hint = expected largest value (0 = unknown); larger
+ * values are fetched in a second pass.  Concurrent callers (and rsp_get / rsp_multi_get callers) share launches. */
+typedef void (*rsp_value_fn)(void* ctx, size_t i, int status, const uint8_t* value, size_t vlen);
+int rsp_multi_get_slices(rsp_shard* s, size_t n, const rsp_slice* keys, size_t value_hint, rsp_value_fn fn, void* ctx);
 
 /* Fixed-key-length form with host buffers (pinned or pageable): keys[i*klen .. +klen). */
 int rsp_multi_get_fixed(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys,

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librsp_b200.so")
 SOURCES = ["k_apply.cu", "k_read.cu", "k_compact.cu", "engine.cu"]
-HEADERS = ["format.cuh", "kernels.h", os.path.join("..", "..", "include", "rsp_b200.h")]
+HEADERS = ["format.cuh", "kernels.h", "stager.h", os.path.join("..", "..", "include", "rsp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + os.environ.get("RSP_NVCC_EXTRA", "").split()
 
@@ -63,7 +63,8 @@ if __name__ == "__main__":
 
 HOST = os.path.join(HERE, "host")
 HOST_SRCS = ["gpu_db.cpp", "rocksdb_replicator/rocksdb_replicator.cpp", "rocksdb_replicator/gpu_db_wrapper.cpp",
-             "rocksdb_admin/application_db.cpp", "rocksdb_admin/application_db_manager.cpp", "sst/sst_c_api.cpp"]
+             "rocksdb_admin/application_db.cpp", "rocksdb_admin/application_db_manager.cpp", "sst/sst_c_api.cpp",
+             "bench/seam_bench.cpp"]
 HOST_SO = os.path.join(HERE, "librsp_host.so")
 HOST_TESTS = os.path.join(os.path.dirname(HERE), "tests", "cpp", "host_tests")
 

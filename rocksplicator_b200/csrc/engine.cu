@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -20,7 +22,7 @@
 #include <vector>
 
 #include "../../include/rsp_b200.h"
-#include "group_commit.h"
+#include "stager.h"
 #include "kernels.h"
 
 using namespace rsp;
@@ -229,19 +231,17 @@ struct rsp_staged {
   mutable bool reserved = false; // its upper bounds are counted in the shards' in-flight totals until the results are folded
 };
 
-// one rsp_apply / rsp_write call waiting for its tick
-struct ApplyReq {
-  uint32_t shard_ix;
-  const uint8_t* batch;
-  size_t len;
-  uint64_t ts_ms;
-  bool has_ts;
-  int32_t status;
-};
+struct ReadCombiner;
+struct ApplyCombiner;
 
 struct rsp_engine {
   int device = 0;
-  std::unique_ptr<rsp::GroupCommit<ApplyReq>> single_applies;  // combines concurrent rsp_apply / rsp_write callers
+  // staging combiners (created on first use): concurrent readers / writers share device batches (stager.h)
+  std::mutex comb_mu;
+  ReadCombiner* read_comb = nullptr;
+  ApplyCombiner* apply_comb = nullptr;
+  std::atomic<ReadCombiner*> read_comb_ready{nullptr};
+  std::atomic<ApplyCombiner*> apply_comb_ready{nullptr};
   rsp_engine_cfg cfg{};
   std::mutex mu;  // serialises GPU work issued through the ABI
   cudaStream_t st = nullptr;
@@ -931,30 +931,6 @@ static int apply_many_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, 
   return worst;
 }
 
-// leader body of the group commit: one tick for every queued single-update call.  Requests with and without the
-// follower's timestamp record cannot share a tick (the trailer is per tick), so they go as two calls.
-static void run_single_applies(rsp_engine* e, std::vector<ApplyReq*>& batch) {
-  std::lock_guard<std::mutex> g(e->mu);
-  CUDA_OK(cudaSetDevice(e->device));
-  for (int pass = 0; pass < 2; pass++) {
-    const bool want_ts = pass == 0;
-    std::vector<ApplyReq*> part;
-    for (ApplyReq* r : batch) if (r->has_ts == want_ts) part.push_back(r);
-    if (part.empty()) continue;
-    const size_t n = part.size();
-    std::vector<uint32_t> six(n);
-    std::vector<uint64_t> off(n + 1, 0), ts(n);
-    size_t total = 0;
-    for (size_t i = 0; i < n; i++) { six[i] = part[i]->shard_ix; off[i] = total; total += part[i]->len; ts[i] = part[i]->ts_ms; }
-    off[n] = total;
-    std::vector<uint8_t> blob(total + 1);
-    for (size_t i = 0; i < n; i++) if (part[i]->len) memcpy(&blob[off[i]], part[i]->batch, part[i]->len);
-    std::vector<int32_t> st(n, 0);
-    const int rc = apply_many_locked(e, n, six.data(), blob.data(), off.data(), want_ts ? ts.data() : nullptr, st.data());
-    for (size_t i = 0; i < n; i++) part[i]->status = (rc == RSP_INVALID_ARGUMENT && st[i] == 0) ? rc : st[i];
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // host-side merge folding (operators that do not live on the device)
 // ------------------------------------------------------------------------------------------------
@@ -1242,6 +1218,342 @@ static void iter_fetch(rsp_iter* it, const std::string* key, bool exclusive, boo
 }
 
 // ------------------------------------------------------------------------------------------------
+// staging combiners: concurrent callers of the reference's seams share device batches (stager.h)
+// ------------------------------------------------------------------------------------------------
+// asynchronous completions run here, not on a dispatcher thread (a dispatcher that runs user code cannot launch)
+struct CompletionPool {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<std::function<void()>> q;
+  bool stop = false;
+  std::vector<std::thread> th;
+  void start(size_t n) {
+    for (size_t i = 0; i < n; i++) th.emplace_back([this] {
+      for (;;) {
+        std::function<void()> f;
+        {
+          std::unique_lock<std::mutex> l(mu);
+          cv.wait(l, [this] { return stop || !q.empty(); });
+          if (q.empty()) return;  // stop requested and drained
+          f = std::move(q.front());
+          q.pop_front();
+        }
+        f();
+      }
+    });
+  }
+  void add_many(std::vector<std::function<void()>>& fs) {
+    if (fs.empty()) return;
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (auto& f : fs) q.push_back(std::move(f));
+    }
+    fs.clear();
+    cv.notify_all();
+  }
+  void shutdown() {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      stop = true;
+    }
+    cv.notify_all();
+    for (auto& t : th) t.join();
+    th.clear();
+  }
+};
+
+static size_t env_size(const char* name, size_t dflt) {
+  const char* v = getenv(name);
+  return v && atoll(v) > 0 ? (size_t)atoll(v) : dflt;
+}
+static u32 stride_class(size_t want) {  // value strides are batched by power-of-two class (>= 64 bytes)
+  u32 c = 64;
+  while (c < want && c < (1u << 30)) c <<= 1;
+  return c;
+}
+
+// pinned + mapped staging: the device reads small batches straight from it (no copy calls at all)
+static u8* pinned_mapped(size_t bytes, u8** dev_alias) {
+  void* p = nullptr;
+  CUDA_OK(cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+  void* d = nullptr;
+  CUDA_OK(cudaHostGetDevicePointer(&d, p, 0));
+  *dev_alias = (u8*)d;
+  return (u8*)p;
+}
+
+struct ReadStage {
+  u8* pin = nullptr;
+  u8* pin_dev = nullptr;  // the same memory through its device address
+  u8* dev = nullptr;      // HBM mirror for large batches
+  u32* d_pending = nullptr;
+  std::atomic<u32> not16{0};  // a key of this batch is not 16 bytes long
+};
+struct ReadCombiner {
+  rsp_engine* e = nullptr;
+  size_t cap_items = 0, cap_key_bytes = 0, cap_val_bytes = 0, zero_copy_max = 0;
+  size_t o_six = 0, o_koff = 0, o_keys = 0, o_st = 0, o_vlen = 0, o_vals = 0, total = 0;
+  ReadStage st[2];
+  cudaStream_t stream = nullptr;
+  std::unique_ptr<Stager> stager;
+
+  void run(const Stager::BatchInfo& info) {
+    ReadStage& S = st[info.buf];
+    const size_t n = info.n_items;
+    const u32 stride = info.klass;
+    CUDA_OK(cudaSetDevice(e->device));
+    reinterpret_cast<u64*>(S.pin + o_koff)[n] = info.n_bytes;
+    const bool fixed16 = S.not16.exchange(0) == 0 && info.n_bytes == n * 16;
+    const bool zc = n <= zero_copy_max;
+    u8* base = zc ? S.pin_dev : S.dev;
+    if (!zc) {
+      CUDA_OK(cudaMemcpyAsync(S.dev + o_six, S.pin + o_six, n * 4, cudaMemcpyHostToDevice, stream));
+      if (!fixed16) CUDA_OK(cudaMemcpyAsync(S.dev + o_koff, S.pin + o_koff, (n + 1) * 8, cudaMemcpyHostToDevice, stream));
+      if (info.n_bytes) CUDA_OK(cudaMemcpyAsync(S.dev + o_keys, S.pin + o_keys, info.n_bytes, cudaMemcpyHostToDevice, stream));
+    }
+    GetArgs a;
+    a.shards = e->d_shards; a.fast = e->d_fast; a.max_shards = e->cfg.max_shards;
+    a.shard_ix = (const u32*)(base + o_six); a.keys = base + o_keys;
+    a.koff = fixed16 ? nullptr : (const u64*)(base + o_koff); a.klen_fixed = fixed16 ? 16u : 0u;
+    a.vals = base + o_vals; a.val_stride = stride; a.vlen = (u32*)(base + o_vlen); a.st = (i32*)(base + o_st); a.n = (u32)n;
+    a.n_special = nullptr; a.n_pending = S.d_pending; a.pending = S.d_pending + 4; a.parity = 0;
+    a.pf_dist = (e->mg_prefetch & ~GET_MULTIRUN) | (e->mg_multirun ? GET_MULTIRUN : 0u);
+    {
+      // ordering against flushes / memtable re-allocations on the engine stream (reader_begin / reader_end)
+      std::lock_guard<std::mutex> g(e->mu);
+      reader_begin(e, stream);
+      if (e->direct_runs || e->mg_prefetch || e->mg_multirun) launch_multi_get_direct(a, stream); else launch_multi_get(a, stream);
+      CUDA_OK(cudaGetLastError());
+      reader_end(e, stream);
+    }
+    e->launches += 2;
+    if (!zc) {
+      CUDA_OK(cudaMemcpyAsync(S.pin + o_st, S.dev + o_st, n * 4, cudaMemcpyDeviceToHost, stream));
+      CUDA_OK(cudaMemcpyAsync(S.pin + o_vlen, S.dev + o_vlen, n * 4, cudaMemcpyDeviceToHost, stream));
+      CUDA_OK(cudaMemcpyAsync(S.pin + o_vals, S.dev + o_vals, n * (size_t)stride, cudaMemcpyDeviceToHost, stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(stream));
+  }
+  void destroy() {
+    stager.reset();  // joins the dispatcher
+    cudaSetDevice(e->device);
+    for (auto& S : st) {
+      if (S.pin) cudaFreeHost(S.pin);
+      if (S.dev) cudaFree(S.dev);
+      if (S.d_pending) cudaFree(S.d_pending);
+    }
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+static ReadCombiner* read_combiner(rsp_engine* e) {
+  if (ReadCombiner* c = e->read_comb_ready.load(std::memory_order_acquire)) return c;
+  std::lock_guard<std::mutex> g(e->comb_mu);
+  if (e->read_comb) return e->read_comb;
+  CUDA_OK(cudaSetDevice(e->device));
+  ReadCombiner* c = new ReadCombiner();
+  c->e = e;
+  c->cap_items = env_size("RSP_READ_COMBINE_ITEMS", 1u << 18);
+  c->cap_key_bytes = env_size("RSP_READ_COMBINE_KEY_BYTES", c->cap_items * 24);
+  c->cap_val_bytes = env_size("RSP_READ_COMBINE_VAL_BYTES", c->cap_items * 128);
+  c->zero_copy_max = getenv("RSP_READ_ZERO_COPY") ? (size_t)atoll(getenv("RSP_READ_ZERO_COPY")) : 2048;
+  c->o_six = 0;
+  c->o_koff = align_up(c->cap_items * 4, 256);
+  c->o_keys = c->o_koff + align_up((c->cap_items + 1) * 8, 256);
+  c->o_st = c->o_keys + align_up(c->cap_key_bytes + 64, 256);
+  c->o_vlen = c->o_st + align_up(c->cap_items * 4, 256);
+  c->o_vals = c->o_vlen + align_up(c->cap_items * 4, 256);
+  c->total = c->o_vals + c->cap_val_bytes + 256;
+  for (auto& S : c->st) {
+    S.pin = pinned_mapped(c->total, &S.pin_dev);
+    CUDA_OK(cudaMalloc(&S.dev, c->total));
+    CUDA_OK(cudaMalloc(&S.d_pending, (c->cap_items + 16) * 4));
+    CUDA_OK(cudaMemset(S.d_pending, 0, 16));
+  }
+  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->stager.reset(new Stager(c->cap_items, c->cap_key_bytes, [c](const Stager::BatchInfo& b) { c->run(b); }));
+  e->read_comb = c;
+  e->read_comb_ready.store(c, std::memory_order_release);
+  return c;
+}
+
+// One read request through the combiner.  six_at(i) -> shard index, key_at(i, &len) -> key pointer, on_res(i, st,
+// value, vlen) with the device's status (7 = the value needs more than `stride` bytes, vlen = needed; statuses
+// other than 0 / 1 / 7 are the generic kernel's special cases: the caller re-runs the request on the direct path).
+// Returns false when the request does not fit the staging buffers (direct path).
+template <class SixAt, class KeyAt, class OnRes>
+static bool read_combined(rsp_engine* e, size_t n, size_t key_bytes, u32 stride, SixAt six_at, KeyAt key_at, OnRes on_res) {
+  ReadCombiner* c = read_combiner(e);
+  const size_t max_items = std::min(c->cap_items, c->cap_val_bytes / stride);
+  if (n > max_items / 2 || key_bytes > c->cap_key_bytes / 2) return false;
+  Stager::Ticket t;
+  if (!c->stager->begin(n, key_bytes, stride, max_items, &t)) return false;
+  ReadStage& S = c->st[t.buf];
+  u32* six = reinterpret_cast<u32*>(S.pin + c->o_six) + t.item0;
+  u64* koff = reinterpret_cast<u64*>(S.pin + c->o_koff) + t.item0;
+  u8* keys = S.pin + c->o_keys;
+  size_t at = t.byte0;
+  bool all16 = true;
+  for (size_t i = 0; i < n; i++) {
+    size_t len = 0;
+    const uint8_t* p = key_at(i, &len);
+    six[i] = six_at(i);
+    koff[i] = at;
+    if (len) memcpy(keys + at, p, len);
+    at += len;
+    all16 &= len == 16;
+  }
+  if (!all16) S.not16.store(1, std::memory_order_relaxed);
+  c->stager->commit(t);
+  c->stager->wait(t);
+  const i32* st = reinterpret_cast<const i32*>(S.pin + c->o_st) + t.item0;
+  const u32* vlen = reinterpret_cast<const u32*>(S.pin + c->o_vlen) + t.item0;
+  const u8* vals = S.pin + c->o_vals + t.item0 * (size_t)stride;
+  for (size_t i = 0; i < n; i++) on_res(i, st[i], vals + i * (size_t)stride, vlen[i]);
+  c->stager->release(t);
+  return true;
+}
+
+// ---- applies --------------------------------------------------------------------------------------
+struct ApplyStage {
+  u8* pin = nullptr;
+  u8* pin_dev = nullptr;
+};
+struct ApplyCombiner {
+  rsp_engine* e = nullptr;
+  size_t cap_items = 0, cap_bytes = 0;
+  size_t o_six = 0, o_off = 0, o_ts = 0, o_blob = 0, o_st = 0, total = 0;
+  ApplyStage st[2];
+  std::unique_ptr<Stager> stager;
+  CompletionPool pool;
+  std::vector<std::function<void()>> done_now;  // dispatcher thread only: completions of the batch that just ran
+
+  void run(const Stager::BatchInfo& info) {
+    ApplyStage& S = st[info.buf];
+    const size_t n = info.n_items;
+    u64* off = reinterpret_cast<u64*>(S.pin + o_off);
+    off[n] = info.n_bytes;
+    int32_t* stv = reinterpret_cast<int32_t*>(S.pin + o_st);
+    memset(stv, 0, n * 4);
+    int rc;
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      CUDA_OK(cudaSetDevice(e->device));
+      rc = apply_many_locked(e, n, reinterpret_cast<const u32*>(S.pin + o_six), S.pin + o_blob, off,
+                             info.klass == 0 ? reinterpret_cast<const u64*>(S.pin + o_ts) : nullptr, stv);
+    }
+    if (rc == RSP_INVALID_ARGUMENT || rc == RSP_BUSY)
+      for (size_t i = 0; i < n; i++) if (stv[i] == 0) stv[i] = rc;
+  }
+  void destroy() {
+    stager.reset();
+    pool.shutdown();
+    cudaSetDevice(e->device);
+    for (auto& S : st) if (S.pin) cudaFreeHost(S.pin);
+  }
+};
+
+static ApplyCombiner* apply_combiner(rsp_engine* e) {
+  if (ApplyCombiner* c = e->apply_comb_ready.load(std::memory_order_acquire)) return c;
+  std::lock_guard<std::mutex> g(e->comb_mu);
+  if (e->apply_comb) return e->apply_comb;
+  CUDA_OK(cudaSetDevice(e->device));
+  ApplyCombiner* c = new ApplyCombiner();
+  c->e = e;
+  c->cap_items = env_size("RSP_APPLY_COMBINE_ITEMS", 1u << 17);
+  c->cap_bytes = env_size("RSP_APPLY_COMBINE_BYTES", c->cap_items * 160);
+  c->o_six = 0;
+  c->o_off = align_up(c->cap_items * 4, 256);
+  c->o_ts = c->o_off + align_up((c->cap_items + 1) * 8, 256);
+  c->o_blob = c->o_ts + align_up(c->cap_items * 8, 256);
+  c->o_st = c->o_blob + align_up(c->cap_bytes + 64, 256);
+  c->total = c->o_st + align_up(c->cap_items * 4, 256);
+  for (auto& S : c->st) S.pin = pinned_mapped(c->total, &S.pin_dev);
+  c->pool.start(env_size("RSP_COMPLETION_THREADS", 8));
+  c->stager.reset(new Stager(c->cap_items, c->cap_bytes, [c](const Stager::BatchInfo& b) { c->run(b); },
+                             [c] { c->pool.add_many(c->done_now); }));
+  e->apply_comb = c;
+  e->apply_comb_ready.store(c, std::memory_order_release);
+  return c;
+}
+
+// n updates of ONE shard, in order, through the apply combiner.  done == nullptr: returns after the tick with the
+// first failing status (0 when all were applied) and *n_applied.  Otherwise returns RSP_OK at once and done runs on
+// a completion thread.  The updates are copied before the call returns.
+static int apply_combined(rsp_shard* s, size_t n, const rsp_slice* batches, const uint64_t* ts_ms, bool has_ts,
+                          rsp_done_fn done, void* ctx, size_t* n_applied) {
+  rsp_engine* e = s->eng;
+  if (n_applied) *n_applied = 0;
+  if (n == 0) {
+    if (done) done(ctx, RSP_OK, 0, rsp_latest_seq(s));
+    return RSP_OK;
+  }
+  size_t bytes = 0;
+  for (size_t i = 0; i < n; i++) bytes += batches[i].size;
+  ApplyCombiner* c = apply_combiner(e);
+  Stager::Ticket t;
+  if (n > c->cap_items / 2 || bytes > c->cap_bytes / 2 || !c->stager->begin(n, bytes, has_ts ? 0u : 1u, c->cap_items, &t)) {
+    // too large for the staging buffers: one tick of its own
+    std::vector<uint32_t> six(n, s->index);
+    std::vector<uint64_t> off(n + 1, 0);
+    std::vector<uint8_t> blob(bytes + 1);
+    for (size_t i = 0; i < n; i++) {
+      off[i + 1] = off[i] + batches[i].size;
+      if (batches[i].size) memcpy(&blob[off[i]], batches[i].data, batches[i].size);
+    }
+    std::vector<int32_t> stv(n, 0);
+    int rc;
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      CUDA_OK(cudaSetDevice(e->device));
+      rc = apply_many_locked(e, n, six.data(), blob.data(), off.data(), has_ts ? ts_ms : nullptr, stv.data());
+    }
+    size_t ok = 0;
+    while (ok < n && stv[ok] == 0) ok++;
+    const int first = ok < n ? (stv[ok] ? stv[ok] : rc) : RSP_OK;
+    if (n_applied) *n_applied = ok;
+    if (done) { done(ctx, first, ok, rsp_latest_seq(s)); return RSP_OK; }
+    return first;
+  }
+  ApplyStage& S = c->st[t.buf];
+  u32* six = reinterpret_cast<u32*>(S.pin + c->o_six) + t.item0;
+  u64* off = reinterpret_cast<u64*>(S.pin + c->o_off) + t.item0;
+  u64* ts = reinterpret_cast<u64*>(S.pin + c->o_ts) + t.item0;
+  u8* blob = S.pin + c->o_blob;
+  size_t at = t.byte0;
+  for (size_t i = 0; i < n; i++) {
+    six[i] = s->index;
+    off[i] = at;
+    ts[i] = has_ts ? ts_ms[i] : 0;
+    if (batches[i].size) memcpy(blob + at, batches[i].data, batches[i].size);
+    at += batches[i].size;
+  }
+  const int32_t* stv = reinterpret_cast<const int32_t*>(S.pin + c->o_st) + t.item0;
+  auto result = [stv, n](size_t* ok_out) {
+    size_t ok = 0;
+    while (ok < n && stv[ok] == 0) ok++;
+    *ok_out = ok;
+    return ok < n ? (int)stv[ok] : (int)RSP_OK;
+  };
+  if (done) {
+    c->stager->commit_async(t, [c, s, done, ctx, result] {
+      size_t ok = 0;
+      const int first = result(&ok);
+      const uint64_t seq = rsp_latest_seq(s);
+      c->done_now.push_back([done, ctx, first, ok, seq] { done(ctx, first, ok, seq); });
+    });
+    return RSP_OK;
+  }
+  c->stager->commit(t);
+  c->stager->wait(t);
+  size_t ok = 0;
+  const int first = result(&ok);
+  c->stager->release(t);
+  if (n_applied) *n_applied = ok;
+  return first;
+}
+
+// ------------------------------------------------------------------------------------------------
 // extern "C"
 // ------------------------------------------------------------------------------------------------
 extern "C" {
@@ -1277,7 +1589,6 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   if (const char* t = getenv("RSP_DIRECT_LOAD")) e->direct_load = std::min(0.9, std::max(0.05, atof(t)));
   if (const char* t = getenv("RSP_MG_PREFETCH")) e->mg_prefetch = (u32)std::max(0, atoi(t));
   CUDA_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
-  e->single_applies.reset(new rsp::GroupCommit<ApplyReq>([e](std::vector<ApplyReq*>& b) { run_single_applies(e, b); }));
   for (int k = 0; k < 3; k++) {
     CUDA_OK(cudaStreamCreateWithFlags(&e->cs[k], cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&e->cs_done[k], cudaEventDisableTiming));
@@ -1301,6 +1612,8 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
 
 void rsp_engine_destroy(rsp_engine* e) {
   if (!e) return;
+  if (e->read_comb) { e->read_comb->destroy(); delete e->read_comb; }
+  if (e->apply_comb) { e->apply_comb->destroy(); delete e->apply_comb; }
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->st);
   for (rsp_shard* s : e->slots)
@@ -1503,35 +1816,118 @@ int rsp_apply_many(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint
 int rsp_apply(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t ts_ms, uint64_t* seq_out) {
   if (!s) return RSP_INVALID_ARGUMENT;
   static const uint8_t empty = 0;
-  ApplyReq r{s->index, batch ? batch : &empty, len, ts_ms, true, 0};
-  s->eng->single_applies->submit(&r);  // concurrent callers share one device tick
+  const rsp_slice b{batch ? batch : &empty, len};
+  const int rc = apply_combined(s, 1, &b, &ts_ms, true, nullptr, nullptr, nullptr);  // concurrent callers share one device tick
   if (seq_out) *seq_out = rsp_latest_seq(s);
-  return r.status;
+  return rc;
 }
 
 int rsp_write(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t* seq_out) {
   if (!s) return RSP_INVALID_ARGUMENT;
   static const uint8_t empty = 0;
-  ApplyReq r{s->index, batch ? batch : &empty, len, 0, false, 0};
-  s->eng->single_applies->submit(&r);
+  const rsp_slice b{batch ? batch : &empty, len};
+  const int rc = apply_combined(s, 1, &b, nullptr, false, nullptr, nullptr, nullptr);
   if (seq_out) *seq_out = rsp_latest_seq(s);
-  return r.status;
+  return rc;
+}
+
+int rsp_apply_updates(rsp_shard* s, size_t n, const rsp_slice* batches, const uint64_t* ts_ms, rsp_done_fn done,
+                      void* ctx, size_t* n_applied) {
+  if (!s || (n && !batches)) return RSP_INVALID_ARGUMENT;
+  return apply_combined(s, n, batches, ts_ms, ts_ms != nullptr, done, ctx, n_applied);
+}
+
+// statuses the fast / generic kernels settle themselves; anything else (host-folded merges, error texts, unknown
+// shards) is post-processed by the direct path
+static inline bool plain_status(int32_t st) { return st == RSP_OK || st == RSP_NOT_FOUND || st == RSP_INCOMPLETE; }
+
+static int multi_get_direct(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, const uint64_t* koff,
+                            uint32_t klen_fixed, uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
+  std::lock_guard<std::mutex> g(e->mu);
+  CUDA_OK(cudaSetDevice(e->device));
+  return multi_get_locked(e, n, shard_ix, keys, koff, klen_fixed, vals, val_stride, vlen, st);
+}
+
+// rsp_multi_get / rsp_multi_get_fixed: through the read combiner when the request fits its staging buffers
+static int multi_get_any(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, const uint64_t* koff,
+                         uint32_t klen_fixed, uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
+  if (n == 0) return RSP_OK;
+  const size_t key_bytes = klen_fixed ? n * (size_t)klen_fixed : (size_t)(koff[n] - koff[0]);
+  const u32 stride = stride_class(val_stride);
+  bool special = false;
+  const bool combined = val_stride <= (1u << 20) && read_combined(
+      e, n, key_bytes, stride, [&](size_t i) { return shard_ix[i]; },
+      [&](size_t i, size_t* len) {
+        if (klen_fixed) { *len = klen_fixed; return keys + i * (size_t)klen_fixed; }
+        *len = (size_t)(koff[i + 1] - koff[i]);
+        return keys + koff[i];
+      },
+      [&](size_t i, int32_t s_i, const u8* v, u32 vl) {
+        st[i] = s_i;
+        vlen[i] = vl;
+        if (s_i == RSP_OK) {
+          if (vl > val_stride) st[i] = RSP_INCOMPLETE;
+          else if (vl) memcpy(vals + i * val_stride, v, vl);
+        } else if (!plain_status(s_i)) special = true;
+      });
+  if (combined && !special) return RSP_OK;
+  return multi_get_direct(e, n, shard_ix, keys, koff, klen_fixed, vals, val_stride, vlen, st);
 }
 
 int rsp_multi_get(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, const uint64_t* koff,
                   uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
   if (!e || (n && (!shard_ix || !koff || !vlen || !st))) return RSP_INVALID_ARGUMENT;
-  std::lock_guard<std::mutex> g(e->mu);
-  CUDA_OK(cudaSetDevice(e->device));
-  return multi_get_locked(e, n, shard_ix, keys, koff, 0, vals, val_stride, vlen, st);
+  return multi_get_any(e, n, shard_ix, keys, koff, 0, vals, val_stride, vlen, st);
 }
 
 int rsp_multi_get_fixed(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, uint32_t klen,
                         uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
   if (!e || !klen || (n && (!shard_ix || !keys || !vlen || !st))) return RSP_INVALID_ARGUMENT;
-  std::lock_guard<std::mutex> g(e->mu);
-  CUDA_OK(cudaSetDevice(e->device));
-  return multi_get_locked(e, n, shard_ix, keys, nullptr, klen, vals, val_stride, vlen, st);
+  return multi_get_any(e, n, shard_ix, keys, nullptr, klen, vals, val_stride, vlen, st);
+}
+
+int rsp_multi_get_slices(rsp_shard* s, size_t n, const rsp_slice* keys, size_t value_hint, rsp_value_fn fn, void* ctx) {
+  if (!s || !fn || (n && !keys)) return RSP_INVALID_ARGUMENT;
+  if (n == 0) return RSP_OK;
+  rsp_engine* e = s->eng;
+  size_t key_bytes = 0;
+  for (size_t i = 0; i < n; i++) key_bytes += keys[i].size;
+  static const uint8_t empty = 0;
+  std::vector<uint32_t> again;  // values larger than the stride of the first pass
+  size_t need = 0;
+  bool special = false;
+  const u32 stride = stride_class(value_hint ? value_hint : 256);
+  const bool combined = read_combined(
+      e, n, key_bytes, stride, [&](size_t) { return s->index; },
+      [&](size_t i, size_t* len) { *len = keys[i].size; return keys[i].data ? keys[i].data : &empty; },
+      [&](size_t i, int32_t st, const u8* v, u32 vl) {
+        if (st == RSP_INCOMPLETE) { again.push_back((uint32_t)i); need = std::max<size_t>(need, vl); }
+        else if (!plain_status(st)) special = true;
+        else if (!special) fn(ctx, i, st, st == RSP_OK ? v : nullptr, st == RSP_OK ? vl : 0);
+      });
+  if (combined && !special && again.empty()) return RSP_OK;
+  // the rest (oversized values; or everything when the request did not fit / met a special status) on the direct path
+  std::vector<uint32_t> idx;
+  if (combined && !special) idx.swap(again);
+  else { idx.resize(n); for (size_t i = 0; i < n; i++) idx[i] = (uint32_t)i; }
+  const size_t m = idx.size();
+  std::vector<uint32_t> six(m, s->index), vlen(m);
+  std::vector<uint64_t> koff(m + 1, 0);
+  std::vector<int32_t> st(m);
+  std::string blob;
+  for (size_t j = 0; j < m; j++) { blob.append((const char*)keys[idx[j]].data, keys[idx[j]].size); koff[j + 1] = blob.size(); }
+  blob.push_back('\0');
+  size_t vs = std::max<size_t>(stride_class(std::max<size_t>(need, value_hint ? value_hint : 256)), 64);
+  for (;;) {
+    std::vector<uint8_t> vals(m * vs);
+    const int rc = multi_get_direct(e, m, six.data(), (const uint8_t*)blob.data(), koff.data(), 0, vals.data(), vs, vlen.data(), st.data());
+    if (rc != RSP_OK) return rc;
+    size_t more = 0;
+    for (size_t j = 0; j < m; j++) if (st[j] == RSP_INCOMPLETE) more = std::max<size_t>(more, vlen[j]);
+    if (more) { vs = stride_class(more); continue; }
+    for (size_t j = 0; j < m; j++) fn(ctx, idx[j], st[j], st[j] == RSP_OK ? &vals[j * vs] : nullptr, st[j] == RSP_OK ? vlen[j] : 0);
+    return RSP_OK;
+  }
 }
 
 int rsp_get(rsp_shard* s, const uint8_t* key, size_t klen, uint8_t* val, size_t cap, size_t* vlen) {
@@ -1541,7 +1937,8 @@ int rsp_get(rsp_shard* s, const uint8_t* key, size_t klen, uint8_t* val, size_t 
   uint32_t vl = 0;
   int32_t st = 0;
   static const uint8_t empty = 0;
-  int rc = rsp_multi_get(s->eng, 1, &six, key ? key : &empty, koff, val, cap, &vl, &st);
+  // n = 1 through the read combiner: concurrent Get callers (up to 256 thrift workers in the reference) share launches
+  int rc = multi_get_any(s->eng, 1, &six, key ? key : &empty, koff, 0, val, cap, &vl, &st);
   if (rc != RSP_OK) return rc;
   if (vlen) *vlen = vl;
   return st;

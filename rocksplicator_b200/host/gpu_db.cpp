@@ -206,6 +206,59 @@ Status GpuDB::ApplyReplicated(const Slice& raw, uint64_t ts) {
   return Status::OK();
 }
 
+void GpuDB::ApplyReplicatedBatch(const std::vector<replicator::Update>& updates,
+                                 std::function<void(size_t, const rocksdb::Status&)> done) {
+  const size_t n = updates.size();
+  if (!n) return done(0, Status::OK());
+  struct Ctx {
+    GpuDB* db;
+    const std::vector<replicator::Update>* updates;
+    std::function<void(size_t, const rocksdb::Status&)> done;
+    uint64_t seq_before;
+  };
+  std::vector<rsp_slice> slices(n);
+  std::vector<uint64_t> ts(n);
+  for (size_t i = 0; i < n; i++) {
+    slices[i] = rsp_slice{(const uint8_t*)updates[i].raw_data.data(), updates[i].raw_data.size()};
+    ts[i] = (uint64_t)updates[i].timestamp;
+  }
+  // one response at a time per shard (the pull loop is serial per shard): the sequence number before the call is the
+  // base of this response's batches in the update log
+  Ctx* ctx = new Ctx{this, &updates, std::move(done), GetLatestSequenceNumber()};
+  const int rc = rsp_apply_updates(
+      shard_, n, slices.data(), ts.data(),
+      [](void* c, int status, size_t n_applied, uint64_t) {
+        std::unique_ptr<Ctx> x(static_cast<Ctx*>(c));
+        uint64_t first = x->seq_before + 1;
+        {
+          std::lock_guard<std::mutex> g(x->db->write_mu_);
+          for (size_t i = 0; i < n_applied; i++) {
+            const std::string& raw = (*x->updates)[i].raw_data;
+            if (raw.size() < rocksdb::WriteBatch::kHeader) continue;
+            uint32_t count;
+            memcpy(&count, raw.data() + 8, 4);
+            if (!count) continue;
+            const uint64_t tsv = (uint64_t)(*x->updates)[i].timestamp;
+            std::string bytes;
+            bytes.reserve(raw.size() + 10);
+            bytes.assign(raw.data(), raw.size());
+            bytes.push_back(0x3);
+            bytes.push_back(8);
+            bytes.append((const char*)&tsv, 8);
+            memcpy(&bytes[0], &first, 8);
+            x->db->LogAppend(first, std::move(bytes), count);
+            first += count;
+          }
+        }
+        x->done(n_applied, status == RSP_OK ? Status::OK() : x->db->ToStatus(status));
+      },
+      ctx, nullptr);
+  if (rc != RSP_OK) {
+    std::unique_ptr<Ctx> x(ctx);
+    x->done(0, ToStatus(rc));
+  }
+}
+
 Status GpuDB::Get(const rocksdb::ReadOptions&, const Slice& key, std::string* value) {
   size_t cap = 256, n = 0;
   for (;;) {
@@ -229,31 +282,28 @@ std::vector<Status> GpuDB::MultiGet(const rocksdb::ReadOptions&, const std::vect
   std::vector<Status> out(n);
   values->assign(n, std::string());
   if (!n) return out;
-  std::vector<uint64_t> koff(n + 1, 0);
-  for (size_t i = 0; i < n; i++) koff[i + 1] = koff[i] + keys[i].size();
-  std::string blob;
-  blob.reserve(koff[n] + 1);
-  for (auto& k : keys) blob.append(k.data(), k.size());
-  blob.push_back('\0');
-  std::vector<uint32_t> six(n, rsp_shard_index(shard_)), vlen(n);
-  std::vector<int32_t> st(n);
-  size_t stride = 256;
-  for (;;) {
-    std::vector<uint8_t> vals(n * stride);
-    if (rsp_multi_get(engine(), n, six.data(), (const uint8_t*)blob.data(), koff.data(), vals.data(), stride, vlen.data(),
-                      st.data()) != RSP_OK) {
-      for (auto& s : out) s = Status::IOError("rsp_multi_get");
-      return out;
-    }
-    size_t need = 0;
-    for (size_t i = 0; i < n; i++) if (st[i] == RSP_INCOMPLETE) need = std::max<size_t>(need, vlen[i]);
-    if (need) { stride = need; continue; }
-    for (size_t i = 0; i < n; i++) {
-      if (st[i] == RSP_OK) (*values)[i].assign((const char*)&vals[i * stride], vlen[i]);
-      else out[i] = st[i] == RSP_NOT_FOUND ? Status::NotFound() : ToStatus(st[i]);
-    }
+  // rocksdb::Slice is {pointer, size}: the key array goes to the engine as it is, and every value is assigned from
+  // the engine's pinned result buffer straight into its std::string (one copy each way)
+  static_assert(sizeof(Slice) == sizeof(rsp_slice), "rocksdb::Slice and rsp_slice share a layout");
+  struct Ctx { GpuDB* db; std::vector<Status>* out; std::vector<std::string>* values; size_t max_vlen; } ctx{this, &out, values, 0};
+  const int rc = rsp_multi_get_slices(
+      shard_, n, reinterpret_cast<const rsp_slice*>(keys.data()), value_hint_.load(std::memory_order_relaxed),
+      [](void* c, size_t i, int st, const uint8_t* v, size_t vlen) {
+        Ctx* x = static_cast<Ctx*>(c);
+        if (st == RSP_OK) {
+          (*x->values)[i].assign((const char*)v, vlen);
+          if (vlen > x->max_vlen) x->max_vlen = vlen;
+        } else {
+          (*x->out)[i] = st == RSP_NOT_FOUND ? Status::NotFound() : x->db->ToStatus(st);
+        }
+      },
+      &ctx);
+  if (rc != RSP_OK) {
+    for (auto& s : out) s = Status::IOError("rsp_multi_get");
     return out;
   }
+  if (ctx.max_vlen > value_hint_.load(std::memory_order_relaxed)) value_hint_.store(ctx.max_vlen, std::memory_order_relaxed);
+  return out;
 }
 
 namespace {

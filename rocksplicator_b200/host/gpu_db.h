@@ -2,13 +2,16 @@
 // RocksDBReplicator::addDB / ApplicationDB in place of the rocksdb::DB* that rocksdb::DB::Open returns at
 // rocksdb_admin/admin_handler.cpp:640.  Host code only: no CUDA types; every data call ends in librsp_b200.so.
 #pragma once
+#include <atomic>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
 
 #include "../../include/rsp_b200.h"
 #include "rocksdb/db.h"
+#include "rocksdb_replicator/replicator_types.h"
 
 namespace b200 {
 
@@ -63,6 +66,11 @@ class GpuDB : public rocksdb::DB {
   // (rocksdb_replicator/rocksdb_wrapper.cpp:13-28) as one engine call — the raw bytes go to the device,
   // which appends the LogData(timestamp) record, decodes, sequences and inserts.
   rocksdb::Status ApplyReplicated(const rocksdb::Slice& raw_data, uint64_t timestamp_ms);
+  // The same for all updates of one ReplicateResponse (rsp_apply_updates): copied into the engine's open tick, applied
+  // in order with every other shard's response; done(n_applied, status of the first failure) runs on an engine
+  // completion thread once the tick has run.  `updates` must stay alive until done has been called.
+  void ApplyReplicatedBatch(const std::vector<replicator::Update>& updates,
+                            std::function<void(size_t, const rocksdb::Status&)> done);
 
   rsp_shard* shard() const { return shard_; }
   rsp_engine* engine() const { return engine_->raw(); }
@@ -89,6 +97,7 @@ class GpuDB : public rocksdb::DB {
   uint64_t log_base_id_ = 0;  // id of log_[0]
   size_t log_bytes_ = 0;
   size_t log_cap_bytes_ = 256u << 20;
+  std::atomic<size_t> value_hint_{0};  // largest value MultiGet has seen (the staging stride of its first pass)
 };
 
 }  // namespace b200

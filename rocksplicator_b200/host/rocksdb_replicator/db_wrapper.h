@@ -6,7 +6,9 @@
 // (rocksdb_wrapper.cpp), the CDC observer (cdc_admin/cdc_application_db.cpp:19-37) and TestDBProxy.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <memory>
+#include <vector>
 
 #include "rocksdb/db.h"
 #include "rocksdb_replicator/replicator_types.h"
@@ -33,6 +35,22 @@ class DbWrapper {
   // FOLLOWER side.  Apply one replicated update (raw WriteBatch bytes + the leader's timestamp).  false = not
   // applied; the pull loop backs off and asks for the same sequence again.
   virtual bool HandleReplicateResponse(Update* update) = 0;
+
+  // FOLLOWER side, B200 addition (not in the reference's interface; the default keeps every existing wrapper valid):
+  // apply the updates of ONE ReplicateResponse in order and report how many were applied — the body of the
+  // reference's hot loop (replicated_db.cpp:369-383: one HandleReplicateResponse per update, stop at the first
+  // failure).  done may run later on another thread; `updates` must stay alive until then.  A wrapper whose store
+  // batches across shards (GpuDbWrapper) overrides this so that the >= 16 executor threads do not wait for the
+  // device one update at a time.
+  using AppliedCallback = std::function<void(size_t n_applied)>;
+  virtual void HandleReplicateResponses(std::vector<Update>* updates, AppliedCallback done) {
+    size_t n = 0;
+    for (auto& u : *updates) {
+      if (!HandleReplicateResponse(&u)) break;
+      n++;
+    }
+    done(n);
+  }
 };
 
 }  // namespace replicator

@@ -37,4 +37,15 @@ bool GpuDbWrapper::HandleReplicateResponse(Update* update) {
   return status.ok();
 }
 
+void GpuDbWrapper::HandleReplicateResponses(std::vector<Update>* updates, AppliedCallback done) {
+  auto* gdb = dynamic_cast<b200::GpuDB*>(db_.get());
+  if (!gdb) return DbWrapper::HandleReplicateResponses(updates, std::move(done));
+  const std::string name = db_name_;
+  gdb->ApplyReplicatedBatch(*updates, [name, done](size_t n_applied, const rocksdb::Status& status) {
+    if (!status.ok())
+      fprintf(stderr, "Failed to apply updates to FOLLOWER %s %s\n", name.c_str(), status.ToString().c_str());
+    done(n_applied);
+  });
+}
+
 }  // namespace replicator

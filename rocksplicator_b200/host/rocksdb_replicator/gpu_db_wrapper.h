@@ -15,6 +15,8 @@ class GpuDbWrapper : public DbWrapper {
   rocksdb::Status GetUpdatesFromLeader(rocksdb::SequenceNumber seq_number,
                                        std::unique_ptr<rocksdb::TransactionLogIterator>* iter) override;       // :9-12
   bool HandleReplicateResponse(Update* update) override;                                 // :13-28
+  // the whole response in one engine call, completion on an engine thread (rsp_apply_updates)
+  void HandleReplicateResponses(std::vector<Update>* updates, AppliedCallback done) override;
 
  private:
   const std::string db_name_;

@@ -169,33 +169,51 @@ void RocksDBReplicator::ReplicatedDB::pullFromUpstream() {
       uint64_t in_bytes = 0;
       const uint64_t now = NowMs();
       for (auto& update : response.updates) {
-        // THE HOT LOOP (replicated_db.cpp:369-383): one DbWrapper call per update, in order
         if (update.timestamp != 0)
           logMetric(kReplicatorLatency, (uint64_t)update.timestamp < now ? (int64_t)(now - (uint64_t)update.timestamp) : 0, db->db_name_);
         in_bytes += update.raw_data.size();
-        if (!db->db_wrapper_->HandleReplicateResponse(&update)) {
-          incCounter(kReplicatorHandleResponseFailure, 1, db->db_name_);
-          delay_next_pull = true;
-          break;
-        }
       }
       incCounter(kReplicatorInBytes, in_bytes, db->db_name_);
       if (response.has_role && response.role != ReplicaRole::LEADER) incCounter(kReplicatorPullFromNonLeader, 1, db->db_name_);
       if (!response.updates.empty()) {
+        // THE HOT LOOP (replicated_db.cpp:369-383: one DbWrapper call per update, in order, stop at the first
+        // failure) as ONE call for the whole response; the rest of this function continues in its completion, on our
+        // executor again (shared_t keeps the updates alive)
+        const size_t n_updates = response.updates.size();
+        Executor* ex = db->owner_->executor();
+        db->db_wrapper_->HandleReplicateResponses(&response.updates, [weak_db, shared_t, n_updates, ex](size_t n_applied) {
+          ex->add([weak_db, shared_t, n_updates, n_applied] {
+            auto db = weak_db.lock();
+            if (!db || db->removed_.load()) return;
+            const bool failed = n_applied < n_updates;
+            if (failed) incCounter(kReplicatorHandleResponseFailure, 1, db->db_name_);
+            db->pullFromUpstreamNoUpdates_ = 0;
+            db->cond_var_.notifyAll();  // chained followers long-polling on us
+            db->scheduleNextPull(failed);
+          });
+        });
+        return;
+      }
+      incCounter(kReplicatorPullRequestsNoUpdates, 1, db->db_name_);
+      db->pullFromUpstreamNoUpdates_++;
+      if (response.has_role && response.role != ReplicaRole::LEADER &&
+          Flags().reset_upstream_on_empty_updates_from_non_leader &&
+          db->pullFromUpstreamNoUpdates_ >= (uint32_t)Flags().replicator_max_consecutive_no_updates_before_upstream_reset) {
+        incCounter(kReplicatorResetUpstreamOnNoUpdates, 1, db->db_name_);
+        db->resetUpstream();
         db->pullFromUpstreamNoUpdates_ = 0;
-        db->cond_var_.notifyAll();  // chained followers long-polling on us
-      } else {
-        incCounter(kReplicatorPullRequestsNoUpdates, 1, db->db_name_);
-        db->pullFromUpstreamNoUpdates_++;
-        if (response.has_role && response.role != ReplicaRole::LEADER &&
-            Flags().reset_upstream_on_empty_updates_from_non_leader &&
-            db->pullFromUpstreamNoUpdates_ >= (uint32_t)Flags().replicator_max_consecutive_no_updates_before_upstream_reset) {
-          incCounter(kReplicatorResetUpstreamOnNoUpdates, 1, db->db_name_);
-          db->resetUpstream();
-          db->pullFromUpstreamNoUpdates_ = 0;
-        }
       }
     }
+    db->scheduleNextPull(delay_next_pull);
+   });
+  });
+}
+
+// the tail of the pull loop (replicated_db.cpp:412-431): back off after an error, otherwise pull again at once
+void RocksDBReplicator::ReplicatedDB::scheduleNextPull(bool delay_next_pull) {
+  std::weak_ptr<ReplicatedDB> weak_db = shared_from_this();
+  {
+    auto* db = this;
     if (delay_next_pull) {
       const uint32_t d = (uint32_t)Flags().replicator_pull_delay_on_error_ms;
       db->owner_->executor()->addDelayed([weak_db] {
@@ -204,8 +222,7 @@ void RocksDBReplicator::ReplicatedDB::pullFromUpstream() {
     } else {
       db->pullFromUpstream();
     }
-   });
-  });
+  }
 }
 
 void RocksDBReplicator::ReplicatedDB::handleReplicateRequest(std::unique_ptr<ReplicateRequest> request,

@@ -73,6 +73,7 @@ class RocksDBReplicator {
     ReplicatedDB(const std::string& db_name, std::shared_ptr<DbWrapper> db_wrapper, RocksDBReplicator* owner,
                  ReplicaRole role, const SocketAddress& upstream_addr);
     void pullFromUpstream();
+    void scheduleNextPull(bool delay_next_pull);
     void resetUpstream();
     rocksdb::Status writeWaitFollowerACK(uint64_t cur_seq_no);
     void handleReplicateRequest(std::unique_ptr<ReplicateRequest> request, ReplicateCallback callback);

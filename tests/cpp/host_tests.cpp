@@ -19,7 +19,7 @@
 
 #include <unistd.h>
 
-#include "../../rocksplicator_b200/csrc/group_commit.h"
+#include "../../rocksplicator_b200/csrc/stager.h"
 #include "common/dbconfig.h"
 #include "common/segment_utils.h"
 #include "common/stats.h"
@@ -126,40 +126,54 @@ static void test_write_batch_and_status() {
   EXPECT_EQ(common::ExtractShardId("seg00042"), 42);
 }
 
-// the batching front-end's core: concurrent single-update callers share device ticks (csrc/group_commit.h)
-static void test_group_commit() {
-  struct Req { int thread, seq; int result; };
-  std::atomic<int> executed{0};
-  std::vector<int> last_seq(16, -1);
-  bool order_ok = true;
-  std::mutex chk;
-  rsp::GroupCommit<Req> gc([&](std::vector<Req*>& batch) {
+// the batching front-end's core: concurrent callers copy into the open batch's staging slices in parallel and share
+// device batches; a dispatcher runs one batch after the other (csrc/stager.h)
+static void test_stager() {
+  constexpr size_t CAP = 256;
+  static int in_buf[2][CAP], out_buf[2][CAP];
+  std::atomic<int> executed{0}, async_done{0}, posts{0};
+  std::atomic<bool> classes_ok{true};
+  rsp::Stager st(CAP, CAP * 4, [&](const rsp::Stager::BatchInfo& b) {
     sleep_ms(1);  // a "tick"
-    std::lock_guard<std::mutex> g(chk);
-    for (Req* r : batch) {
-      if (last_seq[r->thread] != r->seq - 1) order_ok = false;  // a caller's requests stay in order
-      last_seq[r->thread] = r->seq;
-      r->result = r->thread * 1000 + r->seq;
+    for (size_t i = 0; i < b.n_items; i++) {
+      if ((uint32_t)(in_buf[b.buf][i] & 1) != b.klass) classes_ok = false;  // requests of different classes never mix
+      out_buf[b.buf][i] = in_buf[b.buf][i] * 2 + 1;
       executed++;
     }
-  });
+  }, [&] { posts++; });
   std::vector<std::thread> th;
   std::atomic<int> wrong{0};
   for (int t = 0; t < 16; t++)
     th.emplace_back([&, t] {
       for (int i = 0; i < 50; i++) {
-        Req r{t, i, -1};
-        gc.submit(&r);
-        if (r.result != t * 1000 + i) wrong++;
+        rsp::Stager::Ticket k;
+        const int n = 1 + (i % 3);
+        const uint32_t klass = (uint32_t)(t & 1);
+        if (!st.begin(n, n * 4, klass, CAP, &k)) { wrong++; continue; }
+        for (int j = 0; j < n; j++) in_buf[k.buf][k.item0 + j] = ((t * 100000 + i * 10 + j) << 1) | (int)klass;
+        if (i % 5 == 4) {  // asynchronous completion: checked on the dispatcher thread
+          const int buf = k.buf; const size_t i0 = k.item0;
+          st.commit_async(k, [&, buf, i0, n, t, i, klass] {
+            for (int j = 0; j < n; j++) if (out_buf[buf][i0 + j] != ((((t * 100000 + i * 10 + j) << 1) | (int)klass) * 2 + 1)) wrong++;
+            async_done++;
+          });
+        } else {
+          st.commit(k);
+          st.wait(k);
+          for (int j = 0; j < n; j++) if (out_buf[k.buf][k.item0 + j] != in_buf[k.buf][k.item0 + j] * 2 + 1) wrong++;
+          st.release(k);
+        }
       }
     });
   for (auto& t : th) t.join();
-  EXPECT_EQ(executed.load(), 16 * 50);
+  EXPECT_TRUE(wait_until([&] { return async_done.load() == 16 * 10; }));
+  rsp::Stager::Ticket big;
+  EXPECT_TRUE(!st.begin(CAP + 1, 4, 0, CAP, &big));  // can never fit: the caller takes its direct path
   EXPECT_EQ(wrong.load(), 0);
-  EXPECT_TRUE(order_ok);
-  EXPECT_EQ(gc.requests(), (uint64_t)800);
-  EXPECT_TRUE(gc.batches() < 400);  // combining happened: far fewer ticks than requests
-  printf("  group commit: %llu requests in %llu ticks\n", (unsigned long long)gc.requests(), (unsigned long long)gc.batches());
+  EXPECT_TRUE(classes_ok.load());
+  EXPECT_TRUE(st.batches() < 800);  // combining happened: fewer batches than requests
+  EXPECT_TRUE(posts.load() == (int)st.batches() || posts.load() + 1 == (int)st.batches());
+  printf("  stager: 800 requests (%d items) in %llu batches\n", executed.load(), (unsigned long long)st.batches());
 }
 
 // ---- a DbWrapper that only counts and logs: rocksdb_replicator/test_db_proxy.cpp's role -------------
@@ -749,6 +763,40 @@ static void test_application_db_manager() {
   EXPECT_EQ(m.Introspect(), std::string("ApplicationDBManager:\ntest_db1:\n __no_replicated_db__\n"));
 }
 
+// the hot path through the reference's seams (host/bench/seam_bench.cpp): followers pull from a synthetic leader through
+// RocksDBReplicator / DbWrapper, readers call ApplicationDB::MultiGet / Get from several threads, updates race reads;
+// every value read back is checked against the generator
+extern "C" {
+struct rsp_seam_cfg {
+  int32_t device; uint32_t shards; uint64_t kv_total; uint32_t value_len, executor_threads, updates_per_response, update_rounds,
+      multiget_threads, multiget_batch; double multiget_secs; uint32_t get_threads; double get_secs; uint64_t seed;
+  uint32_t first_shard_id, reserved;
+};
+struct rsp_seam_result {
+  double load_s, load_applies_per_s, resp_p50_ms, resp_p99_ms, compact_s, mget_lookups_per_s, mget_p50_ms, mget_p99_ms;
+  uint64_t mget_calls; double get_per_s, get_p50_us, get_p99_us, mixed_applies_per_s, mixed_lookups_per_s, mixed_resp_p50_ms,
+      mixed_resp_p99_ms; uint64_t applied_total, parity_errors, status_errors, engine_launches;
+};
+int rsp_seam_bench(const rsp_seam_cfg*, rsp_seam_result*);
+}
+static void test_gpu_seams() {
+  rsp_seam_cfg c;
+  memset(&c, 0, sizeof(c));
+  c.shards = 6; c.kv_total = 6 * 700; c.value_len = 64; c.executor_threads = 16; c.updates_per_response = 50; c.update_rounds = 4;
+  c.multiget_threads = 4; c.multiget_batch = 256; c.multiget_secs = 0.3; c.get_threads = 4; c.get_secs = 0.2; c.first_shard_id = 40;
+  rsp_seam_result r;
+  EXPECT_EQ(rsp_seam_bench(&c, &r), 0);
+  EXPECT_EQ(r.parity_errors, (uint64_t)0);
+  EXPECT_EQ(r.status_errors, (uint64_t)0);
+  EXPECT_EQ(r.applied_total, (uint64_t)(6 * (700 + 4 * 50)));
+  EXPECT_TRUE(r.mget_calls > 0 && r.get_per_s > 0 && r.load_applies_per_s > 0 && r.mixed_applies_per_s > 0);
+  printf("  seams: load %.0f applies/s, MultiGet %.0f lookups/s (%llu calls), Get %.0f /s, mixed %.0f applies/s + %.0f lookups/s\n",
+         r.load_applies_per_s, r.mget_lookups_per_s, (unsigned long long)r.mget_calls, r.get_per_s, r.mixed_applies_per_s, r.mixed_lookups_per_s);
+  c.value_len = 256; c.first_shard_id = 60; c.update_rounds = 0;  // config-5 shape: 256-byte values
+  EXPECT_EQ(rsp_seam_bench(&c, &r), 0);
+  EXPECT_EQ(r.parity_errors + r.status_errors, (uint64_t)0);
+}
+
 int main(int argc, char** argv) {
   const std::string mode = argc > 1 ? argv[1] : "cpu";
   // `only=<name>` (second argument) runs one test by name, whatever its mode
@@ -759,7 +807,7 @@ int main(int argc, char** argv) {
       {"max_number_box", test_max_number_box, false},
       {"non_blocking_condition_variable", test_nbcv, false},
       {"write_batch_and_status", test_write_batch_and_status, false},
-      {"group_commit", test_group_commit, false},
+      {"stager", test_stager, false},
       {"replication_protocol_counting", test_replication_protocol_counting, false},
       {"tree_counting", test_tree_counting, false},
       {"upstream_reset_counting", test_upstream_reset_counting, false},
@@ -772,6 +820,7 @@ int main(int argc, char** argv) {
       {"gpu_follower_equals_leader", test_gpu_follower_equals_leader, true},
       {"counter_service_config1", test_counter_service_config1, true},
       {"application_db_manager", test_application_db_manager, true},
+      {"gpu_seams", test_gpu_seams, true},
   };
   for (auto& t : tests) {
     if (!only.empty()) {

@@ -51,7 +51,7 @@ typedef struct emul_stream* cudaStream_t;
 typedef struct emul_event* cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyHostToHost = 0 };
-enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0, cudaHostAllocPortable = 1, cudaHostAllocMapped = 2 };
 enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 
@@ -66,6 +66,7 @@ cudaError_t cudaFree(void* p);
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned flags);
 template <class T> static inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned f) { return cudaHostAlloc((void**)p, n, f); }
 cudaError_t cudaFreeHost(void* p);
+static inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return cudaSuccess; }  // one address space
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind k);
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t st = nullptr);
 cudaError_t cudaMemset(void* d, int v, size_t n);
