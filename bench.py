@@ -103,6 +103,50 @@ def run_cpu(lib_kind, threads, shards, kv, apply_cap, get_secs, batch=4096, wal=
     return json.loads(out.strip().splitlines()[-1])
 
 
+class SeamCfg(C.Structure):
+    _fields_ = [("device", C.c_int32), ("shards", C.c_uint32), ("kv_total", C.c_uint64), ("value_len", C.c_uint32),
+                ("executor_threads", C.c_uint32), ("updates_per_response", C.c_uint32), ("update_rounds", C.c_uint32),
+                ("multiget_threads", C.c_uint32), ("multiget_batch", C.c_uint32), ("multiget_secs", C.c_double),
+                ("get_threads", C.c_uint32), ("get_secs", C.c_double), ("seed", C.c_uint64),
+                ("first_shard_id", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class SeamResult(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("load_s", "load_applies_per_s", "resp_p50_ms", "resp_p99_ms", "compact_s",
+                                          "mget_lookups_per_s", "mget_p50_ms", "mget_p99_ms")] + \
+               [("mget_calls", C.c_uint64)] + \
+               [(n, C.c_double) for n in ("get_per_s", "get_p50_us", "get_p99_us", "mixed_applies_per_s",
+                                          "mixed_lookups_per_s", "mixed_resp_p50_ms", "mixed_resp_p99_ms")] + \
+               [(n, C.c_uint64) for n in ("applied_total", "parity_errors", "status_errors", "engine_launches")]
+
+
+def run_seams(device, shards, kv, rank, world, secs=2.0, value_len=64, update_rounds=20):
+    """The hot path through the reference's own seams (rocksplicator_b200/host/bench/seam_bench.cpp): followers pull
+    from a synthetic leader through RocksDBReplicator -> DbWrapper; readers call ApplicationDB::MultiGet(4096) / Get from
+    many threads.  Host buffers, H2D + D2H inside; every value checked against the generator."""
+    from rocksplicator_b200 import build
+    host_so = os.environ.get("RSP_TEST_EMUL_HOST_LIB")  # tests/emul/bench_dryrun.py only (CPU emulation, no timings)
+    if not host_so:
+        build.build_host()
+        host_so = build.HOST_SO
+    lib = C.CDLL(host_so)
+    lib.rsp_seam_bench.restype = C.c_int
+    lib.rsp_seam_bench.argtypes = [C.POINTER(SeamCfg), C.POINTER(SeamResult)]
+    cores = os.cpu_count() or 8
+    share = max(1, cores // max(1, world))
+    cfg = SeamCfg(device=device, shards=shards, kv_total=kv, value_len=value_len,
+                  executor_threads=max(16, min(32, share // 2)), updates_per_response=50, update_rounds=update_rounds,
+                  multiget_threads=max(4, min(64, share // 2)), multiget_batch=4096, multiget_secs=secs,
+                  get_threads=max(8, min(256, share * 2)), get_secs=secs / 2, seed=0x5EED0001 + rank,
+                  first_shard_id=rank * shards)
+    res = SeamResult()
+    rc = lib.rsp_seam_bench(C.byref(cfg), C.byref(res))
+    out = {n: getattr(res, n) for n, _ in SeamResult._fields_}
+    out["rc"] = rc
+    out["threads"] = {"executor": cfg.executor_threads, "multiget": cfg.multiget_threads, "get": cfg.get_threads}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -116,6 +160,7 @@ def main():
     ap.add_argument("--cpu-kv", type=int, default=2_000_000)
     ap.add_argument("--cpu-get-secs", type=float, default=6.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-seams", action="store_true", help="skip the through-the-seams phase (librsp_host.so)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -566,6 +611,24 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # ---- the same path through the reference's seams: DbWrapper (pull loop) and ApplicationDB (MultiGet / Get) ------
+    seams = None
+    if not args.no_seams:
+        for h in staged:
+            lib.rsp_stage_free(h)
+        staged = []
+        barrier()
+        try:
+            seams = run_seams(local_rank, S, NKV, rank, world)
+        except Exception as ex:  # noqa: BLE001
+            seams = {"rc": -1, "error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+        ok = 1.0 if (seams.get("rc") == 0 and seams.get("parity_errors") == 0 and seams.get("status_errors") == 0) else 0.0
+        seams_all_ok = sum_over_ranks(ok) == world
+        seams_sum = {k: sum_over_ranks(float(seams.get(k, 0.0))) for k in (
+            "load_applies_per_s", "mget_lookups_per_s", "get_per_s", "mixed_applies_per_s", "mixed_lookups_per_s")}
+        seams_max = {k: max_over_ranks(float(seams.get(k, 0.0))) for k in (
+            "resp_p50_ms", "resp_p99_ms", "mget_p50_ms", "mget_p99_ms", "get_p50_us", "get_p99_us", "mixed_resp_p50_ms",
+            "mixed_resp_p99_ms")}
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu:
         r = run_cpu("reference", ncores, S, args.cpu_kv, 30.0, args.cpu_get_secs)
@@ -605,6 +668,16 @@ def main():
                       "scan_len": LSC, "scans_per_launch": NSC,
                       "hbm_frac_of_peak": (entries_last * 168 + 16 * NSC) / (sc_total_ms * 1e-3 / max(K, 1)) / 1e9 / peak},
             "e2e": {"value": tot_lookups / mg_e2e_s, "unit": "lookups/s", "h2d_bytes_per_step": Q * 20, "d2h_bytes_per_step": Q * 72},
+            "seams": (None if seams is None else {
+                "what": "the same path through the reference's seams (librsp_host.so): %d follower pull loops (RocksDBReplicator -> DbWrapper::HandleReplicateResponses, 50 updates per response, synthetic leader behind the Transport interface) load %d KV; ApplicationDB::MultiGet(4096 keys of one shard) and ApplicationDB::Get from caller threads; host std::string / Slice buffers, H2D + D2H inside; values checked against the generator" % (S * world, NKV * world),
+                "ok": bool(seams_all_ok), "threads_per_rank": seams.get("threads"), "error": seams.get("error"),
+                "applies_per_s": seams_sum["load_applies_per_s"], "response_to_next_pull_ms": {"p50": seams_max["resp_p50_ms"], "p99": seams_max["resp_p99_ms"]},
+                "multiget_lookups_per_s": seams_sum["mget_lookups_per_s"], "multiget_call_ms": {"p50": seams_max["mget_p50_ms"], "p99": seams_max["mget_p99_ms"]},
+                "get_per_s": seams_sum["get_per_s"], "get_call_us": {"p50": seams_max["get_p50_us"], "p99": seams_max["get_p99_us"]},
+                "mixed": {"what": "config 3: replicated updates flowing through the pull loops while MultiGet runs",
+                          "applies_per_s": seams_sum["mixed_applies_per_s"], "lookups_per_s": seams_sum["mixed_lookups_per_s"],
+                          "response_to_next_pull_ms": {"p50": seams_max["mixed_resp_p50_ms"], "p99": seams_max["mixed_resp_p99_ms"]}},
+                "rank0": {k: seams.get(k) for k in ("load_s", "compact_s", "mget_calls", "applied_total", "parity_errors", "status_errors", "engine_launches")}}),
             "cpu_baseline": cpu,
             "gpu_launches": int(mg_launches + ap_launches),
             "clocks": clk,

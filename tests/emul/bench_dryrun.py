@@ -59,6 +59,7 @@ def _strip_device(fn):
 
 def install():
     engine.SO_PATH = os.environ.get("RSP_TEST_EMUL_LIB", os.path.join(ROOT, "tests", "emul", "build", "librsp_b200_emul.so"))
+    os.environ.setdefault("RSP_TEST_EMUL_HOST_LIB", os.path.join(os.path.dirname(engine.SO_PATH), "librsp_host_emul.so"))
     tc = torch.cuda
     tc.is_available = lambda: True
     tc.set_device = lambda *a, **k: None
