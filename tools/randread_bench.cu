@@ -14,7 +14,7 @@ __device__ __forceinline__ uint64_t mix(uint64_t x) {
 }
 template <int LANES, bool DEP>
 __global__ void k(const uint4* __restrict__ heap, uint64_t heap_entries, const uint4* __restrict__ idx, uint64_t idx_sectors,
-                  uint4* __restrict__ out, uint32_t n, uint64_t salt) {
+                  uint4* __restrict__ out, uint32_t n, uint64_t salt, uint32_t stride_units) {
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
   const uint32_t lane = threadIdx.x % LANES;
   if (q >= n) return;
@@ -27,7 +27,7 @@ __global__ void k(const uint4* __restrict__ heap, uint64_t heap_entries, const u
   if (DEP) e = (e + (s.x & 1)) % heap_entries;  // entry address depends on the index read
   acc.x = s.x ^ s.y;
   // entry: 6 units of 16 B; value = units 2..5
-  const uint4* ep = heap + e * 6;
+  const uint4* ep = heap + e * stride_units;
   if (LANES == 2) {
     uint4 hd = __ldg(ep), ky = __ldg(ep + 1);
     uint4 v0 = __ldg(ep + 2 + lane), v1 = __ldg(ep + 4 + lane);
@@ -42,10 +42,11 @@ __global__ void k(const uint4* __restrict__ heap, uint64_t heap_entries, const u
 int main(int argc, char** argv) {
   size_t heap_mb = argc > 1 ? atoi(argv[1]) : 960, idx_mb = argc > 2 ? atoi(argv[2]) : 80;
   uint32_t n = argc > 3 ? atoi(argv[3]) : (1u << 20);
-  uint64_t heap_entries = heap_mb * 1048576ull / 96, idx_sectors = idx_mb * 1048576ull / 32;
+  uint32_t stride = argc > 4 ? atoi(argv[4]) : 96;  // bytes between entries: 96 = packed (half of them straddle a 128-byte line), 128 = line-aligned
+  uint64_t heap_entries = heap_mb * 1048576ull / stride, idx_sectors = idx_mb * 1048576ull / 32;
   uint4 *heap, *idx, *out;
-  cudaMalloc(&heap, heap_entries * 96); cudaMalloc(&idx, idx_sectors * 32); cudaMalloc(&out, (size_t)n * 64);
-  cudaMemset(heap, 1, heap_entries * 96); cudaMemset(idx, 2, idx_sectors * 32);
+  cudaMalloc(&heap, heap_entries * stride); cudaMalloc(&idx, idx_sectors * 32); cudaMalloc(&out, (size_t)n * 64);
+  cudaMemset(heap, 1, heap_entries * stride); cudaMemset(idx, 2, idx_sectors * 32);
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   for (int dep = 0; dep < 2; dep++)
     for (int lanes : {2, 8})
@@ -54,10 +55,10 @@ int main(int argc, char** argv) {
         for (int it = 0; it < 8; it++) {
           cudaEventRecord(a);
           uint32_t grid = (uint32_t)(((uint64_t)n * lanes + tpb - 1) / tpb);
-          if (lanes == 2) { if (dep) k<2, true><<<grid, tpb>>>(heap, heap_entries, idx, idx_sectors, out, n, it * 7919ull);
-                            else k<2, false><<<grid, tpb>>>(heap, heap_entries, idx, idx_sectors, out, n, it * 7919ull); }
-          else { if (dep) k<8, true><<<grid, tpb>>>(heap, heap_entries, idx, idx_sectors, out, n, it * 7919ull);
-                 else k<8, false><<<grid, tpb>>>(heap, heap_entries, idx, idx_sectors, out, n, it * 7919ull); }
+          if (lanes == 2) { if (dep) k<2, true><<<grid, tpb>>>(heap, heap_entries, idx, idx_sectors, out, n, it * 7919ull, stride / 16);
+                            else k<2, false><<<grid, tpb>>>(heap, heap_entries, idx, idx_sectors, out, n, it * 7919ull, stride / 16); }
+          else { if (dep) k<8, true><<<grid, tpb>>>(heap, heap_entries, idx, idx_sectors, out, n, it * 7919ull, stride / 16);
+                 else k<8, false><<<grid, tpb>>>(heap, heap_entries, idx, idx_sectors, out, n, it * 7919ull, stride / 16); }
           cudaEventRecord(b); cudaEventSynchronize(b);
           float ms; cudaEventElapsedTime(&ms, a, b);
           if (it >= 2 && ms < best) best = ms;
