@@ -213,6 +213,7 @@ struct rsp_shard {
   std::mutex err_mu;
   rsp_stats stats{};
   size_t mt_heap_bytes = 0, mt_slot_bytes = 0, mt_ent_bytes = 0;
+  bool counted_multirun = false;  // this shard is counted in the engine's n_multirun
 };
 
 struct rsp_staged {
@@ -262,16 +263,10 @@ struct rsp_engine {
   cudaEvent_t mut_ev = nullptr;
   bool mut_recorded = false;
   size_t stage_threads = 1;
-  // EXPERIMENT (RSP_DIRECT_RUNS=1): fully compacted fixed-shape runs are laid out as RUN_DIRECT (format.cuh) and
-  // MultiGet goes through k_multi_get16d.  Off by default; direct_load = entries / slots.
-  bool direct_runs = false;
-  double direct_load = 0.5;
-  // EXPERIMENT (RSP_MG_PREFETCH=<lookups>): k_multi_get16d<.., PF> requests lookup q + distance's first sectors into L2
-  u32 mg_prefetch = 0;
-  // EXPERIMENT (RSP_MG_MULTIRUN=1): per-run descriptors for k_multi_get16d, so a shard with several runs stays on the
-  // fast path (newest run first) instead of the generic kernel
-  bool mg_multirun = false;
-  ShardFast* d_fast_runs = nullptr;  // = d_fast + max_shards: [max_shards][RSP_MAX_RUNS], same allocation
+  // per-run descriptors of every shard ([max_shards][RSP_MAX_RUNS], behind d_fast in the same allocation): the fast
+  // MultiGet kernel walks a shard's runs newest first when some shard has more than one (n_multirun counts them)
+  ShardFast* d_fast_runs = nullptr;
+  std::atomic<u32> n_multirun{0};
   u32 mg_parity = 0;
   size_t pending_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -316,22 +311,20 @@ static void upload_shard(rsp_engine* e, rsp_shard* s) {
   auto describe = [](const Run& r, ShardFast* f) {
     f->run0_heap = (u64)r.heap; f->run0_hslots = (u64)r.hslots; f->n_buckets = r.n_buckets;
     f->meta = r.ord_bits | (std::min<u32>(r.uniform_units, 255u) << 8);
-    if (r.flags & RUN_DIRECT) {
-      // uniform_units is 0 for such a run, so k_multi_get16 defers to the generic path; k_multi_get16d reads the
-      // slot geometry from the (for it unused) index pointer field
-      const u32 U = 1u + units_of(r.kv_len & 0xffffu) + units_of(r.kv_len >> 16);
-      f->run0_hslots = (u64)U | ((u64)(r.heap_units / U) << 32);
-      f->meta |= FAST_META_DIRECT;
-    }
   };
   ShardFast f;
   memset(&f, 0, sizeof(f));
   if (!s->runs.empty()) describe(*s->runs[0], &f);
-  if (e->d_fast_runs) {
+  {
     ShardFast fr[RSP_MAX_RUNS];
     memset(fr, 0, sizeof(fr));
     for (size_t i = 0; i < s->runs.size() && i < RSP_MAX_RUNS; i++) describe(*s->runs[i], &fr[i]);
     CUDA_OK(cudaMemcpyAsync(e->d_fast_runs + (size_t)s->index * RSP_MAX_RUNS, fr, sizeof(fr), cudaMemcpyHostToDevice, e->st));
+  }
+  const bool multi_now = s->runs.size() > 1;
+  if (multi_now != s->counted_multirun) {
+    if (multi_now) e->n_multirun++; else e->n_multirun--;
+    s->counted_multirun = multi_now;
   }
   f.meta |= (u32)std::min<size_t>(s->runs.size(), 255) << 16;
   f.meta |= 1u << 24;  // live
@@ -474,44 +467,6 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
   launch_compact_write(d_jobs, nj, max_items, e->st);
   CUDA_OK(cudaGetLastError());
   e->launches += 1;
-  // EXPERIMENT: a fully compacted run of same-size Puts with 16-byte keys, one version per key, is re-laid out as
-  // RUN_DIRECT; the sorted heap it was written to is released after the sync below
-  std::vector<std::pair<void*, size_t>> sorted_heaps;
-  PlaceJob* d_place = nullptr;
-  size_t n_place = 0;
-  if (e->direct_runs) {
-    std::vector<PlaceJob> pj;
-    u32 max_ent = 0;
-    for (u32 i = 0; i < nj; i++) {
-      Run& r = *outs[i];
-      const u32 keys = totals[8 * i + 3];
-      const u32 U = r.uniform_units;
-      const bool only_run = jh[i].full || jh[i].s->runs.empty();
-      if (!(r.flags & RUN_ALL_PUT_FIXED) || !only_run || (r.kv_len & 0xffffu) != 16 || keys != r.n_ent || U < 2 || U > 254) continue;
-      const u64 n_slots = std::max<u64>(8, (u64)((double)r.n_ent / e->direct_load) + 1);
-      if (n_slots * U > 0xffffffffull) continue;
-      PlaceJob p;
-      memset(&p, 0, sizeof(p));
-      p.src_heap = r.heap; p.ent_off = r.ent_off; p.n_ent = r.n_ent; p.U = U; p.n_slots = (u32)n_slots;
-      p.dst_heap = (u8*)a.alloc((size_t)n_slots * U * 16);
-      CUDA_OK(cudaMemsetAsync(p.dst_heap, 0, (size_t)n_slots * U * 16, e->st));
-      sorted_heaps.emplace_back(r.heap, (size_t)r.heap_units * 16);
-      r.heap = p.dst_heap;
-      r.heap_units = (u32)(n_slots * U);
-      r.uniform_units = 0;
-      r.flags = RUN_DIRECT;
-      pj.push_back(p);
-      max_ent = std::max(max_ent, p.n_ent);
-    }
-    if (!pj.empty()) {
-      n_place = pj.size();
-      d_place = (PlaceJob*)a.alloc(sizeof(PlaceJob) * n_place);
-      CUDA_OK(cudaMemcpyAsync(d_place, pj.data(), sizeof(PlaceJob) * n_place, cudaMemcpyHostToDevice, e->st));
-      launch_compact_place(d_place, (u32)n_place, max_ent, e->st);
-      e->launches += 1;
-      // pj is pageable: the copy above is staged before the call returns
-    }
-  }
   CUDA_OK(cudaEventRecord(e->ev1, e->st));
   // install
   for (u32 i = 0; i < nj; i++) {
@@ -544,8 +499,6 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
     a.release(jobs[i].totals, 32);
   }
   a.release(d_jobs, sizeof(CompactJob) * nj);
-  for (auto& h : sorted_heaps) a.release(h.first, h.second);
-  if (d_place) a.release(d_place, sizeof(PlaceJob) * n_place);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1075,8 +1028,8 @@ static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, c
     a.vals = d + o_vals + c0 * val_stride; a.val_stride = val_stride;
     a.vlen = (u32*)(d + o_vlen) + c0; a.st = (i32*)(d + o_st) + c0; a.n = (u32)cn;
     a.n_special = scratch; a.n_pending = scratch + 4 + 2 * c; a.pending = scratch + 4 + 2 * n_chunks + c0; a.parity = 0;
-    a.pf_dist = (e->mg_prefetch & ~GET_MULTIRUN) | (e->mg_multirun ? GET_MULTIRUN : 0u);
-    if (e->direct_runs || e->mg_prefetch || e->mg_multirun) launch_multi_get_direct(a, cs); else launch_multi_get(a, cs);
+    a.fast_runs = e->d_fast_runs; a.multirun = e->n_multirun.load() ? 1u : 0u; a.pad = 0;
+    launch_multi_get(a, cs);
     e->launches += 2;
     CUDA_OK(cudaMemcpyAsync(vlen + c0, d + o_vlen + c0 * 4, cn * 4, cudaMemcpyDeviceToHost, cs));
     CUDA_OK(cudaMemcpyAsync(st + c0, d + o_st + c0 * 4, cn * 4, cudaMemcpyDeviceToHost, cs));
@@ -1168,7 +1121,7 @@ static void iter_fetch(rsp_iter* it, const std::string* key, bool exclusive, boo
     a.shards = nullptr; a.views = it->d_view; a.shard_ix = nullptr; a.keys = d + o_key; a.koff = (const u64*)d;
     a.klen_fixed = 0; a.flags = d + 16; a.max_entries = (u32)it->want; a.out = d + o_out; a.out_stride = it->stride;
     a.n_out = (u32*)(d + 32); a.st = (i32*)(d + 36); a.n = 1;
-    if (e->direct_runs) launch_multi_scan_direct(a, e->st); else launch_multi_scan(a, e->st);
+    launch_multi_scan(a, e->st);
     e->launches++;
     u32 res[2];
     CUDA_OK(cudaMemcpyAsync(res, d + 32, 8, cudaMemcpyDeviceToHost, e->st));
@@ -1317,12 +1270,12 @@ struct ReadCombiner {
     a.koff = fixed16 ? nullptr : (const u64*)(base + o_koff); a.klen_fixed = fixed16 ? 16u : 0u;
     a.vals = base + o_vals; a.val_stride = stride; a.vlen = (u32*)(base + o_vlen); a.st = (i32*)(base + o_st); a.n = (u32)n;
     a.n_special = nullptr; a.n_pending = S.d_pending; a.pending = S.d_pending + 4; a.parity = 0;
-    a.pf_dist = (e->mg_prefetch & ~GET_MULTIRUN) | (e->mg_multirun ? GET_MULTIRUN : 0u);
+    a.fast_runs = e->d_fast_runs; a.multirun = e->n_multirun.load() ? 1u : 0u; a.pad = 0;
     {
       // ordering against flushes / memtable re-allocations on the engine stream (reader_begin / reader_end)
       std::lock_guard<std::mutex> g(e->mu);
       reader_begin(e, stream);
-      if (e->direct_runs || e->mg_prefetch || e->mg_multirun) launch_multi_get_direct(a, stream); else launch_multi_get(a, stream);
+      launch_multi_get(a, stream);
       CUDA_OK(cudaGetLastError());
       reader_end(e, stream);
     }
@@ -1585,9 +1538,6 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   // measured on the B200 host (128 cores): 2 staging threads 29 M applies/s, 1: 27, 8: 19 (spawn cost wins)
   e->stage_threads = 2;
   if (const char* t = getenv("RSP_STAGE_THREADS")) e->stage_threads = (size_t)std::max(1, atoi(t));
-  if (const char* t = getenv("RSP_DIRECT_RUNS")) e->direct_runs = atoi(t) != 0;
-  if (const char* t = getenv("RSP_DIRECT_LOAD")) e->direct_load = std::min(0.9, std::max(0.05, atof(t)));
-  if (const char* t = getenv("RSP_MG_PREFETCH")) e->mg_prefetch = (u32)std::max(0, atoi(t));
   CUDA_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   for (int k = 0; k < 3; k++) {
     CUDA_OK(cudaStreamCreateWithFlags(&e->cs[k], cudaStreamNonBlocking));
@@ -1599,12 +1549,11 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   CUDA_OK(cudaEventCreate(&e->ev1));
   CUDA_OK(cudaMalloc(&e->d_shards, sizeof(ShardDev) * e->cfg.max_shards));
   CUDA_OK(cudaMemset(e->d_shards, 0, sizeof(ShardDev) * e->cfg.max_shards));
-  if (const char* t = getenv("RSP_MG_MULTIRUN")) e->mg_multirun = atoi(t) != 0;
   {
-    const size_t n_fast = (size_t)e->cfg.max_shards * (e->mg_multirun ? 1 + RSP_MAX_RUNS : 1);
+    const size_t n_fast = (size_t)e->cfg.max_shards * (1 + RSP_MAX_RUNS);
     CUDA_OK(cudaMalloc(&e->d_fast, sizeof(ShardFast) * n_fast));
     CUDA_OK(cudaMemset(e->d_fast, 0, sizeof(ShardFast) * n_fast));
-    if (e->mg_multirun) e->d_fast_runs = e->d_fast + e->cfg.max_shards;
+    e->d_fast_runs = e->d_fast + e->cfg.max_shards;
   }
   *out = e;
   return RSP_OK;
@@ -1661,10 +1610,12 @@ static void shard_close_locked(rsp_shard* s) {
   CUDA_OK(cudaStreamSynchronize(e->st));
   e->slots[s->index] = nullptr;
   e->by_name.erase(s->name);
+  if (s->counted_multirun) { e->n_multirun--; s->counted_multirun = false; }
   ShardDev z;
   memset(&z, 0, sizeof(z));
   CUDA_OK(cudaMemcpy(e->d_shards + s->index, &z, sizeof(z), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemset(e->d_fast + s->index, 0, sizeof(ShardFast)));
+  CUDA_OK(cudaMemset(e->d_fast_runs + (size_t)s->index * RSP_MAX_RUNS, 0, sizeof(ShardFast) * RSP_MAX_RUNS));
   e->arena.release(s->h.mt_heap, s->mt_heap_bytes);
   e->arena.release(s->h.mt_slots, s->mt_slot_bytes);
   e->arena.release(s->h.mt_ent_off, s->mt_ent_bytes);
@@ -2095,7 +2046,7 @@ int rsp_multi_scan(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint
   a.koff = (const u64*)(d + o_koff); a.klen_fixed = 0; a.flags = nullptr; a.max_entries = max_entries;
   a.out = d + o_out; a.out_stride = out_stride; a.n_out = (u32*)(d + o_nout); a.st = (i32*)(d + o_st); a.n = (u32)n;
   CUDA_OK(cudaEventRecord(e->ev0, e->st));
-  if (e->direct_runs) launch_multi_scan_direct(a, e->st); else launch_multi_scan(a, e->st);
+  launch_multi_scan(a, e->st);
   e->launches++;
   CUDA_OK(cudaEventRecord(e->ev1, e->st));
   CUDA_OK(cudaMemcpyAsync(n_out, d + o_nout, n * 4, cudaMemcpyDeviceToHost, e->st));
@@ -2137,8 +2088,8 @@ int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, co
     a.max_shards = e->cfg.max_shards;
     cudaStream_t rs = stream ? (cudaStream_t)stream : e->st;
     reader_begin(e, rs);
-    a.pf_dist = (e->mg_prefetch & ~GET_MULTIRUN) | (e->mg_multirun ? GET_MULTIRUN : 0u);
-    if (e->direct_runs || e->mg_prefetch || e->mg_multirun) launch_multi_get_direct(a, rs); else launch_multi_get(a, rs);
+    a.fast_runs = e->d_fast_runs; a.multirun = e->n_multirun.load() ? 1u : 0u; a.pad = 0;
+    launch_multi_get(a, rs);
     reader_end(e, rs);
   }
   e->launches += 2;
@@ -2157,7 +2108,7 @@ int rsp_multi_scan_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, c
     std::lock_guard<std::mutex> g(e->mu);
     cudaStream_t rs = stream ? (cudaStream_t)stream : e->st;
     reader_begin(e, rs);
-    if (e->direct_runs) launch_multi_scan_direct(a, rs); else launch_multi_scan(a, rs);
+    launch_multi_scan(a, rs);
     reader_end(e, rs);
   }
   e->launches++;

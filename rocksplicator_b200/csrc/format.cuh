@@ -107,14 +107,7 @@ struct __align__(16) RunDev {
   u32 kv_len;    // klen | vlen << 16 when RUN_ALL_PUT_FIXED
 };
 constexpr u32 RUN_ALL_PUT_FIXED = 1u;
-// EXPERIMENT (RSP_DIRECT_RUNS=1, off by default): a run of same-size Puts with 16-byte keys whose heap is laid out as
-// an open-addressed table of entry slots (slot = hash(key) * n_slots >> 32, linear probing, empty slot = all-zero
-// header), so a point lookup reaches the entry in ONE dependent access instead of bucket -> entry.  Sorted order is
-// kept by ent_off[] alone (uniform_units = 0 forces every ordinal access through it); kv_len holds klen | vlen << 16,
-// entry size U = 1 + units(klen) + units(vlen), n_slots = heap_units / U.
-constexpr u32 RUN_DIRECT = 2u;
 constexpr u32 FAST_META_LIVE = 1u << 24;
-constexpr u32 FAST_META_DIRECT = 1u << 25;  // ShardFast: run0_hslots then holds U | n_slots << 32
 
 struct __align__(16) ShardDev {
   // ---- memtable

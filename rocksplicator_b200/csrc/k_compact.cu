@@ -303,36 +303,6 @@ __global__ void __launch_bounds__(256) k_compact_write(const CompactJob* jobs) {
   }
 }
 
-// RUN_DIRECT experiment: entry `ord` of the sorted heap moves to the first free slot at or after its home slot.
-// A slot is claimed by CAS on the header's (klen, vlen) word, which is non-zero for every real entry (klen = 16).
-__global__ void __launch_bounds__(256) k_compact_place(const PlaceJob* jobs) {
-  const PlaceJob& j = jobs[blockIdx.y];
-  const u32 ord = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ord >= j.n_ent) return;
-  const uint4* src = reinterpret_cast<const uint4*>(j.src_heap) + (u64)ord * j.U;
-  const uint4 hd = src[0];
-  const uint4 k = src[1];
-  const u64 k0 = ((u64)k.y << 32) | k.x, k1 = ((u64)k.w << 32) | k.z;
-  const u64 h = hash_final(hash_step(hash_step(hash_init(16), k0), k1));
-  u32 slot = (u32)(((u64)(u32)h * j.n_slots) >> 32);
-  const unsigned long long lens = ((unsigned long long)hd.w << 32) | hd.z;
-  uint4* dst;
-  for (;;) {
-    dst = reinterpret_cast<uint4*>(j.dst_heap) + (u64)slot * j.U;
-    if (atomicCAS(reinterpret_cast<unsigned long long*>(dst) + 1, 0ull, lens) == 0ull) break;
-    slot = slot + 1 == j.n_slots ? 0 : slot + 1;
-  }
-  *reinterpret_cast<unsigned long long*>(dst) = ((unsigned long long)hd.y << 32) | hd.x;
-  for (u32 u = 1; u < j.U; u++) dst[u] = src[u];
-  j.ent_off[ord] = slot * j.U;
-}
-
-void launch_compact_place(const PlaceJob* d_jobs, u32 n_jobs, u32 max_ent, cudaStream_t s) {
-  if (!n_jobs || !max_ent) return;
-  dim3 grid((max_ent + 255) / 256, n_jobs);
-  k_compact_place<<<grid, 256, 0, s>>>(d_jobs);
-}
-
 void launch_compact_sort(const CompactJob* d_jobs, const CompactJob* h_jobs, u32 n_jobs, cudaStream_t s) {
   if (!n_jobs) return;
   u32 max_n = 0;

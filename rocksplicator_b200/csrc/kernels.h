@@ -97,13 +97,11 @@ struct GetArgs {
   u32 parity;
   u32* n_special;        // [1] counts lookups whose status is none of OK / NotFound / Incomplete (may be nullptr)
   u32 max_shards;        // shard ids >= this answer InvalidArgument
-  u32 pf_dist;           // experiment (k_multi_get16d<.., PF>): prefetch distance in lookups (low 31 bits), 0 = off;
-                         // bit 31 (GET_MULTIRUN): `fast` is followed by [max_shards][RSP_MAX_RUNS] per-run descriptors
+  const ShardFast* fast_runs;  // [max_shards][RSP_MAX_RUNS] per-run descriptors (runs 1.. of a shard; [0] mirrors fast)
+  u32 multirun;          // some live shard has more than one run: the fast kernel walks the runs newest first
+  u32 pad;
 };
-constexpr u32 GET_MULTIRUN = 1u << 31;
 void launch_multi_get(const GetArgs& a, cudaStream_t s);
-// experiment: shards whose only run is RUN_DIRECT are served by k_multi_get16d (everything else -> generic path)
-void launch_multi_get_direct(const GetArgs& a, cudaStream_t s);
 
 // dump the version stack of each key (newest first, up to and including the first Put/Delete) for
 // host-side merge folding: records [u32 type][u32 vlen][value, padded to 4] at out + i*stride
@@ -151,7 +149,6 @@ struct ScanArgs {
   u32 n;
 };
 void launch_multi_scan(const ScanArgs& a, cudaStream_t s);
-void launch_multi_scan_direct(const ScanArgs& a, cudaStream_t s);  // experiment: + gather fast path for RUN_DIRECT
 
 // ---- flush / compaction ---------------------------------------------------------------------------
 struct SortItem {
@@ -189,17 +186,5 @@ struct CompactJob {
 void launch_compact_sort(const CompactJob* d_jobs, const CompactJob* h_jobs, u32 n_jobs, cudaStream_t s);
 void launch_compact_size(const CompactJob* d_jobs, u32 n_jobs, cudaStream_t s);
 void launch_compact_write(const CompactJob* d_jobs, u32 n_jobs, u32 max_items, cudaStream_t s);
-
-// experiment (RUN_DIRECT): scatter the entries of a freshly written uniform run into hash-addressed slots
-struct PlaceJob {
-  const u8* src_heap;  // sorted, contiguous: entry ord at ord * U units
-  u8* dst_heap;        // n_slots * U units, zeroed
-  u32* ent_off;        // [n_ent] rewritten: ordinal -> unit offset of its slot
-  u32 n_ent;
-  u32 U;
-  u32 n_slots;
-  u32 pad;
-};
-void launch_compact_place(const PlaceJob* d_jobs, u32 n_jobs, u32 max_ent, cudaStream_t s);
 
 }  // namespace rsp
