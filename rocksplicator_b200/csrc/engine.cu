@@ -372,10 +372,32 @@ static void alloc_memtable(rsp_engine* e, rsp_shard* s, u64 units, u64 ents) {
 // ------------------------------------------------------------------------------------------------
 struct JobHost {
   rsp_shard* s;
-  bool full;  // merge every run with the memtable
+  bool full;       // every run of the shard takes part: the output is the shard's only run
+  size_t n_merged; // runs[0 .. n_merged) are replaced by the output
   std::vector<std::shared_ptr<Run>> srcs;
-  size_t items_b, keep_b, fold_b;
+  size_t items_b, items2_b, coranks_b, keep_b, fold_b;
 };
+
+// Which runs join the flush?  Size-tiered (the role of RocksDB's level0_file_num_compaction_trigger + level sizing,
+// examples/counter_service/rocksdb_options.cpp:82-93): below the trigger the memtable becomes a new run by itself;
+// at the trigger the newest runs are merged with it, stopping before a run more than twice as large as everything
+// gathered so far — the big bottom run is rewritten only when the small ones have grown to its order of magnitude,
+// so write amplification stays logarithmic in the shard size instead of shard_bytes / write_buffer.
+static size_t pick_merge_set(const rsp_engine* e, const rsp_shard* s, bool has_mem, bool force_full) {
+  const size_t nr = s->runs.size();
+  if (force_full) return nr;
+  if (nr + (has_mem ? 1 : 0) < e->cfg.l0_compaction_trigger && nr + 1 <= RSP_MAX_RUNS) return 0;
+  u64 acc = has_mem ? (u64)s->h.mt_tail * 16 : 0;
+  size_t j = 0;
+  while (j < nr) {
+    const u64 sz = s->runs[j]->bytes();
+    const bool must = nr - j + 1 > RSP_MAX_RUNS - 1;  // the run table itself is nearly full
+    if (j >= 1 && !must && sz > 2 * acc) break;
+    acc += sz;
+    j++;
+  }
+  return j;
+}
 
 static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards, bool force_full) {
   std::vector<JobHost> jh;
@@ -383,38 +405,48 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
   Arena& a = e->arena;
   for (rsp_shard* s : shards) {
     const bool has_mem = s->h.mt_count > 0;
-    const bool full = force_full || (s->runs.size() + (has_mem ? 1 : 0) >= e->cfg.l0_compaction_trigger) ||
-                      s->runs.size() + 1 > RSP_MAX_RUNS;
-    if (!has_mem && (!full || s->runs.size() <= 1)) {
+    const size_t n_merged = pick_merge_set(e, s, has_mem, force_full);
+    const bool full = n_merged == s->runs.size();
+    if (!has_mem && n_merged <= 1) {
       // nothing to flush; a single run is already fully compacted unless it holds tombstones
       if (!(force_full && s->runs.size() == 1)) continue;
     }
     CompactJob j;
     memset(&j, 0, sizeof(j));
-    JobHost h{s, full, {}, 0, 0, 0};
+    JobHost h{s, full, n_merged, {}, 0, 0, 0, 0, 0};
     u32 ns = 0;
     if (has_mem) {
       j.src_heap[ns] = s->h.mt_heap; j.src_ent_off[ns] = s->h.mt_ent_off; j.src_n[ns] = s->h.mt_count;
       j.src_is_mem[ns] = 1; ns++;
+      j.n_pow2 = next_pow2(std::max<u32>(2, s->h.mt_count));
     }
-    if (full) {
-      for (auto& r : s->runs) {
-        j.src_heap[ns] = r->heap; j.src_ent_off[ns] = r->ent_off; j.src_n[ns] = r->n_ent; j.src_is_mem[ns] = 0;
-        ns++;
-        h.srcs.push_back(r);
-      }
+    for (size_t r = 0; r < n_merged; r++) {
+      auto& run = s->runs[r];
+      j.src_heap[ns] = run->heap; j.src_ent_off[ns] = run->ent_off; j.src_n[ns] = run->n_ent; j.src_is_mem[ns] = 0;
+      ns++;
+      h.srcs.push_back(run);
     }
     j.n_src = ns;
-    u64 n = 0;
-    for (u32 i = 0; i < ns; i++) n += j.src_n[i];
+    u64 n = 0, at = 0;
+    for (u32 i = 0; i < ns; i++) {
+      j.seg_start[i] = (u32)at;
+      at += (i == 0 && has_mem) ? j.n_pow2 : j.src_n[i];
+      n += j.src_n[i];
+    }
     j.n_items = (u32)n;
-    j.n_pow2 = next_pow2(std::max<u32>(2, j.n_items));
-    j.bottom = (full || s->runs.empty()) ? 1 : 0;
+    j.items_len = (u32)at;
+    j.n_tiles = ns > 1 ? (u32)((n + MERGE_TILE - 1) / MERGE_TILE) : 0;
+    j.bottom = full ? 1 : 0;
     j.merge_op = s->opts.merge_op;
-    h.items_b = (size_t)j.n_pow2 * sizeof(SortItem);
+    h.items_b = (size_t)std::max<u32>(1, j.items_len) * sizeof(SortItem);
+    h.items2_b = ns > 1 ? (size_t)std::max<u32>(1, j.n_items) * sizeof(SortItem) : 0;
+    h.coranks_b = ns > 1 ? (size_t)(j.n_tiles + 1) * ns * 4 : 0;
     h.keep_b = (size_t)std::max<u32>(1, j.n_items) * 4;
     h.fold_b = (size_t)std::max<u32>(1, j.n_items) * 8;
     j.items = (SortItem*)a.alloc(h.items_b);
+    j.items2 = ns > 1 ? (SortItem*)a.alloc(h.items2_b) : nullptr;
+    j.coranks = ns > 1 ? (u32*)a.alloc(h.coranks_b) : nullptr;
+    j.sorted = ns > 1 ? j.items2 : j.items;
     j.keep_units = (u32*)a.alloc(h.keep_b);
     j.out_pos = (u32*)a.alloc(h.keep_b);
     j.out_ord = (u32*)a.alloc(h.keep_b);
@@ -432,7 +464,7 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
   launch_compact_sort(d_jobs, jobs.data(), nj, e->st);
   launch_compact_size(d_jobs, nj, e->st);
   CUDA_OK(cudaGetLastError());  // a refused launch (e.g. shared-memory opt-in) must not pass as an unsorted run
-  e->launches += 3;
+  e->launches += 5;
   std::vector<u32> totals(8 * nj);
   for (u32 i = 0; i < nj; i++)
     CUDA_OK(cudaMemcpyAsync(&totals[8 * i], jobs[i].totals, 32, cudaMemcpyDeviceToHost, e->st));
@@ -476,7 +508,8 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
     for (auto& r : jh[i].srcs) read_b += r->bytes();
     s->stats.compaction_bytes_read += read_b;
     s->stats.compaction_bytes_written += outs[i]->bytes();
-    if (jh[i].full) { s->stats.compactions++; s->runs.clear(); } else { s->stats.flushes++; }
+    if (s->h.mt_count) s->stats.flushes++;
+    if (jh[i].n_merged) { s->stats.compactions++; s->runs.erase(s->runs.begin(), s->runs.begin() + jh[i].n_merged); }
     if (outs[i]->n_ent) s->runs.insert(s->runs.begin(), outs[i]);
     if (s->h.mt_count) {
       s->h.mt_tail = 0;
@@ -492,6 +525,8 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
   e->last_ms["compact"] = ms;
   for (u32 i = 0; i < nj; i++) {
     a.release(jobs[i].items, jh[i].items_b);
+    if (jobs[i].items2) a.release(jobs[i].items2, jh[i].items2_b);
+    if (jobs[i].coranks) a.release(jobs[i].coranks, jh[i].coranks_b);
     a.release(jobs[i].keep_units, jh[i].keep_b);
     a.release(jobs[i].out_pos, jh[i].keep_b);
     a.release(jobs[i].out_ord, jh[i].keep_b);
@@ -1246,7 +1281,7 @@ struct ReadCombiner {
   rsp_engine* e = nullptr;
   size_t cap_items = 0, cap_key_bytes = 0, cap_val_bytes = 0, zero_copy_max = 0;
   size_t o_six = 0, o_koff = 0, o_keys = 0, o_st = 0, o_vlen = 0, o_vals = 0, total = 0;
-  ReadStage st[2];
+  ReadStage st[Stager::kBuffers];
   cudaStream_t stream = nullptr;
   std::unique_ptr<Stager> stager;
 
@@ -1376,7 +1411,7 @@ struct ApplyCombiner {
   rsp_engine* e = nullptr;
   size_t cap_items = 0, cap_bytes = 0;
   size_t o_six = 0, o_off = 0, o_ts = 0, o_blob = 0, o_st = 0, total = 0;
-  ApplyStage st[2];
+  ApplyStage st[Stager::kBuffers];
   std::unique_ptr<Stager> stager;
   CompletionPool pool;
   std::vector<std::function<void()>> done_now;  // dispatcher thread only: completions of the batch that just ran

@@ -4,14 +4,21 @@
 // (rocksdb_admin/application_db.cpp:138-144) and the write-buffer / L0 triggers of
 // examples/counter_service/rocksdb_options.cpp:78-93.  Per shard ("job"):
 //
-//   k_compact_fill  : one SortItem {8-byte big-endian key prefix, entry ref, source|rank} per entry
-//   k_compact_sort  : bitonic sort by (user key asc, newest first) — prefix compare, full key on ties
+//   k_compact_fill  : one SortItem {8-byte big-endian key prefix, entry ref, source|rank} per entry, one segment per
+//                     source; a run's segment is sorted as stored
+//   k_compact_sort  : bitonic sort of the MEMTABLE segment by (user key asc, newest first) — prefix compare, full key
+//                     on ties (the unsorted source; tiles of 4096 items in shared memory)
+//   k_merge_partition / k_merge_tiles : merge of the sorted segments without re-sorting them (merge path): a thread
+//                     per tile boundary finds how many items of each segment precede it (multi-sequence selection
+//                     under the strict order key / source / rank), then one CTA per 2048-item tile gathers its
+//                     sub-ranges into shared memory, orders them there and writes the tile — many CTAs per shard
 //   k_compact_size  : per user key: keep what a read can still observe (newest Put; tombstone unless
 //                     bottom-most; Merge operands folded with the device operators, otherwise the
 //                     operand stack down to its base), then an exclusive scan -> output offsets
 //   k_compact_write : copy / synthesise the kept entries into the new heap, write the restart array
 //                     (ent_off), the block index (first-key prefix per 32 entries) and the bucketised
 //                     hash index
+#include <algorithm>
 #include <atomic>
 
 #include "kernels.h"
@@ -64,13 +71,14 @@ __device__ __forceinline__ bool same_key(const CompactJob& j, const SortItem& a,
 __global__ void __launch_bounds__(256) k_compact_fill(const CompactJob* jobs) {
   const CompactJob& j = jobs[blockIdx.y];
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= j.n_pow2) return;
+  if (i >= j.items_len) return;
   SortItem it;
-  if (i >= j.n_items) {
+  u32 src = 0;
+  while (src + 1 < j.n_src && i >= j.seg_start[src + 1]) src++;
+  const u32 k = i - j.seg_start[src];
+  if (k >= j.src_n[src]) {  // padding of the memtable segment up to its power-of-two sort size
     it.prefix = ~0ull; it.ref = PAD_REF; it.srcrank = ~0u;
   } else {
-    u32 src = 0, k = i;
-    while (k >= j.src_n[src]) { k -= j.src_n[src]; src++; }
     it.ref = j.src_ent_off[src][k];
     // ascending rank == newest first: the memtable's ordinals grow with sequence, a run is already
     // stored newest-first within a key
@@ -111,7 +119,8 @@ __global__ void __launch_bounds__(1024) k_compact_sort(const CompactJob* jobs) {
 #endif
   SortItem* tile = reinterpret_cast<SortItem*>(sort_smem);
   const CompactJob& j = jobs[blockIdx.x];
-  const u32 n = j.n_pow2;
+  const u32 n = j.n_pow2;  // the memtable segment at items[0 .. n_pow2); nothing to sort without a memtable
+  if (n < 2) return;
   SortItem* it = j.items;
   const u32 tile_n = n < SORT_TILE ? n : SORT_TILE;
   // phase 1: every tile fully sorted (all steps with k <= tile_n), directions by GLOBAL index
@@ -145,12 +154,86 @@ __global__ void __launch_bounds__(1024) k_compact_sort(const CompactJob* jobs) {
   }
 }
 
+// ---- merge of the sorted segments (merge path) -------------------------------------------------------
+// number of items of segment [lo, hi) of `seg` that order before x
+__device__ __forceinline__ u32 seg_lower_bound(const CompactJob& j, const SortItem* seg, u32 lo, u32 hi, const SortItem& x) {
+  while (lo < hi) {
+    const u32 m = (lo + hi) >> 1;
+    if (item_less(j, seg[m], x)) lo = m + 1; else hi = m;
+  }
+  return lo;
+}
+
+// One thread per tile boundary b: coranks[b * n_src + s] = how many items of segment s are among the first
+// b * MERGE_TILE items of the merged order.  Multi-sequence selection: the order (key, source, rank) is strict, so the
+// split is unique; every round halves the widest remaining range.
+__global__ void __launch_bounds__(64) k_merge_partition(const CompactJob* jobs) {
+  const CompactJob& j = jobs[blockIdx.y];
+  const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j.n_src < 2 || b > j.n_tiles) return;
+  const u32 ns = j.n_src;
+  u32* out = j.coranks + (u64)b * ns;
+  const u32 p = min(b * MERGE_TILE, j.n_items);
+  u32 lo[RSP_MAX_RUNS + 1], hi[RSP_MAX_RUNS + 1];
+  for (u32 s = 0; s < ns; s++) { lo[s] = 0; hi[s] = j.src_n[s]; }
+  if (p == 0) { for (u32 s = 0; s < ns; s++) out[s] = 0; return; }
+  if (p == j.n_items) { for (u32 s = 0; s < ns; s++) out[s] = j.src_n[s]; return; }
+  for (;;) {
+    u32 widest = 0, width = 0;
+    for (u32 s = 0; s < ns; s++) if (hi[s] - lo[s] > width) { width = hi[s] - lo[s]; widest = s; }
+    if (width == 0) break;
+    const u32 mid = lo[widest] + (width >> 1);
+    const SortItem pivot = j.items[j.seg_start[widest] + mid];
+    u32 pos[RSP_MAX_RUNS + 1];
+    u32 total = 0;
+    for (u32 s = 0; s < ns; s++) {
+      pos[s] = s == widest ? mid : seg_lower_bound(j, j.items + j.seg_start[s], lo[s], hi[s], pivot);
+      total += pos[s];
+    }
+    if (total == p) { for (u32 s = 0; s < ns; s++) lo[s] = hi[s] = pos[s]; break; }
+    if (total < p) {  // the pivot is among the first p items: everything before it is too
+      for (u32 s = 0; s < ns; s++) lo[s] = pos[s];
+      lo[widest] = mid + 1;
+    } else {          // the pivot is beyond the boundary: so is everything after it
+      for (u32 s = 0; s < ns; s++) hi[s] = pos[s];
+    }
+  }
+  for (u32 s = 0; s < ns; s++) out[s] = lo[s];
+}
+
+// One CTA per tile: gather the tile's sub-range of every segment into shared memory (together MERGE_TILE items, the
+// last tile fewer), order them there (bitonic network over 2048 items: 66 compare-exchange steps, no global traffic),
+// write the tile of the merged order.
+__global__ void __launch_bounds__(512) k_merge_tiles(const CompactJob* jobs) {
+  __shared__ SortItem tile[MERGE_TILE];
+  const CompactJob& j = jobs[blockIdx.y];
+  const u32 b = blockIdx.x;
+  if (j.n_src < 2 || b >= j.n_tiles) return;
+  const u32 ns = j.n_src;
+  const u32* c0 = j.coranks + (u64)b * ns;
+  const u32* c1 = c0 + ns;
+  u32 at = 0;
+  for (u32 s = 0; s < ns; s++) {
+    const u32 from = c0[s], cnt = c1[s] - from;
+    const SortItem* seg = j.items + j.seg_start[s] + from;
+    for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) tile[at + i] = seg[i];
+    at += cnt;
+  }
+  SortItem pad;
+  pad.prefix = ~0ull; pad.ref = PAD_REF; pad.srcrank = ~0u;
+  for (u32 i = at + threadIdx.x; i < MERGE_TILE; i += blockDim.x) tile[i] = pad;
+  __syncthreads();
+  for (u32 k = 2; k <= MERGE_TILE; k <<= 1) sort_tile_steps(j, tile, MERGE_TILE, 0, k, k >> 1);
+  SortItem* out = j.items2 + (u64)b * MERGE_TILE;
+  for (u32 i = threadIdx.x; i < at; i += blockDim.x) out[i] = tile[i];
+}
+
 __device__ __forceinline__ u32 imm_units(u32 klen) { return 1u + units_of(klen) + 1u; }
 
 __global__ void __launch_bounds__(1024) k_compact_size(const CompactJob* jobs) {
   const CompactJob& j = jobs[blockIdx.x];
   const u32 n = j.n_items;
-  const SortItem* it = j.items;
+  const SortItem* it = j.sorted;
   const bool foldable = j.merge_op == 1 || j.merge_op == 2;
   for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
     if (i > 0 && same_key(j, it[i - 1], it[i])) continue;  // not the newest version of its key
@@ -269,7 +352,7 @@ __global__ void __launch_bounds__(256) k_compact_write(const CompactJob* jobs) {
   const u32 units = ku & KEEP_UNITS_MASK;
   if (!units) return;
   const u32 mode = ku >> KEEP_MODE_SHIFT;
-  const EntView x = view_item(j, j.items[i]);
+  const EntView x = view_item(j, j.sorted[i]);
   const u32 pos = j.out_pos[i], ord = j.out_ord[i];
   u8* d = j.out_heap + (u64)pos * 16u;
   const u32 ku_key = units_of(x.klen);
@@ -286,7 +369,7 @@ __global__ void __launch_bounds__(256) k_compact_write(const CompactJob* jobs) {
     copy_units(d + 16u + 16u * ku_key, x.val, units_of(x.vlen));
   }
   j.out_ent_off[ord] = pos;
-  if (ord % RSP_BLOCK_ENTRIES == 0) j.out_blk_pfx[ord / RSP_BLOCK_ENTRIES] = j.items[i].prefix;
+  if (ord % RSP_BLOCK_ENTRIES == 0) j.out_blk_pfx[ord / RSP_BLOCK_ENTRIES] = j.sorted[i].prefix;
   if (ku & KEEP_HEAD) {
     const u64 h = hash_key_padded(x.key, x.klen);
     const u32 val = (((u32)(h >> 32) >> j.out_ord_bits) << j.out_ord_bits) | (ord + 1u);
@@ -305,21 +388,30 @@ __global__ void __launch_bounds__(256) k_compact_write(const CompactJob* jobs) {
 
 void launch_compact_sort(const CompactJob* d_jobs, const CompactJob* h_jobs, u32 n_jobs, cudaStream_t s) {
   if (!n_jobs) return;
-  u32 max_n = 0;
-  for (u32 i = 0; i < n_jobs; i++) max_n = h_jobs[i].n_pow2 > max_n ? h_jobs[i].n_pow2 : max_n;
-  if (!max_n) return;
-  dim3 grid((max_n + 255) / 256, n_jobs);
-  k_compact_fill<<<grid, 256, 0, s>>>(d_jobs);
-  // the opt-in is a per-DEVICE function attribute: one engine per GPU may live in the same process
-  static std::atomic<unsigned long long> opted_in{0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const unsigned long long bit = 1ull << (dev & 63);
-  if (!(opted_in.load(std::memory_order_acquire) & bit)) {
-    cudaFuncSetAttribute(k_compact_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_TILE * sizeof(SortItem)));
-    opted_in.fetch_or(bit, std::memory_order_release);
+  u32 max_len = 0, max_sort = 0, max_tiles = 0;
+  for (u32 i = 0; i < n_jobs; i++) {
+    max_len = std::max(max_len, h_jobs[i].items_len);
+    max_sort = std::max(max_sort, h_jobs[i].n_pow2);
+    if (h_jobs[i].n_src > 1) max_tiles = std::max(max_tiles, h_jobs[i].n_tiles);
   }
-  k_compact_sort<<<n_jobs, 1024, SORT_TILE * sizeof(SortItem), s>>>(d_jobs);
+  if (!max_len) return;
+  k_compact_fill<<<dim3((max_len + 255) / 256, n_jobs), 256, 0, s>>>(d_jobs);
+  if (max_sort >= 2) {
+    // the opt-in is a per-DEVICE function attribute: one engine per GPU may live in the same process
+    static std::atomic<unsigned long long> opted_in{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(opted_in.load(std::memory_order_acquire) & bit)) {
+      cudaFuncSetAttribute(k_compact_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_TILE * sizeof(SortItem)));
+      opted_in.fetch_or(bit, std::memory_order_release);
+    }
+    k_compact_sort<<<n_jobs, 1024, SORT_TILE * sizeof(SortItem), s>>>(d_jobs);
+  }
+  if (max_tiles) {
+    k_merge_partition<<<dim3((max_tiles + 1 + 63) / 64, n_jobs), 64, 0, s>>>(d_jobs);
+    k_merge_tiles<<<dim3(max_tiles, n_jobs), 512, 0, s>>>(d_jobs);
+  }
 }
 void launch_compact_size(const CompactJob* d_jobs, u32 n_jobs, cudaStream_t s) {
   if (!n_jobs) return;

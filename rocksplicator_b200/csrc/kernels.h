@@ -164,12 +164,18 @@ struct CompactJob {
   u32 src_is_mem[RSP_MAX_RUNS + 1];
   u32 n_src;
   u32 n_items;      // sum of src_n
-  u32 n_pow2;       // padded sort size
+  u32 n_pow2;       // sort size of the memtable segment (0 when there is none): only the memtable needs sorting
   u32 bottom;       // 1 = no older data below the output: tombstones can be dropped
   u32 merge_op;
+  u32 items_len;    // length of items[]: n_pow2 (memtable segment, padded) + the runs' entries
+  u32 seg_start[RSP_MAX_RUNS + 1];  // first item of each source's segment in items[]
+  u32 n_tiles;      // merge tiles of MERGE_TILE items (n_src > 1)
   u32 pad;
   // work buffers
-  SortItem* items;  // [n_pow2]
+  SortItem* items;  // [items_len]: one sorted segment per source (the runs are sorted as stored)
+  SortItem* items2; // [n_items]: the segments merged (n_src > 1)
+  u32* coranks;     // [(n_tiles + 1) * n_src]: how many items of each segment precede each tile boundary
+  const SortItem* sorted;  // what the sizing / writing passes read: items (one source) or items2
   u32* keep_units;  // [n_items] output size in units of each sorted item (0 = dropped)
   u32* out_pos;     // [n_items] exclusive scan of keep_units
   u32* out_ord;     // [n_items] exclusive scan of (keep_units != 0)
@@ -183,6 +189,9 @@ struct CompactJob {
   u32 out_n_buckets;
   u32 out_ord_bits;
 };
+constexpr u32 MERGE_TILE = 2048;
+// fill the per-source item segments, sort the memtable segment, merge the segments (merge path: co-ranks per tile
+// boundary, then one CTA per tile)
 void launch_compact_sort(const CompactJob* d_jobs, const CompactJob* h_jobs, u32 n_jobs, cudaStream_t s);
 void launch_compact_size(const CompactJob* d_jobs, u32 n_jobs, cudaStream_t s);
 void launch_compact_write(const CompactJob* d_jobs, u32 n_jobs, u32 max_items, cudaStream_t s);

@@ -1,4 +1,4 @@
-// stager.h — double-buffered staging combiner (std only, no CUDA): many caller threads, one device batch at a time.
+// stager.h — multi-buffered staging combiner (std only, no CUDA): many caller threads, one device batch at a time.
 //
 // Why: the reference calls ApplicationDB::Get / MultiGet from up to 256 thrift worker threads
 // (rocksdb_admin/application_db.cpp:85-120, examples/counter_service/counter.cpp:39,81) and applies replicated
@@ -13,8 +13,9 @@
 //                opens for new arrivals), waits for the callers still copying, runs the batch (H2D, kernels, D2H,
 //                one synchronisation — the RunFn), fires the asynchronous completions and wakes the waiters.
 //
-// While the device works on batch k, callers fill batch k+1: batches grow with load on their own (no timer), a lone
-// caller pays two thread hand-offs and nothing else.  Requests of one caller thread stay ordered (it does not return
+// While the device works on batch k, callers fill batch k+1 and the callers of batch k-1 are still copying their results
+// out (three buffers): batches grow with load on their own (no timer), a lone caller pays two thread hand-offs and
+// nothing else.  Requests of one caller thread stay ordered (it does not return
 // before its request has run); slices of one batch are ordered by begin() order, which is what per-shard FIFO needs.
 #pragma once
 #include <condition_variable>
@@ -42,6 +43,8 @@ class Stager {
   };
   using RunFn = std::function<void(const BatchInfo&)>;
   using PostFn = std::function<void()>;  // dispatcher thread, after the asynchronous completions of a batch ran
+
+  static constexpr int kBuffers = 3;  // filling | running | results being read
 
   Stager(size_t cap_items, size_t cap_bytes, RunFn run, PostFn post = nullptr)
       : cap_items_(cap_items), cap_bytes_(cap_bytes), run_(std::move(run)), post_(std::move(post)) {
@@ -139,7 +142,7 @@ class Stager {
     }
   }
   void OpenOne() {  // mu_ held
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kBuffers; i++) {
       if (b_[i].state == FREE) {
         b_[i].state = OPEN;
         b_[i].epoch = ++epochs_;
@@ -190,7 +193,7 @@ class Stager {
   PostFn post_;
   std::mutex mu_;
   std::condition_variable cv_disp_, cv_space_, cv_done_;
-  Batch b_[2];
+  Batch b_[kBuffers];
   int open_ = -1;
   uint64_t epochs_ = 0;
   bool stop_ = false;

@@ -48,11 +48,15 @@ inline std::string TaggedName(const char* name, const std::string& db_name) {
   }
   return name;
 }
+inline bool Tagging() { return StatFlags().replicator_enable_per_db_stats || StatFlags().replicator_enable_per_dataset_stats; }
+// the names above are static strings: without per-db tagging a report is a thread-local table hit by pointer
 inline void incCounter(const char* name, uint64_t value, const std::string& db_name) {
-  common::Stats::get()->Incr(TaggedName(name, db_name), value);
+  if (!Tagging()) common::Stats::get()->IncrStatic(name, value);
+  else common::Stats::get()->Incr(TaggedName(name, db_name), value);
 }
 inline void logMetric(const char* name, int64_t value, const std::string& db_name) {
-  common::Stats::get()->AddMetric(TaggedName(name, db_name), value);
+  if (!Tagging()) common::Stats::get()->AddMetricStatic(name, value);
+  else common::Stats::get()->AddMetric(TaggedName(name, db_name), value);
 }
 
 }  // namespace replicator

@@ -130,7 +130,7 @@ static void test_write_batch_and_status() {
 // device batches; a dispatcher runs one batch after the other (csrc/stager.h)
 static void test_stager() {
   constexpr size_t CAP = 256;
-  static int in_buf[2][CAP], out_buf[2][CAP];
+  static int in_buf[rsp::Stager::kBuffers][CAP], out_buf[rsp::Stager::kBuffers][CAP];
   std::atomic<int> executed{0}, async_done{0}, posts{0};
   std::atomic<bool> classes_ok{true};
   rsp::Stager st(CAP, CAP * 4, [&](const rsp::Stager::BatchInfo& b) {
