@@ -229,6 +229,8 @@ struct rsp_staged {
   size_t res_bytes = 0;         // gres + per-batch status words, contiguous
   std::vector<u32> group_first;  // staged position of each group's first batch (+ total at the end)
   bool identity_order = false;   // packed ticks: staged position == caller's batch index
+  bool fused = false;            // small batches: the whole tick is one launch of k_tick_fused
+  FusedTick ftick{};
   mutable bool reserved = false; // its upper bounds are counted in the shards' in-flight totals until the results are folded
 };
 
@@ -267,6 +269,7 @@ struct rsp_engine {
   // MultiGet kernel walks a shard's runs newest first when some shard has more than one (n_multirun counts them)
   ShardFast* d_fast_runs = nullptr;
   std::atomic<u32> n_multirun{0};
+  bool fused_ticks = true;  // RSP_FUSED_TICK=0: always the four general kernels (k_decode .. k_publish)
   u32 mg_parity = 0;
   size_t pending_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -623,7 +626,10 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
   }
   if (ops_cap > 0xfff00000ull) return RSP_INVALID_ARGUMENT;
   const size_t blob_bytes = boff + 64;  // slack for the insert kernel's aligned word reads
-  const size_t desc_b = align_up(n * sizeof(BatchDesc) + ng * sizeof(GroupDesc), 256);
+  // [BatchDesc x n][GroupDesc x g][u64 off x n][u32 len x n] | blob : the last two feed the fused tick kernel
+  const size_t o_foff = align_up(n * sizeof(BatchDesc) + ng * sizeof(GroupDesc), 16);
+  const size_t o_flen = o_foff + n * 8;
+  const size_t desc_b = align_up(o_flen + n * 4, 256);
   const size_t in_b = desc_b + blob_bytes;
   u8* pin = (u8*)e->pin_in.get(in_b);
   BatchDesc* bd = (BatchDesc*)pin;
@@ -657,6 +663,8 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
       const u32 g = g_of[i];
       b.shard_ix = gd[g].shard_ix; b.boff = p_boff[pos]; b.len = (u32)len_eff;
       b.op_base = p_opbase[pos]; b.op_cap = p_cap[pos]; b.group = g; b.raw_len = (u32)len_eff; b.pad1 = 0;
+      reinterpret_cast<u64*>(pin + o_foff)[pos] = p_boff[pos];
+      reinterpret_cast<u32*>(pin + o_flen)[pos] = (u32)len_eff;
     }
   };
   const size_t n_workers = n >= 16384 ? std::min<size_t>(e->stage_threads, 8) : 1;
@@ -698,6 +706,17 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
   t.n_batches = (u32)n; t.n_groups = (u32)ng; t.n_ops_cap = (u32)ops_cap;
   sg->res_bytes = ng * sizeof(GroupRes) + n * 4;  // what comes back: per-shard results + one status word per batch
   sg->group_first.assign(g_start.begin(), g_start.end());
+  {
+    // one launch for the whole tick when every batch is small (a thread walks a batch there) and no group is so long
+    // that its CTA would serialise the tick
+    size_t max_len = 0, max_group = 0;
+    for (size_t i = 0; i < n; i++) max_len = std::max<size_t>(max_len, (size_t)(off[i + 1] - off[i]) + trailer);
+    for (size_t g = 0; g < ng; g++) max_group = std::max<size_t>(max_group, g_count[g]);
+    sg->fused = e->fused_ticks && max_len <= FUSED_MAX_BATCH_BYTES && (max_group <= 4096 || ng >= 64);
+    FusedTick& f = sg->ftick;
+    f.blob = t.blob; f.off = (const u64*)(dev + o_foff); f.len = (const u32*)(dev + o_flen); f.ts = nullptr;
+    f.groups = t.groups; f.bstat = t.bstat; f.gres = t.gres; f.n_groups = (u32)ng; f.n_batches = (u32)n;
+  }
   if (own_dev) CUDA_OK(cudaStreamSynchronize(e->st));  // the pinned staging buffer is reused
   return RSP_OK;
 }
@@ -749,6 +768,12 @@ static int reserve_for(rsp_engine* e, const rsp_staged* sg) {
 }
 
 static void tick_launch(rsp_engine* e, rsp_staged* sg, cudaStream_t st) {
+  if (sg->fused) {
+    launch_tick_fused(sg->ftick, e->d_shards, e->d_fast, st);
+    CUDA_OK(cudaGetLastError());
+    e->launches += 1;
+    return;
+  }
   launch_decode(sg->tick, st);
   launch_sequence(sg->tick, e->d_shards, e->d_fast, st);
   launch_insert(sg->tick, e->d_shards, st);
@@ -800,6 +825,9 @@ static int tick_results(rsp_staged* sg, const u8* pout, int32_t* st_out) {
 // timestamps go to the device as they are (four copies), k_prepare derives the descriptors there, and the
 // follower's LogData(timestamp) record is a VIRTUAL suffix the decode kernel synthesises.  Host work per batch: one
 // comparison.  Returns -1 when the input does not qualify (the general, host-staged path takes over).
+static int apply_many_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob, const uint64_t* off,
+                             const uint64_t* ts_ms, int32_t* st_out, bool allow_packed = true);
+
 static int apply_many_packed(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob, const uint64_t* off,
                              const uint64_t* ts_ms, int32_t* st_out) {
   if (n < 1024 || off[0] != 0 || off[n] > 0xe0000000ull) return -1;
@@ -812,6 +840,7 @@ static int apply_many_packed(rsp_engine* e, size_t n, const uint32_t* shard_ix, 
   std::vector<u8>& seen = e->seen_scratch;
   if (seen.size() < e->slots.size()) seen.assign(e->slots.size(), 0);
   bool ok = true;
+  size_t max_len = 0, max_group = 0;
   for (size_t i = 0; i < n; i++) {
     const u32 six = shard_ix[i];
     if (groups.empty() || six != groups.back().shard_ix) {
@@ -821,73 +850,131 @@ static int apply_many_packed(rsp_engine* e, size_t n, const uint32_t* shard_ix, 
       sg.group_shard.push_back(e->slots[six]);
     }
     groups.back().n_batches++;
+    max_len = std::max<size_t>(max_len, (size_t)(off[i + 1] - off[i]));
   }
-  for (const GroupDesc& g : groups) seen[g.shard_ix] = 0;
+  for (const GroupDesc& g : groups) { seen[g.shard_ix] = 0; max_group = std::max<size_t>(max_group, g.n_batches); }
   if (!ok) return -1;
   const size_t ng = groups.size();
+  const size_t trailer = ts_ms ? 10 : 0;
   sg.group_first.resize(ng + 1);
   for (size_t g = 0; g < ng; g++) sg.group_first[g] = groups[g].first_batch;
   sg.group_first[ng] = (u32)n;
   const size_t blob_b = (size_t)off[n];
+  const bool fused = e->fused_ticks && max_len + trailer <= FUSED_MAX_BATCH_BYTES && (max_group <= 4096 || ng >= 64);
   // device image: [groups][off][ts][need | total][BatchDesc][blob + slack][BatchRes][GroupRes | status]
+  // (the fused tick needs neither the descriptors nor the per-batch results: those regions are empty then)
   const size_t o_groups = 0, o_off = align_up(ng * sizeof(GroupDesc), 256), o_ts = o_off + align_up((n + 1) * 8, 256);
   const size_t o_need = o_ts + align_up(n * 8, 256), o_desc = o_need + align_up((2 * ng + 1) * 4, 256);
-  const size_t o_blob = o_desc + align_up(n * sizeof(BatchDesc), 256), o_bres = o_blob + align_up(blob_b + 64, 256);
-  const size_t o_out = o_bres + align_up(n * sizeof(BatchRes), 256);
+  const size_t o_blob = o_desc + (fused ? 0 : align_up(n * sizeof(BatchDesc), 256)), o_bres = o_blob + align_up(blob_b + 64, 256);
+  const size_t o_out = o_bres + (fused ? 0 : align_up(n * sizeof(BatchRes), 256));
   const size_t total = o_out + align_up(ng * sizeof(GroupRes) + n * 4, 256);
+  sg.res_bytes = ng * sizeof(GroupRes) + n * 4;
+  sg.need_units.resize(ng);
+  sg.need_ents.resize(ng);
+  if (fused) {
+    // No sizing round trip: the memtable room is reserved from an ESTIMATE (bytes / 16 units of payload plus two
+    // header units per expected entry); the kernel's own capacity guard refuses what does not fit after all (status
+    // Busy, unlatched) and those batches are retried below through the general path, which reserves exact bounds.
+    for (size_t g = 0; g < ng; g++) {
+      const size_t first = groups[g].first_batch, nb = groups[g].n_batches;
+      const u64 bytes = off[first + nb] - off[first] + nb * trailer;
+      const u64 ents = nb + bytes / 256;
+      sg.need_ents[g] = (u32)ents;
+      sg.need_units[g] = (u32)(bytes / 16 + 2 * ents + 1);
+    }
+    if (reserve_for(e, &sg) < 0) {
+      if (st_out) for (size_t i = 0; i < n; i++) st_out[i] = RSP_BUSY;
+      return RSP_BUSY;
+    }
+  }
   u8* dev = (u8*)e->dev_tick.get(total);
   CUDA_OK(cudaMemcpyAsync(dev + o_groups, groups.data(), ng * sizeof(GroupDesc), cudaMemcpyHostToDevice, e->st));
   CUDA_OK(cudaMemcpyAsync(dev + o_off, off, (n + 1) * 8, cudaMemcpyHostToDevice, e->st));
   if (ts_ms) CUDA_OK(cudaMemcpyAsync(dev + o_ts, ts_ms, n * 8, cudaMemcpyHostToDevice, e->st));
   CUDA_OK(cudaMemcpyAsync(dev + o_blob, blob, blob_b, cudaMemcpyHostToDevice, e->st));
   CUDA_OK(cudaMemsetAsync(dev + o_blob + blob_b, 0, 64, e->st));
-  CUDA_OK(cudaMemsetAsync(dev + o_need, 0, (2 * ng + 1) * 4, e->st));
-  PrepareArgs pa;
-  pa.blob = dev + o_blob; pa.off = (const u64*)(dev + o_off); pa.ts = ts_ms ? (const u64*)(dev + o_ts) : nullptr;
-  pa.groups = (const GroupDesc*)(dev + o_groups); pa.n_groups = (u32)ng; pa.n_batches = (u32)n;
-  pa.batches = (BatchDesc*)(dev + o_desc); pa.need = (u32*)(dev + o_need); pa.total_ops = (u32*)(dev + o_need) + 2 * ng;
-  launch_prepare(pa, e->st);
-  e->launches++;
   u32* pneed = (u32*)e->pin_out.get((2 * ng + 1) * 4 + ng * sizeof(GroupRes) + n * 4 + 256);
-  CUDA_OK(cudaMemcpyAsync(pneed, dev + o_need, (2 * ng + 1) * 4, cudaMemcpyDeviceToHost, e->st));
-  CUDA_OK(cudaStreamSynchronize(e->st));
-  const double t1 = now_us();
-  sg.need_units.resize(ng);
-  sg.need_ents.resize(ng);
-  for (size_t g = 0; g < ng; g++) { sg.need_units[g] = pneed[2 * g]; sg.need_ents[g] = pneed[2 * g + 1]; }
-  const u32 total_ops = pneed[2 * ng];
-  if (reserve_for(e, &sg) < 0) {
-    // pre-staged ticks are still in flight on these shards and the memtable is full: the caller folds them first
-    if (st_out) for (size_t i = 0; i < n; i++) st_out[i] = RSP_BUSY;
-    return RSP_BUSY;
+  u8* pout = (u8*)pneed + align_up((2 * ng + 1) * 4, 16);
+  double t1 = now_us();
+  if (fused) {
+    sg.fused = true;
+    FusedTick& f = sg.ftick;
+    f.blob = dev + o_blob; f.off = (const u64*)(dev + o_off); f.len = nullptr; f.ts = ts_ms ? (const u64*)(dev + o_ts) : nullptr;
+    f.groups = (const GroupDesc*)(dev + o_groups); f.gres = (GroupRes*)(dev + o_out);
+    f.bstat = (u32*)(dev + o_out + ng * sizeof(GroupRes)); f.n_groups = (u32)ng; f.n_batches = (u32)n;
+    sg.tick.gres = f.gres;
+  } else {
+    CUDA_OK(cudaMemsetAsync(dev + o_need, 0, (2 * ng + 1) * 4, e->st));
+    PrepareArgs pa;
+    pa.blob = dev + o_blob; pa.off = (const u64*)(dev + o_off); pa.ts = ts_ms ? (const u64*)(dev + o_ts) : nullptr;
+    pa.groups = (const GroupDesc*)(dev + o_groups); pa.n_groups = (u32)ng; pa.n_batches = (u32)n;
+    pa.batches = (BatchDesc*)(dev + o_desc); pa.need = (u32*)(dev + o_need); pa.total_ops = (u32*)(dev + o_need) + 2 * ng;
+    launch_prepare(pa, e->st);
+    e->launches++;
+    CUDA_OK(cudaMemcpyAsync(pneed, dev + o_need, (2 * ng + 1) * 4, cudaMemcpyDeviceToHost, e->st));
+    CUDA_OK(cudaStreamSynchronize(e->st));
+    t1 = now_us();
+    for (size_t g = 0; g < ng; g++) { sg.need_units[g] = pneed[2 * g]; sg.need_ents[g] = pneed[2 * g + 1]; }
+    const u32 total_ops = pneed[2 * ng];
+    if (reserve_for(e, &sg) < 0) {
+      // pre-staged ticks are still in flight on these shards and the memtable is full: the caller folds them first
+      if (st_out) for (size_t i = 0; i < n; i++) st_out[i] = RSP_BUSY;
+      return RSP_BUSY;
+    }
+    TickDev& t = sg.tick;
+    t.blob = dev + o_blob; t.ts = pa.ts; t.batches = pa.batches; t.groups = pa.groups;
+    t.bres = (BatchRes*)(dev + o_bres); t.gres = (GroupRes*)(dev + o_out);
+    t.bstat = (u32*)(dev + o_out + ng * sizeof(GroupRes));
+    t.ops = (OpRec*)e->dev_ops.get((size_t)std::max<u32>(total_ops, 1) * sizeof(OpRec));
+    t.n_batches = (u32)n; t.n_groups = (u32)ng; t.n_ops_cap = total_ops;
   }
-  TickDev& t = sg.tick;
-  t.blob = dev + o_blob; t.ts = pa.ts; t.batches = pa.batches; t.groups = pa.groups;
-  t.bres = (BatchRes*)(dev + o_bres); t.gres = (GroupRes*)(dev + o_out);
-  t.bstat = (u32*)(dev + o_out + ng * sizeof(GroupRes));
-  t.ops = (OpRec*)e->dev_ops.get((size_t)std::max<u32>(total_ops, 1) * sizeof(OpRec));
-  t.n_batches = (u32)n; t.n_groups = (u32)ng; t.n_ops_cap = total_ops;
-  sg.res_bytes = ng * sizeof(GroupRes) + n * 4;
   CUDA_OK(cudaEventRecord(e->ev0, e->st));
   tick_launch(e, &sg, e->st);
   CUDA_OK(cudaEventRecord(e->ev1, e->st));
-  u8* pout = (u8*)pneed + align_up((2 * ng + 1) * 4, 16);
-  CUDA_OK(cudaMemcpyAsync(pout, t.gres, sg.res_bytes, cudaMemcpyDeviceToHost, e->st));
+  CUDA_OK(cudaMemcpyAsync(pout, sg.tick.gres, sg.res_bytes, cudaMemcpyDeviceToHost, e->st));
   CUDA_OK(cudaStreamSynchronize(e->st));
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->last_ms["apply"] = ms;
   const double t2 = now_us();
-  const int worst = tick_results(&sg, pout, st_out);
-  if (g_trace) fprintf(stderr, "[rsp trace] apply_many(packed) n=%zu copy+prepare %.0f us tick+sync %.0f us (kernels %.0f us) results %.0f us\n",
-                       n, t1 - t0, t2 - t1, ms * 1e3, now_us() - t2);
+  std::vector<int32_t> st_local;
+  if (fused && !st_out) { st_local.assign(n, 0); st_out = st_local.data(); }
+  int worst = tick_results(&sg, pout, st_out);
+  if (g_trace) fprintf(stderr, "[rsp trace] apply_many(packed%s) n=%zu copy%s %.0f us tick+sync %.0f us (kernels %.0f us) results %.0f us\n",
+                       fused ? ", fused" : "", n, fused ? "" : "+prepare", t1 - t0, t2 - t1, ms * 1e3, now_us() - t2);
+  if (fused) {
+    // batches the capacity guard refused (the estimate was too small for their shard): again, in order, with exact bounds
+    std::vector<uint32_t> again;
+    for (size_t i = 0; i < n; i++)
+      if (st_out[i] == RSP_BUSY && !e->slots[shard_ix[i]]->latch) again.push_back((uint32_t)i);
+    if (!again.empty()) {
+      const size_t m = again.size();
+      std::vector<uint32_t> six(m);
+      std::vector<uint64_t> off2(m + 1, 0), ts2(m);
+      std::vector<uint8_t> blob2;
+      for (size_t k = 0; k < m; k++) {
+        const size_t i = again[k];
+        six[k] = shard_ix[i];
+        blob2.insert(blob2.end(), blob + off[i], blob + off[i + 1]);
+        off2[k + 1] = blob2.size();
+        if (ts_ms) ts2[k] = ts_ms[i];
+      }
+      blob2.push_back(0);
+      std::vector<int32_t> st2(m, 0);
+      const int rc2 = apply_many_locked(e, m, six.data(), blob2.data(), off2.data(), ts_ms ? ts2.data() : nullptr, st2.data(), false);
+      for (size_t k = 0; k < m; k++) st_out[again[k]] = st2[k];
+      worst = RSP_OK;
+      for (size_t i = 0; i < n; i++) if (st_out[i]) { worst = st_out[i]; break; }
+      if (rc2 == RSP_BUSY) worst = RSP_BUSY;
+    }
+  }
   return worst;
 }
 
 static int apply_many_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob,
-                             const uint64_t* off, const uint64_t* ts_ms, int32_t* st_out) {
+                             const uint64_t* off, const uint64_t* ts_ms, int32_t* st_out, bool allow_packed) {
   if (n == 0) return RSP_OK;
-  if (!getenv("RSP_NO_PACKED")) {
+  if (allow_packed && !getenv("RSP_NO_PACKED")) {
     const int prc = apply_many_packed(e, n, shard_ix, blob, off, ts_ms, st_out);
     if (prc >= 0) return prc;
   }
@@ -1573,6 +1660,7 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   // measured on the B200 host (128 cores): 2 staging threads 29 M applies/s, 1: 27, 8: 19 (spawn cost wins)
   e->stage_threads = 2;
   if (const char* t = getenv("RSP_STAGE_THREADS")) e->stage_threads = (size_t)std::max(1, atoi(t));
+  if (const char* t = getenv("RSP_FUSED_TICK")) e->fused_ticks = atoi(t) != 0;
   CUDA_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   for (int k = 0; k < 3; k++) {
     CUDA_OK(cudaStreamCreateWithFlags(&e->cs[k], cudaStreamNonBlocking));

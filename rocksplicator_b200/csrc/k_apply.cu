@@ -23,15 +23,17 @@ namespace rsp {
 // ------------------------------------------------------------------------------------------------
 // k_decode
 // ------------------------------------------------------------------------------------------------
+// A batch as RocksDB sees it after PutLogData(&timestamp, 8) (rocksdb_wrapper.cpp:19-20): `raw_len` bytes that are
+// physically present (in global or in shared memory: plain loads work on both) followed by the VIRTUAL record
+// {0x03, 0x08, timestamp LE} of a packed tick.
 struct Cursor {
   const u8* p;  // batch base
   u32 pos, len;
-  u32 raw_len;  // bytes present in the blob; the rest is the virtual LogData(timestamp) record
+  u32 raw_len;  // bytes present; the rest is the virtual LogData(timestamp) record
   u64 ts;
 };
-// byte `pos` of the batch as RocksDB sees it after PutLogData(&timestamp, 8): rocksdb_wrapper.cpp:19-20
 __device__ __forceinline__ u32 batch_byte(const u8* p, u32 raw_len, u64 ts, u32 pos) {
-  if (pos < raw_len) return __ldg(p + pos);
+  if (pos < raw_len) return p[pos];
   const u32 t = pos - raw_len;
   return t == 0 ? 0x03u : (t == 1 ? 0x08u : (u32)((ts >> (8u * (t - 2u))) & 0xffu));
 }
@@ -63,101 +65,111 @@ __device__ __forceinline__ bool get_slice(Cursor& c, u32& off, u32& n) {
   return true;
 }
 
-// WARP = true: 32 lanes walk the batch `warp` together (uniform control flow, lane 0 writes).  WARP = false
-// (experiment, RSP_DECODE_THREAD=1): the caller is a single thread that owns the batch (lane == 0).
-template <bool WARP>
+// WriteBatch::Iterate's record walk with RocksDB's validation and error classes.  sink(type, koff, klen, voff, vlen,
+// units_before, op_index) is called for every data record (offsets relative to the batch base); returns the batch's
+// status word (0 = well formed) and its op count / entry units.
+struct WalkResult {
+  u32 status, n_ops, units;
+};
+template <class Sink>
+__device__ __forceinline__ WalkResult walk_batch(Cursor c, Sink&& sink) {
+  u32 status = 0, found = 0, units = 0;
+  bool range_del = false;
+  if (c.len < 12) return WalkResult{mk_status(2, MSG_TOO_SMALL), 0u, 0u};
+  const u32 count = cur_byte(c, 8) | (cur_byte(c, 9) << 8) | (cur_byte(c, 10) << 16) | (cur_byte(c, 11) << 24);
+  c.pos = 12;
+  while (c.pos < c.len && status == 0) {
+    const u32 tag = cur_byte(c, c.pos);
+    c.pos++;
+    u32 cf = 0, koff = 0, klen = 0, voff = 0, vlen = 0, type = kTypeInvalid;
+    switch (tag) {
+      case kTypeColumnFamilyValue:
+        if (!get_varint32(c, cf)) { status = mk_status(2, MSG_BAD_PUT); break; }
+        /* fallthrough */
+      case kTypeValue:
+        if (!get_slice(c, koff, klen) || !get_slice(c, voff, vlen)) { status = mk_status(2, MSG_BAD_PUT); break; }
+        type = kTypeValue;
+        break;
+      case kTypeColumnFamilyDeletion:
+      case kTypeColumnFamilySingleDeletion:
+        if (!get_varint32(c, cf)) { status = mk_status(2, MSG_BAD_DELETE); break; }
+        /* fallthrough */
+      case kTypeDeletion:
+      case kTypeSingleDeletion:
+        if (!get_slice(c, koff, klen)) { status = mk_status(2, MSG_BAD_DELETE); break; }
+        type = (tag == kTypeDeletion || tag == kTypeColumnFamilyDeletion) ? kTypeDeletion : kTypeSingleDeletion;
+        break;
+      case kTypeColumnFamilyMerge:
+        if (!get_varint32(c, cf)) { status = mk_status(2, MSG_BAD_MERGE); break; }
+        /* fallthrough */
+      case kTypeMerge:
+        if (!get_slice(c, koff, klen) || !get_slice(c, voff, vlen)) { status = mk_status(2, MSG_BAD_MERGE); break; }
+        type = kTypeMerge;
+        break;
+      case kTypeLogData:
+        if (!get_slice(c, koff, klen)) status = mk_status(2, MSG_BAD_BLOB);
+        continue;  // not counted, no sequence number
+      case kTypeNoop:
+        continue;
+      // two-phase-commit markers: parsed and (outside WAL recovery) ignored by RocksDB; not counted, no sequence number
+      case kTypeBeginPrepareXID:
+        continue;
+      case kTypeEndPrepareXID:
+        if (!get_slice(c, koff, klen)) status = mk_status(2, MSG_BAD_END_PREPARE);
+        continue;
+      case kTypeCommitXID:
+        if (!get_slice(c, koff, klen)) status = mk_status(2, MSG_BAD_COMMIT);
+        continue;
+      case kTypeRollbackXID:
+        if (!get_slice(c, koff, klen)) status = mk_status(2, MSG_BAD_ROLLBACK);
+        continue;
+      // range deletions: parsed and counted with RocksDB's rules; the batch is refused (NotSupported) only if
+      // everything else about it is valid, so any other defect is reported as RocksDB reports it
+      case kTypeColumnFamilyRangeDeletion:
+        if (!get_varint32(c, cf)) { status = mk_status(2, MSG_BAD_DELETE_RANGE); break; }
+        /* fallthrough */
+      case kTypeRangeDeletion:
+        if (!get_slice(c, koff, klen) || !get_slice(c, voff, vlen)) { status = mk_status(2, MSG_BAD_DELETE_RANGE); break; }
+        if (cf != 0) { status = mk_status(4, MSG_BAD_CF); break; }
+        range_del = true;
+        found++;
+        continue;
+      default:
+        status = mk_status(2, MSG_UNKNOWN_TAG);
+        break;
+    }
+    if (status) break;
+    if (cf != 0) { status = mk_status(4, MSG_BAD_CF); break; }
+    sink(type, koff, klen, voff, vlen, units, found);
+    units += entry_units(type, klen, vlen, true);
+    found++;
+  }
+  if (status == 0 && found != count) status = mk_status(2, MSG_WRONG_COUNT);
+  if (status == 0 && range_del) status = mk_status(3, MSG_UNSUPPORTED_TAG);
+  return WalkResult{status, status ? 0u : found, status ? 0u : units};
+}
+
+// k_decode: one warp per batch, every lane walks the same records (uniform control flow; loads broadcast), lane 0
+// writes one OpRec per op
 __device__ __forceinline__ void decode_batch(const TickDev& t, const u32 warp, const u32 lane) {
   const BatchDesc bd = t.batches[warp];
   Cursor c{t.blob + bd.boff, 12, bd.len, bd.raw_len, t.ts ? __ldg(t.ts + warp) : 0ull};
-  u32 status = 0, found = 0, units = 0;
-  bool range_del = false;
-  if (bd.len < 12) {
-    status = mk_status(2, MSG_TOO_SMALL);
-  } else {
-    const u32 count = cur_byte(c, 8) | (cur_byte(c, 9) << 8) | (cur_byte(c, 10) << 16) | (cur_byte(c, 11) << 24);
-    // every lane walks the same records (uniform control flow; loads broadcast); lane 0 writes
-    while (c.pos < c.len && status == 0) {
-      const u32 tag = cur_byte(c, c.pos);
-      c.pos++;
-      u32 cf = 0, koff = 0, klen = 0, voff = 0, vlen = 0, type = kTypeInvalid;
-      switch (tag) {
-        case kTypeColumnFamilyValue:
-          if (!get_varint32(c, cf)) { status = mk_status(2, MSG_BAD_PUT); break; }
-          /* fallthrough */
-        case kTypeValue:
-          if (!get_slice(c, koff, klen) || !get_slice(c, voff, vlen)) { status = mk_status(2, MSG_BAD_PUT); break; }
-          type = kTypeValue;
-          break;
-        case kTypeColumnFamilyDeletion:
-        case kTypeColumnFamilySingleDeletion:
-          if (!get_varint32(c, cf)) { status = mk_status(2, MSG_BAD_DELETE); break; }
-          /* fallthrough */
-        case kTypeDeletion:
-        case kTypeSingleDeletion:
-          if (!get_slice(c, koff, klen)) { status = mk_status(2, MSG_BAD_DELETE); break; }
-          type = (tag == kTypeDeletion || tag == kTypeColumnFamilyDeletion) ? kTypeDeletion : kTypeSingleDeletion;
-          break;
-        case kTypeColumnFamilyMerge:
-          if (!get_varint32(c, cf)) { status = mk_status(2, MSG_BAD_MERGE); break; }
-          /* fallthrough */
-        case kTypeMerge:
-          if (!get_slice(c, koff, klen) || !get_slice(c, voff, vlen)) { status = mk_status(2, MSG_BAD_MERGE); break; }
-          type = kTypeMerge;
-          break;
-        case kTypeLogData:
-          if (!get_slice(c, koff, klen)) status = mk_status(2, MSG_BAD_BLOB);
-          continue;  // not counted, no sequence number
-        case kTypeNoop:
-          continue;
-        // two-phase-commit markers: parsed and (outside WAL recovery) ignored by RocksDB; not counted, no sequence number
-        case kTypeBeginPrepareXID:
-          continue;
-        case kTypeEndPrepareXID:
-          if (!get_slice(c, koff, klen)) status = mk_status(2, MSG_BAD_END_PREPARE);
-          continue;
-        case kTypeCommitXID:
-          if (!get_slice(c, koff, klen)) status = mk_status(2, MSG_BAD_COMMIT);
-          continue;
-        case kTypeRollbackXID:
-          if (!get_slice(c, koff, klen)) status = mk_status(2, MSG_BAD_ROLLBACK);
-          continue;
-        // range deletions: parsed and counted with RocksDB's rules; the batch is refused (NotSupported) only if
-        // everything else about it is valid, so any other defect is reported as RocksDB reports it
-        case kTypeColumnFamilyRangeDeletion:
-          if (!get_varint32(c, cf)) { status = mk_status(2, MSG_BAD_DELETE_RANGE); break; }
-          /* fallthrough */
-        case kTypeRangeDeletion:
-          if (!get_slice(c, koff, klen) || !get_slice(c, voff, vlen)) { status = mk_status(2, MSG_BAD_DELETE_RANGE); break; }
-          if (cf != 0) { status = mk_status(4, MSG_BAD_CF); break; }
-          range_del = true;
-          found++;
-          continue;
-        default:
-          status = mk_status(2, MSG_UNKNOWN_TAG);
-          break;
-      }
-      if (status) break;
-      if (cf != 0) { status = mk_status(4, MSG_BAD_CF); break; }
-      if (found < bd.op_cap && lane == 0) {
-        OpRec r;
-        r.koff = bd.boff + koff; r.klen = klen;
-        r.voff = bd.boff + voff; r.vlen = vlen;
-        r.rel_units = units; r.type = type;
-        r.batch_ix = warp; r.op_ix = found;
-        t.ops[bd.op_base + found] = r;
-      }
-      units += entry_units(type, klen, vlen, true);
-      found++;
+  const WalkResult w = walk_batch(c, [&](u32 type, u32 koff, u32 klen, u32 voff, u32 vlen, u32 units, u32 found) {
+    if (found < bd.op_cap && lane == 0) {
+      OpRec r;
+      r.koff = bd.boff + koff; r.klen = klen;
+      r.voff = bd.boff + voff; r.vlen = vlen;
+      r.rel_units = units; r.type = type;
+      r.batch_ix = warp; r.op_ix = found;
+      t.ops[bd.op_base + found] = r;
     }
-    if (status == 0 && found != count) status = mk_status(2, MSG_WRONG_COUNT);
-    if (status == 0 && range_del) status = mk_status(3, MSG_UNSUPPORTED_TAG);
-  }
+  });
   // unused / rejected reserved op slots must read as invalid for k_insert
-  const u32 first_dead = status ? 0u : min(found, bd.op_cap);
-  for (u32 i = first_dead + lane; i < bd.op_cap; i += (WARP ? 32u : 1u)) t.ops[bd.op_base + i].type = kTypeInvalid;
+  const u32 first_dead = w.status ? 0u : min(w.n_ops, bd.op_cap);
+  for (u32 i = first_dead + lane; i < bd.op_cap; i += 32u) t.ops[bd.op_base + i].type = kTypeInvalid;
   if (lane == 0) {
     BatchRes r;
-    r.status = status; r.n_ops = status ? 0u : found; r.units = status ? 0u : units;
+    r.status = w.status; r.n_ops = w.n_ops; r.units = w.units;
     r.unit_base = 0; r.seq_base = 0; r.ord_base = 0; r.accepted = 0;
     t.bres[warp] = r;
   }
@@ -167,15 +179,7 @@ __global__ void __launch_bounds__(256) k_decode(TickDev t) {
   const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 lane = threadIdx.x & 31;
   if (warp >= t.n_batches) return;
-  decode_batch<true>(t, warp, lane);
-}
-
-// EXPERIMENT (RSP_DECODE_THREAD=1, off by default): a thread per batch.  A 105-byte single-Put batch keeps 31 of the
-// 32 lanes of k_decode idle; here 32 batches share a warp (their bytes are read through L1, a line or two per batch).
-__global__ void __launch_bounds__(128) k_decode_thread(TickDev t) {
-  const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= t.n_batches) return;
-  decode_batch<false>(t, b, 0);
+  decode_batch(t, warp, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -190,10 +194,6 @@ __device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
   return v;
 }
 
-// FUSED = false is the shipped kernel (k_decode ran before it).  FUSED = true (experiment, RSP_FUSE_DECODE=1): each
-// lane decodes its own batch right here (decode_batch<false>), so the tick has one launch and one pass over the
-// per-batch results less.
-template <bool FUSED>
 __device__ __forceinline__ void sequence_body(const TickDev& t, ShardDev* shards, ShardFast* fast, const u32 warp, const u32 lane) {
   const GroupDesc g = t.groups[warp];
   ShardDev* sd = shards + g.shard_ix;
@@ -206,7 +206,6 @@ __device__ __forceinline__ void sequence_body(const TickDev& t, ShardDev* shards
     const bool in = j < g.n_batches;
     BatchRes r;
     r.status = 0; r.n_ops = 0; r.units = 0;
-    if (FUSED && in) decode_batch<false>(t, g.first_batch + j, 0);
     if (in) r = t.bres[g.first_batch + j];
     const u32 bad_mask = __ballot_sync(0xffffffffu, in && r.status != 0);
     const u32 first_bad = bad_mask ? (u32)(__ffs(bad_mask) - 1) : 32u;
@@ -272,15 +271,8 @@ __global__ void __launch_bounds__(128) k_sequence(TickDev t, ShardDev* shards, S
   const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 lane = threadIdx.x & 31;
   if (warp >= t.n_groups) return;
-  sequence_body<false>(t, shards, fast, warp, lane);
+  sequence_body(t, shards, fast, warp, lane);
 }
-__global__ void __launch_bounds__(128) k_decode_sequence(TickDev t, ShardDev* shards, ShardFast* fast) {
-  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 lane = threadIdx.x & 31;
-  if (warp >= t.n_groups) return;
-  sequence_body<true>(t, shards, fast, warp, lane);
-}
-
 // ------------------------------------------------------------------------------------------------
 // k_insert
 // ------------------------------------------------------------------------------------------------
@@ -296,10 +288,10 @@ __device__ __forceinline__ void copy_to_units(u8* dst, const u8* src, u32 n, u32
     const uintptr_t a = reinterpret_cast<uintptr_t>(s);
     const u32* w = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
     const u32 sh = (u32)(a & 3u) * 8u;
-    u32 x0 = __ldg(w), x1 = __ldg(w + 1), x2 = __ldg(w + 2), x3 = __ldg(w + 3);
+    u32 x0 = w[0], x1 = w[1], x2 = w[2], x3 = w[3];  // plain loads: the source may be global or shared memory
     uint4 o;
     if (sh) {
-      u32 x4 = __ldg(w + 4);
+      u32 x4 = w[4];
       o.x = __funnelshift_r(x0, x1, sh);
       o.y = __funnelshift_r(x1, x2, sh);
       o.z = __funnelshift_r(x2, x3, sh);
@@ -440,6 +432,188 @@ __global__ void __launch_bounds__(256) k_insert(TickDev t, ShardDev* shards) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_tick_fused — the whole tick in ONE launch for ticks of small batches (the replication stream: single-Put
+// WriteBatches of ~105 bytes, <= 50 per shard per pull): one CTA per shard group.
+//   stage    : the group's batch bytes — contiguous in a packed tick — are pulled into shared memory with coalesced
+//              16-byte vector loads (chunks of <= 128 batches / 32 KB)
+//   decode   : a thread per batch walks its records in shared memory (walk_batch: RocksDB's validation, error classes)
+//   sequence : block-wide — first failure latches, prefix sums assign sequence numbers / heap units / ordinals
+//   insert   : the same thread walks its batch again and writes each entry (shared -> heap, 16-byte units), then links
+//              it into the shard's table; per-batch results never leave the SM
+//   publish  : when every insert of the group is done
+// Against k_decode -> k_sequence -> k_insert -> k_publish this drops three launches and all the per-batch / per-op
+// records in global memory (BatchDesc, BatchRes, OpRec: ~350 bytes of traffic per 105-byte batch).
+// ------------------------------------------------------------------------------------------------
+constexpr u32 FT_THREADS = 128;
+constexpr u32 FT_STAGE = 32768;  // bytes of batches staged per chunk
+
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32* s_warp, u32* total) {
+  const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const u32 incl = warp_incl_scan(v, lane);
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  u32 base = 0, tot = 0;
+#pragma unroll
+  for (u32 w = 0; w < FT_THREADS / 32; w++) {
+    const u32 x = s_warp[w];
+    if (w < wid) base += x;
+    tot += x;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + incl - v;
+}
+
+__global__ void __launch_bounds__(FT_THREADS) k_tick_fused(FusedTick t, ShardDev* shards, ShardFast* fast) {
+  __shared__ __align__(16) u8 s_blob[FT_STAGE + 64];
+  __shared__ u32 s_warp[FT_THREADS / 32];
+  __shared__ u32 s_first_bad, s_first_over, s_first_status, s_tot_ops, s_tot_units;
+  const u32 tid = threadIdx.x;
+  const GroupDesc g = t.groups[blockIdx.x];
+  ShardDev* sd = shards + g.shard_ix;
+  // group state, identical in every thread
+  u32 latch = sd->latch;
+  u64 seq = sd->last_seq;
+  u32 tail = sd->mt_tail, cnt = sd->mt_count;
+  const u32 heap_cap = sd->mt_heap_cap, ent_cap = sd->mt_ent_cap;
+  u8* heap = sd->mt_heap;
+  const u32 trailer = t.ts ? 10u : 0u;
+  bool stop = false;  // the memtable is full: the rest of the group is refused (busy), unlatched
+  for (u32 c0 = 0; c0 < g.n_batches;) {
+    const u32 b0 = g.first_batch + c0;
+    const u64 base = __ldg(t.off + b0);
+    // ---- chunk extent: as many of the next FT_THREADS batches as fit the stage
+    const u32 j = c0 + tid;
+    u64 my_off = 0, my_end = 0;
+    bool fits = false;
+    if (j < g.n_batches) {
+      my_off = __ldg(t.off + b0 + tid);
+      my_end = t.len ? my_off + __ldg(t.len + b0 + tid) : __ldg(t.off + b0 + tid + 1);
+      fits = my_end - base <= FT_STAGE;
+    }
+    const u32 n_in = (u32)__syncthreads_count(fits);  // offsets grow: the fitting batches are a prefix
+    if (tid == 0) { s_first_bad = 0xffffffffu; s_first_over = 0xffffffffu; s_first_status = 0; }
+    if (n_in == 0) {
+      // a batch larger than the stage (the host routes such ticks to the general kernels; kept as a guard)
+      if (tid == 0) t.bstat[b0] = latch ? latch : mk_status(11, MSG_TOO_LARGE);
+      __syncthreads();
+      c0 += 1;
+      continue;
+    }
+    // (staged images pad every batch to 16 bytes: the last batch's own end bounds the chunk)
+    const u32 chunk_bytes = (u32)((t.len ? __ldg(t.off + b0 + n_in - 1) + __ldg(t.len + b0 + n_in - 1) : __ldg(t.off + b0 + n_in)) - base);
+    // ---- stage (aligned 16-byte loads; `shift` leading bytes belong to the previous batch / group)
+    const u8* src = t.blob + base;
+    const u32 shift = (u32)(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint4* src4 = reinterpret_cast<const uint4*>(src - shift);
+    const u32 n_units = (shift + chunk_bytes + 15u) >> 4;
+    for (u32 u = tid; u < n_units; u += FT_THREADS) reinterpret_cast<uint4*>(s_blob)[u] = __ldg(src4 + u);
+    __syncthreads();
+    // ---- decode (count pass)
+    const bool in = tid < n_in;
+    Cursor c{s_blob + shift + (u32)(my_off - base), 12, (u32)(my_end - my_off) + trailer, (u32)(my_end - my_off),
+             (in && t.ts) ? __ldg(t.ts + b0 + tid) : 0ull};
+    WalkResult w{0u, 0u, 0u};
+    if (in) w = walk_batch(c, [](u32, u32, u32, u32, u32, u32, u32) {});
+    if (in && w.status) atomicMin(&s_first_bad, tid);
+    __syncthreads();
+    const u32 first_bad = s_first_bad;
+    if (in && tid == first_bad) s_first_status = w.status;
+    const bool stopped = stop;
+    bool accepted = in && latch == 0 && !stopped && tid < first_bad;
+    u32 tot_ops, tot_units;
+    const u32 ops_excl = block_excl_scan(accepted ? w.n_ops : 0u, s_warp, &tot_ops);
+    const u32 units_excl = block_excl_scan(accepted ? w.units : 0u, s_warp, &tot_units);
+    // defensive capacity guard (the host reserves from an estimate): the first batch that does not fit and everything
+    // after it is refused, unlatched
+    const bool over = accepted && ((u64)tail + units_excl + w.units > heap_cap || (u64)cnt + ops_excl + w.n_ops > ent_cap);
+    if (over) atomicMin(&s_first_over, tid);
+    __syncthreads();
+    const u32 first_over = s_first_over, first_status = s_first_status;
+    if (tid >= first_over) accepted = false;
+    if (first_over != 0xffffffffu) {  // totals of the accepted prefix only: the exclusive sums at the first refused batch
+      if (tid == first_over) { s_tot_ops = ops_excl; s_tot_units = units_excl; }
+      __syncthreads();
+      tot_ops = s_tot_ops;
+      tot_units = s_tot_units;
+    }
+    if (in) {
+      u32 st_out = 0;
+      if (!accepted) {
+        if (latch) st_out = latch;
+        else if (stopped || tid >= first_over) st_out = mk_status(11, MSG_TOO_LARGE);
+        else if (tid > first_bad) st_out = first_status;  // the latch set by an earlier batch of this tick
+        else st_out = w.status;
+      }
+      t.bstat[b0 + tid] = st_out;
+    }
+    // ---- insert: the batch's thread walks it again and writes / links each entry
+    if (accepted && w.n_ops) {
+      const u64 seq_base = seq + 1 + ops_excl;
+      const u32 unit_base = tail + units_excl, ord_base = cnt + ops_excl;
+      const u8* bp = c.p;
+      const u32 raw_len = c.raw_len;
+      const u64 ts = c.ts;
+      walk_batch(c, [&](u32 type, u32 koff, u32 klen, u32 voff, u32 vlen, u32 units_before, u32 op_ix) {
+        const u32 unit = unit_base + units_before;
+        u8* ent = heap + (u64)unit * 16u;
+        u8* kdst = ent + 32u;
+        u8* vdst = kdst + 16u * units_of(klen);
+        u64 h;
+        if (koff + klen <= raw_len && voff + vlen <= raw_len) {
+          h = hash_key(bp + koff, klen);
+          copy_to_units(kdst, bp + koff, klen, 0, 1);
+          copy_to_units(vdst, bp + voff, vlen, 0, 1);
+        } else {
+          // a record that reaches into the virtual LogData bytes (a truncated batch that still parses): byte by byte
+          const u32 kpad = units_of(klen) * 16u, vpad = units_of(vlen) * 16u;
+          for (u32 b = 0; b < kpad; b++) kdst[b] = b < klen ? (u8)batch_byte(bp, raw_len, ts, koff + b) : (u8)0;
+          for (u32 b = 0; b < vpad; b++) vdst[b] = b < vlen ? (u8)batch_byte(bp, raw_len, ts, voff + b) : (u8)0;
+          __threadfence();
+          u64 hh = hash_init(klen);
+          for (u32 i = 0; i < ((klen + 7u) >> 3); i++) hh = hash_step(hh, ld_cg_u64(reinterpret_cast<const u64*>(kdst) + i));
+          h = hash_final(hh);
+        }
+        const u64 st = ((seq_base + op_ix) << 8) | type;
+        *reinterpret_cast<uint4*>(ent) = make_uint4((u32)st, (u32)(st >> 32), klen, vlen);
+        *reinterpret_cast<uint4*>(ent + 16) = make_uint4(0u, 0u, (u32)h, (u32)(h >> 32));
+        sd->mt_ent_off[ord_base + op_ix] = unit;
+        __threadfence();  // the entry is complete before any pointer to it is published
+        link_into_table(sd, heap, ent, unit, klen, h);
+      });
+    }
+    // ---- group state after this chunk (uniform)
+    seq += tot_ops;
+    tail += tot_units;
+    cnt += tot_ops;
+    const u32 lim = min(n_in, first_over);
+    if (latch == 0 && !stopped && first_bad < lim) latch = first_status;
+    if (first_over != 0xffffffffu && latch == 0) stop = true;
+    c0 += n_in;
+    __syncthreads();  // s_blob and the chunk scalars are reused
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    sd->last_seq = seq;
+    sd->mt_tail = tail;
+    sd->mt_count = cnt;
+    fast[g.shard_ix].mt_count = cnt;
+    sd->latch = latch;
+    GroupRes gr;
+    gr.last_seq = seq; gr.tail = tail; gr.count = cnt; gr.latch = latch; gr.pad = 0;
+    t.gres[blockIdx.x] = gr;
+    __threadfence();
+    sd->pub_seq = seq;  // every insert of the group is done: readers may see the new versions
+  }
+}
+
+void launch_tick_fused(const FusedTick& t, ShardDev* shards, ShardFast* fast, cudaStream_t s) {
+  if (!t.n_groups) return;
+  k_tick_fused<<<t.n_groups, FT_THREADS, 0, s>>>(t, shards, fast);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_prepare — packed ticks: BatchDesc straight from the caller's arrays (no host re-layout of the blob)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_prepare(PrepareArgs a) {
@@ -483,27 +657,13 @@ __global__ void k_publish(TickDev t, ShardDev* shards) {
   sd->pub_seq = sd->last_seq;
 }
 
-static bool fuse_decode() {
-  static const bool on = getenv("RSP_FUSE_DECODE") != nullptr && atoi(getenv("RSP_FUSE_DECODE")) != 0;
-  return on;
-}
 void launch_decode(const TickDev& t, cudaStream_t s) {
   if (!t.n_batches) return;
-  if (fuse_decode()) return;  // experiment: decoded inside k_decode_sequence
-  static const bool per_thread = getenv("RSP_DECODE_THREAD") != nullptr && atoi(getenv("RSP_DECODE_THREAD")) != 0;
-  if (per_thread) {
-    k_decode_thread<<<(t.n_batches + 127) / 128, 128, 0, s>>>(t);
-    return;
-  }
   const u32 warps_per_block = 8;
   k_decode<<<(t.n_batches + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(t);
 }
 void launch_sequence(const TickDev& t, ShardDev* shards, ShardFast* fast, cudaStream_t s) {
   if (!t.n_groups) return;
-  if (fuse_decode()) {
-    k_decode_sequence<<<(t.n_groups + 3) / 4, 128, 0, s>>>(t, shards, fast);
-    return;
-  }
   k_sequence<<<(t.n_groups + 3) / 4, 128, 0, s>>>(t, shards, fast);
 }
 void launch_insert(const TickDev& t, ShardDev* shards, cudaStream_t s) {

@@ -74,6 +74,23 @@ struct PrepareArgs {
   u32* total_ops;       // out [1]
 };
 void launch_prepare(const PrepareArgs& a, cudaStream_t s);
+
+// the whole tick in one launch (ticks of small batches): batch i of group g is blob[off[i] .. off[i] + len[i]) (len ==
+// nullptr: the batches are contiguous, length off[i+1] - off[i]); ts != nullptr: the follower's LogData(timestamp)
+// record is a virtual suffix of every batch
+struct FusedTick {
+  const u8* blob;
+  const u64* off;
+  const u32* len;
+  const u64* ts;
+  const GroupDesc* groups;
+  u32* bstat;     // [n_batches] final status word
+  GroupRes* gres; // [n_groups]
+  u32 n_groups;
+  u32 n_batches;
+};
+constexpr u32 FUSED_MAX_BATCH_BYTES = 16384;  // larger batches take the general kernels (one thread walks a batch here)
+void launch_tick_fused(const FusedTick& t, ShardDev* shards, ShardFast* fast, cudaStream_t s);
 void launch_decode(const TickDev& t, cudaStream_t s);
 void launch_sequence(const TickDev& t, ShardDev* shards, ShardFast* fast, cudaStream_t s);
 void launch_insert(const TickDev& t, ShardDev* shards, cudaStream_t s);

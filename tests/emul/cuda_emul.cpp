@@ -222,6 +222,7 @@ struct emul_event { std::chrono::steady_clock::time_point t; };
 
 // RSP_EMUL_DEVICES=<n>: pretend n devices (memory is malloc-backed, so they are interchangeable) — lets the
 // several-engines-in-one-process paths (router) run on the CPU
+int emul_sync_acc = 0;
 static int emul_n_devices() { const char* e = getenv("RSP_EMUL_DEVICES"); const int n = e ? atoi(e) : 1; return n > 0 ? n : 1; }
 static thread_local int g_cur_device = 0;
 cudaError_t cudaGetDeviceCount(int* n) { *n = emul_n_devices(); return cudaSuccess; }

@@ -115,6 +115,16 @@ static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mas
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emul_collective(EMUL_SYNCWARP, mask, 0, 0); }
 static inline void __syncthreads() { emul_syncthreads(); }
+extern int emul_sync_acc;  // one block at a time, fibers are cooperative: a plain accumulator between barriers
+static inline int __syncthreads_count(int pred) {
+  emul_sync_acc += pred ? 1 : 0;
+  emul_syncthreads();
+  const int v = emul_sync_acc;
+  emul_syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) emul_sync_acc = 0;
+  emul_syncthreads();
+  return v;
+}
 static inline void __threadfence() {}
 
 // ---- loads, atomics, bit tricks -----------------------------------------------------------------------------------
