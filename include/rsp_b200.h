@@ -162,6 +162,26 @@ int rsp_multi_get_slices(rsp_shard* s, size_t n, const rsp_slice* keys, size_t v
 int rsp_multi_get_fixed(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys,
                         uint32_t klen, uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st);
 
+/* ---- one process, several GPUs: the router --------------------------------------------------------------------
+ * Shards partition shard_id -> GPU (one engine per device, no collective: nothing is exchanged between shards).  The
+ * reference's router hashes a key to its shard and fans a request out to the hosts that own the shards
+ * (examples/counter_service/counter_router.cpp:36-66); inside one box the same fan-out goes to the engines: a
+ * cross-shard batch is bucketed by engine on the host (order within a shard preserved), every engine runs its part
+ * concurrently on its own device, and the results are scattered back to the caller's order.
+ * Shards are addressed by the id they were registered under (rsp_router_add_shard; e.g. the segment number). */
+typedef struct rsp_router rsp_router;
+int rsp_router_create(size_t n_engines, rsp_engine* const* engines, rsp_router** out);
+void rsp_router_destroy(rsp_router* r); /* the engines and shards stay open */
+int rsp_router_add_shard(rsp_router* r, uint32_t shard_id, rsp_shard* s);
+int rsp_router_remove_shard(rsp_router* r, uint32_t shard_id);
+/* rsp_multi_get / rsp_multi_get_fixed / rsp_apply_many with router shard ids; an unknown id answers InvalidArgument */
+int rsp_router_multi_get(rsp_router* r, size_t n, const uint32_t* shard_id, const uint8_t* keys, const uint64_t* koff,
+                         uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st);
+int rsp_router_multi_get_fixed(rsp_router* r, size_t n, const uint32_t* shard_id, const uint8_t* keys, uint32_t klen,
+                               uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st);
+int rsp_router_apply_many(rsp_router* r, size_t n, const uint32_t* shard_id, const uint8_t* blob, const uint64_t* off,
+                          const uint64_t* ts_ms, int32_t* st_out);
+
 /* ---- iterator: ApplicationDB::NewIterator (application_db.cpp:78-83) + rocksdb::Iterator ------- */
 rsp_iter* rsp_iter_create(rsp_shard* s);
 void rsp_iter_destroy(rsp_iter* it);

@@ -2018,6 +2018,153 @@ int rsp_get(rsp_shard* s, const uint8_t* key, size_t klen, uint8_t* val, size_t 
   return st;
 }
 
+
+// ---- router: one process, several engines (include/rsp_b200.h) ------------------------------------------------
+struct rsp_router {
+  std::vector<rsp_engine*> engines;
+  std::mutex mu;  // the shard table
+  std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> where;  // router id -> (engine ordinal, shard index there)
+};
+
+int rsp_router_create(size_t n_engines, rsp_engine* const* engines, rsp_router** out) {
+  if (!n_engines || !engines || !out) return RSP_INVALID_ARGUMENT;
+  rsp_router* r = new rsp_router();
+  r->engines.assign(engines, engines + n_engines);
+  *out = r;
+  return RSP_OK;
+}
+void rsp_router_destroy(rsp_router* r) { delete r; }
+int rsp_router_add_shard(rsp_router* r, uint32_t shard_id, rsp_shard* s) {
+  if (!r || !s) return RSP_INVALID_ARGUMENT;
+  for (size_t k = 0; k < r->engines.size(); k++) {
+    if (r->engines[k] != s->eng) continue;
+    std::lock_guard<std::mutex> g(r->mu);
+    if (r->where.count(shard_id)) return RSP_INVALID_ARGUMENT;
+    r->where[shard_id] = {(uint32_t)k, s->index};
+    return RSP_OK;
+  }
+  return RSP_INVALID_ARGUMENT;  // the shard lives on an engine the router does not know
+}
+int rsp_router_remove_shard(rsp_router* r, uint32_t shard_id) {
+  if (!r) return RSP_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(r->mu);
+  return r->where.erase(shard_id) ? RSP_OK : RSP_NOT_FOUND;
+}
+
+extern "C++" {
+namespace {
+// requests bucketed by engine, caller order kept inside a bucket
+struct Buckets {
+  std::vector<std::vector<uint32_t>> idx;    // [engine] -> caller indices
+  std::vector<std::vector<uint32_t>> local;  // [engine] -> shard index on that engine
+  std::vector<uint32_t> unknown;             // caller indices with an unregistered shard id
+};
+Buckets bucket_by_engine(rsp_router* r, size_t n, const uint32_t* shard_id) {
+  Buckets b;
+  b.idx.resize(r->engines.size());
+  b.local.resize(r->engines.size());
+  std::lock_guard<std::mutex> g(r->mu);
+  uint32_t last_id = 0;
+  const std::pair<uint32_t, uint32_t>* last = nullptr;
+  for (size_t i = 0; i < n; i++) {
+    if (!last || shard_id[i] != last_id) {  // batches come grouped by shard more often than not
+      auto it = r->where.find(shard_id[i]);
+      last = it == r->where.end() ? nullptr : &it->second;
+      last_id = shard_id[i];
+    }
+    if (!last) { b.unknown.push_back((uint32_t)i); continue; }
+    b.idx[last->first].push_back((uint32_t)i);
+    b.local[last->first].push_back(last->second);
+  }
+  return b;
+}
+// run fn(k) for every engine with work, concurrently (each call drives its own device and synchronises it)
+template <class F> void for_each_engine(const Buckets& b, F fn) {
+  std::vector<std::thread> th;
+  int first = -1;
+  for (size_t k = 0; k < b.idx.size(); k++) {
+    if (b.idx[k].empty()) continue;
+    if (first < 0) { first = (int)k; continue; }
+    th.emplace_back(fn, k);
+  }
+  if (first >= 0) fn((size_t)first);  // one engine's part on the calling thread
+  for (auto& t : th) t.join();
+}
+}  // namespace
+
+static int router_multi_get(rsp_router* r, size_t n, const uint32_t* shard_id, const uint8_t* keys, const uint64_t* koff,
+                            uint32_t klen_fixed, uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
+  if (n == 0) return RSP_OK;
+  const Buckets b = bucket_by_engine(r, n, shard_id);
+  for (uint32_t i : b.unknown) { st[i] = RSP_INVALID_ARGUMENT; vlen[i] = 0; }
+  std::atomic<int> worst{RSP_OK};
+  for_each_engine(b, [&](size_t k) {
+    const std::vector<uint32_t>& ix = b.idx[k];
+    const size_t m = ix.size();
+    // gather this engine's keys, run, scatter
+    std::vector<uint64_t> off;
+    std::vector<uint8_t> kb;
+    if (klen_fixed) {
+      kb.resize(m * (size_t)klen_fixed + 16);
+      for (size_t j = 0; j < m; j++) memcpy(&kb[j * (size_t)klen_fixed], keys + (size_t)ix[j] * klen_fixed, klen_fixed);
+    } else {
+      off.assign(m + 1, 0);
+      for (size_t j = 0; j < m; j++) off[j + 1] = off[j] + (koff[ix[j] + 1] - koff[ix[j]]);
+      kb.resize((size_t)off[m] + 16);
+      for (size_t j = 0; j < m; j++) memcpy(&kb[off[j]], keys + koff[ix[j]], (size_t)(off[j + 1] - off[j]));
+    }
+    std::vector<uint8_t> v(m * val_stride + 1);
+    std::vector<uint32_t> vl(m);
+    std::vector<int32_t> s(m);
+    const int rc = multi_get_any(r->engines[k], m, b.local[k].data(), kb.data(), klen_fixed ? nullptr : off.data(), klen_fixed,
+                                 v.data(), val_stride, vl.data(), s.data());
+    if (rc != RSP_OK) worst = rc;
+    for (size_t j = 0; j < m; j++) {
+      st[ix[j]] = rc == RSP_OK ? s[j] : rc;
+      vlen[ix[j]] = vl[j];
+      if (rc == RSP_OK && s[j] == RSP_OK && vl[j]) memcpy(vals + (size_t)ix[j] * val_stride, &v[j * val_stride], std::min<size_t>(vl[j], val_stride));
+    }
+  });
+  return worst.load();
+}
+}  // extern "C++"
+
+int rsp_router_multi_get(rsp_router* r, size_t n, const uint32_t* shard_id, const uint8_t* keys, const uint64_t* koff,
+                         uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
+  if (!r || (n && (!shard_id || !koff || !vlen || !st))) return RSP_INVALID_ARGUMENT;
+  return router_multi_get(r, n, shard_id, keys, koff, 0, vals, val_stride, vlen, st);
+}
+int rsp_router_multi_get_fixed(rsp_router* r, size_t n, const uint32_t* shard_id, const uint8_t* keys, uint32_t klen,
+                               uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
+  if (!r || !klen || (n && (!shard_id || !keys || !vlen || !st))) return RSP_INVALID_ARGUMENT;
+  return router_multi_get(r, n, shard_id, keys, nullptr, klen, vals, val_stride, vlen, st);
+}
+
+int rsp_router_apply_many(rsp_router* r, size_t n, const uint32_t* shard_id, const uint8_t* blob, const uint64_t* off,
+                          const uint64_t* ts_ms, int32_t* st_out) {
+  if (!r || (n && (!shard_id || !off))) return RSP_INVALID_ARGUMENT;
+  if (n == 0) return RSP_OK;
+  const Buckets b = bucket_by_engine(r, n, shard_id);
+  if (st_out) for (uint32_t i : b.unknown) st_out[i] = RSP_INVALID_ARGUMENT;
+  std::atomic<int> worst{b.unknown.empty() ? RSP_OK : RSP_INVALID_ARGUMENT};
+  for_each_engine(b, [&](size_t k) {
+    const std::vector<uint32_t>& ix = b.idx[k];
+    const size_t m = ix.size();
+    std::vector<uint64_t> off2(m + 1, 0), ts2(ts_ms ? m : 0);
+    for (size_t j = 0; j < m; j++) off2[j + 1] = off2[j] + (off[ix[j] + 1] - off[ix[j]]);
+    std::vector<uint8_t> bb((size_t)off2[m] + 16);
+    for (size_t j = 0; j < m; j++) {
+      memcpy(&bb[off2[j]], blob + off[ix[j]], (size_t)(off2[j + 1] - off2[j]));
+      if (ts_ms) ts2[j] = ts_ms[ix[j]];
+    }
+    std::vector<int32_t> s(m, 0);
+    const int rc = rsp_apply_many(r->engines[k], m, b.local[k].data(), bb.data(), off2.data(), ts_ms ? ts2.data() : nullptr, s.data());
+    if (rc != RSP_OK) worst = rc;
+    if (st_out) for (size_t j = 0; j < m; j++) st_out[ix[j]] = s[j] ? s[j] : (rc == RSP_INVALID_ARGUMENT ? rc : 0);
+  });
+  return worst.load();
+}
+
 int rsp_flush(rsp_shard* s) {
   if (!s) return RSP_INVALID_ARGUMENT;
   rsp_engine* e = s->eng;

@@ -18,6 +18,7 @@
 // nothing else.  Requests of one caller thread stay ordered (it does not return
 // before its request has run); slices of one batch are ordered by begin() order, which is what per-shard FIFO needs.
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <cstddef>
 #include <cstdint>
@@ -88,54 +89,78 @@ class Stager {
           t->epoch = b.epoch;
           b.n_items += n_items;
           b.n_bytes += n_bytes;
-          b.copiers++;
-          b.users++;
-          if (b.n_items == n_items) cv_disp_.notify_one();  // first request of the batch: the dispatcher may take it
+          b.copiers.fetch_add(1, std::memory_order_relaxed);
+          b.users.fetch_add(1, std::memory_order_relaxed);
+          if (b.n_items == n_items && disp_sleeping_) cv_disp_.notify_one();  // first request: the dispatcher may take the batch
           return true;
         }
         // full or of another class: the dispatcher closes it as soon as it can; wait for the next open batch
-        cv_disp_.notify_one();
+        if (disp_sleeping_) cv_disp_.notify_one();
       }
       cv_space_.wait(l);
     }
   }
+  // the caller finished writing its slice.  Lock-free unless it is the last writer of a batch the dispatcher waits on.
   void commit(const Ticket& t) {
-    std::lock_guard<std::mutex> g(mu_);
-    if (--b_[t.buf].copiers == 0) cv_disp_.notify_one();
+    Batch& b = b_[t.buf];
+    if (b.copiers.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+      std::lock_guard<std::mutex> g(mu_);  // (the dispatcher checks the counter under mu_ before it sleeps)
+      if (disp_sleeping_) cv_disp_.notify_one();
+    }
   }
   // completion without a waiting thread: fn runs on the dispatcher thread once the batch has run; the slice is
   // released when fn returns (fn reads its results from the staging buffers itself)
   void commit_async(const Ticket& t, std::function<void()> fn) {
+    Batch& b = b_[t.buf];
     std::lock_guard<std::mutex> g(mu_);
-    b_[t.buf].async.push_back(std::move(fn));
-    if (--b_[t.buf].copiers == 0) cv_disp_.notify_one();
+    b.async.push_back(std::move(fn));
+    if (b.copiers.fetch_sub(1, std::memory_order_acq_rel) == 1 && disp_sleeping_) cv_disp_.notify_one();
   }
+  // until the batch has run: a short spin on the batch's completion word (hundreds of callers would otherwise convoy
+  // on one mutex just to learn that their batch is done), then a condition variable
   void wait(const Ticket& t) {
+    Batch& b = b_[t.buf];
+    for (int i = 0; i < 4000; i++) {
+      if (b.epoch_done.load(std::memory_order_acquire) >= t.epoch) return;
+      cpu_relax();
+    }
     std::unique_lock<std::mutex> l(mu_);
-    while (!(b_[t.buf].epoch_done >= t.epoch)) cv_done_.wait(l);
+    sleepers_++;
+    while (b.epoch_done.load(std::memory_order_acquire) < t.epoch) cv_done_.wait(l);
+    sleepers_--;
   }
   void release(const Ticket& t) {
-    std::lock_guard<std::mutex> g(mu_);
-    Release(b_[t.buf]);
+    Batch& b = b_[t.buf];
+    if (b.users.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+      std::lock_guard<std::mutex> g(mu_);
+      MaybeFree(b);
+    }
   }
 
-  uint64_t batches() const { return batches_; }
-  uint64_t requests() const { return requests_; }
+  uint64_t batches() const { return batches_.load(std::memory_order_relaxed); }
 
  private:
   enum State { FREE, OPEN, CLOSED, DONE };
   struct Batch {
-    State state = FREE;
-    size_t n_items = 0, n_bytes = 0, n_reqs = 0;
+    State state = FREE;                 // mu_
+    size_t n_items = 0, n_bytes = 0;    // mu_
     uint32_t klass = 0;
-    uint32_t copiers = 0;  // callers still writing their slice
-    uint32_t users = 0;    // callers (sync and async) that have not released their slice yet
-    uint64_t epoch = 0, epoch_done = 0;
-    std::vector<std::function<void()>> async;
+    uint64_t epoch = 0;
+    std::atomic<uint32_t> copiers{0};   // callers still writing their slice
+    std::atomic<uint32_t> users{0};     // callers (sync and async) that have not released their slice yet
+    std::atomic<uint64_t> epoch_done{0};
+    std::vector<std::function<void()>> async;  // mu_
   };
+  static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+  }
 
-  void Release(Batch& b) {  // mu_ held
-    if (--b.users == 0 && b.state == DONE) {
+  void MaybeFree(Batch& b) {  // mu_ held: whoever sees "done and unused" first recycles the buffer
+    if (b.state == DONE && b.users.load(std::memory_order_acquire) == 0) {
       b.state = FREE;
       b.n_items = b.n_bytes = 0;
       if (open_ < 0) OpenOne();
@@ -157,14 +182,20 @@ class Stager {
     for (;;) {
       while (!(open_ >= 0 && b_[open_].n_items > 0)) {  // a stop request still lets queued work run: callers wait on it
         if (stop_) return;
+        disp_sleeping_ = true;
         cv_disp_.wait(l);
+        disp_sleeping_ = false;
       }
       const int bi = open_;
       Batch& b = b_[bi];
       b.state = CLOSED;
       open_ = -1;
       OpenOne();
-      while (b.copiers) cv_disp_.wait(l);  // (a stop request still lets the closed batch run: callers are waiting)
+      while (b.copiers.load(std::memory_order_acquire)) {
+        disp_sleeping_ = true;
+        cv_disp_.wait(l);
+        disp_sleeping_ = false;
+      }
       BatchInfo info{bi, b.n_items, b.n_bytes, b.klass, b.epoch};
       std::vector<std::function<void()>> async;
       async.swap(b.async);
@@ -172,19 +203,13 @@ class Stager {
       run_(info);
       for (auto& f : async) f();
       if (post_) post_();
+      b.epoch_done.store(info.epoch, std::memory_order_release);  // spinning waiters go on at once
       l.lock();
       batches_++;
       b.state = DONE;
-      b.epoch_done = b.epoch;
-      const uint32_t n_async = (uint32_t)async.size();
-      cv_done_.notify_all();
-      if (n_async) {
-        b.users -= n_async - 1;
-        Release(b);
-      } else if (b.users == 0) {  // cannot happen (every slice has a user), kept for symmetry
-        b.users = 1;
-        Release(b);
-      }
+      if (sleepers_) cv_done_.notify_all();
+      if (!async.empty()) b.users.fetch_sub((uint32_t)async.size(), std::memory_order_acq_rel);
+      MaybeFree(b);
     }
   }
 
@@ -196,8 +221,9 @@ class Stager {
   Batch b_[kBuffers];
   int open_ = -1;
   uint64_t epochs_ = 0;
-  bool stop_ = false;
-  uint64_t batches_ = 0, requests_ = 0;
+  bool stop_ = false, disp_sleeping_ = false;
+  uint32_t sleepers_ = 0;
+  std::atomic<uint64_t> batches_{0};
   std::thread thread_;
 };
 

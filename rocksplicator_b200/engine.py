@@ -54,6 +54,16 @@ EXPORTS = {
     "rsp_apply_updates": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_size_t)]),
     "rsp_multi_get_slices": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "rsp_router_create": (C.c_int, [C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rsp_router_destroy": (None, [C.c_void_p]),
+    "rsp_router_add_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "rsp_router_remove_shard": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "rsp_router_multi_get": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.c_void_p, C.c_void_p]),
+    "rsp_router_multi_get_fixed": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                             C.c_size_t, C.c_void_p, C.c_void_p]),
+    "rsp_router_apply_many": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
     "rsp_latest_seq": (C.c_uint64, [C.c_void_p]),
     "rsp_last_error": (C.c_size_t, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "rsp_get": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -351,3 +361,59 @@ class Engine:
     def compact_all(self): return self.lib.rsp_compact_all(self.h)
     def last_kernel_ms(self, what): return self.lib.rsp_last_kernel_ms(self.h, what.encode())
     def kernel_launches(self): return self.lib.rsp_kernel_launches(self.h)
+
+
+class Router:
+    """Several engines (one per GPU) behind one handle: shard_id -> engine fan-out of cross-shard batches
+    (examples/counter_service/counter_router.cpp:36-66 inside one box)."""
+
+    def __init__(self, engines):
+        self.lib = load_library()
+        self.engines = list(engines)
+        arr = (C.c_void_p * len(self.engines))(*[e.h for e in self.engines])
+        h = C.c_void_p()
+        rc = self.lib.rsp_router_create(len(self.engines), arr, C.byref(h))
+        if rc != OK:
+            raise RuntimeError(f"rsp_router_create -> {rc}")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.rsp_router_destroy(self.h)
+            self.h = None
+
+    def add_shard(self, shard_id, shard):
+        rc = self.lib.rsp_router_add_shard(self.h, shard_id, shard.h)
+        if rc != OK:
+            raise RuntimeError(f"rsp_router_add_shard({shard_id}) -> {rc}")
+
+    def apply_many(self, shard_ids, batches, ts_ms=None):
+        n = len(batches)
+        ids = np.ascontiguousarray(shard_ids, dtype=np.uint32)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(np.fromiter((len(b) for b in batches), dtype=np.uint64, count=n), out=off[1:])
+        blob = np.frombuffer(b"".join(batches) + b"\0", dtype=np.uint8)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        ts = None if ts_ms is None else np.ascontiguousarray(ts_ms, dtype=np.uint64)
+        self.lib.rsp_router_apply_many(self.h, n, _ptr(ids), _ptr(blob), _ptr(off), _ptr(ts), _ptr(st))
+        return st[:n]
+
+    def multi_get(self, shard_ids, keys, stride=256):
+        n = len(keys)
+        ids = np.ascontiguousarray(shard_ids, dtype=np.uint32)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(np.fromiter((len(k) for k in keys), dtype=np.uint64, count=n), out=off[1:])
+        blob = np.frombuffer(b"".join(keys) + b"\0", dtype=np.uint8)
+        while True:
+            vals = np.zeros(max(n * stride, 1), dtype=np.uint8)
+            vlen = np.zeros(max(n, 1), dtype=np.uint32)
+            st = np.zeros(max(n, 1), dtype=np.int32)
+            rc = self.lib.rsp_router_multi_get(self.h, n, _ptr(ids), _ptr(blob), _ptr(off), _ptr(vals), stride, _ptr(vlen), _ptr(st))
+            if n and (st[:n] == INCOMPLETE).any():
+                stride = int(vlen[:n][st[:n] == INCOMPLETE].max())
+                continue
+            return [(int(st[i]), vals[i * stride:i * stride + vlen[i]].tobytes() if st[i] == OK else None) for i in range(n)], rc
+
+    def multi_get_fixed(self, shard_ids, keys, klen, vals, stride, vlen, st):
+        return self.lib.rsp_router_multi_get_fixed(self.h, len(shard_ids), _ptr(shard_ids), _ptr(keys), klen, _ptr(vals), stride,
+                                                   _ptr(vlen), _ptr(st))

@@ -45,6 +45,12 @@ def test_parity_suite_under_emulation(emul):
     assert " passed" in out and "failed" not in out
 
 
+def test_router_over_two_emulated_devices(emul):
+    """tests/test_router_gpu.py (two engines behind one router, maintenance on both) against the emulation"""
+    out = _pytest_under_emulation(emul[0], {"RSP_EMUL_DEVICES": "2"}, ["tests/test_router_gpu.py"])
+    assert "1 passed" in out
+
+
 def test_engine_vs_oracle_fuzz_under_emulation(emul):
     """tests/emul/fuzz_engine_vs_port.py on a few dozen seeds (hundreds run in minutes from the command line)"""
     env = dict(os.environ)
