@@ -157,7 +157,9 @@ def main():
     ap.add_argument("--shards", type=int, default=1024)
     ap.add_argument("--mg-batches", type=int, default=2048, help="concurrent MultiGet(4096) calls per launch")
     ap.add_argument("--tick", type=int, default=50, help="replicated updates per shard per apply tick")
-    ap.add_argument("--cpu-kv", type=int, default=2_000_000)
+    ap.add_argument("--cpu-kv", type=int, default=0, help="KV count of the CPU arm (0 = the same --kv as the GPU arm)")
+    ap.add_argument("--big-tick", type=int, default=1000, help="updates per shard in the large apply tick (0 = skip)")
+    ap.add_argument("--c5-secs", type=float, default=2.0, help="seconds of the config-5 sustained phase (0 = skip)")
     ap.add_argument("--cpu-get-secs", type=float, default=6.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-seams", action="store_true", help="skip the through-the-seams phase (librsp_host.so)")
@@ -166,6 +168,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     K, W = args.steps, max(args.warmup, 0)
+    if not args.cpu_kv:
+        args.cpu_kv = args.kv
     ncores = os.cpu_count() or 1
     workload = "%d shards x %d KV total, 16B key/64B value, uniform MultiGet batch=4096 x %d in flight, apply tick %d shards x %d single-Put WriteBatch" % (
         args.shards, args.kv, args.mg_batches, args.shards, args.tick)
@@ -284,6 +288,38 @@ def main():
     got = d_vals.cpu().numpy().reshape(Q, 64)
     assert np.array_equal(got, want), "MultiGet parity failed at full size"
 
+    # ---- config-2 variant: 10 % of the lookups ask for keys that were never written (NotFound) ------------
+    with torch.cuda.stream(stream):
+        m_idx = [rng.integers(0, NKV + NKV // 9, size=Q, dtype=np.uint64) for _ in range(3)]  # index >= NKV: absent
+        m_keys = [torch.from_numpy(synth.keys16(seed, mi).reshape(-1)).cuda() for mi in m_idx]
+        m_six = [torch.from_numpy(six_of[(mi % np.uint64(S)).astype(np.int64)].astype(np.int32)).cuda() for mi in m_idx]
+
+    def mgm(i):
+        j = i % 3
+        assert lib.rsp_multi_get_device(eng.h, Q, m_six[j].data_ptr(), m_keys[j].data_ptr(), 16, d_vals.data_ptr(), 64,
+                                        d_vlen.data_ptr(), d_st.data_ptr(), sp) == 0
+
+    for i in range(W):
+        mgm(i)
+    barrier()
+    ms0, ms1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms0.record(stream)
+    for k in range(K):
+        mgm(W + k)
+    ms1.record(stream)
+    barrier()
+    miss_ms = max_over_ranks(ms0.elapsed_time(ms1))
+    jm = (W + K - 1) % 3
+    st_m = d_st.cpu().numpy()
+    absent = m_idx[jm] >= np.uint64(NKV)
+    assert np.array_equal(st_m != 0, absent) and (st_m[absent] == 1).all(), "miss variant: status"
+    got_m0 = d_vals.cpu().numpy().reshape(Q, 64)[~absent]
+    assert np.array_equal(got_m0, synth.values(seed, (m_idx[jm][~absent] % np.uint64(S)).astype(np.int64), m_idx[jm][~absent], 0)), "miss variant: values"
+    miss_frac = float(absent.mean())
+    # algorithmic bytes: a hit moves A_GET, a miss its key and status (k + 8)
+    a_miss_mix = (1.0 - miss_frac) * A_GET + miss_frac * (16 + 8)
+    del m_keys, m_six
+
     # ---- zipf(0.99) MultiGet (config-4 access pattern on one GPU): hot keys are served from L2 ---------
     zrng = np.random.default_rng(synth.SEED_ZIPF + rank)
     z_idx = [synth.scatter_ranks(synth.zipf_ranks(zrng, NKV, 0.99, Q), NKV) for _ in range(3)]
@@ -384,6 +420,7 @@ def main():
     T = S * args.tick
     ticks = []
     upd_idx = []
+    ver_of = np.zeros(NKV, dtype=np.int32)  # newest version of every key, in application order of the ticks
     for stp in range(n_sets * 2):
         # `tick` updates per shard: shard-local ordinals uniform, global index = shard + ordinal * S
         per = NKV // S
@@ -442,6 +479,57 @@ def main():
     ap_launches = eng.kernel_launches() - launches1
     assert not st_out.any()
 
+    for stp in range(n_sets):
+        ver_of[upd_idx[stp].astype(np.int64)] = stp + 1
+    n_versions = 2 * n_sets + K  # version numbers used by the small ticks (device, e2e, mixed)
+
+    # ---- the same with LARGE ticks (args.big_tick updates per shard): the bandwidth-bound regime of the tick -------
+    big = None
+    if args.big_tick:
+        TB = S * args.big_tick
+        KB, WB = min(K, 4), min(W, 2)
+        per = NKV // S
+        big_staged = []
+        for stp in range(WB + KB):
+            ordn = rng.integers(0, per, size=TB, dtype=np.uint64)
+            shb = np.repeat(np.arange(S, dtype=np.uint64), args.big_tick)
+            idxb = shb + ordn * np.uint64(S)
+            vb = n_versions + 1 + stp
+            bb = synth.single_put_batches(synth.keys16(seed, idxb), synth.values(seed, shb.astype(np.int64), idxb, vb), 7000 + idxb)
+            sixb = six_of[shb.astype(np.int64)]
+            offb = np.arange(TB + 1, dtype=np.uint64) * np.uint64(bb.shape[1])
+            tsb = (7000 + idxb).astype(np.uint64)
+            h = C.c_void_p()
+            assert lib.rsp_stage_build(eng.h, TB, sixb.ctypes.data, bb.ctypes.data, offb.ctypes.data, tsb.ctypes.data, C.byref(h)) == 0
+            big_staged.append(h)
+            ver_of[idxb.astype(np.int64)] = vb
+            del bb
+        assert eng.flush_all() == 0  # empty memtables: the timed ticks fit without a flush in between
+        stb = np.zeros(TB, dtype=np.int32)
+        for i in range(WB):
+            assert lib.rsp_reserve(eng.h, big_staged[i]) == 0
+            assert lib.rsp_apply_staged_device(eng.h, big_staged[i], sp) == 0
+            assert lib.rsp_apply_staged_finish(eng.h, big_staged[i], stb.ctypes.data) == 0 and not stb.any()
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kern = []
+        b0.record(stream)
+        for k in range(KB):
+            assert lib.rsp_reserve(eng.h, big_staged[WB + k]) == 0
+            assert lib.rsp_apply_staged_device(eng.h, big_staged[WB + k], sp) == 0
+            assert lib.rsp_apply_staged_finish(eng.h, big_staged[WB + k], stb.ctypes.data) == 0 and not stb.any()
+            kern.append(eng.last_kernel_ms("apply"))
+        b1.record(stream)
+        barrier()
+        big_ms = max_over_ranks(b0.elapsed_time(b1))
+        big = {"batches_per_tick": TB, "ticks": KB, "ms_per_tick": big_ms / max(KB, 1), "kernel_ms_per_tick": float(np.mean(kern))}
+        for h in big_staged:
+            lib.rsp_stage_free(h)
+        n_versions += WB + KB
+    # back to one run per shard and empty memtables (untimed): the end-to-end ticks below then never meet a flush,
+    # whose cost is what the config-5 phase measures
+    assert eng.compact_all() == 0
+
     # e2e apply: pinned host buffers through rsp_apply_many (H2D + kernels + D2H of statuses inside)
     pinned_ticks = []
     for i in range(n_sets):
@@ -465,6 +553,8 @@ def main():
     barrier()
     ap_e2e_s = max_over_ranks(time.perf_counter() - t0)
     clk = clocks.stop()
+    for stp in range(n_sets, 2 * n_sets):
+        ver_of[upd_idx[stp].astype(np.int64)] = stp + 1
 
     # ---- config 3: apply ticks and MultiGet launches CONCURRENTLY (two streams, lock-free memtable) --------
     mticks = []
@@ -511,7 +601,7 @@ def main():
     got_m = d_vals.cpu().numpy().reshape(Q, 64)[samp]
     idx_m = lastq[samp]
     ok_m = np.zeros(samp.size, dtype=bool)
-    for ver in range(0, 2 * n_sets + K + 1):
+    for ver in range(0, n_versions + 1):
         todo = ~ok_m
         if not todo.any():
             break
@@ -521,29 +611,22 @@ def main():
     for h in mticks:
         lib.rsp_stage_free(h)
     n_ticks_total = 2 * n_sets + K
+    for stp in range(2 * n_sets, n_ticks_total):
+        ver_of[upd_idx[stp].astype(np.int64)] = stp + 1
 
     # parity after the update ticks: the newest version wins for every updated key (last writer)
-    newest = {}
-    for stp in range(n_ticks_total):
-        for i in upd_idx[stp][::97]:
-            newest[int(i)] = stp + 1
-    chk = np.fromiter(newest.keys(), dtype=np.uint64)
-    ver = np.fromiter(newest.values(), dtype=np.int64)
-    # a key sampled at step s may have been rewritten later by an unsampled update: resolve exactly
-    lastver = {}
-    for stp in range(n_ticks_total):
-        for i in upd_idx[stp]:
-            lastver[int(i)] = stp + 1
-    ver = np.array([lastver[int(i)] for i in chk], dtype=np.int64)
+    chk = np.unique(np.concatenate([u[::97] for u in upd_idx]))
+    ver = ver_of[chk.astype(np.int64)]
     res = eng.multi_get(six_of[(chk % np.uint64(S)).astype(np.int64)], [k.tobytes() for k in synth.keys16(seed, chk)], stride=64)
     for (rc, v), i, vr in zip(res, chk, ver):
         w = synth.values(seed, np.array([int(i) % S]), np.array([i], dtype=np.uint64), int(vr))[0].tobytes()
         assert rc == 0 and v == w, "apply parity failed"
-    assert sum(s.latest_seq() for s in shards) == NKV + n_ticks_total * T
+    n_big_applied = (big["ticks"] + min(W, 2)) * big["batches_per_tick"] if big else 0
+    assert sum(s.latest_seq() for s in shards) == NKV + n_ticks_total * T + n_big_applied
 
     # ---- config-2 variant: MultiGet while the newest version of many keys is still in the memtables -----
     # (every update tick above landed in a memtable: nothing has been flushed since the load).  Informational: a
-    # failure here is reported in the line, it does not void the phases above.
+    # failure here fails the bench (r01: informational).
     def mg_phase_checked():
         """W + K MultiGet launches of the uniform query sets, K of them timed; status, length and (full size) values
         checked against the last update tick of every queried key.  Local to the rank: no collectives inside."""
@@ -558,13 +641,8 @@ def main():
         torch.cuda.synchronize()
         ms = float(m0.elapsed_time(m1))
         assert int(d_st.count_nonzero().item()) == 0 and int((d_vlen != 64).count_nonzero().item()) == 0, "status / length"
-        uk = np.fromiter(lastver.keys(), dtype=np.uint64, count=len(lastver))
-        uv = np.fromiter(lastver.values(), dtype=np.int64, count=len(lastver))
-        order = np.argsort(uk)
-        uk, uv = uk[order], uv[order]
         lastq = q_idx[W + K - 1] if K else q_idx[-1]
-        pos = np.minimum(np.searchsorted(uk, lastq), len(uk) - 1)
-        qver = np.where(uk[pos] == lastq, uv[pos], 0)
+        qver = ver_of[lastq.astype(np.int64)]
         got = d_vals.cpu().numpy().reshape(Q, 64)
         qsh = (lastq % np.uint64(S)).astype(np.int64)
         for v in np.unique(qver):
@@ -572,22 +650,80 @@ def main():
             assert np.array_equal(got[m], synth.values(seed, qsh[m], lastq[m], int(v))), "value parity (version %d)" % v
         return ms
 
-    mt_ms, mt_err, mt_entries = -1.0, None, 0
-    try:
-        mt_entries = int(sum(s.stats()["memtable_entries"] for s in shards))
-        mt_ms = mg_phase_checked()
-    except Exception as ex:  # noqa: BLE001
-        mt_err = "%s: %s" % (type(ex).__name__, str(ex)[:160])
+    mt_err = None
+    mt_entries = int(sum(s.stats()["memtable_entries"] for s in shards))
+    mt_ms = mg_phase_checked()
 
     # ---- the same once more after a flush WITHOUT compaction: every shard now has two sorted runs (the state between a
-    # flush and the merge at level0_file_num_compaction_trigger; config 5 lives there).  Informational, non-fatal.
-    r2_ms, r2_err, r2_runs = -1.0, None, 0
-    try:
-        assert eng.flush_all() == 0
-        r2_runs = int(max(s.stats()["n_runs"] for s in shards))
-        r2_ms = mg_phase_checked()
-    except Exception as ex:  # noqa: BLE001
-        r2_err = "%s: %s" % (type(ex).__name__, str(ex)[:160])
+    # flush and the merge at level0_file_num_compaction_trigger; config 5 lives there).
+    r2_err = None
+    assert eng.flush_all() == 0
+    r2_runs = int(max(s.stats()["n_runs"] for s in shards))
+    r2_ms = mg_phase_checked()
+
+    # ---- config 5 shape on this GPU: 256-byte values, 80 % applies / 20 % lookups by operation count, flushes and
+    # merges happening as the memtables fill (BASELINE configs[4]; options examples/counter_service/rocksdb_options.cpp:78-93)
+    c5 = None
+    if args.c5_secs > 0:
+        V5, PER5 = 256, 2048
+        N5 = S * PER5
+        c5_shards = [eng.open_shard("cfive%05d" % (rank * S + i), write_buffer_bytes=2 << 20) for i in range(S)]
+        c5_six = np.array([s.index for s in c5_shards], dtype=np.uint32)
+        seed5 = seed + 0x500
+        for lo in range(0, N5, 1 << 19):
+            idx = np.arange(lo, min(N5, lo + (1 << 19)), dtype=np.uint64)
+            sh = (idx % np.uint64(S)).astype(np.int64)
+            b = synth.single_put_batches(synth.keys16(seed5, idx), synth.values(seed5, sh, idx, 0, V5), 9000 + idx)
+            order = np.argsort(sh, kind="stable")
+            off = np.arange(idx.size + 1, dtype=np.uint64) * np.uint64(b.shape[1])
+            st = eng.apply_packed(c5_six[sh[order]], np.ascontiguousarray(b[order]).reshape(-1), off, (9000 + idx[order]))
+            assert not st.any()
+        stats0 = [s_.stats() for s_ in c5_shards]
+        # a rotating set of pre-built ticks (80 % of the operations) and query sets (20 %)
+        T5, Q5, NT5 = S * 50, S * 50 // 4, 8
+        t5 = []
+        ver5 = np.zeros(N5, dtype=np.int32)
+        for i in range(NT5):
+            ordn = rng.integers(0, PER5, size=T5, dtype=np.uint64)
+            sh = np.repeat(np.arange(S, dtype=np.uint64), 50)
+            idx = sh + ordn * np.uint64(S)
+            b = synth.single_put_batches(synth.keys16(seed5, idx), synth.values(seed5, sh.astype(np.int64), idx, i + 1, V5), 9000 + idx)
+            t5.append(tuple(torch.from_numpy(np.ascontiguousarray(x).reshape(-1)).pin_memory() for x in (
+                c5_six[sh.astype(np.int64)], b, np.arange(T5 + 1, dtype=np.uint64) * np.uint64(b.shape[1]), (9000 + idx).astype(np.uint64))) + (idx,))
+        q5 = [rng.integers(0, N5, size=Q5, dtype=np.uint64) for _ in range(NT5)]
+        q5k = [torch.from_numpy(synth.keys16(seed5, q).reshape(-1)).pin_memory() for q in q5]
+        q5s = [torch.from_numpy(c5_six[(q % np.uint64(S)).astype(np.int64)]).pin_memory() for q in q5]
+        h5_vals = torch.empty(Q5 * V5, dtype=torch.uint8).pin_memory()
+        h5_vlen = torch.empty(Q5, dtype=torch.int32).pin_memory()
+        h5_st = torch.empty(Q5, dtype=torch.int32).pin_memory()
+        h5_ast = torch.zeros(T5, dtype=torch.int32).pin_memory()
+        barrier()
+        n_ticks5 = 0
+        compact_ms0 = max(0.0, eng.last_kernel_ms("compact_total"))
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < args.c5_secs:
+            i = n_ticks5 % NT5
+            six_t, b_t, off_t, ts_t, idx_t = t5[i]
+            assert lib.rsp_apply_many(eng.h, T5, six_t.data_ptr(), b_t.data_ptr(), off_t.data_ptr(), ts_t.data_ptr(), h5_ast.data_ptr()) == 0
+            ver5[idx_t.astype(np.int64)] = i + 1
+            assert lib.rsp_multi_get_fixed(eng.h, Q5, q5s[i].data_ptr(), q5k[i].data_ptr(), 16, h5_vals.data_ptr(), V5, h5_vlen.data_ptr(), h5_st.data_ptr()) == 0
+            n_ticks5 += 1
+        c5_s = time.perf_counter() - t0
+        assert int(h5_ast.count_nonzero().item()) == 0 and int(h5_st.count_nonzero().item()) == 0
+        il = (n_ticks5 - 1) % NT5
+        assert np.array_equal(h5_vals.numpy().reshape(Q5, V5)[::7],
+                              np.concatenate([synth.values(seed5, np.array([int(q) % S]), np.array([q], dtype=np.uint64), int(ver5[int(q)]), V5) for q in q5[il][::7]])), "config-5 lookup parity"
+        stats1 = [s_.stats() for s_ in c5_shards]
+        d = lambda k: sum(b_[k] - a_[k] for a_, b_ in zip(stats0, stats1))  # noqa: E731
+        ingested = n_ticks5 * T5 * (16 + V5 + 8)  # bytes of entries written by the applies (k + v + 8 each)
+        c5_local = {"ticks": n_ticks5, "secs": c5_s, "applies": n_ticks5 * T5, "lookups": n_ticks5 * Q5, "flushes": d("flushes"),
+                    "compactions": d("compactions"), "bytes_read": d("compaction_bytes_read"), "bytes_written": d("compaction_bytes_written"),
+                    "ingested": ingested, "max_runs": max(s_["n_runs"] for s_ in stats1), "compact_ms": max(0.0, eng.last_kernel_ms("compact_total")) - compact_ms0}
+        c5 = {k: sum_over_ranks(float(v)) for k, v in c5_local.items() if k not in ("secs", "max_runs")}
+        c5["secs"] = max_over_ranks(c5_local["secs"])
+        c5["max_runs"] = max_over_ranks(float(c5_local["max_runs"]))
+        for s_ in c5_shards:
+            s_.close()
 
     # ---- numbers ---------------------------------------------------------------------------------------
     peak, peak_src = peaks()
@@ -604,11 +740,15 @@ def main():
     lookups_per_s = tot_lookups / (mg_total_ms * 1e-3)
     applies_per_s = tot_applies / (ap_total_ms * 1e-3)
     ach = A_GET * Q / (mg_kernel_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM traffic of the roofline kernel cannot be measured inside a timed run: it is what one `ncu --set full` capture of
+    # this same command recorded (dram__bytes_read.sum + dram__bytes_write.sum for one launch), kept under profiles/
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "multiget_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            if tj.get("lookups_per_launch") == Q:
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         except Exception:
             traffic = None
     # ---- the same path through the reference's seams: DbWrapper (pull loop) and ApplicationDB (MultiGet / Get) ------
@@ -631,11 +771,13 @@ def main():
             "mixed_resp_p99_ms")}
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu:
-        r = run_cpu("reference", ncores, S, args.cpu_kv, 30.0, args.cpu_get_secs)
+        r = run_cpu("reference", ncores, S, args.cpu_kv, 60.0, args.cpu_get_secs)
         cpu = {"value": r["lookups_per_s"], "unit": "lookups/s", "cores": r["threads"], "kind": r["kind"],
                "sample": "%d KV applied over %d shards with default WriteOptions (WAL on), flush+compact, then %.0f s of MultiGet(4096) split per shard; %d threads" % (
                    r["applied"], r["shards"], r["get_s"], r["threads"]),
-               "applies_per_s": r["applies_per_s"]}
+               "applies_per_s": r["applies_per_s"],
+               "per_core": {"lookups_per_s": r["lookups_per_s"] / max(1, r["threads"]), "applies_per_s": r["applies_per_s"] / max(1, r["threads"])},
+               "note": "the reference's options share one LRU block cache per DB among all reader threads; per-core figures are the fair comparison"}
     if rank == 0:
         line = {
             "metric": "multiget_lookups_per_s", "value": lookups_per_s, "unit": "lookups/s", "n_gpus": world,
@@ -646,11 +788,13 @@ def main():
                        "flags": {k: os.environ[k] for k in sorted(os.environ) if k.startswith("RSP_")}},
             "applies": {"value": applies_per_s, "unit": "applies/s", "ms_per_tick": ap_total_ms / max(K, 1),
                         "kernel_ms_last_tick": ap_kernel_ms, "batches_per_tick": T,
-                        "issue": "the K ticks are launched back to back; statuses read back and folded, in order, inside the timed region",
+                        "what": "device-resident: the ticks are pre-staged device images (rsp_stage_build, H2D outside the timed region); the K ticks are launched back to back, statuses read back and folded, in order, inside the timed region",
+                        "large_ticks": (None if not big else dict(big, applies_per_s=sum_over_ranks(big["batches_per_tick"] * big["ticks"]) / (big["ms_per_tick"] * big["ticks"] * 1e-3),
+                                                                  hbm_frac_of_peak=A_PUT * big["batches_per_tick"] / (big["kernel_ms_per_tick"] * 1e-3) / 1e9 / peak)),
                         "hbm_frac_of_peak": (A_PUT * T / (ap_kernel_ms * 1e-3) / 1e9 / peak) if ap_kernel_ms and ap_kernel_ms > 0 else None,
                         "e2e": {"value": tot_applies / ap_e2e_s, "unit": "applies/s", "h2d_bytes_per_step": int(ticks[0][1].size + 10 * T), "d2h_bytes_per_step": 4 * T + 24 * S}},
             "roofline": {"kernel": "k_multi_get16", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_lookup": A_GET,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_lookup": A_GET,
                          "lookups_per_launch": Q, "launch_ms": mg_kernel_ms},
             "memtable": ({"error": mt_err or "failed on another rank"} if mt_failed else
                          {"what": "config-2 variant: the same uniform MultiGet with the update ticks still in the memtables (entries there = %.0f %% of the key count; nothing flushed since the load); values checked at full size" % (100.0 * mt_entries_all / max(1, NKV * world)),
@@ -660,6 +804,16 @@ def main():
                          {"what": "the same MultiGet after a flush without compaction: %d sorted runs per shard (lookups that miss the newest run go on to the older one); values checked at full size" % r2_runs,
                           "lookups_per_s": tot_lookups / (r2_ms_all * 1e-3),
                           "hbm_frac_of_peak_algorithmic": A_GET * Q / (r2_ms_all * 1e-3 / max(K, 1)) / 1e9 / peak}),
+            "miss10": {"what": "config-2 variant: %.1f %% of the lookups ask for keys that were never written (NotFound); statuses and the values of the hits checked at full size" % (100 * miss_frac),
+                       "lookups_per_s": tot_lookups / (miss_ms * 1e-3),
+                       "hbm_frac_of_peak_algorithmic": a_miss_mix * Q / (miss_ms * 1e-3 / max(K, 1)) / 1e9 / peak},
+            "config5": (None if not c5 else {
+                "what": "config-5 shape per GPU: %d shards, 16 B keys / 256 B values, alternating apply ticks (80 %% of the operations, %d single-Put WriteBatches each) and MultiGet calls (20 %%) through the host-buffer C ABI for %.1f s, flushes and size-tiered merges running as the memtables fill" % (S, S * 50, args.c5_secs),
+                "applies_per_s": c5["applies"] / c5["secs"], "lookups_per_s": c5["lookups"] / c5["secs"],
+                "flushes": int(c5["flushes"]), "merges": int(c5["compactions"]), "max_runs_per_shard": int(c5["max_runs"]),
+                "write_amplification": c5["bytes_written"] / max(1.0, c5["ingested"]),
+                "compaction": {"bytes_read": c5["bytes_read"], "bytes_written": c5["bytes_written"], "kernel_ms": c5["compact_ms"],
+                               "hbm_frac_of_peak": ((c5["bytes_read"] + c5["bytes_written"]) / max(1e-9, c5["compact_ms"] * 1e-3 / max(1, world)) / 1e9 / peak) if c5["compact_ms"] > 0 else None}}),
             "zipf": {"theta": 0.99, "lookups_per_s": tot_lookups / (zipf_ms * 1e-3), "hbm_frac_of_peak_algorithmic": A_GET * Q / (zipf_ms * 1e-3 / max(K, 1)) / 1e9 / peak},
             "mixed": {"what": "config 3: %d apply ticks on the engine stream concurrent with %d MultiGet launches on a second stream" % (K, K),
                       "lookups_per_s": tot_lookups / (mixed_get_ms * 1e-3), "applies_per_s": tot_applies / (mixed_apply_ms * 1e-3),

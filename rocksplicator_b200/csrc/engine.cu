@@ -526,6 +526,7 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->last_ms["compact"] = ms;
+  e->last_ms["compact_total"] += ms;  // kernels of every flush / merge so far (sizing round trip included)
   for (u32 i = 0; i < nj; i++) {
     a.release(jobs[i].items, jh[i].items_b);
     if (jobs[i].items2) a.release(jobs[i].items2, jh[i].items2_b);
@@ -1544,7 +1545,7 @@ static ApplyCombiner* apply_combiner(rsp_engine* e) {
   c->o_st = c->o_blob + align_up(c->cap_bytes + 64, 256);
   c->total = c->o_st + align_up(c->cap_items * 4, 256);
   for (auto& S : c->st) S.pin = pinned_mapped(c->total, &S.pin_dev);
-  c->pool.start(env_size("RSP_COMPLETION_THREADS", 8));
+  c->pool.start(env_size("RSP_COMPLETION_THREADS", 16));
   c->stager.reset(new Stager(c->cap_items, c->cap_bytes, [c](const Stager::BatchInfo& b) { c->run(b); },
                              [c] { c->pool.add_many(c->done_now); }));
   e->apply_comb = c;
@@ -1672,7 +1673,12 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   CUDA_OK(cudaEventCreate(&e->ev1));
   CUDA_OK(cudaMalloc(&e->d_shards, sizeof(ShardDev) * e->cfg.max_shards));
   CUDA_OK(cudaMemset(e->d_shards, 0, sizeof(ShardDev) * e->cfg.max_shards));
-  {
+  if (getenv("RSP_DBG_FASTALLOC")) {  // (bisecting the r02 MultiGet regression: the r01 allocation shape)
+    CUDA_OK(cudaMalloc(&e->d_fast, sizeof(ShardFast) * e->cfg.max_shards));
+    CUDA_OK(cudaMemset(e->d_fast, 0, sizeof(ShardFast) * e->cfg.max_shards));
+    CUDA_OK(cudaMalloc(&e->d_fast_runs, sizeof(ShardFast) * e->cfg.max_shards * RSP_MAX_RUNS));
+    CUDA_OK(cudaMemset(e->d_fast_runs, 0, sizeof(ShardFast) * e->cfg.max_shards * RSP_MAX_RUNS));
+  } else {
     const size_t n_fast = (size_t)e->cfg.max_shards * (1 + RSP_MAX_RUNS);
     CUDA_OK(cudaMalloc(&e->d_fast, sizeof(ShardFast) * n_fast));
     CUDA_OK(cudaMemset(e->d_fast, 0, sizeof(ShardFast) * n_fast));

@@ -240,7 +240,7 @@ extern "C" int rsp_seam_bench(const rsp_seam_cfg* cfg_in, rsp_seam_result* res) 
   const auto saved_flags = F;
   F.rocksdb_replicator_executor_threads = (int32_t)std::max<uint32_t>(16, cfg.executor_threads);
   F.replicator_max_updates_per_response = (int32_t)cfg.updates_per_response;
-  auto leader = std::make_shared<SyntheticLeader>(cfg, std::max<size_t>(8, cfg.executor_threads / 2));
+  auto leader = std::make_shared<SyntheticLeader>(cfg, std::max<size_t>(16, cfg.executor_threads));  // the remote leaders' CPUs
   leader->stride_ = S;  // (single-rank key space: index = shard id + ordinal * S with ids offset by first_shard_id)
   std::atomic<uint64_t> parity_errors{0}, status_errors{0};
   {

@@ -231,7 +231,11 @@ void GpuDB::ApplyReplicatedBatch(const std::vector<replicator::Update>& updates,
         std::unique_ptr<Ctx> x(static_cast<Ctx*>(c));
         uint64_t first = x->seq_before + 1;
         {
-          std::lock_guard<std::mutex> g(x->db->write_mu_);
+          // what the follower's own WAL would hold (its downstream followers pull it): every applied batch + its
+          // LogData(timestamp), stamped with its sequence number; built outside the log's lock, appended in one go
+          std::vector<std::shared_ptr<LogEntry>> fresh;
+          fresh.reserve(n_applied);
+          size_t bytes_total = 0;
           for (size_t i = 0; i < n_applied; i++) {
             const std::string& raw = (*x->updates)[i].raw_data;
             if (raw.size() < rocksdb::WriteBatch::kHeader) continue;
@@ -239,15 +243,28 @@ void GpuDB::ApplyReplicatedBatch(const std::vector<replicator::Update>& updates,
             memcpy(&count, raw.data() + 8, 4);
             if (!count) continue;
             const uint64_t tsv = (uint64_t)(*x->updates)[i].timestamp;
-            std::string bytes;
-            bytes.reserve(raw.size() + 10);
-            bytes.assign(raw.data(), raw.size());
-            bytes.push_back(0x3);
-            bytes.push_back(8);
-            bytes.append((const char*)&tsv, 8);
-            memcpy(&bytes[0], &first, 8);
-            x->db->LogAppend(first, std::move(bytes), count);
+            auto e = std::make_shared<LogEntry>();
+            e->first_seq = first;
+            e->count = count;
+            e->bytes.reserve(raw.size() + 10);
+            e->bytes.assign(raw.data(), raw.size());
+            e->bytes.push_back(0x3);
+            e->bytes.push_back(8);
+            e->bytes.append((const char*)&tsv, 8);
+            memcpy(&e->bytes[0], &first, 8);
+            bytes_total += e->bytes.size();
+            fresh.push_back(std::move(e));
             first += count;
+          }
+          std::lock_guard<std::mutex> g(x->db->write_mu_);
+          std::lock_guard<std::mutex> g2(x->db->log_mu_);
+          GpuDB* db = x->db;
+          db->log_bytes_ += bytes_total;
+          for (auto& e : fresh) db->log_.push_back(std::move(e));
+          while (db->log_bytes_ > db->log_cap_bytes_ && db->log_.size() > 1) {
+            db->log_bytes_ -= db->log_.front()->bytes.size();
+            db->log_.pop_front();
+            db->log_base_id_++;
           }
         }
         x->done(n_applied, status == RSP_OK ? Status::OK() : x->db->ToStatus(status));

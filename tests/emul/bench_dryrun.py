@@ -83,7 +83,7 @@ def main(argv=None):
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     sys.argv = ["bench.py"] + (argv or ["--shards", "8", "--kv", "6000", "--mg-batches", "1", "--tick", "5", "--steps", "2",
-                                        "--warmup", "1", "--no-cpu"])
+                                        "--warmup", "1", "--no-cpu", "--big-tick", "40", "--c5-secs", "0.5"])
     bench.main()
 
 
