@@ -16,6 +16,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -27,15 +28,47 @@
 
 using namespace rsp;
 
-#define CUDA_OK(x)                                                                                   \
-  do {                                                                                               \
-    cudaError_t e_ = (x);                                                                            \
-    if (e_ != cudaSuccess) {                                                                         \
-      fprintf(stderr, "[rsp_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__,     \
-              __LINE__, cudaGetErrorString(e_));                                                     \
-      abort();                                                                                       \
-    }                                                                                                \
+// A failed CUDA call inside the library must not take the host process down (the header promises status codes): it
+// is thrown, unwinds through the RAII locks, and is turned into RSP_IO_ERROR at the C ABI (abi_guard below); the text
+// is kept for rsp_engine_last_error.  Device-side faults are sticky in the CUDA context: later calls fail the same way.
+struct CudaFailure : public std::runtime_error {
+  explicit CudaFailure(const std::string& m) : std::runtime_error(m) {}
+};
+static std::mutex g_fail_mu;
+static std::string g_fail_text;
+[[noreturn]] static void throw_cuda(cudaError_t e, const char* file, int line) {
+  char buf[384];
+  snprintf(buf, sizeof(buf), "CUDA error %s at %s:%d: %s", cudaGetErrorName(e), file, line, cudaGetErrorString(e));
+  fprintf(stderr, "[rsp_b200] %s\n", buf);
+  {
+    std::lock_guard<std::mutex> g(g_fail_mu);
+    g_fail_text = buf;
+  }
+  throw CudaFailure(buf);
+}
+#define CUDA_OK(x)                                            \
+  do {                                                        \
+    cudaError_t e_ = (x);                                     \
+    if (e_ != cudaSuccess) throw_cuda(e_, __FILE__, __LINE__); \
   } while (0)
+// what an extern "C" entry point answers when its body threw
+static int abi_caught() noexcept {
+  try {
+    throw;
+  } catch (const CudaFailure&) {
+    return RSP_IO_ERROR;
+  } catch (const std::bad_alloc&) {
+    std::lock_guard<std::mutex> g(g_fail_mu);
+    g_fail_text = "out of host memory";
+    return RSP_IO_ERROR;
+  } catch (const std::exception& ex) {
+    std::lock_guard<std::mutex> g(g_fail_mu);
+    g_fail_text = ex.what();
+    return RSP_IO_ERROR;
+  } catch (...) {
+    return RSP_IO_ERROR;
+  }
+}
 
 static const char* kMsgText[MSG_COUNT] = {
     "",
@@ -1151,7 +1184,7 @@ static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, c
     a.vals = d + o_vals + c0 * val_stride; a.val_stride = val_stride;
     a.vlen = (u32*)(d + o_vlen) + c0; a.st = (i32*)(d + o_st) + c0; a.n = (u32)cn;
     a.n_special = scratch; a.n_pending = scratch + 4 + 2 * c; a.pending = scratch + 4 + 2 * n_chunks + c0; a.parity = 0;
-    a.fast_runs = e->d_fast_runs; a.multirun = e->n_multirun.load() ? 1u : 0u; a.pad = 0;
+    a.multirun = e->n_multirun.load() ? 1u : 0u;
     launch_multi_get(a, cs);
     e->launches += 2;
     CUDA_OK(cudaMemcpyAsync(vlen + c0, d + o_vlen + c0 * 4, cn * 4, cudaMemcpyDeviceToHost, cs));
@@ -1393,7 +1426,7 @@ struct ReadCombiner {
     a.koff = fixed16 ? nullptr : (const u64*)(base + o_koff); a.klen_fixed = fixed16 ? 16u : 0u;
     a.vals = base + o_vals; a.val_stride = stride; a.vlen = (u32*)(base + o_vlen); a.st = (i32*)(base + o_st); a.n = (u32)n;
     a.n_special = nullptr; a.n_pending = S.d_pending; a.pending = S.d_pending + 4; a.parity = 0;
-    a.fast_runs = e->d_fast_runs; a.multirun = e->n_multirun.load() ? 1u : 0u; a.pad = 0;
+    a.multirun = e->n_multirun.load() ? 1u : 0u;
     {
       // ordering against flushes / memtable re-allocations on the engine stream (reader_begin / reader_end)
       std::lock_guard<std::mutex> g(e->mu);
@@ -1637,6 +1670,7 @@ extern "C" {
 const char* rsp_version(void) { return "rocksplicator_b200 0.1 (sm_100a)"; }
 
 int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
+  try {
   if (!out) return RSP_INVALID_ARGUMENT;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
@@ -1673,12 +1707,7 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   CUDA_OK(cudaEventCreate(&e->ev1));
   CUDA_OK(cudaMalloc(&e->d_shards, sizeof(ShardDev) * e->cfg.max_shards));
   CUDA_OK(cudaMemset(e->d_shards, 0, sizeof(ShardDev) * e->cfg.max_shards));
-  if (getenv("RSP_DBG_FASTALLOC")) {  // (bisecting the r02 MultiGet regression: the r01 allocation shape)
-    CUDA_OK(cudaMalloc(&e->d_fast, sizeof(ShardFast) * e->cfg.max_shards));
-    CUDA_OK(cudaMemset(e->d_fast, 0, sizeof(ShardFast) * e->cfg.max_shards));
-    CUDA_OK(cudaMalloc(&e->d_fast_runs, sizeof(ShardFast) * e->cfg.max_shards * RSP_MAX_RUNS));
-    CUDA_OK(cudaMemset(e->d_fast_runs, 0, sizeof(ShardFast) * e->cfg.max_shards * RSP_MAX_RUNS));
-  } else {
+  {
     const size_t n_fast = (size_t)e->cfg.max_shards * (1 + RSP_MAX_RUNS);
     CUDA_OK(cudaMalloc(&e->d_fast, sizeof(ShardFast) * n_fast));
     CUDA_OK(cudaMemset(e->d_fast, 0, sizeof(ShardFast) * n_fast));
@@ -1686,6 +1715,7 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   }
   *out = e;
   return RSP_OK;
+  } catch (...) { return abi_caught(); }
 }
 
 void rsp_engine_destroy(rsp_engine* e) {
@@ -1753,19 +1783,23 @@ static void shard_close_locked(rsp_shard* s) {
 }
 
 int rsp_shard_open(rsp_engine* e, const char* name, const rsp_shard_opts* opts, rsp_shard** out) {
+  try {
   if (!e || !name || !out) return RSP_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(e->mu);
   CUDA_OK(cudaSetDevice(e->device));
   return shard_open_locked(e, name, opts, out);
+  } catch (...) { return abi_caught(); }
 }
 
 int rsp_shard_close(rsp_shard* s) {
+  try {
   if (!s) return RSP_INVALID_ARGUMENT;
   rsp_engine* e = s->eng;
   std::lock_guard<std::mutex> g(e->mu);
   CUDA_OK(cudaSetDevice(e->device));
   shard_close_locked(s);
   return RSP_OK;
+  } catch (...) { return abi_caught(); }
 }
 
 // first / last user key of a run (two small copies: the run is immutable)
@@ -1792,6 +1826,7 @@ static void run_key_range(rsp_engine* e, const Run& r, std::string* first, std::
 // not consulted by reads: recency is the run order).
 int rsp_ingest_sorted(rsp_shard* s, size_t n, const uint8_t* keys, const uint64_t* koff, const uint8_t* vals,
                       const uint64_t* voff, int allow_global_seqno, uint64_t* seq_out) {
+  try {
   if (!s || !n || !keys || !koff || !voff) return RSP_INVALID_ARGUMENT;
   rsp_engine* e = s->eng;
   std::lock_guard<std::mutex> g(e->mu);
@@ -1872,6 +1907,7 @@ int rsp_ingest_sorted(rsp_shard* s, size_t n, const uint8_t* keys, const uint64_
   shard_close_locked(tmp);
   if (seq_out) *seq_out = s->last_seq.load();
   return rc;
+  } catch (...) { return abi_caught(); }
 }
 
 uint32_t rsp_shard_index(const rsp_shard* s) { return s->index; }
@@ -1879,42 +1915,52 @@ const char* rsp_shard_name(const rsp_shard* s) { return s->name.c_str(); }
 uint64_t rsp_latest_seq(const rsp_shard* s) { return s->last_seq.load(std::memory_order_acquire); }
 
 size_t rsp_last_error(const rsp_shard* s, char* buf, size_t cap) {
+  try {
   rsp_shard* m = const_cast<rsp_shard*>(s);
   std::lock_guard<std::mutex> g(m->err_mu);
   if (buf && cap) snprintf(buf, cap, "%s", m->last_error.c_str());
   return m->last_error.size();
+  } catch (...) { abi_caught(); return 0; }
 }
 
 int rsp_apply_many(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob, const uint64_t* off,
                    const uint64_t* ts_ms, int32_t* st_out) {
+  try {
   if (!e || (n && (!shard_ix || !off))) return RSP_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(e->mu);
   CUDA_OK(cudaSetDevice(e->device));
   return apply_many_locked(e, n, shard_ix, blob, off, ts_ms, st_out);
+  } catch (...) { return abi_caught(); }
 }
 
 int rsp_apply(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t ts_ms, uint64_t* seq_out) {
+  try {
   if (!s) return RSP_INVALID_ARGUMENT;
   static const uint8_t empty = 0;
   const rsp_slice b{batch ? batch : &empty, len};
   const int rc = apply_combined(s, 1, &b, &ts_ms, true, nullptr, nullptr, nullptr);  // concurrent callers share one device tick
   if (seq_out) *seq_out = rsp_latest_seq(s);
   return rc;
+  } catch (...) { return abi_caught(); }
 }
 
 int rsp_write(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t* seq_out) {
+  try {
   if (!s) return RSP_INVALID_ARGUMENT;
   static const uint8_t empty = 0;
   const rsp_slice b{batch ? batch : &empty, len};
   const int rc = apply_combined(s, 1, &b, nullptr, false, nullptr, nullptr, nullptr);
   if (seq_out) *seq_out = rsp_latest_seq(s);
   return rc;
+  } catch (...) { return abi_caught(); }
 }
 
 int rsp_apply_updates(rsp_shard* s, size_t n, const rsp_slice* batches, const uint64_t* ts_ms, rsp_done_fn done,
                       void* ctx, size_t* n_applied) {
+  try {
   if (!s || (n && !batches)) return RSP_INVALID_ARGUMENT;
   return apply_combined(s, n, batches, ts_ms, ts_ms != nullptr, done, ctx, n_applied);
+  } catch (...) { return abi_caught(); }
 }
 
 // statuses the fast / generic kernels settle themselves; anything else (host-folded merges, error texts, unknown
@@ -1956,17 +2002,22 @@ static int multi_get_any(rsp_engine* e, size_t n, const uint32_t* shard_ix, cons
 
 int rsp_multi_get(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, const uint64_t* koff,
                   uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
+  try {
   if (!e || (n && (!shard_ix || !koff || !vlen || !st))) return RSP_INVALID_ARGUMENT;
   return multi_get_any(e, n, shard_ix, keys, koff, 0, vals, val_stride, vlen, st);
+  } catch (...) { return abi_caught(); }
 }
 
 int rsp_multi_get_fixed(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, uint32_t klen,
                         uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
+  try {
   if (!e || !klen || (n && (!shard_ix || !keys || !vlen || !st))) return RSP_INVALID_ARGUMENT;
   return multi_get_any(e, n, shard_ix, keys, nullptr, klen, vals, val_stride, vlen, st);
+  } catch (...) { return abi_caught(); }
 }
 
 int rsp_multi_get_slices(rsp_shard* s, size_t n, const rsp_slice* keys, size_t value_hint, rsp_value_fn fn, void* ctx) {
+  try {
   if (!s || !fn || (n && !keys)) return RSP_INVALID_ARGUMENT;
   if (n == 0) return RSP_OK;
   rsp_engine* e = s->eng;
@@ -2008,9 +2059,11 @@ int rsp_multi_get_slices(rsp_shard* s, size_t n, const rsp_slice* keys, size_t v
     for (size_t j = 0; j < m; j++) fn(ctx, idx[j], st[j], st[j] == RSP_OK ? &vals[j * vs] : nullptr, st[j] == RSP_OK ? vlen[j] : 0);
     return RSP_OK;
   }
+  } catch (...) { return abi_caught(); }
 }
 
 int rsp_get(rsp_shard* s, const uint8_t* key, size_t klen, uint8_t* val, size_t cap, size_t* vlen) {
+  try {
   if (!s) return RSP_INVALID_ARGUMENT;
   const uint64_t koff[2] = {0, klen};
   const uint32_t six = s->index;
@@ -2022,6 +2075,7 @@ int rsp_get(rsp_shard* s, const uint8_t* key, size_t klen, uint8_t* val, size_t 
   if (rc != RSP_OK) return rc;
   if (vlen) *vlen = vl;
   return st;
+  } catch (...) { return abi_caught(); }
 }
 
 
@@ -2033,14 +2087,17 @@ struct rsp_router {
 };
 
 int rsp_router_create(size_t n_engines, rsp_engine* const* engines, rsp_router** out) {
+  try {
   if (!n_engines || !engines || !out) return RSP_INVALID_ARGUMENT;
   rsp_router* r = new rsp_router();
   r->engines.assign(engines, engines + n_engines);
   *out = r;
   return RSP_OK;
+  } catch (...) { return abi_caught(); }
 }
 void rsp_router_destroy(rsp_router* r) { delete r; }
 int rsp_router_add_shard(rsp_router* r, uint32_t shard_id, rsp_shard* s) {
+  try {
   if (!r || !s) return RSP_INVALID_ARGUMENT;
   for (size_t k = 0; k < r->engines.size(); k++) {
     if (r->engines[k] != s->eng) continue;
@@ -2050,11 +2107,14 @@ int rsp_router_add_shard(rsp_router* r, uint32_t shard_id, rsp_shard* s) {
     return RSP_OK;
   }
   return RSP_INVALID_ARGUMENT;  // the shard lives on an engine the router does not know
+  } catch (...) { return abi_caught(); }
 }
 int rsp_router_remove_shard(rsp_router* r, uint32_t shard_id) {
+  try {
   if (!r) return RSP_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(r->mu);
   return r->where.erase(shard_id) ? RSP_OK : RSP_NOT_FOUND;
+  } catch (...) { return abi_caught(); }
 }
 
 extern "C++" {
@@ -2137,17 +2197,22 @@ static int router_multi_get(rsp_router* r, size_t n, const uint32_t* shard_id, c
 
 int rsp_router_multi_get(rsp_router* r, size_t n, const uint32_t* shard_id, const uint8_t* keys, const uint64_t* koff,
                          uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
+  try {
   if (!r || (n && (!shard_id || !koff || !vlen || !st))) return RSP_INVALID_ARGUMENT;
   return router_multi_get(r, n, shard_id, keys, koff, 0, vals, val_stride, vlen, st);
+  } catch (...) { return abi_caught(); }
 }
 int rsp_router_multi_get_fixed(rsp_router* r, size_t n, const uint32_t* shard_id, const uint8_t* keys, uint32_t klen,
                                uint8_t* vals, size_t val_stride, uint32_t* vlen, int32_t* st) {
+  try {
   if (!r || !klen || (n && (!shard_id || !keys || !vlen || !st))) return RSP_INVALID_ARGUMENT;
   return router_multi_get(r, n, shard_id, keys, nullptr, klen, vals, val_stride, vlen, st);
+  } catch (...) { return abi_caught(); }
 }
 
 int rsp_router_apply_many(rsp_router* r, size_t n, const uint32_t* shard_id, const uint8_t* blob, const uint64_t* off,
                           const uint64_t* ts_ms, int32_t* st_out) {
+  try {
   if (!r || (n && (!shard_id || !off))) return RSP_INVALID_ARGUMENT;
   if (n == 0) return RSP_OK;
   const Buckets b = bucket_by_engine(r, n, shard_id);
@@ -2169,23 +2234,28 @@ int rsp_router_apply_many(rsp_router* r, size_t n, const uint32_t* shard_id, con
     if (st_out) for (size_t j = 0; j < m; j++) st_out[ix[j]] = s[j] ? s[j] : (rc == RSP_INVALID_ARGUMENT ? rc : 0);
   });
   return worst.load();
+  } catch (...) { return abi_caught(); }
 }
 
 int rsp_flush(rsp_shard* s) {
+  try {
   if (!s) return RSP_INVALID_ARGUMENT;
   rsp_engine* e = s->eng;
   std::lock_guard<std::mutex> g(e->mu);
   CUDA_OK(cudaSetDevice(e->device));
   compact_shards(e, {s}, false);
   return RSP_OK;
+  } catch (...) { return abi_caught(); }
 }
 int rsp_compact(rsp_shard* s) {
+  try {
   if (!s) return RSP_INVALID_ARGUMENT;
   rsp_engine* e = s->eng;
   std::lock_guard<std::mutex> g(e->mu);
   CUDA_OK(cudaSetDevice(e->device));
   compact_shards(e, {s}, true);
   return RSP_OK;
+  } catch (...) { return abi_caught(); }
 }
 static int all_shards(rsp_engine* e, bool full) {
   std::lock_guard<std::mutex> g(e->mu);
@@ -2199,10 +2269,19 @@ static int all_shards(rsp_engine* e, bool full) {
   }
   return RSP_OK;
 }
-int rsp_flush_all(rsp_engine* e) { return e ? all_shards(e, false) : RSP_INVALID_ARGUMENT; }
-int rsp_compact_all(rsp_engine* e) { return e ? all_shards(e, true) : RSP_INVALID_ARGUMENT; }
+int rsp_flush_all(rsp_engine* e) {
+  try {
+    return e ? all_shards(e, false) : RSP_INVALID_ARGUMENT;
+  } catch (...) { return abi_caught(); }
+}
+int rsp_compact_all(rsp_engine* e) {
+  try {
+    return e ? all_shards(e, true) : RSP_INVALID_ARGUMENT;
+  } catch (...) { return abi_caught(); }
+}
 
 int rsp_get_stats(const rsp_shard* s, rsp_stats* out) {
+  try {
   if (!s || !out) return RSP_INVALID_ARGUMENT;
   rsp_engine* e = s->eng;
   std::lock_guard<std::mutex> g(e->mu);
@@ -2214,10 +2293,12 @@ int rsp_get_stats(const rsp_shard* s, rsp_stats* out) {
   out->run_entries = 0; out->run_bytes = 0;
   for (auto& r : s->runs) { out->run_entries += r->n_ent; out->run_bytes += r->bytes(); }
   return RSP_OK;
+  } catch (...) { return abi_caught(); }
 }
 
 // ---- iterator ----
 rsp_iter* rsp_iter_create(rsp_shard* s) {
+  try {
   if (!s) return nullptr;
   rsp_engine* e = s->eng;
   rsp_iter* it = new rsp_iter();
@@ -2236,8 +2317,10 @@ rsp_iter* rsp_iter_create(rsp_shard* s) {
   CUDA_OK(cudaMemcpyAsync(it->d_view, &v, sizeof(v), cudaMemcpyHostToDevice, e->st));
   CUDA_OK(cudaStreamSynchronize(e->st));
   return it;
+  } catch (...) { abi_caught(); return nullptr; }
 }
 void rsp_iter_destroy(rsp_iter* it) {
+  try {
   if (!it) return;
   rsp_engine* e = it->s->eng;
   {
@@ -2248,15 +2331,27 @@ void rsp_iter_destroy(rsp_iter* it) {
     it->pinned.clear();
   }
   delete it;
+  } catch (...) { abi_caught(); }
 }
-void rsp_iter_seek_to_first(rsp_iter* it) { it->want = 16; iter_fetch(it, nullptr, false, false); }
-void rsp_iter_seek_to_last(rsp_iter* it) { it->want = 16; iter_fetch(it, nullptr, false, true); }
+void rsp_iter_seek_to_first(rsp_iter* it) {
+  try {
+    it->want = 16; iter_fetch(it, nullptr, false, false);
+  } catch (...) { abi_caught(); it->valid = false; it->status = RSP_IO_ERROR; }
+}
+void rsp_iter_seek_to_last(rsp_iter* it) {
+  try {
+    it->want = 16; iter_fetch(it, nullptr, false, true);
+  } catch (...) { abi_caught(); it->valid = false; it->status = RSP_IO_ERROR; }
+}
 void rsp_iter_seek(rsp_iter* it, const uint8_t* key, size_t klen) {
+  try {
   std::string k((const char*)key, klen);
   it->want = 16;
   iter_fetch(it, &k, false, false);
+  } catch (...) { abi_caught(); }
 }
 void rsp_iter_next(rsp_iter* it) {
+  try {
   if (!it->valid) return;
   if (it->reverse) {  // direction change: refetch forward from the current key, exclusive
     std::string k = it->buf[it->pos].first;
@@ -2268,8 +2363,10 @@ void rsp_iter_next(rsp_iter* it) {
   if (it->exhausted) { it->valid = false; return; }
   std::string k = it->buf[it->pos].first;
   iter_fetch(it, &k, true, false);
+  } catch (...) { abi_caught(); }
 }
 void rsp_iter_prev(rsp_iter* it) {
+  try {
   if (!it->valid) return;
   if (!it->reverse) {
     std::string k = it->buf[it->pos].first;
@@ -2281,6 +2378,7 @@ void rsp_iter_prev(rsp_iter* it) {
   if (it->exhausted) { it->valid = false; return; }
   std::string k = it->buf[it->pos].first;
   iter_fetch(it, &k, true, true);
+  } catch (...) { abi_caught(); }
 }
 int rsp_iter_valid(const rsp_iter* it) { return it->valid ? 1 : 0; }
 const uint8_t* rsp_iter_key(const rsp_iter* it, size_t* klen) {
@@ -2298,6 +2396,7 @@ int rsp_iter_status(const rsp_iter* it) { return it->status; }
 // ---- batched scans (host buffers) ----
 int rsp_multi_scan(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* keys, const uint64_t* koff,
                    uint32_t max_entries, uint8_t* out, size_t out_stride, uint32_t* n_out, int32_t* st) {
+  try {
   if (!e || (n && (!shard_ix || !koff || !out || !n_out || !st))) return RSP_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(e->mu);
   CUDA_OK(cudaSetDevice(e->device));
@@ -2349,11 +2448,13 @@ int rsp_multi_scan(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint
     }
   }
   return RSP_OK;
+  } catch (...) { return abi_caught(); }
 }
 
 // ---- device-pointer forms ----
 int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, const uint8_t* d_keys, uint32_t klen,
                          uint8_t* d_vals, uint32_t val_stride, uint32_t* d_vlen, int32_t* d_st, void* stream) {
+  try {
   if (!e || !klen) return RSP_INVALID_ARGUMENT;
   GetArgs a;
   a.shards = e->d_shards; a.fast = e->d_fast; a.shard_ix = d_shard_ix; a.keys = d_keys; a.koff = nullptr; a.klen_fixed = klen;
@@ -2364,17 +2465,19 @@ int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, co
     a.max_shards = e->cfg.max_shards;
     cudaStream_t rs = stream ? (cudaStream_t)stream : e->st;
     reader_begin(e, rs);
-    a.fast_runs = e->d_fast_runs; a.multirun = e->n_multirun.load() ? 1u : 0u; a.pad = 0;
+    a.multirun = e->n_multirun.load() ? 1u : 0u;
     launch_multi_get(a, rs);
     reader_end(e, rs);
   }
   e->launches += 2;
   return cudaPeekAtLastError() == cudaSuccess ? RSP_OK : RSP_IO_ERROR;
+  } catch (...) { return abi_caught(); }
 }
 
 int rsp_multi_scan_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, const uint8_t* d_keys, uint32_t klen,
                           uint32_t max_entries, uint8_t* d_out, uint64_t out_stride, uint32_t* d_n_out, int32_t* d_st,
                           void* stream) {
+  try {
   if (!e || !klen) return RSP_INVALID_ARGUMENT;
   ScanArgs a;
   a.shards = e->d_shards; a.views = nullptr; a.shard_ix = d_shard_ix; a.keys = d_keys; a.koff = nullptr;
@@ -2389,10 +2492,12 @@ int rsp_multi_scan_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, c
   }
   e->launches++;
   return cudaPeekAtLastError() == cudaSuccess ? RSP_OK : RSP_IO_ERROR;
+  } catch (...) { return abi_caught(); }
 }
 
 int rsp_stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob, const uint64_t* off,
                     const uint64_t* ts_ms, rsp_staged** out) {
+  try {
   if (!e || !out || !n) return RSP_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(e->mu);
   CUDA_OK(cudaSetDevice(e->device));
@@ -2401,6 +2506,7 @@ int rsp_stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uin
   if (rc != RSP_OK) { delete sg; return rc; }
   *out = sg;
   return RSP_OK;
+  } catch (...) { return abi_caught(); }
 }
 void rsp_stage_free(rsp_staged* sg) {
   if (!sg) return;
@@ -2409,6 +2515,7 @@ void rsp_stage_free(rsp_staged* sg) {
   delete sg;
 }
 int rsp_reserve(rsp_engine* e, const rsp_staged* sg) {
+  try {
   if (!e || !sg) return RSP_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(e->mu);
   CUDA_OK(cudaSetDevice(e->device));
@@ -2418,16 +2525,20 @@ int rsp_reserve(rsp_engine* e, const rsp_staged* sg) {
   if (r < 0) return RSP_BUSY;  // fold the results of the ticks in flight (rsp_apply_staged_finish), then retry
   if (r > 0) CUDA_OK(cudaStreamSynchronize(e->st));
   return RSP_OK;
+  } catch (...) { return abi_caught(); }
 }
 int rsp_apply_staged_device(rsp_engine* e, rsp_staged* sg, void* stream) {
+  try {
   if (!e || !sg) return RSP_INVALID_ARGUMENT;
   sg->last_stream = stream ? (cudaStream_t)stream : e->st;
   cudaEventRecord(e->ev0, sg->last_stream);
   tick_launch(e, sg, sg->last_stream);
   cudaEventRecord(e->ev1, sg->last_stream);
   return cudaPeekAtLastError() == cudaSuccess ? RSP_OK : RSP_IO_ERROR;
+  } catch (...) { return abi_caught(); }
 }
 int rsp_apply_staged_finish(rsp_engine* e, rsp_staged* sg, int32_t* st_out) {
+  try {
   if (!e || !sg) return RSP_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> g(e->mu);
   CUDA_OK(cudaSetDevice(e->device));
@@ -2438,18 +2549,22 @@ int rsp_apply_staged_finish(rsp_engine* e, rsp_staged* sg, int32_t* st_out) {
   float ms = 0;
   if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_ms["apply"] = ms;
   return tick_results(sg, pout, st_out);
+  } catch (...) { return abi_caught(); }
 }
 
 float rsp_last_kernel_ms(const rsp_engine* e, const char* what) {
+  try {
   rsp_engine* m = const_cast<rsp_engine*>(e);
   std::lock_guard<std::mutex> g(m->mu);
   auto it = m->last_ms.find(what);
   return it == m->last_ms.end() ? -1.f : it->second;
+  } catch (...) { abi_caught(); return -1.f; }
 }
 uint64_t rsp_kernel_launches(const rsp_engine* e) { return e->launches.load(); }
 
 // diagnostics: how many lookups of the last MultiGet launch took the generic path (synchronises)
 uint32_t rsp_debug_last_pending(rsp_engine* e, uint32_t* first, uint32_t cap) {
+  try {
   std::lock_guard<std::mutex> g(e->mu);
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
@@ -2458,6 +2573,7 @@ uint32_t rsp_debug_last_pending(rsp_engine* e, uint32_t* first, uint32_t cap) {
   cudaMemcpy(&n, (u32*)e->dev_pending.p + 2 + (e->mg_parity ^ 1u), 4, cudaMemcpyDeviceToHost);
   if (first && cap) cudaMemcpy(first, (u32*)e->dev_pending.p + 4, 4 * std::min(n, cap), cudaMemcpyDeviceToHost);
   return n;
+  } catch (...) { abi_caught(); return 0; }
 }
 
 }  // extern "C"

@@ -268,35 +268,48 @@ __global__ void __launch_bounds__(256) k_multi_get(GetArgs a) {
   lookup_generic(a, q, lane, gmask, gbase);
 }
 
+// Measured and dropped in r02 (profiles/r02_experiments/): hash-addressed entry slots instead of the index
+// (0.38 / 0.32 / 0.18 of the roofline at load 0.25 / 0.5 / 0.75 against 0.41) and software prefetch of later lookups'
+// sectors (0.18).
 // ---- the hot kernel: 16-byte keys, TWO lanes per lookup, three dependent memory round trips ----------
 //   1. shard id + query key (coalesced across the warp) and the 32-byte ShardFast descriptor
 //      (32 B x #shards: L1/L2-resident); both lanes load the same words (one broadcast transaction)
-//   2. the hash bucket: one 32-byte sector of the run's index, four u32 slots (one 16-byte load) per lane
+//   2. the hash bucket: one 32-byte sector of run 0's index, four u32 slots (one 16-byte load) per lane
 //      (when the memtable is not empty: eight u64 memtable slots first, four per lane)
 //   3. the entry: both lanes read the header and key units (same sector, broadcast) and decide alike with
 //      no shuffles; lane L then moves value units L, L+2, .. straight from its registers to the output
 //      (2 lanes x 2 x 16 B = the 64-byte value)
 // The kernel is issue-bound before it is HBM-bound, so the lane count per lookup is what the instruction
 // budget allows: 8 lanes cost ~70 warp instructions per lookup, 2 lanes ~1/4 of that.
-// A shard with several sorted runs (between a flush and the next merge) is walked newest run first: a run that
-// does not hold the key hands over to the next older one (MULTI = true; per-run descriptors behind the ShardFast
-// array).  Anything else — tag false positive chains longer than the probe, Delete / Merge, version chains, odd
-// sizes — is appended to the pending list and served by the generic path (k_multi_get_pending).
-// Measured and dropped in r02 (profiles/r02_experiments/): hash-addressed entry slots instead of the index
-// (0.38 / 0.32 / 0.18 of the roofline at load 0.25 / 0.5 / 0.75 against 0.41), software prefetch of later lookups'
-// sectors (0.18), L2 evict_first on the streams (-20 %), L1::no_allocate on entry units (-5 %).
+// Anything else — tag false positive, probe longer than 4 buckets, Delete / Merge, version chains, several
+// runs, odd sizes — is appended to the pending list and served by the generic path (k_multi_get_pending).
 static_assert(offsetof(ShardDev, mt_slot_mask) == 24 && offsetof(ShardDev, pub_seq) == 56, "ShardDev units 0-3");
 static_assert(sizeof(ShardFast) == 32, "ShardFast");
 
 constexpr u32 FL = 2;  // lanes per lookup
 
-// the hash-index sectors are the only data with reuse across lookups (80 MB at 10 M keys vs a 126 MB L2): evict_last
+// L2 residency control (createpolicy + ld/st .L2::cache_hint): the hash-index sectors are the only
+// data with reuse across lookups (80 MB at 10 M keys vs a 126 MB L2); entries, query keys and results
+// stream through once.  RSP_MG_HINTS: 0 = none, 1 = index evict_last (+1 %), 2 = also streams evict_first
+// (measured 20 % SLOWER on B200: kept only as an experiment switch).  RSP_MG_NOALLOC: entry units bypass L1.
+#ifndef RSP_MG_HINTS
+#define RSP_MG_HINTS 1
+#endif
 __device__ __forceinline__ u64 pol_evict_last() {
   u64 p;
 #ifdef RSP_EMUL  // tests/emul: cache policies have no meaning on the CPU
   p = 0;
 #else
   asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+#endif
+  return p;
+}
+__device__ __forceinline__ u64 pol_evict_first() {
+  u64 p;
+#ifdef RSP_EMUL
+  p = 0;
+#else
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
 #endif
   return p;
 }
@@ -311,6 +324,15 @@ __device__ __forceinline__ uint4 ldg_pol(const uint4* p, u64 pol) {
 #endif
   return v;
 }
+__device__ __forceinline__ void stg_pol(uint4* p, const uint4& v, u64 pol) {
+#ifdef RSP_EMUL
+  (void)pol;
+  *p = v;
+#else
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+#endif
+}
 #ifndef RSP_MG_TPB
 #define RSP_MG_TPB 64
 #endif
@@ -320,25 +342,46 @@ __device__ __forceinline__ uint4 ldg_pol(const uint4* p, u64 pol) {
 
 // Candidate entry at `ent`: header unit 0, key unit KU, value units KU+1.. (U units in all).
 // Returns 0 = served, 1 = not my key (tag false positive), 2 = needs the generic path.
+#ifndef RSP_MG_NOALLOC
+#define RSP_MG_NOALLOC 0  // measured 5 % slower with L1::no_allocate on the entry units
+#endif
+#ifndef RSP_MG_MEMSET
+#define RSP_MG_MEMSET 1
+#endif
+__device__ __forceinline__ uint4 ldg_noalloc(const uint4* p) {
+  uint4 v;
+#ifdef RSP_EMUL
+  v = *p;
+#else
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#endif
+  return v;
+}
 template <bool CG>
-__device__ __forceinline__ uint4 ld_entry_unit(const uint4* p) {
+__device__ __forceinline__ uint4 ld_entry_unit(const uint4* p, u64 pol) {
   if (CG) return __ldcg(p);
+#if RSP_MG_HINTS >= 2
+  return ldg_pol(p, pol);
+#elif RSP_MG_NOALLOC
+  return ldg_noalloc(p);
+#else
   return __ldg(p);
+#endif
 }
 template <bool CG, bool BIG>
 __device__ __forceinline__ u32 fast_entry(const u8* ent, u32 U, u32 KU, const uint4& kq, u64 snap, u8* dst,
-                                          u64 val_stride, u32 lane, u32& vlen_out) {
+                                          u64 val_stride, u32 lane, u32& vlen_out, u64 pol) {
   const uint4* ep = reinterpret_cast<const uint4*>(ent);
-  const uint4 hd = ld_entry_unit<CG>(ep);
-  const uint4 ek = ld_entry_unit<CG>(ep + KU);
+  const uint4 hd = ld_entry_unit<CG>(ep, pol);
+  const uint4 ek = ld_entry_unit<CG>(ep + KU, pol);
   const u32 fv = KU + 1;  // first value unit; lane L owns value units L, L+2, L+4, ...
   uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
   if (!CG) {
     // a run: the entry size U is known before the header arrives, so the first six value units are
     // requested together with header and key (one round trip for values up to 96 bytes)
-    if (fv + lane < U) v0 = ld_entry_unit<CG>(ep + fv + lane);
-    if (fv + lane + 2 < U) v1 = ld_entry_unit<CG>(ep + fv + lane + 2);
-    if (fv + lane + 4 < U) v2 = ld_entry_unit<CG>(ep + fv + lane + 4);
+    if (fv + lane < U) v0 = ld_entry_unit<CG>(ep + fv + lane, pol);
+    if (fv + lane + 2 < U) v1 = ld_entry_unit<CG>(ep + fv + lane + 2, pol);
+    if (fv + lane + 4 < U) v2 = ld_entry_unit<CG>(ep + fv + lane + 4, pol);
   }
   if (ek.x != kq.x || ek.y != kq.y || ek.z != kq.z || ek.w != kq.w || hd.z != 16) return 1;
   const u64 seq = (((u64)hd.y << 32) | hd.x) >> 8;
@@ -347,13 +390,183 @@ __device__ __forceinline__ u32 fast_entry(const u8* ent, u32 U, u32 KU, const ui
   uint4* out = reinterpret_cast<uint4*>(dst);
   if (CG) {
     // the memtable: the entry's size is only known from its header, so the value follows in a second trip
-    for (u32 u = lane; u < vu; u += FL) out[u] = ld_entry_unit<CG>(ep + fv + u);
+    for (u32 u = lane; u < vu; u += FL) out[u] = ld_entry_unit<CG>(ep + fv + u, pol);
+  } else {
+#if RSP_MG_HINTS >= 2
+    if (lane < vu) stg_pol(out + lane, v0, pol);
+    if (lane + 2 < vu) stg_pol(out + lane + 2, v1, pol);
+    if (lane + 4 < vu) stg_pol(out + lane + 4, v2, pol);
+#else
+    if (lane < vu) out[lane] = v0;
+    if (lane + 2 < vu) out[lane + 2] = v1;
+    if (lane + 4 < vu) out[lane + 4] = v2;
+#endif
+    if (BIG)
+      for (u32 u = lane + 6; u < vu; u += FL) out[u] = ld_entry_unit<CG>(ep + fv + u, pol);  // values > 96 bytes
+  }
+  vlen_out = hd.w;
+  return 0;
+}
+
+// BIG = false: values up to 96 bytes (larger ones take the pending list); BIG = true adds the tail loop for
+// larger values at the price of a few registers — the host picks by the caller's value stride.
+template <bool BIG>
+__global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs a) {
+  const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) / FL;
+  const u32 lane = threadIdx.x & (FL - 1);
+  const u32 pbase = (threadIdx.x & 31u) & ~1u;
+  const u32 pmask = 3u << pbase;  // the two lanes of this lookup always branch together
+  if (q >= a.n) return;
+  // (1)
+  const u64 pol_stream = pol_evict_first();
+  u32 six = __ldg(a.shard_ix + q);
+  const bool bad_shard = six >= a.max_shards;
+  if (bad_shard) six = 0;
+#if RSP_MG_HINTS >= 2
+  const uint4 kq = ldg_pol(reinterpret_cast<const uint4*>(a.keys) + q, pol_stream);
+#else
+  const uint4 kq = __ldg(reinterpret_cast<const uint4*>(a.keys) + q);
+#endif
+  const uint4 f0 = __ldg(reinterpret_cast<const uint4*>(a.fast + six));
+  const uint4 f1 = __ldg(reinterpret_cast<const uint4*>(a.fast + six) + 1);
+  const u32 n_buckets = f1.x, ord_bits = f1.y & 0xffu, U = (f1.y >> 8) & 0xffu, n_runs = (f1.y >> 16) & 0xffu;
+  const u64 k0 = ((u64)kq.y << 32) | kq.x, k1 = ((u64)kq.w << 32) | kq.z;
+  const u64 h = hash_final(hash_step(hash_step(hash_init(16), k0), k1));
+  u8* dst = a.vals + (u64)q * a.val_stride;
+  u32 state = 3;  // 0 served, 2 generic path, 3 undecided, 4 not found
+  u32 vlen = 0;
+  if (n_runs > 1 || ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u) || bad_shard || !(f1.y >> 24)) state = 2;
+  if (state == 3 && f1.z /* mt_count */) {
+    // ---- memtable: eight u64 slots from the home position, four per lane; descriptor through L2
+    const uint4* dp = reinterpret_cast<const uint4*>(a.shards + six);
+    const uint4 d0 = __ldcg(dp), d1 = __ldcg(dp + 1), d3 = __ldcg(dp + 3);
+    const u8* heap = reinterpret_cast<const u8*>(((u64)d0.y << 32) | d0.x);
+    const u64* sp = reinterpret_cast<const u64*>(((u64)d0.w << 32) | d0.z);
+    const u32 mask = d1.z;
+    const u64 snap = ((u64)d3.w << 32) | d3.z;
+    const u32 tag = hash_tag32(h);
+    u32 cand = 0, info = 0;  // info: matches | (position of my first empty + 1) << 8
+#pragma unroll
+    for (u32 i = 0; i < 4; i++) {
+      const u64 sv = ldcg64(sp + (((u32)h + 4u * lane + i) & mask));
+      if (sv == 0) { if (!(info >> 8)) info |= (4u * lane + i + 1u) << 8; }
+      else if ((u32)(sv >> 32) == tag && !(info >> 8)) { if (!cand) cand = (u32)sv; info++; }
+    }
+    const u32 o_cand = __shfl_xor_sync(pmask, cand, 1), o_info = __shfl_xor_sync(pmask, info, 1);
+    // lane 1's slots come after lane 0's in probe order: they count only if lane 0 saw no empty slot
+    const u32 lo_info = lane ? o_info : info, hi_info = lane ? info : o_info;
+    const u32 lo_cand = lane ? o_cand : cand, hi_cand = lane ? cand : o_cand;
+    const bool lo_empty = (lo_info >> 8) != 0;
+    const u32 n_match = (lo_info & 0xffu) + (lo_empty ? 0u : (hi_info & 0xffu));
+    const bool any_empty = lo_empty || (hi_info >> 8) != 0;
+    if (n_match == 1) {
+      const u32 c = (lo_info & 0xffu) ? lo_cand : hi_cand;
+      // memtable entry: unit0 header, unit1 link, unit2 key, units 3.. value
+      const u32 r = fast_entry<true, BIG>(heap + (u64)(c - 1u) * 16u, 7, 2, kq, snap, dst, a.val_stride, lane, vlen, pol_stream);
+      state = r == 0 ? 0 : 2;
+    } else if (n_match > 1 || !any_empty) {
+      state = 2;
+    }
+  }
+  if (state == 3) {
+    if (n_runs == 0) state = 4;
+    else if (U == 0 || U >= 255) state = 2;
+    else {
+      // ---- run 0 through its hash index: one bucket = one 32-byte sector, four slots per lane
+      const u8* heap = reinterpret_cast<const u8*>(((u64)f0.y << 32) | f0.x);
+      const uint4* hs = reinterpret_cast<const uint4*>(((u64)f0.w << 32) | f0.z);
+      u32 bucket = (u32)(((u64)(u32)h * n_buckets) >> 32);
+      const u32 tag = (u32)(h >> 32) >> ord_bits;
+      // Walk the tag matches in probe order; a false positive (18-bit tags at 16 K entries: ~1 per 60 K
+      // lookups) just moves on to the next candidate, a full bucket to the next bucket.
+      u32 m8 = 0, e8 = 1, probe = 0;  // e8 != 0 before the first load only so that the loop loads first
+      uint4 sv = make_uint4(0, 0, 0, 0);
+      state = 2;
+#pragma unroll 1
+      for (;;) {
+        if (!m8) {
+          if (probe && e8) { state = 4; break; }  // an empty slot ends the probe: NOT_FOUND
+          if (probe == n_buckets) { state = 4; break; }  // (a table without an empty slot)
+          if (probe) bucket = bucket + 1 == n_buckets ? 0 : bucket + 1;
+          probe++;
+#if RSP_MG_HINTS >= 1
+          sv = ldg_pol(hs + (u64)bucket * 2u + lane, pol_evict_last());
+#else
+          sv = __ldg(hs + (u64)bucket * 2u + lane);
+#endif
+          const u32 m = ((sv.x && (sv.x >> ord_bits) == tag) ? 1u : 0u) | ((sv.y && (sv.y >> ord_bits) == tag) ? 2u : 0u) |
+                        ((sv.z && (sv.z >> ord_bits) == tag) ? 4u : 0u) | ((sv.w && (sv.w >> ord_bits) == tag) ? 8u : 0u);
+          const u32 e = (sv.x == 0 || sv.y == 0 || sv.z == 0 || sv.w == 0) ? 1u : 0u;
+          const u32 mine = m | (e << 4);
+          const u32 other = __shfl_xor_sync(pmask, mine, 1);
+          m8 = lane ? ((other & 15u) | ((mine & 15u) << 4)) : ((mine & 15u) | ((other & 15u) << 4));
+          e8 = (mine | other) >> 4;
+          if (!m8) continue;
+        }
+        const u32 p = __ffs(m8) - 1;
+        m8 &= m8 - 1;
+        const u32 pick = (p & 2u) ? ((p & 1u) ? sv.w : sv.z) : ((p & 1u) ? sv.y : sv.x);
+        const u32 val = __shfl_sync(pmask, pick, pbase + (p >> 2));
+        // run entry: unit0 header, unit1 key, units 2.. value
+        const u32 r = fast_entry<false, BIG>(heap + (u64)((val & ((1u << ord_bits) - 1u)) - 1u) * U * 16u, U, 1, kq, ~0ull, dst,
+                                        a.val_stride, lane, vlen, pol_stream);
+        if (r == 0) { state = 0; break; }
+        if (r == 2) break;
+      }
+    }
+  }
+  if (lane == 0) {
+    if (state == 2) {
+      a.pending[atomicAdd(a.n_pending + a.parity, 1u)] = q;
+    } else {
+      a.st[q] = state == 0 ? 0 : 1;
+      a.vlen[q] = vlen;
+    }
+  }
+  // this launch counts in n_pending[parity].  Clearing the other counter here instead of a memset node
+  // before the launch measured 20 % SLOWER end to end on B200 (14.98 -> 12.08 G lookups/s), so the
+  // memset node stays (RSP_MG_MEMSET=1).
+#if !RSP_MG_MEMSET
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.n_pending[a.parity ^ 1u] = 0;
+#endif
+}
+
+// Candidate entry at `ent`: header unit 0, key unit KU, value units KU+1.. (U units in all).
+// Returns 0 = served, 1 = not my key (tag false positive), 2 = needs the generic path.
+template <bool CG>
+__device__ __forceinline__ uint4 ld_entry_unit_m(const uint4* p) {
+  if (CG) return __ldcg(p);
+  return __ldg(p);
+}
+template <bool CG, bool BIG>
+__device__ __forceinline__ u32 fast_entry_m(const u8* ent, u32 U, u32 KU, const uint4& kq, u64 snap, u8* dst,
+                                          u64 val_stride, u32 lane, u32& vlen_out) {
+  const uint4* ep = reinterpret_cast<const uint4*>(ent);
+  const uint4 hd = ld_entry_unit_m<CG>(ep);
+  const uint4 ek = ld_entry_unit_m<CG>(ep + KU);
+  const u32 fv = KU + 1;  // first value unit; lane L owns value units L, L+2, L+4, ...
+  uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
+  if (!CG) {
+    // a run: the entry size U is known before the header arrives, so the first six value units are
+    // requested together with header and key (one round trip for values up to 96 bytes)
+    if (fv + lane < U) v0 = ld_entry_unit_m<CG>(ep + fv + lane);
+    if (fv + lane + 2 < U) v1 = ld_entry_unit_m<CG>(ep + fv + lane + 2);
+    if (fv + lane + 4 < U) v2 = ld_entry_unit_m<CG>(ep + fv + lane + 4);
+  }
+  if (ek.x != kq.x || ek.y != kq.y || ek.z != kq.z || ek.w != kq.w || hd.z != 16) return 1;
+  const u64 seq = (((u64)hd.y << 32) | hd.x) >> 8;
+  const u32 vu = (hd.w + 15u) >> 4;
+  if ((hd.x & 0xffu) != kTypeValue || seq > snap || (!CG && fv + vu > U) || (u64)vu * 16u > val_stride || (!BIG && vu > 6)) return 2;
+  uint4* out = reinterpret_cast<uint4*>(dst);
+  if (CG) {
+    // the memtable: the entry's size is only known from its header, so the value follows in a second trip
+    for (u32 u = lane; u < vu; u += FL) out[u] = ld_entry_unit_m<CG>(ep + fv + u);
   } else {
     if (lane < vu) out[lane] = v0;
     if (lane + 2 < vu) out[lane + 2] = v1;
     if (lane + 4 < vu) out[lane + 4] = v2;
     if (BIG)
-      for (u32 u = lane + 6; u < vu; u += FL) out[u] = ld_entry_unit<CG>(ep + fv + u);  // values > 96 bytes
+      for (u32 u = lane + 6; u < vu; u += FL) out[u] = ld_entry_unit_m<CG>(ep + fv + u);  // values > 96 bytes
   }
   vlen_out = hd.w;
   return 0;
@@ -396,18 +609,21 @@ __device__ __forceinline__ u32 probe_one_run(const uint4& g0, const uint4& g1, c
     const u32 pick = (p & 2u) ? ((p & 1u) ? sv.w : sv.z) : ((p & 1u) ? sv.y : sv.x);
     const u32 val = __shfl_sync(pmask, pick, pbase + (p >> 2));
     // run entry: unit0 header, unit1 key, units 2.. value
-    const u32 r = fast_entry<false, BIG>(heap + (u64)((val & ((1u << ord_bits) - 1u)) - 1u) * U * 16u, U, 1, kq, ~0ull, dst,
+    const u32 r = fast_entry_m<false, BIG>(heap + (u64)((val & ((1u << ord_bits) - 1u)) - 1u) * U * 16u, U, 1, kq, ~0ull, dst,
                                          val_stride, lane, vlen);
     if (r == 0) return 0;
     if (r == 2) return 2;
   }
 }
 
-// BIG = false: values up to 96 bytes (larger ones take the pending list); BIG = true adds the tail loop for
-// larger values at the price of a few registers — the host picks by the caller's value stride.
-// MULTI = false: every live shard has at most one run (the host knows): the r01 kernel, SASS unchanged.
-template <bool BIG, bool MULTI>
-__global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs a) {
+// k_multi_get16m: the same lookup for engines where some shard has SEVERAL sorted runs (between a flush and the next
+// merge): the runs are walked newest first, a run that does not hold the key hands over to the next older one
+// (per-run descriptors behind the ShardFast array).  The single-run kernel above is kept exactly as measured in r01:
+// folding both into one template cost it 20 % (13.3 instead of 16.2 G lookups/s on the same B200, same instruction
+// mix — profiles/r02_regression_bisect.md), so the host picks the kernel per launch instead.
+template <bool BIG>
+__global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16m(GetArgs a) {
+  constexpr bool MULTI = true;
   const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) / FL;
   const u32 lane = threadIdx.x & (FL - 1);
   const u32 pbase = (threadIdx.x & 31u) & ~1u;
@@ -453,7 +669,7 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
     if (n_match == 1) {
       const u32 c = (lo_info & 0xffu) ? lo_cand : hi_cand;
       // memtable entry: unit0 header, unit1 link, unit2 key, units 3.. value
-      const u32 r = fast_entry<true, BIG>(heap + (u64)(c - 1u) * 16u, 7, 2, kq, snap, dst, a.val_stride, lane, vlen);
+      const u32 r = fast_entry_m<true, BIG>(heap + (u64)(c - 1u) * 16u, 7, 2, kq, snap, dst, a.val_stride, lane, vlen);
       state = r == 0 ? 0 : 2;
     } else if (n_match > 1 || !any_empty) {
       state = 2;
@@ -466,7 +682,7 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
     for (u32 r = 0; r < nr; r++) {
       uint4 g0 = f0, g1 = f1;
       if (MULTI && r) {
-        const uint4* fr = reinterpret_cast<const uint4*>(a.fast_runs) + ((u64)six * RSP_MAX_RUNS + r) * 2u;
+        const uint4* fr = reinterpret_cast<const uint4*>(a.fast + a.max_shards) + ((u64)six * RSP_MAX_RUNS + r) * 2u;
         g0 = __ldg(fr);
         g1 = __ldg(fr + 1);
       }
@@ -500,15 +716,16 @@ void launch_multi_get(const GetArgs& a, cudaStream_t s) {
   const u32 per_block = 256 / MG_LANES;
   const u32 grid = (a.n + per_block - 1) / per_block;
   if (a.klen_fixed == 16 && (reinterpret_cast<uintptr_t>(a.keys) & 15u) == 0 && a.pending && a.fast) {
-    // this launch counts in n_pending[parity]; a memset node clears it (clearing the other counter inside the kernel
-    // measured 20 % slower end to end on B200)
+    // this launch counts in n_pending[parity]; a memset node clears it
+#if RSP_MG_MEMSET
     cudaMemsetAsync(a.n_pending + a.parity, 0, 4, s);
+#endif
     const u32 g16 = (a.n + RSP_MG_TPB / FL - 1) / (RSP_MG_TPB / FL);
-    const bool multi = a.multirun && a.fast_runs;
+    const bool multi = a.multirun != 0;
     if (a.val_stride > 96) {
-      if (multi) k_multi_get16<true, true><<<g16, RSP_MG_TPB, 0, s>>>(a); else k_multi_get16<true, false><<<g16, RSP_MG_TPB, 0, s>>>(a);
+      if (multi) k_multi_get16m<true><<<g16, RSP_MG_TPB, 0, s>>>(a); else k_multi_get16<true><<<g16, RSP_MG_TPB, 0, s>>>(a);
     } else {
-      if (multi) k_multi_get16<false, true><<<g16, RSP_MG_TPB, 0, s>>>(a); else k_multi_get16<false, false><<<g16, RSP_MG_TPB, 0, s>>>(a);
+      if (multi) k_multi_get16m<false><<<g16, RSP_MG_TPB, 0, s>>>(a); else k_multi_get16<false><<<g16, RSP_MG_TPB, 0, s>>>(a);
     }
     k_multi_get_pending<<<std::min<u32>(grid, 148u), 256, 0, s>>>(a);
   } else {

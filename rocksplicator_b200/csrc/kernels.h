@@ -114,10 +114,12 @@ struct GetArgs {
   u32 parity;
   u32* n_special;        // [1] counts lookups whose status is none of OK / NotFound / Incomplete (may be nullptr)
   u32 max_shards;        // shard ids >= this answer InvalidArgument
-  const ShardFast* fast_runs;  // [max_shards][RSP_MAX_RUNS] per-run descriptors (runs 1.. of a shard; [0] mirrors fast)
-  u32 multirun;          // some live shard has more than one run: the fast kernel walks the runs newest first
-  u32 pad;
+  u32 multirun;          // some live shard has more than one run: k_multi_get16m walks the runs newest first; the per-run
+                         // descriptors ([max_shards][RSP_MAX_RUNS]) follow the ShardFast array in the same allocation.
+                         // (The struct keeps its r01 size and field offsets: growing it by eight bytes changes the
+                         // register allocation of k_multi_get16 and costs it 20 % — profiles/r02_regression_bisect.md)
 };
+static_assert(sizeof(GetArgs) == 128, "GetArgs layout is part of k_multi_get16's measured code generation");
 void launch_multi_get(const GetArgs& a, cudaStream_t s);
 
 // dump the version stack of each key (newest first, up to and including the first Put/Delete) for
