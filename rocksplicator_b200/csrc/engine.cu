@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -247,6 +248,9 @@ struct rsp_shard {
   rsp_stats stats{};
   size_t mt_heap_bytes = 0, mt_slot_bytes = 0, mt_ent_bytes = 0;
   bool counted_multirun = false;  // this shard is counted in the engine's n_multirun
+  bool merging = false;           // a background merge of runs [bg_first_pinned ..] is in flight
+  u64 uid = 0;                    // never reused: a background merge recognises the shard it planned for
+  const Run* bg_first_pinned = nullptr;
 };
 
 struct rsp_staged {
@@ -269,6 +273,7 @@ struct rsp_staged {
 
 struct ReadCombiner;
 struct ApplyCombiner;
+struct Compactor;
 
 struct rsp_engine {
   int device = 0;
@@ -303,6 +308,8 @@ struct rsp_engine {
   ShardFast* d_fast_runs = nullptr;
   std::atomic<u32> n_multirun{0};
   bool fused_ticks = true;  // RSP_FUSED_TICK=0: always the four general kernels (k_decode .. k_publish)
+  bool bg_compaction = true;  // RSP_BG_COMPACT=0: merges run on the apply path (r01 behaviour)
+  struct Compactor* compactor = nullptr;
   u32 mg_parity = 0;
   size_t pending_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -337,13 +344,22 @@ static void reader_end(rsp_engine* e, cudaStream_t s) {
   e->reader_pending++;
 }
 
-static void upload_shard(rsp_engine* e, rsp_shard* s) {
+// runs_only: only the run set changed (a background merge was installed).  The sequencing state of the descriptor
+// (last_seq, pub_seq, mt_tail, mt_count, latch) belongs to the DEVICE while ticks are in flight — the host mirror may
+// lag behind pre-staged ticks — so it is not written then.
+static void upload_shard(rsp_engine* e, rsp_shard* s, bool runs_only = false) {
   s->h.n_runs = (u32)s->runs.size();
   for (u32 i = 0; i < RSP_MAX_RUNS; i++) {
     if (i < s->runs.size()) s->h.runs[i] = s->runs[i]->dev();
     else memset(&s->h.runs[i], 0, sizeof(RunDev));
   }
-  CUDA_OK(cudaMemcpyAsync(e->d_shards + s->index, &s->h, sizeof(ShardDev), cudaMemcpyHostToDevice, e->st));
+  if (runs_only) {
+    const size_t from = offsetof(ShardDev, n_runs);
+    CUDA_OK(cudaMemcpyAsync((u8*)(e->d_shards + s->index) + from, (const u8*)&s->h + from, sizeof(ShardDev) - from,
+                            cudaMemcpyHostToDevice, e->st));
+  } else {
+    CUDA_OK(cudaMemcpyAsync(e->d_shards + s->index, &s->h, sizeof(ShardDev), cudaMemcpyHostToDevice, e->st));
+  }
   auto describe = [](const Run& r, ShardFast* f) {
     f->run0_heap = (u64)r.heap; f->run0_hslots = (u64)r.hslots; f->n_buckets = r.n_buckets;
     f->meta = r.ord_bits | (std::min<u32>(r.uniform_units, 255u) << 8);
@@ -366,7 +382,8 @@ static void upload_shard(rsp_engine* e, rsp_shard* s) {
   f.meta |= 1u << 24;  // live
   f.mt_count = s->h.mt_count;
   f.merge_op = s->h.merge_op;
-  CUDA_OK(cudaMemcpyAsync(e->d_fast + s->index, &f, sizeof(f), cudaMemcpyHostToDevice, e->st));
+  // (runs_only: the first 24 bytes = run 0 + meta; mt_count is written by the sequencing kernels)
+  CUDA_OK(cudaMemcpyAsync(e->d_fast + s->index, &f, runs_only ? offsetof(ShardFast, mt_count) : sizeof(f), cudaMemcpyHostToDevice, e->st));
   // the host mirror is pageable: the copy above is staged before the call returns
 }
 
@@ -408,48 +425,87 @@ static void alloc_memtable(rsp_engine* e, rsp_shard* s, u64 units, u64 ents) {
 // ------------------------------------------------------------------------------------------------
 struct JobHost {
   rsp_shard* s;
-  bool full;       // every run of the shard takes part: the output is the shard's only run
-  size_t n_merged; // runs[0 .. n_merged) are replaced by the output
+  u32 index;        // s->index / s->uid at planning time: a background install checks that the shard is still the same
+  u64 uid;
+  bool full;        // every run of the shard takes part: the output is the shard's only run
+  bool has_mem;     // the memtable is a source (flush)
+  size_t n_merged;  // srcs.size(): the runs replaced by the output
   std::vector<std::shared_ptr<Run>> srcs;
   size_t items_b, items2_b, coranks_b, keep_b, fold_b;
 };
+// one batch of flush / merge jobs: planned under the engine mutex, run on a stream, installed under the mutex again
+struct CompactPlan {
+  std::vector<JobHost> jh;
+  std::vector<CompactJob> jobs;
+  std::vector<std::shared_ptr<Run>> outs;
+  CompactJob* d_jobs = nullptr;
+  float ms = 0;
+};
+enum CompactMode {
+  COMPACT_FLUSH,     // memtable -> new run; the newest runs join only when the run table is nearly full
+  COMPACT_FULL,      // everything into one run (CompactRange(nullptr, nullptr))
+  COMPACT_SNAPSHOT,  // memtable -> a private sorted run for an iterator; the shard is left untouched
+  COMPACT_MERGE      // background: the size-tiered merge set of the runs, no memtable
+};
 
-// Which runs join the flush?  Size-tiered (the role of RocksDB's level0_file_num_compaction_trigger + level sizing,
-// examples/counter_service/rocksdb_options.cpp:82-93): below the trigger the memtable becomes a new run by itself;
-// at the trigger the newest runs are merged with it, stopping before a run more than twice as large as everything
-// gathered so far — the big bottom run is rewritten only when the small ones have grown to its order of magnitude,
-// so write amplification stays logarithmic in the shard size instead of shard_bytes / write_buffer.
-static size_t pick_merge_set(const rsp_engine* e, const rsp_shard* s, bool has_mem, bool force_full) {
-  const size_t nr = s->runs.size();
-  if (force_full) return nr;
-  if (nr + (has_mem ? 1 : 0) < e->cfg.l0_compaction_trigger && nr + 1 <= RSP_MAX_RUNS) return 0;
-  u64 acc = has_mem ? (u64)s->h.mt_tail * 16 : 0;
+// Which runs are merged?  Size-tiered (the role of RocksDB's level0_file_num_compaction_trigger + level sizing,
+// examples/counter_service/rocksdb_options.cpp:82-93): at the trigger the newest runs are merged, stopping before a
+// run more than twice as large as everything gathered so far — the big bottom run is rewritten only when the small
+// ones have grown to its order of magnitude, so write amplification stays logarithmic in the shard size instead of
+// shard_bytes / write_buffer.  `acc` starts with what is merged anyway (the memtable of a foreground flush).  Runs
+// pinned by a background merge in flight (from s->bg_first_pinned on) are not touched.
+static size_t tiered_set(const rsp_shard* s, u64 acc, size_t limit, bool must_shrink) {
   size_t j = 0;
-  while (j < nr) {
+  const size_t min_take = acc ? 1 : 2;  // a merge needs two inputs
+  while (j < limit) {
     const u64 sz = s->runs[j]->bytes();
-    const bool must = nr - j + 1 > RSP_MAX_RUNS - 1;  // the run table itself is nearly full
-    if (j >= 1 && !must && sz > 2 * acc) break;
+    if (j >= min_take && !(must_shrink && j < 2) && sz > 2 * acc) break;
     acc += sz;
     j++;
   }
   return j;
 }
+static size_t unpinned_runs(const rsp_shard* s) {
+  if (!s->merging) return s->runs.size();
+  for (size_t i = 0; i < s->runs.size(); i++) if (s->runs[i].get() == s->bg_first_pinned) return i;
+  return s->runs.size();
+}
 
-static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards, bool force_full) {
-  std::vector<JobHost> jh;
-  std::vector<CompactJob> jobs;
+static void bg_request(rsp_engine* e, rsp_shard* s);
+
+// ---- plan (engine mutex held) ------------------------------------------------------------------------
+static void plan_jobs(rsp_engine* e, const std::vector<rsp_shard*>& shards, CompactMode mode, CompactPlan* plan) {
   Arena& a = e->arena;
   for (rsp_shard* s : shards) {
-    const bool has_mem = s->h.mt_count > 0;
-    const size_t n_merged = pick_merge_set(e, s, has_mem, force_full);
+    const bool has_mem = mode != COMPACT_MERGE && s->h.mt_count > 0;
+    size_t n_merged = 0;
+    const size_t avail = unpinned_runs(s);
+    if (mode == COMPACT_FULL) n_merged = s->runs.size();  // (the caller waited for the shard's background merge)
+    else if (mode == COMPACT_MERGE) {
+      if (s->merging || s->runs.size() < e->cfg.l0_compaction_trigger) continue;
+      n_merged = tiered_set(s, 0, s->runs.size(), false);
+      if (n_merged < 2) continue;
+    } else if (mode == COMPACT_FLUSH) {
+      const bool table_full = s->runs.size() + 1 > RSP_MAX_RUNS - 1;
+      if (!e->bg_compaction) {
+        if (s->runs.size() + (has_mem ? 1 : 0) >= e->cfg.l0_compaction_trigger || table_full)
+          n_merged = tiered_set(s, has_mem ? (u64)s->h.mt_tail * 16 : 0, avail, table_full);
+      } else if (table_full) {
+        // merges belong to the background thread; the foreground only merges when the run table itself fills up
+        n_merged = tiered_set(s, has_mem ? (u64)s->h.mt_tail * 16 : 0, avail, true);
+      }
+    }
+    // the run table must never overflow: if the flush would, everything is merged right here (a background merge of
+    // some of these runs then finds its sources gone at install time and drops its output)
+    if (mode == COMPACT_FLUSH && has_mem && s->runs.size() - n_merged + 1 > RSP_MAX_RUNS) n_merged = s->runs.size();
     const bool full = n_merged == s->runs.size();
     if (!has_mem && n_merged <= 1) {
       // nothing to flush; a single run is already fully compacted unless it holds tombstones
-      if (!(force_full && s->runs.size() == 1)) continue;
+      if (!(mode == COMPACT_FULL && s->runs.size() == 1)) continue;
     }
     CompactJob j;
     memset(&j, 0, sizeof(j));
-    JobHost h{s, full, n_merged, {}, 0, 0, 0, 0, 0};
+    JobHost h{s, s->index, s->uid, full, has_mem, n_merged, {}, 0, 0, 0, 0, 0};
     u32 ns = 0;
     if (has_mem) {
       j.src_heap[ns] = s->h.mt_heap; j.src_ent_off[ns] = s->h.mt_ent_off; j.src_n[ns] = s->h.mt_count;
@@ -472,7 +528,7 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
     j.n_items = (u32)n;
     j.items_len = (u32)at;
     j.n_tiles = ns > 1 ? (u32)((n + MERGE_TILE - 1) / MERGE_TILE) : 0;
-    j.bottom = full ? 1 : 0;
+    j.bottom = (full && mode != COMPACT_SNAPSHOT) ? 1 : 0;
     j.merge_op = s->opts.merge_op;
     h.items_b = (size_t)std::max<u32>(1, j.items_len) * sizeof(SortItem);
     h.items2_b = ns > 1 ? (size_t)std::max<u32>(1, j.n_items) * sizeof(SortItem) : 0;
@@ -488,25 +544,34 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
     j.out_ord = (u32*)a.alloc(h.keep_b);
     j.fold_val = (u64*)a.alloc(h.fold_b);
     j.totals = (u32*)a.alloc(32);
-    jh.push_back(h);
-    jobs.push_back(j);
+    if (mode == COMPACT_MERGE) {
+      s->merging = true;
+      s->bg_first_pinned = h.srcs.front().get();
+    }
+    plan->jh.push_back(h);
+    plan->jobs.push_back(j);
   }
-  if (jobs.empty()) return;
-  wait_readers(e);
+}
+
+// ---- run (no engine mutex needed: sources are pinned, outputs are private until installed) -----------------
+static void run_jobs(rsp_engine* e, CompactPlan* plan, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+  Arena& a = e->arena;
+  std::vector<CompactJob>& jobs = plan->jobs;
   const u32 nj = (u32)jobs.size();
-  CompactJob* d_jobs = (CompactJob*)a.alloc(sizeof(CompactJob) * nj);
-  CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CompactJob) * nj, cudaMemcpyHostToDevice, e->st));
-  CUDA_OK(cudaEventRecord(e->ev0, e->st));
-  launch_compact_sort(d_jobs, jobs.data(), nj, e->st);
-  launch_compact_size(d_jobs, nj, e->st);
+  plan->d_jobs = (CompactJob*)a.alloc(sizeof(CompactJob) * nj);
+  CompactJob* d_jobs = plan->d_jobs;
+  CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CompactJob) * nj, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaEventRecord(ev0, st));
+  launch_compact_sort(d_jobs, jobs.data(), nj, st);
+  launch_compact_size(d_jobs, nj, st);
   CUDA_OK(cudaGetLastError());  // a refused launch (e.g. shared-memory opt-in) must not pass as an unsorted run
   e->launches += 5;
   std::vector<u32> totals(8 * nj);
   for (u32 i = 0; i < nj; i++)
-    CUDA_OK(cudaMemcpyAsync(&totals[8 * i], jobs[i].totals, 32, cudaMemcpyDeviceToHost, e->st));
-  CUDA_OK(cudaStreamSynchronize(e->st));
+    CUDA_OK(cudaMemcpyAsync(&totals[8 * i], jobs[i].totals, 32, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
   u32 max_items = 0;
-  std::vector<std::shared_ptr<Run>> outs(nj);
+  plan->outs.resize(nj);
   for (u32 i = 0; i < nj; i++) {
     CompactJob& j = jobs[i];
     const u32 units = totals[8 * i], ents = totals[8 * i + 1], uni = totals[8 * i + 2], keys = totals[8 * i + 3];
@@ -525,54 +590,176 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
     r->ent_off = (u32*)a.alloc((size_t)ents * 4);
     r->hslots = (u32*)a.alloc((size_t)r->n_buckets * RUN_BUCKET_SLOTS * 4);
     r->blk_pfx = (u64*)a.alloc(blk_pfx_bytes(r->n_blocks));
-    CUDA_OK(cudaMemsetAsync(r->hslots, 0, (size_t)r->n_buckets * RUN_BUCKET_SLOTS * 4, e->st));
+    CUDA_OK(cudaMemsetAsync(r->hslots, 0, (size_t)r->n_buckets * RUN_BUCKET_SLOTS * 4, st));
     j.out_heap = r->heap; j.out_ent_off = r->ent_off; j.out_hslots = r->hslots; j.out_blk_pfx = r->blk_pfx;
     j.out_n_buckets = r->n_buckets; j.out_ord_bits = r->ord_bits;
-    outs[i] = r;
+    plan->outs[i] = r;
     max_items = std::max(max_items, j.n_items);
   }
-  CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CompactJob) * nj, cudaMemcpyHostToDevice, e->st));
-  launch_compact_write(d_jobs, nj, max_items, e->st);
+  CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CompactJob) * nj, cudaMemcpyHostToDevice, st));
+  launch_compact_write(d_jobs, nj, max_items, st);
   CUDA_OK(cudaGetLastError());
   e->launches += 1;
-  CUDA_OK(cudaEventRecord(e->ev1, e->st));
-  // install
+  CUDA_OK(cudaEventRecord(ev1, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&plan->ms, ev0, ev1);
+}
+
+static void release_work(rsp_engine* e, CompactPlan* plan) {
+  Arena& a = e->arena;
+  for (size_t i = 0; i < plan->jobs.size(); i++) {
+    const CompactJob& j = plan->jobs[i];
+    const JobHost& h = plan->jh[i];
+    a.release(j.items, h.items_b);
+    if (j.items2) a.release(j.items2, h.items2_b);
+    if (j.coranks) a.release(j.coranks, h.coranks_b);
+    a.release(j.keep_units, h.keep_b);
+    a.release(j.out_pos, h.keep_b);
+    a.release(j.out_ord, h.keep_b);
+    a.release(j.fold_val, h.fold_b);
+    a.release(j.totals, 32);
+  }
+  if (plan->d_jobs) a.release(plan->d_jobs, sizeof(CompactJob) * plan->jobs.size());
+  plan->d_jobs = nullptr;
+}
+
+// ---- install (engine mutex held): the new run takes the place of its sources in the shard's run list; readers keep
+// the old descriptors until this point and the old runs live until every reader launched before it has finished
+static void install_jobs(rsp_engine* e, CompactPlan* plan, CompactMode mode) {
+  const u32 nj = (u32)plan->jobs.size();
+  if (mode == COMPACT_MERGE) wait_readers(e);  // (the foreground path did this before it touched a memtable)
   for (u32 i = 0; i < nj; i++) {
-    rsp_shard* s = jh[i].s;
+    JobHost& h = plan->jh[i];
+    rsp_shard* s = h.s;
+    if (mode == COMPACT_MERGE) {
+      // the shard may have been closed, or its runs merged by a foreground CompactRange, while the kernels ran: the
+      // output is only installed over exactly the sources it was built from
+      const bool alive = h.index < e->slots.size() && e->slots[h.index] == s && s->uid == h.uid;
+      if (!alive) { h.s = nullptr; continue; }
+      size_t at = 0;
+      while (at < s->runs.size() && s->runs[at].get() != h.srcs.front().get()) at++;
+      bool intact = at + h.n_merged <= s->runs.size();
+      for (size_t k = 0; intact && k < h.n_merged; k++) intact = s->runs[at + k].get() == h.srcs[k].get();
+      s->merging = false;
+      s->bg_first_pinned = nullptr;
+      if (!intact) { h.s = nullptr; continue; }
+    }
     u64 read_b = 0;
-    if (s->h.mt_count) read_b += (u64)s->h.mt_tail * 16;
-    for (auto& r : jh[i].srcs) read_b += r->bytes();
+    if (h.has_mem) read_b += (u64)s->h.mt_tail * 16;
+    for (auto& r : h.srcs) read_b += r->bytes();
     s->stats.compaction_bytes_read += read_b;
-    s->stats.compaction_bytes_written += outs[i]->bytes();
-    if (s->h.mt_count) s->stats.flushes++;
-    if (jh[i].n_merged) { s->stats.compactions++; s->runs.erase(s->runs.begin(), s->runs.begin() + jh[i].n_merged); }
-    if (outs[i]->n_ent) s->runs.insert(s->runs.begin(), outs[i]);
-    if (s->h.mt_count) {
+    s->stats.compaction_bytes_written += plan->outs[i]->bytes();
+    if (h.has_mem) s->stats.flushes++;
+    // the sources sit where they were planned, possibly behind runs that were flushed meanwhile (background merges)
+    size_t at = 0;
+    if (h.n_merged) {
+      while (at < s->runs.size() && s->runs[at].get() != h.srcs.front().get()) at++;
+      s->stats.compactions++;
+      s->runs.erase(s->runs.begin() + at, s->runs.begin() + at + h.n_merged);
+    }
+    if (plan->outs[i]->n_ent) s->runs.insert(s->runs.begin() + at, plan->outs[i]);
+    if (h.has_mem) {
       s->h.mt_tail = 0;
       s->h.mt_count = 0;
       CUDA_OK(cudaMemsetAsync(s->h.mt_slots, 0, s->mt_slot_bytes, e->st));
     }
-    upload_shard(e, s);
+    upload_shard(e, s, mode == COMPACT_MERGE);
   }
   note_mutation(e);
   CUDA_OK(cudaStreamSynchronize(e->st));  // sources may be released once nothing reads them
-  float ms = 0;
-  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
-  e->last_ms["compact"] = ms;
-  e->last_ms["compact_total"] += ms;  // kernels of every flush / merge so far (sizing round trip included)
+  e->last_ms["compact"] = plan->ms;
+  e->last_ms["compact_total"] += plan->ms;  // kernels of every flush / merge so far (sizing round trip included)
   for (u32 i = 0; i < nj; i++) {
-    a.release(jobs[i].items, jh[i].items_b);
-    if (jobs[i].items2) a.release(jobs[i].items2, jh[i].items2_b);
-    if (jobs[i].coranks) a.release(jobs[i].coranks, jh[i].coranks_b);
-    a.release(jobs[i].keep_units, jh[i].keep_b);
-    a.release(jobs[i].out_pos, jh[i].keep_b);
-    a.release(jobs[i].out_ord, jh[i].keep_b);
-    a.release(jobs[i].fold_val, jh[i].fold_b);
-    a.release(jobs[i].totals, 32);
+    rsp_shard* s = plan->jh[i].s;
+    if (s && e->bg_compaction && s->runs.size() >= e->cfg.l0_compaction_trigger && !s->merging) bg_request(e, s);
   }
-  a.release(d_jobs, sizeof(CompactJob) * nj);
 }
 
+// foreground flush / full compaction of a set of shards in one batched pass (engine mutex held throughout)
+static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards, bool force_full) {
+  CompactPlan plan;
+  const CompactMode mode = force_full ? COMPACT_FULL : COMPACT_FLUSH;
+  plan_jobs(e, shards, mode, &plan);
+  if (plan.jobs.empty()) return;
+  wait_readers(e);
+  run_jobs(e, &plan, e->st, e->ev0, e->ev1);
+  install_jobs(e, &plan, mode);
+  release_work(e, &plan);
+}
+
+// the memtable's contents as a private sorted run (an iterator's snapshot): nothing about the shard changes
+static std::shared_ptr<Run> snapshot_memtable(rsp_engine* e, rsp_shard* s) {
+  CompactPlan plan;
+  plan_jobs(e, {s}, COMPACT_SNAPSHOT, &plan);
+  if (plan.jobs.empty()) return nullptr;
+  run_jobs(e, &plan, e->st, e->ev0, e->ev1);
+  release_work(e, &plan);
+  s->stats.compaction_bytes_read += (u64)s->h.mt_tail * 16;
+  return plan.outs[0]->n_ent ? plan.outs[0] : nullptr;
+}
+
+// ---- background merges ------------------------------------------------------------------------------------
+// Flushes stay on the apply path (they are what makes room in a memtable); merging sorted runs is deferred to this
+// thread: planned and installed under the engine mutex, but its kernels run on their own stream with the mutex
+// released, so applies and reads go on while runs are merged (readers keep the old run set until the install).
+struct Compactor {
+  rsp_engine* e = nullptr;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<rsp_shard*> pending;
+  bool stop = false, busy = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::thread th;
+  void loop();
+};
+static void bg_request(rsp_engine* e, rsp_shard* s) {
+  Compactor* c = e->compactor;
+  if (!c) return;
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    if (std::find(c->pending.begin(), c->pending.end(), s) == c->pending.end()) c->pending.push_back(s);
+  }
+  c->cv.notify_one();
+}
+void Compactor::loop() {
+  cudaSetDevice(e->device);
+  for (;;) {
+    std::vector<rsp_shard*> take;
+    {
+      std::unique_lock<std::mutex> l(mu);
+      busy = false;
+      cv.notify_all();
+      cv.wait(l, [this] { return stop || !pending.empty(); });
+      if (stop) return;
+      take.swap(pending);
+      busy = true;
+    }
+    CompactPlan plan;
+    try {
+      {
+        std::lock_guard<std::mutex> g(e->mu);
+        std::vector<rsp_shard*> live;
+        for (rsp_shard* s : take)
+          if (std::find(e->slots.begin(), e->slots.end(), s) != e->slots.end()) live.push_back(s);
+        plan_jobs(e, live, COMPACT_MERGE, &plan);
+      }
+      if (plan.jobs.empty()) continue;
+      run_jobs(e, &plan, stream, ev0, ev1);
+      {
+        std::lock_guard<std::mutex> g(e->mu);
+        cudaSetDevice(e->device);
+        install_jobs(e, &plan, COMPACT_MERGE);
+      }
+      release_work(e, &plan);
+    } catch (...) {
+      abi_caught();  // a CUDA failure: recorded; the shards keep their runs
+      std::lock_guard<std::mutex> g(e->mu);
+      for (JobHost& h : plan.jh)
+        if (h.s && h.index < e->slots.size() && e->slots[h.index] == h.s && h.s->uid == h.uid) { h.s->merging = false; h.s->bg_first_pinned = nullptr; }
+    }
+  }
+}
 // ------------------------------------------------------------------------------------------------
 // apply path
 // ------------------------------------------------------------------------------------------------
@@ -765,6 +952,10 @@ static void unreserve(const rsp_staged* sg) {
   }
   sg->reserved = false;
 }
+
+// pre-staged ticks launched on the device whose results are not folded into the host mirror yet: maintenance that
+// rewrites the memtable from the mirror must not run now (the caller folds them first: rsp_apply_staged_finish)
+static inline bool ticks_in_flight(const rsp_shard* s) { return s->inflight_units != 0 || s->inflight_ents != 0; }
 
 // Make room for the tick's upper bounds.  Returns 1 when memtables were flushed or re-sized (work on the engine
 // stream), 0 when nothing had to be done, -1 when a shard is full while earlier ticks are still in flight (their
@@ -1696,6 +1887,7 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   e->stage_threads = 2;
   if (const char* t = getenv("RSP_STAGE_THREADS")) e->stage_threads = (size_t)std::max(1, atoi(t));
   if (const char* t = getenv("RSP_FUSED_TICK")) e->fused_ticks = atoi(t) != 0;
+  if (const char* t = getenv("RSP_BG_COMPACT")) e->bg_compaction = atoi(t) != 0;
   CUDA_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   for (int k = 0; k < 3; k++) {
     CUDA_OK(cudaStreamCreateWithFlags(&e->cs[k], cudaStreamNonBlocking));
@@ -1713,6 +1905,15 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
     CUDA_OK(cudaMemset(e->d_fast, 0, sizeof(ShardFast) * n_fast));
     e->d_fast_runs = e->d_fast + e->cfg.max_shards;
   }
+  if (e->bg_compaction) {
+    Compactor* c = new Compactor();
+    c->e = e;
+    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreate(&c->ev0));
+    CUDA_OK(cudaEventCreate(&c->ev1));
+    e->compactor = c;
+    c->th = std::thread([c] { c->loop(); });
+  }
   *out = e;
   return RSP_OK;
   } catch (...) { return abi_caught(); }
@@ -1720,6 +1921,21 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
 
 void rsp_engine_destroy(rsp_engine* e) {
   if (!e) return;
+  if (Compactor* c = e->compactor) {  // let a merge in flight finish, then stop the thread
+    {
+      std::lock_guard<std::mutex> g(c->mu);
+      c->stop = true;
+      c->pending.clear();
+    }
+    c->cv.notify_all();
+    if (c->th.joinable()) c->th.join();
+    cudaSetDevice(e->device);
+    cudaStreamDestroy(c->stream);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    delete c;
+    e->compactor = nullptr;
+  }
   if (e->read_comb) { e->read_comb->destroy(); delete e->read_comb; }
   if (e->apply_comb) { e->apply_comb->destroy(); delete e->apply_comb; }
   cudaSetDevice(e->device);
@@ -1748,6 +1964,8 @@ static int shard_open_locked(rsp_engine* e, const char* name, const rsp_shard_op
   if (ix >= e->cfg.max_shards) return RSP_BUSY;
   if (ix == e->slots.size()) e->slots.push_back(nullptr);
   rsp_shard* s = new rsp_shard();
+  static std::atomic<u64> next_uid{1};
+  s->uid = next_uid++;
   s->eng = e; s->name = name; s->index = ix;
   memset(&s->opts, 0, sizeof(s->opts));
   if (opts) s->opts = *opts;
@@ -1796,6 +2014,7 @@ int rsp_shard_close(rsp_shard* s) {
   if (!s) return RSP_INVALID_ARGUMENT;
   rsp_engine* e = s->eng;
   std::lock_guard<std::mutex> g(e->mu);
+  if (ticks_in_flight(s)) return RSP_BUSY;
   CUDA_OK(cudaSetDevice(e->device));
   shard_close_locked(s);
   return RSP_OK;
@@ -1838,6 +2057,7 @@ int rsp_ingest_sorted(rsp_shard* s, size_t n, const uint8_t* keys, const uint64_
     if (c > 0 || (c == 0 && al >= bl)) { set_err(s, "Invalid argument: Keys must be added in order"); return RSP_INVALID_ARGUMENT; }
   }
   if (s->latch) return (int)(s->latch >> 8);
+  if (ticks_in_flight(s)) return RSP_BUSY;
   // everything the shard holds must be in runs before ranges are compared
   if (s->h.mt_count) compact_shards(e, {s}, false);
   if (s->runs.size() + 1 > RSP_MAX_RUNS) compact_shards(e, {s}, true);
@@ -2242,6 +2462,7 @@ int rsp_flush(rsp_shard* s) {
   if (!s) return RSP_INVALID_ARGUMENT;
   rsp_engine* e = s->eng;
   std::lock_guard<std::mutex> g(e->mu);
+  if (ticks_in_flight(s)) return RSP_BUSY;
   CUDA_OK(cudaSetDevice(e->device));
   compact_shards(e, {s}, false);
   return RSP_OK;
@@ -2252,6 +2473,7 @@ int rsp_compact(rsp_shard* s) {
   if (!s) return RSP_INVALID_ARGUMENT;
   rsp_engine* e = s->eng;
   std::lock_guard<std::mutex> g(e->mu);
+  if (ticks_in_flight(s)) return RSP_BUSY;
   CUDA_OK(cudaSetDevice(e->device));
   compact_shards(e, {s}, true);
   return RSP_OK;
@@ -2262,6 +2484,7 @@ static int all_shards(rsp_engine* e, bool full) {
   CUDA_OK(cudaSetDevice(e->device));
   std::vector<rsp_shard*> v;
   for (rsp_shard* s : e->slots) if (s) v.push_back(s);
+  for (rsp_shard* s : v) if (ticks_in_flight(s)) return RSP_BUSY;
   // bounded batches keep the work buffers modest
   for (size_t i = 0; i < v.size(); i += 256) {
     std::vector<rsp_shard*> part(v.begin() + i, v.begin() + std::min(v.size(), i + 256));
@@ -2301,13 +2524,24 @@ rsp_iter* rsp_iter_create(rsp_shard* s) {
   try {
   if (!s) return nullptr;
   rsp_engine* e = s->eng;
+  std::lock_guard<std::mutex> g(e->mu);
+  if (ticks_in_flight(s)) return nullptr;  // fold the pre-staged ticks first (rsp_apply_staged_finish)
   rsp_iter* it = new rsp_iter();
   it->s = s;
-  std::lock_guard<std::mutex> g(e->mu);
   CUDA_OK(cudaSetDevice(e->device));
-  // the memtable is unordered: freeze it into a sorted run, then pin the run set (the iterator's snapshot)
-  if (s->h.mt_count) compact_shards(e, {s}, false);
-  it->pinned = s->runs;
+  // The memtable is unordered: its contents are sorted into a PRIVATE run (the same kernels as a flush), which the
+  // iterator pins in front of the shard's runs.  The shard itself is not touched: no new run, no compaction trigger,
+  // writers go on filling the same memtable (RocksDB: an iterator pins the memtable and the current version).
+  if (s->h.mt_count) {
+    wait_readers(e);
+    if (auto snap = snapshot_memtable(e, s)) it->pinned.push_back(snap);
+  }
+  it->pinned.insert(it->pinned.end(), s->runs.begin(), s->runs.end());
+  if (it->pinned.size() > RSP_MAX_RUNS) {  // the view has room for RSP_MAX_RUNS runs: fold the memtable in after all
+    it->pinned.clear();
+    compact_shards(e, {s}, false);
+    it->pinned = s->runs;
+  }
   ScanView v;
   memset(&v, 0, sizeof(v));
   v.n_runs = (u32)it->pinned.size();
@@ -2405,6 +2639,7 @@ int rsp_multi_scan(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint
   for (size_t i = 0; i < n; i++) {
     if (shard_ix[i] >= e->slots.size() || !e->slots[shard_ix[i]]) return RSP_INVALID_ARGUMENT;
     rsp_shard* s = e->slots[shard_ix[i]];
+    if (ticks_in_flight(s)) return RSP_BUSY;
     if (s->h.mt_count && std::find(fl.begin(), fl.end(), s) == fl.end()) fl.push_back(s);
   }
   if (!fl.empty()) compact_shards(e, fl, false);
