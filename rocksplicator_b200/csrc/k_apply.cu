@@ -77,6 +77,32 @@ __device__ __forceinline__ WalkResult walk_batch(Cursor c, Sink&& sink) {
   bool range_del = false;
   if (c.len < 12) return WalkResult{mk_status(2, MSG_TOO_SMALL), 0u, 0u};
   const u32 count = cur_byte(c, 8) | (cur_byte(c, 9) << 8) | (cur_byte(c, 10) << 16) | (cur_byte(c, 11) << 24);
+  // Fast path for the unit of the replication stream: ONE Put with a short key, followed only by 8-byte LogData
+  // records (the leader's timestamp, the follower's).  Exactly what the general walk below finds for such bytes —
+  // anything else (other tags, long keys, trailing garbage) takes the general walk.
+  if (count == 1 && c.len >= 16 && cur_byte(c, 12) == kTypeValue) {
+    const u32 kl = cur_byte(c, 13);
+    const u32 p = 14u + kl;
+    if (kl < 128u && p < c.len) {
+      const u32 b0 = cur_byte(c, p);
+      u32 vl = b0, nb = 1;
+      bool ok = true;
+      if (b0 >= 128u) {
+        const u32 b1 = p + 1 < c.len ? cur_byte(c, p + 1) : 255u;
+        ok = b1 < 128u;
+        vl = (b0 & 127u) | (b1 << 7);
+        nb = 2;
+      }
+      const u32 vo = p + nb;
+      if (ok && vo <= c.len && c.len - vo >= vl && (c.len - vo - vl) % 10u == 0) {
+        for (u32 q = vo + vl; q < c.len; q += 10u) ok = ok && cur_byte(c, q) == kTypeLogData && cur_byte(c, q + 1) == 8u;
+        if (ok) {
+          sink((u32)kTypeValue, 14u, kl, vo, vl, 0u, 0u);
+          return WalkResult{0u, 1u, entry_units(kTypeValue, kl, vl, true)};
+        }
+      }
+    }
+  }
   c.pos = 12;
   while (c.pos < c.len && status == 0) {
     const u32 tag = cur_byte(c, c.pos);
