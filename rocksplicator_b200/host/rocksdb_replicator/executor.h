@@ -2,6 +2,10 @@
 // folly CPUThreadPoolExecutor "rptor-worker-" (rocksdb_replicator/rocksdb_replicator.cpp:58-67) and for
 // the EventBase::runAfterDelay / futures::sleep calls on the replication path (replicated_db.cpp:412-428,
 // non_blocking_condition_variable.h:113-126).
+//
+// Every worker owns a queue (its own mutex and condition variable); add() deals tasks round-robin and an idle worker
+// steals from the others before it sleeps.  With one shared queue the pull loops of a thousand shards — three short
+// tasks per ReplicateResponse — serialise on that queue's mutex long before the workers are busy.
 #pragma once
 #include <atomic>
 #include <chrono>
@@ -9,6 +13,7 @@
 #include <deque>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -17,60 +22,101 @@ namespace replicator {
 
 class Executor {
  public:
-  explicit Executor(size_t n_threads) {
-    for (size_t i = 0; i < n_threads; i++) workers_.emplace_back([this] { WorkLoop(); });
+  explicit Executor(size_t n_threads) : n_(n_threads ? n_threads : 1) {
+    for (size_t i = 0; i < n_; i++) q_.emplace_back(new Queue());
+    for (size_t i = 0; i < n_; i++) workers_.emplace_back([this, i] { WorkLoop(i); });
     timer_ = std::thread([this] { TimerLoop(); });
   }
   ~Executor() { Stop(); }
   void add(std::function<void()> f) {
+    if (stop_.load(std::memory_order_acquire)) return;
+    Queue& q = *q_[next_.fetch_add(1, std::memory_order_relaxed) % n_];
     {
-      std::lock_guard<std::mutex> g(mu_);
-      if (stop_) return;
-      q_.push_back(std::move(f));
+      std::lock_guard<std::mutex> g(q.mu);
+      q.tasks.push_back(std::move(f));
     }
-    cv_.notify_one();
+    queued_.fetch_add(1, std::memory_order_release);
+    if (q.sleeping.load(std::memory_order_acquire)) q.cv.notify_one();
+    else if (sleepers_.load(std::memory_order_acquire)) WakeOne();  // its owner is busy: let an idle worker steal it
   }
   // run f on the pool after delay_ms
   void addDelayed(std::function<void()> f, uint64_t delay_ms) {
     const auto when = std::chrono::steady_clock::now() + std::chrono::milliseconds(delay_ms);
     {
       std::lock_guard<std::mutex> g(tmu_);
-      if (stop_) return;
+      if (stop_.load()) return;
       timed_.emplace(when, std::move(f));
     }
     tcv_.notify_one();
   }
   void Stop() {
-    {
-      std::lock_guard<std::mutex> g(mu_);
-      std::lock_guard<std::mutex> g2(tmu_);
-      if (stop_) return;
-      stop_ = true;
+    if (stop_.exchange(true)) return;
+    for (auto& q : q_) {
+      std::lock_guard<std::mutex> g(q->mu);
+      q->cv.notify_all();
     }
-    cv_.notify_all();
-    tcv_.notify_all();
+    {
+      std::lock_guard<std::mutex> g(tmu_);
+      tcv_.notify_all();
+    }
     for (auto& t : workers_) t.join();
     timer_.join();
   }
 
  private:
-  void WorkLoop() {
+  struct Queue {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> tasks;
+    std::atomic<bool> sleeping{false};
+  };
+  bool Pop(Queue& q, std::function<void()>* f, bool try_only) {
+    std::unique_lock<std::mutex> l(q.mu, std::defer_lock);
+    if (try_only) {
+      if (!l.try_lock()) return false;
+    } else {
+      l.lock();
+    }
+    if (q.tasks.empty()) return false;
+    *f = std::move(q.tasks.front());
+    q.tasks.pop_front();
+    return true;
+  }
+  void WakeOne() {
+    for (auto& q : q_)
+      if (q->sleeping.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> g(q->mu);
+        q->cv.notify_one();
+        return;
+      }
+  }
+  void WorkLoop(size_t me) {
+    Queue& mine = *q_[me];
     for (;;) {
       std::function<void()> f;
-      {
-        std::unique_lock<std::mutex> l(mu_);
-        cv_.wait(l, [this] { return stop_ || !q_.empty(); });
-        if (stop_) return;
-        f = std::move(q_.front());
-        q_.pop_front();
+      bool got = Pop(mine, &f, false);
+      for (size_t k = 1; !got && k < n_ && queued_.load(std::memory_order_acquire) > 0; k++) got = Pop(*q_[(me + k) % n_], &f, true);
+      if (got) {
+        queued_.fetch_sub(1, std::memory_order_acq_rel);
+        f();
+        continue;
       }
-      f();
+      std::unique_lock<std::mutex> l(mine.mu);
+      if (stop_.load(std::memory_order_acquire)) return;
+      if (!mine.tasks.empty()) continue;
+      mine.sleeping.store(true, std::memory_order_release);
+      sleepers_.fetch_add(1, std::memory_order_acq_rel);
+      // (a bounded sleep: a task dealt to a busy worker's queue is found by the next idle worker at the latest then)
+      if (queued_.load(std::memory_order_acquire) == 0) mine.cv.wait_for(l, std::chrono::milliseconds(2));
+      sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+      mine.sleeping.store(false, std::memory_order_release);
+      if (stop_.load(std::memory_order_acquire) && mine.tasks.empty()) return;
     }
   }
   void TimerLoop() {
     std::unique_lock<std::mutex> l(tmu_);
     for (;;) {
-      if (stop_) return;
+      if (stop_.load()) return;
       if (timed_.empty()) {
         tcv_.wait(l);
         continue;
@@ -87,13 +133,17 @@ class Executor {
       l.lock();
     }
   }
-  std::mutex mu_, tmu_;
-  std::condition_variable cv_, tcv_;
-  std::deque<std::function<void()>> q_;
+  const size_t n_;
+  std::vector<std::unique_ptr<Queue>> q_;
+  std::atomic<size_t> next_{0};
+  std::atomic<int64_t> queued_{0};
+  std::atomic<int> sleepers_{0};
+  std::atomic<bool> stop_{false};
+  std::mutex tmu_;
+  std::condition_variable tcv_;
   std::multimap<std::chrono::steady_clock::time_point, std::function<void()>> timed_;
   std::vector<std::thread> workers_;
   std::thread timer_;
-  bool stop_ = false;
 };
 
 }  // namespace replicator
