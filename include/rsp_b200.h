@@ -136,6 +136,10 @@ int rsp_apply_updates(rsp_shard* s, size_t n, const rsp_slice* batches, const ui
 
 /* RocksDbWrapper::LatestSequenceNumber (rocksdb_wrapper.cpp:4) */
 uint64_t rsp_latest_seq(const rsp_shard* s);
+/* Restore from a backup (rocksdb_admin/admin_handler.cpp:768-860 restoreDBHelper): after the saved contents have been
+ * ingested, the shard continues at the sequence number the backup was taken at, so that it resumes pulling from its
+ * upstream where the backed-up replica stood.  Only forwards; InvalidArgument otherwise. */
+int rsp_set_latest_seq(rsp_shard* s, uint64_t seq);
 /* text of the last non-OK status on this shard ("Corruption: bad WriteBatch Put" ...) */
 size_t rsp_last_error(const rsp_shard* s, char* buf, size_t cap);
 

@@ -2138,6 +2138,24 @@ uint32_t rsp_shard_index(const rsp_shard* s) { return s->index; }
 const char* rsp_shard_name(const rsp_shard* s) { return s->name.c_str(); }
 uint64_t rsp_latest_seq(const rsp_shard* s) { return s->last_seq.load(std::memory_order_acquire); }
 
+int rsp_set_latest_seq(rsp_shard* s, uint64_t seq) {
+  try {
+  if (!s) return RSP_INVALID_ARGUMENT;
+  rsp_engine* e = s->eng;
+  std::lock_guard<std::mutex> g(e->mu);
+  if (ticks_in_flight(s)) return RSP_BUSY;
+  if (seq < s->last_seq.load()) return RSP_INVALID_ARGUMENT;
+  CUDA_OK(cudaSetDevice(e->device));
+  s->h.last_seq = seq;
+  s->h.pub_seq = seq;
+  s->last_seq.store(seq, std::memory_order_release);
+  upload_shard(e, s);
+  note_mutation(e);
+  CUDA_OK(cudaStreamSynchronize(e->st));
+  return RSP_OK;
+  } catch (...) { return abi_caught(); }
+}
+
 size_t rsp_last_error(const rsp_shard* s, char* buf, size_t cap) {
   try {
   rsp_shard* m = const_cast<rsp_shard*>(s);

@@ -359,7 +359,14 @@ __device__ __noinline__ void link_into_table(ShardDev* sd, u8* heap, u8* ent, u3
   const u32 P = unit + 1u;
   u32* my_link = reinterpret_cast<u32*>(ent + 16);
   u32 idx = (u32)h & mask;
-  for (;;) {
+  // The probe is bounded by the table size.  The reservation keeps the table at most half full, so the bound is never
+  // reached; if it ever were (a table without a free slot), the entry stays unreachable and the shard latches an
+  // IOError instead of the kernel spinning forever.
+  for (u32 probes = 0;; probes++) {
+    if (probes > mask) {
+      atomicCAS(&sd->latch, 0u, mk_status(5, MSG_TOO_LARGE));
+      return;
+    }
     u64 cur = ld_cg_u64(slots + idx);
     if (cur == 0) {
       const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(slots + idx), 0ull, ((u64)tag << 32) | P);

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256) k_compact_write(const CompactJob* jobs) {
     const u64 h = hash_key_padded(x.key, x.klen);
     const u32 val = (((u32)(h >> 32) >> j.out_ord_bits) << j.out_ord_bits) | (ord + 1u);
     u32 bucket = (u32)(((u64)(u32)h * j.out_n_buckets) >> 32);
-    for (;;) {
+    for (u32 tries = 0; tries <= j.out_n_buckets; tries++) {  // (load <= 0.5: a free slot exists; bounded anyway)
       u32* b = j.out_hslots + (u64)bucket * RUN_BUCKET_SLOTS;
       bool placed = false;
       for (u32 s = 0; s < RUN_BUCKET_SLOTS && !placed; s++) {

@@ -65,6 +65,7 @@ EXPORTS = {
     "rsp_router_apply_many": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
     "rsp_latest_seq": (C.c_uint64, [C.c_void_p]),
+    "rsp_set_latest_seq": (C.c_int, [C.c_void_p, C.c_uint64]),
     "rsp_last_error": (C.c_size_t, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "rsp_get": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "rsp_multi_get": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -185,6 +185,110 @@ Status GpuDB::ExportSstFile(const std::string& path, uint64_t* entries) {
   return Status::OK();
 }
 
+Status GpuDB::Backup(const std::string& dir, uint64_t* seq_out) {
+  // contents and sequence number must belong together: writers are held off for the export
+  std::lock_guard<std::mutex> g(write_mu_);
+  const uint64_t seq = GetLatestSequenceNumber();
+  const std::string mk = "mkdir -p '" + dir + "'";
+  if (system(mk.c_str()) != 0) return Status::IOError("cannot create " + dir);
+  uint64_t entries = 0;
+  const std::string tmp_sst = dir + "/data.sst.tmp", tmp_meta = dir + "/dbmeta.tmp";
+  Status st = ExportSstFile(tmp_sst, &entries);
+  const bool empty = !st.ok() && st.IsInvalidArgument();  // "nothing to export": an empty shard is a valid backup
+  if (!st.ok() && !empty) return st;
+  if (empty) remove(tmp_sst.c_str());
+  FILE* f = fopen(tmp_meta.c_str(), "wb");
+  if (!f) return Status::IOError("While open a file for appending: " + tmp_meta);
+  fprintf(f, "db_name=%s\nseq_no=%llu\nentries=%llu\nfile=%s\n", name_.c_str(), (unsigned long long)seq,
+          (unsigned long long)entries, empty ? "" : "data.sst");
+  if (fclose(f) != 0) return Status::IOError("While appending to file: " + tmp_meta);
+  if (!empty && rename(tmp_sst.c_str(), (dir + "/data.sst").c_str()) != 0) return Status::IOError("rename " + tmp_sst);
+  if (empty) remove((dir + "/data.sst").c_str());
+  if (rename(tmp_meta.c_str(), (dir + "/dbmeta").c_str()) != 0) return Status::IOError("rename " + tmp_meta);
+  if (seq_out) *seq_out = seq;
+  return Status::OK();
+}
+
+Status GpuDB::Restore(const rocksdb::Options& options, const std::string& name, const std::string& dir, rocksdb::DB** dbptr,
+                      int device) {
+  *dbptr = nullptr;
+  std::string meta;
+  if (!ReadWholeFile(dir + "/dbmeta", &meta)) return Status::IOError("While opening a file for sequentially reading: " + dir + "/dbmeta");
+  auto field = [&](const std::string& key) {
+    const size_t at = meta.find(key + "=");
+    if (at == std::string::npos) return std::string();
+    const size_t end = meta.find('\n', at);
+    return meta.substr(at + key.size() + 1, end == std::string::npos ? std::string::npos : end - at - key.size() - 1);
+  };
+  if (field("seq_no").empty()) return Status::Corruption("dbmeta without seq_no in " + dir);
+  const uint64_t seq = strtoull(field("seq_no").c_str(), nullptr, 10);
+  rocksdb::DB* raw = nullptr;
+  Status st = Open(options, name, &raw, device);
+  if (!st.ok()) return st;
+  std::unique_ptr<rocksdb::DB> db(raw);
+  auto* gdb = static_cast<GpuDB*>(raw);
+  if (!field("file").empty()) {
+    rocksdb::IngestExternalFileOptions io;
+    io.move_files = false;
+    st = gdb->IngestExternalFile({dir + "/" + field("file")}, io);
+    if (!st.ok()) return st;
+  }
+  const int rc = rsp_set_latest_seq(gdb->shard_, seq);
+  if (rc != RSP_OK) return gdb->ToStatus(rc);
+  *dbptr = db.release();
+  return Status::OK();
+}
+
+BackupScheduler::BackupScheduler(const std::string& root, uint64_t period_ms) : root_(root), period_ms_(period_ms) {
+  th_ = std::thread([this] {
+    std::unique_lock<std::mutex> l(mu_);
+    while (!stop_) {
+      cv_.wait_for(l, std::chrono::milliseconds(period_ms_));
+      if (stop_) break;
+      l.unlock();
+      RunOnce();
+      l.lock();
+    }
+  });
+}
+BackupScheduler::~BackupScheduler() {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  th_.join();
+}
+void BackupScheduler::Add(const std::string& name, std::shared_ptr<rocksdb::DB> db) {
+  std::lock_guard<std::mutex> g(mu_);
+  items_[name].db = std::move(db);
+}
+void BackupScheduler::Remove(const std::string& name) {
+  std::lock_guard<std::mutex> g(mu_);
+  items_.erase(name);
+}
+size_t BackupScheduler::RunOnce() {
+  std::vector<std::pair<std::string, Item>> todo;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    for (auto& kv : items_)
+      if (kv.second.db->GetLatestSequenceNumber() != kv.second.last_seq) todo.push_back(kv);
+  }
+  size_t n = 0;
+  for (auto& kv : todo) {
+    auto* gdb = dynamic_cast<GpuDB*>(kv.second.db.get());
+    if (!gdb) continue;
+    uint64_t seq = 0;
+    if (!gdb->Backup(root_ + "/" + kv.first, &seq).ok()) continue;
+    n++;
+    done_++;
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = items_.find(kv.first);
+    if (it != items_.end()) it->second.last_seq = seq;
+  }
+  return n;
+}
+
 Status GpuDB::ApplyReplicated(const Slice& raw, uint64_t ts) {
   std::lock_guard<std::mutex> g(write_mu_);
   uint64_t seq = 0;

@@ -3,7 +3,10 @@
 // rocksdb_admin/admin_handler.cpp:640.  Host code only: no CUDA types; every data call ends in librsp_b200.so.
 #pragma once
 #include <atomic>
+#include <condition_variable>
 #include <deque>
+#include <map>
+#include <thread>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -52,6 +55,14 @@ class GpuDB : public rocksdb::DB {
   // the shard's visible contents (merges folded, tombstones dropped) as one ingestible block-based SST file: what a
   // backup of a volatile HBM shard is.  Returns the number of entries through *entries when it is not null.
   rocksdb::Status ExportSstFile(const std::string& path, uint64_t* entries = nullptr);
+  // HBM is volatile: a backup is the shard's visible contents as one SST file plus a small "dbmeta" file (name,
+  // sequence number, entry count) in `dir` — the role of BackupEngine::CreateNewBackupWithMetadata in
+  // rocksdb_admin/admin_handler.cpp:696-766.  Written to a temporary name and renamed: a crash leaves the old backup.
+  rocksdb::Status Backup(const std::string& dir, uint64_t* seq_out = nullptr);
+  // restoreDBHelper (admin_handler.cpp:768-860): a fresh shard `name` with the backup's contents, continuing at the
+  // backup's sequence number (its pull loop resumes from LatestSequenceNumber() exactly as after a RocksDB restore)
+  static rocksdb::Status Restore(const rocksdb::Options& options, const std::string& name, const std::string& dir,
+                                 rocksdb::DB** dbptr, int device = 0);
   rocksdb::SequenceNumber GetLatestSequenceNumber() const override;
   rocksdb::Status GetUpdatesSince(rocksdb::SequenceNumber seq,
                                   std::unique_ptr<rocksdb::TransactionLogIterator>* iter) override;
@@ -98,6 +109,31 @@ class GpuDB : public rocksdb::DB {
   size_t log_bytes_ = 0;
   size_t log_cap_bytes_ = 256u << 20;
   std::atomic<size_t> value_hint_{0};  // largest value MultiGet has seen (the staging stride of its first pass)
+};
+
+// Spills shards on a schedule: every `period_ms` each registered DB whose sequence number moved since its last backup
+// is backed up to <root>/<db name>/ (the reference's operators schedule backupDB calls from outside; HBM being
+// volatile, the schedule lives next to the engine here).
+class BackupScheduler {
+ public:
+  BackupScheduler(const std::string& root, uint64_t period_ms);
+  ~BackupScheduler();
+  void Add(const std::string& name, std::shared_ptr<rocksdb::DB> db);
+  void Remove(const std::string& name);
+  uint64_t backups_done() const { return done_.load(); }
+  // one pass now (also what the timer thread runs); returns the number of shards written
+  size_t RunOnce();
+
+ private:
+  struct Item { std::shared_ptr<rocksdb::DB> db; uint64_t last_seq = ~0ull; };
+  const std::string root_;
+  const uint64_t period_ms_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::map<std::string, Item> items_;
+  bool stop_ = false;
+  std::atomic<uint64_t> done_{0};
+  std::thread th_;
 };
 
 }  // namespace b200

@@ -797,6 +797,71 @@ static void test_gpu_seams() {
   EXPECT_EQ(r.parity_errors + r.status_errors, (uint64_t)0);
 }
 
+// HBM is volatile: backup = visible contents as one SST + dbmeta (sequence number); restore = a fresh shard that
+// continues at that sequence number; the scheduler spills shards whose sequence number moved
+// (rocksdb_admin/admin_handler.cpp:696-860 backupDBHelper / restoreDBHelper)
+static void test_gpu_backup_restore() {
+  rocksdb::Options opt;
+  opt.merge_operator = std::make_shared<CounterMergeOperator>();
+  rocksdb::DB* raw = nullptr;
+  EXPECT_TRUE(b200::GpuDB::Open(opt, "bk_src00001", &raw).ok());
+  std::shared_ptr<rocksdb::DB> src(raw);
+  for (int i = 0; i < 500; i++) {
+    WriteBatch wb;
+    wb.Put("key" + std::to_string(i), "value" + std::to_string(i));
+    if (i % 7 == 0) wb.Delete("key" + std::to_string(i / 2));
+    int64_t one = i;
+    if (i % 5 == 0) wb.Merge("ctr" + std::to_string(i % 20), Slice((const char*)&one, 8));
+    EXPECT_TRUE(src->Write(rocksdb::WriteOptions(), &wb).ok());
+    if (i == 250) EXPECT_TRUE(src->Flush(rocksdb::FlushOptions()).ok());
+  }
+  const std::string root = "/tmp/rsp_bk_" + std::to_string(getpid());
+  auto* gsrc = static_cast<b200::GpuDB*>(src.get());
+  uint64_t seq = 0;
+  EXPECT_TRUE(gsrc->Backup(root + "/manual", &seq).ok());
+  EXPECT_EQ(seq, (uint64_t)src->GetLatestSequenceNumber());
+  rocksdb::DB* raw2 = nullptr;
+  EXPECT_TRUE(b200::GpuDB::Restore(opt, "bk_dst00001", root + "/manual", &raw2).ok());
+  std::unique_ptr<rocksdb::DB> dst(raw2);
+  EXPECT_TRUE(dst != nullptr);
+  if (dst) {
+    EXPECT_EQ(dst->GetLatestSequenceNumber(), src->GetLatestSequenceNumber());
+    std::unique_ptr<rocksdb::Iterator> a(src->NewIterator(rocksdb::ReadOptions())), b(dst->NewIterator(rocksdb::ReadOptions()));
+    size_t n = 0;
+    for (a->SeekToFirst(), b->SeekToFirst(); a->Valid() && b->Valid(); a->Next(), b->Next(), n++) {
+      EXPECT_TRUE(a->key() == b->key() && a->value() == b->value());
+    }
+    EXPECT_TRUE(!a->Valid() && !b->Valid() && n > 400);
+    // the restored replica goes on from the backup's sequence number
+    WriteBatch wb;
+    wb.Put("after", "restore");
+    EXPECT_TRUE(dst->Write(rocksdb::WriteOptions(), &wb).ok());
+    EXPECT_EQ(dst->GetLatestSequenceNumber(), seq + 1);
+  }
+  // scheduled spilling: only shards whose sequence number moved are written again
+  {
+    b200::BackupScheduler sched(root + "/sched", 20);
+    sched.Add("bk_src00001", src);
+    EXPECT_TRUE(wait_until([&] { return sched.backups_done() >= 1; }));
+    sleep_ms(100);
+    const uint64_t done = sched.backups_done();
+    EXPECT_EQ(done, (uint64_t)1);  // nothing moved: no second backup
+    WriteBatch wb;
+    wb.Put("more", "data");
+    EXPECT_TRUE(src->Write(rocksdb::WriteOptions(), &wb).ok());
+    EXPECT_TRUE(wait_until([&] { return sched.backups_done() >= 2; }));
+    sched.Remove("bk_src00001");
+  }
+  rocksdb::DB* raw3 = nullptr;
+  EXPECT_TRUE(b200::GpuDB::Restore(opt, "bk_dst00002", root + "/sched/bk_src00001", &raw3).ok());
+  std::unique_ptr<rocksdb::DB> dst3(raw3);
+  std::string v;
+  EXPECT_TRUE(dst3 && dst3->Get(rocksdb::ReadOptions(), "more", &v).ok() && v == "data");
+  EXPECT_TRUE(dst3 && dst3->GetLatestSequenceNumber() == src->GetLatestSequenceNumber());
+  const std::string rm = "rm -rf '" + root + "'";
+  EXPECT_EQ(system(rm.c_str()), 0);
+}
+
 int main(int argc, char** argv) {
   const std::string mode = argc > 1 ? argv[1] : "cpu";
   // `only=<name>` (second argument) runs one test by name, whatever its mode
@@ -821,6 +886,7 @@ int main(int argc, char** argv) {
       {"counter_service_config1", test_counter_service_config1, true},
       {"application_db_manager", test_application_db_manager, true},
       {"gpu_seams", test_gpu_seams, true},
+      {"gpu_backup_restore", test_gpu_backup_restore, true},
   };
   for (auto& t : tests) {
     if (!only.empty()) {
