@@ -64,7 +64,7 @@ if __name__ == "__main__":
 HOST = os.path.join(HERE, "host")
 HOST_SRCS = ["gpu_db.cpp", "rocksdb_replicator/rocksdb_replicator.cpp", "rocksdb_replicator/gpu_db_wrapper.cpp",
              "rocksdb_admin/application_db.cpp", "rocksdb_admin/application_db_manager.cpp", "sst/sst_c_api.cpp",
-             "bench/seam_bench.cpp"]
+             "bench/seam_bench.cpp", "rocksdb_admin/message_ingestion.cpp"]
 HOST_SO = os.path.join(HERE, "librsp_host.so")
 HOST_TESTS = os.path.join(os.path.dirname(HERE), "tests", "cpp", "host_tests")
 

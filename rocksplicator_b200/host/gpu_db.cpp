@@ -112,6 +112,31 @@ Status GpuDB::Write(const rocksdb::WriteOptions&, rocksdb::WriteBatch* updates) 
   return Status::OK();
 }
 
+std::vector<Status> GpuDB::WriteMany(const rocksdb::WriteOptions&, const std::vector<rocksdb::WriteBatch*>& updates) {
+  const size_t n = updates.size();
+  std::vector<Status> out(n);
+  if (!n) return out;
+  std::lock_guard<std::mutex> g(write_mu_);  // log order == sequence order
+  std::vector<rsp_slice> slices(n);
+  for (size_t i = 0; i < n; i++) slices[i] = rsp_slice{(const uint8_t*)updates[i]->Data().data(), updates[i]->Data().size()};
+  const uint64_t seq_before = GetLatestSequenceNumber();
+  size_t n_applied = 0;
+  const int rc = rsp_apply_updates(shard_, n, slices.data(), nullptr, nullptr, nullptr, &n_applied);
+  // applied in order until the first failure (which latches the shard, as a failed DB::Write does in RocksDB 5.x)
+  uint64_t first = seq_before + 1;
+  for (size_t i = 0; i < n; i++) {
+    if (i >= n_applied) { out[i] = ToStatus(rc != RSP_OK ? rc : RSP_IO_ERROR); continue; }
+    const uint32_t count = (uint32_t)updates[i]->Count();
+    if (!count) continue;
+    std::string bytes = updates[i]->Data();
+    memcpy(&bytes[0], &first, 8);
+    updates[i]->SetSequence(first);
+    LogAppend(first, std::move(bytes), count);
+    first += count;
+  }
+  return out;
+}
+
 namespace {
 bool ReadWholeFile(const std::string& path, std::string* out) {
   FILE* f = fopen(path.c_str(), "rb");

@@ -38,6 +38,10 @@ class GpuDB : public rocksdb::DB {
   ~GpuDB() override;
 
   rocksdb::Status Write(const rocksdb::WriteOptions& options, rocksdb::WriteBatch* updates) override;
+  // Several independent writes of this shard in ONE engine call (rsp_apply_updates with write semantics): each batch
+  // is its own DB::Write — own sequence numbers, own status — but they share a device tick.  The message-ingestion
+  // writer (rocksdb_admin/message_ingestion.h) turns a poll of Kafka messages into one call here.
+  std::vector<rocksdb::Status> WriteMany(const rocksdb::WriteOptions& options, const std::vector<rocksdb::WriteBatch*>& updates);
   rocksdb::Status Get(const rocksdb::ReadOptions& options, const rocksdb::Slice& key, std::string* value) override;
   rocksdb::Status Get(const rocksdb::ReadOptions& options, rocksdb::ColumnFamilyHandle* cf, const rocksdb::Slice& key,
                       rocksdb::PinnableSlice* value) override;

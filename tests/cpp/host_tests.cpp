@@ -26,6 +26,7 @@
 #include "rocksdb_replicator/replicator_stats.h"
 #include "gpu_db.h"
 #include "rocksdb_admin/application_db_manager.h"
+#include "rocksdb_admin/message_ingestion.h"
 #include "rocksdb_replicator/rocksdb_replicator.h"
 
 using namespace replicator;
@@ -862,6 +863,66 @@ static void test_gpu_backup_restore() {
   EXPECT_EQ(system(rm.c_str()), 0);
 }
 
+// the Kafka-style writer front-end (rocksdb_admin/admin_handler.cpp:1855-2084): messages -> Put / Delete / Merge, one
+// sequence number per message, a whole poll in one engine call; contents equal to the same operations issued one by one
+static void test_gpu_message_ingestion() {
+  struct VecSource : public admin::MessageSource {
+    std::vector<admin::IngestMessage> all;
+    size_t at = 0;
+    size_t Poll(std::vector<admin::IngestMessage>* out, size_t max, int) override {
+      size_t n = 0;
+      while (at < all.size() && n < max) { out->push_back(all[at++]); n++; }
+      if (!n) sleep_ms(1);
+      return n;
+    }
+  };
+  rocksdb::Options opt;
+  opt.merge_operator = std::make_shared<CounterMergeOperator>();
+  rocksdb::DB *ra = nullptr, *rb = nullptr;
+  EXPECT_TRUE(b200::GpuDB::Open(opt, "kafka_a00001", &ra).ok());
+  EXPECT_TRUE(b200::GpuDB::Open(opt, "kafka_b00001", &rb).ok());
+  std::shared_ptr<rocksdb::DB> a(ra), b(rb);
+  auto adb = std::make_shared<admin::ApplicationDB>("kafka_a00001", a, ReplicaRole::FOLLOWER, nullptr);
+  auto src = std::make_shared<VecSource>();
+  for (int i = 0; i < 5000; i++) {
+    admin::IngestMessage m;
+    m.key = "k" + std::to_string(i % 700);
+    m.timestamp_ms = 1000 + i;
+    m.offset = i;
+    if (i % 11 == 0) { m.op_code = admin::KafkaOperationCode::DELETE; }
+    else if (i % 5 == 0) { m.op_code = admin::KafkaOperationCode::MERGE; int64_t v = i; m.key = "c" + std::to_string(i % 30); m.value.assign((const char*)&v, 8); }
+    else { m.op_code = admin::KafkaOperationCode::PUT; m.value = "v" + std::to_string(i); }
+    if (i == 4321) m.op_code = (admin::KafkaOperationCode)9;  // invalid op code: counted and skipped
+    src->all.push_back(m);
+  }
+  // the same operations one DB call at a time on the second shard
+  for (auto& m : src->all) {
+    if (m.op_code == admin::KafkaOperationCode::PUT) EXPECT_TRUE(b->Put(rocksdb::WriteOptions(), m.key, m.value).ok());
+    else if (m.op_code == admin::KafkaOperationCode::DELETE) EXPECT_TRUE(b->Delete(rocksdb::WriteOptions(), m.key).ok());
+    else if (m.op_code == admin::KafkaOperationCode::MERGE) EXPECT_TRUE(b->Merge(rocksdb::WriteOptions(), m.key, m.value).ok());
+  }
+  int64_t seen_ts = 0;
+  admin::MessageIngestionOptions io;
+  io.max_poll_messages = 512;
+  io.on_timestamp = [&](int64_t t) { seen_ts = t; };
+  admin::MessageIngestor ing(adb, src, io);
+  ing.Start();
+  EXPECT_TRUE(wait_until([&] { return ing.messages() == 5000; }));
+  ing.Stop();
+  EXPECT_EQ(ing.errors(), (uint64_t)0);
+  EXPECT_TRUE(seen_ts >= 1000 + 4000);
+  EXPECT_EQ(a->GetLatestSequenceNumber(), b->GetLatestSequenceNumber());  // one sequence number per valid message
+  EXPECT_EQ(a->GetLatestSequenceNumber(), (uint64_t)4999);
+  std::unique_ptr<rocksdb::Iterator> ia(a->NewIterator(rocksdb::ReadOptions())), ib(b->NewIterator(rocksdb::ReadOptions()));
+  size_t n = 0;
+  for (ia->SeekToFirst(), ib->SeekToFirst(); ia->Valid() && ib->Valid(); ia->Next(), ib->Next(), n++)
+    EXPECT_TRUE(ia->key() == ib->key() && ia->value() == ib->value());
+  EXPECT_TRUE(!ia->Valid() && !ib->Valid() && n > 300);
+  // the ingested writes are in the update log: a downstream follower can pull them
+  std::unique_ptr<rocksdb::TransactionLogIterator> li;
+  EXPECT_TRUE(a->GetUpdatesSince(1, &li).ok() && li && li->Valid());
+}
+
 int main(int argc, char** argv) {
   const std::string mode = argc > 1 ? argv[1] : "cpu";
   // `only=<name>` (second argument) runs one test by name, whatever its mode
@@ -887,6 +948,7 @@ int main(int argc, char** argv) {
       {"application_db_manager", test_application_db_manager, true},
       {"gpu_seams", test_gpu_seams, true},
       {"gpu_backup_restore", test_gpu_backup_restore, true},
+      {"gpu_message_ingestion", test_gpu_message_ingestion, true},
   };
   for (auto& t : tests) {
     if (!only.empty()) {
