@@ -1000,52 +1000,114 @@ __device__ __forceinline__ void multi_scan_body(const ScanArgs& a) {
     }
   }
 
-  // cursors: forward = next ordinal to consume; reverse = (last ordinal to consume) + 1
+  // ---- general path: k-way newest-wins merge over the pinned runs.
+  // FORWARD scans are lane-parallel: lane r owns run r's cursor and keeps its head entry cached (pointer, lengths,
+  // type, 8-byte big-endian key prefix).  Every lane seeks its own run at the same time; per output key the warp takes
+  // the minimum prefix by shuffles, settles prefix ties by full-key compares done in parallel by the tied lanes, and
+  // the runs that hold the key are visited newest first while their lanes already load their next heads.
+  // REVERSE scans (Iterator::Prev, rare) keep the scalar walk: every lane executes the same code.
   u32 cur[RSP_MAX_RUNS];
-  for (u32 r = 0; r < n_runs; r++) {
-    if (extreme) cur[r] = reverse ? runs[r].n_ent : 0u;
-    else if (!reverse) cur[r] = run_lower_bound(runs[r], kp, klen, exclusive);
-    else cur[r] = run_lower_bound(runs[r], kp, klen, !exclusive);  // entries < key (or <= key)
+  // forward state of lane r (r < n_runs)
+  u32 my_cur = 0, h_klen = 0, h_vlen = 0, h_type = 0;
+  const u8* h_e = nullptr;
+  u64 h_pfx = 0;
+  bool h_valid = false;
+  auto load_head = [&]() {
+    h_valid = lane < n_runs && my_cur < runs[lane].n_ent;
+    if (h_valid) {
+      h_e = run_entry(runs[lane], my_cur);
+      const uint4 hd = __ldg(reinterpret_cast<const uint4*>(h_e));
+      h_type = hd.x & 0xffu; h_klen = hd.z; h_vlen = hd.w;
+      h_pfx = h_klen ? bswap64(__ldg(reinterpret_cast<const u64*>(h_e + 16))) : 0ull;
+    }
+  };
+  if (!reverse) {
+    if (lane < n_runs) my_cur = extreme ? 0u : run_lower_bound(runs[lane], kp, klen, exclusive);
+    load_head();
+  } else {
+    for (u32 r = 0; r < n_runs; r++) {
+      if (extreme) cur[r] = runs[r].n_ent;
+      else cur[r] = run_lower_bound(runs[r], kp, klen, !exclusive);  // entries < key (or <= key)
+    }
   }
 
   while (n_out < a.max_entries) {
-    // pick the next user key: min over forward cursors / max over reverse cursors (newest run wins ties)
-    int best = -1;
     EntRef bk;
+    Acc acc;
+    acc.init(merge_op);
+    if (!reverse) {
+      const u32 vmask = __ballot_sync(0xffffffffu, h_valid);
+      if (!vmask) break;
+      // minimum prefix over the valid heads (lanes 0 .. 7 hold the runs: three butterfly steps)
+      u64 mp = h_valid ? h_pfx : ~0ull;
+#pragma unroll
+      for (u32 d = 1; d < RSP_MAX_RUNS; d <<= 1) {
+        const u64 o = __shfl_xor_sync(0xffffffffu, mp, d);
+        mp = o < mp ? o : mp;
+      }
+      mp = __shfl_sync(0xffffffffu, mp, 0);
+      u32 cand = __ballot_sync(0xffffffffu, h_valid && h_pfx == mp);
+      u32 group, w;
+      for (;;) {  // the smallest full key among the tied prefixes, and every run whose head is that key
+        w = (u32)__ffs(cand) - 1u;
+        const u64 wk = __shfl_sync(0xffffffffu, (u64)reinterpret_cast<uintptr_t>(h_e), w);
+        const u32 wkl = __shfl_sync(0xffffffffu, h_klen, w);
+        int c = 0;
+        const bool mine = ((cand >> lane) & 1u) && lane != w;
+        if (mine) c = cmp_padded(reinterpret_cast<const u64*>(h_e + 16), h_klen, reinterpret_cast<const u64*>(reinterpret_cast<const u8*>(wk) + 16), wkl);
+        const u32 less = __ballot_sync(0xffffffffu, mine && c < 0);
+        if (less) { cand = less; continue; }
+        group = __ballot_sync(0xffffffffu, mine && c == 0) | (1u << w);
+        break;
+      }
+      bk.e = reinterpret_cast<const u8*>(__shfl_sync(0xffffffffu, (u64)reinterpret_cast<uintptr_t>(h_e), w));
+      bk.klen = __shfl_sync(0xffffffffu, h_klen, w);
+      bk.vlen = 0; bk.type = 0;
+      // newest run first; inside a run the versions of a key follow each other, newest first
+      for (u32 g = group; g;) {
+        const u32 r = (u32)__ffs(g) - 1u;
+        g &= g - 1u;
+        for (;;) {
+          const u32 t = __shfl_sync(0xffffffffu, h_type, r), vl = __shfl_sync(0xffffffffu, h_vlen, r);
+          const u64 ep = __shfl_sync(0xffffffffu, (u64)reinterpret_cast<uintptr_t>(h_e), r);
+          const u32 kl = __shfl_sync(0xffffffffu, h_klen, r);
+          if (!acc.done) acc.visit(t, reinterpret_cast<const u8*>(ep) + 16u + 16u * units_of(kl), vl);
+          bool same = false;
+          if (lane == r) {
+            my_cur++;
+            load_head();
+            same = h_valid && cmp_padded(reinterpret_cast<const u64*>(h_e + 16), h_klen, bk.key(), bk.klen) == 0;
+          }
+          if (!__shfl_sync(0xffffffffu, (u32)same, r)) break;
+        }
+      }
+    } else {
+    // pick the next user key: the maximum over the reverse cursors (newest run wins ties)
+    int best = -1;
     for (u32 r = 0; r < n_runs; r++) {
-      if (!reverse ? cur[r] >= runs[r].n_ent : cur[r] == 0) continue;
-      const EntRef x = load_ent(runs[r], reverse ? cur[r] - 1 : cur[r]);
+      if (cur[r] == 0) continue;
+      const EntRef x = load_ent(runs[r], cur[r] - 1);
       if (best < 0) { best = (int)r; bk = x; continue; }
       const int c = cmp_padded(x.key(), x.klen, bk.key(), bk.klen);
-      if (!reverse ? c < 0 : c > 0) { best = (int)r; bk = x; }
+      if (c > 0) { best = (int)r; bk = x; }
     }
     if (best < 0) break;
     // resolve this key across the runs that hold it, newest run first
-    Acc acc;
-    acc.init(merge_op);
     for (u32 r = 0; r < n_runs; r++) {
       const RunDev& R = runs[r];
-      if (!reverse) {
-        while (cur[r] < R.n_ent) {
-          const EntRef x = load_ent(R, cur[r]);
-          if (cmp_padded(x.key(), x.klen, bk.key(), bk.klen) != 0) break;
-          if (!acc.done) acc.visit(x.type, x.val(), x.vlen);
-          cur[r]++;
-        }
-      } else {
-        // group = [g, cur[r]) with the same key; versions are newest-first from g upward
-        u32 g = cur[r];
-        while (g > 0) {
-          const EntRef x = load_ent(R, g - 1);
-          if (cmp_padded(x.key(), x.klen, bk.key(), bk.klen) != 0) break;
-          g--;
-        }
-        for (u32 o = g; o < cur[r] && !acc.done; o++) {
-          const EntRef x = load_ent(R, o);
-          acc.visit(x.type, x.val(), x.vlen);
-        }
-        cur[r] = g;
+      // group = [g, cur[r]) with the same key; versions are newest-first from g upward
+      u32 g = cur[r];
+      while (g > 0) {
+        const EntRef x = load_ent(R, g - 1);
+        if (cmp_padded(x.key(), x.klen, bk.key(), bk.klen) != 0) break;
+        g--;
       }
+      for (u32 o = g; o < cur[r] && !acc.done; o++) {
+        const EntRef x = load_ent(R, o);
+        acc.visit(x.type, x.val(), x.vlen);
+      }
+      cur[r] = g;
+    }
     }
     acc.end_of_versions();
     if (acc.status == 1) continue;  // deleted
