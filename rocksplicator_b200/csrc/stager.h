@@ -5,20 +5,26 @@
 // updates from >= 16 executor threads (rocksdb_replicator/rocksdb_replicator.cpp:58-67).  A device batch costs the same
 // launch + synchronisation whether it carries 1 request or 100 000, so concurrent callers share batches:
 //
-//   caller:      begin()  -> a slice of the OPEN batch's pinned staging (items + bytes)     [short lock]
-//                copy its own inputs into the slice, in parallel with every other caller     [no lock]
-//                commit() -> wait() until the batch has run -> read its own results          [no lock]
-//                release()
-//   dispatcher:  one thread; as soon as it is idle and the open batch is not empty it CLOSES it (the other buffer
+//   caller:      begin()  -> a slice of the OPEN batch's pinned staging (items + bytes)
+//                copy its own inputs into the slice, in parallel with every other caller
+//                commit() -> wait() until the batch has run -> read its own results -> release()
+//   dispatcher:  one thread; as soon as it is idle and the open batch is not empty it CLOSES it (another buffer
 //                opens for new arrivals), waits for the callers still copying, runs the batch (H2D, kernels, D2H,
-//                one synchronisation — the RunFn), fires the asynchronous completions and wakes the waiters.
+//                one synchronisation — the RunFn), fires the asynchronous completions and publishes the batch's epoch.
 //
 // While the device works on batch k, callers fill batch k+1 and the callers of batch k-1 are still copying their results
-// out (three buffers): batches grow with load on their own (no timer), a lone caller pays two thread hand-offs and
-// nothing else.  Requests of one caller thread stay ordered (it does not return
-// before its request has run); slices of one batch are ordered by begin() order, which is what per-shard FIFO needs.
+// out (three buffers): batches grow with load on their own (no timer).  Requests of one caller thread stay ordered (it
+// does not return before its request has run); slices of one batch are ordered by begin() order, which is what
+// per-shard FIFO needs.
+//
+// Locking: every state change is a few loads and stores under a SPIN lock (nothing blocks while holding it); waiting is
+// spin-then-yield on an atomic word (a batch cycle is tens of microseconds: hundreds of sleeping callers woken through
+// one condition variable would queue on its mutex for longer than the batch took — measured: ApplicationDB::Get from
+// 256 threads went at 55 K/s that way); only long waits — no room in any buffer, an idle dispatcher — fall back to
+// sleeping on a condition variable.
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstddef>
 #include <cstdint>
@@ -56,14 +62,8 @@ class Stager {
   }
   ~Stager() { Stop(); }
   void Stop() {
-    {
-      std::lock_guard<std::mutex> g(mu_);
-      if (stop_) return;
-      stop_ = true;
-    }
-    cv_disp_.notify_all();
-    cv_space_.notify_all();
-    cv_done_.notify_all();
+    if (stop_.exchange(true)) return;
+    WakeSleepers();
     if (thread_.joinable()) thread_.join();
   }
 
@@ -71,69 +71,71 @@ class Stager {
   size_t cap_bytes() const { return cap_bytes_; }
 
   // Reserve n_items / n_bytes in a batch of class `klass` (requests of different classes never share a batch);
-  // max_items bounds the items of a batch of this class (<= cap_items).  Blocks while nothing can take the request.
+  // max_items bounds the items of a batch of this class (<= cap_items).  Waits while nothing can take the request.
   // false: the stager is stopping, or the request can never fit (the caller takes its direct path).
   bool begin(size_t n_items, size_t n_bytes, uint32_t klass, size_t max_items, Ticket* t) {
     if (max_items > cap_items_) max_items = cap_items_;
     if (n_items > max_items || n_bytes > cap_bytes_) return false;
-    std::unique_lock<std::mutex> l(mu_);
-    for (;;) {
-      if (stop_) return false;
-      if (open_ >= 0) {
-        Batch& b = b_[open_];
-        if (b.n_items == 0) b.klass = klass;
-        if (b.klass == klass && b.n_items + n_items <= max_items && b.n_bytes + n_bytes <= cap_bytes_) {
-          t->buf = open_;
-          t->item0 = b.n_items;
-          t->byte0 = b.n_bytes;
-          t->epoch = b.epoch;
-          b.n_items += n_items;
-          b.n_bytes += n_bytes;
-          b.copiers.fetch_add(1, std::memory_order_relaxed);
-          b.users.fetch_add(1, std::memory_order_relaxed);
-          if (b.n_items == n_items && disp_sleeping_) cv_disp_.notify_one();  // first request: the dispatcher may take the batch
-          return true;
+    for (int spins = 0;; spins++) {
+      if (stop_.load(std::memory_order_acquire)) return false;
+      {
+        SpinGuard g(sl_);
+        if (open_ >= 0) {
+          Batch& b = b_[open_];
+          if (b.n_items == 0) b.klass = klass;
+          if (b.klass == klass && b.n_items + n_items <= max_items && b.n_bytes + n_bytes <= cap_bytes_) {
+            t->buf = open_;
+            t->item0 = b.n_items;
+            t->byte0 = b.n_bytes;
+            t->epoch = b.epoch;
+            b.n_items += n_items;
+            b.n_bytes += n_bytes;
+            b.copiers.fetch_add(1, std::memory_order_relaxed);
+            b.users.fetch_add(1, std::memory_order_relaxed);
+            work_.fetch_add(1, std::memory_order_seq_cst);
+            break;
+          }
+          b.full = true;  // full, or of another class: the dispatcher closes it as soon as it can
         }
-        // full or of another class: the dispatcher closes it as soon as it can; wait for the next open batch
-        if (disp_sleeping_) cv_disp_.notify_one();
       }
-      cv_space_.wait(l);
+      // no room right now: a buffer frees up within a batch cycle
+      if (spins < 2000) cpu_relax();
+      else if (spins < 6000) std::this_thread::yield();
+      else Sleep([this] { SpinGuard g(sl_); return stop_.load() || (open_ >= 0 && !b_[open_].full); });
     }
+    if (disp_sleeping_.load(std::memory_order_seq_cst)) WakeSleepers();
+    return true;
   }
-  // the caller finished writing its slice.  Lock-free unless it is the last writer of a batch the dispatcher waits on.
-  void commit(const Ticket& t) {
-    Batch& b = b_[t.buf];
-    if (b.copiers.fetch_sub(1, std::memory_order_acq_rel) == 1) {
-      std::lock_guard<std::mutex> g(mu_);  // (the dispatcher checks the counter under mu_ before it sleeps)
-      if (disp_sleeping_) cv_disp_.notify_one();
-    }
-  }
+  // the caller finished writing its slice
+  void commit(const Ticket& t) { b_[t.buf].copiers.fetch_sub(1, std::memory_order_acq_rel); }
   // completion without a waiting thread: fn runs on the dispatcher thread once the batch has run; the slice is
   // released when fn returns (fn reads its results from the staging buffers itself)
   void commit_async(const Ticket& t, std::function<void()> fn) {
     Batch& b = b_[t.buf];
-    std::lock_guard<std::mutex> g(mu_);
-    b.async.push_back(std::move(fn));
-    if (b.copiers.fetch_sub(1, std::memory_order_acq_rel) == 1 && disp_sleeping_) cv_disp_.notify_one();
+    {
+      SpinGuard g(sl_);
+      b.async.push_back(std::move(fn));
+    }
+    b.copiers.fetch_sub(1, std::memory_order_acq_rel);
   }
-  // until the batch has run: a short spin on the batch's completion word (hundreds of callers would otherwise convoy
-  // on one mutex just to learn that their batch is done), then a condition variable
+  // until the batch has run
   void wait(const Ticket& t) {
     Batch& b = b_[t.buf];
-    for (int i = 0; i < 4000; i++) {
-      if (b.epoch_done.load(std::memory_order_acquire) >= t.epoch) return;
-      cpu_relax();
+    for (int spins = 0; b.epoch_done.load(std::memory_order_acquire) < t.epoch; spins++) {
+      if (spins < 4000) cpu_relax();
+      else if (spins < 40000) std::this_thread::yield();
+      else Sleep([&] { return b.epoch_done.load(std::memory_order_acquire) >= t.epoch; });
     }
-    std::unique_lock<std::mutex> l(mu_);
-    sleepers_++;
-    while (b.epoch_done.load(std::memory_order_acquire) < t.epoch) cv_done_.wait(l);
-    sleepers_--;
   }
   void release(const Ticket& t) {
     Batch& b = b_[t.buf];
     if (b.users.fetch_sub(1, std::memory_order_acq_rel) == 1) {
-      std::lock_guard<std::mutex> g(mu_);
-      MaybeFree(b);
+      bool freed;
+      {
+        SpinGuard g(sl_);
+        freed = MaybeFree(b);
+      }
+      if (freed && sleepers_.load(std::memory_order_seq_cst)) WakeSleepers();
     }
   }
 
@@ -142,14 +144,15 @@ class Stager {
  private:
   enum State { FREE, OPEN, CLOSED, DONE };
   struct Batch {
-    State state = FREE;                 // mu_
-    size_t n_items = 0, n_bytes = 0;    // mu_
+    State state = FREE;                 // sl_
+    size_t n_items = 0, n_bytes = 0;    // sl_
     uint32_t klass = 0;
+    bool full = false;
     uint64_t epoch = 0;
     std::atomic<uint32_t> copiers{0};   // callers still writing their slice
     std::atomic<uint32_t> users{0};     // callers (sync and async) that have not released their slice yet
     std::atomic<uint64_t> epoch_done{0};
-    std::vector<std::function<void()>> async;  // mu_
+    std::vector<std::function<void()>> async;  // sl_
   };
   static inline void cpu_relax() {
 #if defined(__x86_64__) || defined(__i386__)
@@ -158,71 +161,121 @@ class Stager {
     std::this_thread::yield();
 #endif
   }
+  struct SpinLock {
+    std::atomic<bool> f{false};
+    void lock() {
+      for (;;) {
+        if (!f.exchange(true, std::memory_order_acquire)) return;
+        while (f.load(std::memory_order_relaxed)) cpu_relax();
+      }
+    }
+    void unlock() { f.store(false, std::memory_order_release); }
+  };
+  struct SpinGuard {
+    SpinLock& l;
+    explicit SpinGuard(SpinLock& x) : l(x) { l.lock(); }
+    ~SpinGuard() { l.unlock(); }
+  };
 
-  void MaybeFree(Batch& b) {  // mu_ held: whoever sees "done and unused" first recycles the buffer
+  // the slow path of every wait: sleep until `ready` (re-checked under the sleepers' mutex, so a wake-up between the
+  // check and the sleep is not lost: wakers publish their state change first and take the same mutex to notify);
+  // bounded, so a missed edge costs a millisecond, never a hang
+  template <class Ready>
+  void Sleep(Ready ready) {
+    std::unique_lock<std::mutex> l(slow_mu_);
+    sleepers_.fetch_add(1, std::memory_order_seq_cst);
+    if (!ready()) slow_cv_.wait_for(l, std::chrono::milliseconds(1));
+    sleepers_.fetch_sub(1, std::memory_order_seq_cst);
+  }
+  void WakeSleepers() {
+    std::lock_guard<std::mutex> g(slow_mu_);
+    slow_cv_.notify_all();
+  }
+
+  bool MaybeFree(Batch& b) {  // sl_ held: whoever sees "done and unused" first recycles the buffer
     if (b.state == DONE && b.users.load(std::memory_order_acquire) == 0) {
       b.state = FREE;
       b.n_items = b.n_bytes = 0;
       if (open_ < 0) OpenOne();
+      return true;
     }
+    return false;
   }
-  void OpenOne() {  // mu_ held
+  void OpenOne() {  // sl_ held
     for (int i = 0; i < kBuffers; i++) {
       if (b_[i].state == FREE) {
         b_[i].state = OPEN;
+        b_[i].full = false;
         b_[i].epoch = ++epochs_;
         open_ = i;
-        cv_space_.notify_all();
         return;
       }
     }
   }
   void Loop() {
-    std::unique_lock<std::mutex> l(mu_);
     for (;;) {
-      while (!(open_ >= 0 && b_[open_].n_items > 0)) {  // a stop request still lets queued work run: callers wait on it
-        if (stop_) return;
-        disp_sleeping_ = true;
-        cv_disp_.wait(l);
-        disp_sleeping_ = false;
+      // ---- take the open batch once it holds work
+      int bi = -1;
+      for (int spins = 0;; spins++) {
+        {
+          SpinGuard g(sl_);
+          if (open_ >= 0 && b_[open_].n_items > 0) {
+            bi = open_;
+            b_[bi].state = CLOSED;
+            open_ = -1;
+            OpenOne();
+            break;
+          }
+        }
+        if (stop_.load(std::memory_order_acquire)) return;  // (queued work was taken above: callers wait on it)
+        if (spins < 20000) cpu_relax();  // stay hot between batches under load
+        else {
+          disp_sleeping_.store(true, std::memory_order_seq_cst);
+          Sleep([this] { return stop_.load() || work_.load(std::memory_order_seq_cst) != seen_work_; });
+          disp_sleeping_.store(false, std::memory_order_seq_cst);
+        }
       }
-      const int bi = open_;
+      seen_work_ = work_.load(std::memory_order_seq_cst);
+      if (sleepers_.load(std::memory_order_seq_cst)) WakeSleepers();  // a fresh buffer is open: callers short of room
       Batch& b = b_[bi];
-      b.state = CLOSED;
-      open_ = -1;
-      OpenOne();
-      while (b.copiers.load(std::memory_order_acquire)) {
-        disp_sleeping_ = true;
-        cv_disp_.wait(l);
-        disp_sleeping_ = false;
+      for (int spins = 0; b.copiers.load(std::memory_order_acquire); spins++) {
+        if (spins < 4000) cpu_relax(); else std::this_thread::yield();
       }
-      BatchInfo info{bi, b.n_items, b.n_bytes, b.klass, b.epoch};
+      BatchInfo info;
       std::vector<std::function<void()>> async;
-      async.swap(b.async);
-      l.unlock();
+      {
+        SpinGuard g(sl_);
+        info = BatchInfo{bi, b.n_items, b.n_bytes, b.klass, b.epoch};
+        async.swap(b.async);
+      }
       run_(info);
       for (auto& f : async) f();
       if (post_) post_();
-      b.epoch_done.store(info.epoch, std::memory_order_release);  // spinning waiters go on at once
-      l.lock();
-      batches_++;
-      b.state = DONE;
-      if (sleepers_) cv_done_.notify_all();
-      if (!async.empty()) b.users.fetch_sub((uint32_t)async.size(), std::memory_order_acq_rel);
-      MaybeFree(b);
+      b.epoch_done.store(info.epoch, std::memory_order_release);  // waiting callers go on at once
+      batches_.fetch_add(1, std::memory_order_relaxed);
+      {
+        SpinGuard g(sl_);
+        b.state = DONE;
+        if (!async.empty()) b.users.fetch_sub((uint32_t)async.size(), std::memory_order_acq_rel);
+        MaybeFree(b);
+      }
+      if (sleepers_.load(std::memory_order_seq_cst)) WakeSleepers();
     }
   }
 
   const size_t cap_items_, cap_bytes_;
   RunFn run_;
   PostFn post_;
-  std::mutex mu_;
-  std::condition_variable cv_disp_, cv_space_, cv_done_;
+  SpinLock sl_;
   Batch b_[kBuffers];
   int open_ = -1;
   uint64_t epochs_ = 0;
-  bool stop_ = false, disp_sleeping_ = false;
-  uint32_t sleepers_ = 0;
+  std::atomic<bool> stop_{false}, disp_sleeping_{false};
+  std::atomic<uint64_t> work_{0};  // requests ever accepted: the idle dispatcher sleeps until it moves
+  uint64_t seen_work_ = 0;
+  std::atomic<uint32_t> sleepers_{0};
+  std::mutex slow_mu_;
+  std::condition_variable slow_cv_;
   std::atomic<uint64_t> batches_{0};
   std::thread thread_;
 };
