@@ -93,6 +93,7 @@ inline size_t put_varint32(uint8_t* p, uint32_t v) {
 // header(seq = 0, count = 1) Put(key, value) LogData(ts): what the leader serves (replicated_db.cpp:115-117, 527-530)
 inline void single_put_batch(const uint8_t* key, const uint8_t* val, uint32_t vlen, uint64_t ts, std::string* out) {
   uint8_t buf[32];
+  out->reserve(12 + 2 + 16 + 5 + vlen + 10);
   out->assign(12, '\0');
   (*out)[8] = 1;
   out->push_back(0x1);
