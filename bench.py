@@ -108,7 +108,7 @@ class SeamCfg(C.Structure):
                 ("executor_threads", C.c_uint32), ("updates_per_response", C.c_uint32), ("update_rounds", C.c_uint32),
                 ("multiget_threads", C.c_uint32), ("multiget_batch", C.c_uint32), ("multiget_secs", C.c_double),
                 ("get_threads", C.c_uint32), ("get_secs", C.c_double), ("seed", C.c_uint64),
-                ("first_shard_id", C.c_uint32), ("reserved", C.c_uint32)]
+                ("first_shard_id", C.c_uint32), ("steady_rounds", C.c_uint32)]
 
 
 class SeamResult(C.Structure):
@@ -117,11 +117,13 @@ class SeamResult(C.Structure):
                [("mget_calls", C.c_uint64)] + \
                [(n, C.c_double) for n in ("get_per_s", "get_p50_us", "get_p99_us", "mixed_applies_per_s",
                                           "mixed_lookups_per_s", "mixed_resp_p50_ms", "mixed_resp_p99_ms")] + \
-               [(n, C.c_uint64) for n in ("applied_total", "parity_errors", "status_errors", "engine_launches")]
+               [(n, C.c_uint64) for n in ("applied_total", "parity_errors", "status_errors", "engine_launches")] + \
+               [(n, C.c_double) for n in ("steady_applies_per_s", "steady_resp_p50_ms", "steady_resp_p99_ms")] + \
+               [("trace_us", C.c_double * 6), ("apply_comb", C.c_double * 5), ("read_comb", C.c_double * 5)]
 
 
 def run_seams(device, shards, kv, rank, world, secs=2.0, value_len=64, update_rounds=20, updates_per_response=50,
-              reads=True, shard_base=0):
+              reads=True, shard_base=0, steady_rounds=200):
     """The hot path through the reference's own seams (rocksplicator_b200/host/bench/seam_bench.cpp): followers pull
     from a synthetic leader through RocksDBReplicator -> DbWrapper; readers call ApplicationDB::MultiGet(4096) / Get from
     many threads.  Host buffers, H2D + D2H inside; every value checked against the generator."""
@@ -140,10 +142,10 @@ def run_seams(device, shards, kv, rank, world, secs=2.0, value_len=64, update_ro
                   update_rounds=update_rounds if reads else 0,
                   multiget_threads=max(4, min(64, share // 2)) if reads else 0, multiget_batch=4096, multiget_secs=secs,
                   get_threads=max(8, min(256, share * 2)) if reads else 0, get_secs=secs / 2, seed=0x5EED0001 + rank,
-                  first_shard_id=shard_base + rank * shards)
+                  first_shard_id=shard_base + rank * shards, steady_rounds=steady_rounds)
     res = SeamResult()
     rc = lib.rsp_seam_bench(C.byref(cfg), C.byref(res))
-    out = {n: getattr(res, n) for n, _ in SeamResult._fields_}
+    out = {n: (list(getattr(res, n)) if n in ("trace_us", "apply_comb", "read_comb") else getattr(res, n)) for n, _ in SeamResult._fields_}
     out["rc"] = rc
     out["threads"] = {"executor": cfg.executor_threads, "multiget": cfg.multiget_threads, "get": cfg.get_threads}
     return out
@@ -765,7 +767,7 @@ def main():
             # the pull protocol keeps ONE response in flight per shard (replicated_db.cpp:430): its size is the reference's
             # flag replicator_max_updates_per_response (default 50).  The same pull loops with 500 updates per response:
             big_resp = run_seams(local_rank, S, min(NKV, S * 4000), rank, world, updates_per_response=500, reads=False,
-                                 shard_base=20000)
+                                 shard_base=20000, steady_rounds=0)
             seams["load500_applies_per_s"] = big_resp.get("load_applies_per_s", 0.0) if big_resp.get("rc") == 0 and not big_resp.get("status_errors") else 0.0
             seams["load500_p50_ms"] = big_resp.get("resp_p50_ms", 0.0)
         except Exception as ex:  # noqa: BLE001
@@ -773,10 +775,11 @@ def main():
         ok = 1.0 if (seams.get("rc") == 0 and seams.get("parity_errors") == 0 and seams.get("status_errors") == 0) else 0.0
         seams_all_ok = sum_over_ranks(ok) == world
         seams_sum = {k: sum_over_ranks(float(seams.get(k, 0.0))) for k in (
-            "load_applies_per_s", "mget_lookups_per_s", "get_per_s", "mixed_applies_per_s", "mixed_lookups_per_s", "load500_applies_per_s")}
+            "load_applies_per_s", "mget_lookups_per_s", "get_per_s", "mixed_applies_per_s", "mixed_lookups_per_s", "load500_applies_per_s",
+            "steady_applies_per_s")}
         seams_max = {k: max_over_ranks(float(seams.get(k, 0.0))) for k in (
             "resp_p50_ms", "resp_p99_ms", "mget_p50_ms", "mget_p99_ms", "get_p50_us", "get_p99_us", "mixed_resp_p50_ms",
-            "mixed_resp_p99_ms")}
+            "mixed_resp_p99_ms", "steady_resp_p50_ms", "steady_resp_p99_ms")}
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu:
         r = run_cpu("reference", ncores, S, args.cpu_kv, 60.0, args.cpu_get_secs)
@@ -834,6 +837,12 @@ def main():
                 "what": "the same path through the reference's seams (librsp_host.so): %d follower pull loops (RocksDBReplicator -> DbWrapper::HandleReplicateResponses, 50 updates per response, synthetic leader behind the Transport interface) load %d KV; ApplicationDB::MultiGet(4096 keys of one shard) and ApplicationDB::Get from caller threads; host std::string / Slice buffers, H2D + D2H inside; values checked against the generator" % (S * world, NKV * world),
                 "ok": bool(seams_all_ok), "threads_per_rank": seams.get("threads"), "error": seams.get("error"),
                 "applies_per_s": seams_sum["load_applies_per_s"], "response_to_next_pull_ms": {"p50": seams_max["resp_p50_ms"], "p99": seams_max["resp_p99_ms"]},
+                "steady": {"what": "the pull loops alone on the loaded shards (200 more responses per shard, flushes running as the memtables fill): the sustained follower rate",
+                           "applies_per_s": seams_sum["steady_applies_per_s"],
+                           "response_to_next_pull_ms": {"p50": seams_max["steady_resp_p50_ms"], "p99": seams_max["steady_resp_p99_ms"]},
+                           "round_trip_stage_us_rank0": dict(zip(("transport", "to_executor", "handle_and_stage", "engine", "to_continuation", "to_next_pull"), seams.get("trace_us") or [])),
+                           "apply_combiner_rank0": dict(zip(("batches", "updates", "ms_running", "ms_waiting_copiers", "ms_idle"), seams.get("apply_comb") or []))},
+                "get_combiner_rank0": dict(zip(("batches", "keys", "ms_running", "ms_waiting_copiers", "ms_idle"), seams.get("read_comb") or [])),
                 "applies_per_s_at_500_updates_per_response": seams_sum["load500_applies_per_s"],
                 "note": "one response in flight per shard (the pull protocol): applies/s = shards x updates per response / round trip; 50 per response is the reference's default flag, 500 shows the same loops with a larger flag value",
                 "multiget_lookups_per_s": seams_sum["mget_lookups_per_s"], "multiget_call_ms": {"p50": seams_max["mget_p50_ms"], "p99": seams_max["mget_p99_ms"]},

@@ -86,6 +86,8 @@ typedef struct rsp_stats {
   uint64_t n_runs, run_entries, run_bytes;
   uint64_t flushes, compactions;
   uint64_t compaction_bytes_read, compaction_bytes_written;
+  uint64_t flush_comparison_sorts; /* flushes whose memtable took the comparison sort (distinct keys sharing their first
+                                    * 8 bytes, or a memtable beyond the radix sort's shared-memory budget) */
 } rsp_stats;
 
 /* ---- engine / shard lifecycle -----------------------------------------------------------------
@@ -259,6 +261,10 @@ uint64_t rsp_kernel_launches(const rsp_engine* e);
 
 /* diagnostics: lookups of the last MultiGet launch that left the fast kernel for the generic path */
 uint32_t rsp_debug_last_pending(rsp_engine* e, uint32_t* first, uint32_t cap);
+
+/* diagnostics: the staging combiners' counters — which = 0 reads, 1 applies; out = {batches run, items carried,
+ * ns inside the device batches, ns waiting for callers still copying, ns idle}; zeros before first use */
+void rsp_debug_combiner_stats(rsp_engine* e, int which, uint64_t out[5]);
 
 const char* rsp_version(void);
 

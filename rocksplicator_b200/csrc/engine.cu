@@ -293,8 +293,10 @@ struct rsp_engine {
   ShardFast* d_fast = nullptr;
   std::vector<rsp_shard*> slots;
   std::unordered_map<std::string, rsp_shard*> by_name;
-  PinBuf pin_in, pin_out;
-  DevBuf dev_tick, dev_q, dev_pending, dev_ops;
+  PinBuf pin_in, pin_out, pin_up, pin_totals;
+  DevBuf dev_tick, dev_q, dev_pending, dev_ops, dev_up;
+  cudaEvent_t up_ev = nullptr;  // the last batched descriptor upload (its staging buffers are reused)
+  bool up_ev_recorded = false;
   std::vector<u32> gid_scratch;
   std::vector<u8> seen_scratch;
   // ordering between reads launched on caller streams and memtable flushes / re-allocations on the engine stream
@@ -347,18 +349,12 @@ static void reader_end(rsp_engine* e, cudaStream_t s) {
 // runs_only: only the run set changed (a background merge was installed).  The sequencing state of the descriptor
 // (last_seq, pub_seq, mt_tail, mt_count, latch) belongs to the DEVICE while ticks are in flight — the host mirror may
 // lag behind pre-staged ticks — so it is not written then.
-static void upload_shard(rsp_engine* e, rsp_shard* s, bool runs_only = false) {
+// host bookkeeping + the compact descriptors of a shard (ShardFast, one per run) from its run list
+static void describe_shard(rsp_engine* e, rsp_shard* s, ShardFast* f_out, ShardFast* fr) {
   s->h.n_runs = (u32)s->runs.size();
   for (u32 i = 0; i < RSP_MAX_RUNS; i++) {
     if (i < s->runs.size()) s->h.runs[i] = s->runs[i]->dev();
     else memset(&s->h.runs[i], 0, sizeof(RunDev));
-  }
-  if (runs_only) {
-    const size_t from = offsetof(ShardDev, n_runs);
-    CUDA_OK(cudaMemcpyAsync((u8*)(e->d_shards + s->index) + from, (const u8*)&s->h + from, sizeof(ShardDev) - from,
-                            cudaMemcpyHostToDevice, e->st));
-  } else {
-    CUDA_OK(cudaMemcpyAsync(e->d_shards + s->index, &s->h, sizeof(ShardDev), cudaMemcpyHostToDevice, e->st));
   }
   auto describe = [](const Run& r, ShardFast* f) {
     f->run0_heap = (u64)r.heap; f->run0_hslots = (u64)r.hslots; f->n_buckets = r.n_buckets;
@@ -367,12 +363,8 @@ static void upload_shard(rsp_engine* e, rsp_shard* s, bool runs_only = false) {
   ShardFast f;
   memset(&f, 0, sizeof(f));
   if (!s->runs.empty()) describe(*s->runs[0], &f);
-  {
-    ShardFast fr[RSP_MAX_RUNS];
-    memset(fr, 0, sizeof(fr));
-    for (size_t i = 0; i < s->runs.size() && i < RSP_MAX_RUNS; i++) describe(*s->runs[i], &fr[i]);
-    CUDA_OK(cudaMemcpyAsync(e->d_fast_runs + (size_t)s->index * RSP_MAX_RUNS, fr, sizeof(fr), cudaMemcpyHostToDevice, e->st));
-  }
+  memset(fr, 0, sizeof(ShardFast) * RSP_MAX_RUNS);
+  for (size_t i = 0; i < s->runs.size() && i < RSP_MAX_RUNS; i++) describe(*s->runs[i], &fr[i]);
   const bool multi_now = s->runs.size() > 1;
   if (multi_now != s->counted_multirun) {
     if (multi_now) e->n_multirun++; else e->n_multirun--;
@@ -382,9 +374,51 @@ static void upload_shard(rsp_engine* e, rsp_shard* s, bool runs_only = false) {
   f.meta |= 1u << 24;  // live
   f.mt_count = s->h.mt_count;
   f.merge_op = s->h.merge_op;
+  *f_out = f;
+}
+static void upload_shard(rsp_engine* e, rsp_shard* s, bool runs_only = false) {
+  ShardFast f, fr[RSP_MAX_RUNS];
+  describe_shard(e, s, &f, fr);
+  if (runs_only) {
+    const size_t from = offsetof(ShardDev, n_runs);
+    CUDA_OK(cudaMemcpyAsync((u8*)(e->d_shards + s->index) + from, (const u8*)&s->h + from, sizeof(ShardDev) - from,
+                            cudaMemcpyHostToDevice, e->st));
+  } else {
+    CUDA_OK(cudaMemcpyAsync(e->d_shards + s->index, &s->h, sizeof(ShardDev), cudaMemcpyHostToDevice, e->st));
+  }
+  CUDA_OK(cudaMemcpyAsync(e->d_fast_runs + (size_t)s->index * RSP_MAX_RUNS, fr, sizeof(fr), cudaMemcpyHostToDevice, e->st));
   // (runs_only: the first 24 bytes = run 0 + meta; mt_count is written by the sequencing kernels)
   CUDA_OK(cudaMemcpyAsync(e->d_fast + s->index, &f, runs_only ? offsetof(ShardFast, mt_count) : sizeof(f), cudaMemcpyHostToDevice, e->st));
   // the host mirror is pageable: the copy above is staged before the call returns
+}
+// The same for a batch of shards (a flush / merge batch installs up to thousands of descriptors): records staged in
+// pinned memory, one copy, one launch (k_upload_shards) — three pageable copies and a memset per shard cost the
+// install of a 1024-shard flush tens of milliseconds of driver calls.
+struct UploadBatch {
+  std::vector<ShardUpload> recs;
+};
+static void stage_upload(rsp_engine* e, rsp_shard* s, bool runs_only, bool zero_mt, UploadBatch* b) {
+  b->recs.emplace_back();
+  ShardUpload& u = b->recs.back();
+  describe_shard(e, s, &u.fast, u.fast_runs);
+  u.index = s->index; u.runs_only = runs_only ? 1u : 0u; u.zero_mt = zero_mt ? 1u : 0u; u.pad = 0;
+  u.sd = s->h;
+}
+static void commit_uploads(rsp_engine* e, UploadBatch* b) {
+  const size_t n = b->recs.size();
+  if (!n) return;
+  const size_t bytes = n * sizeof(ShardUpload);
+  if (e->up_ev_recorded) CUDA_OK(cudaEventSynchronize(e->up_ev));  // the staging buffers of the previous batch
+  void* pin = e->pin_up.get(bytes);
+  memcpy(pin, b->recs.data(), bytes);
+  ShardUpload* d_up = (ShardUpload*)e->dev_up.get(bytes);
+  CUDA_OK(cudaMemcpyAsync(d_up, pin, bytes, cudaMemcpyHostToDevice, e->st));
+  launch_upload_shards(d_up, (u32)n, e->d_shards, e->d_fast, e->d_fast_runs, e->st);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(e->up_ev, e->st));
+  e->up_ev_recorded = true;
+  e->launches += 1;
+  b->recs.clear();
 }
 
 static u32 next_pow2(u32 x) {
@@ -432,6 +466,7 @@ struct JobHost {
   size_t n_merged;  // srcs.size(): the runs replaced by the output
   std::vector<std::shared_ptr<Run>> srcs;
   size_t items_b, items2_b, coranks_b, keep_b, fold_b;
+  bool generic_sort = false;  // the memtable took the comparison sort (k_flush_sort left it: totals[7])
 };
 // one batch of flush / merge jobs: planned under the engine mutex, run on a stream, installed under the mutex again
 struct CompactPlan {
@@ -439,6 +474,7 @@ struct CompactPlan {
   std::vector<CompactJob> jobs;
   std::vector<std::shared_ptr<Run>> outs;
   CompactJob* d_jobs = nullptr;
+  u32* d_totals = nullptr;  // [8 x jobs], contiguous: one copy brings every job's sizes back
   float ms = 0;
 };
 enum CompactMode {
@@ -543,7 +579,6 @@ static void plan_jobs(rsp_engine* e, const std::vector<rsp_shard*>& shards, Comp
     j.out_pos = (u32*)a.alloc(h.keep_b);
     j.out_ord = (u32*)a.alloc(h.keep_b);
     j.fold_val = (u64*)a.alloc(h.fold_b);
-    j.totals = (u32*)a.alloc(32);
     if (mode == COMPACT_MERGE) {
       s->merging = true;
       s->bg_first_pinned = h.srcs.front().get();
@@ -554,11 +589,14 @@ static void plan_jobs(rsp_engine* e, const std::vector<rsp_shard*>& shards, Comp
 }
 
 // ---- run (no engine mutex needed: sources are pinned, outputs are private until installed) -----------------
-static void run_jobs(rsp_engine* e, CompactPlan* plan, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+static void run_jobs(rsp_engine* e, CompactPlan* plan, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, PinBuf* pin_totals) {
   Arena& a = e->arena;
   std::vector<CompactJob>& jobs = plan->jobs;
   const u32 nj = (u32)jobs.size();
   plan->d_jobs = (CompactJob*)a.alloc(sizeof(CompactJob) * nj);
+  plan->d_totals = (u32*)a.alloc((size_t)32 * nj);
+  for (u32 i = 0; i < nj; i++) jobs[i].totals = plan->d_totals + 8 * (size_t)i;
+  CUDA_OK(cudaMemsetAsync(plan->d_totals, 0, (size_t)32 * nj, st));
   CompactJob* d_jobs = plan->d_jobs;
   CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CompactJob) * nj, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaEventRecord(ev0, st));
@@ -566,16 +604,17 @@ static void run_jobs(rsp_engine* e, CompactPlan* plan, cudaStream_t st, cudaEven
   launch_compact_size(d_jobs, nj, st);
   CUDA_OK(cudaGetLastError());  // a refused launch (e.g. shared-memory opt-in) must not pass as an unsorted run
   e->launches += 5;
-  std::vector<u32> totals(8 * nj);
-  for (u32 i = 0; i < nj; i++)
-    CUDA_OK(cudaMemcpyAsync(&totals[8 * i], jobs[i].totals, 32, cudaMemcpyDeviceToHost, st));
+  // the sizing round trip: ONE copy into pinned memory (r02 issued a 32-byte pageable copy per job)
+  const u32* totals = (const u32*)pin_totals->get((size_t)32 * nj);
+  CUDA_OK(cudaMemcpyAsync((void*)totals, plan->d_totals, (size_t)32 * nj, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
-  u32 max_items = 0;
+  u32 max_items = 0, max_buckets = 0;
   plan->outs.resize(nj);
   for (u32 i = 0; i < nj; i++) {
     CompactJob& j = jobs[i];
     const u32 units = totals[8 * i], ents = totals[8 * i + 1], uni = totals[8 * i + 2], keys = totals[8 * i + 3];
     const u32 non_put = totals[8 * i + 4], kvmin = totals[8 * i + 5], kvmax = totals[8 * i + 6];
+    plan->jh[i].generic_sort = totals[8 * i + 7] != 0;
     auto r = std::make_shared<Run>();
     r->arena = &a;
     r->n_ent = ents; r->heap_units = units; r->uniform_units = uni;
@@ -590,16 +629,17 @@ static void run_jobs(rsp_engine* e, CompactPlan* plan, cudaStream_t st, cudaEven
     r->ent_off = (u32*)a.alloc((size_t)ents * 4);
     r->hslots = (u32*)a.alloc((size_t)r->n_buckets * RUN_BUCKET_SLOTS * 4);
     r->blk_pfx = (u64*)a.alloc(blk_pfx_bytes(r->n_blocks));
-    CUDA_OK(cudaMemsetAsync(r->hslots, 0, (size_t)r->n_buckets * RUN_BUCKET_SLOTS * 4, st));
+    max_buckets = std::max(max_buckets, r->n_buckets);
     j.out_heap = r->heap; j.out_ent_off = r->ent_off; j.out_hslots = r->hslots; j.out_blk_pfx = r->blk_pfx;
     j.out_n_buckets = r->n_buckets; j.out_ord_bits = r->ord_bits;
     plan->outs[i] = r;
     max_items = std::max(max_items, j.n_items);
   }
   CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CompactJob) * nj, cudaMemcpyHostToDevice, st));
+  launch_zero_out_hslots(d_jobs, nj, max_buckets, st);  // every output's hash index in one launch
   launch_compact_write(d_jobs, nj, max_items, st);
   CUDA_OK(cudaGetLastError());
-  e->launches += 1;
+  e->launches += 2;
   CUDA_OK(cudaEventRecord(ev1, st));
   CUDA_OK(cudaStreamSynchronize(st));
   cudaEventElapsedTime(&plan->ms, ev0, ev1);
@@ -617,10 +657,11 @@ static void release_work(rsp_engine* e, CompactPlan* plan) {
     a.release(j.out_pos, h.keep_b);
     a.release(j.out_ord, h.keep_b);
     a.release(j.fold_val, h.fold_b);
-    a.release(j.totals, 32);
   }
   if (plan->d_jobs) a.release(plan->d_jobs, sizeof(CompactJob) * plan->jobs.size());
+  if (plan->d_totals) a.release(plan->d_totals, (size_t)32 * plan->jobs.size());
   plan->d_jobs = nullptr;
+  plan->d_totals = nullptr;
 }
 
 // ---- install (engine mutex held): the new run takes the place of its sources in the shard's run list; readers keep
@@ -628,6 +669,8 @@ static void release_work(rsp_engine* e, CompactPlan* plan) {
 static void install_jobs(rsp_engine* e, CompactPlan* plan, CompactMode mode) {
   const u32 nj = (u32)plan->jobs.size();
   if (mode == COMPACT_MERGE) wait_readers(e);  // (the foreground path did this before it touched a memtable)
+  UploadBatch up;
+  up.recs.reserve(nj);
   for (u32 i = 0; i < nj; i++) {
     JobHost& h = plan->jh[i];
     rsp_shard* s = h.s;
@@ -650,6 +693,7 @@ static void install_jobs(rsp_engine* e, CompactPlan* plan, CompactMode mode) {
     s->stats.compaction_bytes_read += read_b;
     s->stats.compaction_bytes_written += plan->outs[i]->bytes();
     if (h.has_mem) s->stats.flushes++;
+    if (h.has_mem && h.generic_sort) s->stats.flush_comparison_sorts++;
     // the sources sit where they were planned, possibly behind runs that were flushed meanwhile (background merges)
     size_t at = 0;
     if (h.n_merged) {
@@ -661,10 +705,10 @@ static void install_jobs(rsp_engine* e, CompactPlan* plan, CompactMode mode) {
     if (h.has_mem) {
       s->h.mt_tail = 0;
       s->h.mt_count = 0;
-      CUDA_OK(cudaMemsetAsync(s->h.mt_slots, 0, s->mt_slot_bytes, e->st));
     }
-    upload_shard(e, s, mode == COMPACT_MERGE);
+    stage_upload(e, s, mode == COMPACT_MERGE, h.has_mem, &up);  // (+ the flushed memtable's slot table cleared)
   }
+  commit_uploads(e, &up);
   note_mutation(e);
   CUDA_OK(cudaStreamSynchronize(e->st));  // sources may be released once nothing reads them
   e->last_ms["compact"] = plan->ms;
@@ -682,7 +726,7 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
   plan_jobs(e, shards, mode, &plan);
   if (plan.jobs.empty()) return;
   wait_readers(e);
-  run_jobs(e, &plan, e->st, e->ev0, e->ev1);
+  run_jobs(e, &plan, e->st, e->ev0, e->ev1, &e->pin_totals);
   install_jobs(e, &plan, mode);
   release_work(e, &plan);
 }
@@ -692,7 +736,7 @@ static std::shared_ptr<Run> snapshot_memtable(rsp_engine* e, rsp_shard* s) {
   CompactPlan plan;
   plan_jobs(e, {s}, COMPACT_SNAPSHOT, &plan);
   if (plan.jobs.empty()) return nullptr;
-  run_jobs(e, &plan, e->st, e->ev0, e->ev1);
+  run_jobs(e, &plan, e->st, e->ev0, e->ev1, &e->pin_totals);
   release_work(e, &plan);
   s->stats.compaction_bytes_read += (u64)s->h.mt_tail * 16;
   return plan.outs[0]->n_ent ? plan.outs[0] : nullptr;
@@ -710,6 +754,7 @@ struct Compactor {
   bool stop = false, busy = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  PinBuf pin_totals;  // this thread's sizing round trips
   std::thread th;
   void loop();
 };
@@ -745,7 +790,7 @@ void Compactor::loop() {
         plan_jobs(e, live, COMPACT_MERGE, &plan);
       }
       if (plan.jobs.empty()) continue;
-      run_jobs(e, &plan, stream, ev0, ev1);
+      run_jobs(e, &plan, stream, ev0, ev1, &pin_totals);
       {
         std::lock_guard<std::mutex> g(e->mu);
         cudaSetDevice(e->device);
@@ -771,6 +816,14 @@ static const bool g_trace = getenv("RSP_TRACE") != nullptr;
 
 // Build the tick image (pinned) for n batches and copy it to the device.  Layout of the image:
 //   [BatchDesc x n][GroupDesc x g][blob ...] ; results [BatchRes x n][GroupRes x g] ; [OpRec x ops]
+// Pitch of a batch in a staged image: whole 4-byte words, an ODD number of them — k_tick_fused walks a batch per thread
+// in shared memory, and equal-sized batches at an even word pitch (r02 padded to 16 bytes: 128 for the 115-byte
+// replication unit) put all 32 lanes of a warp on the same bank (ncu: 29.7-way conflicts, 97 % of the wavefronts).
+static inline size_t stage_pitch(size_t len_eff) {
+  const size_t w = (len_eff + 3) / 4;
+  return 4 * (w | 1);
+}
+
 static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint8_t* blob, const uint64_t* off,
                        const uint64_t* ts_ms, rsp_staged* sg, bool own_dev) {
   sg->eng = e;
@@ -840,13 +893,13 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
         // upper bound on heap units: 2 header units + padding per op, payload bytes / 16
         sg->need_units[g] += cap * 4u + (u32)(len_eff / 16) + 1u;
         sg->need_ents[g] += cap;
-        boff += align_up(len_eff, 16);
+        boff += stage_pitch(len_eff);
         if (boff > 0xf0000000ull) return RSP_INVALID_ARGUMENT;
       }
     }
   }
   if (ops_cap > 0xfff00000ull) return RSP_INVALID_ARGUMENT;
-  const size_t blob_bytes = boff + 64;  // slack for the insert kernel's aligned word reads
+  const size_t blob_bytes = align_up(boff + 64, 256);  // slack for the insert kernel's aligned word reads; what follows stays aligned
   // [BatchDesc x n][GroupDesc x g][u64 off x n][u32 len x n] | blob : the last two feed the fused tick kernel
   const size_t o_foff = align_up(n * sizeof(BatchDesc) + ng * sizeof(GroupDesc), 16);
   const size_t o_flen = o_foff + n * 8;
@@ -878,7 +931,7 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
         dst[len + 1] = 8;
         memcpy(dst + len + 2, &ts_ms[i], 8);
       }
-      const size_t padded = align_up(len_eff, 16);
+      const size_t padded = stage_pitch(len_eff);
       if (padded > len_eff) memset(dst + len_eff, 0, padded - len_eff);
       BatchDesc& b = bd[pos];
       const u32 g = g_of[i];
@@ -937,6 +990,7 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
     FusedTick& f = sg->ftick;
     f.blob = t.blob; f.off = (const u64*)(dev + o_foff); f.len = (const u32*)(dev + o_flen); f.ts = nullptr;
     f.groups = t.groups; f.bstat = t.bstat; f.gres = t.gres; f.n_groups = (u32)ng; f.n_batches = (u32)n;
+    f.max_group = (u32)max_group; f.max_len = (u32)(max_len + 16);
   }
   if (own_dev) CUDA_OK(cudaStreamSynchronize(e->st));  // the pinned staging buffer is reused
   return RSP_OK;
@@ -1127,6 +1181,7 @@ static int apply_many_packed(rsp_engine* e, size_t n, const uint32_t* shard_ix, 
     f.blob = dev + o_blob; f.off = (const u64*)(dev + o_off); f.len = nullptr; f.ts = ts_ms ? (const u64*)(dev + o_ts) : nullptr;
     f.groups = (const GroupDesc*)(dev + o_groups); f.gres = (GroupRes*)(dev + o_out);
     f.bstat = (u32*)(dev + o_out + ng * sizeof(GroupRes)); f.n_groups = (u32)ng; f.n_batches = (u32)n;
+    f.max_group = (u32)max_group; f.max_len = (u32)(max_len + 16);
     sg.tick.gres = f.gres;
   } else {
     CUDA_OK(cudaMemsetAsync(dev + o_need, 0, (2 * ng + 1) * 4, e->st));
@@ -1901,6 +1956,7 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   CUDA_OK(cudaEventCreateWithFlags(&e->mut_ev, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&e->ev0));
   CUDA_OK(cudaEventCreate(&e->ev1));
+  CUDA_OK(cudaEventCreateWithFlags(&e->up_ev, cudaEventDisableTiming));
   CUDA_OK(cudaMalloc(&e->d_shards, sizeof(ShardDev) * e->cfg.max_shards));
   CUDA_OK(cudaMemset(e->d_shards, 0, sizeof(ShardDev) * e->cfg.max_shards));
   {
@@ -1937,6 +1993,7 @@ void rsp_engine_destroy(rsp_engine* e) {
     cudaStreamDestroy(c->stream);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    c->pin_totals.destroy();
     delete c;
     e->compactor = nullptr;
   }
@@ -1947,10 +2004,10 @@ void rsp_engine_destroy(rsp_engine* e) {
   for (rsp_shard* s : e->slots)
     if (s) { s->runs.clear(); delete s; }
   e->arena.destroy();
-  e->pin_in.destroy(); e->pin_out.destroy(); e->dev_tick.destroy(); e->dev_q.destroy(); e->dev_pending.destroy(); e->dev_ops.destroy();
+  e->pin_in.destroy(); e->pin_out.destroy(); e->pin_up.destroy(); e->pin_totals.destroy(); e->dev_up.destroy(); e->dev_tick.destroy(); e->dev_q.destroy(); e->dev_pending.destroy(); e->dev_ops.destroy();
   cudaFree(e->d_shards);
   cudaFree(e->d_fast);
-  cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+  cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->up_ev);
   for (int k = 0; k < 8; k++) cudaEventDestroy(e->reader_ev[k]);
   cudaEventDestroy(e->mut_ev);
   for (int k = 0; k < 3; k++) { cudaStreamDestroy(e->cs[k]); cudaEventDestroy(e->cs_done[k]); }
@@ -2818,6 +2875,13 @@ float rsp_last_kernel_ms(const rsp_engine* e, const char* what) {
   } catch (...) { abi_caught(); return -1.f; }
 }
 uint64_t rsp_kernel_launches(const rsp_engine* e) { return e->launches.load(); }
+
+void rsp_debug_combiner_stats(rsp_engine* e, int which, uint64_t out[5]) {
+  for (int i = 0; i < 5; i++) out[i] = 0;
+  if (!e) return;
+  if (which == 0) { if (ReadCombiner* c = e->read_comb_ready.load(std::memory_order_acquire)) c->stager->stats(out); }
+  else if (ApplyCombiner* c = e->apply_comb_ready.load(std::memory_order_acquire)) c->stager->stats(out);
+}
 
 // diagnostics: how many lookups of the last MultiGet launch took the generic path (synchronises)
 uint32_t rsp_debug_last_pending(rsp_engine* e, uint32_t* first, uint32_t cap) {

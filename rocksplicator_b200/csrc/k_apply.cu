@@ -352,10 +352,10 @@ __device__ __forceinline__ bool eq_heap_keys_cg(const u8* a, u32 an, const u8* b
     if (ld_cg_u64(reinterpret_cast<const u64*>(a) + i) != ld_cg_u64(reinterpret_cast<const u64*>(b) + i)) return false;
   return true;
 }
-__device__ __noinline__ void link_into_table(ShardDev* sd, u8* heap, u8* ent, u32 unit, u32 klen, u64 h) {
+// `first` is the home slot's word, loaded by the caller BEFORE its __threadfence (the probe's first round trip overlaps
+// the fence's wait for the entry stores).
+__device__ __noinline__ void link_into_table(ShardDev* sd, u64* slots, u32 mask, u8* heap, u8* ent, u32 unit, u32 klen, u64 h, u64 first) {
   const u32 tag = hash_tag32(h);
-  const u32 mask = sd->mt_slot_mask;
-  u64* slots = sd->mt_slots;
   const u32 P = unit + 1u;
   u32* my_link = reinterpret_cast<u32*>(ent + 16);
   u32 idx = (u32)h & mask;
@@ -367,7 +367,7 @@ __device__ __noinline__ void link_into_table(ShardDev* sd, u8* heap, u8* ent, u3
       atomicCAS(&sd->latch, 0u, mk_status(5, MSG_TOO_LARGE));
       return;
     }
-    u64 cur = ld_cg_u64(slots + idx);
+    u64 cur = probes ? ld_cg_u64(slots + idx) : first;
     if (cur == 0) {
       const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(slots + idx), 0ull, ((u64)tag << 32) | P);
       if (old == 0) return;  // first version of a new key
@@ -458,10 +458,13 @@ __global__ void __launch_bounds__(256) k_insert(TickDev t, ShardDev* shards) {
     sd->mt_ent_off[ord] = unit;
   }
   if (lane == 1) *reinterpret_cast<uint4*>(ent + 16) = make_uint4(0u, 0u, (u32)h, (u32)(h >> 32));
+  u64* slots = sd->mt_slots;
+  const u32 mask = sd->mt_slot_mask;
+  const u64 first = lane == 0 ? ld_cg_u64(slots + ((u32)h & mask)) : 0ull;
   __threadfence();  // the entry is complete before any pointer to it is published
   __syncwarp(gmask);
   if (lane != 0) return;
-  link_into_table(sd, heap, ent, unit, op.klen, h);
+  link_into_table(sd, slots, mask, heap, ent, unit, op.klen, h, first);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -477,29 +480,34 @@ __global__ void __launch_bounds__(256) k_insert(TickDev t, ShardDev* shards) {
 // Against k_decode -> k_sequence -> k_insert -> k_publish this drops three launches and all the per-batch / per-op
 // records in global memory (BatchDesc, BatchRes, OpRec: ~350 bytes of traffic per 105-byte batch).
 // ------------------------------------------------------------------------------------------------
-constexpr u32 FT_THREADS = 128;
-constexpr u32 FT_STAGE = 32768;  // bytes of batches staged per chunk
+// Two shapes: 128 threads / 16 KB stage (8 CTAs per SM at 64 registers: a 1024-group tick is one wave) for long groups, 64 threads / 8 KB stage when no group of the tick
+// holds more than 64 batches (the pull protocol's <= 50 per shard: every CTA of a 1024-shard tick is resident at once).
+constexpr u32 FT_STAGE_PER_THREAD = 128;  // bytes of stage per thread: a chunk of single-Put batches (105-116 B) fills the block
 
-__device__ __forceinline__ u32 block_excl_scan(u32 v, u32* s_warp, u32* total) {
+// exclusive block-wide prefix sums of two values at once: one exchange through shared memory, ONE barrier (before the
+// read; the caller's next barrier protects the reuse of s_warp)
+template <u32 THREADS>
+__device__ __forceinline__ void block_excl_scan2(u32 a, u32 b, u32 (*s_warp)[2], u32* a_excl, u32* b_excl, u32* a_tot, u32* b_tot) {
   const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-  const u32 incl = warp_incl_scan(v, lane);
-  if (lane == 31) s_warp[wid] = incl;
+  const u32 ai = warp_incl_scan(a, lane), bi = warp_incl_scan(b, lane);
+  if (lane == 31) { s_warp[wid][0] = ai; s_warp[wid][1] = bi; }
   __syncthreads();
-  u32 base = 0, tot = 0;
+  u32 ab = 0, bb = 0, at = 0, bt = 0;
 #pragma unroll
-  for (u32 w = 0; w < FT_THREADS / 32; w++) {
-    const u32 x = s_warp[w];
-    if (w < wid) base += x;
-    tot += x;
+  for (u32 w = 0; w < THREADS / 32; w++) {
+    const u32 x = s_warp[w][0], y = s_warp[w][1];
+    if (w < wid) { ab += x; bb += y; }
+    at += x; bt += y;
   }
-  __syncthreads();
-  *total = tot;
-  return base + incl - v;
+  *a_excl = ab + ai - a; *b_excl = bb + bi - b;
+  *a_tot = at; *b_tot = bt;
 }
 
-__global__ void __launch_bounds__(FT_THREADS) k_tick_fused(FusedTick t, ShardDev* shards, ShardFast* fast) {
-  __shared__ __align__(16) u8 s_blob[FT_STAGE + 64];
-  __shared__ u32 s_warp[FT_THREADS / 32];
+template <u32 THREADS, u32 MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_tick_fused(FusedTick t, ShardDev* shards, ShardFast* fast) {
+  constexpr u32 STAGE = THREADS * FT_STAGE_PER_THREAD;
+  __shared__ __align__(16) u8 s_blob[STAGE + 64];
+  __shared__ u32 s_warp[THREADS / 32][2];
   __shared__ u32 s_first_bad, s_first_over, s_first_status, s_tot_ops, s_tot_units;
   const u32 tid = threadIdx.x;
   const GroupDesc g = t.groups[blockIdx.x];
@@ -510,66 +518,71 @@ __global__ void __launch_bounds__(FT_THREADS) k_tick_fused(FusedTick t, ShardDev
   u32 tail = sd->mt_tail, cnt = sd->mt_count;
   const u32 heap_cap = sd->mt_heap_cap, ent_cap = sd->mt_ent_cap;
   u8* heap = sd->mt_heap;
+  u64* slots = sd->mt_slots;
+  u32* ent_off = sd->mt_ent_off;
+  const u32 slot_mask = sd->mt_slot_mask;
   const u32 trailer = t.ts ? 10u : 0u;
   bool stop = false;  // the memtable is full: the rest of the group is refused (busy), unlatched
+  if (tid == 0) { s_first_bad = 0xffffffffu; s_first_over = 0xffffffffu; s_first_status = 0; }
   for (u32 c0 = 0; c0 < g.n_batches;) {
     const u32 b0 = g.first_batch + c0;
     const u64 base = __ldg(t.off + b0);
-    // ---- chunk extent: as many of the next FT_THREADS batches as fit the stage
+    // ---- chunk extent: as many of the next THREADS batches as fit the stage
     const u32 j = c0 + tid;
     u64 my_off = 0, my_end = 0;
     bool fits = false;
     if (j < g.n_batches) {
       my_off = __ldg(t.off + b0 + tid);
       my_end = t.len ? my_off + __ldg(t.len + b0 + tid) : __ldg(t.off + b0 + tid + 1);
-      fits = my_end - base <= FT_STAGE;
+      fits = my_end - base <= STAGE;
     }
     const u32 n_in = (u32)__syncthreads_count(fits);  // offsets grow: the fitting batches are a prefix
-    if (tid == 0) { s_first_bad = 0xffffffffu; s_first_over = 0xffffffffu; s_first_status = 0; }
     if (n_in == 0) {
       // a batch larger than the stage (the host routes such ticks to the general kernels; kept as a guard)
       if (tid == 0) t.bstat[b0] = latch ? latch : mk_status(11, MSG_TOO_LARGE);
-      __syncthreads();
       c0 += 1;
       continue;
     }
-    // (staged images pad every batch to 16 bytes: the last batch's own end bounds the chunk)
+    // (the last fitting batch's own end bounds the chunk)
     const u32 chunk_bytes = (u32)((t.len ? __ldg(t.off + b0 + n_in - 1) + __ldg(t.len + b0 + n_in - 1) : __ldg(t.off + b0 + n_in)) - base);
     // ---- stage (aligned 16-byte loads; `shift` leading bytes belong to the previous batch / group)
     const u8* src = t.blob + base;
     const u32 shift = (u32)(reinterpret_cast<uintptr_t>(src) & 15u);
     const uint4* src4 = reinterpret_cast<const uint4*>(src - shift);
     const u32 n_units = (shift + chunk_bytes + 15u) >> 4;
-    for (u32 u = tid; u < n_units; u += FT_THREADS) reinterpret_cast<uint4*>(s_blob)[u] = __ldg(src4 + u);
+    for (u32 u = tid; u < n_units; u += THREADS) reinterpret_cast<uint4*>(s_blob)[u] = __ldg(src4 + u);
+    const bool in = tid < n_in;
+    const u64 my_ts = (in && t.ts) ? __ldg(t.ts + b0 + tid) : 0ull;
     __syncthreads();
     // ---- decode (count pass)
-    const bool in = tid < n_in;
-    Cursor c{s_blob + shift + (u32)(my_off - base), 12, (u32)(my_end - my_off) + trailer, (u32)(my_end - my_off),
-             (in && t.ts) ? __ldg(t.ts + b0 + tid) : 0ull};
+    Cursor c{s_blob + shift + (u32)(my_off - base), 12, (u32)(my_end - my_off) + trailer, (u32)(my_end - my_off), my_ts};
     WalkResult w{0u, 0u, 0u};
     if (in) w = walk_batch(c, [](u32, u32, u32, u32, u32, u32, u32) {});
     if (in && w.status) atomicMin(&s_first_bad, tid);
-    __syncthreads();
-    const u32 first_bad = s_first_bad;
-    if (in && tid == first_bad) s_first_status = w.status;
+    // ---- sequence: the prefix sums run over every well-formed batch of the chunk; what lies behind the first failure
+    // (or the first batch without room) is cut off afterwards — a prefix does not depend on what follows it
+    u32 ops_excl, units_excl, tot_ops, tot_units;
+    block_excl_scan2<THREADS>(w.status ? 0u : w.n_ops, w.status ? 0u : w.units, s_warp, &ops_excl, &units_excl, &tot_ops, &tot_units);
+    const u32 first_bad = s_first_bad;  // (the scan's barrier ordered the atomicMin)
     const bool stopped = stop;
-    bool accepted = in && latch == 0 && !stopped && tid < first_bad;
-    u32 tot_ops, tot_units;
-    const u32 ops_excl = block_excl_scan(accepted ? w.n_ops : 0u, s_warp, &tot_ops);
-    const u32 units_excl = block_excl_scan(accepted ? w.units : 0u, s_warp, &tot_units);
+    const bool live = latch == 0 && !stopped;
     // defensive capacity guard (the host reserves from an estimate): the first batch that does not fit and everything
     // after it is refused, unlatched
-    const bool over = accepted && ((u64)tail + units_excl + w.units > heap_cap || (u64)cnt + ops_excl + w.n_ops > ent_cap);
+    const bool over = in && live && tid < first_bad && ((u64)tail + units_excl + w.units > heap_cap || (u64)cnt + ops_excl + w.n_ops > ent_cap);
     if (over) atomicMin(&s_first_over, tid);
+    if (in && tid == first_bad) { s_first_status = w.status; s_tot_ops = ops_excl; s_tot_units = units_excl; }
     __syncthreads();
     const u32 first_over = s_first_over, first_status = s_first_status;
-    if (tid >= first_over) accepted = false;
+    if (first_bad != 0xffffffffu) { tot_ops = s_tot_ops; tot_units = s_tot_units; }
     if (first_over != 0xffffffffu) {  // totals of the accepted prefix only: the exclusive sums at the first refused batch
+      __syncthreads();
       if (tid == first_over) { s_tot_ops = ops_excl; s_tot_units = units_excl; }
       __syncthreads();
       tot_ops = s_tot_ops;
       tot_units = s_tot_units;
     }
+    if (!live) { tot_ops = 0; tot_units = 0; }
+    const bool accepted = in && live && tid < first_bad && tid < first_over;
     if (in) {
       u32 st_out = 0;
       if (!accepted) {
@@ -610,9 +623,10 @@ __global__ void __launch_bounds__(FT_THREADS) k_tick_fused(FusedTick t, ShardDev
         const u64 st = ((seq_base + op_ix) << 8) | type;
         *reinterpret_cast<uint4*>(ent) = make_uint4((u32)st, (u32)(st >> 32), klen, vlen);
         *reinterpret_cast<uint4*>(ent + 16) = make_uint4(0u, 0u, (u32)h, (u32)(h >> 32));
-        sd->mt_ent_off[ord_base + op_ix] = unit;
+        ent_off[ord_base + op_ix] = unit;
+        const u64 first = ld_cg_u64(slots + ((u32)h & slot_mask));  // (in flight across the fence)
         __threadfence();  // the entry is complete before any pointer to it is published
-        link_into_table(sd, heap, ent, unit, klen, h);
+        link_into_table(sd, slots, slot_mask, heap, ent, unit, klen, h, first);
       });
     }
     // ---- group state after this chunk (uniform)
@@ -620,10 +634,11 @@ __global__ void __launch_bounds__(FT_THREADS) k_tick_fused(FusedTick t, ShardDev
     tail += tot_units;
     cnt += tot_ops;
     const u32 lim = min(n_in, first_over);
-    if (latch == 0 && !stopped && first_bad < lim) latch = first_status;
+    if (live && first_bad < lim) latch = first_status;
     if (first_over != 0xffffffffu && latch == 0) stop = true;
     c0 += n_in;
     __syncthreads();  // s_blob and the chunk scalars are reused
+    if (tid == 0) { s_first_bad = 0xffffffffu; s_first_over = 0xffffffffu; s_first_status = 0; }
   }
   __threadfence();
   __syncthreads();
@@ -643,7 +658,8 @@ __global__ void __launch_bounds__(FT_THREADS) k_tick_fused(FusedTick t, ShardDev
 
 void launch_tick_fused(const FusedTick& t, ShardDev* shards, ShardFast* fast, cudaStream_t s) {
   if (!t.n_groups) return;
-  k_tick_fused<<<t.n_groups, FT_THREADS, 0, s>>>(t, shards, fast);
+  if (t.max_group <= 64 && t.max_len <= 4096) k_tick_fused<64, 16><<<t.n_groups, 64, 0, s>>>(t, shards, fast);
+  else k_tick_fused<128, 8><<<t.n_groups, 128, 0, s>>>(t, shards, fast);
 }
 
 // ------------------------------------------------------------------------------------------------

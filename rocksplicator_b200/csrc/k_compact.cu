@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(1024) k_compact_sort(const CompactJob* jobs) {
   SortItem* tile = reinterpret_cast<SortItem*>(sort_smem);
   const CompactJob& j = jobs[blockIdx.x];
   const u32 n = j.n_pow2;  // the memtable segment at items[0 .. n_pow2); nothing to sort without a memtable
-  if (n < 2) return;
+  if (n < 2 || j.totals[7] == 0) return;  // (totals[7] == 0: k_flush_sort has sorted it)
   SortItem* it = j.items;
   const u32 tile_n = n < SORT_TILE ? n : SORT_TILE;
   // phase 1: every tile fully sorted (all steps with k <= tile_n), directions by GLOBAL index
@@ -152,6 +152,164 @@ __global__ void __launch_bounds__(1024) k_compact_sort(const CompactJob* jobs) {
       __syncthreads();
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// k_flush_sort — the memtable segment by LSD radix sort in shared memory (one CTA per shard).
+//
+// The sort key of an entry is its 8-byte big-endian key prefix; within a shard the prefixes differ in their low V bits
+// only (V from min ^ max), so an item packs into ONE 64-bit word: (varying prefix bits << 16) | rank, the rank (newest
+// first) in the low 16 bits.  ceil(V / 8) stable counting passes order the words by prefix and, being stable, leave
+// equal prefixes in rank order — what the compaction wants for the versions of one key.  A pass: every warp owns a
+// contiguous range, rows of 32 are ranked with __match_any_sync (no atomics: one histogram row per warp), the digit
+// totals are scanned, the words are scattered.  The two buffers are shared memory and the (dead) front half of the
+// job's own items[] in global memory, alternating so that the last pass lands in shared memory, from where the sorted
+// SortItems are written out coalesced.  Afterwards neighbours with equal prefixes are compared in full: distinct keys
+// that share their first 8 bytes (or V > 48, or a memtable beyond the shared-memory budget) leave the job to the
+// generic comparison sort (k_compact_sort), flagged in totals[7].  The bitonic network this replaces moved every
+// 16-byte item through shared memory ~180 times per 8 K-entry memtable; here it is 2 x ceil(V / 8) + 2 times.
+// ------------------------------------------------------------------------------------------------------------
+constexpr u32 FS_THREADS = 512;
+constexpr u32 FS_WARPS = FS_THREADS / 32;
+constexpr u32 FS_MAX_ITEMS = 24576;  // 192 KB of packed words + 8 KB of histograms: one CTA per SM at that size
+
+__global__ void __launch_bounds__(FS_THREADS) k_flush_sort(const CompactJob* jobs, u32 cap) {
+#ifdef RSP_EMUL
+  unsigned char* fs_smem = emul_dyn_smem;
+#else
+  extern __shared__ __align__(16) unsigned char fs_smem[];
+#endif
+  __shared__ unsigned long long s_min, s_max;
+  __shared__ u32 s_bad, s_dig_tot[256], s_dig_base[256];
+  const CompactJob& j = jobs[blockIdx.x];
+  const u32 tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  const u32 n = (j.n_src >= 1 && j.src_is_mem[0]) ? j.src_n[0] : 0u;
+  if (tid == 0) { j.totals[7] = n >= 2 ? 1u : 0u; s_min = ~0ull; s_max = 0ull; s_bad = 0; }  // 1: the generic sort is still needed
+  if (n < 2 || n > cap) return;
+  u64* keys = reinterpret_cast<u64*>(fs_smem);                          // [cap]
+  u16* hist = reinterpret_cast<u16*>(fs_smem + (size_t)cap * 8);        // [FS_WARPS][256]
+  SortItem* items = j.items;
+  u64* gbuf = reinterpret_cast<u64*>(items);  // n words over items[0 .. n/2): dead once the prefixes sit in shared memory
+  __syncthreads();
+  // ---- range of the prefixes
+  {
+    u64 mn = ~0ull, mx = 0ull;
+    for (u32 i = tid; i < n; i += FS_THREADS) {
+      const u64 p = items[i].prefix;
+      mn = min(mn, p); mx = max(mx, p);
+    }
+#pragma unroll
+    for (u32 d = 16; d > 0; d >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    if (lane == 0) { atomicMin(&s_min, (unsigned long long)mn); atomicMax(&s_max, (unsigned long long)mx); }
+  }
+  __syncthreads();
+  const u64 pmin = s_min, diff = s_min ^ s_max;
+  const u32 V = diff ? 64u - (u32)__clzll((long long)diff) : 0u;
+  if (V > 48u) return;  // (uniform) the varying bits do not fit beside the rank
+  const u64 vmask = V ? (~0ull >> (64u - V)) : 0ull;
+  const u32 P = (V + 7u) / 8u;
+  // ---- packed words in rank order: rank r = item n-1-r (k_compact_fill stores the memtable in ordinal order)
+  for (u32 r = tid; r < n; r += FS_THREADS) keys[r] = ((items[n - 1u - r].prefix & vmask) << 16) | (u64)r;
+  __syncthreads();
+  if (P & 1u) {  // an odd number of passes starts from the global buffer, so that the last one ends in shared memory
+    for (u32 r = tid; r < n; r += FS_THREADS) __stcg(reinterpret_cast<unsigned long long*>(gbuf) + r, (unsigned long long)keys[r]);
+    __syncthreads();
+  }
+  const u32 per = ((n + FS_WARPS - 1u) / FS_WARPS + 31u) & ~31u;  // a warp's contiguous range, whole rows
+  const u32 w_lo = min(n, wid * per), w_hi = min(n, w_lo + per);
+  u16* my_hist = hist + wid * 256u;
+  const u32 lt_mask = (1u << lane) - 1u;
+  for (u32 pass = 0; pass < P; pass++) {
+    const u32 shift = 16u + 8u * pass;
+    const bool src_smem = ((P - pass) & 1u) == 0u;
+    for (u32 i = tid; i < FS_WARPS * 256u; i += FS_THREADS) hist[i] = 0;
+    __syncthreads();
+    // count
+    for (u32 row = w_lo; row < w_hi; row += 32u) {
+      const u32 i = row + lane;
+      const bool valid = i < w_hi;
+      const u64 key = valid ? (src_smem ? keys[i] : (u64)__ldcg(reinterpret_cast<const unsigned long long*>(gbuf) + i)) : 0ull;
+      const u32 d = valid ? (u32)(key >> shift) & 255u : (256u + lane);
+      const u32 m = __match_any_sync(0xffffffffu, d);
+      if (valid && (m & lt_mask) == 0u) my_hist[d] = (u16)(my_hist[d] + __popc(m));
+      __syncwarp();
+    }
+    __syncthreads();
+    // digit-major, warp-minor exclusive offsets
+    if (tid < 256u) {
+      u32 run = 0;
+      for (u32 w = 0; w < FS_WARPS; w++) {
+        const u32 c = hist[w * 256u + tid];
+        hist[w * 256u + tid] = (u16)run;
+        run += c;
+      }
+      s_dig_tot[tid] = run;
+    }
+    __syncthreads();
+    if (wid == 0) {
+      u32 v[8], sum = 0;
+#pragma unroll
+      for (u32 q = 0; q < 8; q++) { v[q] = s_dig_tot[lane * 8u + q]; sum += v[q]; }
+      u32 incl = sum;
+#pragma unroll
+      for (u32 d = 1; d < 32; d <<= 1) {
+        const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      u32 base = incl - sum;
+#pragma unroll
+      for (u32 q = 0; q < 8; q++) { s_dig_base[lane * 8u + q] = base; base += v[q]; }
+    }
+    __syncthreads();
+    // scatter (the source rows are re-read: a word is 8 bytes, a register array of a whole range is not)
+    for (u32 row = w_lo; row < w_hi; row += 32u) {
+      const u32 i = row + lane;
+      const bool valid = i < w_hi;
+      const u64 key = valid ? (src_smem ? keys[i] : (u64)__ldcg(reinterpret_cast<const unsigned long long*>(gbuf) + i)) : 0ull;
+      const u32 d = valid ? (u32)(key >> shift) & 255u : (256u + lane);
+      const u32 m = __match_any_sync(0xffffffffu, d);
+      u32 dst = 0;
+      if (valid) dst = s_dig_base[d] + my_hist[d] + (u32)__popc(m & lt_mask);
+      __syncwarp();
+      if (valid && (m & lt_mask) == 0u) my_hist[d] = (u16)(my_hist[d] + __popc(m));
+      __syncwarp();
+      if (valid) {
+        if (src_smem) __stcg(reinterpret_cast<unsigned long long*>(gbuf) + dst, (unsigned long long)key);
+        else keys[dst] = key;
+      }
+    }
+    __syncthreads();
+  }
+  // (a shared-memory source is scattered into global memory and the other way round: no pass overwrites what another
+  // warp still reads)
+  // ---- the sorted SortItems, coalesced; neighbours with equal prefixes must be versions of ONE key
+  const u8* heap = j.src_heap[0];
+  const u32* ent_off = j.src_ent_off[0];
+  const u64 phigh = pmin & ~vmask;
+  for (u32 p = tid; p < n; p += FS_THREADS) {
+    const u64 key = keys[p];
+    const u32 r = (u32)key & 0xffffu;
+    SortItem it;
+    it.prefix = phigh | (key >> 16);
+    it.ref = ent_off[n - 1u - r];
+    it.srcrank = r;  // source 0 (the memtable) | rank
+    if (p > 0) {
+      const u64 prev = keys[p - 1];
+      if ((prev >> 16) == (key >> 16)) {
+        const u8* a = heap + (u64)ent_off[n - 1u - ((u32)prev & 0xffffu)] * 16u;
+        const u8* b = heap + (u64)it.ref * 16u;
+        const u32 ka = reinterpret_cast<const u32*>(a)[2], kb = reinterpret_cast<const u32*>(b)[2];
+        if (cmp_padded(reinterpret_cast<const u64*>(a + 32), ka, reinterpret_cast<const u64*>(b + 32), kb) != 0) s_bad = 1;
+      }
+    }
+    items[p] = it;
+  }
+  __syncthreads();
+  if (tid == 0) j.totals[7] = s_bad ? 1u : 0u;
 }
 
 // ---- merge of the sorted segments (merge path) -------------------------------------------------------
@@ -329,7 +487,7 @@ __global__ void __launch_bounds__(1024) k_compact_size(const CompactJob* jobs) {
       anp += s_np[t]; akmin = min(akmin, s_kvmin[t]); akmax = max(akmax, s_kvmax[t]);
     }
     j.totals[0] = au; j.totals[1] = ac; j.totals[2] = (ac && amn == amx) ? amn : 0u; j.totals[3] = ak;
-    j.totals[4] = anp; j.totals[5] = akmin; j.totals[6] = akmax; j.totals[7] = 0;
+    j.totals[4] = anp; j.totals[5] = akmin; j.totals[6] = akmax;  // ([7]: k_flush_sort's flag, read by the host)
   }
   __syncthreads();
   u32 pu = s_units[threadIdx.x], pc = s_cnt[threadIdx.x];
@@ -386,6 +544,51 @@ __global__ void __launch_bounds__(256) k_compact_write(const CompactJob* jobs) {
   }
 }
 
+// ---- maintenance helpers: one launch per batch of shards ---------------------------------------------------
+__global__ void __launch_bounds__(256) k_zero_out_hslots(const CompactJob* jobs) {
+  const CompactJob& j = jobs[blockIdx.y];
+  uint4* p = reinterpret_cast<uint4*>(j.out_hslots);
+  const u32 n = j.out_n_buckets * (RUN_BUCKET_SLOTS * 4u / 16u);
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+void launch_zero_out_hslots(const CompactJob* d_jobs, u32 n_jobs, u32 max_buckets, cudaStream_t s) {
+  if (!n_jobs || !max_buckets) return;
+  const u32 units = max_buckets * (RUN_BUCKET_SLOTS * 4u / 16u);
+  const u32 gx = std::min<u32>(64u, (units + 1023u) / 1024u);
+  k_zero_out_hslots<<<dim3(std::max<u32>(gx, 1u), n_jobs), 256, 0, s>>>(d_jobs);
+}
+
+__global__ void __launch_bounds__(128) k_upload_shards(const ShardUpload* up, ShardDev* shards, ShardFast* fast, ShardFast* fast_runs) {
+  const ShardUpload& u = up[blockIdx.x];
+  const u32 ix = u.index;
+  {
+    constexpr u32 words = sizeof(ShardDev) / 4, keep = offsetof(ShardDev, n_runs) / 4;
+    const u32* src = reinterpret_cast<const u32*>(&u.sd);
+    u32* dst = reinterpret_cast<u32*>(shards + ix);
+    for (u32 w = (u.runs_only ? keep : 0u) + threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+  }
+  {
+    // (runs_only: run 0 + meta; mt_count is written by the sequencing kernels)
+    const u32 words = u.runs_only ? offsetof(ShardFast, mt_count) / 4 : sizeof(ShardFast) / 4;
+    if (threadIdx.x < words) reinterpret_cast<u32*>(fast + ix)[threadIdx.x] = reinterpret_cast<const u32*>(&u.fast)[threadIdx.x];
+  }
+  {
+    constexpr u32 words = sizeof(ShardFast) * RSP_MAX_RUNS / 4;
+    const u32* src = reinterpret_cast<const u32*>(u.fast_runs);
+    u32* dst = reinterpret_cast<u32*>(fast_runs + (size_t)ix * RSP_MAX_RUNS);
+    for (u32 w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+  }
+  if (u.zero_mt && u.sd.mt_slots) {
+    uint4* p = reinterpret_cast<uint4*>(u.sd.mt_slots);
+    const u32 n = (u.sd.mt_slot_mask + 1u) / 2u;  // 8-byte slots, 16-byte stores (the table holds >= 16 slots)
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) p[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+void launch_upload_shards(const ShardUpload* d_up, u32 n, ShardDev* shards, ShardFast* fast, ShardFast* fast_runs, cudaStream_t s) {
+  if (!n) return;
+  k_upload_shards<<<n, 128, 0, s>>>(d_up, shards, fast, fast_runs);
+}
+
 void launch_compact_sort(const CompactJob* d_jobs, const CompactJob* h_jobs, u32 n_jobs, cudaStream_t s) {
   if (!n_jobs) return;
   u32 max_len = 0, max_sort = 0, max_tiles = 0;
@@ -397,15 +600,22 @@ void launch_compact_sort(const CompactJob* d_jobs, const CompactJob* h_jobs, u32
   if (!max_len) return;
   k_compact_fill<<<dim3((max_len + 255) / 256, n_jobs), 256, 0, s>>>(d_jobs);
   if (max_sort >= 2) {
-    // the opt-in is a per-DEVICE function attribute: one engine per GPU may live in the same process
+    // the opt-ins are per-DEVICE function attributes: one engine per GPU may live in the same process
     static std::atomic<unsigned long long> opted_in{0};
     int dev = 0;
     cudaGetDevice(&dev);
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(opted_in.load(std::memory_order_acquire) & bit)) {
       cudaFuncSetAttribute(k_compact_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SORT_TILE * sizeof(SortItem)));
+      cudaFuncSetAttribute(k_flush_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_MAX_ITEMS * 8 + FS_WARPS * 256 * 2));
       opted_in.fetch_or(bit, std::memory_order_release);
     }
+    // radix sort in shared memory for the memtables that fit; the comparison sort takes what is left (flag in totals[7])
+    u32 cap = 32;
+    for (u32 i = 0; i < n_jobs; i++)
+      if (h_jobs[i].n_src && h_jobs[i].src_is_mem[0]) cap = std::max(cap, std::min(h_jobs[i].src_n[0], FS_MAX_ITEMS));
+    cap = (cap + 31u) & ~31u;
+    k_flush_sort<<<n_jobs, FS_THREADS, (size_t)cap * 8 + FS_WARPS * 256 * 2, s>>>(d_jobs, cap);
     k_compact_sort<<<n_jobs, 1024, SORT_TILE * sizeof(SortItem), s>>>(d_jobs);
   }
   if (max_tiles) {

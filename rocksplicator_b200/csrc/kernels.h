@@ -88,6 +88,8 @@ struct FusedTick {
   GroupRes* gres; // [n_groups]
   u32 n_groups;
   u32 n_batches;
+  u32 max_group;  // batches of the longest group and bytes of the longest batch: pick the kernel shape (64 threads /
+  u32 max_len;    // 8 KB stage when no group holds more than 64 batches and no batch more than 4 KB)
 };
 constexpr u32 FUSED_MAX_BATCH_BYTES = 16384;  // larger batches take the general kernels (one thread walks a batch here)
 void launch_tick_fused(const FusedTick& t, ShardDev* shards, ShardFast* fast, cudaStream_t s);
@@ -214,5 +216,22 @@ constexpr u32 MERGE_TILE = 2048;
 void launch_compact_sort(const CompactJob* d_jobs, const CompactJob* h_jobs, u32 n_jobs, cudaStream_t s);
 void launch_compact_size(const CompactJob* d_jobs, u32 n_jobs, cudaStream_t s);
 void launch_compact_write(const CompactJob* d_jobs, u32 n_jobs, u32 max_items, cudaStream_t s);
+// zero the hash index of every job's output run (out_hslots, out_n_buckets buckets): one launch for the whole batch
+void launch_zero_out_hslots(const CompactJob* d_jobs, u32 n_jobs, u32 max_buckets, cudaStream_t s);
+
+// ---- batched descriptor upload ------------------------------------------------------------------------
+// One record per shard whose descriptors changed (a flush / merge batch installs up to thousands at once): staged in
+// pinned memory, ONE copy, ONE launch that scatters them — instead of three small pageable copies and a memset per shard.
+struct ShardUpload {
+  u32 index;
+  u32 runs_only;  // 1: only the run set changed — the sequencing state (last_seq .. latch) stays the device's
+  u32 zero_mt;    // 1: clear the memtable's slot table (the memtable was flushed)
+  u32 pad;
+  ShardDev sd;
+  ShardFast fast;
+  ShardFast fast_runs[RSP_MAX_RUNS];
+};
+static_assert(sizeof(ShardUpload) % 32 == 0, "records are copied as words from an array");
+void launch_upload_shards(const ShardUpload* d_up, u32 n, ShardDev* shards, ShardFast* fast, ShardFast* fast_runs, cudaStream_t s);
 
 }  // namespace rsp

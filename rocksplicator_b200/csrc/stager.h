@@ -18,9 +18,10 @@
 // per-shard FIFO needs.
 //
 // Locking: every state change is a few loads and stores under a SPIN lock (nothing blocks while holding it).  A caller
-// waits for its batch with a short spin and then sleeps on the batch's own futex word; the dispatcher wakes TWO sleepers
-// and every woken caller wakes two more (a tree: the wake-up of hundreds of callers costs the dispatcher two system
-// calls and nobody queues on a mutex).  Both alternatives were measured with 256 ApplicationDB::Get threads on the
+// waits for its batch with a short spin and then sleeps on the batch's own futex word; the dispatcher wakes kWakeFan
+// sleepers and every woken caller wakes kWakeFan more (a tree: nobody queues on a mutex, and the depth — every level costs
+// the wake-up latency of an idle core, 50-100 us out of a deep C-state — stays at two for 256 callers; with a fan-out
+// of two the eight levels were the whole 1.5 ms p50 of ApplicationDB::Get).  Both alternatives were measured with 256 ApplicationDB::Get threads on the
 // 128-core host: one condition variable for everybody = 55 K Gets/s (the herd re-acquiring its mutex takes longer than
 // the batch), spin-then-yield = p50 0.27 ms but p99 300 ms (spinners starve the dispatcher once threads outnumber
 // cores).
@@ -58,7 +59,8 @@ class Stager {
   using RunFn = std::function<void(const BatchInfo&)>;
   using PostFn = std::function<void()>;  // dispatcher thread, after the asynchronous completions of a batch ran
 
-  static constexpr int kBuffers = 3;  // filling | running | results being read
+  static constexpr int kBuffers = 4;  // filling | running | results being read (callers still waking up: two)
+  static constexpr int kWakeFan = 16;
 
   Stager(size_t cap_items, size_t cap_bytes, RunFn run, PostFn post = nullptr)
       : cap_items_(cap_items), cap_bytes_(cap_bytes), run_(std::move(run)), post_(std::move(post)) {
@@ -138,21 +140,23 @@ class Stager {
       FutexWait(&b.seq, s, 2000000);  // (bounded: 2 ms)
       slept = true;
     }
-    if (slept) FutexWake(&b.seq, 2);  // pass the wake-up on
+    if (slept) FutexWake(&b.seq, kWakeFan);  // pass the wake-up on
   }
   void release(const Ticket& t) {
     Batch& b = b_[t.buf];
     if (b.users.fetch_sub(1, std::memory_order_acq_rel) == 1) {
-      bool freed;
-      {
-        SpinGuard g(sl_);
-        freed = MaybeFree(b);
-      }
-      (void)freed;
+      SpinGuard g(sl_);
+      MaybeFree(b);
     }
   }
 
   uint64_t batches() const { return batches_.load(std::memory_order_relaxed); }
+  // diagnostics: batches run, items carried, ns inside the RunFn, ns waiting for callers still copying, ns idle
+  void stats(uint64_t out[5]) const {
+    out[0] = batches_.load(std::memory_order_relaxed); out[1] = st_items_.load(std::memory_order_relaxed);
+    out[2] = st_run_ns_.load(std::memory_order_relaxed); out[3] = st_copy_ns_.load(std::memory_order_relaxed);
+    out[4] = st_idle_ns_.load(std::memory_order_relaxed);
+  }
 
  private:
   enum State { FREE, OPEN, CLOSED, DONE };
@@ -206,6 +210,9 @@ class Stager {
   static void FutexWake(std::atomic<uint32_t>* w, int n) {
     syscall(SYS_futex, reinterpret_cast<uint32_t*>(w), FUTEX_WAKE_PRIVATE, n, nullptr, nullptr, 0);
   }
+  static int64_t NowNs() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
   static void NapUs(long us) {
     struct timespec ts;
     ts.tv_sec = 0;
@@ -240,6 +247,7 @@ class Stager {
     for (;;) {
       // ---- take the open batch once it holds work
       int bi = -1;
+      const int64_t t_idle0 = NowNs();
       for (int spins = 0;; spins++) {
         {
           SpinGuard g(sl_);
@@ -262,9 +270,13 @@ class Stager {
       }
       seen_work_ = work32_.load(std::memory_order_seq_cst);
       Batch& b = b_[bi];
+      const int64_t t_copy0 = NowNs();
+      st_idle_ns_.fetch_add((uint64_t)(t_copy0 - t_idle0), std::memory_order_relaxed);
       for (int spins = 0; b.copiers.load(std::memory_order_acquire); spins++) {
         if (spins < 2000) cpu_relax(); else NapUs(10);  // (a copier may have been descheduled)
       }
+      const int64_t t_run0 = NowNs();
+      st_copy_ns_.fetch_add((uint64_t)(t_run0 - t_copy0), std::memory_order_relaxed);
       BatchInfo info;
       std::vector<std::function<void()>> async;
       {
@@ -273,11 +285,13 @@ class Stager {
         async.swap(b.async);
       }
       run_(info);
+      st_run_ns_.fetch_add((uint64_t)(NowNs() - t_run0), std::memory_order_relaxed);
+      st_items_.fetch_add(info.n_items, std::memory_order_relaxed);
       for (auto& f : async) f();
       if (post_) post_();
       b.epoch_done.store(info.epoch, std::memory_order_release);  // spinning callers go on at once
       b.seq.fetch_add(1, std::memory_order_release);
-      FutexWake(&b.seq, 2);                                        // sleeping ones: two, who wake two more each
+      FutexWake(&b.seq, kWakeFan);                                 // sleeping ones: a few, who wake the others
       batches_.fetch_add(1, std::memory_order_relaxed);
       {
         SpinGuard g(sl_);
@@ -298,7 +312,7 @@ class Stager {
   std::atomic<bool> stop_{false}, disp_sleeping_{false};
   std::atomic<uint32_t> work32_{0};  // requests ever accepted (futex word): the idle dispatcher sleeps until it moves
   uint32_t seen_work_ = 0;
-  std::atomic<uint64_t> batches_{0};
+  std::atomic<uint64_t> batches_{0}, st_items_{0}, st_run_ns_{0}, st_copy_ns_{0}, st_idle_ns_{0};
   std::thread thread_;
 };
 

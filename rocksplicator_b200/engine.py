@@ -33,7 +33,7 @@ class ShardOpts(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "latest_seq", "memtable_entries", "memtable_bytes", "n_runs", "run_entries", "run_bytes", "flushes",
-        "compactions", "compaction_bytes_read", "compaction_bytes_written")]
+        "compactions", "compaction_bytes_read", "compaction_bytes_written", "flush_comparison_sorts")]
 
 
 EXPORTS = {
@@ -105,6 +105,7 @@ EXPORTS = {
     "rsp_last_kernel_ms": (C.c_float, [C.c_void_p, C.c_char_p]),
     "rsp_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "rsp_debug_last_pending": (C.c_uint32, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "rsp_debug_combiner_stats": (None, [C.c_void_p, C.c_int, C.c_void_p]),
 }
 
 _lib = None

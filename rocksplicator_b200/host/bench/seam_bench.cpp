@@ -28,36 +28,7 @@
 #include "rocksdb_admin/application_db.h"
 #include "rocksdb_replicator/rocksdb_replicator.h"
 
-extern "C" {
-typedef struct rsp_seam_cfg {
-  int32_t device;
-  uint32_t shards;
-  uint64_t kv_total;           // loaded through the pull loop: kv_total / shards keys per shard
-  uint32_t value_len;          // 64 (config 2) or 256 (config 5)
-  uint32_t executor_threads;   // replicator executor threads (reference default 32, floor 16)
-  uint32_t updates_per_response;  // replicator_max_updates_per_response (50)
-  uint32_t update_rounds;      // mixed phase: this many more responses per shard while MultiGet runs
-  uint32_t multiget_threads, multiget_batch;
-  double multiget_secs;
-  uint32_t get_threads;
-  double get_secs;
-  uint64_t seed;
-  uint32_t first_shard_id;     // shard ids first .. first + shards - 1 (multi-rank runs)
-  uint32_t reserved;
-} rsp_seam_cfg;
-
-typedef struct rsp_seam_result {
-  double load_s, load_applies_per_s;
-  double resp_p50_ms, resp_p99_ms;        // response handed to the follower -> its next pull arrives (load phase)
-  double compact_s;
-  double mget_lookups_per_s, mget_p50_ms, mget_p99_ms;
-  uint64_t mget_calls;
-  double get_per_s, get_p50_us, get_p99_us;
-  double mixed_applies_per_s, mixed_lookups_per_s, mixed_resp_p50_ms, mixed_resp_p99_ms;
-  uint64_t applied_total, parity_errors, status_errors;
-  uint64_t engine_launches;
-} rsp_seam_result;
-}
+#include "bench/seam_bench.h"
 
 namespace {
 
@@ -384,17 +355,52 @@ extern "C" int rsp_seam_bench(const rsp_seam_cfg* cfg_in, rsp_seam_result* res) 
       res->mget_p99_ms = lat.pct(0.99);
     }
     // ---- ApplicationDB::Get from many threads -------------------------------------------------------
+    auto comb_delta = [&](int which, const uint64_t before[5], double out[5]) {
+      uint64_t now[5];
+      rsp_debug_combiner_stats(gdb0->engine(), which, now);
+      out[0] = (double)(now[0] - before[0]);
+      out[1] = (double)(now[1] - before[1]);
+      for (int k = 2; k < 5; k++) out[k] = 1e-6 * (double)(now[k] - before[k]);
+    };
     if (cfg.get_threads && cfg.get_secs > 0) {
       Percentiles lat;
+      uint64_t before[5];
+      rsp_debug_combiner_stats(gdb0->engine(), 0, before);
       reader(cfg.get_threads, 1, cfg.get_secs, &applied_now, false, &lat, &res->get_per_s, nullptr, true);
+      comb_delta(0, before, res->read_comb);
       res->get_p50_us = lat.pct(0.5);
       res->get_p99_us = lat.pct(0.99);
     }
+    uint64_t cur_target = per_shard;
+    // ---- steady state of the pull loops alone ---------------------------------------------------------
+    if (cfg.steady_rounds) {
+      const uint64_t target = cur_target + (uint64_t)cfg.steady_rounds * cfg.updates_per_response;
+      leader->lat_ms.clear();
+      uint64_t before[5];
+      rsp_debug_combiner_stats(gdb0->engine(), 1, before);
+      auto& tr = replicator::PullTrace::Get();
+      tr.Reset();
+      tr.enabled = true;
+      t0 = Clock::now();
+      leader->SetTargets(target);
+      if (!wait_seq(target, 600)) status_errors++;
+      const double el = secs_since(t0);
+      tr.enabled = false;
+      res->steady_applies_per_s = (double)cfg.steady_rounds * cfg.updates_per_response * S / el;
+      res->steady_resp_p50_ms = leader->lat_ms.pct(0.5);
+      res->steady_resp_p99_ms = leader->lat_ms.pct(0.99);
+      for (int k = 0; k < replicator::PullTrace::kStages; k++)
+        res->trace_us[k] = tr.n[k].load() ? 1e-3 * (double)tr.ns[k].load() / (double)tr.n[k].load() : 0.0;
+      comb_delta(1, before, res->apply_comb);
+      leader->lat_ms.clear();
+      cur_target = target;
+      applied_now = target;
+    }
     // ---- config 3: replicated updates flowing while MultiGet runs -----------------------------------
     if (cfg.update_rounds) {
-      const uint64_t target = per_shard + (uint64_t)cfg.update_rounds * cfg.updates_per_response;
+      const uint64_t target = cur_target + (uint64_t)cfg.update_rounds * cfg.updates_per_response;
       std::atomic<bool> done{false};
-      std::atomic<uint64_t> racing_seq{per_shard};
+      std::atomic<uint64_t> racing_seq{cur_target};
       std::thread watcher([&] {  // the smallest applied count over the shards, sampled: what a racing read may rely on
         while (!done.load()) {
           uint64_t mn = ~0ull;

@@ -136,6 +136,7 @@ void RocksDBReplicator::ReplicatedDB::pullFromUpstream() {
   req.max_wait_ms = Flags().replicator_max_server_wait_time_ms;
   req.max_updates = Flags().replicator_max_updates_per_response;
   req.set_role(role_);
+  if (trace_cont_) { PullTrace::Get().Add(5, trace_cont_, PullTrace::Now()); trace_cont_ = 0; }
   incCounter(kReplicatorPullRequests, 1, db_name_);
   SocketAddress up;
   {
@@ -146,11 +147,14 @@ void RocksDBReplicator::ReplicatedDB::pullFromUpstream() {
   const uint32_t timeout = (uint32_t)(Flags().replicator_max_server_wait_time_ms +
                                       Flags().replicator_client_server_timeout_difference_ms);
   Executor* my_executor = owner_->executor();
-  owner_->transport()->replicate(up, req, timeout, [weak_db, my_executor](ReplicateResult&& tr) {
+  const int64_t t_call = PullTrace::Get().enabled.load(std::memory_order_relaxed) ? PullTrace::Now() : 0;
+  owner_->transport()->replicate(up, req, timeout, [weak_db, my_executor, t_call](ReplicateResult&& tr) {
    // continue on OUR executor (the reference's `.via(executor_)`, replicated_db.cpp:328)
    auto shared_t = std::make_shared<ReplicateResult>(std::move(tr));
+   if (t_call) { const int64_t now = PullTrace::Now(); PullTrace::Get().Add(0, t_call, now); shared_t->t_mark = now; }
    my_executor->add([weak_db, shared_t] {
     ReplicateResult& t = *shared_t;
+    if (t.t_mark) { const int64_t now = PullTrace::Now(); PullTrace::Get().Add(1, t.t_mark, now); t.t_mark = now; }
     auto db = weak_db.lock();
     if (!db || db->removed_.load()) return;
     bool delay_next_pull = false;
@@ -181,10 +185,20 @@ void RocksDBReplicator::ReplicatedDB::pullFromUpstream() {
         // executor again (shared_t keeps the updates alive)
         const size_t n_updates = response.updates.size();
         Executor* ex = db->owner_->executor();
-        db->db_wrapper_->HandleReplicateResponses(&response.updates, [weak_db, shared_t, n_updates, ex](size_t n_applied) {
-          ex->add([weak_db, shared_t, n_updates, n_applied] {
+        auto staged_at = std::make_shared<std::atomic<int64_t>>(0);
+        db->db_wrapper_->HandleReplicateResponses(&response.updates, [weak_db, shared_t, n_updates, ex, staged_at](size_t n_applied) {
+          int64_t t_done = 0;
+          if (shared_t->t_mark) {
+            t_done = PullTrace::Now();
+            const int64_t st = staged_at->load(std::memory_order_acquire);
+            if (st) PullTrace::Get().Add(3, st, t_done);
+          }
+          ex->add([weak_db, shared_t, n_updates, n_applied, t_done] {
+            int64_t t_cont = 0;
+            if (t_done) { t_cont = PullTrace::Now(); PullTrace::Get().Add(4, t_done, t_cont); }
             auto db = weak_db.lock();
             if (!db || db->removed_.load()) return;
+            db->trace_cont_ = t_cont;
             const bool failed = n_applied < n_updates;
             if (failed) incCounter(kReplicatorHandleResponseFailure, 1, db->db_name_);
             db->pullFromUpstreamNoUpdates_ = 0;
@@ -192,6 +206,7 @@ void RocksDBReplicator::ReplicatedDB::pullFromUpstream() {
             db->scheduleNextPull(failed);
           });
         });
+        if (t.t_mark) { const int64_t now = PullTrace::Now(); PullTrace::Get().Add(2, t.t_mark, now); staged_at->store(now, std::memory_order_release); }
         return;
       }
       incCounter(kReplicatorPullRequestsNoUpdates, 1, db->db_name_);

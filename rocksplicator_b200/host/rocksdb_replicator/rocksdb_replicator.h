@@ -88,6 +88,7 @@ class RocksDBReplicator {
     SocketAddress upstream_addr_;
     std::mutex upstream_mu_;
     uint32_t pullFromUpstreamNoUpdates_{0};
+    int64_t trace_cont_{0};  // PullTrace: when the continuation of the last response ran (one pull in flight per db)
     std::atomic<uint32_t> resetUpstreamAttempts_{0};
     detail::NonBlockingConditionVariable cond_var_;
     std::unordered_multimap<rocksdb::SequenceNumber,

@@ -767,33 +767,23 @@ static void test_application_db_manager() {
 // the hot path through the reference's seams (host/bench/seam_bench.cpp): followers pull from a synthetic leader through
 // RocksDBReplicator / DbWrapper, readers call ApplicationDB::MultiGet / Get from several threads, updates race reads;
 // every value read back is checked against the generator
-extern "C" {
-struct rsp_seam_cfg {
-  int32_t device; uint32_t shards; uint64_t kv_total; uint32_t value_len, executor_threads, updates_per_response, update_rounds,
-      multiget_threads, multiget_batch; double multiget_secs; uint32_t get_threads; double get_secs; uint64_t seed;
-  uint32_t first_shard_id, reserved;
-};
-struct rsp_seam_result {
-  double load_s, load_applies_per_s, resp_p50_ms, resp_p99_ms, compact_s, mget_lookups_per_s, mget_p50_ms, mget_p99_ms;
-  uint64_t mget_calls; double get_per_s, get_p50_us, get_p99_us, mixed_applies_per_s, mixed_lookups_per_s, mixed_resp_p50_ms,
-      mixed_resp_p99_ms; uint64_t applied_total, parity_errors, status_errors, engine_launches;
-};
-int rsp_seam_bench(const rsp_seam_cfg*, rsp_seam_result*);
-}
+#include "bench/seam_bench.h"
 static void test_gpu_seams() {
   rsp_seam_cfg c;
   memset(&c, 0, sizeof(c));
   c.shards = 6; c.kv_total = 6 * 700; c.value_len = 64; c.executor_threads = 16; c.updates_per_response = 50; c.update_rounds = 4;
   c.multiget_threads = 4; c.multiget_batch = 256; c.multiget_secs = 0.3; c.get_threads = 4; c.get_secs = 0.2; c.first_shard_id = 40;
+  c.steady_rounds = 3;
   rsp_seam_result r;
   EXPECT_EQ(rsp_seam_bench(&c, &r), 0);
   EXPECT_EQ(r.parity_errors, (uint64_t)0);
   EXPECT_EQ(r.status_errors, (uint64_t)0);
-  EXPECT_EQ(r.applied_total, (uint64_t)(6 * (700 + 4 * 50)));
-  EXPECT_TRUE(r.mget_calls > 0 && r.get_per_s > 0 && r.load_applies_per_s > 0 && r.mixed_applies_per_s > 0);
+  EXPECT_EQ(r.applied_total, (uint64_t)(6 * (700 + 4 * 50 + 3 * 50)));
+  EXPECT_TRUE(r.mget_calls > 0 && r.get_per_s > 0 && r.load_applies_per_s > 0 && r.mixed_applies_per_s > 0 && r.steady_applies_per_s > 0);
+  EXPECT_TRUE(r.trace_us[0] > 0 && r.apply_comb[1] >= 6 * 3 * 50);
   printf("  seams: load %.0f applies/s, MultiGet %.0f lookups/s (%llu calls), Get %.0f /s, mixed %.0f applies/s + %.0f lookups/s\n",
          r.load_applies_per_s, r.mget_lookups_per_s, (unsigned long long)r.mget_calls, r.get_per_s, r.mixed_applies_per_s, r.mixed_lookups_per_s);
-  c.value_len = 256; c.first_shard_id = 60; c.update_rounds = 0;  // config-5 shape: 256-byte values
+  c.value_len = 256; c.first_shard_id = 60; c.update_rounds = 0; c.steady_rounds = 0;  // config-5 shape: 256-byte values
   EXPECT_EQ(rsp_seam_bench(&c, &r), 0);
   EXPECT_EQ(r.parity_errors + r.status_errors, (uint64_t)0);
 }

@@ -114,6 +114,12 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) { return (unsigned
 static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, !pred) == 0; }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emul_collective(EMUL_SYNCWARP, mask, 0, 0); }
+template <class T> static inline unsigned __match_any_sync(unsigned mask, T v) {  // lanes of `mask` holding the same value
+  unsigned r = 0;
+  for (int l = 0; l < 32; l++)
+    if ((mask >> l) & 1u) { const T o = __shfl_sync(mask, v, l); if (o == v) r |= 1u << l; }
+  return r;
+}
 static inline void __syncthreads() { emul_syncthreads(); }
 extern int emul_sync_acc;  // one block at a time, fibers are cooperative: a plain accumulator between barriers
 static inline int __syncthreads_count(int pred) {
@@ -130,6 +136,7 @@ static inline void __threadfence() {}
 // ---- loads, atomics, bit tricks -----------------------------------------------------------------------------------
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
+template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 template <class T> struct emul_same { typedef T type; };
 template <class T> static inline T atomicCAS(T* p, typename emul_same<T>::type cmp, typename emul_same<T>::type val) {
   T old = *p;
@@ -143,6 +150,7 @@ template <class T> static inline T atomicOr(T* p, typename emul_same<T>::type v)
 template <class T> static inline T atomicExch(T* p, typename emul_same<T>::type v) { T old = *p; *p = v; return old; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)((((uint64_t)hi << 32) | lo) >> (sh & 31u)); }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
   const uint64_t src = ((uint64_t)y << 32) | x;

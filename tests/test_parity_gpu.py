@@ -579,3 +579,49 @@ def test_range_deletion_is_refused(eng, port_lib):
         assert s.latest_seq() == o.latest_seq() and s.scan() == o.scan()
         s.close()
         o.close()
+
+
+@pytest.mark.parametrize("shape", ["distinct_prefixes", "shared_prefix", "short_and_padded", "versions"])
+def test_flush_sort_paths(eng, port_lib, shape):
+    """The flush sorts the memtable by an LSD radix sort over the keys' 8-byte prefixes (k_flush_sort) and leaves a
+    shard to the comparison sort when distinct keys share their prefix: both paths, the boundary between them (keys
+    shorter than 8 bytes vs the same bytes zero-extended) and many versions per key (stability = newest first), each
+    flushed at several sizes and read back through scans and MultiGet against the oracle."""
+    rnd = random.Random(hash(shape) & 0xffff)
+    for n in (1, 2, 31, 33, 700, 5000):
+        s = new_shard(eng, 0)
+        o = okv.Okv(port_lib)
+        if shape == "distinct_prefixes":
+            keys = [struct.pack(">Q", rnd.getrandbits(40)) + b"tail%d" % i for i in range(n)]
+        elif shape == "shared_prefix":
+            keys = [b"user_profile_%06d" % rnd.randrange(10 ** 6) for _ in range(n)]
+        elif shape == "short_and_padded":
+            base = [bytes([rnd.randrange(97, 100) for _ in range(rnd.randrange(1, 8))]) for _ in range(n)]
+            keys = base + [k + b"\x00" * rnd.randrange(1, 4) for k in base[::2]]
+        else:
+            pool = [struct.pack(">Q", rnd.getrandbits(24)) + b"k" for _ in range(max(1, n // 8))]
+            keys = [rnd.choice(pool) for _ in range(n)]
+        six, batches, ts = [], [], []
+        for i, k in enumerate(keys):
+            wb = WriteBatch()
+            if shape == "versions" and i % 5 == 4:
+                wb.delete(k)
+            else:
+                wb.put(k, b"v%d-" % i + k[:6])
+            six.append(s.index); batches.append(wb.data()); ts.append(i)
+        for lo in range(0, len(six), 4096):
+            assert not eng.apply_many(six[lo:lo + 4096], batches[lo:lo + 4096], ts[lo:lo + 4096]).any()
+        for b, t in zip(batches, ts):
+            assert o.apply(b, t) == 0
+        assert s.flush() == 0
+        assert s.latest_seq() == o.latest_seq()
+        generic = s.stats()["flush_comparison_sorts"]
+        if shape in ("distinct_prefixes", "versions"):
+            assert generic == 0, "the radix sort should have handled this memtable"
+        elif shape == "shared_prefix" and n >= 31:
+            assert generic == 1, "distinct keys share their 8-byte prefix: the comparison sort must take over"
+        got = s.scan()
+        assert got == o.scan(), (shape, n)
+        probe = list(dict.fromkeys(keys))[:300] + [b"zz-missing"]
+        assert s.multi_get(probe) == o.multi_get(probe)
+        s.close()
