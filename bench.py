@@ -119,7 +119,7 @@ class SeamResult(C.Structure):
                                           "mixed_lookups_per_s", "mixed_resp_p50_ms", "mixed_resp_p99_ms")] + \
                [(n, C.c_uint64) for n in ("applied_total", "parity_errors", "status_errors", "engine_launches")] + \
                [(n, C.c_double) for n in ("steady_applies_per_s", "steady_resp_p50_ms", "steady_resp_p99_ms")] + \
-               [("trace_us", C.c_double * 6), ("apply_comb", C.c_double * 5), ("read_comb", C.c_double * 5)]
+               [("trace_us", C.c_double * 6), ("apply_comb", C.c_double * 9), ("read_comb", C.c_double * 5)]
 
 
 def run_seams(device, shards, kv, rank, world, secs=2.0, value_len=64, update_rounds=20, updates_per_response=50,
@@ -693,7 +693,7 @@ def main():
             idx = sh + ordn * np.uint64(S)
             b = synth.single_put_batches(synth.keys16(seed5, idx), synth.values(seed5, sh.astype(np.int64), idx, i + 1, V5), 9000 + idx)
             t5.append(tuple(torch.from_numpy(np.ascontiguousarray(x).reshape(-1)).pin_memory() for x in (
-                c5_six[sh.astype(np.int64)], b, np.arange(T5 + 1, dtype=np.uint64) * np.uint64(b.shape[1]), (9000 + idx).astype(np.uint64))) + (idx,))
+                c5_six[sh.astype(np.int64)], b, np.arange(T5 + 1, dtype=np.uint64) * np.uint64(b.shape[1]), (9000 + idx).astype(np.uint64))) + (idx.astype(np.int64),))
         q5 = [rng.integers(0, N5, size=Q5, dtype=np.uint64) for _ in range(NT5)]
         q5k = [torch.from_numpy(synth.keys16(seed5, q).reshape(-1)).pin_memory() for q in q5]
         q5s = [torch.from_numpy(c5_six[(q % np.uint64(S)).astype(np.int64)]).pin_memory() for q in q5]
@@ -709,7 +709,7 @@ def main():
             i = n_ticks5 % NT5
             six_t, b_t, off_t, ts_t, idx_t = t5[i]
             assert lib.rsp_apply_many(eng.h, T5, six_t.data_ptr(), b_t.data_ptr(), off_t.data_ptr(), ts_t.data_ptr(), h5_ast.data_ptr()) == 0
-            ver5[idx_t.astype(np.int64)] = i + 1
+            ver5[idx_t] = i + 1
             assert lib.rsp_multi_get_fixed(eng.h, Q5, q5s[i].data_ptr(), q5k[i].data_ptr(), 16, h5_vals.data_ptr(), V5, h5_vlen.data_ptr(), h5_st.data_ptr()) == 0
             n_ticks5 += 1
         c5_s = time.perf_counter() - t0
@@ -841,7 +841,7 @@ def main():
                            "applies_per_s": seams_sum["steady_applies_per_s"],
                            "response_to_next_pull_ms": {"p50": seams_max["steady_resp_p50_ms"], "p99": seams_max["steady_resp_p99_ms"]},
                            "round_trip_stage_us_rank0": dict(zip(("transport", "to_executor", "handle_and_stage", "engine", "to_continuation", "to_next_pull"), seams.get("trace_us") or [])),
-                           "apply_combiner_rank0": dict(zip(("batches", "updates", "ms_running", "ms_waiting_copiers", "ms_idle"), seams.get("apply_comb") or []))},
+                           "apply_combiner_rank0": dict(zip(("batches", "updates", "ms_running", "ms_waiting_copiers", "ms_idle", "sum_ms_call_to_batch_ran", "sum_ms_to_callback_start", "sum_ms_in_callbacks", "callbacks"), seams.get("apply_comb") or []))},
                 "get_combiner_rank0": dict(zip(("batches", "keys", "ms_running", "ms_waiting_copiers", "ms_idle"), seams.get("read_comb") or [])),
                 "applies_per_s_at_500_updates_per_response": seams_sum["load500_applies_per_s"],
                 "note": "one response in flight per shard (the pull protocol): applies/s = shards x updates per response / round trip; 50 per response is the reference's default flag, 500 shows the same loops with a larger flag value",

@@ -263,8 +263,10 @@ uint64_t rsp_kernel_launches(const rsp_engine* e);
 uint32_t rsp_debug_last_pending(rsp_engine* e, uint32_t* first, uint32_t cap);
 
 /* diagnostics: the staging combiners' counters — which = 0 reads, 1 applies; out = {batches run, items carried,
- * ns inside the device batches, ns waiting for callers still copying, ns idle}; zeros before first use */
-void rsp_debug_combiner_stats(rsp_engine* e, int which, uint64_t out[5]);
+ * ns inside the device batches, ns waiting for callers still copying, ns idle, and for the asynchronous applies
+ * (rsp_apply_updates): ns from the call to its batch having run, ns until a completion thread picked the callback
+ * up, ns inside the callbacks, number of callbacks}; zeros before first use */
+void rsp_debug_combiner_stats(rsp_engine* e, int which, uint64_t out[9]);
 
 const char* rsp_version(void);
 

@@ -816,6 +816,25 @@ static const bool g_trace = getenv("RSP_TRACE") != nullptr;
 
 // Build the tick image (pinned) for n batches and copy it to the device.  Layout of the image:
 //   [BatchDesc x n][GroupDesc x g][blob ...] ; results [BatchRes x n][GroupRes x g] ; [OpRec x ops]
+// Cut every group into chunks of <= FUSED_CHUNK_BATCHES batches and <= FUSED_STAGE_BYTES of blob (k_tick_chunks: a CTA
+// per chunk); start(i) / end(i) = byte offsets of staged batch i in the blob.  GroupDesc.pad receives the chunk count.
+template <class Start, class End>
+static void cut_chunks(GroupDesc* groups, size_t ng, Start start, End end, std::vector<ChunkDesc>* out) {
+  out->clear();
+  for (size_t g = 0; g < ng; g++) {
+    const size_t first = groups[g].first_batch, last = first + groups[g].n_batches;
+    u32 ci = 0;
+    for (size_t b = first; b < last;) {
+      const u64 base = start(b);
+      size_t e = b + 1;  // (a batch beyond the stage cannot reach here: such ticks take the general kernels)
+      while (e < last && e - b < FUSED_CHUNK_BATCHES && end(e) - base <= FUSED_STAGE_BYTES) e++;
+      out->push_back(ChunkDesc{(u32)g, (u32)b, (u32)(e - b), ci++});
+      b = e;
+    }
+    groups[g].pad = ci;
+  }
+}
+
 // Pitch of a batch in a staged image: whole 4-byte words, an ODD number of them — k_tick_fused walks a batch per thread
 // in shared memory, and equal-sized batches at an even word pitch (r02 padded to 16 bytes: 128 for the 115-byte
 // replication unit) put all 32 lanes of a warp on the same bank (ncu: 29.7-way conflicts, 97 % of the wavefronts).
@@ -958,7 +977,19 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
   const size_t bres_b = align_up(n * sizeof(BatchRes), 256);
   const size_t out_b = align_up(ng * sizeof(GroupRes) + n * 4, 256);
   const size_t ops_b = (size_t)ops_cap * sizeof(OpRec);
-  const size_t dev_b = in_b + bres_b + out_b + ops_b + 256;
+  // k_tick_chunks (groups longer than one chunk): chunk table, chain records, per-group counters behind everything else
+  std::vector<ChunkDesc> chunks;
+  {
+    size_t mg = 0, ml = 0;
+    for (size_t g = 0; g < ng; g++) mg = std::max<size_t>(mg, g_count[g]);
+    for (size_t pos = 0; pos < n; pos++) ml = std::max<size_t>(ml, reinterpret_cast<const u32*>(pin + o_flen)[pos]);
+    if (!fused_small_shape((u32)mg, (u32)(ml + 16)) && ml <= FUSED_MAX_BATCH_BYTES) {
+      const u32* lens = reinterpret_cast<const u32*>(pin + o_flen);
+      cut_chunks(gd, ng, [&](size_t i) { return (u64)p_boff[i]; }, [&](size_t i) { return (u64)p_boff[i] + lens[i]; }, &chunks);
+    }
+  }
+  const size_t dev_b_base = align_up(in_b + bres_b + out_b + ops_b, 256);
+  const size_t dev_b = dev_b_base + align_up(chunks.size() * sizeof(ChunkDesc), 256) + chunks.size() * 32 + ng * 4 + 256;
   u8* dev;
   if (own_dev) {
     CUDA_OK(cudaMalloc(&sg->dev, dev_b));
@@ -991,6 +1022,11 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
     f.blob = t.blob; f.off = (const u64*)(dev + o_foff); f.len = (const u32*)(dev + o_flen); f.ts = nullptr;
     f.groups = t.groups; f.bstat = t.bstat; f.gres = t.gres; f.n_groups = (u32)ng; f.n_batches = (u32)n;
     f.max_group = (u32)max_group; f.max_len = (u32)(max_len + 16);
+    f.chunks = (const ChunkDesc*)(dev + dev_b_base); f.n_chunks = (u32)chunks.size(); f.pad = 0;
+    f.chain = (u64*)(dev + dev_b_base + align_up(chunks.size() * sizeof(ChunkDesc), 256));
+    f.group_done = (u32*)((u8*)f.chain + chunks.size() * 32);
+    if (!chunks.empty())
+      CUDA_OK(cudaMemcpyAsync(dev + dev_b_base, chunks.data(), chunks.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, e->st));
   }
   if (own_dev) CUDA_OK(cudaStreamSynchronize(e->st));  // the pinned staging buffer is reused
   return RSP_OK;
@@ -1146,7 +1182,13 @@ static int apply_many_packed(rsp_engine* e, size_t n, const uint32_t* shard_ix, 
   const size_t o_need = o_ts + align_up(n * 8, 256), o_desc = o_need + align_up((2 * ng + 1) * 4, 256);
   const size_t o_blob = o_desc + (fused ? 0 : align_up(n * sizeof(BatchDesc), 256)), o_bres = o_blob + align_up(blob_b + 64, 256);
   const size_t o_out = o_bres + (fused ? 0 : align_up(n * sizeof(BatchRes), 256));
-  const size_t total = o_out + align_up(ng * sizeof(GroupRes) + n * 4, 256);
+  // groups longer than one chunk: k_tick_chunks' chunk table, chain records and per-group counters
+  std::vector<ChunkDesc> chunks;
+  if (fused && !fused_small_shape((u32)max_group, (u32)(max_len + trailer + 16)))
+    cut_chunks(groups.data(), ng, [&](size_t i) { return (u64)off[i]; }, [&](size_t i) { return (u64)off[i + 1]; }, &chunks);
+  const size_t o_chunks = o_out + align_up(ng * sizeof(GroupRes) + n * 4, 256);
+  const size_t o_chain = o_chunks + align_up(chunks.size() * sizeof(ChunkDesc), 256);
+  const size_t total = o_chain + align_up(chunks.size() * 32 + ng * 4, 256);
   sg.res_bytes = ng * sizeof(GroupRes) + n * 4;
   sg.need_units.resize(ng);
   sg.need_ents.resize(ng);
@@ -1181,7 +1223,11 @@ static int apply_many_packed(rsp_engine* e, size_t n, const uint32_t* shard_ix, 
     f.blob = dev + o_blob; f.off = (const u64*)(dev + o_off); f.len = nullptr; f.ts = ts_ms ? (const u64*)(dev + o_ts) : nullptr;
     f.groups = (const GroupDesc*)(dev + o_groups); f.gres = (GroupRes*)(dev + o_out);
     f.bstat = (u32*)(dev + o_out + ng * sizeof(GroupRes)); f.n_groups = (u32)ng; f.n_batches = (u32)n;
-    f.max_group = (u32)max_group; f.max_len = (u32)(max_len + 16);
+    f.max_group = (u32)max_group; f.max_len = (u32)(max_len + trailer + 16);
+    f.chunks = (const ChunkDesc*)(dev + o_chunks); f.n_chunks = (u32)chunks.size(); f.pad = 0;
+    f.chain = (u64*)(dev + o_chain); f.group_done = (u32*)(dev + o_chain + chunks.size() * 32);
+    if (!chunks.empty())
+      CUDA_OK(cudaMemcpyAsync(dev + o_chunks, chunks.data(), chunks.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, e->st));
     sg.tick.gres = f.gres;
   } else {
     CUDA_OK(cudaMemsetAsync(dev + o_need, 0, (2 * ng + 1) * 4, e->st));
@@ -1786,6 +1832,9 @@ struct ApplyCombiner {
   std::unique_ptr<Stager> stager;
   CompletionPool pool;
   std::vector<std::function<void()>> done_now;  // dispatcher thread only: completions of the batch that just ran
+  // diagnostics of the asynchronous form: ns from commit to the batch having run, from there to a completion thread
+  // picking the callback up, inside the callback; and the number of callbacks
+  std::atomic<u64> dbg_ns[3] = {}, dbg_n{0};
 
   void run(const Stager::BatchInfo& info) {
     ApplyStage& S = st[info.buf];
@@ -1895,11 +1944,20 @@ static int apply_combined(rsp_shard* s, size_t n, const rsp_slice* batches, cons
     return ok < n ? (int)stv[ok] : (int)RSP_OK;
   };
   if (done) {
-    c->stager->commit_async(t, [c, s, done, ctx, result] {
+    const double t_commit = now_us();
+    c->stager->commit_async(t, [c, s, done, ctx, result, t_commit] {
       size_t ok = 0;
       const int first = result(&ok);
       const uint64_t seq = rsp_latest_seq(s);
-      c->done_now.push_back([done, ctx, first, ok, seq] { done(ctx, first, ok, seq); });
+      const double t_ran = now_us();
+      c->dbg_ns[0].fetch_add((u64)(1e3 * (t_ran - t_commit)), std::memory_order_relaxed);
+      c->done_now.push_back([c, done, ctx, first, ok, seq, t_ran] {
+        const double t_start = now_us();
+        done(ctx, first, ok, seq);
+        c->dbg_ns[1].fetch_add((u64)(1e3 * (t_start - t_ran)), std::memory_order_relaxed);
+        c->dbg_ns[2].fetch_add((u64)(1e3 * (now_us() - t_start)), std::memory_order_relaxed);
+        c->dbg_n.fetch_add(1, std::memory_order_relaxed);
+      });
     });
     return RSP_OK;
   }
@@ -2876,11 +2934,15 @@ float rsp_last_kernel_ms(const rsp_engine* e, const char* what) {
 }
 uint64_t rsp_kernel_launches(const rsp_engine* e) { return e->launches.load(); }
 
-void rsp_debug_combiner_stats(rsp_engine* e, int which, uint64_t out[5]) {
-  for (int i = 0; i < 5; i++) out[i] = 0;
+void rsp_debug_combiner_stats(rsp_engine* e, int which, uint64_t out[9]) {
+  for (int i = 0; i < 9; i++) out[i] = 0;
   if (!e) return;
   if (which == 0) { if (ReadCombiner* c = e->read_comb_ready.load(std::memory_order_acquire)) c->stager->stats(out); }
-  else if (ApplyCombiner* c = e->apply_comb_ready.load(std::memory_order_acquire)) c->stager->stats(out);
+  else if (ApplyCombiner* c = e->apply_comb_ready.load(std::memory_order_acquire)) {
+    c->stager->stats(out);
+    for (int k = 0; k < 3; k++) out[5 + k] = c->dbg_ns[k].load(std::memory_order_relaxed);
+    out[8] = c->dbg_n.load(std::memory_order_relaxed);
+  }
 }
 
 // diagnostics: how many lookups of the last MultiGet launch took the generic path (synchronises)

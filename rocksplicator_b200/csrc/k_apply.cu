@@ -480,8 +480,9 @@ __global__ void __launch_bounds__(256) k_insert(TickDev t, ShardDev* shards) {
 // Against k_decode -> k_sequence -> k_insert -> k_publish this drops three launches and all the per-batch / per-op
 // records in global memory (BatchDesc, BatchRes, OpRec: ~350 bytes of traffic per 105-byte batch).
 // ------------------------------------------------------------------------------------------------
-// Two shapes: 128 threads / 16 KB stage (8 CTAs per SM at 64 registers: a 1024-group tick is one wave) for long groups, 64 threads / 8 KB stage when no group of the tick
-// holds more than 64 batches (the pull protocol's <= 50 per shard: every CTA of a 1024-shard tick is resident at once).
+// One CTA per group: the shape for ticks whose groups are short — 64 threads / 8 KB stage when no group holds more than 64
+// batches (the pull protocol's <= 50 per shard: every CTA of a 1024-shard tick is resident at once).  Longer groups go to
+// k_tick_chunks below (a CTA per chunk).
 constexpr u32 FT_STAGE_PER_THREAD = 128;  // bytes of stage per thread: a chunk of single-Put batches (105-116 B) fills the block
 
 // exclusive block-wide prefix sums of two values at once: one exchange through shared memory, ONE barrier (before the
@@ -503,6 +504,49 @@ __device__ __forceinline__ void block_excl_scan2(u32 a, u32 b, u32 (*s_warp)[2],
   *a_tot = at; *b_tot = bt;
 }
 
+// the memtable of the group's shard as the insert code needs it (loaded once per CTA)
+struct MtView {
+  ShardDev* sd;
+  u8* heap;
+  u64* slots;
+  u32* ent_off;
+  u32 slot_mask;
+};
+// second walk of an accepted batch: every entry written (shared memory -> heap, 16-byte units) and linked
+__device__ __forceinline__ void insert_batch(const Cursor& c, const MtView& m, u64 seq_base, u32 unit_base, u32 ord_base) {
+  const u8* bp = c.p;
+  const u32 raw_len = c.raw_len;
+  const u64 ts = c.ts;
+  walk_batch(c, [&](u32 type, u32 koff, u32 klen, u32 voff, u32 vlen, u32 units_before, u32 op_ix) {
+    const u32 unit = unit_base + units_before;
+    u8* ent = m.heap + (u64)unit * 16u;
+    u8* kdst = ent + 32u;
+    u8* vdst = kdst + 16u * units_of(klen);
+    u64 h;
+    if (koff + klen <= raw_len && voff + vlen <= raw_len) {
+      h = hash_key(bp + koff, klen);
+      copy_to_units(kdst, bp + koff, klen, 0, 1);
+      copy_to_units(vdst, bp + voff, vlen, 0, 1);
+    } else {
+      // a record that reaches into the virtual LogData bytes (a truncated batch that still parses): byte by byte
+      const u32 kpad = units_of(klen) * 16u, vpad = units_of(vlen) * 16u;
+      for (u32 b = 0; b < kpad; b++) kdst[b] = b < klen ? (u8)batch_byte(bp, raw_len, ts, koff + b) : (u8)0;
+      for (u32 b = 0; b < vpad; b++) vdst[b] = b < vlen ? (u8)batch_byte(bp, raw_len, ts, voff + b) : (u8)0;
+      __threadfence();
+      u64 hh = hash_init(klen);
+      for (u32 i = 0; i < ((klen + 7u) >> 3); i++) hh = hash_step(hh, ld_cg_u64(reinterpret_cast<const u64*>(kdst) + i));
+      h = hash_final(hh);
+    }
+    const u64 st = ((seq_base + op_ix) << 8) | type;
+    *reinterpret_cast<uint4*>(ent) = make_uint4((u32)st, (u32)(st >> 32), klen, vlen);
+    *reinterpret_cast<uint4*>(ent + 16) = make_uint4(0u, 0u, (u32)h, (u32)(h >> 32));
+    m.ent_off[ord_base + op_ix] = unit;
+    const u64 first = ld_cg_u64(m.slots + ((u32)h & m.slot_mask));  // (in flight across the fence)
+    __threadfence();  // the entry is complete before any pointer to it is published
+    link_into_table(m.sd, m.slots, m.slot_mask, m.heap, ent, unit, klen, h, first);
+  });
+}
+
 template <u32 THREADS, u32 MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_tick_fused(FusedTick t, ShardDev* shards, ShardFast* fast) {
   constexpr u32 STAGE = THREADS * FT_STAGE_PER_THREAD;
@@ -517,10 +561,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tick_fused(FusedTick t, Shard
   u64 seq = sd->last_seq;
   u32 tail = sd->mt_tail, cnt = sd->mt_count;
   const u32 heap_cap = sd->mt_heap_cap, ent_cap = sd->mt_ent_cap;
-  u8* heap = sd->mt_heap;
-  u64* slots = sd->mt_slots;
-  u32* ent_off = sd->mt_ent_off;
-  const u32 slot_mask = sd->mt_slot_mask;
+  MtView mt;
+  mt.sd = sd; mt.heap = sd->mt_heap; mt.slots = sd->mt_slots; mt.ent_off = sd->mt_ent_off; mt.slot_mask = sd->mt_slot_mask;
   const u32 trailer = t.ts ? 10u : 0u;
   bool stop = false;  // the memtable is full: the rest of the group is refused (busy), unlatched
   if (tid == 0) { s_first_bad = 0xffffffffu; s_first_over = 0xffffffffu; s_first_status = 0; }
@@ -594,41 +636,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tick_fused(FusedTick t, Shard
       t.bstat[b0 + tid] = st_out;
     }
     // ---- insert: the batch's thread walks it again and writes / links each entry
-    if (accepted && w.n_ops) {
-      const u64 seq_base = seq + 1 + ops_excl;
-      const u32 unit_base = tail + units_excl, ord_base = cnt + ops_excl;
-      const u8* bp = c.p;
-      const u32 raw_len = c.raw_len;
-      const u64 ts = c.ts;
-      walk_batch(c, [&](u32 type, u32 koff, u32 klen, u32 voff, u32 vlen, u32 units_before, u32 op_ix) {
-        const u32 unit = unit_base + units_before;
-        u8* ent = heap + (u64)unit * 16u;
-        u8* kdst = ent + 32u;
-        u8* vdst = kdst + 16u * units_of(klen);
-        u64 h;
-        if (koff + klen <= raw_len && voff + vlen <= raw_len) {
-          h = hash_key(bp + koff, klen);
-          copy_to_units(kdst, bp + koff, klen, 0, 1);
-          copy_to_units(vdst, bp + voff, vlen, 0, 1);
-        } else {
-          // a record that reaches into the virtual LogData bytes (a truncated batch that still parses): byte by byte
-          const u32 kpad = units_of(klen) * 16u, vpad = units_of(vlen) * 16u;
-          for (u32 b = 0; b < kpad; b++) kdst[b] = b < klen ? (u8)batch_byte(bp, raw_len, ts, koff + b) : (u8)0;
-          for (u32 b = 0; b < vpad; b++) vdst[b] = b < vlen ? (u8)batch_byte(bp, raw_len, ts, voff + b) : (u8)0;
-          __threadfence();
-          u64 hh = hash_init(klen);
-          for (u32 i = 0; i < ((klen + 7u) >> 3); i++) hh = hash_step(hh, ld_cg_u64(reinterpret_cast<const u64*>(kdst) + i));
-          h = hash_final(hh);
-        }
-        const u64 st = ((seq_base + op_ix) << 8) | type;
-        *reinterpret_cast<uint4*>(ent) = make_uint4((u32)st, (u32)(st >> 32), klen, vlen);
-        *reinterpret_cast<uint4*>(ent + 16) = make_uint4(0u, 0u, (u32)h, (u32)(h >> 32));
-        ent_off[ord_base + op_ix] = unit;
-        const u64 first = ld_cg_u64(slots + ((u32)h & slot_mask));  // (in flight across the fence)
-        __threadfence();  // the entry is complete before any pointer to it is published
-        link_into_table(sd, slots, slot_mask, heap, ent, unit, klen, h, first);
-      });
-    }
+    if (accepted && w.n_ops) insert_batch(c, mt, seq + 1 + ops_excl, tail + units_excl, cnt + ops_excl);
     // ---- group state after this chunk (uniform)
     seq += tot_ops;
     tail += tot_units;
@@ -656,10 +664,176 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tick_fused(FusedTick t, Shard
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_tick_chunks — the fused tick for groups longer than one chunk: ONE CTA PER CHUNK (<= 128 batches / 16 KB, cut by the
+// host), all chunks of a tick in flight at once.  A chunk stages and decodes on its own, then takes the group's
+// sequencing state (last sequence number, heap tail, entry count, latch, stop) from its predecessor's chain record —
+// the first chunk of a group from the shard descriptor — adds its own totals, publishes its record and only then
+// writes its entries: the decode of chunk i + 1 overlaps the insert of chunk i, and a 1024 x 1000-batch tick is 8192
+// short CTAs instead of 1024 CTAs walking eight chunks each (k_tick_fused: one wave of long latency chains).
+// The chunks of a group are consecutive blocks: a waiting chunk's predecessor has a smaller block index, so it is
+// resident or finished (blocks are dispatched in index order) and the chain always advances; the wait is bounded
+// anyway (a chunk that gives up poisons the chain: the shard latches an IOError).  The CTA that finishes a group last
+// (a counter per group) publishes the group's state and pub_seq.
+// ------------------------------------------------------------------------------------------------
+constexpr u32 TC_THREADS = 128;
+constexpr u32 TC_STAGE = TC_THREADS * FT_STAGE_PER_THREAD;
+static_assert(TC_THREADS == FUSED_CHUNK_BATCHES && TC_STAGE == FUSED_STAGE_BYTES, "the host cuts the chunks by these bounds");
+constexpr u32 CHAIN_READY = 1u << 31, CHAIN_STOP = 1u << 30, CHAIN_POISON = 1u << 29;
+
+__device__ __forceinline__ u64 ld_volatile_u64(const u64* p) { return *reinterpret_cast<const volatile u64*>(p); }
+__device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) { *reinterpret_cast<volatile u64*>(p) = v; }
+
+__global__ void __launch_bounds__(TC_THREADS, 8) k_tick_chunks(FusedTick t, ShardDev* shards, ShardFast* fast) {
+  __shared__ __align__(16) u8 s_blob[TC_STAGE + 64];
+  __shared__ u32 s_warp[TC_THREADS / 32][2];
+  __shared__ u32 s_first_bad, s_first_over, s_first_status, s_tot_ops, s_tot_units;
+  __shared__ u64 s_seq;
+  __shared__ u32 s_tail, s_cnt, s_latch, s_flags;
+  const u32 tid = threadIdx.x;
+  const ChunkDesc ck = t.chunks[blockIdx.x];
+  const GroupDesc g = t.groups[ck.group];
+  ShardDev* sd = shards + g.shard_ix;
+  MtView mt;
+  mt.sd = sd; mt.heap = sd->mt_heap; mt.slots = sd->mt_slots; mt.ent_off = sd->mt_ent_off; mt.slot_mask = sd->mt_slot_mask;
+  const u32 heap_cap = sd->mt_heap_cap, ent_cap = sd->mt_ent_cap;
+  const u32 trailer = t.ts ? 10u : 0u;
+  if (tid == 0) { s_first_bad = 0xffffffffu; s_first_over = 0xffffffffu; s_first_status = 0; }
+  // ---- stage
+  const u32 b0 = ck.first_batch, n_in = ck.n_batches;
+  const u64 base = __ldg(t.off + b0);
+  const bool in = tid < n_in;
+  u64 my_off = 0, my_end = 0;
+  if (in) {
+    my_off = __ldg(t.off + b0 + tid);
+    my_end = t.len ? my_off + __ldg(t.len + b0 + tid) : __ldg(t.off + b0 + tid + 1);
+  }
+  const u32 chunk_bytes = (u32)((t.len ? __ldg(t.off + b0 + n_in - 1) + __ldg(t.len + b0 + n_in - 1) : __ldg(t.off + b0 + n_in)) - base);
+  const u8* src = t.blob + base;
+  const u32 shift = (u32)(reinterpret_cast<uintptr_t>(src) & 15u);
+  const uint4* src4 = reinterpret_cast<const uint4*>(src - shift);
+  const u32 n_units = (shift + chunk_bytes + 15u) >> 4;
+  for (u32 u = tid; u < n_units; u += TC_THREADS) reinterpret_cast<uint4*>(s_blob)[u] = __ldg(src4 + u);
+  const u64 my_ts = (in && t.ts) ? __ldg(t.ts + b0 + tid) : 0ull;
+  // ---- the predecessor's record (thread 0 polls while the others decode)
+  if (tid == 0) {
+    u64 seq; u32 tail, cnt, latch, flags = 0;
+    if (ck.index_in_group == 0) {
+      seq = sd->last_seq; tail = sd->mt_tail; cnt = sd->mt_count; latch = sd->latch;
+    } else {
+      const u64* rec = t.chain + 4ull * (blockIdx.x - 1u);
+      u64 w2 = 0;
+      u32 polls = 0;
+      for (;; polls++) {
+        w2 = ld_volatile_u64(rec + 2);
+        if ((u32)(w2 >> 32) & CHAIN_READY) break;
+        if (polls > (1u << 24)) break;  // (never expected: the predecessor is resident or finished)
+        __nanosleep(polls < 64 ? 20u : 200u);
+      }
+      __threadfence();
+      if ((u32)(w2 >> 32) & CHAIN_READY) {
+        seq = ld_volatile_u64(rec + 0);
+        const u64 w1 = ld_volatile_u64(rec + 1);
+        tail = (u32)w1; cnt = (u32)(w1 >> 32);
+        latch = (u32)w2; flags = (u32)(w2 >> 32) & (CHAIN_STOP | CHAIN_POISON);
+      } else {
+        seq = 0; tail = 0; cnt = 0; latch = mk_status(5, MSG_TOO_LARGE); flags = CHAIN_POISON;
+      }
+    }
+    s_seq = seq; s_tail = tail; s_cnt = cnt; s_latch = latch; s_flags = flags;
+  }
+  __syncthreads();
+  // ---- decode (count pass) + prefix sums over the well-formed batches
+  Cursor c{s_blob + shift + (u32)(my_off - base), 12, (u32)(my_end - my_off) + trailer, (u32)(my_end - my_off), my_ts};
+  WalkResult w{0u, 0u, 0u};
+  if (in) w = walk_batch(c, [](u32, u32, u32, u32, u32, u32, u32) {});
+  if (in && w.status) atomicMin(&s_first_bad, tid);
+  u32 ops_excl, units_excl, tot_ops, tot_units;
+  block_excl_scan2<TC_THREADS>(w.status ? 0u : w.n_ops, w.status ? 0u : w.units, s_warp, &ops_excl, &units_excl, &tot_ops, &tot_units);
+  const u32 first_bad = s_first_bad;
+  const u64 seq = s_seq;
+  const u32 tail = s_tail, cnt = s_cnt, latch = s_latch, flags_in = s_flags;
+  const bool stopped = (flags_in & CHAIN_STOP) != 0;
+  const bool live = latch == 0 && !stopped;
+  const bool over = in && live && tid < first_bad && ((u64)tail + units_excl + w.units > heap_cap || (u64)cnt + ops_excl + w.n_ops > ent_cap);
+  if (over) atomicMin(&s_first_over, tid);
+  if (in && tid == first_bad) { s_first_status = w.status; s_tot_ops = ops_excl; s_tot_units = units_excl; }
+  __syncthreads();
+  const u32 first_over = s_first_over, first_status = s_first_status;
+  if (first_bad != 0xffffffffu) { tot_ops = s_tot_ops; tot_units = s_tot_units; }
+  if (first_over != 0xffffffffu) {
+    __syncthreads();
+    if (tid == first_over) { s_tot_ops = ops_excl; s_tot_units = units_excl; }
+    __syncthreads();
+    tot_ops = s_tot_ops;
+    tot_units = s_tot_units;
+  }
+  if (!live) { tot_ops = 0; tot_units = 0; }
+  // ---- this chunk's record: the successor goes on while the entries below are written
+  u32 latch_out = latch, flags_out = flags_in;
+  {
+    const u32 lim = min(n_in, first_over);
+    if (live && first_bad < lim) latch_out = first_status;
+    if (first_over != 0xffffffffu && latch_out == 0) flags_out |= CHAIN_STOP;
+  }
+  if (tid == 0) {
+    u64* rec = t.chain + 4ull * blockIdx.x;
+    st_volatile_u64(rec + 0, seq + tot_ops);
+    st_volatile_u64(rec + 1, (u64)(tail + tot_units) | ((u64)(cnt + tot_ops) << 32));
+    __threadfence();
+    st_volatile_u64(rec + 2, (u64)latch_out | ((u64)(flags_out | CHAIN_READY) << 32));
+  }
+  const bool accepted = in && live && tid < first_bad && tid < first_over;
+  if (in) {
+    u32 st_out = 0;
+    if (!accepted) {
+      if (latch) st_out = latch;
+      else if (stopped || tid >= first_over) st_out = mk_status(11, MSG_TOO_LARGE);
+      else if (tid > first_bad) st_out = first_status;
+      else st_out = w.status;
+    }
+    t.bstat[b0 + tid] = st_out;
+  }
+  if (accepted && w.n_ops) insert_batch(c, mt, seq + 1 + ops_excl, tail + units_excl, cnt + ops_excl);
+  // ---- the group's last finisher publishes its state
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const u32 done = atomicAdd(t.group_done + ck.group, 1u);
+    if (done + 1u == g.pad) {  // (GroupDesc.pad: the group's chunk count)
+      __threadfence();
+      const u64* rec = t.chain + 4ull * (blockIdx.x - ck.index_in_group + g.pad - 1u);
+      const u64 fseq = ld_volatile_u64(rec + 0), w1 = ld_volatile_u64(rec + 1), w2 = ld_volatile_u64(rec + 2);
+      const u32 flatch = (u32)w2;
+      GroupRes gr;
+      if ((u32)(w2 >> 32) & CHAIN_POISON) {
+        sd->latch = flatch;
+        gr.last_seq = sd->last_seq; gr.tail = sd->mt_tail; gr.count = sd->mt_count; gr.latch = flatch; gr.pad = 0;
+        t.gres[ck.group] = gr;
+      } else {
+        sd->last_seq = fseq;
+        sd->mt_tail = (u32)w1;
+        sd->mt_count = (u32)(w1 >> 32);
+        fast[g.shard_ix].mt_count = (u32)(w1 >> 32);
+        sd->latch = flatch;
+        gr.last_seq = fseq; gr.tail = (u32)w1; gr.count = (u32)(w1 >> 32); gr.latch = flatch; gr.pad = 0;
+        t.gres[ck.group] = gr;
+        __threadfence();
+        sd->pub_seq = fseq;  // every insert of the group is done: readers may see the new versions
+      }
+    }
+  }
+}
+
 void launch_tick_fused(const FusedTick& t, ShardDev* shards, ShardFast* fast, cudaStream_t s) {
   if (!t.n_groups) return;
-  if (t.max_group <= 64 && t.max_len <= 4096) k_tick_fused<64, 16><<<t.n_groups, 64, 0, s>>>(t, shards, fast);
-  else k_tick_fused<128, 8><<<t.n_groups, 128, 0, s>>>(t, shards, fast);
+  if (fused_small_shape(t.max_group, t.max_len)) {
+    k_tick_fused<64, 16><<<t.n_groups, 64, 0, s>>>(t, shards, fast);
+  } else {
+    // (chain records and the per-group counters sit next to each other: one clear)
+    cudaMemsetAsync(t.chain, 0, (size_t)t.n_chunks * 32 + (size_t)t.n_groups * 4, s);
+    k_tick_chunks<<<t.n_chunks, TC_THREADS, 0, s>>>(t, shards, fast);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -78,6 +78,15 @@ void launch_prepare(const PrepareArgs& a, cudaStream_t s);
 // the whole tick in one launch (ticks of small batches): batch i of group g is blob[off[i] .. off[i] + len[i]) (len ==
 // nullptr: the batches are contiguous, length off[i+1] - off[i]); ts != nullptr: the follower's LogData(timestamp)
 // record is a virtual suffix of every batch
+// one chunk of a group (cut by the host): <= FUSED_CHUNK_BATCHES consecutive batches, <= FUSED_STAGE_BYTES of blob
+struct ChunkDesc {
+  u32 group;
+  u32 first_batch;     // staged position of the chunk's first batch
+  u32 n_batches;
+  u32 index_in_group;  // the chunks of a group are consecutive; GroupDesc.pad holds their number
+};
+constexpr u32 FUSED_CHUNK_BATCHES = 128;
+constexpr u32 FUSED_STAGE_BYTES = 16384;
 struct FusedTick {
   const u8* blob;
   const u64* off;
@@ -88,9 +97,16 @@ struct FusedTick {
   GroupRes* gres; // [n_groups]
   u32 n_groups;
   u32 n_batches;
-  u32 max_group;  // batches of the longest group and bytes of the longest batch: pick the kernel shape (64 threads /
-  u32 max_len;    // 8 KB stage when no group holds more than 64 batches and no batch more than 4 KB)
+  u32 max_group;  // batches of the longest group and bytes of the longest batch: pick the kernel (64 threads /
+  u32 max_len;    // 8 KB stage, a CTA per group, when no group holds more than 64 batches and no batch more than 4 KB)
+  // otherwise k_tick_chunks, a CTA per chunk:
+  const ChunkDesc* chunks;
+  u64* chain;        // [n_chunks][4]: the group's sequencing state after each chunk (zeroed before the launch)
+  u32* group_done;   // [n_groups]: chunks of the group that have finished (zeroed before the launch)
+  u32 n_chunks;
+  u32 pad;
 };
+inline bool fused_small_shape(u32 max_group, u32 max_len) { return max_group <= 64 && max_len <= 4096; }
 constexpr u32 FUSED_MAX_BATCH_BYTES = 16384;  // larger batches take the general kernels (one thread walks a batch here)
 void launch_tick_fused(const FusedTick& t, ShardDev* shards, ShardFast* fast, cudaStream_t s);
 void launch_decode(const TickDev& t, cudaStream_t s);

@@ -31,6 +31,7 @@
 #include <condition_variable>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -129,7 +130,8 @@ class Stager {
   // until the batch has run
   void wait(const Ticket& t) {
     Batch& b = b_[t.buf];
-    for (int spins = 0; spins < 1500; spins++) {  // a batch cycle is often shorter than a sleep + wake-up
+    static const int kSpins = [] { const char* v = getenv("RSP_WAIT_SPINS"); return v ? atoi(v) : 1500; }();
+    for (int spins = 0; spins < kSpins; spins++) {  // a batch cycle is often shorter than a sleep + wake-up
       if (b.epoch_done.load(std::memory_order_acquire) >= t.epoch) return;
       cpu_relax();
     }

@@ -355,16 +355,20 @@ extern "C" int rsp_seam_bench(const rsp_seam_cfg* cfg_in, rsp_seam_result* res) 
       res->mget_p99_ms = lat.pct(0.99);
     }
     // ---- ApplicationDB::Get from many threads -------------------------------------------------------
-    auto comb_delta = [&](int which, const uint64_t before[5], double out[5]) {
-      uint64_t now[5];
+    auto comb_delta = [&](int which, const uint64_t before[9], double* out) {
+      uint64_t now[9];
       rsp_debug_combiner_stats(gdb0->engine(), which, now);
       out[0] = (double)(now[0] - before[0]);
       out[1] = (double)(now[1] - before[1]);
       for (int k = 2; k < 5; k++) out[k] = 1e-6 * (double)(now[k] - before[k]);
+      if (which == 1) {
+        for (int k = 5; k < 8; k++) out[k] = 1e-6 * (double)(now[k] - before[k]);
+        out[8] = (double)(now[8] - before[8]);
+      }
     };
     if (cfg.get_threads && cfg.get_secs > 0) {
       Percentiles lat;
-      uint64_t before[5];
+      uint64_t before[9];
       rsp_debug_combiner_stats(gdb0->engine(), 0, before);
       reader(cfg.get_threads, 1, cfg.get_secs, &applied_now, false, &lat, &res->get_per_s, nullptr, true);
       comb_delta(0, before, res->read_comb);
@@ -376,7 +380,7 @@ extern "C" int rsp_seam_bench(const rsp_seam_cfg* cfg_in, rsp_seam_result* res) 
     if (cfg.steady_rounds) {
       const uint64_t target = cur_target + (uint64_t)cfg.steady_rounds * cfg.updates_per_response;
       leader->lat_ms.clear();
-      uint64_t before[5];
+      uint64_t before[9];
       rsp_debug_combiner_stats(gdb0->engine(), 1, before);
       auto& tr = replicator::PullTrace::Get();
       tr.Reset();

@@ -34,7 +34,8 @@ typedef struct rsp_seam_result {
   // steady state of the pull loops alone (shards already loaded, flushes running as memtables fill)
   double steady_applies_per_s, steady_resp_p50_ms, steady_resp_p99_ms;
   double trace_us[6];          // replicator::PullTrace: mean microseconds per stage of a pull round trip
-  double apply_comb[5];        // apply combiner over the steady phase: batches, items, ms running, ms waiting for copiers, ms idle
+  double apply_comb[9];        // apply combiner over the steady phase: batches, items, ms running, ms waiting for copiers, ms idle,
+                               // ms (summed over responses) until the batch ran / until the callback started / inside callbacks, callbacks
   double read_comb[5];         // read combiner over the Get phase
 } rsp_seam_result;
 

@@ -150,6 +150,7 @@ template <class T> static inline T atomicOr(T* p, typename emul_same<T>::type v)
 template <class T> static inline T atomicExch(T* p, typename emul_same<T>::type v) { T old = *p; *p = v; return old; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline void __nanosleep(unsigned) {}
 static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)((((uint64_t)hi << 32) | lo) >> (sh & 31u)); }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {

@@ -625,3 +625,59 @@ def test_flush_sort_paths(eng, port_lib, shape):
         probe = list(dict.fromkeys(keys))[:300] + [b"zz-missing"]
         assert s.multi_get(probe) == o.multi_get(probe)
         s.close()
+
+
+@pytest.mark.parametrize("grouped", [False, True])
+def test_long_groups_chunked_tick(eng, port_lib, grouped):
+    """Ticks whose groups are longer than one chunk (k_tick_chunks: a CTA per chunk of <= 128 batches / 16 KB, the
+    sequencing state handed from chunk to chunk): batch sizes that cut chunks by bytes as well as by count, multi-op
+    batches, a corrupt batch deep inside one shard's group (it and everything after it on THAT shard fail with the
+    latched status, chunks later), a second tick on the latched shard; per-batch statuses, sequence numbers and
+    contents against the oracle.  grouped: the caller's batches already sit shard by shard (the packed tick)."""
+    rnd = random.Random(4242 + grouped)
+    n_shards = 3
+    shards = [new_shard(eng, okv.MERGE_COUNTER, write_buffer_bytes=8 << 20) for _ in range(n_shards)]
+    oracles = [okv.Okv(port_lib, merge_op=okv.MERGE_COUNTER) for _ in range(n_shards)]
+    keys_of = [set() for _ in range(n_shards)]
+    for tick in range(2):
+        per = [[] for _ in range(n_shards)]
+        for j in range(n_shards):
+            for i in range(1500 if j else 700):
+                wb = WriteBatch()
+                for _ in range(1 if rnd.random() < 0.8 else rnd.randint(2, 5)):
+                    k = bench_key(11, rnd.randrange(3000))
+                    keys_of[j].add(k)
+                    r = rnd.random()
+                    if r < 0.7:
+                        wb.put(k, bytes([rnd.randrange(256)]) * (rnd.choice((8, 64, 64, 64, 300, 3000)) if r < 0.05 else 64))
+                    elif r < 0.85:
+                        wb.merge(k, struct.pack("<q", rnd.randint(-5, 5)))
+                    else:
+                        wb.delete(k)
+                b = wb.data()
+                if tick == 0 and j == 1 and i == 777:
+                    b = b[:-3]  # corrupt: shard 1 latches in the middle of its group
+                per[j].append(b)
+        if grouped:
+            order = [(j, b) for j in range(n_shards) for b in per[j]]
+        else:
+            order = []
+            cursors = [0] * n_shards
+            while any(cursors[j] < len(per[j]) for j in range(n_shards)):
+                j = rnd.choice([x for x in range(n_shards) if cursors[x] < len(per[x])])
+                order.append((j, per[j][cursors[j]]))
+                cursors[j] += 1
+        six = [shards[j].index for j, _ in order]
+        batches = [b for _, b in order]
+        ts = [1000 + i for i in range(len(order))]
+        st = eng.apply_many(six, batches, ts)
+        want = [oracles[j].apply(b, t) for (j, b), t in zip(order, ts)]
+        assert list(st) == want, tick
+        assert any(want) and not all(want)
+    for j in range(n_shards):
+        assert shards[j].latest_seq() == oracles[j].latest_seq()
+        keys = sorted(keys_of[j])
+        assert shards[j].multi_get(keys, stride=4096) == oracles[j].multi_get(keys)
+        assert shards[j].scan() == oracles[j].scan()
+    for s in shards:
+        s.close()
