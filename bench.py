@@ -119,7 +119,7 @@ class SeamResult(C.Structure):
                                           "mixed_lookups_per_s", "mixed_resp_p50_ms", "mixed_resp_p99_ms")] + \
                [(n, C.c_uint64) for n in ("applied_total", "parity_errors", "status_errors", "engine_launches")] + \
                [(n, C.c_double) for n in ("steady_applies_per_s", "steady_resp_p50_ms", "steady_resp_p99_ms")] + \
-               [("trace_us", C.c_double * 6), ("apply_comb", C.c_double * 9), ("read_comb", C.c_double * 5)]
+               [("trace_us", C.c_double * 6), ("apply_comb", C.c_double * 9), ("read_comb", C.c_double * 5), ("cpu_s", C.c_double * 4)]
 
 
 def run_seams(device, shards, kv, rank, world, secs=2.0, value_len=64, update_rounds=20, updates_per_response=50,
@@ -145,7 +145,7 @@ def run_seams(device, shards, kv, rank, world, secs=2.0, value_len=64, update_ro
                   first_shard_id=shard_base + rank * shards, steady_rounds=steady_rounds)
     res = SeamResult()
     rc = lib.rsp_seam_bench(C.byref(cfg), C.byref(res))
-    out = {n: (list(getattr(res, n)) if n in ("trace_us", "apply_comb", "read_comb") else getattr(res, n)) for n, _ in SeamResult._fields_}
+    out = {n: (list(getattr(res, n)) if n in ("trace_us", "apply_comb", "read_comb", "cpu_s") else getattr(res, n)) for n, _ in SeamResult._fields_}
     out["rc"] = rc
     out["threads"] = {"executor": cfg.executor_threads, "multiget": cfg.multiget_threads, "get": cfg.get_threads}
     return out
@@ -843,6 +843,7 @@ def main():
                            "round_trip_stage_us_rank0": dict(zip(("transport", "to_executor", "handle_and_stage", "engine", "to_continuation", "to_next_pull"), seams.get("trace_us") or [])),
                            "apply_combiner_rank0": dict(zip(("batches", "updates", "ms_running", "ms_waiting_copiers", "ms_idle", "sum_ms_call_to_batch_ran", "sum_ms_to_callback_start", "sum_ms_in_callbacks", "callbacks"), seams.get("apply_comb") or []))},
                 "get_combiner_rank0": dict(zip(("batches", "keys", "ms_running", "ms_waiting_copiers", "ms_idle"), seams.get("read_comb") or [])),
+                "cpu_seconds_rank0": dict(zip(("load", "multiget", "get", "steady"), seams.get("cpu_s") or [])),
                 "applies_per_s_at_500_updates_per_response": seams_sum["load500_applies_per_s"],
                 "note": "one response in flight per shard (the pull protocol): applies/s = shards x updates per response / round trip; 50 per response is the reference's default flag, 500 shows the same loops with a larger flag value",
                 "multiget_lookups_per_s": seams_sum["mget_lookups_per_s"], "multiget_call_ms": {"p50": seams_max["mget_p50_ms"], "p99": seams_max["mget_p99_ms"]},

@@ -308,6 +308,7 @@ struct rsp_engine {
   // per-run descriptors of every shard ([max_shards][RSP_MAX_RUNS], behind d_fast in the same allocation): the fast
   // MultiGet kernel walks a shard's runs newest first when some shard has more than one (n_multirun counts them)
   ShardFast* d_fast_runs = nullptr;
+  u32* d_mt_filter = nullptr;  // behind d_fast_runs in the same allocation (format.cuh: memtable filter)
   std::atomic<u32> n_multirun{0};
   bool fused_ticks = true;  // RSP_FUSED_TICK=0: always the four general kernels (k_decode .. k_publish)
   bool bg_compaction = true;  // RSP_BG_COMPACT=0: merges run on the apply path (r01 behaviour)
@@ -413,7 +414,7 @@ static void commit_uploads(rsp_engine* e, UploadBatch* b) {
   memcpy(pin, b->recs.data(), bytes);
   ShardUpload* d_up = (ShardUpload*)e->dev_up.get(bytes);
   CUDA_OK(cudaMemcpyAsync(d_up, pin, bytes, cudaMemcpyHostToDevice, e->st));
-  launch_upload_shards(d_up, (u32)n, e->d_shards, e->d_fast, e->d_fast_runs, e->st);
+  launch_upload_shards(d_up, (u32)n, e->d_shards, e->d_fast, e->d_fast_runs, e->d_mt_filter, e->st);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(e->up_ev, e->st));
   e->up_ev_recorded = true;
@@ -452,6 +453,7 @@ static void alloc_memtable(rsp_engine* e, rsp_shard* s, u64 units, u64 ents) {
   s->h.mt_tail = 0;
   s->h.mt_count = 0;
   CUDA_OK(cudaMemsetAsync(s->h.mt_slots, 0, s->mt_slot_bytes, e->st));
+  CUDA_OK(cudaMemsetAsync(e->d_mt_filter + (size_t)s->index * MT_FILTER_WORDS, 0, MT_FILTER_WORDS * 4, e->st));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1084,14 +1086,14 @@ static int reserve_for(rsp_engine* e, const rsp_staged* sg) {
 
 static void tick_launch(rsp_engine* e, rsp_staged* sg, cudaStream_t st) {
   if (sg->fused) {
-    launch_tick_fused(sg->ftick, e->d_shards, e->d_fast, st);
+    launch_tick_fused(sg->ftick, e->d_shards, e->d_fast, e->d_mt_filter, st);
     CUDA_OK(cudaGetLastError());
     e->launches += 1;
     return;
   }
   launch_decode(sg->tick, st);
   launch_sequence(sg->tick, e->d_shards, e->d_fast, st);
-  launch_insert(sg->tick, e->d_shards, st);
+  launch_insert(sg->tick, e->d_shards, e->d_mt_filter, st);
   launch_publish(sg->tick, e->d_shards, st);
   CUDA_OK(cudaGetLastError());
   e->launches += 4;
@@ -1621,40 +1623,56 @@ static void iter_fetch(rsp_iter* it, const std::string* key, bool exclusive, boo
 // ------------------------------------------------------------------------------------------------
 // staging combiners: concurrent callers of the reference's seams share device batches (stager.h)
 // ------------------------------------------------------------------------------------------------
-// asynchronous completions run here, not on a dispatcher thread (a dispatcher that runs user code cannot launch)
+// Asynchronous completions run here, not on a dispatcher thread (a dispatcher that runs user code cannot launch).
+// One task = ALL the completions of one device batch, run back to back by one thread: a wake-up per batch, not per
+// response (the box's CPU time is capped: a thread hand-off per response was most of the follower's cost,
+// profiles/r02_seams_trace.md); a large batch is split over a few threads, eight completions or more each.
 struct CompletionPool {
   std::mutex mu;
   std::condition_variable cv;
-  std::deque<std::function<void()>> q;
+  std::deque<std::vector<std::function<void()>>> q;
   bool stop = false;
+  size_t idle = 0;
   std::vector<std::thread> th;
   void start(size_t n) {
     for (size_t i = 0; i < n; i++) th.emplace_back([this] {
       for (;;) {
-        std::function<void()> f[8];  // a few per lock acquisition: a tick completes a thousand responses at once
-        size_t n = 0;
+        std::vector<std::function<void()>> fs;
         {
           std::unique_lock<std::mutex> l(mu);
+          idle++;
           cv.wait(l, [this] { return stop || !q.empty(); });
+          idle--;
           if (q.empty()) return;  // stop requested and drained
-          const size_t share = std::max<size_t>(1, std::min<size_t>(8, q.size() / (th.size() ? th.size() : 1)));
-          while (n < share && !q.empty()) {
-            f[n++] = std::move(q.front());
-            q.pop_front();
-          }
+          fs = std::move(q.front());
+          q.pop_front();
         }
-        for (size_t i = 0; i < n; i++) f[i]();
+        for (auto& f : fs) f();
       }
     });
   }
   void add_many(std::vector<std::function<void()>>& fs) {
     if (fs.empty()) return;
+    // tasks of >= kMinPerTask completions: a batch of a thousand shards' responses is shared by a few threads
+    constexpr size_t kMinPerTask = 8;
+    const size_t n_tasks = std::max<size_t>(1, std::min(th.size(), fs.size() / kMinPerTask));
+    size_t wake;
     {
       std::lock_guard<std::mutex> g(mu);
-      for (auto& f : fs) q.push_back(std::move(f));
+      if (n_tasks == 1) {
+        q.emplace_back(std::move(fs));
+      } else {
+        const size_t per = (fs.size() + n_tasks - 1) / n_tasks;
+        for (size_t lo = 0; lo < fs.size(); lo += per) {
+          q.emplace_back();
+          auto& v = q.back();
+          for (size_t i = lo; i < std::min(fs.size(), lo + per); i++) v.push_back(std::move(fs[i]));
+        }
+      }
+      wake = std::min(idle, n_tasks);
     }
     fs.clear();
-    cv.notify_all();
+    for (size_t i = 0; i < wake; i++) cv.notify_one();
   }
   void shutdown() {
     {
@@ -1877,7 +1895,7 @@ static ApplyCombiner* apply_combiner(rsp_engine* e) {
   c->o_st = c->o_blob + align_up(c->cap_bytes + 64, 256);
   c->total = c->o_st + align_up(c->cap_items * 4, 256);
   for (auto& S : c->st) S.pin = pinned_mapped(c->total, &S.pin_dev);
-  c->pool.start(env_size("RSP_COMPLETION_THREADS", 16));
+  c->pool.start(env_size("RSP_COMPLETION_THREADS", 8));
   c->stager.reset(new Stager(c->cap_items, c->cap_bytes, [c](const Stager::BatchInfo& b) { c->run(b); },
                              [c] { c->pool.add_many(c->done_now); }));
   e->apply_comb = c;
@@ -2018,10 +2036,13 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   CUDA_OK(cudaMalloc(&e->d_shards, sizeof(ShardDev) * e->cfg.max_shards));
   CUDA_OK(cudaMemset(e->d_shards, 0, sizeof(ShardDev) * e->cfg.max_shards));
   {
+    // [ShardFast x max_shards][ShardFast x max_shards x RSP_MAX_RUNS][memtable filter: MT_FILTER_WORDS x max_shards]
     const size_t n_fast = (size_t)e->cfg.max_shards * (1 + RSP_MAX_RUNS);
-    CUDA_OK(cudaMalloc(&e->d_fast, sizeof(ShardFast) * n_fast));
-    CUDA_OK(cudaMemset(e->d_fast, 0, sizeof(ShardFast) * n_fast));
+    const size_t fast_b = sizeof(ShardFast) * n_fast + (size_t)e->cfg.max_shards * MT_FILTER_WORDS * 4;
+    CUDA_OK(cudaMalloc(&e->d_fast, fast_b));
+    CUDA_OK(cudaMemset(e->d_fast, 0, fast_b));
     e->d_fast_runs = e->d_fast + e->cfg.max_shards;
+    e->d_mt_filter = reinterpret_cast<u32*>(e->d_fast + n_fast);
   }
   if (e->bg_compaction) {
     Compactor* c = new Compactor();
@@ -2112,6 +2133,7 @@ static void shard_close_locked(rsp_shard* s) {
   CUDA_OK(cudaMemcpy(e->d_shards + s->index, &z, sizeof(z), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemset(e->d_fast + s->index, 0, sizeof(ShardFast)));
   CUDA_OK(cudaMemset(e->d_fast_runs + (size_t)s->index * RSP_MAX_RUNS, 0, sizeof(ShardFast) * RSP_MAX_RUNS));
+  CUDA_OK(cudaMemset(e->d_mt_filter + (size_t)s->index * MT_FILTER_WORDS, 0, MT_FILTER_WORDS * 4));
   e->arena.release(s->h.mt_heap, s->mt_heap_bytes);
   e->arena.release(s->h.mt_slots, s->mt_slot_bytes);
   e->arena.release(s->h.mt_ent_off, s->mt_ent_bytes);

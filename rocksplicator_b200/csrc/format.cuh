@@ -140,6 +140,16 @@ struct __align__(32) ShardFast {
   u32 merge_op;
 };
 
+// ---- memtable filter -------------------------------------------------------------------------------
+// One bit per inserted key hash, MT_FILTER_BITS per shard, in one array behind the ShardFast descriptors (8 MB for 1024
+// shards: L2-resident).  The 16-byte-key MultiGet kernels consult it before they touch a memtable: a clear bit means the
+// key is not there, and the lookup skips the descriptor + slot-table round trips (a non-empty memtable used to cost
+// every lookup of its shard two dependent accesses, one of them to HBM).  Set by the insert kernels before an entry
+// is published, cleared when the memtable is flushed.
+constexpr u32 MT_FILTER_BITS = 65536;
+constexpr u32 MT_FILTER_WORDS = MT_FILTER_BITS / 32;
+__host__ __device__ inline u32 mt_filter_bit(u64 h) { return (u32)(h >> 40) & (MT_FILTER_BITS - 1u); }
+
 // ---- entry accessors ----------------------------------------------------------------------------
 struct EntryHdr {
   u64 seqtype;

@@ -341,6 +341,13 @@ __device__ __forceinline__ void copy_to_units(u8* dst, const u8* src, u32 n, u32
 
 __device__ __forceinline__ u64 ld_cg_u64(const u64* p) { return __ldcg(reinterpret_cast<const unsigned long long*>(p)); }
 __device__ __forceinline__ u32 ld_cg_u32(const u32* p) { return __ldcg(p); }
+// memtable filter (format.cuh): the bit of an inserted key, set before the entry is published
+__device__ __forceinline__ void mt_filter_set(u32* filter, u64 h) {
+  const u32 b = mt_filter_bit(h);
+  u32* w = filter + (b >> 5);
+  const u32 m = 1u << (b & 31u);
+  if (!(ld_cg_u32(w) & m)) atomicOr(w, m);  // (overwrites of a hot key find the bit set: no atomic)
+}
 
 // Link the finished entry at `unit` into the shard's table: find (or claim) the user key's slot, then insert
 // the version into the key's chain in sequence order (lock-free; unit offsets grow with sequence).  Keys are
@@ -405,7 +412,7 @@ __device__ __noinline__ void link_into_table(ShardDev* sd, u64* slots, u32 mask,
   }
 }
 
-__global__ void __launch_bounds__(256) k_insert(TickDev t, ShardDev* shards) {
+__global__ void __launch_bounds__(256) k_insert(TickDev t, ShardDev* shards, u32* mt_filter) {
   const u32 gid = (blockIdx.x * blockDim.x + threadIdx.x) / INS_LANES;
   const u32 lane = threadIdx.x & (INS_LANES - 1);
   const u32 gmask = ((1u << INS_LANES) - 1u) << ((threadIdx.x & 31u) & ~(INS_LANES - 1u));
@@ -460,6 +467,7 @@ __global__ void __launch_bounds__(256) k_insert(TickDev t, ShardDev* shards) {
   if (lane == 1) *reinterpret_cast<uint4*>(ent + 16) = make_uint4(0u, 0u, (u32)h, (u32)(h >> 32));
   u64* slots = sd->mt_slots;
   const u32 mask = sd->mt_slot_mask;
+  if (lane == 0) mt_filter_set(mt_filter + (size_t)bdx.shard_ix * MT_FILTER_WORDS, h);
   const u64 first = lane == 0 ? ld_cg_u64(slots + ((u32)h & mask)) : 0ull;
   __threadfence();  // the entry is complete before any pointer to it is published
   __syncwarp(gmask);
@@ -510,8 +518,10 @@ struct MtView {
   u8* heap;
   u64* slots;
   u32* ent_off;
+  u32* filter;  // the shard's row of the memtable filter
   u32 slot_mask;
 };
+
 // second walk of an accepted batch: every entry written (shared memory -> heap, 16-byte units) and linked
 __device__ __forceinline__ void insert_batch(const Cursor& c, const MtView& m, u64 seq_base, u32 unit_base, u32 ord_base) {
   const u8* bp = c.p;
@@ -541,6 +551,7 @@ __device__ __forceinline__ void insert_batch(const Cursor& c, const MtView& m, u
     *reinterpret_cast<uint4*>(ent) = make_uint4((u32)st, (u32)(st >> 32), klen, vlen);
     *reinterpret_cast<uint4*>(ent + 16) = make_uint4(0u, 0u, (u32)h, (u32)(h >> 32));
     m.ent_off[ord_base + op_ix] = unit;
+    mt_filter_set(m.filter, h);
     const u64 first = ld_cg_u64(m.slots + ((u32)h & m.slot_mask));  // (in flight across the fence)
     __threadfence();  // the entry is complete before any pointer to it is published
     link_into_table(m.sd, m.slots, m.slot_mask, m.heap, ent, unit, klen, h, first);
@@ -548,7 +559,7 @@ __device__ __forceinline__ void insert_batch(const Cursor& c, const MtView& m, u
 }
 
 template <u32 THREADS, u32 MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_tick_fused(FusedTick t, ShardDev* shards, ShardFast* fast) {
+__global__ void __launch_bounds__(THREADS, MINB) k_tick_fused(FusedTick t, ShardDev* shards, ShardFast* fast, u32* mt_filter) {
   constexpr u32 STAGE = THREADS * FT_STAGE_PER_THREAD;
   __shared__ __align__(16) u8 s_blob[STAGE + 64];
   __shared__ u32 s_warp[THREADS / 32][2];
@@ -563,6 +574,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tick_fused(FusedTick t, Shard
   const u32 heap_cap = sd->mt_heap_cap, ent_cap = sd->mt_ent_cap;
   MtView mt;
   mt.sd = sd; mt.heap = sd->mt_heap; mt.slots = sd->mt_slots; mt.ent_off = sd->mt_ent_off; mt.slot_mask = sd->mt_slot_mask;
+  mt.filter = mt_filter + (size_t)g.shard_ix * MT_FILTER_WORDS;
   const u32 trailer = t.ts ? 10u : 0u;
   bool stop = false;  // the memtable is full: the rest of the group is refused (busy), unlatched
   if (tid == 0) { s_first_bad = 0xffffffffu; s_first_over = 0xffffffffu; s_first_status = 0; }
@@ -684,7 +696,7 @@ constexpr u32 CHAIN_READY = 1u << 31, CHAIN_STOP = 1u << 30, CHAIN_POISON = 1u <
 __device__ __forceinline__ u64 ld_volatile_u64(const u64* p) { return *reinterpret_cast<const volatile u64*>(p); }
 __device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) { *reinterpret_cast<volatile u64*>(p) = v; }
 
-__global__ void __launch_bounds__(TC_THREADS, 8) k_tick_chunks(FusedTick t, ShardDev* shards, ShardFast* fast) {
+__global__ void __launch_bounds__(TC_THREADS, 8) k_tick_chunks(FusedTick t, ShardDev* shards, ShardFast* fast, u32* mt_filter) {
   __shared__ __align__(16) u8 s_blob[TC_STAGE + 64];
   __shared__ u32 s_warp[TC_THREADS / 32][2];
   __shared__ u32 s_first_bad, s_first_over, s_first_status, s_tot_ops, s_tot_units;
@@ -696,6 +708,7 @@ __global__ void __launch_bounds__(TC_THREADS, 8) k_tick_chunks(FusedTick t, Shar
   ShardDev* sd = shards + g.shard_ix;
   MtView mt;
   mt.sd = sd; mt.heap = sd->mt_heap; mt.slots = sd->mt_slots; mt.ent_off = sd->mt_ent_off; mt.slot_mask = sd->mt_slot_mask;
+  mt.filter = mt_filter + (size_t)g.shard_ix * MT_FILTER_WORDS;
   const u32 heap_cap = sd->mt_heap_cap, ent_cap = sd->mt_ent_cap;
   const u32 trailer = t.ts ? 10u : 0u;
   if (tid == 0) { s_first_bad = 0xffffffffu; s_first_over = 0xffffffffu; s_first_status = 0; }
@@ -825,14 +838,14 @@ __global__ void __launch_bounds__(TC_THREADS, 8) k_tick_chunks(FusedTick t, Shar
   }
 }
 
-void launch_tick_fused(const FusedTick& t, ShardDev* shards, ShardFast* fast, cudaStream_t s) {
+void launch_tick_fused(const FusedTick& t, ShardDev* shards, ShardFast* fast, u32* mt_filter, cudaStream_t s) {
   if (!t.n_groups) return;
   if (fused_small_shape(t.max_group, t.max_len)) {
-    k_tick_fused<64, 16><<<t.n_groups, 64, 0, s>>>(t, shards, fast);
+    k_tick_fused<64, 16><<<t.n_groups, 64, 0, s>>>(t, shards, fast, mt_filter);
   } else {
     // (chain records and the per-group counters sit next to each other: one clear)
     cudaMemsetAsync(t.chain, 0, (size_t)t.n_chunks * 32 + (size_t)t.n_groups * 4, s);
-    k_tick_chunks<<<t.n_chunks, TC_THREADS, 0, s>>>(t, shards, fast);
+    k_tick_chunks<<<t.n_chunks, TC_THREADS, 0, s>>>(t, shards, fast, mt_filter);
   }
 }
 
@@ -889,10 +902,10 @@ void launch_sequence(const TickDev& t, ShardDev* shards, ShardFast* fast, cudaSt
   if (!t.n_groups) return;
   k_sequence<<<(t.n_groups + 3) / 4, 128, 0, s>>>(t, shards, fast);
 }
-void launch_insert(const TickDev& t, ShardDev* shards, cudaStream_t s) {
+void launch_insert(const TickDev& t, ShardDev* shards, u32* mt_filter, cudaStream_t s) {
   if (!t.n_ops_cap) return;
   const u32 per_block = 256 / INS_LANES;
-  k_insert<<<(t.n_ops_cap + per_block - 1) / per_block, 256, 0, s>>>(t, shards);
+  k_insert<<<(t.n_ops_cap + per_block - 1) / per_block, 256, 0, s>>>(t, shards, mt_filter);
 }
 void launch_publish(const TickDev& t, ShardDev* shards, cudaStream_t s) {
   if (!t.n_groups) return;

@@ -558,7 +558,8 @@ void launch_zero_out_hslots(const CompactJob* d_jobs, u32 n_jobs, u32 max_bucket
   k_zero_out_hslots<<<dim3(std::max<u32>(gx, 1u), n_jobs), 256, 0, s>>>(d_jobs);
 }
 
-__global__ void __launch_bounds__(128) k_upload_shards(const ShardUpload* up, ShardDev* shards, ShardFast* fast, ShardFast* fast_runs) {
+__global__ void __launch_bounds__(128) k_upload_shards(const ShardUpload* up, ShardDev* shards, ShardFast* fast, ShardFast* fast_runs,
+                                                        u32* mt_filter) {
   const ShardUpload& u = up[blockIdx.x];
   const u32 ix = u.index;
   {
@@ -582,11 +583,14 @@ __global__ void __launch_bounds__(128) k_upload_shards(const ShardUpload* up, Sh
     uint4* p = reinterpret_cast<uint4*>(u.sd.mt_slots);
     const u32 n = (u.sd.mt_slot_mask + 1u) / 2u;  // 8-byte slots, 16-byte stores (the table holds >= 16 slots)
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) p[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint4* f = reinterpret_cast<uint4*>(mt_filter + (size_t)ix * MT_FILTER_WORDS);  // and its filter
+    for (u32 i = threadIdx.x; i < MT_FILTER_WORDS / 4u; i += blockDim.x) f[i] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
-void launch_upload_shards(const ShardUpload* d_up, u32 n, ShardDev* shards, ShardFast* fast, ShardFast* fast_runs, cudaStream_t s) {
+void launch_upload_shards(const ShardUpload* d_up, u32 n, ShardDev* shards, ShardFast* fast, ShardFast* fast_runs, u32* mt_filter,
+                          cudaStream_t s) {
   if (!n) return;
-  k_upload_shards<<<n, 128, 0, s>>>(d_up, shards, fast, fast_runs);
+  k_upload_shards<<<n, 128, 0, s>>>(d_up, shards, fast, fast_runs, mt_filter);
 }
 
 void launch_compact_sort(const CompactJob* d_jobs, const CompactJob* h_jobs, u32 n_jobs, cudaStream_t s) {

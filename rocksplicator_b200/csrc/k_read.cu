@@ -436,7 +436,14 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16(GetArgs
   u32 state = 3;  // 0 served, 2 generic path, 3 undecided, 4 not found
   u32 vlen = 0;
   if (n_runs > 1 || ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u) || bad_shard || !(f1.y >> 24)) state = 2;
+  bool in_mem = false;
   if (state == 3 && f1.z /* mt_count */) {
+    // the shard's memtable filter (L2-resident, behind the descriptors): a clear bit = the key is not in the memtable
+    const u32 fb = mt_filter_bit(h);
+    const u32 fw = __ldcg(reinterpret_cast<const u32*>(a.fast + (size_t)a.max_shards * (1u + RSP_MAX_RUNS)) + (size_t)six * MT_FILTER_WORDS + (fb >> 5));
+    in_mem = (fw >> (fb & 31u)) & 1u;
+  }
+  if (in_mem) {
     // ---- memtable: eight u64 slots from the home position, four per lane; descriptor through L2
     const uint4* dp = reinterpret_cast<const uint4*>(a.shards + six);
     const uint4 d0 = __ldcg(dp), d1 = __ldcg(dp + 1), d3 = __ldcg(dp + 3);
@@ -643,7 +650,14 @@ __global__ void __launch_bounds__(RSP_MG_TPB, RSP_MG_MINB) k_multi_get16m(GetArg
   u32 state = 3;  // 0 served, 2 generic path, 3 undecided, 4 not found
   u32 vlen = 0;
   if ((!MULTI && n_runs > 1) || ((a.val_stride | reinterpret_cast<uintptr_t>(a.vals)) & 15u) || bad_shard || !(f1.y & FAST_META_LIVE)) state = 2;
+  bool in_mem = false;
   if (state == 3 && f1.z /* mt_count */) {
+    // the shard's memtable filter (L2-resident, behind the descriptors): a clear bit = the key is not in the memtable
+    const u32 fb = mt_filter_bit(h);
+    const u32 fw = __ldcg(reinterpret_cast<const u32*>(a.fast + (size_t)a.max_shards * (1u + RSP_MAX_RUNS)) + (size_t)six * MT_FILTER_WORDS + (fb >> 5));
+    in_mem = (fw >> (fb & 31u)) & 1u;
+  }
+  if (in_mem) {
     // ---- memtable: eight u64 slots from the home position, four per lane; descriptor through L2
     const uint4* dp = reinterpret_cast<const uint4*>(a.shards + six);
     const uint4 d0 = __ldcg(dp), d1 = __ldcg(dp + 1), d3 = __ldcg(dp + 3);

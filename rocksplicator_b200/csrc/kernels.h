@@ -108,10 +108,10 @@ struct FusedTick {
 };
 inline bool fused_small_shape(u32 max_group, u32 max_len) { return max_group <= 64 && max_len <= 4096; }
 constexpr u32 FUSED_MAX_BATCH_BYTES = 16384;  // larger batches take the general kernels (one thread walks a batch here)
-void launch_tick_fused(const FusedTick& t, ShardDev* shards, ShardFast* fast, cudaStream_t s);
+void launch_tick_fused(const FusedTick& t, ShardDev* shards, ShardFast* fast, u32* mt_filter, cudaStream_t s);
 void launch_decode(const TickDev& t, cudaStream_t s);
 void launch_sequence(const TickDev& t, ShardDev* shards, ShardFast* fast, cudaStream_t s);
-void launch_insert(const TickDev& t, ShardDev* shards, cudaStream_t s);
+void launch_insert(const TickDev& t, ShardDev* shards, u32* mt_filter, cudaStream_t s);
 void launch_publish(const TickDev& t, ShardDev* shards, cudaStream_t s);
 
 // ---- reads ---------------------------------------------------------------------------------------
@@ -248,6 +248,7 @@ struct ShardUpload {
   ShardFast fast_runs[RSP_MAX_RUNS];
 };
 static_assert(sizeof(ShardUpload) % 32 == 0, "records are copied as words from an array");
-void launch_upload_shards(const ShardUpload* d_up, u32 n, ShardDev* shards, ShardFast* fast, ShardFast* fast_runs, cudaStream_t s);
+void launch_upload_shards(const ShardUpload* d_up, u32 n, ShardDev* shards, ShardFast* fast, ShardFast* fast_runs, u32* mt_filter,
+                          cudaStream_t s);
 
 }  // namespace rsp

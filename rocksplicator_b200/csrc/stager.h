@@ -24,7 +24,9 @@
 // of two the eight levels were the whole 1.5 ms p50 of ApplicationDB::Get).  Both alternatives were measured with 256 ApplicationDB::Get threads on the
 // 128-core host: one condition variable for everybody = 55 K Gets/s (the herd re-acquiring its mutex takes longer than
 // the batch), spin-then-yield = p50 0.27 ms but p99 300 ms (spinners starve the dispatcher once threads outnumber
-// cores).
+// cores).  Spins are SHORT (a few microseconds: RSP_WAIT_SPINS / RSP_DISPATCH_SPINS pauses): the GPU boxes cap the
+// container's CPU time (16 CPUs of 128 visible), and spinning callers spend the budget the dispatcher needs — 64 Get
+// callers: 151 K Gets/s with 1500-pause spins, 574 K without (profiles/r02_seams_trace.md).
 #pragma once
 #include <atomic>
 #include <chrono>
@@ -61,7 +63,8 @@ class Stager {
   using PostFn = std::function<void()>;  // dispatcher thread, after the asynchronous completions of a batch ran
 
   static constexpr int kBuffers = 4;  // filling | running | results being read (callers still waking up: two)
-  static constexpr int kWakeFan = 16;
+  static constexpr int kWakeFan = 4;     // per futex word (kWakeWords of them per batch)
+  static constexpr int kWakeWords = 16;
 
   Stager(size_t cap_items, size_t cap_bytes, RunFn run, PostFn post = nullptr)
       : cap_items_(cap_items), cap_bytes_(cap_bytes), run_(std::move(run)), post_(std::move(post)) {
@@ -88,6 +91,7 @@ class Stager {
     if (n_items > max_items || n_bytes > cap_bytes_) return false;
     for (int spins = 0;; spins++) {
       if (stop_.load(std::memory_order_acquire)) return false;
+      const uint32_t seen_free = free32_.load(std::memory_order_acquire);
       {
         SpinGuard g(sl_);
         if (open_ >= 0) {
@@ -108,11 +112,17 @@ class Stager {
           b.full = true;  // full, or of another class: the dispatcher closes it as soon as it can
         }
       }
-      // no room right now: a buffer frees up within a batch cycle
-      if (spins < 200) cpu_relax();
-      else NapUs(20);
+      // no room right now: a buffer opens within a batch cycle.  Sleep on the word that counts openings (no polling:
+      // the box's CPU time is capped, profiles/r02_seams_trace.md); bounded, in case the opening raced the read above
+      if (spins < 20) cpu_relax();
+      else {
+        buf_waiters_.fetch_add(1, std::memory_order_seq_cst);
+        FutexWait(&free32_, seen_free, 500000);
+        buf_waiters_.fetch_sub(1, std::memory_order_seq_cst);
+      }
     }
     if (disp_sleeping_.load(std::memory_order_seq_cst)) FutexWake(&work32_, 1);
+    if (buf_waiters_.load(std::memory_order_relaxed)) FutexWake(&free32_, 2);  // (a few at a time: they all fit one batch)
     return true;
   }
   // the caller finished writing its slice
@@ -130,25 +140,33 @@ class Stager {
   // until the batch has run
   void wait(const Ticket& t) {
     Batch& b = b_[t.buf];
-    static const int kSpins = [] { const char* v = getenv("RSP_WAIT_SPINS"); return v ? atoi(v) : 1500; }();
+    static const int kSpins = [] { const char* v = getenv("RSP_WAIT_SPINS"); return v ? atoi(v) : 100; }();
     for (int spins = 0; spins < kSpins; spins++) {  // a batch cycle is often shorter than a sleep + wake-up
       if (b.epoch_done.load(std::memory_order_acquire) >= t.epoch) return;
       cpu_relax();
     }
+    // sleepers spread over kWakeWords futex words (the kernel hashes a futex by its address: hundreds of callers waiting
+    // on and waking ONE word queue on one hash-bucket lock inside the kernel)
+    WakeWord& ww = b.wake[(uint32_t)((t.item0 * 2654435761u) >> 16) % kWakeWords];
     bool slept = false;
     for (;;) {
-      const uint32_t s = b.seq.load(std::memory_order_acquire);
+      const uint32_t s = ww.seq.load(std::memory_order_acquire);
       if (b.epoch_done.load(std::memory_order_acquire) >= t.epoch) break;
-      FutexWait(&b.seq, s, 2000000);  // (bounded: 2 ms)
+      ww.sleepers.fetch_add(1, std::memory_order_seq_cst);
+      FutexWait(&ww.seq, s, 2000000);  // (bounded: 2 ms)
+      ww.sleepers.fetch_sub(1, std::memory_order_seq_cst);
       slept = true;
     }
-    if (slept) FutexWake(&b.seq, kWakeFan);  // pass the wake-up on
+    if (slept && ww.sleepers.load(std::memory_order_seq_cst)) FutexWake(&ww.seq, kWakeFan);  // pass the wake-up on
   }
   void release(const Ticket& t) {
     Batch& b = b_[t.buf];
     if (b.users.fetch_sub(1, std::memory_order_acq_rel) == 1) {
-      SpinGuard g(sl_);
-      MaybeFree(b);
+      {
+        SpinGuard g(sl_);
+        MaybeFree(b);
+      }
+      WakeBufferWaiters();
     }
   }
 
@@ -162,6 +180,10 @@ class Stager {
 
  private:
   enum State { FREE, OPEN, CLOSED, DONE };
+  struct alignas(64) WakeWord {
+    std::atomic<uint32_t> seq{0};
+    std::atomic<uint32_t> sleepers{0};  // callers inside FutexWait on seq (a wake-up is a system call: skipped when 0)
+  };
   struct Batch {
     State state = FREE;                 // sl_
     size_t n_items = 0, n_bytes = 0;    // sl_
@@ -171,7 +193,7 @@ class Stager {
     std::atomic<uint32_t> copiers{0};   // callers still writing their slice
     std::atomic<uint32_t> users{0};     // callers (sync and async) that have not released their slice yet
     std::atomic<uint64_t> epoch_done{0};
-    std::atomic<uint32_t> seq{0};       // futex word: bumped when the batch has run
+    WakeWord wake[kWakeWords];          // futex words: bumped when the batch has run
     std::vector<std::function<void()>> async;  // sl_
   };
   static inline void cpu_relax() {
@@ -221,8 +243,12 @@ class Stager {
     ts.tv_nsec = us * 1000L;
     nanosleep(&ts, nullptr);
   }
-  void WakeSleepers() {  // Stop(): the dispatcher may be asleep
+  void WakeBufferWaiters() {  // after a buffer may have opened (sl_ NOT held: a system call)
+    if (buf_waiters_.load(std::memory_order_seq_cst)) FutexWake(&free32_, kWakeFan);
+  }
+  void WakeSleepers() {  // Stop(): the dispatcher may be asleep, callers may wait for a buffer
     FutexWake(&work32_, 1);
+    FutexWake(&free32_, 1 << 20);
   }
 
   bool MaybeFree(Batch& b) {  // sl_ held: whoever sees "done and unused" first recycles the buffer
@@ -241,6 +267,7 @@ class Stager {
         b_[i].full = false;
         b_[i].epoch = ++epochs_;
         open_ = i;
+        free32_.fetch_add(1, std::memory_order_seq_cst);  // (whoever called wakes the waiters after dropping sl_)
         return;
       }
     }
@@ -262,7 +289,8 @@ class Stager {
           }
         }
         if (stop_.load(std::memory_order_acquire)) return;  // (queued work was taken above: callers wait on it)
-        if (spins < 3000) cpu_relax();  // stay hot between batches under load
+        static const int kIdleSpins = [] { const char* v = getenv("RSP_DISPATCH_SPINS"); return v ? atoi(v) : 100; }();
+        if (spins < kIdleSpins) cpu_relax();  // stay hot between batches under load
         else {
           disp_sleeping_.store(true, std::memory_order_seq_cst);
           const uint32_t w = work32_.load(std::memory_order_seq_cst);
@@ -271,6 +299,7 @@ class Stager {
         }
       }
       seen_work_ = work32_.load(std::memory_order_seq_cst);
+      WakeBufferWaiters();  // (the next buffer opened when this one was closed)
       Batch& b = b_[bi];
       const int64_t t_copy0 = NowNs();
       st_idle_ns_.fetch_add((uint64_t)(t_copy0 - t_idle0), std::memory_order_relaxed);
@@ -292,8 +321,10 @@ class Stager {
       for (auto& f : async) f();
       if (post_) post_();
       b.epoch_done.store(info.epoch, std::memory_order_release);  // spinning callers go on at once
-      b.seq.fetch_add(1, std::memory_order_release);
-      FutexWake(&b.seq, kWakeFan);                                 // sleeping ones: a few, who wake the others
+      for (int w = 0; w < kWakeWords; w++) {  // sleeping ones: a few per word, who wake the others
+        b.wake[w].seq.fetch_add(1, std::memory_order_seq_cst);
+        if (b.wake[w].sleepers.load(std::memory_order_seq_cst)) FutexWake(&b.wake[w].seq, 2);
+      }
       batches_.fetch_add(1, std::memory_order_relaxed);
       {
         SpinGuard g(sl_);
@@ -301,6 +332,7 @@ class Stager {
         if (!async.empty()) b.users.fetch_sub((uint32_t)async.size(), std::memory_order_acq_rel);
         MaybeFree(b);
       }
+      WakeBufferWaiters();
     }
   }
 
@@ -313,6 +345,8 @@ class Stager {
   uint64_t epochs_ = 0;
   std::atomic<bool> stop_{false}, disp_sleeping_{false};
   std::atomic<uint32_t> work32_{0};  // requests ever accepted (futex word): the idle dispatcher sleeps until it moves
+  std::atomic<uint32_t> free32_{0};  // buffers ever opened (futex word): callers without a buffer sleep until it moves
+  std::atomic<uint32_t> buf_waiters_{0};
   uint32_t seen_work_ = 0;
   std::atomic<uint64_t> batches_{0}, st_items_{0}, st_run_ns_{0}, st_copy_ns_{0}, st_idle_ns_{0};
   std::thread thread_;

@@ -23,6 +23,8 @@
 #include <thread>
 #include <vector>
 
+#include <sys/resource.h>
+
 #include "common/segment_utils.h"
 #include "gpu_db.h"
 #include "rocksdb_admin/application_db.h"
@@ -75,6 +77,12 @@ inline void single_put_batch(const uint8_t* key, const uint8_t* val, uint32_t vl
   out->push_back(0x3);
   out->push_back(8);
   out->append((const char*)&ts, 8);
+}
+
+double cpu_seconds() {
+  struct rusage ru;
+  getrusage(RUSAGE_SELF, &ru);
+  return ru.ru_utime.tv_sec + ru.ru_stime.tv_sec + 1e-6 * (ru.ru_utime.tv_usec + ru.ru_stime.tv_usec);
 }
 
 uint64_t now_ms() {
@@ -242,12 +250,14 @@ extern "C" int rsp_seam_bench(const rsp_seam_cfg* cfg_in, rsp_seam_result* res) 
     // ---- load: every shard pulls its keys from the synthetic leader --------------------------------
     leader->SetTargets(per_shard);
     auto t0 = Clock::now();
+    double cpu0 = cpu_seconds();
     for (uint32_t i = 0; i < S; i++)
       adbs[i].reset(new admin::ApplicationDB(common::SegmentToDbName("seam", (int)(cfg.first_shard_id + i)), dbs[i],
                                              replicator::ReplicaRole::FOLLOWER,
                                              std::make_unique<replicator::SocketAddress>("127.0.0.1", 1), &repl));
     if (!wait_seq(per_shard, 600)) status_errors++;
     res->load_s = secs_since(t0);
+    res->cpu_s[0] = cpu_seconds() - cpu0;
     res->load_applies_per_s = (double)per_shard * S / res->load_s;
     res->resp_p50_ms = leader->lat_ms.pct(0.5);
     res->resp_p99_ms = leader->lat_ms.pct(0.99);
@@ -349,8 +359,10 @@ extern "C" int rsp_seam_bench(const rsp_seam_cfg* cfg_in, rsp_seam_result* res) 
     // ---- ApplicationDB::MultiGet(batch) from many threads, compacted shards -------------------------
     if (cfg.multiget_threads && cfg.multiget_secs > 0) {
       Percentiles lat;
+      cpu0 = cpu_seconds();
       reader(cfg.multiget_threads, cfg.multiget_batch, cfg.multiget_secs, &applied_now, false, &lat, &res->mget_lookups_per_s,
              &res->mget_calls, false);
+      res->cpu_s[1] = cpu_seconds() - cpu0;
       res->mget_p50_ms = lat.pct(0.5);
       res->mget_p99_ms = lat.pct(0.99);
     }
@@ -370,7 +382,9 @@ extern "C" int rsp_seam_bench(const rsp_seam_cfg* cfg_in, rsp_seam_result* res) 
       Percentiles lat;
       uint64_t before[9];
       rsp_debug_combiner_stats(gdb0->engine(), 0, before);
+      cpu0 = cpu_seconds();
       reader(cfg.get_threads, 1, cfg.get_secs, &applied_now, false, &lat, &res->get_per_s, nullptr, true);
+      res->cpu_s[2] = cpu_seconds() - cpu0;
       comb_delta(0, before, res->read_comb);
       res->get_p50_us = lat.pct(0.5);
       res->get_p99_us = lat.pct(0.99);
@@ -386,9 +400,11 @@ extern "C" int rsp_seam_bench(const rsp_seam_cfg* cfg_in, rsp_seam_result* res) 
       tr.Reset();
       tr.enabled = true;
       t0 = Clock::now();
+      cpu0 = cpu_seconds();
       leader->SetTargets(target);
       if (!wait_seq(target, 600)) status_errors++;
       const double el = secs_since(t0);
+      res->cpu_s[3] = cpu_seconds() - cpu0;
       tr.enabled = false;
       res->steady_applies_per_s = (double)cfg.steady_rounds * cfg.updates_per_response * S / el;
       res->steady_resp_p50_ms = leader->lat_ms.pct(0.5);

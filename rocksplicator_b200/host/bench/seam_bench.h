@@ -37,6 +37,8 @@ typedef struct rsp_seam_result {
   double apply_comb[9];        // apply combiner over the steady phase: batches, items, ms running, ms waiting for copiers, ms idle,
                                // ms (summed over responses) until the batch ran / until the callback started / inside callbacks, callbacks
   double read_comb[5];         // read combiner over the Get phase
+  double cpu_s[4];             // CPU seconds of the process (getrusage: user + system) spent in the load, MultiGet, Get and
+                               // steady phases — the GPU boxes cap the container's CPU time
 } rsp_seam_result;
 
 int rsp_seam_bench(const rsp_seam_cfg* cfg, rsp_seam_result* res);

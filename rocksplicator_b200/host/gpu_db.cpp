@@ -80,19 +80,23 @@ Status GpuDB::ToStatus(int code) const {
   return Status::FromCode(code, buf);
 }
 
-void GpuDB::LogAppend(rocksdb::SequenceNumber first_seq, std::string&& bytes, uint32_t count) {
-  auto e = std::make_shared<LogEntry>();
-  e->first_seq = first_seq;
-  e->count = count;
-  e->bytes = std::move(bytes);
-  std::lock_guard<std::mutex> g(log_mu_);
-  log_bytes_ += e->bytes.size();
-  log_.push_back(std::move(e));
+void GpuDB::LogPush(std::shared_ptr<const LogChunk> c) {
+  log_bytes_ += c->bytes.size();
+  log_.push_back(std::move(c));
   while (log_bytes_ > log_cap_bytes_ && log_.size() > 1) {  // WAL TTL / size limit stand-in
     log_bytes_ -= log_.front()->bytes.size();
     log_.pop_front();
     log_base_id_++;
   }
+}
+void GpuDB::LogAppend(rocksdb::SequenceNumber first_seq, std::string&& bytes, uint32_t count) {
+  auto c = std::make_shared<LogChunk>();
+  c->first_seq = first_seq;
+  c->last_seq = first_seq + count - 1;
+  c->bytes = std::move(bytes);
+  c->recs.push_back(LogChunk::Rec{0u, (uint32_t)c->bytes.size(), count, first_seq});
+  std::lock_guard<std::mutex> g(log_mu_);
+  LogPush(std::move(c));
 }
 
 Status GpuDB::Write(const rocksdb::WriteOptions&, rocksdb::WriteBatch* updates) {
@@ -362,9 +366,12 @@ void GpuDB::ApplyReplicatedBatch(const std::vector<replicator::Update>& updates,
         {
           // what the follower's own WAL would hold (its downstream followers pull it): every applied batch + its
           // LogData(timestamp), stamped with its sequence number; built outside the log's lock, appended in one go
-          std::vector<std::shared_ptr<LogEntry>> fresh;
-          fresh.reserve(n_applied);
-          size_t bytes_total = 0;
+          auto chunk = std::make_shared<LogChunk>();
+          size_t total = 0;
+          for (size_t i = 0; i < n_applied; i++) total += (*x->updates)[i].raw_data.size() + 10;
+          chunk->bytes.reserve(total);
+          chunk->recs.reserve(n_applied);
+          chunk->first_seq = first;
           for (size_t i = 0; i < n_applied; i++) {
             const std::string& raw = (*x->updates)[i].raw_data;
             if (raw.size() < rocksdb::WriteBatch::kHeader) continue;
@@ -372,28 +379,20 @@ void GpuDB::ApplyReplicatedBatch(const std::vector<replicator::Update>& updates,
             memcpy(&count, raw.data() + 8, 4);
             if (!count) continue;
             const uint64_t tsv = (uint64_t)(*x->updates)[i].timestamp;
-            auto e = std::make_shared<LogEntry>();
-            e->first_seq = first;
-            e->count = count;
-            e->bytes.reserve(raw.size() + 10);
-            e->bytes.assign(raw.data(), raw.size());
-            e->bytes.push_back(0x3);
-            e->bytes.push_back(8);
-            e->bytes.append((const char*)&tsv, 8);
-            memcpy(&e->bytes[0], &first, 8);
-            bytes_total += e->bytes.size();
-            fresh.push_back(std::move(e));
+            const size_t at = chunk->bytes.size();
+            chunk->bytes.append(raw.data(), raw.size());
+            chunk->bytes.push_back(0x3);
+            chunk->bytes.push_back(8);
+            chunk->bytes.append((const char*)&tsv, 8);
+            memcpy(&chunk->bytes[at], &first, 8);
+            chunk->recs.push_back(LogChunk::Rec{(uint32_t)at, (uint32_t)(chunk->bytes.size() - at), count, first});
             first += count;
           }
-          std::lock_guard<std::mutex> g(x->db->write_mu_);
-          std::lock_guard<std::mutex> g2(x->db->log_mu_);
-          GpuDB* db = x->db;
-          db->log_bytes_ += bytes_total;
-          for (auto& e : fresh) db->log_.push_back(std::move(e));
-          while (db->log_bytes_ > db->log_cap_bytes_ && db->log_.size() > 1) {
-            db->log_bytes_ -= db->log_.front()->bytes.size();
-            db->log_.pop_front();
-            db->log_base_id_++;
+          chunk->last_seq = first - 1;
+          if (!chunk->recs.empty()) {
+            std::lock_guard<std::mutex> g(x->db->write_mu_);
+            std::lock_guard<std::mutex> g2(x->db->log_mu_);
+            x->db->LogPush(std::move(chunk));
           }
         }
         x->done(n_applied, status == RSP_OK ? Status::OK() : x->db->ToStatus(status));
@@ -487,44 +486,57 @@ rocksdb::SequenceNumber GpuDB::GetLatestSequenceNumber() const { return rsp_late
 // TransactionLogIterator over the update log; tails new writes like RocksDB's WAL iterator
 class GpuDB::LogIter : public rocksdb::TransactionLogIterator {
  public:
-  LogIter(GpuDB* db, uint64_t id) : db_(db), id_(id) { Load(); }
+  LogIter(GpuDB* db, uint64_t chunk_id, size_t idx) : db_(db), id_(chunk_id), idx_(idx) { Load(); }
   bool Valid() override { return cur_ != nullptr; }
-  void Next() override { if (cur_) id_++; Load(); }
+  void Next() override { if (cur_) idx_++; Load(); }
   Status status() override { return Status::OK(); }
   rocksdb::BatchResult GetBatch() override {
     rocksdb::BatchResult r;
-    r.sequence = cur_->first_seq;
-    r.writeBatchPtr.reset(new rocksdb::WriteBatch(cur_->bytes));
+    const LogChunk::Rec& rec = cur_->recs[idx_];
+    r.sequence = rec.first_seq;
+    r.writeBatchPtr.reset(new rocksdb::WriteBatch(std::string(cur_->bytes.data() + rec.off, rec.len)));
     return r;
   }
 
  private:
   void Load() {
     std::lock_guard<std::mutex> g(db_->log_mu_);
-    if (id_ < db_->log_base_id_) id_ = db_->log_base_id_;  // trimmed: first available (a gap, as after WAL TTL)
-    const uint64_t off = id_ - db_->log_base_id_;
-    cur_ = off < db_->log_.size() ? db_->log_[off] : nullptr;
+    if (id_ < db_->log_base_id_) { id_ = db_->log_base_id_; idx_ = 0; }  // trimmed: first available (a gap, as after WAL TTL)
+    for (;;) {
+      const uint64_t off = id_ - db_->log_base_id_;
+      if (off >= db_->log_.size()) { cur_ = nullptr; return; }  // at the tail: a later Next() finds what was appended since
+      cur_ = db_->log_[off];
+      if (idx_ < cur_->recs.size()) return;
+      id_++;
+      idx_ = 0;
+    }
   }
   GpuDB* db_;
-  uint64_t id_;
-  std::shared_ptr<const LogEntry> cur_;
+  uint64_t id_;   // chunk id
+  size_t idx_;    // batch within the chunk
+  std::shared_ptr<const LogChunk> cur_;
 };
 
 Status GpuDB::GetUpdatesSince(rocksdb::SequenceNumber seq, std::unique_ptr<rocksdb::TransactionLogIterator>* iter) {
   iter->reset();
   if (seq > GetLatestSequenceNumber()) return Status::NotFound("Requested sequence not yet written in the db");
   uint64_t id;
+  size_t idx = 0;
   {
     std::lock_guard<std::mutex> g(log_mu_);
-    // first entry whose last sequence >= seq
+    // first chunk whose last sequence >= seq, then the first batch in it whose last sequence >= seq
     size_t lo = 0, hi = log_.size();
     while (lo < hi) {
       const size_t m = (lo + hi) / 2;
-      if (log_[m]->first_seq + log_[m]->count - 1 < seq) lo = m + 1; else hi = m;
+      if (log_[m]->last_seq < seq) lo = m + 1; else hi = m;
     }
     id = log_base_id_ + lo;
+    if (lo < log_.size()) {
+      const auto& recs = log_[lo]->recs;
+      while (idx < recs.size() && recs[idx].first_seq + recs[idx].count - 1 < seq) idx++;
+    }
   }
-  iter->reset(new LogIter(this, id));
+  iter->reset(new LogIter(this, id, idx));
   return Status::OK();
 }
 

@@ -97,7 +97,16 @@ class GpuDB : public rocksdb::DB {
   static int MergeTrampoline(void* state, const uint8_t* key, size_t klen, const uint8_t* existing, size_t elen,
                              const uint8_t* operand, size_t olen, void (*out_set)(void*, const uint8_t*, size_t),
                              void* out_ctx);
-  struct LogEntry { rocksdb::SequenceNumber first_seq; uint32_t count; std::string bytes; };
+  // One chunk of the update log = what ONE call appended (a leader's Write: one batch; a follower's response: its <= 50
+  // updates), the batches back to back in one string: three allocations per response instead of two per update — with
+  // a std::string + shared_ptr per update the completion threads spent 170 us per response in malloc / free
+  // (profiles/r02_seams_trace.md) and bounded the whole pull loop.
+  struct LogChunk {
+    struct Rec { uint32_t off, len, count; rocksdb::SequenceNumber first_seq; };
+    rocksdb::SequenceNumber first_seq = 0, last_seq = 0;
+    std::vector<Rec> recs;
+    std::string bytes;
+  };
   class LogIter;
 
   std::string name_;
@@ -108,8 +117,9 @@ class GpuDB : public rocksdb::DB {
   // update log (the WAL's role for GetUpdatesSince): applied batches by sequence number, bounded
   std::mutex write_mu_;  // keeps log order == sequence order
   std::mutex log_mu_;
-  std::deque<std::shared_ptr<const LogEntry>> log_;
-  uint64_t log_base_id_ = 0;  // id of log_[0]
+  std::deque<std::shared_ptr<const LogChunk>> log_;
+  uint64_t log_base_id_ = 0;  // id of log_[0] (chunk ids)
+  void LogPush(std::shared_ptr<const LogChunk> c);  // log_mu_ held
   size_t log_bytes_ = 0;
   size_t log_cap_bytes_ = 256u << 20;
   std::atomic<size_t> value_hint_{0};  // largest value MultiGet has seen (the staging stride of its first pass)

@@ -4,7 +4,8 @@
 // non_blocking_condition_variable.h:113-126).
 //
 // Every worker owns a queue (its own mutex and condition variable); add() deals tasks round-robin and an idle worker
-// steals from the others before it sleeps.  With one shared queue the pull loops of a thousand shards — three short
+// steals from the others before it sleeps; a sleeping worker is woken only when the awake ones are outnumbered by the
+// queued tasks.  With one shared queue the pull loops of a thousand shards — three short
 // tasks per ReplicateResponse — serialise on that queue's mutex long before the workers are busy.
 #pragma once
 #include <atomic>
@@ -35,9 +36,15 @@ class Executor {
       std::lock_guard<std::mutex> g(q.mu);
       q.tasks.push_back(std::move(f));
     }
-    queued_.fetch_add(1, std::memory_order_release);
-    if (q.sleeping.load(std::memory_order_acquire)) q.cv.notify_one();
-    else if (sleepers_.load(std::memory_order_acquire)) WakeOne();  // its owner is busy: let an idle worker steal it
+    const int64_t queued = queued_.fetch_add(1, std::memory_order_acq_rel) + 1;
+    // Wake a worker only when the ones already awake will not get to the task soon: a wake-up and the sleep after it
+    // cost more CPU time than a short task, and the GPU boxes cap the container's CPU time (profiles/
+    // r02_seams_trace.md).  An awake worker drains its own queue and steals from the others before it sleeps.
+    const int64_t awake = (int64_t)n_ - sleepers_.load(std::memory_order_acquire);
+    if (awake <= 0 || queued > 2 * awake) {
+      if (q.sleeping.load(std::memory_order_acquire)) q.cv.notify_one();
+      else WakeOne();
+    }
   }
   // run f on the pool after delay_ms
   void addDelayed(std::function<void()> f, uint64_t delay_ms) {

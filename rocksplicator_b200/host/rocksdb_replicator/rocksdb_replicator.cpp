@@ -181,30 +181,29 @@ void RocksDBReplicator::ReplicatedDB::pullFromUpstream() {
       if (response.has_role && response.role != ReplicaRole::LEADER) incCounter(kReplicatorPullFromNonLeader, 1, db->db_name_);
       if (!response.updates.empty()) {
         // THE HOT LOOP (replicated_db.cpp:369-383: one DbWrapper call per update, in order, stop at the first
-        // failure) as ONE call for the whole response; the rest of this function continues in its completion, on our
-        // executor again (shared_t keeps the updates alive)
+        // failure) as ONE call for the whole response; the rest of this function continues in its completion
+        // (shared_t keeps the updates alive)
         const size_t n_updates = response.updates.size();
-        Executor* ex = db->owner_->executor();
+        // The completion runs on one of the engine's completion threads; what is left of this function — counters, the
+        // wake-up of chained followers, the next pull (an asynchronous call) — is short and never blocks, so it runs
+        // right there instead of hopping to our executor once more (the reference has no such hop either: its loop
+        // continues in the same task, replicated_db.cpp:384-431).
         auto staged_at = std::make_shared<std::atomic<int64_t>>(0);
-        db->db_wrapper_->HandleReplicateResponses(&response.updates, [weak_db, shared_t, n_updates, ex, staged_at](size_t n_applied) {
+        db->db_wrapper_->HandleReplicateResponses(&response.updates, [weak_db, shared_t, n_updates, staged_at](size_t n_applied) {
           int64_t t_done = 0;
           if (shared_t->t_mark) {
             t_done = PullTrace::Now();
             const int64_t st = staged_at->load(std::memory_order_acquire);
             if (st) PullTrace::Get().Add(3, st, t_done);
           }
-          ex->add([weak_db, shared_t, n_updates, n_applied, t_done] {
-            int64_t t_cont = 0;
-            if (t_done) { t_cont = PullTrace::Now(); PullTrace::Get().Add(4, t_done, t_cont); }
-            auto db = weak_db.lock();
-            if (!db || db->removed_.load()) return;
-            db->trace_cont_ = t_cont;
-            const bool failed = n_applied < n_updates;
-            if (failed) incCounter(kReplicatorHandleResponseFailure, 1, db->db_name_);
-            db->pullFromUpstreamNoUpdates_ = 0;
-            db->cond_var_.notifyAll();  // chained followers long-polling on us
-            db->scheduleNextPull(failed);
-          });
+          auto db = weak_db.lock();
+          if (!db || db->removed_.load()) return;
+          db->trace_cont_ = t_done;
+          const bool failed = n_applied < n_updates;
+          if (failed) incCounter(kReplicatorHandleResponseFailure, 1, db->db_name_);
+          db->pullFromUpstreamNoUpdates_ = 0;
+          db->cond_var_.notifyAll();  // chained followers long-polling on us
+          db->scheduleNextPull(failed);
         });
         if (t.t_mark) { const int64_t now = PullTrace::Now(); PullTrace::Get().Add(2, t.t_mark, now); staged_at->store(now, std::memory_order_release); }
         return;

@@ -28,7 +28,7 @@ cfg = bench.SeamCfg(device=0, shards=a.shards, kv_total=a.kv, value_len=64, exec
                     get_threads=a.get_threads, get_secs=a.get_secs, seed=0x5EED0001, first_shard_id=a.base, steady_rounds=a.steady)
 res = bench.SeamResult()
 rc = lib.rsp_seam_bench(C.byref(cfg), C.byref(res))
-out = {n: (list(getattr(res, n)) if n in ("trace_us", "apply_comb", "read_comb") else getattr(res, n)) for n, _ in bench.SeamResult._fields_}
+out = {n: (list(getattr(res, n)) if n in ("trace_us", "apply_comb", "read_comb", "cpu_s") else getattr(res, n)) for n, _ in bench.SeamResult._fields_}
 out["rc"] = rc
 out["env"] = {k: v for k, v in os.environ.items() if k.startswith("RSP_")}
 print(json.dumps(out))
