@@ -38,6 +38,22 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def cpu_quota():
+    """CPUs of time the container may use per second (cgroup v2 cpu.max / v1 cfs quota); None when uncapped.  The GPU
+    boxes show 128 logical CPUs and cap the container at 16: every host-side figure is a figure under that quota."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
 
@@ -188,7 +204,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload, "sample": "%d KV applied (WAL on, default WriteOptions), flush+compact, %.0f s of MultiGet(4096) split per shard" % (r["applied"], r["get_s"])},
             "applies": {"value": r["applies_per_s"], "unit": "applies/s"},
-            "cpu_baseline": {"value": r["lookups_per_s"], "unit": "lookups/s", "cores": r["threads"], "kind": r["kind"],
+            "cpu_baseline": {"value": r["lookups_per_s"], "unit": "lookups/s", "cores": r["threads"], "kind": r["kind"], "cpu_quota": cpu_quota(),
                              "sample": "%d KV over %d shards, %d threads" % (r["applied"], r["shards"], r["threads"]),
                              "applies_per_s": r["applies_per_s"]},
             "e2e": {"value": r["lookups_per_s"], "unit": "lookups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -787,7 +803,10 @@ def main():
                "sample": "%d KV applied over %d shards with default WriteOptions (WAL on), flush+compact, then %.0f s of MultiGet(4096) split per shard; %d threads" % (
                    r["applied"], r["shards"], r["get_s"], r["threads"]),
                "applies_per_s": r["applies_per_s"],
-               "per_core": {"lookups_per_s": r["lookups_per_s"] / max(1, r["threads"]), "applies_per_s": r["applies_per_s"] / max(1, r["threads"])},
+               "cpu_quota": cpu_quota(),
+               "per_core": {"lookups_per_s": r["lookups_per_s"] / max(1.0, min(r["threads"], cpu_quota() or r["threads"])),
+                            "applies_per_s": r["applies_per_s"] / max(1.0, min(r["threads"], cpu_quota() or r["threads"])),
+                            "what": "per CPU of time available: min(threads, the container's CPU quota)"},
                "note": "the reference's options share one LRU block cache per DB among all reader threads; per-core figures are the fair comparison"}
     if rank == 0:
         line = {
@@ -853,6 +872,8 @@ def main():
                           "response_to_next_pull_ms": {"p50": seams_max["mixed_resp_p50_ms"], "p99": seams_max["mixed_resp_p99_ms"]}},
                 "rank0": {k: seams.get(k) for k in ("load_s", "compact_s", "mget_calls", "applied_total", "parity_errors", "status_errors", "engine_launches")}}),
             "cpu_baseline": cpu,
+            "host": {"cpus_visible": ncores, "cpu_quota": cpu_quota(),
+                     "note": "figures through host buffers / the seams are bounded by the container's CPU time"},
             "gpu_launches": int(mg_launches + ap_launches),
             "clocks": clk,
         }

@@ -830,10 +830,11 @@ static void cut_chunks(GroupDesc* groups, size_t ng, Start start, End end, std::
       const u64 base = start(b);
       size_t e = b + 1;  // (a batch beyond the stage cannot reach here: such ticks take the general kernels)
       while (e < last && e - b < FUSED_CHUNK_BATCHES && end(e) - base <= FUSED_STAGE_BYTES) e++;
-      out->push_back(ChunkDesc{(u32)g, (u32)b, (u32)(e - b), ci++});
+      out->push_back(ChunkDesc{(u32)g, (u32)b, (u32)(e - b), ci++, groups[g].shard_ix, 0u, 0u, 0u});
       b = e;
     }
     groups[g].pad = ci;
+    for (size_t k = out->size() - ci; k < out->size(); k++) (*out)[k].group_chunks = ci;
   }
 }
 
@@ -1019,7 +1020,7 @@ static int stage_build(rsp_engine* e, size_t n, const uint32_t* shard_ix, const 
     size_t max_len = 0, max_group = 0;
     for (size_t i = 0; i < n; i++) max_len = std::max<size_t>(max_len, (size_t)(off[i + 1] - off[i]) + trailer);
     for (size_t g = 0; g < ng; g++) max_group = std::max<size_t>(max_group, g_count[g]);
-    sg->fused = e->fused_ticks && max_len <= FUSED_MAX_BATCH_BYTES && (max_group <= 4096 || ng >= 64);
+    sg->fused = e->fused_ticks && max_len <= FUSED_MAX_BATCH_BYTES;
     FusedTick& f = sg->ftick;
     f.blob = t.blob; f.off = (const u64*)(dev + o_foff); f.len = (const u32*)(dev + o_flen); f.ts = nullptr;
     f.groups = t.groups; f.bstat = t.bstat; f.gres = t.gres; f.n_groups = (u32)ng; f.n_batches = (u32)n;
@@ -1177,7 +1178,7 @@ static int apply_many_packed(rsp_engine* e, size_t n, const uint32_t* shard_ix, 
   for (size_t g = 0; g < ng; g++) sg.group_first[g] = groups[g].first_batch;
   sg.group_first[ng] = (u32)n;
   const size_t blob_b = (size_t)off[n];
-  const bool fused = e->fused_ticks && max_len + trailer <= FUSED_MAX_BATCH_BYTES && (max_group <= 4096 || ng >= 64);
+  const bool fused = e->fused_ticks && max_len + trailer <= FUSED_MAX_BATCH_BYTES;
   // device image: [groups][off][ts][need | total][BatchDesc][blob + slack][BatchRes][GroupRes | status]
   // (the fused tick needs neither the descriptors nor the per-batch results: those regions are empty then)
   const size_t o_groups = 0, o_off = align_up(ng * sizeof(GroupDesc), 256), o_ts = o_off + align_up((n + 1) * 8, 256);

@@ -704,11 +704,10 @@ __global__ void __launch_bounds__(TC_THREADS, 8) k_tick_chunks(FusedTick t, Shar
   __shared__ u32 s_tail, s_cnt, s_latch, s_flags;
   const u32 tid = threadIdx.x;
   const ChunkDesc ck = t.chunks[blockIdx.x];
-  const GroupDesc g = t.groups[ck.group];
-  ShardDev* sd = shards + g.shard_ix;
+  ShardDev* sd = shards + ck.shard_ix;
   MtView mt;
   mt.sd = sd; mt.heap = sd->mt_heap; mt.slots = sd->mt_slots; mt.ent_off = sd->mt_ent_off; mt.slot_mask = sd->mt_slot_mask;
-  mt.filter = mt_filter + (size_t)g.shard_ix * MT_FILTER_WORDS;
+  mt.filter = mt_filter + (size_t)ck.shard_ix * MT_FILTER_WORDS;
   const u32 heap_cap = sd->mt_heap_cap, ent_cap = sd->mt_ent_cap;
   const u32 trailer = t.ts ? 10u : 0u;
   if (tid == 0) { s_first_bad = 0xffffffffu; s_first_over = 0xffffffffu; s_first_status = 0; }
@@ -728,7 +727,18 @@ __global__ void __launch_bounds__(TC_THREADS, 8) k_tick_chunks(FusedTick t, Shar
   const u32 n_units = (shift + chunk_bytes + 15u) >> 4;
   for (u32 u = tid; u < n_units; u += TC_THREADS) reinterpret_cast<uint4*>(s_blob)[u] = __ldg(src4 + u);
   const u64 my_ts = (in && t.ts) ? __ldg(t.ts + b0 + tid) : 0ull;
-  // ---- the predecessor's record (thread 0 polls while the others decode)
+  __syncthreads();
+  // ---- decode (count pass) + prefix sums over the well-formed batches
+  Cursor c{s_blob + shift + (u32)(my_off - base), 12, (u32)(my_end - my_off) + trailer, (u32)(my_end - my_off), my_ts};
+  WalkResult w{0u, 0u, 0u};
+  if (in) w = walk_batch(c, [](u32, u32, u32, u32, u32, u32, u32) {});
+  if (in && w.status) atomicMin(&s_first_bad, tid);
+  u32 ops_excl, units_excl, tot_ops, tot_units;
+  block_excl_scan2<TC_THREADS>(w.status ? 0u : w.n_ops, w.status ? 0u : w.units, s_warp, &ops_excl, &units_excl, &tot_ops, &tot_units);
+  const u32 first_bad = s_first_bad;
+  // ---- the predecessor's record, AFTER this chunk's own decode: a chunk that waits has nothing left to do but the
+  // totals, so the chain advances in a few hundred nanoseconds per link (polling before the decode serialised the
+  // decodes of a group: 250 us per 1 M-batch tick instead of the 186 us of the CTA-per-group kernel)
   if (tid == 0) {
     u64 seq; u32 tail, cnt, latch, flags = 0;
     if (ck.index_in_group == 0) {
@@ -756,14 +766,6 @@ __global__ void __launch_bounds__(TC_THREADS, 8) k_tick_chunks(FusedTick t, Shar
     s_seq = seq; s_tail = tail; s_cnt = cnt; s_latch = latch; s_flags = flags;
   }
   __syncthreads();
-  // ---- decode (count pass) + prefix sums over the well-formed batches
-  Cursor c{s_blob + shift + (u32)(my_off - base), 12, (u32)(my_end - my_off) + trailer, (u32)(my_end - my_off), my_ts};
-  WalkResult w{0u, 0u, 0u};
-  if (in) w = walk_batch(c, [](u32, u32, u32, u32, u32, u32, u32) {});
-  if (in && w.status) atomicMin(&s_first_bad, tid);
-  u32 ops_excl, units_excl, tot_ops, tot_units;
-  block_excl_scan2<TC_THREADS>(w.status ? 0u : w.n_ops, w.status ? 0u : w.units, s_warp, &ops_excl, &units_excl, &tot_ops, &tot_units);
-  const u32 first_bad = s_first_bad;
   const u64 seq = s_seq;
   const u32 tail = s_tail, cnt = s_cnt, latch = s_latch, flags_in = s_flags;
   const bool stopped = (flags_in & CHAIN_STOP) != 0;
@@ -813,9 +815,9 @@ __global__ void __launch_bounds__(TC_THREADS, 8) k_tick_chunks(FusedTick t, Shar
   __syncthreads();
   if (tid == 0) {
     const u32 done = atomicAdd(t.group_done + ck.group, 1u);
-    if (done + 1u == g.pad) {  // (GroupDesc.pad: the group's chunk count)
+    if (done + 1u == ck.group_chunks) {
       __threadfence();
-      const u64* rec = t.chain + 4ull * (blockIdx.x - ck.index_in_group + g.pad - 1u);
+      const u64* rec = t.chain + 4ull * (blockIdx.x - ck.index_in_group + ck.group_chunks - 1u);
       const u64 fseq = ld_volatile_u64(rec + 0), w1 = ld_volatile_u64(rec + 1), w2 = ld_volatile_u64(rec + 2);
       const u32 flatch = (u32)w2;
       GroupRes gr;
@@ -827,7 +829,7 @@ __global__ void __launch_bounds__(TC_THREADS, 8) k_tick_chunks(FusedTick t, Shar
         sd->last_seq = fseq;
         sd->mt_tail = (u32)w1;
         sd->mt_count = (u32)(w1 >> 32);
-        fast[g.shard_ix].mt_count = (u32)(w1 >> 32);
+        fast[ck.shard_ix].mt_count = (u32)(w1 >> 32);
         sd->latch = flatch;
         gr.last_seq = fseq; gr.tail = (u32)w1; gr.count = (u32)(w1 >> 32); gr.latch = flatch; gr.pad = 0;
         t.gres[ck.group] = gr;
@@ -843,6 +845,16 @@ void launch_tick_fused(const FusedTick& t, ShardDev* shards, ShardFast* fast, u3
   if (fused_small_shape(t.max_group, t.max_len)) {
     k_tick_fused<64, 16><<<t.n_groups, 64, 0, s>>>(t, shards, fast, mt_filter);
   } else {
+    // Long groups: a CTA per group (k_tick_fused at 128 threads, the chunks of a group one after the other) when the
+    // groups alone fill the machine, a CTA per chunk (k_tick_chunks) when they do not — measured on 1024 groups x 1000
+    // batches: 198 us per group vs 233 us per chunk (the chain of a group costs more than the tail of one wave,
+    // profiles/r02_tick_ab.md); a tick of a few very long groups has no other source of parallelism than its chunks.
+    static const int force = [] { const char* v = getenv("RSP_TICK_CHUNKS"); return v ? (atoi(v) ? 1 : 0) : -1; }();
+    const bool per_group = force < 0 ? t.n_groups >= 4u * 148u : force == 0;
+    if (per_group) {
+      k_tick_fused<128, 8><<<t.n_groups, 128, 0, s>>>(t, shards, fast, mt_filter);
+      return;
+    }
     // (chain records and the per-group counters sit next to each other: one clear)
     cudaMemsetAsync(t.chain, 0, (size_t)t.n_chunks * 32 + (size_t)t.n_groups * 4, s);
     k_tick_chunks<<<t.n_chunks, TC_THREADS, 0, s>>>(t, shards, fast, mt_filter);

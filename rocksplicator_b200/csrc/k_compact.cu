@@ -399,7 +399,10 @@ __global__ void __launch_bounds__(1024) k_compact_size(const CompactJob* jobs) {
     const EntView e0 = view_item(j, it[i]);
     u32 g_end = i + 1;  // exclusive end of the group
     while (g_end < n && same_key(j, it[i], it[g_end])) g_end++;
-    for (u32 k = i; k < g_end; k++) j.keep_units[k] = 0;
+    for (u32 k = i; k < g_end; k++) { j.keep_units[k] = 0; j.out_ord[k] = 0; }
+    // the head's shape for the pass below (which would otherwise read the entry header from the heap again: a second
+    // random sector per item); out_pos / out_ord get their real contents after that pass
+    if (e0.klen <= 0xffffu && e0.vlen <= 0xffffu) { j.out_pos[i] = e0.klen | (e0.vlen << 16); j.out_ord[i] = 0x100u | e0.type; }
     if (e0.type == kTypeValue) {
       j.keep_units[i] = entry_units(e0.type, e0.klen, e0.vlen, false) | KEEP_HEAD;
     } else if (e0.type != kTypeMerge) {  // Delete / SingleDelete
@@ -465,11 +468,19 @@ __global__ void __launch_bounds__(1024) k_compact_size(const CompactJob* jobs) {
       su += u; sc++; mn = min(mn, u); mx = max(mx, u); if (ku & KEEP_HEAD) sk++;
       // entry shape as it will be written (folded merges become 8-byte Puts / Merges)
       const u32 mode = ku >> KEEP_MODE_SHIFT;
-      const EntView x = view_item(j, it[i]);
-      const u32 type = (mode == MODE_PUT_IMM || mode == MODE_PUT_BYTES) ? (u32)kTypeValue : (mode == MODE_MERGE_IMM ? (u32)kTypeMerge : x.type);
-      const u32 vlen = (mode == MODE_PUT_IMM || mode == MODE_MERGE_IMM) ? 8u : x.vlen;
-      if (type != kTypeValue || x.klen > 0xffffu || vlen > 0xffffu) np++;
-      const u32 kv = (x.klen & 0xffffu) | (vlen << 16);
+      u32 x_type, x_klen, x_vlen;
+      const u32 cached = j.out_ord[i];
+      if (cached & 0x100u) {
+        const u32 kvc = j.out_pos[i];
+        x_type = cached & 0xffu; x_klen = kvc & 0xffffu; x_vlen = kvc >> 16;
+      } else {
+        const EntView x = view_item(j, it[i]);
+        x_type = x.type; x_klen = x.klen; x_vlen = x.vlen;
+      }
+      const u32 type = (mode == MODE_PUT_IMM || mode == MODE_PUT_BYTES) ? (u32)kTypeValue : (mode == MODE_MERGE_IMM ? (u32)kTypeMerge : x_type);
+      const u32 vlen = (mode == MODE_PUT_IMM || mode == MODE_MERGE_IMM) ? 8u : x_vlen;
+      if (type != kTypeValue || x_klen > 0xffffu || vlen > 0xffffu) np++;
+      const u32 kv = (x_klen & 0xffffu) | (vlen << 16);
       kvmin = min(kvmin, kv); kvmax = max(kvmax, kv);
     }
   }
@@ -498,8 +509,21 @@ __global__ void __launch_bounds__(1024) k_compact_size(const CompactJob* jobs) {
   }
 }
 
+// several loads in flight before the first store (the kernel is latency-bound: one entry per thread)
 __device__ __forceinline__ void copy_units(u8* dst, const u8* src, u32 units) {
-  for (u32 u = 0; u < units; u++) reinterpret_cast<uint4*>(dst)[u] = reinterpret_cast<const uint4*>(src)[u];
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  u32 u = 0;
+  for (; u + 4 <= units; u += 4) {
+    const uint4 a = s[u], b = s[u + 1], c = s[u + 2], e = s[u + 3];
+    d[u] = a; d[u + 1] = b; d[u + 2] = c; d[u + 3] = e;
+  }
+  if (u + 2 <= units) {
+    const uint4 a = s[u], b = s[u + 1];
+    d[u] = a; d[u + 1] = b;
+    u += 2;
+  }
+  if (u < units) d[u] = s[u];
 }
 
 __global__ void __launch_bounds__(256) k_compact_write(const CompactJob* jobs) {
@@ -519,12 +543,13 @@ __global__ void __launch_bounds__(256) k_compact_write(const CompactJob* jobs) {
   if (mode == MODE_PUT_IMM || mode == MODE_MERGE_IMM) vlen = 8;
   const u64 st = (x.seqtype & ~0xffull) | type;
   *reinterpret_cast<uint4*>(d) = make_uint4((u32)st, (u32)(st >> 32), x.klen, vlen);
-  copy_units(d + 16, reinterpret_cast<const u8*>(x.key), ku_key);
   if (mode == MODE_PUT_IMM || mode == MODE_MERGE_IMM) {
+    copy_units(d + 16, reinterpret_cast<const u8*>(x.key), ku_key);
     const u64 v = j.fold_val[i];
     *reinterpret_cast<uint4*>(d + 16u + 16u * ku_key) = make_uint4((u32)v, (u32)(v >> 32), 0u, 0u);
   } else {
-    copy_units(d + 16u + 16u * ku_key, x.val, units_of(x.vlen));
+    // key and value units follow each other in a memtable entry as in a run entry: one copy
+    copy_units(d + 16, reinterpret_cast<const u8*>(x.key), ku_key + units_of(x.vlen));
   }
   j.out_ent_off[ord] = pos;
   if (ord % RSP_BLOCK_ENTRIES == 0) j.out_blk_pfx[ord / RSP_BLOCK_ENTRIES] = j.sorted[i].prefix;

@@ -83,7 +83,10 @@ struct ChunkDesc {
   u32 group;
   u32 first_batch;     // staged position of the chunk's first batch
   u32 n_batches;
-  u32 index_in_group;  // the chunks of a group are consecutive; GroupDesc.pad holds their number
+  u32 index_in_group;  // the chunks of a group are consecutive
+  u32 shard_ix;        // (the group's, so that a chunk's CTA reaches its shard with one dependent load less)
+  u32 group_chunks;    // chunks of its group
+  u32 pad0, pad1;
 };
 constexpr u32 FUSED_CHUNK_BATCHES = 128;
 constexpr u32 FUSED_STAGE_BYTES = 16384;
