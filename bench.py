@@ -808,6 +808,8 @@ def main():
                             "applies_per_s": r["applies_per_s"] / max(1.0, min(r["threads"], cpu_quota() or r["threads"])),
                             "what": "per CPU of time available: min(threads, the container's CPU quota)"},
                "note": "the reference's options share one LRU block cache per DB among all reader threads; per-core figures are the fair comparison"}
+    # (collectives are issued by every rank: none inside the rank-0 block below)
+    big_applies_all = sum_over_ranks(big["batches_per_tick"] * big["ticks"]) if big else 0.0
     if rank == 0:
         line = {
             "metric": "multiget_lookups_per_s", "value": lookups_per_s, "unit": "lookups/s", "n_gpus": world,
@@ -819,7 +821,7 @@ def main():
             "applies": {"value": applies_per_s, "unit": "applies/s", "ms_per_tick": ap_total_ms / max(K, 1),
                         "kernel_ms_last_tick": ap_kernel_ms, "batches_per_tick": T,
                         "what": "device-resident: the ticks are pre-staged device images (rsp_stage_build, H2D outside the timed region); the K ticks are launched back to back, statuses read back and folded, in order, inside the timed region",
-                        "large_ticks": (None if not big else dict(big, applies_per_s=sum_over_ranks(big["batches_per_tick"] * big["ticks"]) / (big["ms_per_tick"] * big["ticks"] * 1e-3),
+                        "large_ticks": (None if not big else dict(big, applies_per_s=big_applies_all / (big["ms_per_tick"] * big["ticks"] * 1e-3),
                                                                   hbm_frac_of_peak=A_PUT * big["batches_per_tick"] / (big["kernel_ms_per_tick"] * 1e-3) / 1e9 / peak)),
                         "hbm_frac_of_peak": (A_PUT * T / (ap_kernel_ms * 1e-3) / 1e9 / peak) if ap_kernel_ms and ap_kernel_ms > 0 else None,
                         "e2e": {"value": tot_applies / ap_e2e_s, "unit": "applies/s", "h2d_bytes_per_step": int(ticks[0][1].size + 10 * T), "d2h_bytes_per_step": 4 * T + 24 * S}},

@@ -31,3 +31,19 @@ def test_default_arm_fails_loudly_without_gpu():
                        text=True, timeout=300, cwd=ROOT)
     assert p.returncode != 0
     assert "no CUDA device" in (p.stderr + p.stdout)
+
+
+def test_no_collective_inside_the_rank0_block():
+    """every rank must issue every collective: a sum_over_ranks / max_over_ranks call inside the block only rank 0 runs
+    hangs the job at N > 1 until NCCL's watchdog aborts it (r02 call 17: the N = 2 line was printed after 600 s)"""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read().splitlines()
+    start = next(i for i, l in enumerate(src) if re.match(r"\s+if rank == 0:\s*$", l) and "line = {" in src[i + 1])
+    indent = len(src[start]) - len(src[start].lstrip())
+    block = []
+    for l in src[start + 1:]:
+        if l.strip() and len(l) - len(l.lstrip()) <= indent:
+            break
+        block.append(l)
+    assert block and not any("_over_ranks(" in l or "barrier()" in l for l in block)

@@ -31,3 +31,21 @@ def test_host_gpu_backed(host_tests):
     if os.environ.get("RSP_TEST_EMUL_LIB"):  # tests/test_emul_cpu.py: the same binary linked against the emulation
         host_tests = os.path.join(os.path.dirname(os.environ["RSP_TEST_EMUL_LIB"]), "host_tests_emul")
     _run(host_tests, "gpu-only", 600)
+
+
+def test_stager_stress(tmp_path):
+    """csrc/stager.h alone (std only): 64 callers, two classes, sync + async completions, every result checked; once
+    more under ThreadSanitizer when the toolchain has it"""
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "stager_stress.cpp")
+    cxx = os.environ.get("CXX", "g++")
+    exe = str(tmp_path / "stager_stress")
+    subprocess.check_call([cxx, "-std=c++17", "-O2", "-pthread", src, "-o", exe])
+    p = subprocess.run([exe, "64", "800"], capture_output=True, text=True, timeout=300)
+    print(p.stdout, p.stderr)
+    assert p.returncode == 0 and "wrong 0" in p.stdout
+    exe_t = str(tmp_path / "stager_stress_tsan")
+    if subprocess.call([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", src, "-o", exe_t],
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 0:
+        p = subprocess.run([exe_t, "16", "300"], capture_output=True, text=True, timeout=600)
+        print(p.stdout, p.stderr[-3000:])
+        assert p.returncode == 0 and "wrong 0" in p.stdout and "ThreadSanitizer" not in p.stderr
