@@ -295,6 +295,9 @@ struct rsp_engine {
   std::unordered_map<std::string, rsp_shard*> by_name;
   PinBuf pin_in, pin_out, pin_up, pin_totals;
   DevBuf dev_tick, dev_q, dev_pending, dev_ops, dev_up;
+  cudaEvent_t pending_ev = nullptr;  // the last device-form MultiGet launch (the pending list is per engine)
+  bool pending_ev_recorded = false;
+  cudaStream_t pending_last_stream = nullptr;
   cudaEvent_t up_ev = nullptr;  // the last batched descriptor upload (its staging buffers are reused)
   bool up_ev_recorded = false;
   std::vector<u32> gid_scratch;
@@ -1425,11 +1428,24 @@ static int host_fold_get(rsp_engine* e, rsp_shard* s, const uint8_t* key, size_t
 // reads
 // ------------------------------------------------------------------------------------------------
 // pending-list scratch of the 16-byte-key kernel: [2 counters][n indices]; the counters alternate per launch
-static void set_pending(rsp_engine* e, GetArgs& a, size_t n) {
+// ONE list per engine: a launch that would share it with a launch still running on ANOTHER stream waits for that one
+// (launches on one stream are ordered anyway; ADVICE r01: two device-form launches on different streams wrote the
+// same list).
+static void pending_order(rsp_engine* e, cudaStream_t stream) {
+  if (e->pending_ev_recorded && e->pending_last_stream != stream) CUDA_OK(cudaStreamWaitEvent(stream, e->pending_ev, 0));
+}
+static void pending_mark(rsp_engine* e, cudaStream_t stream) {
+  CUDA_OK(cudaEventRecord(e->pending_ev, stream));
+  e->pending_ev_recorded = true;
+  e->pending_last_stream = stream;
+}
+static void set_pending(rsp_engine* e, GetArgs& a, size_t n, cudaStream_t stream) {
+  pending_order(e, stream);
   if ((n + 8) * 4 > e->pending_cap) {
+    if (e->pending_ev_recorded) CUDA_OK(cudaEventSynchronize(e->pending_ev));  // the old list may still be read
     e->pending_cap = std::max<size_t>((n + 8) * 4, e->pending_cap * 2);
     u32* p = (u32*)e->dev_pending.get(e->pending_cap);
-    CUDA_OK(cudaMemset(p, 0, 16));
+    CUDA_OK(cudaMemsetAsync(p, 0, 16, stream));
     e->mg_parity = 0;
   }
   a.n_special = (u32*)e->dev_pending.p;
@@ -1456,6 +1472,10 @@ static int multi_get_locked(rsp_engine* e, size_t n, const uint32_t* shard_ix, c
   const size_t n_chunks = piped ? (n + CH - 1) / CH : 1;
   // scratch: [n_special][pad][2 counters per chunk][pending indices]
   const size_t scratch_u32 = 4 + 2 * n_chunks + n + 16;
+  if (e->pending_ev_recorded) {  // a device-form launch on a caller's stream may still use the list: this call is
+    CUDA_OK(cudaEventSynchronize(e->pending_ev));  // synchronous anyway
+    e->pending_ev_recorded = false;
+  }
   if (scratch_u32 * 4 > e->pending_cap) {
     e->pending_cap = std::max(scratch_u32 * 4, e->pending_cap * 2);
     e->dev_pending.get(e->pending_cap);
@@ -2034,6 +2054,7 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   CUDA_OK(cudaEventCreate(&e->ev0));
   CUDA_OK(cudaEventCreate(&e->ev1));
   CUDA_OK(cudaEventCreateWithFlags(&e->up_ev, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&e->pending_ev, cudaEventDisableTiming));
   CUDA_OK(cudaMalloc(&e->d_shards, sizeof(ShardDev) * e->cfg.max_shards));
   CUDA_OK(cudaMemset(e->d_shards, 0, sizeof(ShardDev) * e->cfg.max_shards));
   {
@@ -2087,7 +2108,7 @@ void rsp_engine_destroy(rsp_engine* e) {
   e->pin_in.destroy(); e->pin_out.destroy(); e->pin_up.destroy(); e->pin_totals.destroy(); e->dev_up.destroy(); e->dev_tick.destroy(); e->dev_q.destroy(); e->dev_pending.destroy(); e->dev_ops.destroy();
   cudaFree(e->d_shards);
   cudaFree(e->d_fast);
-  cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->up_ev);
+  cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->up_ev); cudaEventDestroy(e->pending_ev);
   for (int k = 0; k < 8; k++) cudaEventDestroy(e->reader_ev[k]);
   cudaEventDestroy(e->mut_ev);
   for (int k = 0; k < 3; k++) { cudaStreamDestroy(e->cs[k]); cudaEventDestroy(e->cs_done[k]); }
@@ -2856,13 +2877,14 @@ int rsp_multi_get_device(rsp_engine* e, size_t n, const uint32_t* d_shard_ix, co
   a.vals = d_vals; a.val_stride = val_stride; a.vlen = d_vlen; a.st = d_st; a.n = (u32)n;
   {
     std::lock_guard<std::mutex> g(e->mu);  // the pending-list scratch is per engine
-    set_pending(e, a, n);
-    a.max_shards = e->cfg.max_shards;
     cudaStream_t rs = stream ? (cudaStream_t)stream : e->st;
+    set_pending(e, a, n, rs);
+    a.max_shards = e->cfg.max_shards;
     reader_begin(e, rs);
     a.multirun = e->n_multirun.load() ? 1u : 0u;
     launch_multi_get(a, rs);
     reader_end(e, rs);
+    pending_mark(e, rs);
   }
   e->launches += 2;
   return cudaPeekAtLastError() == cudaSuccess ? RSP_OK : RSP_IO_ERROR;

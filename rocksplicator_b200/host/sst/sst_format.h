@@ -83,7 +83,8 @@ inline uint32_t MaskCrc(uint32_t crc) { return ((crc >> 15) | (crc << 17)) + 0xa
 inline bool SnappyUncompress(const uint8_t* p, size_t n, std::string* out) {
   const uint8_t* lim = p + n;
   uint64_t ulen;
-  if (!GetVarint64(&p, lim, &ulen) || ulen > (1ull << 32)) return false;
+  // (an untrusted length: a block never inflates beyond a few hundred times its stored size, and blocks are KBs)
+  if (!GetVarint64(&p, lim, &ulen) || ulen > (64ull << 20) || ulen > 256ull * n + 4096) return false;
   out->clear();
   out->reserve((size_t)ulen);
   while (p < lim) {
@@ -136,7 +137,8 @@ struct BlockHandle {
 
 // read the block at `h` (verifying its checksum when present) into its uncompressed contents
 inline bool ReadBlock(const std::string& file, const BlockHandle& h, bool verify, std::string* contents, std::string* err) {
-  if (h.offset + h.size + 5 > file.size()) { *err = "block handle out of range"; return false; }
+  // (the handle's varint64s come from the file: no sums that can wrap)
+  if (h.offset > file.size() || h.size > file.size() - h.offset || file.size() - h.offset - h.size < 5) { *err = "block handle out of range"; return false; }
   const uint8_t* p = (const uint8_t*)file.data() + h.offset;
   const uint8_t type = p[h.size];
   if (verify) {
