@@ -243,6 +243,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # the timed regions run Python between engine calls: a generational collection over the setup's large object graph
+    # inside ten timed ticks is a 70-80 ms stall (two of the r02 runs show exactly that in applies.e2e)
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc.disable()
     lib = engine.load_library()
     eng = engine.Engine(local_rank, max_shards=max(16384, args.shards))
     stream = torch.cuda.ExternalStream(lib.rsp_engine_stream(eng.h), device=torch.device("cuda", local_rank))

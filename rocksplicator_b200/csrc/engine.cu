@@ -104,9 +104,15 @@ struct Arena {
   std::vector<void*> big;  // allocations larger than a slab get their own cudaMalloc
   size_t in_use = 0;
 
+  // four classes per octave from 4 KB up (5/8, 6/8, 7/8, 8/8 of a power of two: multiples of 256 bytes): a 103 MB run
+  // occupies 112 MB, not 128 — with powers of two alone the config-2 stretch point (> 100 GB resident) ran out of HBM
   static size_t cls(size_t n) {
     size_t c = 256;
     while (c < n) c <<= 1;
+    if (c >= 4096) {
+      for (size_t k = 5; k < 8; k++)
+        if (c / 8 * k >= n) return c / 8 * k;
+    }
     return c;
   }
 #ifdef RSP_EMUL
@@ -2666,11 +2672,23 @@ static int all_shards(rsp_engine* e, bool full) {
   std::vector<rsp_shard*> v;
   for (rsp_shard* s : e->slots) if (s) v.push_back(s);
   for (rsp_shard* s : v) if (ticks_in_flight(s)) return RSP_BUSY;
-  // bounded batches keep the work buffers modest
-  for (size_t i = 0; i < v.size(); i += 256) {
-    std::vector<rsp_shard*> part(v.begin() + i, v.begin() + std::min(v.size(), i + 256));
-    compact_shards(e, part, full);
+  // bounded batches keep the work buffers modest: <= 256 shards and <= 8 GB of sources (a batch needs about half its
+  // sources again for sort items / scratch, plus its outputs, before the sources are released)
+  std::vector<rsp_shard*> part;
+  u64 part_bytes = 0;
+  auto run_part = [&] {
+    if (!part.empty()) compact_shards(e, part, full);
+    part.clear();
+    part_bytes = 0;
+  };
+  for (rsp_shard* s : v) {
+    u64 b = (u64)s->h.mt_tail * 16;
+    for (auto& r : s->runs) b += r->bytes();
+    if (!part.empty() && (part.size() >= 256 || part_bytes + b > (8ull << 30))) run_part();
+    part.push_back(s);
+    part_bytes += b;
   }
+  run_part();
   return RSP_OK;
 }
 int rsp_flush_all(rsp_engine* e) {

@@ -93,3 +93,53 @@ def zipf_ranks(rng, n_items, theta, size):
 def scatter_ranks(ranks, n_items):
     """spread popularity ranks over the key space (hot keys land on many shards)"""
     return (ranks * np.uint64(2654435761) + np.uint64(12345)) % np.uint64(n_items)
+
+
+# ---- the same generator on a torch device (tools/stretch.py: a billion keys would take numpy minutes of CPU time) ----
+def _t_splitmix64(x):
+    """splitmix64 on int64 torch tensors (two's complement arithmetic wraps; logical shifts are masked)"""
+    import torch
+
+    def lsr(v, s):
+        return (v >> s) & ((1 << (64 - s)) - 1)
+
+    def c(u):  # a uint64 constant as the int64 with the same bits
+        return u - (1 << 64) if u >= (1 << 63) else u
+    x = x + c(0x9E3779B97F4A7C15)
+    z = (x ^ lsr(x, 30)) * c(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * c(0x94D049BB133111EB)
+    return z ^ lsr(z, 31)
+
+
+def torch_single_put_batches(seed, shard, idx, version, ts_ms, vlen=64):
+    """== single_put_batches(keys16(seed, idx), values(seed, shard, idx, version, vlen), ts_ms) for 16-byte keys and
+    vlen < 128, computed on idx's device: (n, 105) uint8 at vlen 64.  shard / idx / ts_ms: int64 tensors."""
+    import torch
+    assert vlen < 128 and vlen % 8 == 0
+    n = idx.numel()
+    L = 12 + 2 + 16 + 1 + vlen + 10
+    dev = idx.device
+    b = torch.zeros((n, L), dtype=torch.uint8, device=dev)
+    b[:, 8] = 1
+    b[:, 12] = 1
+    b[:, 13] = 16
+
+    def be_bytes(v):  # (n,) int64 -> (n, 8) uint8 big-endian
+        return v.view(torch.uint8).reshape(n, 8).flip(1)
+
+    def le_bytes(v):
+        return v.view(torch.uint8).reshape(n, 8)
+    idx = idx.contiguous()
+    b[:, 14:22] = be_bytes(idx)
+    b[:, 22:30] = be_bytes(_t_splitmix64(idx ^ seed).contiguous())
+    b[:, 30] = vlen
+    s = _t_splitmix64(((shard << 40) ^ (idx << 8) ^ version) ^ seed)
+    at = 31
+    for _ in range(vlen // 8):
+        s = _t_splitmix64(s)
+        b[:, at:at + 8] = le_bytes(s.contiguous())
+        at += 8
+    b[:, at] = 3
+    b[:, at + 1] = 8
+    b[:, at + 2:at + 10] = le_bytes(ts_ms.contiguous())
+    return b

@@ -11,7 +11,7 @@ import torch
 from rocksplicator_b200 import engine, synth
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--kv", type=int, default=1_100_000_000)
+ap.add_argument("--kv", type=int, default=1_000_000_000)
 ap.add_argument("--shards", type=int, default=1024)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
@@ -23,16 +23,28 @@ shards = [eng.open_shard("segment%05d" % i, write_buffer_bytes=32 << 20) for i i
 six_of = np.array([s.index for s in shards], dtype=np.uint32)
 seed = synth.SEED_DATA
 t0 = time.perf_counter()
-CH = 1 << 22
+CH = 1 << 23
+# the wire batches are generated on the GPU (synth.torch_single_put_batches == the numpy generator, bit for bit) in
+# shard-grouped order, copied to pinned memory and handed to the packed tick: the host only moves bytes
+dev = torch.device("cuda", 0)
+pin_b = torch.empty((CH, 105), dtype=torch.uint8).pin_memory()
+pin_i = torch.empty(CH, dtype=torch.int64).pin_memory()
+six_t = torch.from_numpy(six_of.astype(np.int64)).to(dev)
 for lo in range(0, NKV, CH):
-    idx = np.arange(lo, min(NKV, lo + CH), dtype=np.uint64)
-    sh = (idx % np.uint64(S)).astype(np.int64)
-    b = synth.single_put_batches(synth.keys16(seed, idx), synth.values(seed, sh, idx, 0), 1000 + idx)
-    order = np.argsort(sh, kind="stable")  # grouped by shard: the packed / fused tick
-    off = np.arange(idx.size + 1, dtype=np.uint64) * np.uint64(b.shape[1])
-    st = eng.apply_packed(six_of[sh[order]], np.ascontiguousarray(b[order]).reshape(-1), off, 1000 + idx[order])
+    n = min(NKV, lo + CH) - lo
+    idx = torch.arange(lo, lo + n, dtype=torch.int64, device=dev)
+    sh = idx % S
+    sh_sorted, order = torch.sort(sh, stable=True)  # grouped by shard: the packed / fused tick
+    idx_o = idx[order]
+    b = synth.torch_single_put_batches(seed, sh_sorted, idx_o, 0, idx_o + 1000)
+    pin_b[:n].copy_(b, non_blocking=True)
+    pin_i[:n].copy_(idx_o, non_blocking=True)
+    six_o = six_t[sh_sorted].to(torch.int32).cpu().numpy().astype(np.uint32)
+    torch.cuda.synchronize()
+    off = np.arange(n + 1, dtype=np.uint64) * np.uint64(105)
+    st = eng.apply_packed(six_o, pin_b[:n].numpy().reshape(-1), off, (pin_i[:n].numpy() + 1000).astype(np.uint64))
     assert not st.any(), "load failed"
-    if (lo // CH) % 32 == 0:
+    if (lo // CH) % 16 == 0:
         print("loaded %d M in %.0f s" % (lo >> 20, time.perf_counter() - t0), file=sys.stderr, flush=True)
 t_load = time.perf_counter() - t0
 t1 = time.perf_counter()
