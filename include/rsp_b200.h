@@ -268,6 +268,10 @@ uint32_t rsp_debug_last_pending(rsp_engine* e, uint32_t* first, uint32_t cap);
  * up, ns inside the callbacks, number of callbacks}; zeros before first use */
 void rsp_debug_combiner_stats(rsp_engine* e, int which, uint64_t out[9]);
 
+/* diagnostics: the device arena — out = {bytes handed out, bytes reserved from the device (slabs), number of blocks,
+ * bytes free inside the slabs} */
+void rsp_debug_arena(rsp_engine* e, uint64_t out[4]);
+
 const char* rsp_version(void);
 
 #ifdef __cplusplus

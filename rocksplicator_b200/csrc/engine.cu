@@ -92,91 +92,103 @@ static const char* kMsgText[MSG_COUNT] = {
 };
 
 // ------------------------------------------------------------------------------------------------
-// device arena: power-of-two size classes carved from large slabs
+// device arena: best-fit blocks with splitting and coalescing, carved from large slabs
 // ------------------------------------------------------------------------------------------------
+// Requests are rounded to 256 bytes and served from the smallest free block that fits (the remainder stays free); a
+// released block merges with its free neighbours inside its slab.  (r01 / early r02: power-of-two size classes with
+// per-class free lists.  A shard's runs grow from generation to generation, so the classes of the earlier generations
+// filled up with blocks nobody asked for again: the config-2 stretch point had 48 GB parked in free lists beside 125 GB
+// in use when the device ran out of memory — profiles/r02_stretch.md.)
 struct Arena {
   std::mutex mu;
-  size_t slab_bytes;
+  size_t slab_bytes = 0;
   std::vector<void*> slabs;
-  u8* cur = nullptr;
-  size_t cur_left = 0;
-  std::map<size_t, std::vector<void*>> free_lists;
-  std::vector<void*> big;  // allocations larger than a slab get their own cudaMalloc
-  size_t in_use = 0;
+  struct Block { size_t size; u32 slab; bool free; };
+  std::map<uintptr_t, Block> blocks;                 // every block of every slab, by address
+  std::multimap<size_t, uintptr_t> free_by_size;     // the free ones, by size
+  size_t in_use = 0, reserved = 0, free_bytes = 0;
 
-  // four classes per octave from 4 KB up (5/8, 6/8, 7/8, 8/8 of a power of two: multiples of 256 bytes): a 103 MB run
-  // occupies 112 MB, not 128 — with powers of two alone the config-2 stretch point (> 100 GB resident) ran out of HBM
-  static size_t cls(size_t n) {
-    size_t c = 256;
-    while (c < n) c <<= 1;
-    if (c >= 4096) {
-      for (size_t k = 5; k < 8; k++)
-        if (c / 8 * k >= n) return c / 8 * k;
-    }
-    return c;
-  }
+  static size_t round_up(size_t n) { return (std::max<size_t>(n, 1) + 255) & ~(size_t)255; }
 #ifdef RSP_EMUL
   // tests/emul under AddressSanitizer: every request is its own exactly-sized allocation, freed on release, so an
   // access past the requested size or after release is reported instead of landing in a neighbour
   static bool exact() { static const bool on = getenv("RSP_EMUL_EXACT_ALLOC") != nullptr; return on; }
 #endif
+  void drop_free(std::map<uintptr_t, Block>::iterator it) {  // mu held: *it leaves the size index
+    auto r = free_by_size.equal_range(it->second.size);
+    for (auto f = r.first; f != r.second; ++f)
+      if (f->second == it->first) { free_by_size.erase(f); break; }
+    free_bytes -= it->second.size;
+  }
+  void add_free(std::map<uintptr_t, Block>::iterator it) {
+    it->second.free = true;
+    free_by_size.emplace(it->second.size, it->first);
+    free_bytes += it->second.size;
+  }
   void* alloc(size_t n) {
-    if (n == 0) n = 1;
 #ifdef RSP_EMUL
-    if (exact()) { void* p = nullptr; CUDA_OK(cudaMalloc(&p, n)); return p; }
+    if (exact()) { void* p = nullptr; CUDA_OK(cudaMalloc(&p, n ? n : 1)); return p; }
 #endif
-    const size_t c = cls(n);
+    const size_t c = round_up(n);
     std::lock_guard<std::mutex> g(mu);
-    in_use += c;
-    auto& fl = free_lists[c];
-    if (!fl.empty()) {
-      void* p = fl.back();
-      fl.pop_back();
-      return p;
-    }
-    if (c > slab_bytes / 2) {
-      void* p = nullptr;
-      CUDA_OK(cudaMalloc(&p, c));
-      big.push_back(p);
-      return p;
-    }
-    if (cur_left < c) {
-      // the tail of the old slab is abandoned to the free lists in class-sized pieces
-      while (cur_left >= 256) {
-        size_t piece = 256;
-        while (piece * 2 <= cur_left) piece <<= 1;
-        free_lists[piece].push_back(cur);
-        cur += piece;
-        cur_left -= piece;
-      }
+    auto f = free_by_size.lower_bound(c);
+    if (f == free_by_size.end()) {
+      // nothing fits: one more slab (a request beyond the slab size gets a slab of its own size)
+      const size_t sb = std::max(slab_bytes, c);
       void* s = nullptr;
-      CUDA_OK(cudaMalloc(&s, slab_bytes));
+      CUDA_OK(cudaMalloc(&s, sb));
       slabs.push_back(s);
-      cur = (u8*)s;
-      cur_left = slab_bytes;
+      reserved += sb;
+      auto it = blocks.emplace((uintptr_t)s, Block{sb, (u32)(slabs.size() - 1), true}).first;
+      add_free(it);
+      f = free_by_size.lower_bound(c);
     }
-    void* p = cur;
-    cur += c;
-    cur_left -= c;
-    return p;
+    auto it = blocks.find(f->second);
+    drop_free(it);
+    it->second.free = false;
+    if (it->second.size > c) {  // the tail stays free
+      const size_t rest = it->second.size - c;
+      it->second.size = c;
+      auto tail = blocks.emplace(it->first + c, Block{rest, it->second.slab, true}).first;
+      add_free(tail);
+    }
+    in_use += c;
+    return (void*)it->first;
   }
   void release(void* p, size_t n) {
+    (void)n;
     if (!p) return;
 #ifdef RSP_EMUL
     if (exact()) { cudaFree(p); return; }
 #endif
-    if (n == 0) n = 1;
-    const size_t c = cls(n);
     std::lock_guard<std::mutex> g(mu);
-    in_use -= c;
-    free_lists[c].push_back(p);
+    auto it = blocks.find((uintptr_t)p);
+    if (it == blocks.end() || it->second.free) return;  // (not ours / released twice: ignored)
+    in_use -= it->second.size;
+    // merge with the free neighbours of the same slab
+    auto nx = std::next(it);
+    if (nx != blocks.end() && nx->second.free && nx->second.slab == it->second.slab && it->first + it->second.size == nx->first) {
+      drop_free(nx);
+      it->second.size += nx->second.size;
+      blocks.erase(nx);
+    }
+    if (it != blocks.begin()) {
+      auto pv = std::prev(it);
+      if (pv->second.free && pv->second.slab == it->second.slab && pv->first + pv->second.size == it->first) {
+        drop_free(pv);
+        pv->second.size += it->second.size;
+        blocks.erase(it);
+        it = pv;
+      }
+    }
+    add_free(it);
   }
   void destroy() {
     for (void* s : slabs) cudaFree(s);
-    for (void* s : big) cudaFree(s);
     slabs.clear();
-    big.clear();
-    free_lists.clear();
+    blocks.clear();
+    free_by_size.clear();
+    in_use = reserved = free_bytes = 0;
   }
 };
 
@@ -791,28 +803,47 @@ void Compactor::loop() {
       take.swap(pending);
       busy = true;
     }
-    CompactPlan plan;
-    try {
-      {
+    // in parts bounded by source bytes (<= 8 GB, <= 256 shards): a uniform load brings every shard to its merge trigger at
+    // the same time, and one plan over all of them needs their outputs and work buffers at once (the config-2 stretch
+    // point ran out of HBM that way)
+    size_t pos = 0;
+    while (pos < take.size()) {
+      CompactPlan plan;
+      try {
+        {
+          std::lock_guard<std::mutex> g(e->mu);
+          std::vector<rsp_shard*> part;
+          u64 part_bytes = 0;
+          while (pos < take.size() && part.size() < 256) {
+            rsp_shard* s = take[pos];
+            if (std::find(e->slots.begin(), e->slots.end(), s) != e->slots.end()) {
+              u64 b = 0;
+              for (auto& r : s->runs) b += r->bytes();
+              if (!part.empty() && part_bytes + b > (8ull << 30)) break;
+              part.push_back(s);
+              part_bytes += b;
+            }
+            pos++;
+          }
+          plan_jobs(e, part, COMPACT_MERGE, &plan);
+        }
+        if (plan.jobs.empty()) continue;
+        run_jobs(e, &plan, stream, ev0, ev1, &pin_totals);
+        {
+          std::lock_guard<std::mutex> g(e->mu);
+          cudaSetDevice(e->device);
+          install_jobs(e, &plan, COMPACT_MERGE);
+        }
+        release_work(e, &plan);
+      } catch (...) {
+        abi_caught();  // a CUDA failure: recorded; the shards keep their runs, the work buffers go back
+        cudaStreamSynchronize(stream);
         std::lock_guard<std::mutex> g(e->mu);
-        std::vector<rsp_shard*> live;
-        for (rsp_shard* s : take)
-          if (std::find(e->slots.begin(), e->slots.end(), s) != e->slots.end()) live.push_back(s);
-        plan_jobs(e, live, COMPACT_MERGE, &plan);
+        for (JobHost& h : plan.jh)
+          if (h.s && h.index < e->slots.size() && e->slots[h.index] == h.s && h.s->uid == h.uid) { h.s->merging = false; h.s->bg_first_pinned = nullptr; }
+        release_work(e, &plan);
+        plan.outs.clear();
       }
-      if (plan.jobs.empty()) continue;
-      run_jobs(e, &plan, stream, ev0, ev1, &pin_totals);
-      {
-        std::lock_guard<std::mutex> g(e->mu);
-        cudaSetDevice(e->device);
-        install_jobs(e, &plan, COMPACT_MERGE);
-      }
-      release_work(e, &plan);
-    } catch (...) {
-      abi_caught();  // a CUDA failure: recorded; the shards keep their runs
-      std::lock_guard<std::mutex> g(e->mu);
-      for (JobHost& h : plan.jh)
-        if (h.s && h.index < e->slots.size() && e->slots[h.index] == h.s && h.s->uid == h.uid) { h.s->merging = false; h.s->bg_first_pinned = nullptr; }
     }
   }
 }
@@ -2996,6 +3027,16 @@ float rsp_last_kernel_ms(const rsp_engine* e, const char* what) {
   } catch (...) { abi_caught(); return -1.f; }
 }
 uint64_t rsp_kernel_launches(const rsp_engine* e) { return e->launches.load(); }
+
+void rsp_debug_arena(rsp_engine* e, uint64_t out[4]) {
+  for (int i = 0; i < 4; i++) out[i] = 0;
+  if (!e) return;
+  std::lock_guard<std::mutex> g(e->arena.mu);
+  out[0] = e->arena.in_use;       // bytes handed out (rounded to 256)
+  out[1] = e->arena.reserved;     // bytes reserved from the device (slabs)
+  out[2] = e->arena.blocks.size();  // blocks, free and used
+  out[3] = e->arena.free_bytes;   // free inside the slabs
+}
 
 void rsp_debug_combiner_stats(rsp_engine* e, int which, uint64_t out[9]) {
   for (int i = 0; i < 9; i++) out[i] = 0;

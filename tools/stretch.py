@@ -18,8 +18,8 @@ ap.add_argument("--warmup", type=int, default=3)
 args = ap.parse_args()
 S, NKV, K, W, Q = args.shards, args.kv, args.steps, args.warmup, 2048 * 4096
 lib = engine.load_library()
-eng = engine.Engine(0, max_shards=max(16384, S), arena_bytes=4 << 30)
-shards = [eng.open_shard("segment%05d" % i, write_buffer_bytes=32 << 20) for i in range(S)]
+eng = engine.Engine(0, max_shards=max(2048, S))  # (default 1 GiB arena slabs: near the HBM limit a large slab is what fails first)
+shards = [eng.open_shard("segment%05d" % i, write_buffer_bytes=16 << 20) for i in range(S)]
 six_of = np.array([s.index for s in shards], dtype=np.uint32)
 seed = synth.SEED_DATA
 t0 = time.perf_counter()
@@ -47,8 +47,21 @@ for lo in range(0, NKV, CH):
     if (lo // CH) % 16 == 0:
         print("loaded %d M in %.0f s" % (lo >> 20, time.perf_counter() - t0), file=sys.stderr, flush=True)
 t_load = time.perf_counter() - t0
+def mem_report(tag):
+    a = (C.c_uint64 * 4)()
+    lib.rsp_debug_arena(eng.h, a)
+    free_b, total_b = torch.cuda.mem_get_info()
+    st_ = [s.stats() for s in shards]
+    print("%s: runs %.1f GB in %d runs (max %d per shard), memtables %.1f GB | arena handed out %.1f GB, reserved %.1f GB, %.0f K blocks, free inside %.1f GB | device used %.1f GB (torch %.1f GB)" % (
+        tag, sum(x["run_bytes"] for x in st_) / 1e9, sum(x["n_runs"] for x in st_), max(x["n_runs"] for x in st_), sum(x["memtable_bytes"] for x in st_) / 1e9,
+        a[0] / 1e9, a[1] / 1e9, a[2] / 1e3, a[3] / 1e9, (total_b - free_b) / 1e9, torch.cuda.memory_reserved() / 1e9), file=sys.stderr, flush=True)
+mem_report("after the load")
+del pin_b, b, idx, sh, sh_sorted, order, idx_o
+torch.cuda.empty_cache()
 t1 = time.perf_counter()
-assert eng.compact_all() == 0
+rc_c = eng.compact_all()
+mem_report("after compact_all (rc %d)" % rc_c)
+assert rc_c == 0
 t_compact = time.perf_counter() - t1
 assert sum(s.latest_seq() for s in shards) == NKV
 stats = [s.stats() for s in shards]
