@@ -681,3 +681,61 @@ def test_long_groups_chunked_tick(eng, port_lib, grouped):
         assert shards[j].scan() == oracles[j].scan()
     for s in shards:
         s.close()
+
+
+def test_memtable_filter_across_flush_cycles(eng, port_lib):
+    """The 16-byte-key MultiGet kernels consult a per-shard filter (one bit per inserted key hash) before they probe a
+    memtable, and the flush clears it: a false negative would serve a stale value from a run (or NotFound) for a key whose
+    newest version sits in the memtable.  Several rounds of overwrite-some / insert-some / delete-some WITHOUT flushing,
+    every key of the shard looked up through the fixed-shape entry point after each round, then a flush (answers must
+    not change), single-run and two-run shapes, both kernels (k_multi_get16, k_multi_get16m)."""
+    rnd = random.Random(777)
+    S, N = 3, 3000
+    shards = [new_shard(eng, 0) for _ in range(S)]
+    oracles = [okv.Okv(port_lib) for _ in range(S)]
+    universe = [[bench_key(5, j * 100000 + i) for i in range(N)] for j in range(S)]
+
+    def tick(ops):
+        six, batches, ts = [], [], []
+        for j, wb in ops:
+            six.append(shards[j].index); batches.append(wb.data()); ts.append(len(six))
+        for lo in range(0, len(six), 4096):
+            assert not eng.apply_many(six[lo:lo + 4096], batches[lo:lo + 4096], ts[lo:lo + 4096]).any()
+        for (j, wb), t in zip(ops, ts):
+            assert oracles[j].apply(wb.data(), t) == 0
+
+    def check(tag):
+        for j in range(S):
+            keys = universe[j] + [bench_key(6, i) for i in range(50)]  # (never written: NotFound)
+            n = len(keys)
+            vals = np.zeros((n, 64), dtype=np.uint8)
+            vlen = np.zeros(n, dtype=np.uint32)
+            st = np.full(n, -1, dtype=np.int32)
+            six = np.full(n, shards[j].index, dtype=np.uint32)
+            assert eng.multi_get_fixed(six, np.frombuffer(b"".join(keys), dtype=np.uint8), 16, vals.reshape(-1), 64, vlen, st) == 0
+            want = oracles[j].multi_get(keys)
+            for i, (wst, wv) in enumerate(want):
+                assert int(st[i]) == wst, (tag, j, i, int(st[i]), wst)
+                if wst == 0:
+                    assert vals[i, :vlen[i]].tobytes() == wv, (tag, j, i)
+
+    tick([(j, WriteBatch().put(k, bench_value(5, j, i, 0))) for j in range(S) for i, k in enumerate(universe[j][:N // 2])])
+    assert eng.compact_all() == 0
+    check("compacted")
+    for rnd_no in range(1, 5):
+        ops = []
+        for j in range(S):
+            for i in rnd.sample(range(N), 400):  # overwrites of run keys, first writes of new keys
+                ops.append((j, WriteBatch().put(universe[j][i], bench_value(5, j, i, rnd_no))))
+            for i in rnd.sample(range(N), 60):
+                ops.append((j, WriteBatch().delete(universe[j][i])))
+        tick(ops)
+        check("round %d, memtable" % rnd_no)
+        if rnd_no % 2 == 0:
+            for s in shards:
+                assert s.flush() == 0  # a second run: the multi-run kernel; the filter rows start over
+            check("round %d, flushed" % rnd_no)
+    assert eng.compact_all() == 0
+    check("compacted again")
+    for s in shards:
+        s.close()
