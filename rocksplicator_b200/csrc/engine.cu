@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "../../include/rsp_b200.h"
+#include "arena.h"
 #include "stager.h"
 #include "kernels.h"
 
@@ -92,105 +93,14 @@ static const char* kMsgText[MSG_COUNT] = {
 };
 
 // ------------------------------------------------------------------------------------------------
-// device arena: best-fit blocks with splitting and coalescing, carved from large slabs
+// device arena (arena.h): best-fit blocks with splitting and coalescing over cudaMalloc'ed slabs
 // ------------------------------------------------------------------------------------------------
-// Requests are rounded to 256 bytes and served from the smallest free block that fits (the remainder stays free); a
-// released block merges with its free neighbours inside its slab.  (r01 / early r02: power-of-two size classes with
-// per-class free lists.  A shard's runs grow from generation to generation, so the classes of the earlier generations
-// filled up with blocks nobody asked for again: the config-2 stretch point had 48 GB parked in free lists beside 125 GB
-// in use when the device ran out of memory — profiles/r02_stretch.md.)
-struct Arena {
-  std::mutex mu;
-  size_t slab_bytes = 0;
-  std::vector<void*> slabs;
-  struct Block { size_t size; u32 slab; bool free; };
-  std::map<uintptr_t, Block> blocks;                 // every block of every slab, by address
-  std::multimap<size_t, uintptr_t> free_by_size;     // the free ones, by size
-  size_t in_use = 0, reserved = 0, free_bytes = 0;
-
-  static size_t round_up(size_t n) { return (std::max<size_t>(n, 1) + 255) & ~(size_t)255; }
-#ifdef RSP_EMUL
-  // tests/emul under AddressSanitizer: every request is its own exactly-sized allocation, freed on release, so an
-  // access past the requested size or after release is reported instead of landing in a neighbour
-  static bool exact() { static const bool on = getenv("RSP_EMUL_EXACT_ALLOC") != nullptr; return on; }
-#endif
-  void drop_free(std::map<uintptr_t, Block>::iterator it) {  // mu held: *it leaves the size index
-    auto r = free_by_size.equal_range(it->second.size);
-    for (auto f = r.first; f != r.second; ++f)
-      if (f->second == it->first) { free_by_size.erase(f); break; }
-    free_bytes -= it->second.size;
-  }
-  void add_free(std::map<uintptr_t, Block>::iterator it) {
-    it->second.free = true;
-    free_by_size.emplace(it->second.size, it->first);
-    free_bytes += it->second.size;
-  }
-  void* alloc(size_t n) {
-#ifdef RSP_EMUL
-    if (exact()) { void* p = nullptr; CUDA_OK(cudaMalloc(&p, n ? n : 1)); return p; }
-#endif
-    const size_t c = round_up(n);
-    std::lock_guard<std::mutex> g(mu);
-    auto f = free_by_size.lower_bound(c);
-    if (f == free_by_size.end()) {
-      // nothing fits: one more slab (a request beyond the slab size gets a slab of its own size)
-      const size_t sb = std::max(slab_bytes, c);
-      void* s = nullptr;
-      CUDA_OK(cudaMalloc(&s, sb));
-      slabs.push_back(s);
-      reserved += sb;
-      auto it = blocks.emplace((uintptr_t)s, Block{sb, (u32)(slabs.size() - 1), true}).first;
-      add_free(it);
-      f = free_by_size.lower_bound(c);
-    }
-    auto it = blocks.find(f->second);
-    drop_free(it);
-    it->second.free = false;
-    if (it->second.size > c) {  // the tail stays free
-      const size_t rest = it->second.size - c;
-      it->second.size = c;
-      auto tail = blocks.emplace(it->first + c, Block{rest, it->second.slab, true}).first;
-      add_free(tail);
-    }
-    in_use += c;
-    return (void*)it->first;
-  }
-  void release(void* p, size_t n) {
-    (void)n;
-    if (!p) return;
-#ifdef RSP_EMUL
-    if (exact()) { cudaFree(p); return; }
-#endif
-    std::lock_guard<std::mutex> g(mu);
-    auto it = blocks.find((uintptr_t)p);
-    if (it == blocks.end() || it->second.free) return;  // (not ours / released twice: ignored)
-    in_use -= it->second.size;
-    // merge with the free neighbours of the same slab
-    auto nx = std::next(it);
-    if (nx != blocks.end() && nx->second.free && nx->second.slab == it->second.slab && it->first + it->second.size == nx->first) {
-      drop_free(nx);
-      it->second.size += nx->second.size;
-      blocks.erase(nx);
-    }
-    if (it != blocks.begin()) {
-      auto pv = std::prev(it);
-      if (pv->second.free && pv->second.slab == it->second.slab && pv->first + pv->second.size == it->first) {
-        drop_free(pv);
-        pv->second.size += it->second.size;
-        blocks.erase(it);
-        it = pv;
-      }
-    }
-    add_free(it);
-  }
-  void destroy() {
-    for (void* s : slabs) cudaFree(s);
-    slabs.clear();
-    blocks.clear();
-    free_by_size.clear();
-    in_use = reserved = free_bytes = 0;
-  }
-};
+static void* arena_slab_alloc(size_t n) {
+  void* p = nullptr;
+  CUDA_OK(cudaMalloc(&p, n));
+  return p;
+}
+static void arena_slab_free(void* p) { cudaFree(p); }
 
 // growable device / pinned scratch
 struct DevBuf {
@@ -2076,6 +1986,8 @@ int rsp_engine_create(int device, const rsp_engine_cfg* cfg, rsp_engine** out) {
   if (!e->cfg.l0_compaction_trigger) e->cfg.l0_compaction_trigger = 4;
   if (e->cfg.l0_compaction_trigger > RSP_MAX_RUNS) e->cfg.l0_compaction_trigger = RSP_MAX_RUNS;
   e->arena.slab_bytes = e->cfg.arena_bytes;
+  e->arena.slab_alloc = arena_slab_alloc;
+  e->arena.slab_free = arena_slab_free;
   // measured on the B200 host (128 cores): 2 staging threads 29 M applies/s, 1: 27, 8: 19 (spawn cost wins)
   e->stage_threads = 2;
   if (const char* t = getenv("RSP_STAGE_THREADS")) e->stage_threads = (size_t)std::max(1, atoi(t));

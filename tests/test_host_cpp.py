@@ -49,3 +49,17 @@ def test_stager_stress(tmp_path):
         p = subprocess.run([exe_t, "16", "300"], capture_output=True, text=True, timeout=600)
         print(p.stdout, p.stderr[-3000:])
         assert p.returncode == 0 and "wrong 0" in p.stdout and "ThreadSanitizer" not in p.stderr
+
+
+def test_arena_allocator(tmp_path):
+    """csrc/arena.h over malloc: 60 000 random allocations / releases, contents and invariants checked (no overlap, slabs
+    tiled exactly, free neighbours coalesced, a whole slab served again after everything was released)"""
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "arena_test.cpp")
+    cxx = os.environ.get("CXX", "g++")
+    exe = str(tmp_path / "arena_test")
+    flags = ["-std=c++17", "-O1", "-g", "-pthread"]
+    if subprocess.call([cxx] + flags + ["-fsanitize=address", src, "-o", exe], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) != 0:
+        subprocess.check_call([cxx] + flags + [src, "-o", exe])
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(p.stdout, p.stderr[-2000:])
+    assert p.returncode == 0 and "bad 0" in p.stdout
