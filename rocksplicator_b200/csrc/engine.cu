@@ -659,7 +659,13 @@ static void compact_shards(rsp_engine* e, const std::vector<rsp_shard*>& shards,
   plan_jobs(e, shards, mode, &plan);
   if (plan.jobs.empty()) return;
   wait_readers(e);
-  run_jobs(e, &plan, e->st, e->ev0, e->ev1, &e->pin_totals);
+  try {
+    run_jobs(e, &plan, e->st, e->ev0, e->ev1, &e->pin_totals);
+  } catch (...) {  // (out of device memory, typically): nothing was installed; the work buffers and partial outputs go back
+    cudaStreamSynchronize(e->st);
+    release_work(e, &plan);
+    throw;
+  }
   install_jobs(e, &plan, mode);
   release_work(e, &plan);
 }
@@ -669,7 +675,13 @@ static std::shared_ptr<Run> snapshot_memtable(rsp_engine* e, rsp_shard* s) {
   CompactPlan plan;
   plan_jobs(e, {s}, COMPACT_SNAPSHOT, &plan);
   if (plan.jobs.empty()) return nullptr;
-  run_jobs(e, &plan, e->st, e->ev0, e->ev1, &e->pin_totals);
+  try {
+    run_jobs(e, &plan, e->st, e->ev0, e->ev1, &e->pin_totals);
+  } catch (...) {
+    cudaStreamSynchronize(e->st);
+    release_work(e, &plan);
+    throw;
+  }
   release_work(e, &plan);
   s->stats.compaction_bytes_read += (u64)s->h.mt_tail * 16;
   return plan.outs[0]->n_ent ? plan.outs[0] : nullptr;
