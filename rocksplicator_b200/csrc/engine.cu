@@ -1701,6 +1701,15 @@ struct ReadCombiner {
   std::unique_ptr<Stager> stager;
 
   void run(const Stager::BatchInfo& info) {
+    try {
+      run_batch(info);
+    } catch (...) {  // (the dispatcher thread must survive: the callers of this batch get an IO error)
+      const int rc = abi_caught();
+      i32* stp = reinterpret_cast<i32*>(st[info.buf].pin + o_st);
+      for (size_t i = 0; i < info.n_items; i++) stp[i] = rc;
+    }
+  }
+  void run_batch(const Stager::BatchInfo& info) {
     ReadStage& S = st[info.buf];
     const size_t n = info.n_items;
     const u32 stride = info.klass;
@@ -1842,11 +1851,16 @@ struct ApplyCombiner {
     int32_t* stv = reinterpret_cast<int32_t*>(S.pin + o_st);
     memset(stv, 0, n * 4);
     int rc;
-    {
+    try {
       std::lock_guard<std::mutex> g(e->mu);
       CUDA_OK(cudaSetDevice(e->device));
       rc = apply_many_locked(e, n, reinterpret_cast<const u32*>(S.pin + o_six), S.pin + o_blob, off,
                              info.klass == 0 ? reinterpret_cast<const u64*>(S.pin + o_ts) : nullptr, stv);
+    } catch (...) {
+      // this is the dispatcher thread: an exception that leaves it ends the process.  A failed CUDA call (out of device
+      // memory while making room, typically) fails the batch instead, every caller of it with an IO error.
+      rc = abi_caught();
+      for (size_t i = 0; i < n; i++) stv[i] = rc;
     }
     if (rc == RSP_INVALID_ARGUMENT || rc == RSP_BUSY)
       for (size_t i = 0; i < n; i++) if (stv[i] == 0) stv[i] = rc;
@@ -2292,7 +2306,12 @@ int rsp_apply_many(rsp_engine* e, size_t n, const uint32_t* shard_ix, const uint
   std::lock_guard<std::mutex> g(e->mu);
   CUDA_OK(cudaSetDevice(e->device));
   return apply_many_locked(e, n, shard_ix, blob, off, ts_ms, st_out);
-  } catch (...) { return abi_caught(); }
+  } catch (...) {
+    // (a failed CUDA call — out of device memory while making room, typically: before the tick ran, nothing of it applied)
+    const int rc = abi_caught();
+    if (st_out) for (size_t i = 0; i < n; i++) st_out[i] = rc;
+    return rc;
+  }
 }
 
 int rsp_apply(rsp_shard* s, const uint8_t* batch, size_t len, uint64_t ts_ms, uint64_t* seq_out) {

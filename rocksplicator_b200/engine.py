@@ -305,7 +305,8 @@ class Engine:
         n = len(six)
         st = np.zeros(n, dtype=np.int32)
         ts = None if ts_ms is None else np.ascontiguousarray(ts_ms, dtype=np.uint64)
-        self.lib.rsp_apply_many(self.h, n, _ptr(six), _ptr(blob), _ptr(off), _ptr(ts), _ptr(st))
+        rc = self.lib.rsp_apply_many(self.h, n, _ptr(six), _ptr(blob), _ptr(off), _ptr(ts), _ptr(st))
+        self.last_rc = rc  # (the call's own status: the first failing batch's, or an engine failure)
         return st
 
     def multi_get(self, shard_ix, keys, stride=256):

@@ -4,6 +4,7 @@
 #include <ucontext.h>
 
 #include <chrono>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -230,14 +231,37 @@ cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= emul_n_devices()) return cu
 cudaError_t cudaGetDevice(int* d) { *d = g_cur_device; return cudaSuccess; }
 cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-cudaError_t cudaMalloc(void** p, size_t n) {
+// RSP_EMUL_DEVICE_BYTES: the emulated device's memory (tests of the out-of-memory paths); pinned host memory does not count
+static std::mutex g_mem_mu;
+static std::map<void*, size_t> g_dev_blocks;
+static size_t g_dev_bytes = 0;
+static size_t emul_device_limit() { static const size_t v = [] { const char* e = getenv("RSP_EMUL_DEVICE_BYTES"); return e ? (size_t)atoll(e) : (size_t)0; }(); return v; }
+static cudaError_t emul_alloc(void** p, size_t n) {
   // exactly n bytes (ASan's red zone starts right behind them), 256-byte aligned like the real allocator
   if (posix_memalign(p, 256, n ? n : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
   if (n <= (16u << 20)) memset(*p, 0xCD, n);  // device memory is not zeroed: make a missing memset visible (big slabs stay lazy)
   return cudaSuccess;
 }
-cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
+cudaError_t cudaMalloc(void** p, size_t n) {
+  if (emul_device_limit()) {
+    std::lock_guard<std::mutex> g(g_mem_mu);
+    if (g_dev_bytes + n > emul_device_limit()) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    const cudaError_t rc = emul_alloc(p, n);
+    if (rc == cudaSuccess) { g_dev_blocks[*p] = n; g_dev_bytes += n; }
+    return rc;
+  }
+  return emul_alloc(p, n);
+}
+cudaError_t cudaFree(void* p) {
+  if (emul_device_limit() && p) {
+    std::lock_guard<std::mutex> g(g_mem_mu);
+    auto it = g_dev_blocks.find(p);
+    if (it != g_dev_blocks.end()) { g_dev_bytes -= it->second; g_dev_blocks.erase(it); }
+  }
+  free(p);
+  return cudaSuccess;
+}
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return emul_alloc(p, n); }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t) {

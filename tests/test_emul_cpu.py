@@ -109,3 +109,15 @@ def test_host_mirror_over_emulated_engine(emul):
         p = subprocess.run([emul[1]] + args, capture_output=True, text=True, timeout=900)
         print(p.stdout[-3000:], p.stderr[-1500:])
         assert p.returncode == 0 and " 0 failures" in p.stdout, p.stdout[-3000:]
+
+
+def test_out_of_device_memory_paths(emul):
+    """tests/emul/oom_probe.py with the emulated device capped at 8 MB: once the device is full applies are refused with an
+    IO error (the flush that would make room cannot allocate), everything acknowledged before stays readable bit for bit,
+    and applies go on after shards were closed.  (No GPU twin: driving a B200 out of memory under gpurun is a strike.)"""
+    env = dict(os.environ)
+    env.update({"RSP_TEST_EMUL_LIB": emul[0], "RSP_EMUL_DEVICE_BYTES": str(8 << 20)})
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "oom_probe.py")], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=900)
+    print(p.stdout[-1500:], p.stderr[-1500:])
+    assert p.returncode == 0 and "OOM PROBE OK" in p.stdout
