@@ -1627,7 +1627,9 @@ struct CompletionPool {
           fs = std::move(q.front());
           q.pop_front();
         }
-        for (auto& f : fs) f();
+        for (auto& f : fs) {
+          try { f(); } catch (...) { abi_caught(); }  // (a caller's completion must not take the pool thread down)
+        }
       }
     });
   }
