@@ -1820,11 +1820,14 @@ static bool read_combined(rsp_engine* e, size_t n, size_t key_bytes, u32 stride,
   if (!all16) S.not16.store(1, std::memory_order_relaxed);
   c->stager->commit(t);
   c->stager->wait(t);
+  struct Release {  // (the caller's result handler may throw: a slice that is never released would park its buffer for good)
+    Stager* s; const Stager::Ticket& t;
+    ~Release() { s->release(t); }
+  } release{c->stager.get(), t};
   const i32* st = reinterpret_cast<const i32*>(S.pin + c->o_st) + t.item0;
   const u32* vlen = reinterpret_cast<const u32*>(S.pin + c->o_vlen) + t.item0;
   const u8* vals = S.pin + c->o_vals + t.item0 * (size_t)stride;
   for (size_t i = 0; i < n; i++) on_res(i, st[i], vals + i * (size_t)stride, vlen[i]);
-  c->stager->release(t);
   return true;
 }
 

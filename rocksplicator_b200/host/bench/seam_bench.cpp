@@ -260,7 +260,7 @@ extern "C" int rsp_seam_bench(const rsp_seam_cfg* cfg_in, rsp_seam_result* res) 
       adbs[i].reset(new admin::ApplicationDB(common::SegmentToDbName("seam", (int)(cfg.first_shard_id + i)), dbs[i],
                                              replicator::ReplicaRole::FOLLOWER,
                                              std::make_unique<replicator::SocketAddress>("127.0.0.1", 1), &repl));
-    if (!wait_seq(per_shard, 600)) status_errors++;
+    if (!wait_seq(per_shard, 180)) status_errors++;
     res->load_s = secs_since(t0);
     res->cpu_s[0] = cpu_seconds() - cpu0;
     res->load_applies_per_s = (double)per_shard * S / res->load_s;
@@ -407,7 +407,7 @@ extern "C" int rsp_seam_bench(const rsp_seam_cfg* cfg_in, rsp_seam_result* res) 
       t0 = Clock::now();
       cpu0 = cpu_seconds();
       leader->SetTargets(target);
-      if (!wait_seq(target, 600)) status_errors++;
+      if (!wait_seq(target, 180)) status_errors++;
       const double el = secs_since(t0);
       res->cpu_s[3] = cpu_seconds() - cpu0;
       tr.enabled = false;
@@ -451,7 +451,7 @@ extern "C" int rsp_seam_bench(const rsp_seam_cfg* cfg_in, rsp_seam_result* res) 
           }
           reads_done = true;
         });
-      if (!wait_seq(target, 600)) status_errors++;
+      if (!wait_seq(target, 180)) status_errors++;
       const double el = secs_since(t0);
       done = true;
       if (with_reads) readers.join();
