@@ -574,10 +574,15 @@ def main():
         apply_e2e(i)
     barrier()
     t0 = time.perf_counter()
+    e2e_tick_ms = []
     for k in range(K):
+        tk = time.perf_counter()
         apply_e2e(W + k)
+        e2e_tick_ms.append(1e3 * (time.perf_counter() - tk))
     barrier()
     ap_e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_tick_p50 = max_over_ranks(float(np.percentile(e2e_tick_ms, 50)))
+    e2e_tick_p99 = max_over_ranks(float(np.percentile(e2e_tick_ms, 99)))
     clk = clocks.stop()
     for stp in range(n_sets, 2 * n_sets):
         ver_of[upd_idx[stp].astype(np.int64)] = stp + 1
@@ -830,7 +835,8 @@ def main():
                         "large_ticks": (None if not big else dict(big, applies_per_s=big_applies_all / (big["ms_per_tick"] * big["ticks"] * 1e-3),
                                                                   hbm_frac_of_peak=A_PUT * big["batches_per_tick"] / (big["kernel_ms_per_tick"] * 1e-3) / 1e9 / peak)),
                         "hbm_frac_of_peak": (A_PUT * T / (ap_kernel_ms * 1e-3) / 1e9 / peak) if ap_kernel_ms and ap_kernel_ms > 0 else None,
-                        "e2e": {"value": tot_applies / ap_e2e_s, "unit": "applies/s", "h2d_bytes_per_step": int(ticks[0][1].size + 10 * T), "d2h_bytes_per_step": 4 * T + 24 * S}},
+                        "e2e": {"value": tot_applies / ap_e2e_s, "unit": "applies/s", "h2d_bytes_per_step": int(ticks[0][1].size + 10 * T), "d2h_bytes_per_step": 4 * T + 24 * S,
+                                "tick_ms": {"p50": e2e_tick_p50, "p99": e2e_tick_p99, "what": "one rsp_apply_many call of %d batches from pinned host memory, host clock" % T}}},
             "roofline": {"kernel": "k_multi_get16", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_lookup": A_GET,
                          "lookups_per_launch": Q, "launch_ms": mg_kernel_ms},
